@@ -1,0 +1,53 @@
+# Builds the product libraries in-tree (they travel to the GPU box with the
+# snapshot):
+#   form_b200/lib/libformgpu.so   CUDA hot path + C-ABI (include/formgpu.h)
+#   form_b200/lib/libformhost.so  C++ host facade (form::Estimator, synthetic scans)
+# and, for tests / bench baselines only, oracle/_build/liboracle.so.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       ?= g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude -Iform_b200/csrc
+# index-determining kernels: no FMA contraction so results match the oracle bit for bit
+EXACT     := -fmad=false
+CXXFLAGS  := -O3 -std=c++17 -fPIC -pthread -ffp-contract=off -Wall -Iinclude -Iform_b200/host
+LIBDIR    := form_b200/lib
+OBJDIR    := build/obj
+
+GPU_OBJS  := $(OBJDIR)/extract.o $(OBJDIR)/api.o $(OBJDIR)/api_stage23.o
+HOST_SRCS := $(wildcard form_b200/host/src/*.cpp)
+HOST_OBJS := $(HOST_SRCS:form_b200/host/src/%.cpp=$(OBJDIR)/host_%.o)
+CSRC_HDRS := $(wildcard form_b200/csrc/*.hpp) include/formgpu.h
+HOST_HDRS := $(wildcard form_b200/host/form/*.hpp) include/formgpu.h
+
+all: $(LIBDIR)/libformgpu.so $(LIBDIR)/libformhost.so oracle
+
+$(OBJDIR)/extract.o: form_b200/csrc/extract.cu $(CSRC_HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) $(EXACT) -Xptxas -v -c $< -o $@
+
+$(OBJDIR)/map_assoc.o: form_b200/csrc/map_assoc.cu $(CSRC_HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) $(EXACT) -Xptxas -v -c $< -o $@
+
+$(OBJDIR)/%.o: form_b200/csrc/%.cu $(CSRC_HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@
+
+$(LIBDIR)/libformgpu.so: $(GPU_OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $(GPU_OBJS) -cudart static
+
+$(OBJDIR)/host_%.o: form_b200/host/src/%.cpp $(HOST_HDRS)
+	@mkdir -p $(OBJDIR)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(LIBDIR)/libformhost.so: $(HOST_OBJS) $(LIBDIR)/libformgpu.so
+	$(CXX) -shared -pthread -o $@ $(HOST_OBJS) -L$(LIBDIR) -lformgpu -Wl,-rpath,'$$ORIGIN'
+
+oracle:
+	$(MAKE) -s -C oracle
+
+clean:
+	rm -rf build $(LIBDIR)/*.so oracle/_build
+
+.PHONY: all oracle clean

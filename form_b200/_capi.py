@@ -1,0 +1,155 @@
+"""ctypes view of the C-ABI in include/formgpu.h (and of libformhost's helpers).
+
+Plain structs are mirrored as numpy dtypes so buffers cross the boundary
+without copies.  Nothing here computes: it only declares prototypes and loads
+the shared libraries built by ``__graft_entry__.build()`` / ``make``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(_HERE, "lib")
+
+# ---- plain data (include/formgpu.h) ------------------------------------------
+POINT4F = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("w", "<f4")])
+POINT_FEAT = np.dtype([("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("pad", "<f8"), ("scan", "<u8")])
+PLANAR_FEAT = np.dtype(
+    [("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("pad", "<f8"),
+     ("nx", "<f8"), ("ny", "<f8"), ("nz", "<f8"), ("npad", "<f8"), ("scan", "<u8")]
+)
+POSE = np.dtype([("R", "<f8", (9,)), ("t", "<f8", (3,))])
+SCAN_POSE = np.dtype([("scan", "<u8"), ("R", "<f8", (9,)), ("t", "<f8", (3,))])
+PAIR = np.dtype([("i", "<u8"), ("j", "<u8")])
+PAIR_COUNT = np.dtype([("i", "<u8"), ("n_planar", "<u4"), ("n_point", "<u4")])
+MATCH = np.dtype([("scan", "<u8"), ("k", "<u4"), ("found", "<u4"), ("dist_sqrd", "<f8")])
+
+assert POINT4F.itemsize == 16 and POINT_FEAT.itemsize == 40 and PLANAR_FEAT.itemsize == 72
+assert POSE.itemsize == 96 and SCAN_POSE.itemsize == 104 and MATCH.itemsize == 24
+
+NUM_STAGES = 6
+STAGE_NAMES = ("extract", "map", "assoc", "linearize", "error", "commit")
+
+OK, ERR_INVALID_ARG, ERR_BAD_SCAN_SIZE, ERR_CAPACITY, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = range(7)
+
+
+class Params(C.Structure):
+    """formgpu_params"""
+
+    _fields_ = [
+        ("neighbor_points", C.c_int32),
+        ("num_sectors", C.c_int32),
+        ("planar_feats_per_sector", C.c_int32),
+        ("point_feats_per_sector", C.c_int32),
+        ("min_points", C.c_int32),
+        ("num_columns", C.c_int32),
+        ("num_rows", C.c_int32),
+        ("max_window_scans", C.c_int32),
+        ("planar_threshold", C.c_double),
+        ("radius", C.c_double),
+        ("min_norm_squared", C.c_double),
+        ("max_norm_squared", C.c_double),
+        ("max_dist_matching", C.c_double),
+        ("min_dist_map", C.c_double),
+        ("sigma", C.c_double),
+        ("max_batch_scans", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+def default_params(rows: int = 64, cols: int = 1024, **overrides) -> Params:
+    """Reference defaults (python/bindings.cpp:66-88 of FORM); pure Python so it
+    also works where the CUDA library is not built."""
+    p = Params(
+        neighbor_points=5, num_sectors=6, planar_feats_per_sector=50, point_feats_per_sector=3,
+        min_points=5, num_columns=cols, num_rows=rows, max_window_scans=64,
+        planar_threshold=1.0, radius=1.0, min_norm_squared=1.0, max_norm_squared=1.0e4,
+        max_dist_matching=0.8, min_dist_map=0.1, sigma=0.1, max_batch_scans=1, reserved=0,
+    )
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError(f"formgpu_params has no field {k!r}")
+        setattr(p, k, v)
+    return p
+
+
+def ptr(a):
+    """void* of a numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+_vp, _sz, _u64, _i = C.c_void_p, C.c_size_t, C.c_uint64, C.c_int
+_psz = C.POINTER(C.c_size_t)
+
+# name -> (restype, argtypes); exactly the symbols include/formgpu.h declares
+FORMGPU_SYMBOLS = {
+    "formgpu_default_params": (None, [C.POINTER(Params)]),
+    "formgpu_create": (_i, [C.POINTER(Params), _i, _vp, C.POINTER(_vp)]),
+    "formgpu_destroy": (None, [_vp]),
+    "formgpu_last_error": (C.c_char_p, [_vp]),
+    "formgpu_abi_version": (_i, []),
+    "formgpu_extract": (_i, [_vp, _vp, _sz, _u64, _vp, _sz, _psz, _vp, _sz, _psz]),
+    "formgpu_extract_device": (_i, [_vp, _vp, _sz, _u64, _psz, _psz]),
+    "formgpu_max_planar": (_sz, [_vp]),
+    "formgpu_max_point": (_sz, [_vp]),
+    "formgpu_extract_debug": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _psz, _vp, _psz]),
+    "formgpu_map_rebuild": (_i, [_vp, _vp, _sz]),
+    "formgpu_associate": (_i, [_vp, _vp, _vp, _sz, _psz]),
+    "formgpu_get_matches": (_i, [_vp, _i, _vp, _sz, _psz]),
+    "formgpu_commit_scan": (_i, [_vp, _psz, _psz]),
+    "formgpu_remove_scans": (_i, [_vp, _vp, _sz]),
+    "formgpu_get_keypoints": (_i, [_vp, _i, _u64, _vp, _sz, _psz]),
+    "formgpu_world_keypoints": (_i, [_vp, _vp, _sz, _vp, _sz, _psz, _vp, _sz, _psz]),
+    "formgpu_linearize": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "formgpu_error": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "formgpu_profile_enable": (_i, [_vp, _i]),
+    "formgpu_profile_read": (_i, [_vp, _vp, _vp, _vp]),
+    "formgpu_launch_count": (_u64, [_vp]),
+    "formgpu_synchronize": (_i, [_vp]),
+}
+
+FORMHOST_SYMBOLS = {
+    "formhost_synth_shape": (_sz, [_i, C.POINTER(_i), C.POINTER(_i)]),
+    "formhost_synth_scan": (_i, [_i, _u64, _u64, _vp, _i]),
+    "formhost_synth_gt_pose": (None, [_u64, _u64, _vp]),
+}
+
+
+def _load(path: str, symbols: dict) -> C.CDLL:
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make`) at the repository root"
+        )
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in symbols.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_gpu = None
+_host = None
+
+
+def gpu_lib() -> C.CDLL:
+    """libformgpu.so: the CUDA hot path behind the C-ABI.  No fallback."""
+    global _gpu
+    if _gpu is None:
+        _gpu = _load(os.path.join(LIB_DIR, "libformgpu.so"), FORMGPU_SYMBOLS)
+    return _gpu
+
+
+def host_lib() -> C.CDLL:
+    """libformhost.so: host-side C++ (synthetic scans, Estimator facade)."""
+    global _host
+    if _host is None:
+        gpu_lib()  # libformhost links against libformgpu
+        _host = _load(os.path.join(LIB_DIR, "libformhost.so"), FORMHOST_SYMBOLS)
+    return _host

@@ -1,0 +1,460 @@
+// C-ABI (include/formgpu.h): lifecycle, instrumentation and stage 1.
+#include "api_common.hpp"
+
+#include <algorithm>
+#include <new>
+
+using namespace formgpu;
+
+namespace {
+std::string g_create_error;
+
+size_t next_pow2(size_t v) {
+  size_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+} // namespace
+
+namespace formgpu {
+
+int ensure_upload(formgpu_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->h_upload_bytes) return FORMGPU_OK;
+  // growing is rare (first full-window request); drain the stream first
+  FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_upload) cudaFreeHost(ctx->h_upload);
+  if (ctx->d_request) cudaFree(ctx->d_request);
+  ctx->h_upload = nullptr;
+  ctx->d_request = nullptr;
+  const size_t cap = next_pow2(bytes);
+  FORMGPU_CUDA(ctx, cudaHostAlloc(&ctx->h_upload, cap, cudaHostAllocDefault));
+  FORMGPU_CUDA(ctx, cudaMalloc(&ctx->d_request, cap));
+  ctx->h_upload_bytes = cap;
+  ctx->request_bytes = cap;
+  return FORMGPU_OK;
+}
+
+int ensure_out(formgpu_ctx *ctx, size_t pairs) {
+  if (pairs <= ctx->out_cap) return FORMGPU_OK;
+  FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_out) cudaFreeHost(ctx->h_out);
+  if (ctx->d_out) cudaFree(ctx->d_out);
+  ctx->h_out = nullptr;
+  ctx->d_out = nullptr;
+  const size_t cap = next_pow2(pairs);
+  FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_out), cap * 91 * sizeof(double),
+                                  cudaHostAllocDefault));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_out, cap * 91));
+  ctx->out_cap = cap;
+  ctx->h_out_bytes = cap * 91 * sizeof(double);
+  return FORMGPU_OK;
+}
+
+} // namespace formgpu
+
+extern "C" {
+
+int formgpu_abi_version(void) { return FORMGPU_ABI_VERSION; }
+
+void formgpu_default_params(formgpu_params *p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->neighbor_points = 5;
+  p->num_sectors = 6;
+  p->planar_feats_per_sector = 50;
+  p->point_feats_per_sector = 3;
+  p->min_points = 5;
+  p->num_columns = 1024;
+  p->num_rows = 64;
+  p->max_window_scans = 64;
+  p->planar_threshold = 1.0;
+  p->radius = 1.0;
+  p->min_norm_squared = 1.0;
+  p->max_norm_squared = 100.0 * 100.0;
+  p->max_dist_matching = 0.8;
+  p->min_dist_map = 0.1;
+  p->sigma = 0.1;
+  p->max_batch_scans = 1;
+}
+
+const char *formgpu_last_error(const formgpu_ctx *ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+static int create_impl(formgpu_ctx *ctx) {
+  const formgpu_params &P = ctx->P;
+  if (P.neighbor_points < 1 || P.neighbor_points > 16)
+    return fail(ctx, FORMGPU_ERR_UNSUPPORTED, "neighbor_points must be in [1, 16]");
+  if (P.num_sectors < 1 || P.num_rows < 1 || P.num_columns < 2 * P.neighbor_points + 1 ||
+      P.num_columns > 4096 || P.num_columns / P.num_sectors < 1)
+    return fail(ctx, FORMGPU_ERR_UNSUPPORTED,
+                "need 2*neighbor_points < num_columns <= 4096, num_rows >= 1, "
+                "1 <= num_sectors <= num_columns");
+  if (P.planar_feats_per_sector < 0 || P.point_feats_per_sector < 0 || P.min_points < 0)
+    return fail(ctx, FORMGPU_ERR_INVALID_ARG, "negative feature counts");
+  if (P.max_window_scans < 2 || P.max_window_scans > kMaxWindow)
+    return fail(ctx, FORMGPU_ERR_UNSUPPORTED, "max_window_scans must be in [2, 128]");
+  if (!(P.max_dist_matching > 0) || !(P.sigma > 0))
+    return fail(ctx, FORMGPU_ERR_INVALID_ARG, "max_dist_matching and sigma must be positive");
+
+  ctx->rows = P.num_rows;
+  ctx->cols = P.num_columns;
+  ctx->words = (ctx->cols + 31) / 32;
+  ctx->W = P.max_window_scans;
+  ctx->B = std::max(1, P.max_batch_scans);
+  ctx->n_points = (size_t)ctx->rows * ctx->cols;
+  // picks in one row are pairwise >= neighbor_points apart (suppression +-(np-1))
+  ctx->qr_cap = (ctx->cols + P.neighbor_points - 1) / P.neighbor_points + 1;
+  ctx->pr_cap = std::min(P.num_sectors * (P.planar_feats_per_sector + 1), ctx->qr_cap);
+  ctx->pr_cap = std::max(ctx->pr_cap, 1);
+  ctx->kp_cap = (size_t)ctx->rows * ctx->pr_cap;
+  ctx->kq_cap = (size_t)ctx->rows * ctx->qr_cap;
+  if (ctx->kp_cap >= (1u << 24) || ctx->kq_cap >= (1u << 24))
+    return fail(ctx, FORMGPU_ERR_UNSUPPORTED, "more than 2^24 keypoints per scan");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(ctx, FORMGPU_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+  if (ctx->device < 0 || ctx->device >= ndev)
+    return fail(ctx, FORMGPU_ERR_INVALID_ARG, "device index out of range");
+  FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  FORMGPU_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+  if (prop.major < 10)
+    return fail(ctx, FORMGPU_ERR_CUDA, "formgpu is built for sm_100a (Blackwell) only");
+  if (!ctx->stream) {
+    FORMGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  FORMGPU_CUDA(ctx, cudaEventCreate(&ctx->ev_a));
+  FORMGPU_CUDA(ctx, cudaEventCreate(&ctx->ev_b));
+
+  const size_t B = ctx->B, R = ctx->rows, W = ctx->W;
+  // stage 1
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_scan, B * ctx->n_points));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_valid_bits, B * R * ctx->words));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_planar_cols, B * R * ctx->pr_cap));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_planar_cnt, B * R));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_point_cols, B * R * ctx->qr_cap));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_point_cnt, B * R));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_normals, B * R * ctx->pr_cap));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_keep_cnt, B * R));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_cur_planar, B * ctx->kp_cap));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_cur_point, B * ctx->kq_cap));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_cur_counts, B * 2 + 8));
+  FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_counts),
+                                  (B * 2 + 8) * sizeof(int), cudaHostAllocDefault));
+  FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_planar),
+                                  ctx->kp_cap * sizeof(PlanarRec), cudaHostAllocDefault));
+  FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_point),
+                                  ctx->kq_cap * sizeof(PointRec), cudaHostAllocDefault));
+  FORMGPU_CUDA(ctx, extract_configure(ctx->cols, ctx->words * 32, ctx->words, ctx->pr_cap));
+
+  // window / keypoint store
+  ctx->slot_scan.assign(W, 0);
+  ctx->slot_used.assign(W, 0);
+  ctx->store_n[0].assign(W, 0);
+  ctx->store_n[1].assign(W, 0);
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_store_planar, W * ctx->kp_cap));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_store_point, W * ctx->kq_cap));
+
+  // world map: capacity for every store slot full
+  const size_t cap[2] = {W * ctx->kp_cap, W * ctx->kq_cap};
+  for (int t = 0; t < 2; ++t) {
+    ctx->map_cap[t] = cap[t];
+    ctx->hash_cap[t] = next_pow2(2 * cap[t]);
+    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_hash[t], ctx->hash_cap[t]));
+    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_world[t], cap[t]));
+    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_world_tmp[t], cap[t]));
+    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_world_slot[t], cap[t]));
+    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_world_src[t], cap[t]));
+  }
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_map_cursor, 8));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_slot_pose, W * 12));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_slot_scan, W));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_slot_off, 2 * (W + 1)));
+
+  // matches / correspondences
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_match[0], ctx->kp_cap));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_match[1], ctx->kq_cap));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_match_q_planar, ctx->kp_cap));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_match_q_point, ctx->kq_cap));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_seg_planar, W * 9 * ctx->kp_cap));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_seg_point, W * 6 * ctx->kq_cap));
+  const size_t max_blocks = (std::max(ctx->kp_cap, ctx->kq_cap) + 255) / 256 + 1;
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_block_hist, 2 * max_blocks * W));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_pair_table, W * W));
+  FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_pair_table, 0, W * W * sizeof(PairEntry), ctx->stream));
+  ctx->h_pair_table.assign(W * W, PairEntry{0, 0, 0, 0});
+  FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pair_row),
+                                  W * sizeof(PairEntry), cudaHostAllocDefault));
+
+  int rc = ensure_upload(ctx, 1 << 16);
+  if (rc) return rc;
+  rc = ensure_out(ctx, 64);
+  if (rc) return rc;
+  FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FORMGPU_OK;
+}
+
+int formgpu_create(const formgpu_params *p, int device, void *stream, formgpu_ctx **out) {
+  if (!p || !out) {
+    g_create_error = "formgpu_create: null argument";
+    return FORMGPU_ERR_INVALID_ARG;
+  }
+  *out = nullptr;
+  formgpu_ctx *ctx = new (std::nothrow) formgpu_ctx();
+  if (!ctx) {
+    g_create_error = "out of host memory";
+    return FORMGPU_ERR_CAPACITY;
+  }
+  ctx->P = *p;
+  ctx->device = device;
+  ctx->stream = static_cast<cudaStream_t>(stream);
+  const int rc = create_impl(ctx);
+  if (rc != FORMGPU_OK) {
+    g_create_error = ctx->err;
+    formgpu_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return FORMGPU_OK;
+}
+
+void formgpu_destroy(formgpu_ctx *ctx) {
+  if (!ctx) return;
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  auto F = [](auto *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  auto H = [](auto *&p) {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+  };
+  F(ctx->d_scan); F(ctx->d_valid_bits); F(ctx->d_planar_cols); F(ctx->d_planar_cnt);
+  F(ctx->d_point_cols); F(ctx->d_point_cnt); F(ctx->d_normals); F(ctx->d_closest);
+  F(ctx->d_keep_cnt); F(ctx->d_cur_planar); F(ctx->d_cur_point); F(ctx->d_cur_counts);
+  F(ctx->d_dbg_valid); F(ctx->d_dbg_pvalid); F(ctx->d_dbg_curv);
+  F(ctx->d_store_planar); F(ctx->d_store_point);
+  for (int t = 0; t < 2; ++t) {
+    F(ctx->d_hash[t]); F(ctx->d_world[t]); F(ctx->d_world_tmp[t]);
+    F(ctx->d_world_slot[t]); F(ctx->d_world_src[t]); F(ctx->d_match[t]);
+  }
+  F(ctx->d_map_cursor); F(ctx->d_slot_pose); F(ctx->d_slot_scan); F(ctx->d_slot_off);
+  F(ctx->d_match_q_planar); F(ctx->d_match_q_point);
+  F(ctx->d_seg_planar); F(ctx->d_seg_point); F(ctx->d_block_hist); F(ctx->d_pair_table);
+  F(ctx->d_partials); F(ctx->d_request); F(ctx->d_out);
+  H(ctx->h_counts); H(ctx->h_planar); H(ctx->h_point); H(ctx->h_upload); H(ctx->h_out);
+  H(ctx->h_pair_row);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+size_t formgpu_max_planar(const formgpu_ctx *ctx) { return ctx ? ctx->kp_cap : 0; }
+size_t formgpu_max_point(const formgpu_ctx *ctx) { return ctx ? ctx->kq_cap : 0; }
+
+// ---------------------------------------------------------------------------
+// stage 1
+// ---------------------------------------------------------------------------
+static ExtractArgs make_extract_args(formgpu_ctx *ctx, const float4 *scan_dev, bool debug) {
+  const formgpu_params &P = ctx->P;
+  ExtractArgs a{};
+  a.rows = ctx->rows;
+  a.cols = ctx->cols;
+  a.words = ctx->words;
+  a.cols_pad = ctx->words * 32;
+  a.np = P.neighbor_points;
+  a.num_sectors = P.num_sectors;
+  a.pps = ctx->cols / P.num_sectors;
+  a.planar_per_sector = P.planar_feats_per_sector;
+  a.point_per_sector = P.point_feats_per_sector;
+  a.min_points = P.min_points;
+  a.pr_cap = ctx->pr_cap;
+  a.qr_cap = ctx->qr_cap;
+  a.kp_cap = ctx->kp_cap;
+  a.kq_cap = ctx->kq_cap;
+  a.min_norm2 = P.min_norm_squared;
+  a.max_norm2 = P.max_norm_squared;
+  a.planar_threshold = P.planar_threshold;
+  a.radius = P.radius;
+  a.scan = scan_dev;
+  a.valid_bits = ctx->d_valid_bits;
+  a.planar_cols = ctx->d_planar_cols;
+  a.planar_cnt = ctx->d_planar_cnt;
+  a.point_cols = ctx->d_point_cols;
+  a.point_cnt = ctx->d_point_cnt;
+  a.normals = ctx->d_normals;
+  a.closest = debug ? ctx->d_closest : nullptr;
+  a.keep_cnt = ctx->d_keep_cnt;
+  a.cur_planar = ctx->d_cur_planar;
+  a.cur_point = ctx->d_cur_point;
+  a.cur_counts = ctx->d_cur_counts;
+  a.dbg_valid = debug ? ctx->d_dbg_valid : nullptr;
+  a.dbg_pvalid = debug ? ctx->d_dbg_pvalid : nullptr;
+  a.dbg_curv = debug ? ctx->d_dbg_curv : nullptr;
+  return a;
+}
+
+// runs the kernels on a device-resident scan and fetches the two counts
+static int extract_run(formgpu_ctx *ctx, const float4 *scan_dev, uint64_t scan_idx,
+                       StageScope &scope) {
+  const ExtractArgs a = make_extract_args(ctx, scan_dev, false);
+  scope.launches(extract_launch(a, 1, ctx->stream));
+  FORMGPU_CUDA(ctx, cudaGetLastError());
+  FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, ctx->d_cur_counts, 2 * sizeof(int),
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+  FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->cur_n[0] = ctx->h_counts[0];
+  ctx->cur_n[1] = ctx->h_counts[1];
+  ctx->cur_scan = scan_idx;
+  ctx->have_current = true;
+  return FORMGPU_OK;
+}
+
+int formgpu_extract(formgpu_ctx *ctx, const formgpu_point4f *scan, size_t n, uint64_t scan_idx,
+                    formgpu_planar_feat *planar_out, size_t planar_cap, size_t *n_planar,
+                    formgpu_point_feat *point_out, size_t point_cap, size_t *n_point) {
+  if (!ctx) return FORMGPU_ERR_INVALID_ARG;
+  if (!scan || !n_planar || !n_point)
+    return fail(ctx, FORMGPU_ERR_INVALID_ARG, "formgpu_extract: null argument");
+  if (n != ctx->n_points)
+    return fail(ctx, FORMGPU_ERR_BAD_SCAN_SIZE,
+                "Provided scan does not match the expected size " +
+                    std::to_string(ctx->n_points) + " != " + std::to_string(n));
+  FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  StageScope scope(ctx, FORMGPU_STAGE_EXTRACT);
+  FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_scan, scan, n * sizeof(float4), cudaMemcpyHostToDevice,
+                                    ctx->stream));
+  const int rc = extract_run(ctx, ctx->d_scan, scan_idx, scope);
+  if (rc) return rc;
+  const size_t np = (size_t)ctx->cur_n[0], nq = (size_t)ctx->cur_n[1];
+  *n_planar = np;
+  *n_point = nq;
+  if ((np && !planar_out) || (nq && !point_out) || np > planar_cap || nq > point_cap)
+    return fail(ctx, FORMGPU_ERR_CAPACITY, "formgpu_extract: output buffers too small");
+  // compact lossless f32 records come back over PCIe; widen to the f64 API structs here
+  if (np)
+    FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_planar, ctx->d_cur_planar, np * sizeof(PlanarRec),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+  if (nq)
+    FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_point, ctx->d_cur_point, nq * sizeof(PointRec),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+  FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < np; ++i) {
+    const PlanarRec &r = ctx->h_planar[i];
+    formgpu_planar_feat &o = planar_out[i];
+    o.x = r.x; o.y = r.y; o.z = r.z; o.pad = 0.0;
+    o.nx = r.nx; o.ny = r.ny; o.nz = r.nz; o.npad = 0.0;
+    o.scan = scan_idx;
+  }
+  for (size_t i = 0; i < nq; ++i) {
+    const PointRec &r = ctx->h_point[i];
+    formgpu_point_feat &o = point_out[i];
+    o.x = r.x; o.y = r.y; o.z = r.z; o.pad = 0.0;
+    o.scan = scan_idx;
+  }
+  return FORMGPU_OK;
+}
+
+int formgpu_extract_device(formgpu_ctx *ctx, const formgpu_point4f *scan_dev, size_t n,
+                           uint64_t scan_idx, size_t *n_planar, size_t *n_point) {
+  if (!ctx) return FORMGPU_ERR_INVALID_ARG;
+  if (!scan_dev || !n_planar || !n_point)
+    return fail(ctx, FORMGPU_ERR_INVALID_ARG, "formgpu_extract_device: null argument");
+  if (n != ctx->n_points)
+    return fail(ctx, FORMGPU_ERR_BAD_SCAN_SIZE, "Provided scan does not match the expected size");
+  FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  StageScope scope(ctx, FORMGPU_STAGE_EXTRACT);
+  // keep a copy so extract_debug can re-run on it (device-to-device, off the PCIe path)
+  FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_scan, scan_dev, n * sizeof(float4),
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+  const int rc = extract_run(ctx, ctx->d_scan, scan_idx, scope);
+  if (rc) return rc;
+  *n_planar = (size_t)ctx->cur_n[0];
+  *n_point = (size_t)ctx->cur_n[1];
+  return FORMGPU_OK;
+}
+
+int formgpu_extract_debug(formgpu_ctx *ctx, uint8_t *valid_mask, uint8_t *point_valid_mask,
+                          float *curvature, uint32_t *planar_indices, uint8_t *planar_keep,
+                          int32_t *closest_prev, int32_t *closest_next, size_t *n_planar_picks,
+                          uint32_t *point_indices, size_t *n_point_picks) {
+  if (!ctx) return FORMGPU_ERR_INVALID_ARG;
+  if (!ctx->have_current) return fail(ctx, FORMGPU_ERR_STATE, "no scan has been extracted");
+  FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t N = ctx->n_points, R = ctx->rows;
+  if (!ctx->d_dbg_valid) {
+    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_dbg_valid, N));
+    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_dbg_pvalid, N));
+    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_dbg_curv, N));
+    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_closest, R * ctx->pr_cap * 2));
+  }
+  // re-run stage 1 on the resident scan with the debug outputs switched on
+  const ExtractArgs a = make_extract_args(ctx, ctx->d_scan, true);
+  ctx->launches += (uint64_t)extract_launch(a, 1, ctx->stream);
+  FORMGPU_CUDA(ctx, cudaGetLastError());
+  std::vector<int> pcnt(R), qcnt(R), closest(R * ctx->pr_cap * 2);
+  std::vector<uint16_t> pcols(R * ctx->pr_cap), qcols(R * ctx->qr_cap);
+  std::vector<float4> normals(R * ctx->pr_cap);
+  cudaStream_t s = ctx->stream;
+  if (valid_mask) FORMGPU_CUDA(ctx, cudaMemcpyAsync(valid_mask, ctx->d_dbg_valid, N, cudaMemcpyDeviceToHost, s));
+  if (point_valid_mask) FORMGPU_CUDA(ctx, cudaMemcpyAsync(point_valid_mask, ctx->d_dbg_pvalid, N, cudaMemcpyDeviceToHost, s));
+  if (curvature) FORMGPU_CUDA(ctx, cudaMemcpyAsync(curvature, ctx->d_dbg_curv, N * sizeof(float), cudaMemcpyDeviceToHost, s));
+  FORMGPU_CUDA(ctx, cudaMemcpyAsync(pcnt.data(), ctx->d_planar_cnt, R * sizeof(int), cudaMemcpyDeviceToHost, s));
+  FORMGPU_CUDA(ctx, cudaMemcpyAsync(qcnt.data(), ctx->d_point_cnt, R * sizeof(int), cudaMemcpyDeviceToHost, s));
+  FORMGPU_CUDA(ctx, cudaMemcpyAsync(pcols.data(), ctx->d_planar_cols, pcols.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+  FORMGPU_CUDA(ctx, cudaMemcpyAsync(qcols.data(), ctx->d_point_cols, qcols.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+  FORMGPU_CUDA(ctx, cudaMemcpyAsync(normals.data(), ctx->d_normals, normals.size() * sizeof(float4), cudaMemcpyDeviceToHost, s));
+  FORMGPU_CUDA(ctx, cudaMemcpyAsync(closest.data(), ctx->d_closest, closest.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+  FORMGPU_CUDA(ctx, cudaStreamSynchronize(s));
+  size_t kp = 0, kq = 0;
+  for (size_t r = 0; r < R; ++r) {
+    for (int j = 0; j < pcnt[r]; ++j, ++kp) {
+      const size_t e = r * ctx->pr_cap + j;
+      if (planar_indices) planar_indices[kp] = (uint32_t)(r * ctx->cols + pcols[e]);
+      if (planar_keep) planar_keep[kp] = normals[e].w != 0.0f;
+      if (closest_prev) closest_prev[kp] = closest[2 * e];
+      if (closest_next) closest_next[kp] = closest[2 * e + 1];
+    }
+    for (int j = 0; j < qcnt[r]; ++j, ++kq)
+      if (point_indices) point_indices[kq] = (uint32_t)(r * ctx->cols + qcols[r * ctx->qr_cap + j]);
+  }
+  if (n_planar_picks) *n_planar_picks = kp;
+  if (n_point_picks) *n_point_picks = kq;
+  return FORMGPU_OK;
+}
+
+// ---------------------------------------------------------------------------
+// instrumentation
+// ---------------------------------------------------------------------------
+int formgpu_profile_enable(formgpu_ctx *ctx, int on) {
+  if (!ctx) return FORMGPU_ERR_INVALID_ARG;
+  ctx->profiling = on != 0;
+  return FORMGPU_OK;
+}
+
+int formgpu_profile_read(formgpu_ctx *ctx, double ms[FORMGPU_NUM_STAGES],
+                         uint64_t calls[FORMGPU_NUM_STAGES],
+                         uint64_t launches[FORMGPU_NUM_STAGES]) {
+  if (!ctx) return FORMGPU_ERR_INVALID_ARG;
+  for (int s = 0; s < FORMGPU_NUM_STAGES; ++s) {
+    if (ms) ms[s] = ctx->prof[s].ms;
+    if (calls) calls[s] = ctx->prof[s].calls;
+    if (launches) launches[s] = ctx->prof[s].launches;
+    ctx->prof[s] = StageProf();
+  }
+  return FORMGPU_OK;
+}
+
+uint64_t formgpu_launch_count(const formgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int formgpu_synchronize(formgpu_ctx *ctx) {
+  if (!ctx) return FORMGPU_ERR_INVALID_ARG;
+  FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FORMGPU_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,177 @@
+// Internal definition of the opaque formgpu_ctx (include/formgpu.h).
+//
+// Device memory layout (all allocated once in formgpu_create; nothing is
+// allocated on the per-scan path):
+//
+//   scan staging   d_scan          [B][rows*cols] float4       input scans
+//   stage 1        d_valid_bits    [B][rows][words] u32        validity masks
+//                  d_planar_cols   [B][rows][pr_cap] u16       planar picks per row
+//                  d_point_cols    [B][rows][qr_cap] u16       point picks per row
+//                  d_normals       [B][rows][pr_cap] float4    normal + keep flag
+//                  d_cur_planar    [B][kp_cap] PlanarRec (32B) packed keypoints
+//                  d_cur_point     [B][kq_cap] PointRec  (16B)
+//   keypoint store d_store_planar  [W][kp_cap] PlanarRec       scan-local, lossless f32
+//                  d_store_point   [W][kq_cap] PointRec
+//   world map      d_hash_*        open-addressing voxel hash (per type)
+//                  d_world_*       voxel-sorted world points (32 B each)
+//   matches        d_match_*       per current keypoint: map id + dist^2
+//   correspondences d_seg_planar   [W][9][kp_cap] float        SoA p_i,n_i,p_j
+//                  d_seg_point     [W][6][kq_cap] float        SoA p_i,p_j
+//                  d_pair_table    [W][W] PairEntry            offsets/counts per (k,i)
+//
+// W = max_window_scans slots; a scan id is mapped to a slot by the host side
+// of the C-ABI (slot_of).  B = max_batch_scans.
+#pragma once
+
+#include "formgpu.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace formgpu {
+
+struct PlanarRec { // 32 B, one L2 sector
+  float x, y, z;
+  float nx, ny, nz;
+  uint32_t pad0, pad1;
+};
+struct PointRec { // 16 B
+  float x, y, z, w;
+};
+static_assert(sizeof(PlanarRec) == 32 && sizeof(PointRec) == 16, "record sizes");
+
+struct WorldPoint { // 32 B: world coordinates (f64) + tie-break key
+  double x, y, z;
+  uint64_t tie; // (scan_id << 24) | k  -> rule R4/R5 ordering
+};
+static_assert(sizeof(WorldPoint) == 32, "WorldPoint size");
+
+struct HashSlot { // 16 B
+  unsigned long long key; // packed voxel coords, EMPTY = ~0ull
+  uint32_t start;
+  uint32_t count;
+};
+
+struct MatchRec { // 16 B
+  double dist_sqrd;
+  uint32_t slot; // window slot of the matched point's scan (0xffffffff = none)
+  uint32_t k;
+};
+
+struct PairEntry { // per (current slot k, map slot i)
+  uint32_t off_planar, n_planar;
+  uint32_t off_point, n_point;
+};
+
+constexpr int kMaxWindow = 128;
+constexpr uint32_t kNoSlot = 0xffffffffu;
+
+struct StageProf {
+  double ms = 0;
+  uint64_t calls = 0;
+  uint64_t launches = 0;
+};
+
+} // namespace formgpu
+
+struct formgpu_ctx {
+  formgpu_params P{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  mutable std::string err;
+
+  // derived sizes
+  int rows = 0, cols = 0, words = 0, W = 0, B = 1;
+  int pr_cap = 0, qr_cap = 0;   // picks per row
+  size_t kp_cap = 0, kq_cap = 0; // keypoints per scan
+  size_t n_points = 0;
+
+  // ---- stage 1 ----
+  float4 *d_scan = nullptr;
+  uint32_t *d_valid_bits = nullptr;
+  uint16_t *d_planar_cols = nullptr;
+  int *d_planar_cnt = nullptr;
+  uint16_t *d_point_cols = nullptr;
+  int *d_point_cnt = nullptr;
+  float4 *d_normals = nullptr;
+  int *d_closest = nullptr; // [B][rows][pr_cap][2]
+  int *d_keep_cnt = nullptr;
+  formgpu::PlanarRec *d_cur_planar = nullptr;
+  formgpu::PointRec *d_cur_point = nullptr;
+  int *d_cur_counts = nullptr; // [B][2]
+  // debug (allocated lazily)
+  uint8_t *d_dbg_valid = nullptr, *d_dbg_pvalid = nullptr;
+  float *d_dbg_curv = nullptr;
+  bool debug_extract = false;
+
+  // pinned host staging
+  int *h_counts = nullptr;               // [B][2] + misc
+  formgpu::PlanarRec *h_planar = nullptr; // kp_cap
+  formgpu::PointRec *h_point = nullptr;   // kq_cap
+  void *h_upload = nullptr;              // request staging (poses, pairs, chunks)
+  size_t h_upload_bytes = 0;
+  double *h_out = nullptr; // result staging (91 * pairs)
+  size_t h_out_bytes = 0;
+
+  // ---- current scan ----
+  bool have_current = false;
+  uint64_t cur_scan = 0;
+  int cur_n[2] = {0, 0}; // planar, point keypoints of the current scan
+  bool cur_device_resident = false;
+
+  // ---- window / keypoint store ----
+  std::unordered_map<uint64_t, int> slot_of; // scan id -> slot
+  std::vector<uint64_t> slot_scan;           // slot -> scan id
+  std::vector<uint8_t> slot_used;
+  std::vector<int> store_n[2];               // keypoints stored per slot
+  formgpu::PlanarRec *d_store_planar = nullptr;
+  formgpu::PointRec *d_store_point = nullptr;
+
+  // ---- world map (per type t) ----
+  size_t hash_cap[2] = {0, 0}; // power of two
+  formgpu::HashSlot *d_hash[2] = {nullptr, nullptr};
+  formgpu::WorldPoint *d_world[2] = {nullptr, nullptr}; // voxel-sorted
+  formgpu::WorldPoint *d_world_tmp[2] = {nullptr, nullptr}; // unsorted, store order
+  uint32_t *d_world_slot[2] = {nullptr, nullptr}; // hash slot of each store point
+  uint32_t *d_world_src[2] = {nullptr, nullptr};  // voxel-sorted -> (slot<<20 | k)... see map.cu
+  uint32_t *d_map_cursor = nullptr;               // [2]
+  size_t map_n[2] = {0, 0};                       // points in the built map
+  size_t map_cap[2] = {0, 0};
+  double *d_slot_pose = nullptr;   // [W][12]
+  uint64_t *d_slot_scan = nullptr; // [W]
+  int *d_slot_off = nullptr;       // [2][W+1] prefix of store counts at rebuild
+  bool map_built = false;
+
+  // ---- matches / correspondences ----
+  formgpu::MatchRec *d_match[2] = {nullptr, nullptr};
+  int match_n[2] = {0, 0};
+  uint64_t match_scan[2] = {0, 0};
+  bool match_valid[2] = {false, false};
+  formgpu::PlanarRec *d_match_q_planar = nullptr; // queries of the last match (planar)
+  formgpu::PointRec *d_match_q_point = nullptr;
+  float *d_seg_planar = nullptr; // [W][9][kp_cap]
+  float *d_seg_point = nullptr;  // [W][6][kq_cap]
+  uint32_t *d_block_hist = nullptr;
+  formgpu::PairEntry *d_pair_table = nullptr; // [W][W]
+  std::vector<formgpu::PairEntry> h_pair_table; // host mirror [W][W]
+  formgpu::PairEntry *h_pair_row = nullptr;    // pinned [W]
+
+  // ---- linearisation scratch ----
+  double *d_partials = nullptr;
+  size_t partial_cap = 0; // chunks
+  void *d_request = nullptr;
+  size_t request_bytes = 0;
+  double *d_out = nullptr;
+  size_t out_cap = 0; // pairs
+
+  // ---- instrumentation ----
+  bool profiling = false;
+  formgpu::StageProf prof[FORMGPU_NUM_STAGES];
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  uint64_t launches = 0;
+};

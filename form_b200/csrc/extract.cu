@@ -1,0 +1,682 @@
+// Stage 1 on sm_100a: scan-line feature extraction.
+//
+// Replaces FeatureExtractor::extract (/root/reference/form/feature/
+// extraction.tpp:29-132) and its helpers (:136-448).  Compiled with
+// -fmad=false: every float/double operation below is evaluated in the same
+// order, without contraction, as the CPU oracle, so validity
+// masks, curvature bits, feature indices, closest indices AND normals come out
+// bit-identical.
+//
+// Mapping to the hardware: one CTA per scan row (rows are independent,
+// extraction.tpp:44-68; suppression never crosses rows), grid.y = scan in the
+// batch.  The 16-32 KB row is staged once in shared memory with coalesced
+// 128-bit loads and every later access (11-tap curvature window, O(n^2) rank
+// sort inside a sector, greedy walks) hits shared memory only.  The greedy
+// selections are sequential by definition; they run on warp 0, 32 sorted
+// candidates per step: candidates are fetched in parallel, conflicts inside
+// the group are resolved with shuffles, and the row's "used" bitmask lives in
+// shared memory.
+#include "ctx.hpp"
+#include "kernels.hpp"
+
+#include <cfloat>
+
+namespace formgpu {
+
+namespace {
+
+__device__ __forceinline__ float diff_sqnorm4(const float4 a, const float4 b) {
+  // (d0^2 + d2^2) + (d1^2 + d3^2): Eigen's 4-lane packet reduction (A.2)
+  const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+  return (d0 * d0 + d2 * d2) + (d1 * d1 + d3 * d3);
+}
+
+__device__ __forceinline__ bool get_bit(const uint32_t *m, int c) {
+  return (m[c >> 5] >> (c & 31)) & 1u;
+}
+
+// clear bits [lo, hi] (inclusive) of a shared-memory bitmask, hi - lo < 32
+__device__ __forceinline__ void clear_bits(uint32_t *m, int lo, int hi) {
+  const int wl = lo >> 5, wh = hi >> 5;
+  if (wl == wh) {
+    const uint32_t width = (uint32_t)(hi - lo + 1);
+    const uint32_t mask = (width >= 32 ? 0xffffffffu : ((1u << width) - 1u)) << (lo & 31);
+    atomicAnd(&m[wl], ~mask);
+  } else {
+    atomicAnd(&m[wl], ~(0xffffffffu << (lo & 31)));
+    atomicAnd(&m[wh], ~(0xffffffffu >> (31 - (hi & 31))));
+  }
+}
+
+// Resolve the sequential "take it if still unused, then suppress +-(np-1)"
+// rule inside a group of 32 candidates ordered by lane: lane l survives iff it
+// is a candidate and no surviving earlier lane lies within np-1 columns.
+__device__ __forceinline__ bool resolve_group(bool cand, int col, int np, int lane) {
+  bool alive = cand;
+  const unsigned any = __ballot_sync(0xffffffffu, cand);
+  if (any == 0) return false;
+  const int last = 31 - __clz(any);
+  for (int k = 0; k < last; ++k) {
+    const int ck = __shfl_sync(0xffffffffu, col, k);
+    const int ak = __shfl_sync(0xffffffffu, (int)alive, k);
+    if (ak && lane > k) {
+      const int d = col - ck;
+      if (d < np && d > -np) alive = false;
+    }
+  }
+  return alive;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------
+// K1: validity masks, curvature, per-sector sort, greedy planar + point picks
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+extract_select_kernel(ExtractArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int cols = a.cols, words = a.words, np = a.np;
+  float4 *pts = reinterpret_cast<float4 *>(smem_raw);
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(pts + cols);
+  uint16_t *sorted = reinterpret_cast<uint16_t *>(keys + cols);
+  uint16_t *ulist = sorted + a.cols_pad;
+  uint32_t *m_range = reinterpret_cast<uint32_t *>(ulist + a.cols_pad);
+  uint32_t *m_valid = m_range + words;
+  uint32_t *m_pvalid = m_valid + words;
+  uint32_t *m_used = m_pvalid + words;
+
+  const int row = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const size_t row_base = ((size_t)b * a.rows + row) * cols;
+  const float4 *g = a.scan + row_base;
+
+  for (int c = tid; c < cols; c += blockDim.x) pts[c] = __ldg(&g[c]);
+  __syncthreads();
+
+  // range test (extraction.tpp:167-168): float norm promoted to double
+  for (int c0 = 0; c0 < words * 32; c0 += blockDim.x) {
+    const int c = c0 + tid;
+    bool ok = false;
+    if (c < cols) {
+      const float4 p = pts[c];
+      const double r2 = (double)((p.x * p.x + p.z * p.z) + (p.y * p.y + p.w * p.w));
+      ok = !(r2 < a.min_norm2 || r2 > a.max_norm2);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0 && (c >> 5) < words) m_range[c >> 5] = bal;
+  }
+  __syncthreads();
+
+  // validity masks (extraction.tpp:136-222) in closed form:
+  //   valid(c)  = !edge(c) && for all j in [c-np, c+np]: !edge(j) => range_ok(j)
+  //   pvalid(c) = !edge(c) && range_ok(c)
+  for (int c0 = 0; c0 < words * 32; c0 += blockDim.x) {
+    const int c = c0 + tid;
+    bool v = false, pv = false;
+    if (c < cols && c >= np && c < cols - np) {
+      pv = get_bit(m_range, c);
+      v = true;
+      const int lo = max(c - np, np), hi = min(c + np, cols - np - 1);
+      for (int j = lo; j <= hi; ++j) v = v && get_bit(m_range, j);
+    }
+    const unsigned bv = __ballot_sync(0xffffffffu, v);
+    const unsigned bp = __ballot_sync(0xffffffffu, pv);
+    if (lane == 0 && (c >> 5) < words) {
+      m_valid[c >> 5] = bv;
+      m_used[c >> 5] = bv;
+      m_pvalid[c >> 5] = bp;
+      a.valid_bits[((size_t)b * a.rows + row) * words + (c >> 5)] = bv;
+    }
+  }
+  __syncthreads();
+
+  // curvature (extraction.tpp:226-261): double accumulation in the reference's
+  // order, rounded to float; sort key = (float bits << 32) | column (rule R1)
+  for (int c = tid; c < cols; c += blockDim.x) {
+    float cf = FLT_MAX;
+    if (get_bit(m_valid, c)) {
+      const double k = -(2.0 * (double)np);
+      const float4 p = pts[c];
+      double dx = k * (double)p.x, dy = k * (double)p.y, dz = k * (double)p.z;
+      for (int n = 1; n <= np; ++n) {
+        const float4 pa = pts[c - n], pb = pts[c + n];
+        dx = (dx + (double)pa.x) + (double)pb.x;
+        dy = (dy + (double)pa.y) + (double)pb.y;
+        dz = (dz + (double)pa.z) + (double)pb.z;
+      }
+      cf = (float)((dx * dx + dy * dy) + dz * dz);
+    }
+    keys[c] = ((unsigned long long)__float_as_uint(cf) << 32) | (unsigned)c;
+    if (a.dbg_curv) a.dbg_curv[row_base + c] = cf;
+    if (a.dbg_valid) {
+      a.dbg_valid[row_base + c] = get_bit(m_valid, c);
+      a.dbg_pvalid[row_base + c] = get_bit(m_pvalid, c);
+    }
+  }
+  __syncthreads();
+
+  // per-sector rank sort (std::sort at extraction.tpp:57-58 with rule R1)
+  const int pps = a.pps, S = a.num_sectors;
+  for (int c = tid; c < cols; c += blockDim.x) {
+    const int s = min(c / pps, S - 1);
+    const int start = s * pps;
+    const int end = (s == S - 1) ? cols : start + pps;
+    const unsigned long long kc = keys[c];
+    int rank = 0;
+    for (int j = start; j < end; ++j) rank += (keys[j] < kc) ? 1 : 0;
+    sorted[start + rank] = (uint16_t)c;
+  }
+  __syncthreads();
+
+  if (tid >= 32) return;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  // ---- extract_planar (extraction.tpp:332-358), sectors in ascending order ----
+  uint16_t *out_pl = a.planar_cols + ((size_t)b * a.rows + row) * a.pr_cap;
+  int total = 0;
+  for (int s = 0; s < S; ++s) {
+    const int start = s * pps;
+    const int len = ((s == S - 1) ? cols : start + pps) - start;
+    int count = 0;
+    bool done = false;
+    for (int base = 0; base < len && !done; base += 32) {
+      const int i = base + lane;
+      const bool in = i < len;
+      const int col = in ? (int)sorted[start + i] : 0;
+      const float curv = in ? __uint_as_float((unsigned)(keys[col] >> 32)) : FLT_MAX;
+      const bool below = in && ((double)curv < a.planar_threshold);
+      const bool cand = below && get_bit(m_used, col);
+      const bool alive = resolve_group(cand, col, np, lane);
+      const unsigned sel = __ballot_sync(0xffffffffu, alive);
+      const int rank = __popc(sel & lt_mask);
+      // visited iff the count after all earlier visits is still <= cap (:354 '>')
+      const bool accept = alive && (count + rank <= a.planar_per_sector);
+      if (accept) {
+        out_pl[total + count + rank] = (uint16_t)col;
+        clear_bits(m_used, col - (np - 1), col + (np - 1));
+      }
+      count += __popc(__ballot_sync(0xffffffffu, accept));
+      if (count > a.planar_per_sector) done = true;
+      // sorted ascending: once one in-range lane is >= threshold nothing later qualifies
+      if (__ballot_sync(0xffffffffu, below) != __ballot_sync(0xffffffffu, in)) done = true;
+      __syncwarp();
+    }
+    total += count;
+  }
+  if (lane == 0) a.planar_cnt[(size_t)b * a.rows + row] = total;
+
+  // ---- point candidates (extraction.tpp:72-80): untouched by planar picks and
+  // range-valid.  m_pvalid becomes the working mask of extract_point. ----
+  for (int w = lane; w < words; w += 32) m_pvalid[w] = ~(m_used[w] ^ m_valid[w]) & m_pvalid[w];
+  __syncwarp();
+
+  // ---- extract_point (extraction.tpp:360-399) ----
+  uint16_t *out_pt = a.point_cols + ((size_t)b * a.rows + row) * a.qr_cap;
+  int ptotal = 0;
+  const int pfps = a.point_per_sector;
+  for (int s = 0; s < S && pfps > 0; ++s) {
+    const int start = s * pps;
+    const int end = (s == S - 1) ? cols : start + pps;
+    // unused_points (:371-376): ascending list of still-valid columns
+    int U = 0;
+    for (int base = start; base < end; base += 32) {
+      const int c = base + lane;
+      const bool bit = c < end && get_bit(m_pvalid, c);
+      const unsigned bal = __ballot_sync(0xffffffffu, bit);
+      if (bit) ulist[U + __popc(bal & lt_mask)] = (uint16_t)c;
+      U += __popc(bal);
+    }
+    __syncwarp();
+    const int factor = 1 + U / pfps; // :379
+    int count = 0;
+    int offset = 0;
+    // Phase A: full strided passes while the pass starts with count <= pfps
+    while (offset < factor && count <= pfps) {
+      bool broken = false;
+      for (int m0 = 0; !broken; m0 += 32) {
+        const long long u = (long long)offset + (long long)(m0 + lane) * factor;
+        const bool in = u < U;
+        if (__ballot_sync(0xffffffffu, in) == 0) break;
+        const int col = in ? (int)ulist[u] : 0;
+        const bool cand = in && get_bit(m_pvalid, col);
+        const bool alive = resolve_group(cand, col, np, lane);
+        const unsigned sel = __ballot_sync(0xffffffffu, alive);
+        const int rank = __popc(sel & lt_mask);
+        // element m of a pass is visited iff m == 0 or the count after the
+        // earlier visits is still <= pfps (the break at :394-396 sits after the
+        // visit and leaves only the inner loop)
+        const bool visited = in && ((m0 + lane == 0) || (count + rank <= pfps));
+        const bool accept = alive && visited;
+        if (accept) {
+          out_pt[ptotal + count + rank] = (uint16_t)col;
+          clear_bits(m_pvalid, col - (np - 1), col + (np - 1));
+        }
+        count += __popc(__ballot_sync(0xffffffffu, accept));
+        if (count > pfps) broken = true;
+        __syncwarp();
+      }
+      ++offset;
+    }
+    // Phase B: count > pfps, so every remaining pass visits only u = offset
+    for (int base = offset; base < factor; base += 32) {
+      const int o = base + lane;
+      const bool in = o < factor && o < U;
+      if (__ballot_sync(0xffffffffu, in) == 0) break;
+      const int col = in ? (int)ulist[o] : 0;
+      const bool cand = in && get_bit(m_pvalid, col);
+      const bool alive = resolve_group(cand, col, np, lane);
+      const unsigned sel = __ballot_sync(0xffffffffu, alive);
+      const int rank = __popc(sel & lt_mask);
+      if (alive) {
+        out_pt[ptotal + count + rank] = (uint16_t)col;
+        clear_bits(m_pvalid, col - (np - 1), col + (np - 1));
+      }
+      count += __popc(sel);
+      __syncwarp();
+    }
+    ptotal += count;
+  }
+  if (lane == 0) a.point_cnt[(size_t)b * a.rows + row] = ptotal;
+}
+
+// ---------------------------------------------------------------------------
+// K2: PCA normals of the planar picks (compute_normal, extraction.tpp:263-329)
+// ---------------------------------------------------------------------------
+namespace {
+
+struct PickDesc {
+  short c_prev, c_next; // closest column on the adjacent rows, -1 = none
+  unsigned char n_plus, n_minus, pp, pm, np_, nm;
+  unsigned char pad[2];
+};
+
+// find_neighbors (extraction.tpp:422-448): counts of consecutive in-radius
+// neighbours in the + and - direction around column c of `rowp`.
+__device__ __forceinline__ void neighbor_counts(const float4 *rowp, int c, int np, double r2,
+                                                int lane, int &n_plus, int &n_minus) {
+  bool flag = false;
+  const float4 p = rowp[c];
+  if (lane < np) flag = (double)diff_sqnorm4(rowp[c + lane + 1], p) < r2;
+  else if (lane >= 16 && lane < 16 + np) flag = (double)diff_sqnorm4(rowp[c - (lane - 16) - 1], p) < r2;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  n_plus = __ffs(~(bal & 0xffffu)) - 1;   // trailing ones = neighbours before the first miss
+  n_minus = __ffs(~(bal >> 16)) - 1;
+  if (n_plus > np) n_plus = np;
+  if (n_minus > np) n_minus = np;
+}
+
+// find_closest (extraction.tpp:402-420), rule R2: arg-min (dist2, column) over
+// the valid points of one row.
+__device__ __forceinline__ int closest_in_row(const float4 *rowp, const uint32_t *valid,
+                                              const float4 p, int cols, int lane) {
+  float best = INFINITY;
+  int bc = 0x7fffffff;
+  for (int c = lane; c < cols; c += 32) {
+    if ((valid[c >> 5] >> (c & 31)) & 1u) {
+      const float d2 = diff_sqnorm4(rowp[c], p);
+      if (d2 < best) {
+        best = d2;
+        bc = c;
+      }
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oc = __shfl_xor_sync(0xffffffffu, bc, off);
+    if (od < best || (od == best && oc < bc)) {
+      best = od;
+      bc = oc;
+    }
+  }
+  return bc == 0x7fffffff ? -1 : bc;
+}
+
+__device__ __forceinline__ float hypot_pos(float x, float y) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float p = ax > ay ? ax : ay;
+  if (p == 0.0f) return 0.0f;
+  const float q = ax > ay ? ay : ax;
+  const float qp = q / p;
+  return p * sqrtf(1.0f + qp * qp);
+}
+
+__device__ __forceinline__ void make_givens(float p, float q, float &c, float &s) {
+  if (q == 0.0f) {
+    c = p < 0.0f ? -1.0f : 1.0f;
+    s = 0.0f;
+  } else if (p == 0.0f) {
+    c = 0.0f;
+    s = q < 0.0f ? 1.0f : -1.0f;
+  } else if (fabsf(p) > fabsf(q)) {
+    const float t = q / p;
+    float u = sqrtf(1.0f + t * t);
+    if (p < 0.0f) u = -u;
+    c = 1.0f / u;
+    s = -t * c;
+  } else {
+    const float t = p / q;
+    float u = sqrtf(1.0f + t * t);
+    if (q < 0.0f) u = -u;
+    s = -1.0f / u;
+    c = -t * s;
+  }
+}
+
+// SelfAdjointEigenSolver<Matrix3f> (iterative path), same operation order as
+// oracle/oracle_extract.cpp::self_adjoint_eigen3f.  Returns the normalised
+// eigenvector of the smallest eigenvalue.
+__device__ void smallest_eigvec3f(float m00, float m10, float m11, float m20, float m21,
+                                  float m22, float n[3]) {
+  float scale = fabsf(m00);
+  scale = fmaxf(scale, fabsf(m10));
+  scale = fmaxf(scale, fabsf(m11));
+  scale = fmaxf(scale, fabsf(m20));
+  scale = fmaxf(scale, fabsf(m21));
+  scale = fmaxf(scale, fabsf(m22));
+  if (scale == 0.0f) scale = 1.0f;
+  m00 = m00 / scale; m10 = m10 / scale; m11 = m11 / scale;
+  m20 = m20 / scale; m21 = m21 / scale; m22 = m22 / scale;
+
+  float diag[3], sub[2], Q[9];
+  diag[0] = m00;
+  const float v1norm2 = m20 * m20;
+  if (v1norm2 <= FLT_MIN) {
+    diag[1] = m11; diag[2] = m22; sub[0] = m10; sub[1] = m21;
+    Q[0] = 1; Q[1] = 0; Q[2] = 0; Q[3] = 0; Q[4] = 1; Q[5] = 0; Q[6] = 0; Q[7] = 0; Q[8] = 1;
+  } else {
+    const float beta = sqrtf(m10 * m10 + v1norm2);
+    const float invBeta = 1.0f / beta;
+    const float m01 = m10 * invBeta;
+    const float m02 = m20 * invBeta;
+    const float q = 2.0f * m01 * m21 + m02 * (m22 - m11);
+    diag[1] = m11 + m02 * q;
+    diag[2] = m22 - m02 * q;
+    sub[0] = beta;
+    sub[1] = m21 - m01 * q;
+    Q[0] = 1; Q[1] = 0; Q[2] = 0; Q[3] = 0; Q[4] = m01; Q[5] = m02; Q[6] = 0; Q[7] = m02; Q[8] = -m01;
+  }
+  int end = 2, start = 0, iter = 0;
+  const float precision_inv = 1.0f / FLT_EPSILON;
+  while (end > 0) {
+    for (int i = start; i < end; ++i) {
+      if (fabsf(sub[i]) < FLT_MIN) {
+        sub[i] = 0.0f;
+      } else {
+        const float scaled = precision_inv * sub[i];
+        if (scaled * scaled <= (fabsf(diag[i]) + fabsf(diag[i + 1]))) sub[i] = 0.0f;
+      }
+    }
+    while (end > 0 && sub[end - 1] == 0.0f) end--;
+    if (end <= 0) break;
+    iter++;
+    if (iter > 90) break;
+    start = end - 1;
+    while (start > 0 && sub[start - 1] != 0.0f) start--;
+
+    const float td = (diag[end - 1] - diag[end]) * 0.5f;
+    const float e = sub[end - 1];
+    float mu = diag[end];
+    if (td == 0.0f) {
+      mu = mu - fabsf(e);
+    } else if (e != 0.0f) {
+      const float e2 = e * e;
+      const float h = hypot_pos(td, e);
+      if (e2 == 0.0f) mu = mu - e / ((td + (td > 0.0f ? h : -h)) / e);
+      else mu = mu - e2 / (td + (td > 0.0f ? h : -h));
+    }
+    float x = diag[start] - mu;
+    float z = sub[start];
+    for (int k = start; k < end && z != 0.0f; ++k) {
+      float c, s;
+      make_givens(x, z, c, s);
+      const float sdk = s * diag[k] + c * sub[k];
+      const float dkp1 = s * sub[k] + c * diag[k + 1];
+      diag[k] = c * (c * diag[k] - s * sub[k]) - s * (c * sub[k] - s * diag[k + 1]);
+      diag[k + 1] = s * sdk + c * dkp1;
+      sub[k] = c * sdk - s * dkp1;
+      if (k > start) sub[k - 1] = c * sub[k - 1] - s * z;
+      x = sub[k];
+      if (k < end - 1) {
+        z = -s * sub[k + 1];
+        sub[k + 1] = c * sub[k + 1];
+      }
+      for (int r = 0; r < 3; ++r) {
+        const float xi = Q[3 * r + k], yi = Q[3 * r + k + 1];
+        Q[3 * r + k] = c * xi - s * yi;
+        Q[3 * r + k + 1] = s * xi + c * yi;
+      }
+    }
+  }
+  // column of the smallest eigenvalue after the ascending selection sort:
+  // the first minimum of diag (minCoeff returns the first occurrence)
+  int k = 0;
+  if (diag[1] < diag[k]) k = 1;
+  if (diag[2] < diag[k]) k = 2;
+  float n0 = Q[k], n1 = Q[3 + k], n2 = Q[6 + k];
+  const float zz = n0 * n0 + (n1 * n1 + n2 * n2);
+  if (zz > 0.0f) {
+    const float s = sqrtf(zz);
+    n0 = n0 / s; n1 = n1 / s; n2 = n2 / s;
+  }
+  n[0] = n0; n[1] = n1; n[2] = n2;
+}
+
+} // namespace
+
+__global__ void __launch_bounds__(256)
+extract_normals_kernel(ExtractArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int cols = a.cols, words = a.words, np = a.np;
+  float4 *own = reinterpret_cast<float4 *>(smem_raw);
+  float4 *prv = own + cols;
+  float4 *nxt = prv + cols;
+  uint32_t *v_prv = reinterpret_cast<uint32_t *>(nxt + cols);
+  uint32_t *v_nxt = v_prv + words;
+  PickDesc *desc = reinterpret_cast<PickDesc *>(v_nxt + words);
+  __shared__ int s_keep;
+
+  const int row = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const size_t rb = (size_t)b * a.rows + row;
+  const int n_picks = a.planar_cnt[rb];
+  if (tid == 0) s_keep = 0;
+  if (n_picks == 0) {
+    if (tid == 0) a.keep_cnt[rb] = 0;
+    return;
+  }
+  const bool has_prev = row > 0, has_next = row < a.rows - 1;
+  const float4 *g = a.scan + rb * cols;
+  for (int c = tid; c < cols; c += blockDim.x) {
+    own[c] = __ldg(&g[c]);
+    if (has_prev) prv[c] = __ldg(&g[c - cols]);
+    if (has_next) nxt[c] = __ldg(&g[c + cols]);
+  }
+  for (int w = tid; w < words; w += blockDim.x) {
+    v_prv[w] = has_prev ? a.valid_bits[(rb - 1) * words + w] : 0u;
+    v_nxt[w] = has_next ? a.valid_bits[(rb + 1) * words + w] : 0u;
+  }
+  __syncthreads();
+
+  const uint16_t *picks = a.planar_cols + rb * a.pr_cap;
+  const double r2 = a.radius * a.radius;
+
+  // phase A: one warp per pick - neighbour counts and closest points
+  for (int pk = warp; pk < n_picks; pk += nwarps) {
+    const int c = picks[pk];
+    const float4 p = own[c];
+    int n_plus, n_minus, pp = 0, pm = 0, nq = 0, nm = 0;
+    neighbor_counts(own, c, np, r2, lane, n_plus, n_minus);
+    int cp = -1, cn = -1;
+    if (has_prev) {
+      cp = closest_in_row(prv, v_prv, p, cols, lane);
+      if (cp >= 0) neighbor_counts(prv, cp, np, r2, lane, pp, pm);
+    }
+    if (has_next) {
+      cn = closest_in_row(nxt, v_nxt, p, cols, lane);
+      if (cn >= 0) neighbor_counts(nxt, cn, np, r2, lane, nq, nm);
+    }
+    if (lane == 0) {
+      PickDesc d;
+      d.c_prev = (short)cp; d.c_next = (short)cn;
+      d.n_plus = (unsigned char)n_plus; d.n_minus = (unsigned char)n_minus;
+      d.pp = (unsigned char)pp; d.pm = (unsigned char)pm;
+      d.np_ = (unsigned char)nq; d.nm = (unsigned char)nm;
+      d.pad[0] = d.pad[1] = 0;
+      desc[pk] = d;
+    }
+  }
+  __syncthreads();
+
+  // phase B: one thread per pick - covariance + eigenvector
+  for (int pk = tid; pk < n_picks; pk += blockDim.x) {
+    const int c = picks[pk];
+    const float4 p = own[c];
+    const PickDesc d = desc[pk];
+    const int n = d.n_plus + d.n_minus + (d.c_prev >= 0 ? 1 + d.pp + d.pm : 0) +
+                  (d.c_next >= 0 ? 1 + d.np_ + d.nm : 0);
+    const bool other = d.c_prev >= 0 || d.c_next >= 0;
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (other && n >= a.min_points) {
+      const float nf = (float)n;
+      float c00 = 0.f, c10 = 0.f, c11 = 0.f, c20 = 0.f, c21 = 0.f, c22 = 0.f;
+      auto acc = [&](const float4 q) {
+        const float a0 = (q.x - p.x) / nf, a1 = (q.y - p.y) / nf, a2 = (q.z - p.z) / nf;
+        c00 = c00 + a0 * a0;
+        c10 = c10 + a1 * a0;
+        c11 = c11 + a1 * a1;
+        c20 = c20 + a2 * a0;
+        c21 = c21 + a2 * a1;
+        c22 = c22 + a2 * a2;
+      };
+      for (int i = 1; i <= d.n_plus; ++i) acc(own[c + i]);
+      for (int i = 1; i <= d.n_minus; ++i) acc(own[c - i]);
+      if (d.c_prev >= 0) {
+        acc(prv[d.c_prev]);
+        for (int i = 1; i <= d.pp; ++i) acc(prv[d.c_prev + i]);
+        for (int i = 1; i <= d.pm; ++i) acc(prv[d.c_prev - i]);
+      }
+      if (d.c_next >= 0) {
+        acc(nxt[d.c_next]);
+        for (int i = 1; i <= d.np_; ++i) acc(nxt[d.c_next + i]);
+        for (int i = 1; i <= d.nm; ++i) acc(nxt[d.c_next - i]);
+      }
+      float nrm[3];
+      smallest_eigvec3f(c00, c10, c11, c20, c21, c22, nrm);
+      out = make_float4(nrm[0], nrm[1], nrm[2], 1.0f);
+      atomicAdd(&s_keep, 1);
+    }
+    a.normals[rb * a.pr_cap + pk] = out;
+    if (a.closest) {
+      a.closest[(rb * a.pr_cap + pk) * 2 + 0] = d.c_prev >= 0 ? (row - 1) * cols + d.c_prev : -1;
+      a.closest[(rb * a.pr_cap + pk) * 2 + 1] = d.c_next >= 0 ? (row + 1) * cols + d.c_next : -1;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) a.keep_cnt[rb] = s_keep;
+}
+
+// ---------------------------------------------------------------------------
+// K3: pack kept planar picks and point picks into the current-scan keypoint
+// arrays in rule R3 order (row, sector, selection order; dropped normals removed)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+extract_pack_kernel(ExtractArgs a) {
+  const int row = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const size_t rb0 = (size_t)b * a.rows;
+  __shared__ int s_off[2];
+  __shared__ int s_tot[2];
+  // exclusive prefix over earlier rows (and totals) - at most a few hundred ints
+  if (tid < 32) {
+    int offp = 0, offq = 0, totp = 0, totq = 0;
+    for (int r = lane; r < a.rows; r += 32) {
+      const int kp = a.keep_cnt[rb0 + r], kq = a.point_cnt[rb0 + r];
+      totp += kp;
+      totq += kq;
+      if (r < row) {
+        offp += kp;
+        offq += kq;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      offp += __shfl_xor_sync(0xffffffffu, offp, o);
+      offq += __shfl_xor_sync(0xffffffffu, offq, o);
+      totp += __shfl_xor_sync(0xffffffffu, totp, o);
+      totq += __shfl_xor_sync(0xffffffffu, totq, o);
+    }
+    if (lane == 0) {
+      s_off[0] = offp; s_off[1] = offq; s_tot[0] = totp; s_tot[1] = totq;
+    }
+  }
+  __syncthreads();
+  const size_t rb = rb0 + row;
+  const float4 *g = a.scan + rb * a.cols;
+  if (row == 0 && tid == 0) {
+    a.cur_counts[2 * b + 0] = s_tot[0];
+    a.cur_counts[2 * b + 1] = s_tot[1];
+  }
+  // planar: stable compaction of the keep flags by warp 0
+  if (tid < 32) {
+    const int n_picks = a.planar_cnt[rb];
+    int base_out = s_off[0];
+    for (int base = 0; base < n_picks; base += 32) {
+      const int pk = base + lane;
+      float4 nrm = make_float4(0, 0, 0, 0);
+      if (pk < n_picks) nrm = a.normals[rb * a.pr_cap + pk];
+      const bool keep = pk < n_picks && nrm.w != 0.0f;
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int c = a.planar_cols[rb * a.pr_cap + pk];
+        const float4 p = __ldg(&g[c]);
+        PlanarRec r;
+        r.x = p.x; r.y = p.y; r.z = p.z;
+        r.nx = nrm.x; r.ny = nrm.y; r.nz = nrm.z;
+        r.pad0 = (uint32_t)(row * a.cols + c);
+        r.pad1 = 0;
+        a.cur_planar[(size_t)b * a.kp_cap + base_out + __popc(bal & ((1u << lane) - 1u))] = r;
+      }
+      base_out += __popc(bal);
+    }
+  }
+  // points
+  const int nq = a.point_cnt[rb];
+  for (int j = tid; j < nq; j += blockDim.x) {
+    const int c = a.point_cols[rb * a.qr_cap + j];
+    const float4 p = __ldg(&g[c]);
+    PointRec r;
+    r.x = p.x; r.y = p.y; r.z = p.z;
+    r.w = 0.0f;
+    a.cur_point[(size_t)b * a.kq_cap + s_off[1] + j] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host-side launcher
+// ---------------------------------------------------------------------------
+size_t extract_select_smem(int cols, int cols_pad, int words) {
+  return (size_t)cols * (sizeof(float4) + sizeof(unsigned long long)) +
+         (size_t)cols_pad * 2 * sizeof(uint16_t) + (size_t)words * 4 * sizeof(uint32_t);
+}
+size_t extract_normals_smem(int cols, int words, int pr_cap) {
+  return (size_t)cols * 3 * sizeof(float4) + (size_t)words * 2 * sizeof(uint32_t) +
+         (size_t)pr_cap * sizeof(PickDesc);
+}
+
+cudaError_t extract_configure(int cols, int cols_pad, int words, int pr_cap) {
+  cudaError_t e = cudaFuncSetAttribute(extract_select_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)extract_select_smem(cols, cols_pad, words));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(extract_normals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)extract_normals_smem(cols, words, pr_cap));
+}
+
+int extract_launch(const ExtractArgs &a, int n_scans, cudaStream_t stream) {
+  const dim3 grid(a.rows, n_scans);
+  extract_select_kernel<<<grid, 256, extract_select_smem(a.cols, a.cols_pad, a.words), stream>>>(a);
+  extract_normals_kernel<<<grid, 256, extract_normals_smem(a.cols, a.words, a.pr_cap), stream>>>(a);
+  extract_pack_kernel<<<grid, 128, 0, stream>>>(a);
+  return 3;
+}
+
+} // namespace formgpu

@@ -1,0 +1,142 @@
+// Kernel argument blocks and host-side launchers shared between the .cu files.
+#pragma once
+
+#include "ctx.hpp"
+
+namespace formgpu {
+
+// ---- stage 1 (extract.cu, compiled with -fmad=false) ----
+struct ExtractArgs {
+  int rows, cols, cols_pad, words;
+  int np, num_sectors, pps;
+  int planar_per_sector, point_per_sector, min_points;
+  int pr_cap, qr_cap;
+  size_t kp_cap, kq_cap;
+  double min_norm2, max_norm2, planar_threshold, radius;
+  const float4 *scan;      // [B][rows*cols]
+  uint32_t *valid_bits;    // [B][rows][words]
+  uint16_t *planar_cols;   // [B][rows][pr_cap]
+  int *planar_cnt;         // [B][rows]
+  uint16_t *point_cols;    // [B][rows][qr_cap]
+  int *point_cnt;          // [B][rows]
+  float4 *normals;         // [B][rows][pr_cap]  (nx, ny, nz, keep)
+  int *closest;            // [B][rows][pr_cap][2] or nullptr
+  int *keep_cnt;           // [B][rows]
+  PlanarRec *cur_planar;   // [B][kp_cap]
+  PointRec *cur_point;     // [B][kq_cap]
+  int *cur_counts;         // [B][2]
+  uint8_t *dbg_valid, *dbg_pvalid; // [B][rows*cols] or nullptr
+  float *dbg_curv;                 // [B][rows*cols] or nullptr
+};
+
+cudaError_t extract_configure(int cols, int cols_pad, int words, int pr_cap);
+size_t extract_select_smem(int cols, int cols_pad, int words);
+size_t extract_normals_smem(int cols, int words, int pr_cap);
+/// Launches the three stage-1 kernels; returns the number of launches.
+int extract_launch(const ExtractArgs &a, int n_scans, cudaStream_t stream);
+
+// ---- stage 2 (map_assoc.cu, compiled with -fmad=false) ----
+struct MapArgs {
+  int type;            // 0 planar, 1 point
+  int W;
+  size_t kcap;         // keypoints per slot in the store
+  const void *store;   // PlanarRec* or PointRec*
+  const int *slot_off; // [W+1] exclusive prefix of store counts (device)
+  const double *slot_pose;   // [W][12]
+  const uint64_t *slot_scan; // [W]
+  int n_total;
+  double voxel_width;
+  HashSlot *hash;
+  uint32_t hash_mask;
+  WorldPoint *world_tmp; // store order
+  uint32_t *world_slot;  // hash slot per store-order point
+  uint32_t *world_src;   // voxel-sorted -> (window slot << 24 | k) packed id
+  WorldPoint *world;     // voxel-sorted
+  uint32_t *cursor;      // allocation cursor
+};
+int map_build_launch(const MapArgs &a, size_t hash_cap, cudaStream_t stream);
+
+struct AssocArgs {
+  int type;
+  int n_query;
+  const void *queries; // PlanarRec* / PointRec* of the current scan
+  double pose[12];     // pose of the current scan
+  double voxel_width;
+  const HashSlot *hash;
+  uint32_t hash_mask;
+  const WorldPoint *world;
+  const uint32_t *world_src;
+  MatchRec *match;
+};
+int assoc_launch(const AssocArgs &a, cudaStream_t stream);
+
+struct SegmentArgs {
+  int type;
+  int W;
+  int n_query;
+  double max_dist2;
+  size_t kcap;
+  const void *queries;  // current scan keypoints
+  const void *store;    // keypoint store
+  const MatchRec *match;
+  uint32_t *block_hist; // [blocks][W]
+  PairEntry *pair_row;  // [W] row of the pair table for the current slot
+  float *seg;           // segment base of the current slot: [9 or 6][kcap]
+};
+int segment_build_launch(const SegmentArgs &a, cudaStream_t stream);
+
+struct CommitArgs {
+  int type;
+  int n_query;
+  double min_dist2;
+  const void *queries;
+  const MatchRec *match;
+  void *store_dst;   // store slot base of the scan being appended to
+  int dst_count;     // keypoints already stored there
+  int *out_count;    // device: number appended
+};
+int commit_launch(const CommitArgs &a, cudaStream_t stream);
+
+struct WorldExportArgs {
+  int type;
+  int W;
+  size_t kcap;
+  const void *store;
+  const int *slot_off;
+  const double *slot_pose;
+  const uint64_t *slot_scan;
+  int n_total;
+  void *out; // formgpu_planar_feat* / formgpu_point_feat* (device)
+};
+int world_export_launch(const WorldExportArgs &a, cudaStream_t stream);
+
+// ---- stage 3 (linearize.cu, FMA allowed: tolerance class) ----
+struct LinPair {   // one requested pair
+  int slot_i, slot_j;
+  uint32_t off_planar, n_planar, off_point, n_point;
+  int chunk_begin_planar, n_chunks_planar;
+  int chunk_begin_point, n_chunks_point;
+};
+struct LinChunk {  // one block's work
+  int pair;
+  int type;        // 0 planar, 1 point
+  uint32_t start;  // offset inside the segment of slot_j
+  uint32_t len;
+};
+struct LinArgs {
+  int W;
+  size_t kp_cap, kq_cap;
+  const float *seg_planar; // [W][9][kp_cap]
+  const float *seg_point;  // [W][6][kq_cap]
+  const double *poses;     // [W][12] poses of this request, by slot
+  const LinPair *pairs;
+  const LinChunk *chunks;
+  int n_pairs, n_chunks;
+  double inv_sigma2;
+  double *partials; // [n_chunks][28] (linearize) or [n_chunks] (error)
+  double *out;      // [n_pairs][91] or [n_pairs]
+};
+int linearize_launch(const LinArgs &a, cudaStream_t stream);
+int error_launch(const LinArgs &a, cudaStream_t stream);
+
+} // namespace formgpu

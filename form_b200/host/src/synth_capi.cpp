@@ -1,0 +1,49 @@
+// C entry points of the synthetic scan generator (form/synth.hpp) for the
+// Python tests and bench.py.
+#include "form/synth.hpp"
+#include "formgpu.h"
+
+extern "C" {
+
+/// sensor: 0 = OS1-64 (64x1024), 1 = OS0-128 (128x1024), 2 = VLP-16 (16x1800),
+/// 3 = stress 128x2048.  Returns rows*cols, or 0 for an unknown sensor.
+size_t formhost_synth_shape(int sensor, int *rows, int *cols) {
+  using form::synth::SensorModel;
+  SensorModel sm;
+  switch (sensor) {
+  case 0: sm = SensorModel::OS1_64(); break;
+  case 1: sm = SensorModel::OS0_128(); break;
+  case 2: sm = SensorModel::VLP_16(); break;
+  case 3: sm = SensorModel::Stress_128x2048(); break;
+  default: return 0;
+  }
+  if (rows) *rows = sm.rows;
+  if (cols) *cols = sm.cols;
+  return (size_t)sm.rows * sm.cols;
+}
+
+/// Fill `out` (rows*cols points) with scan k of `sequence_id`.
+int formhost_synth_scan(int sensor, uint64_t sequence_id, uint64_t k, formgpu_point4f *out,
+                        int threads) {
+  using form::synth::SensorModel;
+  SensorModel sm;
+  switch (sensor) {
+  case 0: sm = SensorModel::OS1_64(); break;
+  case 1: sm = SensorModel::OS0_128(); break;
+  case 2: sm = SensorModel::VLP_16(); break;
+  case 3: sm = SensorModel::Stress_128x2048(); break;
+  default: return 1;
+  }
+  form::synth::generate_scan(sm, sequence_id, (size_t)k, reinterpret_cast<form::PointXYZf *>(out),
+                             threads);
+  return 0;
+}
+
+/// Ground-truth sensor pose of scan k.
+void formhost_synth_gt_pose(uint64_t sequence_id, uint64_t k, formgpu_pose *out) {
+  const form::Pose3 T = form::synth::gt_pose(sequence_id, (size_t)k);
+  for (int i = 0; i < 9; ++i) out->R[i] = T.R[i];
+  for (int i = 0; i < 3; ++i) out->t[i] = T.t[i];
+}
+
+} // extern "C"

@@ -1,0 +1,250 @@
+/*
+ * formgpu.h - C-ABI of the B200 (sm_100a) implementation of FORM's per-scan
+ * data-parallel hot path: scan-line feature extraction, voxel-hashed keypoint
+ * association, and point-to-plane / point-to-point linearisation into per-pair
+ * normal-equation blocks, plus the reparative map rebuild.
+ *
+ * This is the drop-in boundary.  Plain C types, caller-owned buffers, int status
+ * codes; no exceptions, no C++ or torch types cross it.  Every entry point
+ * names the reference interface it replaces (paths relative to the FORM
+ * repository).  The C++ facade in form_b200/host/form/ (namespace form:
+ * Estimator, FeatureExtractor, ...) sits on top of exactly these calls; see
+ * INTEGRATION.md for the binding a FORM maintainer would add.
+ *
+ * Threading: one caller thread per context; contexts are independent (one per
+ * sequence / GPU).  All work of a context is ordered on one CUDA stream.
+ *
+ * There is no CPU fallback: every compute entry point fails with
+ * FORMGPU_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef FORMGPU_H
+#define FORMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FORMGPU_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------- */
+#define FORMGPU_OK 0
+#define FORMGPU_ERR_INVALID_ARG 1 /* null pointer, bad enum, unknown scan id   */
+#define FORMGPU_ERR_BAD_SCAN_SIZE 2 /* n != rows*cols (extraction.tpp:141-145) */
+#define FORMGPU_ERR_CAPACITY 3    /* caller buffer or internal arena too small */
+#define FORMGPU_ERR_CUDA 4        /* CUDA runtime error / no device            */
+#define FORMGPU_ERR_STATE 5       /* call order violated (e.g. no current scan)*/
+#define FORMGPU_ERR_UNSUPPORTED 6 /* parameter outside the supported range     */
+
+/* ---- plain data --------------------------------------------------------- */
+
+/* form::PointXYZf, form/utils.hpp:38-91.  Organised scans are row-major:
+ * idx = row * num_columns + col (form/feature/extraction.tpp:155). */
+typedef struct formgpu_point4f {
+  float x, y, z, w;
+} formgpu_point4f;
+
+/* form::PointFeat, form/feature/features.hpp:31-86 (40 bytes). */
+typedef struct formgpu_point_feat {
+  double x, y, z, pad;
+  uint64_t scan;
+} formgpu_point_feat;
+
+/* form::PlanarFeat, form/feature/features.hpp:89-163 (72 bytes). */
+typedef struct formgpu_planar_feat {
+  double x, y, z, pad;
+  double nx, ny, nz, npad;
+  uint64_t scan;
+} formgpu_planar_feat;
+
+/* gtsam::Pose3 as 12 doubles: row-major rotation then translation (96 bytes).
+ * T * p = R p + t. */
+typedef struct formgpu_pose {
+  double R[9];
+  double t[3];
+} formgpu_pose;
+
+/* Pose of one scan of the window: gtsam::Values entry X(scan). */
+typedef struct formgpu_scan_pose {
+  uint64_t scan;
+  formgpu_pose pose;
+} formgpu_scan_pose;
+
+/* m_constraints[j][i], j > i (form/optimization/constraints.hpp:91-99). */
+typedef struct formgpu_pair {
+  uint64_t i;
+  uint64_t j;
+} formgpu_pair;
+
+typedef struct formgpu_pair_count {
+  uint64_t i;
+  uint32_t n_planar;
+  uint32_t n_point;
+} formgpu_pair_count;
+
+/* One nearest-neighbour result (form::Match, form/mapping/map.hpp:48-61).  The
+ * matched map point is identified by its stable id (scan, k) = k-th stored
+ * keypoint of that scan (rule R4).  found == 0 <=> dist_sqrd == DBL_MAX. */
+typedef struct formgpu_match {
+  uint64_t scan;
+  uint32_t k;
+  uint32_t found;
+  double dist_sqrd;
+} formgpu_match;
+
+/* FeatureExtractor::Params (form/feature/extraction.hpp:59-88), MatcherParams
+ * (form/optimization/matcher.hpp:32-41), KeypointMapParams
+ * (form/mapping/map.hpp:97-100), planar_constraint_sigma
+ * (form/optimization/constraints.hpp:60), plus arena capacities. */
+typedef struct formgpu_params {
+  int32_t neighbor_points;         /* 5   */
+  int32_t num_sectors;             /* 6   */
+  int32_t planar_feats_per_sector; /* 50  */
+  int32_t point_feats_per_sector;  /* 3   */
+  int32_t min_points;              /* 5   */
+  int32_t num_columns;             /* 1024 */
+  int32_t num_rows;                /* 64  */
+  int32_t max_window_scans;        /* 64: scans resident at once (<= 1+10+50)   */
+  double planar_threshold;         /* 1.0 */
+  double radius;                   /* 1.0 */
+  double min_norm_squared;         /* 1.0 */
+  double max_norm_squared;         /* 1e4 */
+  double max_dist_matching;        /* 0.8 (also the voxel width, form.cpp:61-65) */
+  double min_dist_map;             /* 0.1 */
+  double sigma;                    /* 0.1 */
+  int32_t max_batch_scans;         /* 1: scans per formgpu_extract_batch call    */
+  int32_t reserved;
+} formgpu_params;
+
+typedef struct formgpu_ctx formgpu_ctx;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+
+/* Reference defaults (python/bindings.cpp:66-88). */
+void formgpu_default_params(formgpu_params *p);
+
+/* Estimator::Estimator(const Params&) (form/form.cpp:31-38).  `stream` is a
+ * cudaStream_t to run on, or NULL to create a private non-blocking stream. */
+int formgpu_create(const formgpu_params *p, int device, void *stream, formgpu_ctx **out);
+void formgpu_destroy(formgpu_ctx *ctx);
+
+/* Message of the last failing call on this context ("" if none).  With a NULL
+ * context returns the message of the last failed formgpu_create. */
+const char *formgpu_last_error(const formgpu_ctx *ctx);
+
+int formgpu_abi_version(void);
+
+/* ---- stage 1: feature extraction ---------------------------------------- */
+
+/* FeatureExtractor::extract (form/feature/extraction.hpp:99-101,
+ * extraction.tpp:29-132).  `scan` is a HOST buffer of n = rows*cols points.
+ * Writes up to *_cap keypoints (rule R3 order) and the true counts; makes
+ * scan_idx the context's "current scan".  FORMGPU_ERR_BAD_SCAN_SIZE when
+ * n != rows*cols; FORMGPU_ERR_CAPACITY when a caller buffer is too small (the
+ * counts are still written). */
+int formgpu_extract(formgpu_ctx *ctx, const formgpu_point4f *scan, size_t n, uint64_t scan_idx,
+                    formgpu_planar_feat *planar_out, size_t planar_cap, size_t *n_planar,
+                    formgpu_point_feat *point_out, size_t point_cap, size_t *n_point);
+
+/* Same, but `scan_dev` is a DEVICE pointer and nothing is copied back: only
+ * the counts are returned (used to time the kernels with inputs resident). */
+int formgpu_extract_device(formgpu_ctx *ctx, const formgpu_point4f *scan_dev, size_t n,
+                           uint64_t scan_idx, size_t *n_planar, size_t *n_point);
+
+/* Upper bounds for sizing caller buffers. */
+size_t formgpu_max_planar(const formgpu_ctx *ctx);
+size_t formgpu_max_point(const formgpu_ctx *ctx);
+
+/* Intermediates of the last extraction, for parity tests (any pointer may be
+ * NULL): validity masks (extraction.tpp:136-222), float curvature (:226-261),
+ * planar picks before the normal drop with their keep flag and the
+ * find_closest results (:402-420), point picks. */
+int formgpu_extract_debug(formgpu_ctx *ctx, uint8_t *valid_mask, uint8_t *point_valid_mask,
+                          float *curvature, uint32_t *planar_indices, uint8_t *planar_keep,
+                          int32_t *closest_prev, int32_t *closest_next, size_t *n_planar_picks,
+                          uint32_t *point_indices, size_t *n_point_picks);
+
+/* ---- stage 2: reparative map + association ------------------------------ */
+
+/* KeypointMap::to_voxel_map for both keypoint types (form/mapping/map.hpp:137,
+ * map.tpp:128-146; called once per scan at form/form.cpp:61-65): transform all
+ * stored keypoints by their scan's pose and rebuild the voxel hash with voxel
+ * width max_dist_matching.  Every stored scan must appear in `poses`. */
+int formgpu_map_rebuild(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t n_poses);
+
+/* Matcher::match<0> + match<1> (form/optimization/matcher.hpp:67-112,
+ * form/form.cpp:75-79) for the current scan at pose_k.  Replaces the current
+ * scan's correspondences; writes one entry per non-empty pair. */
+int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k,
+                      formgpu_pair_count *counts_out, size_t counts_cap, size_t *n_counts);
+
+/* Matcher::get_matches (matcher.hpp:114): per-keypoint results of the last
+ * association; type 0 = planar, 1 = point. */
+int formgpu_get_matches(formgpu_ctx *ctx, int type, formgpu_match *out, size_t cap, size_t *n);
+
+/* KeypointMap::insert_matches for both types (form/mapping/map.hpp:142,
+ * map.tpp:148-165; form/form.cpp:99-101). */
+int formgpu_commit_scan(formgpu_ctx *ctx, size_t *n_planar_added, size_t *n_point_added);
+
+/* KeypointMap::remove (map.hpp:130-133) + erase of all pairs touching the
+ * scans (form/optimization/constraints.cpp:186-194). */
+int formgpu_remove_scans(formgpu_ctx *ctx, const uint64_t *scans, size_t n);
+
+/* Stored (scan-local) keypoints of one scan; type 0 planar -> formgpu_planar_feat,
+ * 1 point -> formgpu_point_feat.  out may be NULL to query the count. */
+int formgpu_get_keypoints(formgpu_ctx *ctx, int type, uint64_t scan, void *out, size_t cap,
+                          size_t *n);
+
+/* FORM::map() (python/bindings.cpp:96-119): all stored keypoints in the world
+ * frame, ordered by (scan, k). */
+int formgpu_world_keypoints(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t n_poses,
+                            formgpu_planar_feat *planar_out, size_t planar_cap, size_t *n_planar,
+                            formgpu_point_feat *point_out, size_t point_cap, size_t *n_point);
+
+/* ---- stage 3: linearisation --------------------------------------------- */
+
+/* DenseFactor::linearize of FeatureFactor(X(i), X(j)) for every listed pair
+ * (form/optimization/gtsam.hpp:67-86, form/feature/factor.cpp:30-186) under
+ * the pair-set policy of ConstraintManager::get_graph
+ * (form/optimization/constraints.cpp:252-308).  out91 receives 91 doubles per
+ * pair: the row-major packed upper triangle of
+ *   [[A^T A, A^T b], [b^T A, b^T b]],  A = [J_i J_j] / sigma,  b = -r / sigma,
+ * variable order (xi_i, xi_j), tangent order [omega, v].  Pairs without
+ * correspondences yield zeros. */
+int formgpu_linearize(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
+                      const formgpu_scan_pose *poses, size_t n_poses, double *out91);
+
+/* NoiseModelFactor::error = 0.5 |r / sigma|^2 per pair (LM trial steps). */
+int formgpu_error(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
+                  const formgpu_scan_pose *poses, size_t n_poses, double *out);
+
+/* ---- instrumentation ---------------------------------------------------- */
+
+#define FORMGPU_STAGE_EXTRACT 0
+#define FORMGPU_STAGE_MAP 1
+#define FORMGPU_STAGE_ASSOC 2
+#define FORMGPU_STAGE_LINEARIZE 3
+#define FORMGPU_STAGE_ERROR 4
+#define FORMGPU_STAGE_COMMIT 5
+#define FORMGPU_NUM_STAGES 6
+
+/* When enabled every stage is bracketed by CUDA events on the context's
+ * stream; formgpu_profile_read synchronises and returns accumulated device
+ * milliseconds, call counts and kernel-launch counts per stage, then resets. */
+int formgpu_profile_enable(formgpu_ctx *ctx, int on);
+int formgpu_profile_read(formgpu_ctx *ctx, double ms[FORMGPU_NUM_STAGES],
+                         uint64_t calls[FORMGPU_NUM_STAGES],
+                         uint64_t launches[FORMGPU_NUM_STAGES]);
+
+/* Total kernels launched by this context since creation. */
+uint64_t formgpu_launch_count(const formgpu_ctx *ctx);
+
+/* Block the caller until all queued work of the context has finished. */
+int formgpu_synchronize(formgpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FORMGPU_H */
