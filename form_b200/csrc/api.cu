@@ -139,8 +139,12 @@ static int create_impl(formgpu_ctx *ctx) {
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_point_cnt, B * R));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_normals, B * R * ctx->pr_cap));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_keep_cnt, B * R));
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_cur_planar, B * ctx->kp_cap));
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_cur_point, B * ctx->kq_cap));
+  for (int i = 0; i < 2; ++i) {
+    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_cur_planar_buf[i], B * ctx->kp_cap));
+    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_cur_point_buf[i], B * ctx->kq_cap));
+  }
+  ctx->d_cur_planar = ctx->d_cur_planar_buf[0];
+  ctx->d_cur_point = ctx->d_cur_point_buf[0];
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_cur_counts, B * 2 + 8));
   FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_counts),
                                   (B * 2 + 8) * sizeof(int), cudaHostAllocDefault));
@@ -163,31 +167,31 @@ static int create_impl(formgpu_ctx *ctx) {
   for (int t = 0; t < 2; ++t) {
     ctx->map_cap[t] = cap[t];
     ctx->hash_cap[t] = next_pow2(2 * cap[t]);
-    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_hash[t], ctx->hash_cap[t]));
     FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_world[t], cap[t]));
     FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_world_tmp[t], cap[t]));
     FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_world_slot[t], cap[t]));
     FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_world_src[t], cap[t]));
   }
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_map_cursor, 8));
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_slot_pose, W * 12));
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_slot_scan, W));
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_slot_off, 2 * (W + 1)));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_mapmem,
+                              256 + (ctx->hash_cap[0] + ctx->hash_cap[1]) * sizeof(HashSlot)));
+  ctx->map_req_bytes = W * 12 * sizeof(double) + W * sizeof(uint64_t) +
+                       (2 * (W + 1) + W) * sizeof(int);
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_map_req, ctx->map_req_bytes));
+  FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_map_req), ctx->map_req_bytes,
+                                  cudaHostAllocDefault));
+  FORMGPU_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_upload, cudaEventDisableTiming));
 
   // matches / correspondences
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_match[0], ctx->kp_cap));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_match[1], ctx->kq_cap));
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_match_q_planar, ctx->kp_cap));
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_match_q_point, ctx->kq_cap));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_seg_planar, W * 9 * ctx->kp_cap));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_seg_point, W * 6 * ctx->kq_cap));
-  const size_t max_blocks = (std::max(ctx->kp_cap, ctx->kq_cap) + 255) / 256 + 1;
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_block_hist, 2 * max_blocks * W));
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_pair_table, W * W));
-  FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_pair_table, 0, W * W * sizeof(PairEntry), ctx->stream));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_block_hist[0], ((ctx->kp_cap + 255) / 256 + 1) * (W + 1)));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_block_hist[1], ((ctx->kq_cap + 255) / 256 + 1) * (W + 1)));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_pair, 4 * (W + 1)));
   ctx->h_pair_table.assign(W * W, PairEntry{0, 0, 0, 0});
-  FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pair_row),
-                                  W * sizeof(PairEntry), cudaHostAllocDefault));
+  FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pair), 4 * (W + 1) * sizeof(uint32_t),
+                                  cudaHostAllocDefault));
 
   int rc = ensure_upload(ctx, 1 << 16);
   if (rc) return rc;
@@ -234,19 +238,20 @@ void formgpu_destroy(formgpu_ctx *ctx) {
   };
   F(ctx->d_scan); F(ctx->d_valid_bits); F(ctx->d_planar_cols); F(ctx->d_planar_cnt);
   F(ctx->d_point_cols); F(ctx->d_point_cnt); F(ctx->d_normals); F(ctx->d_closest);
-  F(ctx->d_keep_cnt); F(ctx->d_cur_planar); F(ctx->d_cur_point); F(ctx->d_cur_counts);
+  F(ctx->d_keep_cnt); F(ctx->d_cur_counts);
+  for (int i = 0; i < 2; ++i) { F(ctx->d_cur_planar_buf[i]); F(ctx->d_cur_point_buf[i]); F(ctx->d_block_hist[i]); }
   F(ctx->d_dbg_valid); F(ctx->d_dbg_pvalid); F(ctx->d_dbg_curv);
   F(ctx->d_store_planar); F(ctx->d_store_point);
   for (int t = 0; t < 2; ++t) {
-    F(ctx->d_hash[t]); F(ctx->d_world[t]); F(ctx->d_world_tmp[t]);
+    F(ctx->d_world[t]); F(ctx->d_world_tmp[t]);
     F(ctx->d_world_slot[t]); F(ctx->d_world_src[t]); F(ctx->d_match[t]);
   }
-  F(ctx->d_map_cursor); F(ctx->d_slot_pose); F(ctx->d_slot_scan); F(ctx->d_slot_off);
-  F(ctx->d_match_q_planar); F(ctx->d_match_q_point);
-  F(ctx->d_seg_planar); F(ctx->d_seg_point); F(ctx->d_block_hist); F(ctx->d_pair_table);
+  F(ctx->d_mapmem); F(ctx->d_map_req); F(ctx->d_export); H(ctx->h_map_req);
+  if (ctx->ev_upload) cudaEventDestroy(ctx->ev_upload);
+  F(ctx->d_seg_planar); F(ctx->d_seg_point); F(ctx->d_pair);
   F(ctx->d_partials); F(ctx->d_request); F(ctx->d_out);
   H(ctx->h_counts); H(ctx->h_planar); H(ctx->h_point); H(ctx->h_upload); H(ctx->h_out);
-  H(ctx->h_pair_row);
+  H(ctx->h_pair);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -301,6 +306,9 @@ static ExtractArgs make_extract_args(formgpu_ctx *ctx, const float4 *scan_dev, b
 // runs the kernels on a device-resident scan and fetches the two counts
 static int extract_run(formgpu_ctx *ctx, const float4 *scan_dev, uint64_t scan_idx,
                        StageScope &scope) {
+  ctx->cur_buf ^= 1;
+  ctx->d_cur_planar = ctx->d_cur_planar_buf[ctx->cur_buf];
+  ctx->d_cur_point = ctx->d_cur_point_buf[ctx->cur_buf];
   const ExtractArgs a = make_extract_args(ctx, scan_dev, false);
   scope.launches(extract_launch(a, 1, ctx->stream));
   FORMGPU_CUDA(ctx, cudaGetLastError());
@@ -309,6 +317,9 @@ static int extract_run(formgpu_ctx *ctx, const float4 *scan_dev, uint64_t scan_i
   FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->cur_n[0] = ctx->h_counts[0];
   ctx->cur_n[1] = ctx->h_counts[1];
+  // a stale match set whose query buffer has just been overwritten is gone
+  if (ctx->match_queries[0] == ctx->d_cur_planar && ctx->cur_n[0] > 0) ctx->match_n[0] = 0;
+  if (ctx->match_queries[1] == ctx->d_cur_point && ctx->cur_n[1] > 0) ctx->match_n[1] = 0;
   ctx->cur_scan = scan_idx;
   ctx->have_current = true;
   return FORMGPU_OK;

@@ -101,7 +101,12 @@ struct formgpu_ctx {
   float4 *d_normals = nullptr;
   int *d_closest = nullptr; // [B][rows][pr_cap][2]
   int *d_keep_cnt = nullptr;
-  formgpu::PlanarRec *d_cur_planar = nullptr;
+  // current-scan keypoints, ping-pong: the previous scan's stay intact so that a
+  // stale Matcher::matches can still be committed
+  formgpu::PlanarRec *d_cur_planar_buf[2] = {nullptr, nullptr};
+  formgpu::PointRec *d_cur_point_buf[2] = {nullptr, nullptr};
+  int cur_buf = 0;
+  formgpu::PlanarRec *d_cur_planar = nullptr; // = d_cur_planar_buf[cur_buf]
   formgpu::PointRec *d_cur_point = nullptr;
   int *d_cur_counts = nullptr; // [B][2]
   // debug (allocated lazily)
@@ -133,33 +138,40 @@ struct formgpu_ctx {
   formgpu::PointRec *d_store_point = nullptr;
 
   // ---- world map (per type t) ----
-  size_t hash_cap[2] = {0, 0}; // power of two
-  formgpu::HashSlot *d_hash[2] = {nullptr, nullptr};
+  size_t hash_cap[2] = {0, 0}; // power of two, worst case
+  // one allocation: [cursor (256 B)][hash planar][hash point]; the point table
+  // starts right after the part of the planar table used by the last rebuild,
+  // so one memset clears cursor + both tables
+  unsigned char *d_mapmem = nullptr;
+  formgpu::HashSlot *d_hash[2] = {nullptr, nullptr}; // views into d_mapmem (per rebuild)
+  uint32_t hash_mask[2] = {0, 0};
   formgpu::WorldPoint *d_world[2] = {nullptr, nullptr}; // voxel-sorted
   formgpu::WorldPoint *d_world_tmp[2] = {nullptr, nullptr}; // unsorted, store order
   uint32_t *d_world_slot[2] = {nullptr, nullptr}; // hash slot of each store point
   uint32_t *d_world_src[2] = {nullptr, nullptr};  // voxel-sorted -> (slot<<20 | k)... see map.cu
-  uint32_t *d_map_cursor = nullptr;               // [2]
   size_t map_n[2] = {0, 0};                       // points in the built map
   size_t map_cap[2] = {0, 0};
-  double *d_slot_pose = nullptr;   // [W][12]
-  uint64_t *d_slot_scan = nullptr; // [W]
-  int *d_slot_off = nullptr;       // [2][W+1] prefix of store counts at rebuild
+  // rebuild request, one H2D: [W][12] poses | [W] scan ids | [2][W+1] offsets | [W] order
+  unsigned char *d_map_req = nullptr;
+  unsigned char *h_map_req = nullptr; // pinned
+  size_t map_req_bytes = 0;
+  cudaEvent_t ev_upload = nullptr;    // guards reuse of the pinned request buffers
   bool map_built = false;
+  void *d_export = nullptr;           // lazily allocated world export buffer
+  size_t export_bytes = 0;
 
   // ---- matches / correspondences ----
   formgpu::MatchRec *d_match[2] = {nullptr, nullptr};
-  int match_n[2] = {0, 0};
-  uint64_t match_scan[2] = {0, 0};
-  bool match_valid[2] = {false, false};
-  formgpu::PlanarRec *d_match_q_planar = nullptr; // queries of the last match (planar)
-  formgpu::PointRec *d_match_q_point = nullptr;
+  int match_n[2] = {0, 0};            // Matcher::matches.size() per type
+  uint64_t match_scan[2] = {0, 0};    // matches.front().query.scan
+  const void *match_queries[2] = {nullptr, nullptr}; // keypoint buffer the matches refer to
+  uint32_t match_novel[2] = {0, 0};   // keypoints insert_matches would append
   float *d_seg_planar = nullptr; // [W][9][kp_cap]
   float *d_seg_point = nullptr;  // [W][6][kq_cap]
-  uint32_t *d_block_hist = nullptr;
-  formgpu::PairEntry *d_pair_table = nullptr; // [W][W]
-  std::vector<formgpu::PairEntry> h_pair_table; // host mirror [W][W]
-  formgpu::PairEntry *h_pair_row = nullptr;    // pinned [W]
+  uint32_t *d_block_hist[2] = {nullptr, nullptr}; // [blocks][W+1]
+  uint32_t *d_pair = nullptr;     // [type][off|cnt][W+1]
+  uint32_t *h_pair = nullptr;     // pinned mirror of d_pair
+  std::vector<formgpu::PairEntry> h_pair_table; // host mirror [W(k)][W(i)]
 
   // ---- linearisation scratch ----
   double *d_partials = nullptr;

@@ -50,15 +50,16 @@ struct MapArgs {
   uint32_t hash_mask;
   WorldPoint *world_tmp; // store order
   uint32_t *world_slot;  // hash slot per store-order point
-  uint32_t *world_src;   // voxel-sorted -> (window slot << 24 | k) packed id
+  uint32_t *world_src;   // voxel-sorted -> (window slot << 24 | k)
   WorldPoint *world;     // voxel-sorted
-  uint32_t *cursor;      // allocation cursor
+  uint32_t *cursor;      // allocation cursor (zeroed before the build)
 };
-int map_build_launch(const MapArgs &a, size_t hash_cap, cudaStream_t stream);
+int map_build_launch(const MapArgs &planar, const MapArgs &point, cudaStream_t stream);
 
 struct AssocArgs {
   int type;
   int n_query;
+  int n_map;
   const void *queries; // PlanarRec* / PointRec* of the current scan
   double pose[12];     // pose of the current scan
   double voxel_width;
@@ -68,41 +69,45 @@ struct AssocArgs {
   const uint32_t *world_src;
   MatchRec *match;
 };
-int assoc_launch(const AssocArgs &a, cudaStream_t stream);
+int assoc_launch(const AssocArgs &planar, const AssocArgs &point, cudaStream_t stream);
 
 struct SegmentArgs {
   int type;
   int W;
   int n_query;
   double max_dist2;
+  double min_dist2;
   size_t kcap;
   const void *queries;  // current scan keypoints
   const void *store;    // keypoint store
   const MatchRec *match;
-  uint32_t *block_hist; // [blocks][W]
-  PairEntry *pair_row;  // [W] row of the pair table for the current slot
+  uint32_t *block_hist; // [blocks][W+1]
+  uint32_t *pair_off;   // [W+1]
+  uint32_t *pair_cnt;   // [W+1] (entry W = novel keypoints)
   float *seg;           // segment base of the current slot: [9 or 6][kcap]
 };
-int segment_build_launch(const SegmentArgs &a, cudaStream_t stream);
+int segment_build_launch(const SegmentArgs &planar, const SegmentArgs &point, cudaStream_t stream);
 
 struct CommitArgs {
   int type;
+  int W;
   int n_query;
   double min_dist2;
   const void *queries;
   const MatchRec *match;
+  const uint32_t *block_hist;
   void *store_dst;   // store slot base of the scan being appended to
-  int dst_count;     // keypoints already stored there
-  int *out_count;    // device: number appended
+  uint32_t dst_count; // keypoints already stored there
 };
-int commit_launch(const CommitArgs &a, cudaStream_t stream);
+int commit_launch(const CommitArgs &planar, const CommitArgs &point, cudaStream_t stream);
 
 struct WorldExportArgs {
   int type;
   int W;
   size_t kcap;
   const void *store;
-  const int *slot_off;
+  const int *slot_off;  // [W+1] prefix in scan-id order
+  const int *order;     // [W] slot at each position of that order
   const double *slot_pose;
   const uint64_t *slot_scan;
   int n_total;

@@ -1,0 +1,282 @@
+// Stage 3 on sm_100a: residual / Jacobian linearisation reduced into per-pair
+// 13x13 normal-equation blocks.
+//
+// Replaces PlanePoint/PointPoint::evaluateError + FeatureFactor::evaluateError
+// (/root/reference/form/feature/factor.cpp:30-186) followed by
+// DenseFactor::linearize / FastIsotropic whitening / HessianFactor(JacobianFactor)
+// (/root/reference/form/optimization/gtsam.hpp:59-140).  Tolerance class
+// (H/b rel <= 1e-5), so FMA contraction is allowed here.
+//
+// The reference materialises an (n+3m) x 13 dense Jacobian per pair and forms
+// A^T A.  Here each correspondence is streamed once from HBM (coalesced SoA
+// floats - the keypoints are float-exact) and reduced on the fly.  Working in
+// the frame of scan i,
+//     q = R_i^T (R_j p_j + t_j - t_i)           (p_j seen from scan i)
+// every row of [J_i J_j | -r] is LINEAR in a 7-vector that depends on the
+// correspondence, with coefficients that depend only on the pair's relative
+// pose (R_rel, t_rel):
+//     plane-point:  s = [ n x q,  n,  n.(q - p_i) ]
+//     point-point:  z = [ p_i,  q - p_i,  1 ]         (3 rows, rotated by R_i^T,
+//                                                      which leaves A^T A unchanged)
+// so a thread only accumulates the 28 unique products of its 7-vector (56
+// registers instead of 182 for the 91 entries) and the 13x13 block is
+// recovered per pair in the finalize kernel as  sum_kl W_kl B_k^T B_l.
+// Reduction order is fixed (strided per thread, shuffle tree per warp, warps
+// and chunks in index order) so results are run-to-run deterministic.
+#include "ctx.hpp"
+#include "kernels.hpp"
+
+namespace formgpu {
+
+namespace {
+
+constexpr int kLinThreads = 128;
+
+struct RelPose {
+  double R[9]; // R_i^T R_j, row-major
+  double t[3]; // R_i^T (t_j - t_i)
+};
+
+__device__ __forceinline__ RelPose rel_pose(const double *Ti, const double *Tj) {
+  RelPose r;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+      r.R[3 * a + b] = Ti[a] * Tj[b] + Ti[3 + a] * Tj[3 + b] + Ti[6 + a] * Tj[6 + b];
+  const double dx = Tj[9] - Ti[9], dy = Tj[10] - Ti[10], dz = Tj[11] - Ti[11];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) r.t[a] = Ti[a] * dx + Ti[3 + a] * dy + Ti[6 + a] * dz;
+  return r;
+}
+
+__device__ __forceinline__ void apply_rel(const RelPose &r, double x, double y, double z,
+                                          double &qx, double &qy, double &qz) {
+  qx = r.R[0] * x + r.R[1] * y + r.R[2] * z + r.t[0];
+  qy = r.R[3] * x + r.R[4] * y + r.R[5] * z + r.t[1];
+  qz = r.R[6] * x + r.R[7] * y + r.R[8] * z + r.t[2];
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------
+// chunk kernel: one CTA per chunk of one pair's correspondences
+// ---------------------------------------------------------------------------
+template <bool kErrorOnly>
+__global__ void __launch_bounds__(kLinThreads) lin_chunk_kernel(LinArgs a) {
+  const LinChunk ch = a.chunks[blockIdx.x];
+  const LinPair pr = a.pairs[ch.pair];
+  const RelPose rel = rel_pose(a.poses + 12 * pr.slot_i, a.poses + 12 * pr.slot_j);
+  const int tid = threadIdx.x;
+
+  double acc[kErrorOnly ? 1 : 28];
+#pragma unroll
+  for (int k = 0; k < (kErrorOnly ? 1 : 28); ++k) acc[k] = 0.0;
+
+  if (ch.type == 0) {
+    const float *s = a.seg_planar + (size_t)pr.slot_j * 9 * a.kp_cap + ch.start;
+    const size_t st = a.kp_cap;
+    for (uint32_t c = tid; c < ch.len; c += kLinThreads) {
+      const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
+      const double nx = s[3 * st + c], ny = s[4 * st + c], nz = s[5 * st + c];
+      const double pjx = s[6 * st + c], pjy = s[7 * st + c], pjz = s[8 * st + c];
+      double qx, qy, qz;
+      apply_rel(rel, pjx, pjy, pjz, qx, qy, qz);
+      const double r = nx * (qx - pix) + ny * (qy - piy) + nz * (qz - piz);
+      if (kErrorOnly) {
+        acc[0] += r * r;
+      } else {
+        const double v[7] = {ny * qz - nz * qy, nz * qx - nx * qz, nx * qy - ny * qx, nx, ny, nz, r};
+        int e = 0;
+#pragma unroll
+        for (int p = 0; p < 7; ++p)
+#pragma unroll
+          for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
+      }
+    }
+  } else {
+    const float *s = a.seg_point + (size_t)pr.slot_j * 6 * a.kq_cap + ch.start;
+    const size_t st = a.kq_cap;
+    for (uint32_t c = tid; c < ch.len; c += kLinThreads) {
+      const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
+      const double pjx = s[3 * st + c], pjy = s[4 * st + c], pjz = s[5 * st + c];
+      double qx, qy, qz;
+      apply_rel(rel, pjx, pjy, pjz, qx, qy, qz);
+      const double ex = qx - pix, ey = qy - piy, ez = qz - piz;
+      if (kErrorOnly) {
+        acc[0] += ex * ex + ey * ey + ez * ez;
+      } else {
+        const double v[7] = {pix, piy, piz, ex, ey, ez, 1.0};
+        int e = 0;
+#pragma unroll
+        for (int p = 0; p < 7; ++p)
+#pragma unroll
+          for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
+      }
+    }
+  }
+
+  constexpr int NV = kErrorOnly ? 1 : 28;
+  __shared__ double s_part[kLinThreads / 32][NV];
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) s_part[warp][k] = v;
+  }
+  __syncthreads();
+  if (tid < NV) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLinThreads / 32; ++w) v += s_part[w][tid];
+    a.partials[(size_t)blockIdx.x * NV + tid] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// finalize: per pair, sum the chunk partials in order and expand to 13x13
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(96) lin_finalize_kernel(LinArgs a) {
+  const LinPair pr = a.pairs[blockIdx.x];
+  const int tid = threadIdx.x;
+  __shared__ double Wp[7][7], Wq[7][7];
+  __shared__ double Bp[7][13];    // plane-point basis rows
+  __shared__ double Bq[7][3][13]; // point-point basis (3 rows each)
+  __shared__ RelPose s_rel;
+
+  if (tid < 28) {
+    double sp = 0.0, sq = 0.0;
+    for (int c = 0; c < pr.n_chunks_planar; ++c) sp += a.partials[(size_t)(pr.chunk_begin_planar + c) * 28 + tid];
+    for (int c = 0; c < pr.n_chunks_point; ++c) sq += a.partials[(size_t)(pr.chunk_begin_point + c) * 28 + tid];
+    // unpack upper-triangular index tid -> (p, q)
+    int p = 0, e = tid;
+    while (e >= 7 - p) {
+      e -= 7 - p;
+      ++p;
+    }
+    const int q = p + e;
+    Wp[p][q] = Wp[q][p] = sp;
+    Wq[p][q] = Wq[q][p] = sq;
+  }
+  if (tid == 32) s_rel = rel_pose(a.poses + 12 * pr.slot_i, a.poses + 12 * pr.slot_j);
+  for (int i = tid; i < 7 * 13; i += blockDim.x) (&Bp[0][0])[i] = 0.0;
+  for (int i = tid; i < 7 * 3 * 13; i += blockDim.x) (&Bq[0][0][0])[i] = 0.0;
+  __syncthreads();
+
+  if (tid == 0) {
+    const double *R = s_rel.R, *t = s_rel.t;
+    // ---- plane-point: row = [ u1, -u2, -R^T u1 - R^T [t]x u2, R^T u2, -r ] ----
+    // skew(t)[b][a]
+    const double K[3][3] = {{0, -t[2], t[1]}, {t[2], 0, -t[0]}, {-t[1], t[0], 0}};
+    for (int k = 0; k < 3; ++k) {
+      Bp[k][k] = 1.0;           // J_i rot  =  u1
+      Bp[3 + k][3 + k] = -1.0;  // J_i trans = -u2
+      for (int c = 0; c < 3; ++c) {
+        Bp[k][6 + c] = -R[3 * k + c];                 // -R^T u1
+        double bt = 0.0;                              // (R^T [t]x)[c][k]
+        for (int b = 0; b < 3; ++b) bt += R[3 * b + c] * K[b][k];
+        Bp[3 + k][6 + c] = -bt;                       // -R^T [t]x u2
+        Bp[3 + k][9 + c] = R[3 * k + c];              //  R^T u2
+      }
+    }
+    Bp[6][12] = -1.0; // b = -r
+    // ---- point-point: rows = [ [P]x, -I, -[c]x R, R, -e ],  c = P + e - t ----
+    // E_a = skew(unit a): E_a[r][cc]
+    for (int k = 0; k < 3; ++k) {
+      double E[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+      E[k2][k1] = 1.0;  // skew(e_k): [k2][k1] = +1, [k1][k2] = -1
+      E[k1][k2] = -1.0;
+      double ER[3][3]; // E_k * R
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) ER[r][c] = E[r][0] * R[c] + E[r][1] * R[3 + c] + E[r][2] * R[6 + c];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          Bq[k][r][c] = E[r][c];            // [P]x
+          Bq[k][r][6 + c] = -ER[r][c];      // -[P]x R
+          Bq[3 + k][r][6 + c] = -ER[r][c];  // -[e]x R
+          Bq[6][r][6 + c] += t[k] * ER[r][c]; // +[t]x R
+        }
+      Bq[3 + k][k][12] = -1.0;              // -e
+    }
+    for (int r = 0; r < 3; ++r) {
+      Bq[6][r][3 + r] = -1.0;               // -I
+      for (int c = 0; c < 3; ++c) Bq[6][r][9 + c] = R[3 * r + c]; // R
+    }
+  }
+  __syncthreads();
+
+  if (tid < 91) {
+    int x = 0, e = tid;
+    while (e >= 13 - x) {
+      e -= 13 - x;
+      ++x;
+    }
+    const int y = x + e;
+    double sum = 0.0;
+    if (pr.n_chunks_planar > 0) {
+      for (int k = 0; k < 7; ++k) {
+        const double bx = Bp[k][x];
+        if (bx == 0.0) continue;
+        double inner = 0.0;
+        for (int l = 0; l < 7; ++l) inner += Wp[k][l] * Bp[l][y];
+        sum += bx * inner;
+      }
+    }
+    if (pr.n_chunks_point > 0) {
+      for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 7; ++k) {
+          const double bx = Bq[k][r][x];
+          if (bx == 0.0) continue;
+          double inner = 0.0;
+          for (int l = 0; l < 7; ++l) inner += Wq[k][l] * Bq[l][r][y];
+          sum += bx * inner;
+        }
+    }
+    a.out[(size_t)blockIdx.x * 91 + tid] = sum * a.inv_sigma2;
+  }
+}
+
+__global__ void __launch_bounds__(128) err_finalize_kernel(LinArgs a) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.n_pairs) return;
+  const LinPair pr = a.pairs[p];
+  double s = 0.0;
+  for (int c = 0; c < pr.n_chunks_planar; ++c) s += a.partials[pr.chunk_begin_planar + c];
+  for (int c = 0; c < pr.n_chunks_point; ++c) s += a.partials[pr.chunk_begin_point + c];
+  a.out[p] = 0.5 * s * a.inv_sigma2;
+}
+
+int linearize_launch(const LinArgs &a, cudaStream_t stream) {
+  int launches = 0;
+  if (a.n_chunks > 0) {
+    lin_chunk_kernel<false><<<a.n_chunks, kLinThreads, 0, stream>>>(a);
+    ++launches;
+  }
+  if (a.n_pairs > 0) {
+    lin_finalize_kernel<<<a.n_pairs, 96, 0, stream>>>(a);
+    ++launches;
+  }
+  return launches;
+}
+
+int error_launch(const LinArgs &a, cudaStream_t stream) {
+  int launches = 0;
+  if (a.n_chunks > 0) {
+    lin_chunk_kernel<true><<<a.n_chunks, kLinThreads, 0, stream>>>(a);
+    ++launches;
+  }
+  if (a.n_pairs > 0) {
+    err_finalize_kernel<<<(a.n_pairs + 127) / 128, 128, 0, stream>>>(a);
+    ++launches;
+  }
+  return launches;
+}
+
+} // namespace formgpu

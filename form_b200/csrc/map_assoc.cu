@@ -1,0 +1,422 @@
+// Stage 2 on sm_100a: reparative map rebuild, voxel-hash nearest neighbour,
+// correspondence segments and novel-keypoint commit.
+//
+// Replaces KeypointMap::to_voxel_map / VoxelMap::push_back / find_closest
+// (/root/reference/form/mapping/map.tpp:34-165), Matcher::match
+// (/root/reference/form/optimization/matcher.hpp:67-112) and
+// KeypointMap::insert_matches (map.tpp:148-165).  Compiled with -fmad=false:
+// world coordinates, voxel keys and squared distances are evaluated in the
+// oracle's operation order so keys and neighbour ids are bit-exact.
+//
+// Data structure: tsl::robin_map<Vector3i, vector<Point>> becomes
+//   * an open-addressing table of 16-byte slots {packed voxel key, start, count}
+//     (linear probing, 64-bit CAS insert, load factor <= 0.5), and
+//   * the world points (32 B: x, y, z f64 + tie-break id) stored contiguously
+//     per voxel (CSR), so a bucket scan is a run of whole 32-byte sectors.
+// Search is warp-cooperative: one warp per query, lane l < 27 probes the
+// neighbour voxel with the reference's shift l (map.tpp:54-68) and scans its
+// bucket; a shuffle arg-min with the key (dist^2, shift rank, scan, k)
+// implements rule R5 (identical to the reference's strict-< visiting order).
+#include "ctx.hpp"
+#include "kernels.hpp"
+
+#include <cfloat>
+
+namespace formgpu {
+
+namespace {
+
+// map.tpp:54-68 in the reference's order
+__constant__ int c_shift[27][3] = {
+    {0, 0, 0},   {1, 0, 0},   {-1, 0, 0},  {0, 1, 0},   {0, -1, 0},  {0, 0, 1},   {0, 0, -1},
+    {1, 1, 0},   {1, -1, 0},  {-1, 1, 0},  {-1, -1, 0}, {1, 0, 1},   {1, 0, -1},  {-1, 0, 1},
+    {-1, 0, -1}, {0, 1, 1},   {0, 1, -1},  {0, -1, 1},  {0, -1, -1}, {1, 1, 1},   {1, 1, -1},
+    {1, -1, 1},  {1, -1, -1}, {-1, 1, 1},  {-1, 1, -1}, {-1, -1, 1}, {-1, -1, -1}};
+
+constexpr unsigned long long kEmptyKey = 0ull; // table is cleared with memset(0)
+
+// 21 bits per axis (two's complement wrap), bit 63 marks "occupied".
+__device__ __forceinline__ unsigned long long pack_key(int x, int y, int z) {
+  return (1ull << 63) | ((unsigned long long)(x & 0x1FFFFF) << 42) |
+         ((unsigned long long)(y & 0x1FFFFF) << 21) | (unsigned long long)(z & 0x1FFFFF);
+}
+
+__device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (uint32_t)k;
+}
+
+// VoxelMap::computeCoords (map.tpp:34-38): floor(p / width), IEEE division
+__device__ __forceinline__ int voxel_coord(double v, double width) {
+  return (int)floor(v / width);
+}
+
+// R p + t in the oracle's order ((r0 x + r1 y) + r2 z) + t
+__device__ __forceinline__ void transform_point(const double *T, double x, double y, double z,
+                                                double &ox, double &oy, double &oz) {
+  ox = ((T[0] * x + T[1] * y) + T[2] * z) + T[9];
+  oy = ((T[3] * x + T[4] * y) + T[5] * z) + T[10];
+  oz = ((T[6] * x + T[7] * y) + T[8] * z) + T[11];
+}
+
+template <typename Rec> __device__ __forceinline__ void load_xyz(const Rec *r, double &x, double &y, double &z) {
+  x = (double)r->x;
+  y = (double)r->y;
+  z = (double)r->z;
+}
+
+// global index -> (slot, k) through the exclusive prefix of the store counts
+__device__ __forceinline__ int find_slot_of(const int *off, int W, int g) {
+  int lo = 0, hi = W; // largest s with off[s] <= g
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= g) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------
+// map build, pass 1: transform + key + hash insert + per-voxel count
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) map_insert_kernel(MapArgs pa, MapArgs qa) {
+  const MapArgs &a = blockIdx.y == 0 ? pa : qa;
+  __shared__ int s_off[kMaxWindow + 1];
+  for (int i = threadIdx.x; i <= a.W; i += blockDim.x) s_off[i] = a.slot_off[i];
+  __syncthreads();
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.n_total) return;
+  const int slot = find_slot_of(s_off, a.W, g);
+  const int k = g - s_off[slot];
+  double x, y, z;
+  if (a.type == 0) load_xyz(reinterpret_cast<const PlanarRec *>(a.store) + (size_t)slot * a.kcap + k, x, y, z);
+  else load_xyz(reinterpret_cast<const PointRec *>(a.store) + (size_t)slot * a.kcap + k, x, y, z);
+  const double *T = a.slot_pose + 12 * slot;
+  double wx, wy, wz;
+  transform_point(T, x, y, z, wx, wy, wz);
+  const unsigned long long key = pack_key(voxel_coord(wx, a.voxel_width), voxel_coord(wy, a.voxel_width),
+                                          voxel_coord(wz, a.voxel_width));
+  uint32_t h = hash_key(key) & a.hash_mask;
+  for (;;) {
+    unsigned long long *kp = &a.hash[h].key;
+    unsigned long long cur = *kp;
+    if (cur == kEmptyKey) cur = atomicCAS(kp, kEmptyKey, key);
+    if (cur == kEmptyKey || cur == key) break;
+    h = (h + 1) & a.hash_mask;
+  }
+  atomicAdd(&a.hash[h].count, 1u);
+  a.world_slot[g] = h;
+  WorldPoint wp;
+  wp.x = wx; wp.y = wy; wp.z = wz;
+  wp.tie = (a.slot_scan[slot] << 24) | (unsigned long long)k; // rule R4 id
+  a.world_tmp[g] = wp;
+}
+
+// pass 2: give every occupied voxel a contiguous range; start is left pointing
+// one past the end and is walked down by the scatter pass
+__global__ void __launch_bounds__(256) map_alloc_kernel(MapArgs pa, MapArgs qa) {
+  const MapArgs &a = blockIdx.y == 0 ? pa : qa;
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h > a.hash_mask) return;
+  const uint32_t cnt = a.hash[h].count;
+  if (cnt) a.hash[h].start = atomicAdd(a.cursor, cnt) + cnt;
+}
+
+// pass 3: scatter into voxel-contiguous order
+__global__ void __launch_bounds__(256) map_scatter_kernel(MapArgs pa, MapArgs qa) {
+  const MapArgs &a = blockIdx.y == 0 ? pa : qa;
+  __shared__ int s_off[kMaxWindow + 1];
+  for (int i = threadIdx.x; i <= a.W; i += blockDim.x) s_off[i] = a.slot_off[i];
+  __syncthreads();
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.n_total) return;
+  const uint32_t h = a.world_slot[g];
+  const uint32_t pos = atomicSub(&a.hash[h].start, 1u) - 1u;
+  a.world[pos] = a.world_tmp[g];
+  const int slot = find_slot_of(s_off, a.W, g);
+  a.world_src[pos] = ((uint32_t)slot << 24) | (uint32_t)(g - s_off[slot]);
+}
+
+int map_build_launch(const MapArgs &pa, const MapArgs &qa, cudaStream_t stream) {
+  const int n = max(pa.n_total, qa.n_total);
+  int launches = 0;
+  if (n > 0) {
+    const dim3 gp((n + 255) / 256, 2);
+    map_insert_kernel<<<gp, 256, 0, stream>>>(pa, qa);
+    const uint32_t hs = max(pa.hash_mask, qa.hash_mask) + 1;
+    map_alloc_kernel<<<dim3((hs + 255) / 256, 2), 256, 0, stream>>>(pa, qa);
+    map_scatter_kernel<<<gp, 256, 0, stream>>>(pa, qa);
+    launches = 3;
+  }
+  return launches;
+}
+
+// ---------------------------------------------------------------------------
+// nearest neighbour: one warp per query keypoint
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs qa) {
+  const AssocArgs &a = blockIdx.y == 0 ? pa : qa;
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= a.n_query) return;
+  double x, y, z;
+  if (a.type == 0) load_xyz(reinterpret_cast<const PlanarRec *>(a.queries) + q, x, y, z);
+  else load_xyz(reinterpret_cast<const PointRec *>(a.queries) + q, x, y, z);
+  double wx, wy, wz;
+  transform_point(a.pose, x, y, z, wx, wy, wz); // kp->transform(init), matcher.hpp:89
+  const int cx = voxel_coord(wx, a.voxel_width), cy = voxel_coord(wy, a.voxel_width),
+            cz = voxel_coord(wz, a.voxel_width);
+
+  double best = DBL_MAX;                     // Match::dist_sqrd default (map.hpp:55)
+  unsigned long long best_tie = ~0ull;
+  uint32_t best_src = kNoSlot;
+  if (lane < 27 && a.n_map > 0) {
+    const unsigned long long key = pack_key(cx + c_shift[lane][0], cy + c_shift[lane][1], cz + c_shift[lane][2]);
+    uint32_t h = hash_key(key) & a.hash_mask;
+    uint32_t start = 0, count = 0;
+    for (;;) {
+      const HashSlot s = a.hash[h];
+      if (s.key == key) {
+        start = s.start;
+        count = s.count;
+        break;
+      }
+      if (s.key == kEmptyKey) break;
+      h = (h + 1) & a.hash_mask;
+    }
+    for (uint32_t i = 0; i < count; ++i) {
+      const WorldPoint p = a.world[start + i];
+      // 4-lane double squared norm, lane 3 = 0 padding: (d0^2 + d2^2) + (d1^2 + 0)
+      const double d0 = p.x - wx, d1 = p.y - wy, d2 = p.z - wz;
+      const double dist = (d0 * d0 + d2 * d2) + (d1 * d1 + 0.0);
+      if (dist < best || (dist == best && p.tie < best_tie)) {
+        best = dist;
+        best_tie = p.tie;
+        best_src = a.world_src[start + i];
+      }
+    }
+  }
+  // arg-min over lanes with key (dist, shift rank = lane, tie): rule R5
+  int best_lane = lane;
+  for (int off = 16; off > 0; off >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, best, off);
+    const unsigned long long ot = __shfl_xor_sync(0xffffffffu, best_tie, off);
+    const uint32_t os = __shfl_xor_sync(0xffffffffu, best_src, off);
+    const int ol = __shfl_xor_sync(0xffffffffu, best_lane, off);
+    const bool take = (os != kNoSlot) &&
+                      (best_src == kNoSlot || od < best ||
+                       (od == best && (ol < best_lane || (ol == best_lane && ot < best_tie))));
+    if (take) {
+      best = od;
+      best_tie = ot;
+      best_src = os;
+      best_lane = ol;
+    }
+  }
+  if (lane == 0) {
+    MatchRec m;
+    m.dist_sqrd = best_src == kNoSlot ? DBL_MAX : best;
+    m.slot = best_src == kNoSlot ? kNoSlot : (best_src >> 24);
+    m.k = best_src == kNoSlot ? 0u : (best_src & 0xFFFFFFu);
+    a.match[q] = m;
+  }
+}
+
+int assoc_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream) {
+  const int n = max(pa.n_query, qa.n_query);
+  if (n <= 0) return 0;
+  assoc_nn_kernel<<<dim3((n + 7) / 8, 2), 256, 0, stream>>>(pa, qa);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------
+// correspondence segment of the current scan: stable counting sort of the
+// accepted matches by the matched scan's slot (rule R6 order inside a pair)
+// ---------------------------------------------------------------------------
+// bin of a query: matched slot if dist^2 < max_dist^2 (matcher.hpp:104), else none.
+// Bin W counts the keypoints that insert_matches would add (map.tpp:161).
+__device__ __forceinline__ int match_bin(const MatchRec &m, double max_d2) {
+  return (m.slot != kNoSlot && m.dist_sqrd < max_d2) ? (int)m.slot : -1;
+}
+
+__global__ void __launch_bounds__(256) segment_hist_kernel(SegmentArgs pa, SegmentArgs qa) {
+  const SegmentArgs &a = blockIdx.y == 0 ? pa : qa;
+  __shared__ uint32_t s_hist[kMaxWindow + 1];
+  const int nb = a.W + 1;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((int)(blockIdx.x * blockDim.x) >= a.n_query) return;
+  if (q < a.n_query) {
+    const MatchRec m = a.match[q];
+    const int b = match_bin(m, a.max_dist2);
+    if (b >= 0) atomicAdd(&s_hist[b], 1u);
+    if (m.dist_sqrd > a.min_dist2) atomicAdd(&s_hist[a.W], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x)
+    a.block_hist[(size_t)blockIdx.x * nb + i] = s_hist[i];
+}
+
+// one block: per bin exclusive prefix over the query blocks, then the pair row
+__global__ void __launch_bounds__(256) segment_scan_kernel(SegmentArgs pa, SegmentArgs qa) {
+  const SegmentArgs &a = blockIdx.x == 0 ? pa : qa;
+  __shared__ uint32_t s_tot[kMaxWindow + 1];
+  const int nb = a.W + 1;
+  const int nblocks = (a.n_query + 255) / 256;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    uint32_t run = 0;
+    for (int blk = 0; blk < nblocks; ++blk) {
+      const uint32_t c = a.block_hist[(size_t)blk * nb + b];
+      a.block_hist[(size_t)blk * nb + b] = run;
+      run += c;
+    }
+    s_tot[b] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t off = 0;
+    for (int b = 0; b < a.W; ++b) {
+      a.pair_off[b] = off;
+      a.pair_cnt[b] = s_tot[b];
+      off += s_tot[b];
+    }
+    a.pair_off[a.W] = off;        // total correspondences
+    a.pair_cnt[a.W] = s_tot[a.W]; // novel keypoints
+  }
+}
+
+__global__ void __launch_bounds__(256) segment_scatter_kernel(SegmentArgs pa, SegmentArgs qa) {
+  const SegmentArgs &a = blockIdx.y == 0 ? pa : qa;
+  __shared__ uint32_t s_warp[8][kMaxWindow];
+  if ((int)(blockIdx.x * blockDim.x) >= a.n_query) return;
+  const int nb = a.W + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 8 * kMaxWindow; i += blockDim.x) (&s_warp[0][0])[i] = 0;
+  __syncthreads();
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  MatchRec m;
+  m.slot = kNoSlot;
+  m.dist_sqrd = DBL_MAX;
+  m.k = 0;
+  if (q < a.n_query) m = a.match[q];
+  const int b = q < a.n_query ? match_bin(m, a.max_dist2) : -1;
+  // stable rank inside the warp among lanes with the same bin
+  const unsigned peers = __match_any_sync(0xffffffffu, b);
+  const int rank_w = __popc(peers & ((1u << lane) - 1u));
+  if (b >= 0 && rank_w == 0) s_warp[warp][b] = __popc(peers);
+  __syncthreads();
+  if (b < 0) return;
+  uint32_t pos = a.pair_off[b] + a.block_hist[(size_t)blockIdx.x * nb + b] + rank_w;
+  for (int w = 0; w < warp; ++w) pos += s_warp[w][b];
+  // correspondence = (map point in its own scan frame, current keypoint):
+  // PlanePoint/PointPoint::push_back (factor.hpp:71-75, :113-116).  The map point
+  // is the stored local keypoint (the reference's world->local round trip,
+  // matcher.hpp:93-96, reproduces it to a few ulp).
+  if (a.type == 0) {
+    const PlanarRec pi = reinterpret_cast<const PlanarRec *>(a.store)[(size_t)m.slot * a.kcap + m.k];
+    const PlanarRec pj = reinterpret_cast<const PlanarRec *>(a.queries)[q];
+    float *s = a.seg;
+    const size_t st = a.kcap;
+    s[0 * st + pos] = pi.x;  s[1 * st + pos] = pi.y;  s[2 * st + pos] = pi.z;
+    s[3 * st + pos] = pi.nx; s[4 * st + pos] = pi.ny; s[5 * st + pos] = pi.nz;
+    s[6 * st + pos] = pj.x;  s[7 * st + pos] = pj.y;  s[8 * st + pos] = pj.z;
+  } else {
+    const PointRec pi = reinterpret_cast<const PointRec *>(a.store)[(size_t)m.slot * a.kcap + m.k];
+    const PointRec pj = reinterpret_cast<const PointRec *>(a.queries)[q];
+    float *s = a.seg;
+    const size_t st = a.kcap;
+    s[0 * st + pos] = pi.x; s[1 * st + pos] = pi.y; s[2 * st + pos] = pi.z;
+    s[3 * st + pos] = pj.x; s[4 * st + pos] = pj.y; s[5 * st + pos] = pj.z;
+  }
+}
+
+int segment_build_launch(const SegmentArgs &pa, const SegmentArgs &qa, cudaStream_t stream) {
+  const int n = max(pa.n_query, qa.n_query);
+  if (n <= 0) return 0;
+  const dim3 g((n + 255) / 256, 2);
+  segment_hist_kernel<<<g, 256, 0, stream>>>(pa, qa);
+  segment_scan_kernel<<<2, 256, 0, stream>>>(pa, qa);
+  segment_scatter_kernel<<<g, 256, 0, stream>>>(pa, qa);
+  return 3;
+}
+
+// ---------------------------------------------------------------------------
+// commit: append the novel keypoints (dist^2 > min_dist_map^2, unmatched
+// included) to the scan's stored keypoints, in keypoint order (map.tpp:160-164)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) commit_kernel(CommitArgs pa, CommitArgs qa) {
+  const CommitArgs &a = blockIdx.y == 0 ? pa : qa;
+  if ((int)(blockIdx.x * blockDim.x) >= a.n_query) return;
+  __shared__ uint32_t s_warp[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool novel = q < a.n_query && a.match[q].dist_sqrd > a.min_dist2;
+  const unsigned bal = __ballot_sync(0xffffffffu, novel);
+  if (lane == 0) s_warp[warp] = __popc(bal);
+  __syncthreads();
+  if (!novel) return;
+  uint32_t pos = a.dst_count + a.block_hist[(size_t)blockIdx.x * (a.W + 1) + a.W] +
+                 __popc(bal & ((1u << lane) - 1u));
+  for (int w = 0; w < warp; ++w) pos += s_warp[w];
+  if (a.type == 0)
+    reinterpret_cast<PlanarRec *>(a.store_dst)[pos] = reinterpret_cast<const PlanarRec *>(a.queries)[q];
+  else
+    reinterpret_cast<PointRec *>(a.store_dst)[pos] = reinterpret_cast<const PointRec *>(a.queries)[q];
+}
+
+int commit_launch(const CommitArgs &pa, const CommitArgs &qa, cudaStream_t stream) {
+  const int n = max(pa.n_query, qa.n_query);
+  if (n <= 0) return 0;
+  commit_kernel<<<dim3((n + 255) / 256, 2), 256, 0, stream>>>(pa, qa);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------
+// export: stored keypoints in the world frame as the API's f64 structs
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) world_export_kernel(WorldExportArgs a) {
+  __shared__ int s_off[kMaxWindow + 1];
+  for (int i = threadIdx.x; i <= a.W; i += blockDim.x) s_off[i] = a.slot_off[i];
+  __syncthreads();
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.n_total) return;
+  const int ord = find_slot_of(s_off, a.W, g); // position in scan-id order
+  const int slot = a.order[ord];
+  const int k = g - s_off[ord];
+  const double *T = a.slot_pose + 12 * slot;
+  if (a.type == 0) {
+    const PlanarRec r = reinterpret_cast<const PlanarRec *>(a.store)[(size_t)slot * a.kcap + k];
+    formgpu_planar_feat o;
+    transform_point(T, (double)r.x, (double)r.y, (double)r.z, o.x, o.y, o.z);
+    const double nx = r.nx, ny = r.ny, nz = r.nz;
+    o.nx = (T[0] * nx + T[1] * ny) + T[2] * nz;
+    o.ny = (T[3] * nx + T[4] * ny) + T[5] * nz;
+    o.nz = (T[6] * nx + T[7] * ny) + T[8] * nz;
+    o.pad = 0.0;
+    o.npad = 0.0;
+    o.scan = a.slot_scan[slot];
+    reinterpret_cast<formgpu_planar_feat *>(a.out)[g] = o;
+  } else {
+    const PointRec r = reinterpret_cast<const PointRec *>(a.store)[(size_t)slot * a.kcap + k];
+    formgpu_point_feat o;
+    transform_point(T, (double)r.x, (double)r.y, (double)r.z, o.x, o.y, o.z);
+    o.pad = 0.0;
+    o.scan = a.slot_scan[slot];
+    reinterpret_cast<formgpu_point_feat *>(a.out)[g] = o;
+  }
+}
+
+int world_export_launch(const WorldExportArgs &a, cudaStream_t stream) {
+  if (a.n_total <= 0) return 0;
+  world_export_kernel<<<(a.n_total + 255) / 256, 256, 0, stream>>>(a);
+  return 1;
+}
+
+} // namespace formgpu

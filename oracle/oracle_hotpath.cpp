@@ -16,8 +16,10 @@ namespace {
 class Pool {
 public:
   static Pool &get() {
-    static Pool p;
-    return p;
+    // leaked on purpose: the detached workers wait on its condition variable for the
+    // whole process lifetime, and destroying a condvar with waiters blocks at exit
+    static Pool *p = new Pool();
+    return *p;
   }
   void parallel_for(size_t n, int nthreads, const std::function<void(size_t, size_t)> &fn) {
     if (nthreads <= 1 || n < 2) {
