@@ -44,7 +44,7 @@ $(OBJDIR)/host_%.o: form_b200/host/src/%.cpp $(HOST_HDRS)
 $(LIBDIR)/libformhost.so: $(HOST_OBJS) $(LIBDIR)/libformgpu.so
 	$(CXX) -shared -pthread -o $@ $(HOST_OBJS) -L$(LIBDIR) -lformgpu -Wl,-rpath,'$$ORIGIN'
 
-oracle:
+oracle: $(LIBDIR)/libformgpu.so
 	$(MAKE) -s -C oracle
 
 clean:

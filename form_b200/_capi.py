@@ -30,8 +30,9 @@ MATCH = np.dtype([("scan", "<u8"), ("k", "<u4"), ("found", "<u4"), ("dist_sqrd",
 assert POINT4F.itemsize == 16 and POINT_FEAT.itemsize == 40 and PLANAR_FEAT.itemsize == 72
 assert POSE.itemsize == 96 and SCAN_POSE.itemsize == 104 and MATCH.itemsize == 24
 
-NUM_STAGES = 6
-STAGE_NAMES = ("extract", "map", "assoc", "linearize", "error", "commit")
+KG_COUNT = 12
+KG_NAMES = ("extract_select", "extract_normals", "extract_pack", "map_build", "assoc_nn", "segment",
+            "lin_chunk", "lin_finalize", "err_chunk", "err_finalize", "commit", "export")
 
 OK, ERR_INVALID_ARG, ERR_BAD_SCAN_SIZE, ERR_CAPACITY, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = range(7)
 
@@ -58,6 +59,41 @@ class Params(C.Structure):
         ("max_batch_scans", C.c_int32),
         ("reserved", C.c_int32),
     ]
+
+
+class EstParams(C.Structure):
+    """formhost_est_params (form/capi_impl.hpp)"""
+
+    _fields_ = [
+        ("hot", Params),
+        ("new_pose_threshold", C.c_double),
+        ("keyscan_match_ratio", C.c_double),
+        ("max_num_rematches", C.c_int32),
+        ("disable_smoothing", C.c_int32),
+        ("max_num_keyscans", C.c_int32),
+        ("max_num_recent_scans", C.c_int32),
+        ("max_steps_unused_keyscan", C.c_int32),
+        ("num_threads", C.c_int32),
+        ("device", C.c_int32),
+        ("record_trace", C.c_int32),
+    ]
+
+
+def default_est_params(rows: int = 64, cols: int = 1024, **overrides) -> EstParams:
+    """Estimator::Params defaults (python/bindings.cpp:66-88 of FORM).  Keys of
+    formgpu_params and of the estimator-level struct can both be overridden."""
+    hot_keys = {f[0] for f in Params._fields_}
+    hot = default_params(rows, cols, **{k: v for k, v in overrides.items() if k in hot_keys})
+    p = EstParams(hot=hot, new_pose_threshold=1e-4, keyscan_match_ratio=0.1, max_num_rematches=30,
+                  disable_smoothing=0, max_num_keyscans=50, max_num_recent_scans=10,
+                  max_steps_unused_keyscan=10, num_threads=0, device=0, record_trace=0)
+    for k, v in overrides.items():
+        if k in hot_keys:
+            continue
+        if not hasattr(p, k):
+            raise AttributeError(f"formhost_est_params has no field {k!r}")
+        setattr(p, k, v)
+    return p
 
 
 def default_params(rows: int = 64, cols: int = 1024, **overrides) -> Params:
@@ -108,16 +144,54 @@ FORMGPU_SYMBOLS = {
     "formgpu_linearize": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "formgpu_error": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "formgpu_profile_enable": (_i, [_vp, _i]),
-    "formgpu_profile_read": (_i, [_vp, _vp, _vp, _vp]),
+    "formgpu_profile_read": (_i, [_vp, _vp, _vp]),
     "formgpu_launch_count": (_u64, [_vp]),
     "formgpu_synchronize": (_i, [_vp]),
 }
+
+_pest = C.POINTER(EstParams)
+_d = C.c_double
+
+
+def estimator_symbols(prefix: str) -> dict:
+    """The C API generated from form/capi_impl.hpp (prefix formhost_ or oracle_)."""
+    return {
+        f"{prefix}est_create": (_vp, [_pest]),
+        f"{prefix}est_destroy": (None, [_vp]),
+        f"{prefix}est_register_scan": (_i, [_vp, _vp, _sz, _vp, _sz, _psz, _vp, _sz, _psz]),
+        f"{prefix}est_pose": (None, [_vp, _vp]),
+        f"{prefix}est_window": (_i, [_vp, _vp, _sz, _psz]),
+        f"{prefix}est_stats": (None, [_vp, _vp]),
+        f"{prefix}est_map": (_i, [_vp, _vp, _sz, _psz, _vp, _sz, _psz]),
+        f"{prefix}est_trace": (_vp, [_vp]),
+        f"{prefix}trace_num_scans": (_sz, [_vp]),
+        f"{prefix}replay_destroy": (None, [_vp]),
+        f"{prefix}replay_run_host": (_d, [_vp, _sz, _sz, _vp]),
+        f"{prefix}replay_stats": (None, [_vp, _vp, C.POINTER(_d)]),
+        f"{prefix}replay_reset_stats": (None, [_vp]),
+    }
+
 
 FORMHOST_SYMBOLS = {
     "formhost_synth_shape": (_sz, [_i, C.POINTER(_i), C.POINTER(_i)]),
     "formhost_synth_scan": (_i, [_i, _u64, _u64, _vp, _i]),
     "formhost_synth_gt_pose": (None, [_u64, _u64, _vp]),
+    "formhost_default_est_params": (None, [_pest]),
+    "formhost_last_error": (C.c_char_p, []),
+    "formhost_est_error": (C.c_char_p, [_vp]),
+    "formhost_est_ctx": (_vp, [_vp]),
+    "formhost_trace_num_ops": (_sz, [_vp]),
+    "formhost_replay_create": (_vp, [_vp, _pest, _vp]),
+    "formhost_replay_ctx": (_vp, [_vp]),
+    "formhost_replay_run_device": (_d, [_vp, _sz, _sz, _vp]),
+    **estimator_symbols("formhost_"),
 }
+
+REPLAY_STAT_NAMES = (
+    "scans", "points", "planar_kp", "point_kp", "assoc_calls", "assoc_queries", "map_rebuilds",
+    "map_points", "lin_calls", "lin_pairs", "lin_planar", "lin_point", "err_calls", "err_pairs",
+    "err_planar", "err_point", "novel_planar", "novel_point",
+)
 
 
 def _load(path: str, symbols: dict) -> C.CDLL:

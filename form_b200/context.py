@@ -163,12 +163,11 @@ class Context:
         self._check(self._lib.formgpu_profile_enable(self._h, int(on)))
 
     def profile_read(self):
-        ms = np.zeros(_capi.NUM_STAGES)
-        calls = np.zeros(_capi.NUM_STAGES, np.uint64)
-        launches = np.zeros(_capi.NUM_STAGES, np.uint64)
-        self._check(self._lib.formgpu_profile_read(self._h, _capi.ptr(ms), _capi.ptr(calls), _capi.ptr(launches)))
-        return {name: dict(ms=float(ms[i]), calls=int(calls[i]), launches=int(launches[i]))
-                for i, name in enumerate(_capi.STAGE_NAMES)}
+        ms = np.zeros(_capi.KG_COUNT)
+        launches = np.zeros(_capi.KG_COUNT, np.uint64)
+        self._check(self._lib.formgpu_profile_read(self._h, _capi.ptr(ms), _capi.ptr(launches)))
+        return {name: dict(ms=float(ms[i]), launches=int(launches[i]))
+                for i, name in enumerate(_capi.KG_NAMES)}
 
     def launch_count(self) -> int:
         return int(self._lib.formgpu_launch_count(self._h))

@@ -126,8 +126,7 @@ static int create_impl(formgpu_ctx *ctx) {
     FORMGPU_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->own_stream = true;
   }
-  FORMGPU_CUDA(ctx, cudaEventCreate(&ctx->ev_a));
-  FORMGPU_CUDA(ctx, cudaEventCreate(&ctx->ev_b));
+  ctx->prof.stream = ctx->stream;
 
   const size_t B = ctx->B, R = ctx->rows, W = ctx->W;
   // stage 1
@@ -252,8 +251,7 @@ void formgpu_destroy(formgpu_ctx *ctx) {
   F(ctx->d_partials); F(ctx->d_request); F(ctx->d_out);
   H(ctx->h_counts); H(ctx->h_planar); H(ctx->h_point); H(ctx->h_upload); H(ctx->h_out);
   H(ctx->h_pair);
-  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
-  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  ctx->prof.destroy();
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -304,13 +302,12 @@ static ExtractArgs make_extract_args(formgpu_ctx *ctx, const float4 *scan_dev, b
 }
 
 // runs the kernels on a device-resident scan and fetches the two counts
-static int extract_run(formgpu_ctx *ctx, const float4 *scan_dev, uint64_t scan_idx,
-                       StageScope &scope) {
+static int extract_run(formgpu_ctx *ctx, const float4 *scan_dev, uint64_t scan_idx) {
   ctx->cur_buf ^= 1;
   ctx->d_cur_planar = ctx->d_cur_planar_buf[ctx->cur_buf];
   ctx->d_cur_point = ctx->d_cur_point_buf[ctx->cur_buf];
   const ExtractArgs a = make_extract_args(ctx, scan_dev, false);
-  scope.launches(extract_launch(a, 1, ctx->stream));
+  extract_launch(a, 1, ctx->stream, ctx->prof);
   FORMGPU_CUDA(ctx, cudaGetLastError());
   FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, ctx->d_cur_counts, 2 * sizeof(int),
                                     cudaMemcpyDeviceToHost, ctx->stream));
@@ -336,11 +333,12 @@ int formgpu_extract(formgpu_ctx *ctx, const formgpu_point4f *scan, size_t n, uin
                 "Provided scan does not match the expected size " +
                     std::to_string(ctx->n_points) + " != " + std::to_string(n));
   FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
-  StageScope scope(ctx, FORMGPU_STAGE_EXTRACT);
+  ProfScope scope(ctx);
   FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_scan, scan, n * sizeof(float4), cudaMemcpyHostToDevice,
                                     ctx->stream));
-  const int rc = extract_run(ctx, ctx->d_scan, scan_idx, scope);
+  const int rc = extract_run(ctx, ctx->d_scan, scan_idx);
   if (rc) return rc;
+  ctx->cur_device_resident = false;
   const size_t np = (size_t)ctx->cur_n[0], nq = (size_t)ctx->cur_n[1];
   *n_planar = np;
   *n_point = nq;
@@ -378,11 +376,11 @@ int formgpu_extract_device(formgpu_ctx *ctx, const formgpu_point4f *scan_dev, si
   if (n != ctx->n_points)
     return fail(ctx, FORMGPU_ERR_BAD_SCAN_SIZE, "Provided scan does not match the expected size");
   FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
-  StageScope scope(ctx, FORMGPU_STAGE_EXTRACT);
-  // keep a copy so extract_debug can re-run on it (device-to-device, off the PCIe path)
-  FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_scan, scan_dev, n * sizeof(float4),
-                                    cudaMemcpyDeviceToDevice, ctx->stream));
-  const int rc = extract_run(ctx, ctx->d_scan, scan_idx, scope);
+  ProfScope scope(ctx);
+  // the kernels read the caller's device buffer in place; extract_debug is only
+  // available after formgpu_extract (which keeps its own copy)
+  const int rc = extract_run(ctx, reinterpret_cast<const float4 *>(scan_dev), scan_idx);
+  ctx->cur_device_resident = true;
   if (rc) return rc;
   *n_planar = (size_t)ctx->cur_n[0];
   *n_point = (size_t)ctx->cur_n[1];
@@ -394,7 +392,8 @@ int formgpu_extract_debug(formgpu_ctx *ctx, uint8_t *valid_mask, uint8_t *point_
                           int32_t *closest_prev, int32_t *closest_next, size_t *n_planar_picks,
                           uint32_t *point_indices, size_t *n_point_picks) {
   if (!ctx) return FORMGPU_ERR_INVALID_ARG;
-  if (!ctx->have_current) return fail(ctx, FORMGPU_ERR_STATE, "no scan has been extracted");
+  if (!ctx->have_current || ctx->cur_device_resident)
+    return fail(ctx, FORMGPU_ERR_STATE, "formgpu_extract_debug needs a preceding formgpu_extract");
   FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t N = ctx->n_points, R = ctx->rows;
   if (!ctx->d_dbg_valid) {
@@ -405,7 +404,7 @@ int formgpu_extract_debug(formgpu_ctx *ctx, uint8_t *valid_mask, uint8_t *point_
   }
   // re-run stage 1 on the resident scan with the debug outputs switched on
   const ExtractArgs a = make_extract_args(ctx, ctx->d_scan, true);
-  ctx->launches += (uint64_t)extract_launch(a, 1, ctx->stream);
+  extract_launch(a, 1, ctx->stream, ctx->prof);
   FORMGPU_CUDA(ctx, cudaGetLastError());
   std::vector<int> pcnt(R), qcnt(R), closest(R * ctx->pr_cap * 2);
   std::vector<uint16_t> pcols(R * ctx->pr_cap), qcols(R * ctx->qr_cap);
@@ -443,24 +442,24 @@ int formgpu_extract_debug(formgpu_ctx *ctx, uint8_t *valid_mask, uint8_t *point_
 // ---------------------------------------------------------------------------
 int formgpu_profile_enable(formgpu_ctx *ctx, int on) {
   if (!ctx) return FORMGPU_ERR_INVALID_ARG;
-  ctx->profiling = on != 0;
+  ctx->prof.collect();
+  ctx->prof.timing = on != 0;
   return FORMGPU_OK;
 }
 
-int formgpu_profile_read(formgpu_ctx *ctx, double ms[FORMGPU_NUM_STAGES],
-                         uint64_t calls[FORMGPU_NUM_STAGES],
-                         uint64_t launches[FORMGPU_NUM_STAGES]) {
+int formgpu_profile_read(formgpu_ctx *ctx, double ms[FORMGPU_KG_COUNT],
+                         uint64_t launches[FORMGPU_KG_COUNT]) {
   if (!ctx) return FORMGPU_ERR_INVALID_ARG;
-  for (int s = 0; s < FORMGPU_NUM_STAGES; ++s) {
-    if (ms) ms[s] = ctx->prof[s].ms;
-    if (calls) calls[s] = ctx->prof[s].calls;
-    if (launches) launches[s] = ctx->prof[s].launches;
-    ctx->prof[s] = StageProf();
+  ctx->prof.collect();
+  for (int g = 0; g < FORMGPU_KG_COUNT; ++g) {
+    if (ms) ms[g] = ctx->prof.group[g].ms;
+    if (launches) launches[g] = ctx->prof.group[g].launches;
+    ctx->prof.group[g] = GroupProf();
   }
   return FORMGPU_OK;
 }
 
-uint64_t formgpu_launch_count(const formgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t formgpu_launch_count(const formgpu_ctx *ctx) { return ctx ? ctx->prof.total_launches : 0; }
 
 int formgpu_synchronize(formgpu_ctx *ctx) {
   if (!ctx) return FORMGPU_ERR_INVALID_ARG;

@@ -22,26 +22,12 @@ inline int fail(const formgpu_ctx *ctx, int code, const std::string &msg) {
                              std::string(#expr) + ": " + cudaGetErrorString(e_));      \
   } while (0)
 
-/// Brackets one stage with CUDA events when profiling is on and counts launches.
-struct StageScope {
+/// Collects the event timings of an API call on scope exit (profiling mode only).
+struct ProfScope {
   formgpu_ctx *ctx;
-  int stage;
-  StageScope(formgpu_ctx *c, int s) : ctx(c), stage(s) {
-    if (ctx->profiling) cudaEventRecord(ctx->ev_a, ctx->stream);
-  }
-  void launches(int n) {
-    ctx->launches += (uint64_t)n;
-    ctx->prof[stage].launches += (uint64_t)n;
-  }
-  ~StageScope() {
-    ctx->prof[stage].calls += 1;
-    if (ctx->profiling) {
-      cudaEventRecord(ctx->ev_b, ctx->stream);
-      cudaEventSynchronize(ctx->ev_b);
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
-      ctx->prof[stage].ms += (double)ms;
-    }
+  explicit ProfScope(formgpu_ctx *c) : ctx(c) {}
+  ~ProfScope() {
+    if (ctx->prof.timing) ctx->prof.collect();
   }
 };
 

@@ -65,7 +65,7 @@ int formgpu_map_rebuild(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
   if (n_poses && !poses) return fail(ctx, FORMGPU_ERR_INVALID_ARG, "formgpu_map_rebuild: null poses");
   FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   const int W = ctx->W;
-  StageScope scope(ctx, FORMGPU_STAGE_MAP);
+  ProfScope scope(ctx);
   FORMGPU_CUDA(ctx, cudaEventSynchronize(ctx->ev_upload));
   MapReq h = map_req_view(ctx->h_map_req, W);
   std::vector<uint8_t> has_pose(W, 0);
@@ -125,7 +125,7 @@ int formgpu_map_rebuild(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
     a[t].world = ctx->d_world[t];
     a[t].cursor = reinterpret_cast<uint32_t *>(ctx->d_mapmem) + 16 * t;
   }
-  scope.launches(map_build_launch(a[0], a[1], ctx->stream));
+  map_build_launch(a[0], a[1], ctx->stream, ctx->prof);
   FORMGPU_CUDA(ctx, cudaGetLastError());
   ctx->map_built = true;
   return FORMGPU_OK;
@@ -142,7 +142,7 @@ int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k, formgpu_pair
   const int W = ctx->W;
   const int slot_k = ensure_slot(ctx, ctx->cur_scan);
   if (slot_k < 0) return fail(ctx, FORMGPU_ERR_CAPACITY, "window is full (max_window_scans)");
-  StageScope scope(ctx, FORMGPU_STAGE_ASSOC);
+  ProfScope scope(ctx);
 
   const int nq[2] = {ctx->cur_n[0], ctx->cur_n[1]};
   if (nq[0] > 0 || nq[1] > 0) {
@@ -177,8 +177,8 @@ int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k, formgpu_pair
       sa[t].seg = t == 0 ? ctx->d_seg_planar + (size_t)slot_k * 9 * kcap
                          : ctx->d_seg_point + (size_t)slot_k * 6 * kcap;
     }
-    scope.launches(assoc_launch(aa[0], aa[1], ctx->stream));
-    scope.launches(segment_build_launch(sa[0], sa[1], ctx->stream));
+    assoc_launch(aa[0], aa[1], ctx->stream, ctx->prof);
+    segment_build_launch(sa[0], sa[1], ctx->stream, ctx->prof);
     FORMGPU_CUDA(ctx, cudaGetLastError());
     FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_pair, ctx->d_pair, 4 * (W + 1) * sizeof(uint32_t),
                                       cudaMemcpyDeviceToHost, ctx->stream));
@@ -245,7 +245,7 @@ int formgpu_get_matches(formgpu_ctx *ctx, int type, formgpu_match *out, size_t c
 int formgpu_commit_scan(formgpu_ctx *ctx, size_t *n_planar_added, size_t *n_point_added) {
   if (!ctx) return FORMGPU_ERR_INVALID_ARG;
   FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
-  StageScope scope(ctx, FORMGPU_STAGE_COMMIT);
+  ProfScope scope(ctx);
   CommitArgs ca[2];
   size_t added[2] = {0, 0};
   int slots[2] = {-1, -1};
@@ -272,7 +272,7 @@ int formgpu_commit_scan(formgpu_ctx *ctx, size_t *n_planar_added, size_t *n_poin
                              : (void *)(ctx->d_store_point + (size_t)slot * kcap);
     ca[t].dst_count = (uint32_t)ctx->store_n[t][slot];
   }
-  scope.launches(commit_launch(ca[0], ca[1], ctx->stream));
+  commit_launch(ca[0], ca[1], ctx->stream, ctx->prof);
   FORMGPU_CUDA(ctx, cudaGetLastError());
   for (int t = 0; t < 2; ++t)
     if (slots[t] >= 0) ctx->store_n[t][slots[t]] += (int)added[t];
@@ -396,7 +396,7 @@ int formgpu_world_keypoints(formgpu_ctx *ctx, const formgpu_scan_pose *poses, si
     a.slot_scan = d.scan;
     a.n_total = (int)total[t];
     a.out = t == 0 ? out_dev : out_dev + total[0] * sizeof(formgpu_planar_feat);
-    ctx->launches += (uint64_t)world_export_launch(a, ctx->stream);
+    world_export_launch(a, ctx->stream, ctx->prof);
   }
   FORMGPU_CUDA(ctx, cudaGetLastError());
   if (total[0])

@@ -119,11 +119,11 @@ int formgpu_linearize(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pair
   if (!pairs || !out91 || (n_poses && !poses))
     return fail(ctx, FORMGPU_ERR_INVALID_ARG, "formgpu_linearize: null argument");
   FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
-  StageScope scope(ctx, FORMGPU_STAGE_LINEARIZE);
+  ProfScope scope(ctx);
   LinArgs a{};
   const int rc = prepare(ctx, pairs, n_pairs, poses, n_poses, 28, a);
   if (rc) return rc;
-  scope.launches(linearize_launch(a, ctx->stream));
+  linearize_launch(a, ctx->stream, ctx->prof);
   FORMGPU_CUDA(ctx, cudaGetLastError());
   FORMGPU_CUDA(ctx, cudaMemcpyAsync(out91, ctx->d_out, n_pairs * 91 * sizeof(double),
                                     cudaMemcpyDeviceToHost, ctx->stream));
@@ -138,11 +138,11 @@ int formgpu_error(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
   if (!pairs || !out || (n_poses && !poses))
     return fail(ctx, FORMGPU_ERR_INVALID_ARG, "formgpu_error: null argument");
   FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
-  StageScope scope(ctx, FORMGPU_STAGE_ERROR);
+  ProfScope scope(ctx);
   LinArgs a{};
   const int rc = prepare(ctx, pairs, n_pairs, poses, n_poses, 1, a);
   if (rc) return rc;
-  scope.launches(error_launch(a, ctx->stream));
+  error_launch(a, ctx->stream, ctx->prof);
   FORMGPU_CUDA(ctx, cudaGetLastError());
   FORMGPU_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n_pairs * sizeof(double), cudaMemcpyDeviceToHost,
                                     ctx->stream));

@@ -70,10 +70,54 @@ struct PairEntry { // per (current slot k, map slot i)
 constexpr int kMaxWindow = 128;
 constexpr uint32_t kNoSlot = 0xffffffffu;
 
-struct StageProf {
+struct GroupProf {
   double ms = 0;
-  uint64_t calls = 0;
   uint64_t launches = 0;
+};
+
+/// Brackets kernel launches with CUDA events when timing is on; always counts launches.
+struct Profiler {
+  bool timing = false;
+  cudaStream_t stream = nullptr;
+  GroupProf group[FORMGPU_KG_COUNT];
+  uint64_t total_launches = 0;
+  struct Pending { int g; cudaEvent_t a, b; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t take() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void begin(int g) {
+    if (!timing) return;
+    Pending p{g, take(), take()};
+    cudaEventRecord(p.a, stream);
+    pending.push_back(p);
+  }
+  void end(int g, int launches) {
+    group[g].launches += (uint64_t)launches;
+    total_launches += (uint64_t)launches;
+    if (!timing) return;
+    cudaEventRecord(pending.back().b, stream);
+  }
+  /// after the work has been queued: wait and fold the event pairs into the sums
+  void collect() {
+    if (pending.empty()) return;
+    cudaEventSynchronize(pending.back().b);
+    for (auto &p : pending) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, p.a, p.b);
+      group[p.g].ms += (double)ms;
+      pool.push_back(p.a);
+      pool.push_back(p.b);
+    }
+    pending.clear();
+  }
+  void destroy() {
+    collect();
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    pool.clear();
+  }
 };
 
 } // namespace formgpu
@@ -182,8 +226,5 @@ struct formgpu_ctx {
   size_t out_cap = 0; // pairs
 
   // ---- instrumentation ----
-  bool profiling = false;
-  formgpu::StageProf prof[FORMGPU_NUM_STAGES];
-  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
-  uint64_t launches = 0;
+  formgpu::Profiler prof;
 };

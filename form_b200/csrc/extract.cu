@@ -671,12 +671,17 @@ cudaError_t extract_configure(int cols, int cols_pad, int words, int pr_cap) {
                               (int)extract_normals_smem(cols, words, pr_cap));
 }
 
-int extract_launch(const ExtractArgs &a, int n_scans, cudaStream_t stream) {
+void extract_launch(const ExtractArgs &a, int n_scans, cudaStream_t stream, Profiler &prof) {
   const dim3 grid(a.rows, n_scans);
+  prof.begin(FORMGPU_KG_EXTRACT_SELECT);
   extract_select_kernel<<<grid, 256, extract_select_smem(a.cols, a.cols_pad, a.words), stream>>>(a);
+  prof.end(FORMGPU_KG_EXTRACT_SELECT, 1);
+  prof.begin(FORMGPU_KG_EXTRACT_NORMALS);
   extract_normals_kernel<<<grid, 256, extract_normals_smem(a.cols, a.words, a.pr_cap), stream>>>(a);
+  prof.end(FORMGPU_KG_EXTRACT_NORMALS, 1);
+  prof.begin(FORMGPU_KG_EXTRACT_PACK);
   extract_pack_kernel<<<grid, 128, 0, stream>>>(a);
-  return 3;
+  prof.end(FORMGPU_KG_EXTRACT_PACK, 1);
 }
 
 } // namespace formgpu

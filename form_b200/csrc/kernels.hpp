@@ -32,8 +32,8 @@ struct ExtractArgs {
 cudaError_t extract_configure(int cols, int cols_pad, int words, int pr_cap);
 size_t extract_select_smem(int cols, int cols_pad, int words);
 size_t extract_normals_smem(int cols, int words, int pr_cap);
-/// Launches the three stage-1 kernels; returns the number of launches.
-int extract_launch(const ExtractArgs &a, int n_scans, cudaStream_t stream);
+/// Launches the three stage-1 kernels.
+void extract_launch(const ExtractArgs &a, int n_scans, cudaStream_t stream, Profiler &prof);
 
 // ---- stage 2 (map_assoc.cu, compiled with -fmad=false) ----
 struct MapArgs {
@@ -54,7 +54,7 @@ struct MapArgs {
   WorldPoint *world;     // voxel-sorted
   uint32_t *cursor;      // allocation cursor (zeroed before the build)
 };
-int map_build_launch(const MapArgs &planar, const MapArgs &point, cudaStream_t stream);
+void map_build_launch(const MapArgs &planar, const MapArgs &point, cudaStream_t stream, Profiler &prof);
 
 struct AssocArgs {
   int type;
@@ -69,7 +69,7 @@ struct AssocArgs {
   const uint32_t *world_src;
   MatchRec *match;
 };
-int assoc_launch(const AssocArgs &planar, const AssocArgs &point, cudaStream_t stream);
+void assoc_launch(const AssocArgs &planar, const AssocArgs &point, cudaStream_t stream, Profiler &prof);
 
 struct SegmentArgs {
   int type;
@@ -86,7 +86,7 @@ struct SegmentArgs {
   uint32_t *pair_cnt;   // [W+1] (entry W = novel keypoints)
   float *seg;           // segment base of the current slot: [9 or 6][kcap]
 };
-int segment_build_launch(const SegmentArgs &planar, const SegmentArgs &point, cudaStream_t stream);
+void segment_build_launch(const SegmentArgs &planar, const SegmentArgs &point, cudaStream_t stream, Profiler &prof);
 
 struct CommitArgs {
   int type;
@@ -99,7 +99,7 @@ struct CommitArgs {
   void *store_dst;   // store slot base of the scan being appended to
   uint32_t dst_count; // keypoints already stored there
 };
-int commit_launch(const CommitArgs &planar, const CommitArgs &point, cudaStream_t stream);
+void commit_launch(const CommitArgs &planar, const CommitArgs &point, cudaStream_t stream, Profiler &prof);
 
 struct WorldExportArgs {
   int type;
@@ -113,7 +113,7 @@ struct WorldExportArgs {
   int n_total;
   void *out; // formgpu_planar_feat* / formgpu_point_feat* (device)
 };
-int world_export_launch(const WorldExportArgs &a, cudaStream_t stream);
+void world_export_launch(const WorldExportArgs &a, cudaStream_t stream, Profiler &prof);
 
 // ---- stage 3 (linearize.cu, FMA allowed: tolerance class) ----
 struct LinPair {   // one requested pair
@@ -141,7 +141,7 @@ struct LinArgs {
   double *partials; // [n_chunks][28] (linearize) or [n_chunks] (error)
   double *out;      // [n_pairs][91] or [n_pairs]
 };
-int linearize_launch(const LinArgs &a, cudaStream_t stream);
-int error_launch(const LinArgs &a, cudaStream_t stream);
+void linearize_launch(const LinArgs &a, cudaStream_t stream, Profiler &prof);
+void error_launch(const LinArgs &a, cudaStream_t stream, Profiler &prof);
 
 } // namespace formgpu

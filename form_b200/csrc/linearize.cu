@@ -253,30 +253,30 @@ __global__ void __launch_bounds__(128) err_finalize_kernel(LinArgs a) {
   a.out[p] = 0.5 * s * a.inv_sigma2;
 }
 
-int linearize_launch(const LinArgs &a, cudaStream_t stream) {
-  int launches = 0;
+void linearize_launch(const LinArgs &a, cudaStream_t stream, Profiler &prof) {
   if (a.n_chunks > 0) {
+    prof.begin(FORMGPU_KG_LIN_CHUNK);
     lin_chunk_kernel<false><<<a.n_chunks, kLinThreads, 0, stream>>>(a);
-    ++launches;
+    prof.end(FORMGPU_KG_LIN_CHUNK, 1);
   }
   if (a.n_pairs > 0) {
+    prof.begin(FORMGPU_KG_LIN_FINALIZE);
     lin_finalize_kernel<<<a.n_pairs, 96, 0, stream>>>(a);
-    ++launches;
+    prof.end(FORMGPU_KG_LIN_FINALIZE, 1);
   }
-  return launches;
 }
 
-int error_launch(const LinArgs &a, cudaStream_t stream) {
-  int launches = 0;
+void error_launch(const LinArgs &a, cudaStream_t stream, Profiler &prof) {
   if (a.n_chunks > 0) {
+    prof.begin(FORMGPU_KG_ERR_CHUNK);
     lin_chunk_kernel<true><<<a.n_chunks, kLinThreads, 0, stream>>>(a);
-    ++launches;
+    prof.end(FORMGPU_KG_ERR_CHUNK, 1);
   }
   if (a.n_pairs > 0) {
+    prof.begin(FORMGPU_KG_ERR_FINALIZE);
     err_finalize_kernel<<<(a.n_pairs + 127) / 128, 128, 0, stream>>>(a);
-    ++launches;
+    prof.end(FORMGPU_KG_ERR_FINALIZE, 1);
   }
-  return launches;
 }
 
 } // namespace formgpu

@@ -143,18 +143,16 @@ __global__ void __launch_bounds__(256) map_scatter_kernel(MapArgs pa, MapArgs qa
   a.world_src[pos] = ((uint32_t)slot << 24) | (uint32_t)(g - s_off[slot]);
 }
 
-int map_build_launch(const MapArgs &pa, const MapArgs &qa, cudaStream_t stream) {
+void map_build_launch(const MapArgs &pa, const MapArgs &qa, cudaStream_t stream, Profiler &prof) {
   const int n = max(pa.n_total, qa.n_total);
-  int launches = 0;
-  if (n > 0) {
-    const dim3 gp((n + 255) / 256, 2);
-    map_insert_kernel<<<gp, 256, 0, stream>>>(pa, qa);
-    const uint32_t hs = max(pa.hash_mask, qa.hash_mask) + 1;
-    map_alloc_kernel<<<dim3((hs + 255) / 256, 2), 256, 0, stream>>>(pa, qa);
-    map_scatter_kernel<<<gp, 256, 0, stream>>>(pa, qa);
-    launches = 3;
-  }
-  return launches;
+  if (n <= 0) return;
+  prof.begin(FORMGPU_KG_MAP_BUILD);
+  const dim3 gp((n + 255) / 256, 2);
+  map_insert_kernel<<<gp, 256, 0, stream>>>(pa, qa);
+  const uint32_t hs = max(pa.hash_mask, qa.hash_mask) + 1;
+  map_alloc_kernel<<<dim3((hs + 255) / 256, 2), 256, 0, stream>>>(pa, qa);
+  map_scatter_kernel<<<gp, 256, 0, stream>>>(pa, qa);
+  prof.end(FORMGPU_KG_MAP_BUILD, 3);
 }
 
 // ---------------------------------------------------------------------------
@@ -228,11 +226,12 @@ __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs q
   }
 }
 
-int assoc_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream) {
+void assoc_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream, Profiler &prof) {
   const int n = max(pa.n_query, qa.n_query);
-  if (n <= 0) return 0;
+  if (n <= 0) return;
+  prof.begin(FORMGPU_KG_ASSOC_NN);
   assoc_nn_kernel<<<dim3((n + 7) / 8, 2), 256, 0, stream>>>(pa, qa);
-  return 1;
+  prof.end(FORMGPU_KG_ASSOC_NN, 1);
 }
 
 // ---------------------------------------------------------------------------
@@ -337,14 +336,16 @@ __global__ void __launch_bounds__(256) segment_scatter_kernel(SegmentArgs pa, Se
   }
 }
 
-int segment_build_launch(const SegmentArgs &pa, const SegmentArgs &qa, cudaStream_t stream) {
+void segment_build_launch(const SegmentArgs &pa, const SegmentArgs &qa, cudaStream_t stream,
+                          Profiler &prof) {
   const int n = max(pa.n_query, qa.n_query);
-  if (n <= 0) return 0;
+  if (n <= 0) return;
+  prof.begin(FORMGPU_KG_SEGMENT);
   const dim3 g((n + 255) / 256, 2);
   segment_hist_kernel<<<g, 256, 0, stream>>>(pa, qa);
   segment_scan_kernel<<<2, 256, 0, stream>>>(pa, qa);
   segment_scatter_kernel<<<g, 256, 0, stream>>>(pa, qa);
-  return 3;
+  prof.end(FORMGPU_KG_SEGMENT, 3);
 }
 
 // ---------------------------------------------------------------------------
@@ -371,11 +372,12 @@ __global__ void __launch_bounds__(256) commit_kernel(CommitArgs pa, CommitArgs q
     reinterpret_cast<PointRec *>(a.store_dst)[pos] = reinterpret_cast<const PointRec *>(a.queries)[q];
 }
 
-int commit_launch(const CommitArgs &pa, const CommitArgs &qa, cudaStream_t stream) {
+void commit_launch(const CommitArgs &pa, const CommitArgs &qa, cudaStream_t stream, Profiler &prof) {
   const int n = max(pa.n_query, qa.n_query);
-  if (n <= 0) return 0;
+  if (n <= 0) return;
+  prof.begin(FORMGPU_KG_COMMIT);
   commit_kernel<<<dim3((n + 255) / 256, 2), 256, 0, stream>>>(pa, qa);
-  return 1;
+  prof.end(FORMGPU_KG_COMMIT, 1);
 }
 
 // ---------------------------------------------------------------------------
@@ -413,10 +415,11 @@ __global__ void __launch_bounds__(256) world_export_kernel(WorldExportArgs a) {
   }
 }
 
-int world_export_launch(const WorldExportArgs &a, cudaStream_t stream) {
-  if (a.n_total <= 0) return 0;
+void world_export_launch(const WorldExportArgs &a, cudaStream_t stream, Profiler &prof) {
+  if (a.n_total <= 0) return;
+  prof.begin(FORMGPU_KG_EXPORT);
   world_export_kernel<<<(a.n_total + 255) / 256, 256, 0, stream>>>(a);
-  return 1;
+  prof.end(FORMGPU_KG_EXPORT, 1);
 }
 
 } // namespace formgpu

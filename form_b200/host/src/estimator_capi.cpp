@@ -1,0 +1,127 @@
+// libformhost.so: form::Estimator and the trace replayer over the CUDA hot path.
+#include "form/capi_impl.hpp"
+
+using namespace form;
+using namespace form::capi;
+
+namespace {
+std::string g_error;
+std::shared_ptr<HotPath> make_gpu(const HotPathParams &hp, const formhost_est_params &p) {
+  const int window = p.hot.max_window_scans > 0 ? p.hot.max_window_scans : 64;
+  return std::make_shared<GpuHotPath>(hp, p.device, nullptr, window);
+}
+} // namespace
+
+extern "C" {
+
+void formhost_default_est_params(formhost_est_params *p) {
+  std::memset(p, 0, sizeof(*p));
+  formgpu_default_params(&p->hot);
+  p->new_pose_threshold = 1e-4;
+  p->keyscan_match_ratio = 0.1;
+  p->max_num_rematches = 30;
+  p->disable_smoothing = 0;
+  p->max_num_keyscans = 50;
+  p->max_num_recent_scans = 10;
+  p->max_steps_unused_keyscan = 10;
+  p->num_threads = 0;
+  p->device = 0;
+  p->record_trace = 0;
+}
+
+const char *formhost_last_error(void) { return g_error.c_str(); }
+
+void *formhost_est_create(const formhost_est_params *p) { return est_create(p, make_gpu, g_error); }
+void formhost_est_destroy(void *h) { delete static_cast<EstimatorHandle *>(h); }
+const char *formhost_est_error(void *h) { return static_cast<EstimatorHandle *>(h)->error.c_str(); }
+
+int formhost_est_register_scan(void *h, const formgpu_point4f *scan, size_t n,
+                               formgpu_planar_feat *planar, size_t planar_cap, size_t *n_planar,
+                               formgpu_point_feat *point, size_t point_cap, size_t *n_point) {
+  return est_register_scan(static_cast<EstimatorHandle *>(h), scan, n, planar, planar_cap, n_planar,
+                           point, point_cap, n_point);
+}
+void formhost_est_pose(void *h, formgpu_pose *out) { est_pose(static_cast<EstimatorHandle *>(h), out); }
+int formhost_est_window(void *h, formgpu_scan_pose *out, size_t cap, size_t *n) {
+  return est_window(static_cast<EstimatorHandle *>(h), out, cap, n);
+}
+void formhost_est_stats(void *h, uint64_t out[8]) { est_stats(static_cast<EstimatorHandle *>(h), out); }
+int formhost_est_map(void *h, formgpu_planar_feat *planar, size_t planar_cap, size_t *n_planar,
+                     formgpu_point_feat *point, size_t point_cap, size_t *n_point) {
+  return est_map(static_cast<EstimatorHandle *>(h), planar, planar_cap, n_planar, point, point_cap,
+                 n_point);
+}
+/// The context behind the estimator (profiling, launch counts).
+void *formhost_est_ctx(void *h) {
+  auto *g = dynamic_cast<GpuHotPath *>(static_cast<EstimatorHandle *>(h)->backend.get());
+  return g ? g->ctx() : nullptr;
+}
+/// Borrowed pointer to the recorded trace (valid while the estimator lives).
+const void *formhost_est_trace(void *h) { return &static_cast<EstimatorHandle *>(h)->trace; }
+size_t formhost_trace_num_scans(const void *t) { return static_cast<const Trace *>(t)->num_scans(); }
+size_t formhost_trace_num_ops(const void *t) { return static_cast<const Trace *>(t)->ops.size(); }
+
+/// A fresh CUDA context that replays a recorded trace.  `stream` may be a
+/// cudaStream_t the caller times with its own events (NULL = private stream).
+void *formhost_replay_create(const void *trace, const formhost_est_params *p, void *stream) {
+  try {
+    auto r = std::make_unique<ReplayHandle>();
+    r->trace = static_cast<const Trace *>(trace);
+    const Estimator::Params ep = to_estimator_params(*p);
+    const int window = p->hot.max_window_scans > 0 ? p->hot.max_window_scans : 64;
+    r->backend = std::make_shared<GpuHotPath>(Estimator::hotpath_params(ep), p->device, stream, window);
+    r->points_per_scan = (size_t)p->hot.num_rows * p->hot.num_columns;
+    return r.release();
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return nullptr;
+  }
+}
+void formhost_replay_destroy(void *r) { delete static_cast<ReplayHandle *>(r); }
+void *formhost_replay_ctx(void *r) {
+  return static_cast<GpuHotPath *>(static_cast<ReplayHandle *>(r)->backend.get())->ctx();
+}
+
+/// Replay with HOST scans: every EXTRACT copies the scan to the device and the
+/// keypoints back, as Estimator::register_scan does.  Returns seconds, < 0 on error.
+double formhost_replay_run_host(void *r, size_t first, size_t last,
+                                const formgpu_point4f *const *scans) {
+  try {
+    return replay_run_host(static_cast<ReplayHandle *>(r), first, last, scans);
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return -1.0;
+  }
+}
+
+/// Replay with scans already resident in DEVICE memory (scans_dev[s] = device
+/// pointer); keypoints stay on the device.  Returns seconds, < 0 on error.
+double formhost_replay_run_device(void *rv, size_t first, size_t last,
+                                  const formgpu_point4f *const *scans_dev) {
+  auto *r = static_cast<ReplayHandle *>(rv);
+  auto *gpu = static_cast<GpuHotPath *>(r->backend.get());
+  try {
+    const auto t0 = std::chrono::steady_clock::now();
+    replay(*r->trace, *r->backend, first, last,
+           [&](uint64_t scan_idx, size_t &np, size_t &nq) {
+             gpu->extract_device(scans_dev[scan_idx], r->points_per_scan, scan_idx, np, nq);
+           },
+           r->points_per_scan, r->stats);
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return -1.0;
+  }
+}
+
+void formhost_replay_stats(void *r, uint64_t out[20], double *checksum) {
+  replay_stats(static_cast<ReplayHandle *>(r), out, checksum);
+}
+void formhost_replay_reset_stats(void *r) {
+  auto *h = static_cast<ReplayHandle *>(r);
+  auto table = std::move(h->stats.table);
+  h->stats = ReplayStats();
+  h->stats.table = std::move(table);
+}
+
+} // extern "C"

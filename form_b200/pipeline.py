@@ -1,0 +1,184 @@
+"""form::Estimator (C++ host facade over the CUDA hot path) and the trace
+replayer, as Python handles.  ``FORM`` mirrors the evalio pipeline class of the
+reference's python/bindings.cpp."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+
+class EstimatorBase:
+    """Shared wrapper over the C API generated from form/capi_impl.hpp."""
+
+    _prefix = "formhost_"
+
+    def _lib(self):
+        return _capi.host_lib()
+
+    def _fn(self, name):
+        return getattr(self._lib(), self._prefix + name)
+
+    def _last_error(self) -> str:
+        return (self._lib().formhost_last_error() or b"").decode()
+
+    def __init__(self, params: _capi.EstParams):
+        self.params = params
+        self.rows, self.cols = params.hot.num_rows, params.hot.num_columns
+        self._h = self._fn("est_create")(C.byref(params))
+        if not self._h:
+            raise RuntimeError(f"{self._prefix}est_create failed: {self._last_error()}")
+        cap = self.rows * self.cols
+        self._planar = np.zeros(cap, dtype=_capi.PLANAR_FEAT)
+        self._point = np.zeros(cap, dtype=_capi.POINT_FEAT)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._fn("est_destroy")(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def register_scan(self, scan: np.ndarray):
+        """Estimator::register_scan: returns (planar, point) keypoints of the scan."""
+        a, b = C.c_size_t(), C.c_size_t()
+        rc = self._fn("est_register_scan")(self._h, _capi.ptr(scan), scan.shape[0],
+                                           _capi.ptr(self._planar), self._planar.shape[0], C.byref(a),
+                                           _capi.ptr(self._point), self._point.shape[0], C.byref(b))
+        if rc != 0:
+            raise RuntimeError(f"register_scan failed (rc={rc})")
+        return self._planar[: a.value].copy(), self._point[: b.value].copy()
+
+    def pose(self) -> np.ndarray:
+        """Estimator::current_lidar_estimate as a POSE record."""
+        out = np.zeros(1, dtype=_capi.POSE)
+        self._fn("est_pose")(self._h, _capi.ptr(out))
+        return out[0]
+
+    def window(self) -> np.ndarray:
+        out = np.zeros(256, dtype=_capi.SCAN_POSE)
+        n = C.c_size_t()
+        rc = self._fn("est_window")(self._h, _capi.ptr(out), out.shape[0], C.byref(n))
+        assert rc == 0
+        return out[: n.value].copy()
+
+    def stats(self) -> dict:
+        out = np.zeros(8, np.uint64)
+        self._fn("est_stats")(self._h, _capi.ptr(out))
+        names = ("optimize_calls", "lm_iterations", "linearize_calls", "error_calls",
+                 "linearized_pairs", "error_pairs", "icp_iterations", "window_size")
+        return {k: int(v) for k, v in zip(names, out)}
+
+    def map(self):
+        W = max(self.params.hot.max_window_scans, 64)
+        pl = np.zeros(W * self.rows * 64, dtype=_capi.PLANAR_FEAT)
+        pt = np.zeros(W * self.rows * 64, dtype=_capi.POINT_FEAT)
+        a, b = C.c_size_t(), C.c_size_t()
+        rc = self._fn("est_map")(self._h, _capi.ptr(pl), pl.shape[0], C.byref(a), _capi.ptr(pt),
+                                 pt.shape[0], C.byref(b))
+        if rc != 0:
+            raise RuntimeError(f"map failed (rc={rc})")
+        return pl[: a.value].copy(), pt[: b.value].copy()
+
+    def trace(self):
+        return self._fn("est_trace")(self._h)
+
+    def trace_num_scans(self) -> int:
+        return int(self._fn("trace_num_scans")(self.trace()))
+
+
+class Estimator(EstimatorBase):
+    """form::Estimator on the CUDA hot path (libformhost.so + libformgpu.so)."""
+
+    def ctx(self):
+        return self._lib().formhost_est_ctx(self._h)
+
+
+def _scan_ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))(*ptrs)
+    return arr
+
+
+class ReplayBase:
+    _prefix = "formhost_"
+
+    def _lib(self):
+        return _capi.host_lib()
+
+    def _fn(self, name):
+        return getattr(self._lib(), self._prefix + name)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._fn("replay_destroy")(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_host(self, first: int, last: int, scans) -> float:
+        """Replay scans [first, last) with host scans (list of POINT4F arrays)."""
+        arr = _scan_ptr_array([s.ctypes.data for s in scans])
+        t = self._fn("replay_run_host")(self._h, first, last, arr)
+        if t < 0:
+            raise RuntimeError("replay failed")
+        return t
+
+    def stats(self) -> dict:
+        out = np.zeros(20, np.uint64)
+        cs = C.c_double()
+        self._fn("replay_stats")(self._h, _capi.ptr(out), C.byref(cs))
+        d = {k: int(v) for k, v in zip(_capi.REPLAY_STAT_NAMES, out)}
+        d["checksum"] = cs.value
+        return d
+
+    def reset_stats(self):
+        self._fn("replay_reset_stats")(self._h)
+
+
+class Replay(ReplayBase):
+    """Replays a recorded hot-path trace on a fresh CUDA context."""
+
+    def __init__(self, trace, params: _capi.EstParams, stream: int | None = None):
+        self._h = self._lib().formhost_replay_create(trace, C.byref(params), C.c_void_p(stream or 0))
+        if not self._h:
+            raise RuntimeError("formhost_replay_create failed: " +
+                               (self._lib().formhost_last_error() or b"").decode())
+
+    def ctx(self):
+        return self._lib().formhost_replay_ctx(self._h)
+
+    def run_device(self, first: int, last: int, dev_ptrs) -> float:
+        arr = _scan_ptr_array(list(dev_ptrs))
+        t = self._lib().formhost_replay_run_device(self._h, first, last, arr)
+        if t < 0:
+            raise RuntimeError("replay failed: " + (self._lib().formhost_last_error() or b"").decode())
+        return t
+
+    def profile_enable(self, on=True):
+        _capi.gpu_lib().formgpu_profile_enable(self.ctx(), int(on))
+
+    def profile_read(self):
+        ms = np.zeros(_capi.KG_COUNT)
+        launches = np.zeros(_capi.KG_COUNT, np.uint64)
+        _capi.gpu_lib().formgpu_profile_read(self.ctx(), _capi.ptr(ms), _capi.ptr(launches))
+        return {name: dict(ms=float(ms[i]), launches=int(launches[i]))
+                for i, name in enumerate(_capi.KG_NAMES)}
+
+    def launch_count(self) -> int:
+        return int(_capi.gpu_lib().formgpu_launch_count(self.ctx()))

@@ -222,21 +222,29 @@ int formgpu_error(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
 
 /* ---- instrumentation ---------------------------------------------------- */
 
-#define FORMGPU_STAGE_EXTRACT 0
-#define FORMGPU_STAGE_MAP 1
-#define FORMGPU_STAGE_ASSOC 2
-#define FORMGPU_STAGE_LINEARIZE 3
-#define FORMGPU_STAGE_ERROR 4
-#define FORMGPU_STAGE_COMMIT 5
-#define FORMGPU_NUM_STAGES 6
+/* Kernel groups of the hot path (one or a few kernels each). */
+#define FORMGPU_KG_EXTRACT_SELECT 0  /* masks, curvature, sector sort, greedy picks */
+#define FORMGPU_KG_EXTRACT_NORMALS 1 /* closest-row search + PCA normals            */
+#define FORMGPU_KG_EXTRACT_PACK 2    /* keypoint compaction                         */
+#define FORMGPU_KG_MAP_BUILD 3       /* transform + hash insert + alloc + scatter   */
+#define FORMGPU_KG_ASSOC_NN 4        /* warp-cooperative voxel-hash NN              */
+#define FORMGPU_KG_SEGMENT 5         /* correspondence segment (hist, scan, scatter)*/
+#define FORMGPU_KG_LIN_CHUNK 6       /* streaming residual/Jacobian reduction       */
+#define FORMGPU_KG_LIN_FINALIZE 7    /* per-pair 13x13 expansion                    */
+#define FORMGPU_KG_ERR_CHUNK 8       /* streaming residual-only reduction           */
+#define FORMGPU_KG_ERR_FINALIZE 9
+#define FORMGPU_KG_COMMIT 10         /* novel keypoint append                       */
+#define FORMGPU_KG_EXPORT 11         /* world-frame keypoint export                 */
+#define FORMGPU_KG_COUNT 12
 
-/* When enabled every stage is bracketed by CUDA events on the context's
- * stream; formgpu_profile_read synchronises and returns accumulated device
- * milliseconds, call counts and kernel-launch counts per stage, then resets. */
+/* When enabled every kernel group is bracketed by CUDA events on the context's
+ * stream (the calls then synchronise once more at their end).
+ * formgpu_profile_read returns the accumulated device milliseconds and launch
+ * counts per group since the last read, then resets them.  Launches are counted
+ * whether or not timing is enabled. */
 int formgpu_profile_enable(formgpu_ctx *ctx, int on);
-int formgpu_profile_read(formgpu_ctx *ctx, double ms[FORMGPU_NUM_STAGES],
-                         uint64_t calls[FORMGPU_NUM_STAGES],
-                         uint64_t launches[FORMGPU_NUM_STAGES]);
+int formgpu_profile_read(formgpu_ctx *ctx, double ms[FORMGPU_KG_COUNT],
+                         uint64_t launches[FORMGPU_KG_COUNT]);
 
 /* Total kernels launched by this context since creation. */
 uint64_t formgpu_launch_count(const formgpu_ctx *ctx);

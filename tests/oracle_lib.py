@@ -160,3 +160,47 @@ class Oracle:
         if n.value:
             lib().oracle_get_keypoints(self._h, type_, scan, _capi.ptr(out), n.value, C.byref(n))
         return out
+
+
+# ---- the shared host pipeline over the oracle (oracle_pipeline_capi.cpp) ----
+from form_b200 import pipeline as _pipeline  # noqa: E402
+
+_pipe_ready = False
+
+
+def _pipe_lib():
+    global _pipe_ready
+    l = lib()
+    if not _pipe_ready:
+        for name, (res, args) in _capi.estimator_symbols("oracle_").items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        l.oracle_est_last_error.restype = C.c_char_p
+        l.oracle_replay_create.restype = _vp
+        l.oracle_replay_create.argtypes = [_vp, C.POINTER(_capi.EstParams)]
+        _pipe_ready = True
+    return l
+
+
+class OracleEstimator(_pipeline.EstimatorBase):
+    """form::Estimator host logic running over the CPU oracle."""
+
+    _prefix = "oracle_"
+
+    def _lib(self):
+        return _pipe_lib()
+
+    def _last_error(self):
+        return (self._lib().oracle_est_last_error() or b"").decode()
+
+
+class OracleReplay(_pipeline.ReplayBase):
+    """Replays a recorded hot-path trace on the CPU oracle (cpu_baseline leg)."""
+
+    _prefix = "oracle_"
+
+    def _lib(self):
+        return _pipe_lib()
+
+    def __init__(self, trace, params: _capi.EstParams):
+        self._h = self._lib().oracle_replay_create(trace, C.byref(params))
