@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py - FORM per-scan hot path (feature + association + linearisation) on B200.
+
+Contract (see the round brief): `python bench.py --gpus N --steps K --warmup W`
+prints ONE JSON line on rank 0.  A step = the hot-path work of one scan
+(extraction, reparative map rebuild, every ICP association, every LM linearisation
+/ error evaluation, novel-keypoint commit), replayed from a trace that one untimed
+run of the real pipeline (form::Estimator with the host smoother) records; the
+host smoother itself is therefore not inside the timed region.
+
+  value     scans/s with the scans already resident in HBM (formgpu_extract_device),
+            whole job over all ranks (independent sequence per rank, weak scaling)
+  e2e       same, through the host-buffer C-ABI (pinned scan -> H2D, keypoints and
+            blocks -> D2H inside the timed region)
+  roofline  dominant kernel group: algorithmic bytes / CUDA-event time vs measured HBM
+  cpu_baseline  the same trace replayed on the CPU oracle (kind "port") on all host
+            cores, bounded sample, rank 0 / N=1 only
+
+`--impl reference` times the CPU oracle pipeline's hot-path calls on the host
+cores (the reference itself cannot be built here: no Eigen/GTSAM/TBB).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+SENSOR_OF_WORKLOAD = {
+    "os0-128": "configs[1]: synthetic OS0-128 (128x1024) sequence, full fixed-lag window",
+    "os1-64": "configs[0]/[3]: synthetic OS1-64 (64x1024) sequence",
+    "vlp-16": "configs[2]: sparse VLP-16 (16x1800) sequence",
+    "stress-128x2048": "configs[4]: dense 128x2048 stress scans",
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, smax = [], set(), None
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    c = [x.strip() for x in line.split(",")]
+                    if len(c) < 9:
+                        continue
+                    try:
+                        sm.append(float(c[1]))
+                        smax = float(c[2])
+                    except ValueError:
+                        continue
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                        "sw_power_cap"), c[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = smax
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def algorithmic_bytes(stats: dict, group: str, n_points: int) -> float:
+    """Compulsory HBM bytes of one kernel group over the replayed region:
+    every input read once, every output written once; re-reads that hit L2/smem are
+    not counted."""
+    s = stats
+    if group in ("lin_chunk", "lin_finalize"):
+        # lossless f32 SoA correspondences: 36 B planar, 24 B point (+ 728 B block per pair)
+        return 36.0 * s["lin_planar"] + 24.0 * s["lin_point"] + 728.0 * s["lin_pairs"]
+    if group in ("err_chunk", "err_finalize"):
+        return 36.0 * s["err_planar"] + 24.0 * s["err_point"] + 8.0 * s["err_pairs"]
+    if group in ("extract_select", "extract_normals", "extract_pack"):
+        # scan read (16 B/pt) + keypoint records written (32 B planar, 16 B point)
+        return 16.0 * s["points"] + 32.0 * s["planar_kp"] + 16.0 * s["point_kp"]
+    if group == "assoc_nn":
+        # query record + 27 hash slots (16 B) + one 32 B candidate sector per probed voxel
+        # (lower bound) + 16 B match record
+        q = s["assoc_queries"]
+        return q * (32.0 + 27 * 16.0 + 32.0 + 16.0)
+    if group == "segment":
+        return s["assoc_queries"] * (16.0 + 36.0 + 32.0)
+    if group == "map_build":
+        return s["map_points_rebuilt"] * (32.0 + 2 * 32.0 + 16.0)
+    return 0.0
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    from form_b200 import _capi, synth
+    from form_b200.pipeline import Estimator, Replay
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rows, cols = synth.shape(args.sensor)
+    n_points = rows * cols
+    W, K = args.warmup, args.steps
+    S = W + K
+    seq = rank  # independent sequence per GPU (BASELINE.json configs[3]): weak scaling
+    p = _capi.default_est_params(rows, cols, record_trace=1, device=local_rank)
+
+    # ---- synthetic scans, pinned host copies and device-resident copies ----
+    t0 = time.time()
+    scans_np = [synth.scan(args.sensor, seq, k) for k in range(S)]
+    pinned = [torch.from_numpy(s.view(np.uint8)).pin_memory() for s in scans_np]
+    pinned_np = [t.numpy().view(_capi.POINT4F) for t in pinned]
+    dev = [t.cuda(non_blocking=True) for t in pinned]
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+
+    # ---- untimed recording pass: the real pipeline (host smoother in the loop) ----
+    t0 = time.time()
+    est = Estimator(p)
+    for s in scans_np:
+        est.register_scan(s)
+    t_record = time.time() - t0
+    est_stats = est.stats()
+    g0, gk = synth.gt_pose(seq, 0), synth.gt_pose(seq, S - 1)
+    rel_gt = g0["R"].reshape(3, 3).T @ (gk["t"] - g0["t"])
+    final_err = float(np.linalg.norm(est.pose()["t"] - rel_gt))
+    trace = est.trace()
+
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def timed_replay(rep, run, first, last):
+        """Per-step CUDA-event timing on the launching stream; L2 flushed between steps
+        outside the timed intervals.  Returns (device ms list, host seconds)."""
+        ms, host_s = [], 0.0
+        for s in range(first, last):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            host_s += run(s, s + 1)
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        return ms, host_s
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: scans resident in HBM ----
+    rep_d = Replay(trace, p, stream=stream)
+    dev_ptrs = [d.data_ptr() for d in dev]
+    rep_d.run_device(0, W, dev_ptrs)  # warm-up: fills the fixed-lag window
+    rep_d.reset_stats()
+    launches0 = rep_d.launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ms_d, _ = timed_replay(rep_d, lambda a, b: rep_d.run_device(a, b, dev_ptrs), W, S)
+    barrier()
+    clocks = sampler.stop()
+    stats_d = rep_d.stats()
+    gpu_launches = rep_d.launch_count() - launches0
+    t_value = sum(ms_d) / 1e3
+
+    # ---- e2e: pinned host scans through the host-buffer C-ABI ----
+    rep_h = Replay(trace, p, stream=stream)
+    rep_h.run_host(0, W, pinned_np)
+    rep_h.reset_stats()
+    barrier()
+    ms_h, _ = timed_replay(rep_h, lambda a, b: rep_h.run_host(a, b, pinned_np), W, S)
+    barrier()
+    stats_h = rep_h.stats()
+    t_e2e = sum(ms_h) / 1e3
+
+    # ---- per-kernel-group CUDA-event timing over the same region (roofline) ----
+    rep_p = Replay(trace, p, stream=stream)
+    rep_p.run_device(0, W, dev_ptrs)
+    rep_p.reset_stats()
+    rep_p.profile_read()
+    rep_p.profile_enable(True)
+    for s in range(W, S):
+        flush.zero_()
+        rep_p.run_device(s, s + 1, dev_ptrs)
+    prof = rep_p.profile_read()
+    rep_p.profile_enable(False)
+    stats_p = rep_p.stats()
+
+    # max over ranks, whole-job aggregate
+    if dist is not None:
+        t = torch.tensor([t_value, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_value, t_e2e = float(t[0]), float(t[1])
+    total_scans = world * K
+    value = total_scans / t_value
+    e2e_value = total_scans / t_e2e
+
+    result = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        kernel_ms = {g: v["ms"] for g, v in prof.items() if v["launches"]}
+        total_kernel_ms = sum(kernel_ms.values()) or 1.0
+        dom = max(kernel_ms, key=kernel_ms.get)
+        stats_p["map_points_rebuilt"] = 0
+        launches_dom = prof[dom]["launches"]
+        abytes = algorithmic_bytes(stats_p, dom, n_points)
+        achieved = abytes / (kernel_ms[dom] / 1e3) / 1e9 if kernel_ms[dom] > 0 else 0.0
+        # whole-step figure: SURVEY 8(d) B_scan with this implementation's record sizes
+        b_scan = (16.0 * stats_p["points"] + 32.0 * stats_p["planar_kp"] + 16.0 * stats_p["point_kp"]
+                  + stats_p["assoc_queries"] * (32.0 + 27 * 16.0 + 32.0 + 16.0)
+                  + 36.0 * (stats_p["lin_planar"] + stats_p["err_planar"])
+                  + 24.0 * (stats_p["lin_point"] + stats_p["err_point"])
+                  + 728.0 * stats_p["lin_pairs"] + 8.0 * stats_p["err_pairs"]
+                  + 32.0 * stats_p["novel_planar"] + 16.0 * stats_p["novel_point"])
+        roofline = {
+            "bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak,
+            "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": None,
+            "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": round(abytes / max(launches_dom, 1), 1),
+            "avg_launch_us": round(1e3 * kernel_ms[dom] / max(launches_dom, 1), 3),
+            "launches": launches_dom,
+            "kernel_share_of_gpu_time": round(kernel_ms[dom] / total_kernel_ms, 4),
+            "kernel_ms_per_step": {g: round(v / K, 5) for g, v in sorted(kernel_ms.items())},
+            "whole_step_algorithmic_GBps": round(b_scan / t_value / 1e9, 3),
+        }
+        h2d = 16.0 * n_points  # the scan (requests are < 1% of it)
+        d2h = (32.0 * stats_h["planar_kp"] + 16.0 * stats_h["point_kp"] + 728.0 * stats_h["lin_pairs"]
+               + 8.0 * stats_h["err_pairs"] + stats_h["assoc_calls"] * 4 * 4 * (p.hot.max_window_scans + 1)) / K
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_replay(trace, p, scans_np, W, S, args.cpu_sample)
+        result = {
+            "metric": "scans/sec (feature+assoc+linearize hot path)", "value": round(value, 3),
+            "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(1e3 * t_value / K, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 index arithmetic, f64 transforms/normal equations",
+            "data": "synthetic", "mpoints_per_s": round(value * n_points / 1e6, 3),
+            "config": {
+                "workload": SENSOR_OF_WORKLOAD[args.sensor], "sensor": args.sensor, "rows": rows,
+                "cols": cols, "scans_per_sequence": S, "sequences": world,
+                "step": "hot-path calls of one scan, replayed from the recorded pipeline trace",
+                "l2": "256 MiB buffer written between timed steps (outside the timed intervals)",
+                "icp_iterations_per_scan": round(est_stats["icp_iterations"] / S, 2),
+                "lm_iterations_per_scan": round(est_stats["lm_iterations"] / S, 2),
+                "window_size": est_stats["window_size"],
+                "pipeline_final_position_error_m": round(final_err, 4),
+                "assoc_calls_per_step": round(stats_d["assoc_calls"] / K, 2),
+                "linearize_calls_per_step": round(stats_d["lin_calls"] / K, 2),
+                "error_calls_per_step": round(stats_d["err_calls"] / K, 2),
+                "correspondences_linearized_per_step": round((stats_d["lin_planar"] + stats_d["lin_point"]) / K),
+                "keypoints_per_scan": round((stats_d["planar_kp"] + stats_d["point_kp"]) / K),
+                "parallelism": f"{world} independent sequence(s), one per GPU, no collective",
+                "recording_pass_s": round(t_record, 2), "scan_generation_s": round(t_gen, 2),
+            },
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 3), "unit": "scans/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": round(1e3 * t_e2e / K, 4)},
+            "gpu_launches": int(gpu_launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        if cpu:
+            result["config"]["speedup_value_vs_cpu"] = round(value / cpu["value"], 2)
+            result["config"]["speedup_e2e_vs_cpu"] = round(e2e_value / cpu["value"], 2)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+def cpu_baseline_replay(trace, p, scans_np, W, S, sample):
+    """Replay the recorded trace on the CPU oracle with all host cores: warm the window
+    untimed, then time a bounded sample of the measured region."""
+    import oracle_lib
+
+    cores = os.cpu_count() or 1
+    ro = oracle_lib.OracleReplay(trace, p)
+    ro.run_host(0, W, scans_np)
+    ro.reset_stats()
+    last = min(S, W + max(1, sample))
+    t = ro.run_host(W, last, scans_np)
+    n = last - W
+    return {"value": round(n / t, 4), "unit": "scans/s", "cores": cores, "kind": "port",
+            "sample": f"{n} scans of the measured region (scans {W}..{last - 1}) after an untimed "
+                      f"{W}-scan window warm-up; oracle/ C++17 restatement, -O3 no -march, "
+                      f"{cores} worker threads where the reference uses TBB",
+            "ms_per_step": round(1e3 * t / n, 3)}
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU path (oracle port: the reference cannot be built here)."""
+    if rank != 0:
+        return None
+    import oracle_lib
+    from form_b200 import _capi, synth
+
+    rows, cols = synth.shape(args.sensor)
+    W, K = args.warmup, args.steps
+    S = W + K
+    cores = os.cpu_count() or 1
+    p = _capi.default_est_params(rows, cols, record_trace=1)
+    scans_np = [synth.scan(args.sensor, 0, k) for k in range(S)]
+    # pipeline over the oracle records its own hot-path trace (no CUDA code on this path) ...
+    est = oracle_lib.OracleEstimator(p)
+    for s in scans_np:
+        est.register_scan(s)
+    # ... and the timed region replays the hot-path calls of scans W..S-1 on the oracle
+    ro = oracle_lib.OracleReplay(est.trace(), p)
+    ro.run_host(0, W, scans_np)
+    ro.reset_stats()
+    t = ro.run_host(W, S, scans_np)
+    value = K / t
+    n_points = rows * cols
+    cpu = {"value": round(value, 4), "unit": "scans/s", "cores": cores, "kind": "port",
+           "sample": f"{K} scans (scans {W}..{S - 1}) after an untimed {W}-scan warm-up"}
+    return {
+        "impl": "reference", "metric": "scans/sec (feature+assoc+linearize hot path)",
+        "value": round(value, 4), "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(1e3 * t / K, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 index arithmetic, f64 transforms/normal equations",
+        "data": "synthetic", "mpoints_per_s": round(value * n_points / 1e6, 4),
+        "config": {"workload": SENSOR_OF_WORKLOAD[args.sensor], "sensor": args.sensor, "rows": rows,
+                   "cols": cols, "scans_per_sequence": S,
+                   "note": "FORM cannot be compiled here (Eigen3/GTSAM/oneTBB/tsl absent); this arm "
+                           "is the oracle/ C++17 restatement of its hot path on the host cores"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": round(value, 4), "unit": "scans/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=40)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sensor", default="os0-128", choices=sorted(SENSOR_OF_WORKLOAD))
+    ap.add_argument("--cpu-sample", type=int, default=30, help="scans timed for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import __graft_entry__ as g
+
+    g.build(only_if_missing=True)
+    if args.impl == "reference":
+        res = run_reference(args, rank, world)
+    else:
+        res = run_ours(args, rank, world, local_rank)
+    if rank == 0 and res is not None:
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -176,6 +176,13 @@ FORMHOST_SYMBOLS = {
     "formhost_synth_shape": (_sz, [_i, C.POINTER(_i), C.POINTER(_i)]),
     "formhost_synth_scan": (_i, [_i, _u64, _u64, _vp, _i]),
     "formhost_synth_gt_pose": (None, [_u64, _u64, _vp]),
+    "formhost_pose_expmap": (None, [_vp, _vp]),
+    "formhost_pose_logmap": (None, [_vp, _vp]),
+    "formhost_pose_logmap_derivative": (None, [_vp, _vp]),
+    "formhost_pose_compose": (None, [_vp, _vp, _vp]),
+    "formhost_pose_inverse": (None, [_vp, _vp]),
+    "formhost_pose_rzryrx": (None, [_d, _d, _d, _vp, _vp]),
+    "formhost_pose_normalized": (None, [_vp, _vp]),
     "formhost_default_est_params": (None, [_pest]),
     "formhost_last_error": (C.c_char_p, []),
     "formhost_est_error": (C.c_char_p, [_vp]),

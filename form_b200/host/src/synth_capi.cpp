@@ -47,3 +47,33 @@ void formhost_synth_gt_pose(uint64_t sequence_id, uint64_t k, formgpu_pose *out)
 }
 
 } // extern "C"
+
+// ---- small hooks so the Python tests can exercise the host-side SE(3) math ----
+extern "C" {
+void formhost_pose_expmap(const double xi[6], formgpu_pose *out) {
+  const form::Pose3 T = form::Pose3::Expmap({xi[0], xi[1], xi[2], xi[3], xi[4], xi[5]});
+  for (int i = 0; i < 9; ++i) out->R[i] = T.R[i];
+  for (int i = 0; i < 3; ++i) out->t[i] = T.t[i];
+}
+void formhost_pose_logmap(const formgpu_pose *p, double xi[6]) {
+  const form::Vec6 v = form::Pose3::Logmap(*reinterpret_cast<const form::Pose3 *>(p));
+  for (int i = 0; i < 6; ++i) xi[i] = v[i];
+}
+void formhost_pose_logmap_derivative(const formgpu_pose *p, double J[36]) {
+  const form::Mat6 M = form::Pose3::LogmapDerivative(*reinterpret_cast<const form::Pose3 *>(p));
+  for (int i = 0; i < 36; ++i) J[i] = M[i];
+}
+void formhost_pose_compose(const formgpu_pose *a, const formgpu_pose *b, formgpu_pose *out) {
+  const form::Pose3 T = *reinterpret_cast<const form::Pose3 *>(a) * *reinterpret_cast<const form::Pose3 *>(b);
+  *reinterpret_cast<form::Pose3 *>(out) = T;
+}
+void formhost_pose_inverse(const formgpu_pose *a, formgpu_pose *out) {
+  *reinterpret_cast<form::Pose3 *>(out) = reinterpret_cast<const form::Pose3 *>(a)->inverse();
+}
+void formhost_pose_rzryrx(double rx, double ry, double rz, const double t[3], formgpu_pose *out) {
+  *reinterpret_cast<form::Pose3 *>(out) = form::Pose3::RzRyRx(rx, ry, rz, {t[0], t[1], t[2]});
+}
+void formhost_pose_normalized(const formgpu_pose *a, formgpu_pose *out) {
+  *reinterpret_cast<form::Pose3 *>(out) = reinterpret_cast<const form::Pose3 *>(a)->normalized();
+}
+}

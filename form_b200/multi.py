@@ -1,0 +1,50 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed).
+
+The hot path partitions by independent sequences: rank r runs sequence r on its own GPU
+and no data-path collective exists (mode 1).  The only cross-rank traffic is
+timing (max over ranks).  For the optional point-sharded mode of very dense scans (mode
+2) every rank linearises its shard of the correspondences and the tiny per-pair
+normal-equation blocks are summed: one all-reduce of 91*P doubles (error: P doubles)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def sequence_of_rank(rank: int, world: int, base_sequence: int = 0) -> int:
+    """Sequence id processed by a rank (weak scaling: one sequence per GPU)."""
+    if not 0 <= rank < world:
+        raise ValueError("rank outside the world")
+    return base_sequence + rank
+
+
+def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous shard [lo, hi) of n keypoints / correspondences for a rank."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def max_over_ranks(seconds: float, device=None) -> float:
+    """Timing rule: the job takes as long as its slowest rank."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(seconds)
+    t = torch.tensor([seconds], dtype=torch.float64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def allreduce_blocks(blocks: np.ndarray, device=None) -> np.ndarray:
+    """Sum per-pair blocks (P x 91, or P errors) over the ranks of a point-sharded job.
+    The blocks are additive in the correspondences (A^T A), so the sum of the shard blocks
+    is the block of the whole pair."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return blocks
+    t = torch.from_numpy(np.ascontiguousarray(blocks, dtype=np.float64))
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()

@@ -1,0 +1,56 @@
+"""Host logic (form::Estimator, smoother, key-scan bookkeeping) exercised on CPU over the
+oracle backend: tracks the synthetic ground truth, keeps a bounded window, is deterministic
+and independent of the oracle's thread count."""
+import numpy as np
+
+import oracle_lib
+from form_b200 import _capi, synth
+
+
+def _run(n, threads, **over):
+    rows, cols = synth.shape("vlp-16")
+    p = _capi.default_est_params(rows, cols, num_threads=threads, record_trace=1, **over)
+    est = oracle_lib.OracleEstimator(p)
+    poses = []
+    for k in range(n):
+        est.register_scan(synth.scan("vlp-16", 0, k))
+        poses.append(est.pose().copy())
+    return est, poses
+
+
+def test_tracks_ground_truth_and_bounds_window():
+    n = 24
+    est, poses = _run(n, threads=0)
+    g0 = synth.gt_pose(0, 0)
+    for k in (5, 12, n - 1):
+        gk = synth.gt_pose(0, k)
+        rel = g0["R"].reshape(3, 3).T @ (gk["t"] - g0["t"])
+        assert np.linalg.norm(poses[k]["t"] - rel) < 0.05, k
+    st = est.stats()
+    # 10 recent scans + the key scans that survived; never more than 1 + 10 + 50
+    assert 11 <= st["window_size"] <= 61
+    w = est.window()
+    assert w["scan"][-1] == n - 1 and np.all(np.diff(w["scan"].astype(np.int64)) > 0)
+    assert st["icp_iterations"] >= n and st["lm_iterations"] > 0
+    assert est.trace_num_scans() == n
+    pl, pt = est.map()
+    assert len(pl) > 1000 and len(pt) > 100
+
+
+def test_deterministic_and_thread_independent():
+    _, a = _run(8, threads=1)
+    _, b = _run(8, threads=4)
+    _, c = _run(8, threads=4)
+    for x, y, z in zip(a, b, c):
+        assert y.tobytes() == z.tobytes()
+        # parallel linearisation only changes which thread handles a pair, not the sums
+        assert x.tobytes() == y.tobytes()
+
+
+def test_ablations_run():
+    est, poses = _run(6, threads=0, point_feats_per_sector=0)
+    assert est.stats()["window_size"] == 6
+    est, poses = _run(6, threads=0, disable_smoothing=1)
+    g0, gk = synth.gt_pose(0, 0), synth.gt_pose(0, 5)
+    rel = g0["R"].reshape(3, 3).T @ (gk["t"] - g0["t"])
+    assert np.linalg.norm(poses[5]["t"] - rel) < 0.05
