@@ -281,7 +281,7 @@ def run_ours(args, rank, world, local_rank):
                + 8.0 * stats_h["err_pairs"] + stats_h["assoc_calls"] * 4 * 4 * (p.hot.max_window_scans + 1)) / K
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline_replay(trace, p, scans_np, W, S, args.cpu_sample)
+            cpu = cpu_baseline_replay(rows, cols, scans_np, W, S, args.cpu_sample)
         result = {
             "metric": "scans/sec (feature+assoc+linearize hot path)", "value": round(value, 3),
             "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -295,6 +295,7 @@ def run_ours(args, rank, world, local_rank):
                 "l2": "256 MiB buffer written between timed steps (outside the timed intervals)",
                 "icp_iterations_per_scan": round(est_stats["icp_iterations"] / S, 2),
                 "lm_iterations_per_scan": round(est_stats["lm_iterations"] / S, 2),
+                "lm_schedule": "fused: trial steps are linearised (error = f/2), accepted blocks reused",
                 "window_size": est_stats["window_size"],
                 "pipeline_final_position_error_m": round(final_err, 4),
                 "assoc_calls_per_step": round(stats_d["assoc_calls"] / K, 2),
@@ -321,16 +322,23 @@ def run_ours(args, rank, world, local_rank):
     return result
 
 
-def cpu_baseline_replay(trace, p, scans_np, W, S, sample):
-    """Replay the recorded trace on the CPU oracle with all host cores: warm the window
-    untimed, then time a bounded sample of the measured region."""
+def cpu_baseline_replay(rows, cols, scans_np, W, S, sample):
+    """CPU baseline on all host cores: the pipeline over the oracle records ITS OWN hot-path
+    trace with the reference's (GTSAM) LM call schedule - one linearisation per LM iteration
+    plus one error evaluation per trial step - then the hot-path calls of a bounded sample
+    of the measured region are replayed and timed after an untimed window warm-up."""
     import oracle_lib
+    from form_b200 import _capi
 
     cores = os.cpu_count() or 1
-    ro = oracle_lib.OracleReplay(trace, p)
+    last = min(S, W + max(1, sample))
+    p = _capi.default_est_params(rows, cols, record_trace=1, gtsam_lm_schedule=1)
+    est = oracle_lib.OracleEstimator(p)
+    for s in scans_np[:last]:
+        est.register_scan(s)
+    ro = oracle_lib.OracleReplay(est.trace(), p)
     ro.run_host(0, W, scans_np)
     ro.reset_stats()
-    last = min(S, W + max(1, sample))
     t = ro.run_host(W, last, scans_np)
     n = last - W
     return {"value": round(n / t, 4), "unit": "scans/s", "cores": cores, "kind": "port",
@@ -351,9 +359,10 @@ def run_reference(args, rank, world):
     W, K = args.warmup, args.steps
     S = W + K
     cores = os.cpu_count() or 1
-    p = _capi.default_est_params(rows, cols, record_trace=1)
+    p = _capi.default_est_params(rows, cols, record_trace=1, gtsam_lm_schedule=1)
     scans_np = [synth.scan(args.sensor, 0, k) for k in range(S)]
-    # pipeline over the oracle records its own hot-path trace (no CUDA code on this path) ...
+    # pipeline over the oracle records its own hot-path trace (no CUDA code on this path,
+    # the reference's GTSAM call schedule) ...
     est = oracle_lib.OracleEstimator(p)
     for s in scans_np:
         est.register_scan(s)

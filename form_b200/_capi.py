@@ -76,6 +76,8 @@ class EstParams(C.Structure):
         ("num_threads", C.c_int32),
         ("device", C.c_int32),
         ("record_trace", C.c_int32),
+        ("gtsam_lm_schedule", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -86,7 +88,8 @@ def default_est_params(rows: int = 64, cols: int = 1024, **overrides) -> EstPara
     hot = default_params(rows, cols, **{k: v for k, v in overrides.items() if k in hot_keys})
     p = EstParams(hot=hot, new_pose_threshold=1e-4, keyscan_match_ratio=0.1, max_num_rematches=30,
                   disable_smoothing=0, max_num_keyscans=50, max_num_recent_scans=10,
-                  max_steps_unused_keyscan=10, num_threads=0, device=0, record_trace=0)
+                  max_steps_unused_keyscan=10, num_threads=0, device=0, record_trace=0,
+                  gtsam_lm_schedule=0, reserved=0)
     for k, v in overrides.items():
         if k in hot_keys:
             continue

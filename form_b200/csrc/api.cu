@@ -38,16 +38,39 @@ int ensure_out(formgpu_ctx *ctx, size_t pairs) {
   if (pairs <= ctx->out_cap) return FORMGPU_OK;
   FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
-  if (ctx->d_out) cudaFree(ctx->d_out);
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
   ctx->h_out = nullptr;
-  ctx->d_out = nullptr;
+  ctx->d_counters = nullptr;
   const size_t cap = next_pow2(pairs);
+  // results are written by the kernels straight into this mapped pinned buffer
   FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_out), cap * 91 * sizeof(double),
-                                  cudaHostAllocDefault));
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_out, cap * 91));
+                                  cudaHostAllocMapped));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_counters, cap + 8));
+  FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, (cap + 8) * sizeof(unsigned), ctx->stream));
+  FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->counter_cap = cap;
   ctx->out_cap = cap;
   ctx->h_out_bytes = cap * 91 * sizeof(double);
   return FORMGPU_OK;
+}
+
+int wait_flag(formgpu_ctx *ctx, int which, unsigned long long seq) {
+  volatile unsigned long long *f = ctx->h_flags + which;
+  for (unsigned spins = 0;; ++spins) {
+    if (*f == seq) return FORMGPU_OK;
+    if ((spins & 0xfff) == 0xfff) {
+      const cudaError_t e = cudaStreamQuery(ctx->stream);
+      if (e == cudaSuccess) {
+        if (*f == seq) return FORMGPU_OK;
+        return fail(ctx, FORMGPU_ERR_STATE, "kernel finished without publishing its results");
+      }
+      if (e != cudaErrorNotReady)
+        return fail(ctx, FORMGPU_ERR_CUDA, std::string("kernel failed: ") + cudaGetErrorString(e));
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
 }
 
 } // namespace formgpu
@@ -127,6 +150,9 @@ static int create_impl(formgpu_ctx *ctx) {
     ctx->own_stream = true;
   }
   ctx->prof.stream = ctx->stream;
+  FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(const_cast<unsigned long long **>(&ctx->h_flags)),
+                                  8 * sizeof(unsigned long long), cudaHostAllocMapped));
+  for (int i = 0; i < 8; ++i) ctx->h_flags[i] = 0;
 
   const size_t B = ctx->B, R = ctx->rows, W = ctx->W;
   // stage 1
@@ -146,11 +172,11 @@ static int create_impl(formgpu_ctx *ctx) {
   ctx->d_cur_point = ctx->d_cur_point_buf[0];
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_cur_counts, B * 2 + 8));
   FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_counts),
-                                  (B * 2 + 8) * sizeof(int), cudaHostAllocDefault));
+                                  (B * 2 + 8) * sizeof(int), cudaHostAllocMapped));
   FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_planar),
-                                  ctx->kp_cap * sizeof(PlanarRec), cudaHostAllocDefault));
+                                  ctx->kp_cap * sizeof(PlanarRec), cudaHostAllocMapped));
   FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_point),
-                                  ctx->kq_cap * sizeof(PointRec), cudaHostAllocDefault));
+                                  ctx->kq_cap * sizeof(PointRec), cudaHostAllocMapped));
   FORMGPU_CUDA(ctx, extract_configure(ctx->cols, ctx->words * 32, ctx->words, ctx->pr_cap));
 
   // window / keypoint store
@@ -190,7 +216,7 @@ static int create_impl(formgpu_ctx *ctx) {
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_pair, 4 * (W + 1)));
   ctx->h_pair_table.assign(W * W, PairEntry{0, 0, 0, 0});
   FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pair), 4 * (W + 1) * sizeof(uint32_t),
-                                  cudaHostAllocDefault));
+                                  cudaHostAllocMapped));
 
   int rc = ensure_upload(ctx, 1 << 16);
   if (rc) return rc;
@@ -248,7 +274,8 @@ void formgpu_destroy(formgpu_ctx *ctx) {
   F(ctx->d_mapmem); F(ctx->d_map_req); F(ctx->d_export); H(ctx->h_map_req);
   if (ctx->ev_upload) cudaEventDestroy(ctx->ev_upload);
   F(ctx->d_seg_planar); F(ctx->d_seg_point); F(ctx->d_pair);
-  F(ctx->d_partials); F(ctx->d_request); F(ctx->d_out);
+  F(ctx->d_partials); F(ctx->d_request); F(ctx->d_counters);
+  if (ctx->h_flags) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_flags));
   H(ctx->h_counts); H(ctx->h_planar); H(ctx->h_point); H(ctx->h_upload); H(ctx->h_out);
   H(ctx->h_pair);
   ctx->prof.destroy();
@@ -262,7 +289,8 @@ size_t formgpu_max_point(const formgpu_ctx *ctx) { return ctx ? ctx->kq_cap : 0;
 // ---------------------------------------------------------------------------
 // stage 1
 // ---------------------------------------------------------------------------
-static ExtractArgs make_extract_args(formgpu_ctx *ctx, const float4 *scan_dev, bool debug) {
+static ExtractArgs make_extract_args(formgpu_ctx *ctx, const float4 *scan_dev, bool debug,
+                                     bool host_records = false, bool publish = false) {
   const formgpu_params &P = ctx->P;
   ExtractArgs a{};
   a.rows = ctx->rows;
@@ -298,20 +326,28 @@ static ExtractArgs make_extract_args(formgpu_ctx *ctx, const float4 *scan_dev, b
   a.dbg_valid = debug ? ctx->d_dbg_valid : nullptr;
   a.dbg_pvalid = debug ? ctx->d_dbg_pvalid : nullptr;
   a.dbg_curv = debug ? ctx->d_dbg_curv : nullptr;
+  a.host_planar = host_records ? ctx->h_planar : nullptr;
+  a.host_point = host_records ? ctx->h_point : nullptr;
+  a.host_counts = ctx->h_counts;
+  a.done_counter = ctx->d_counters + ctx->counter_cap + 2;
+  a.flag = publish ? ctx->h_flags + 2 : nullptr;
+  a.seq = publish ? ++ctx->seq : 0;
   return a;
 }
 
 // runs the kernels on a device-resident scan and fetches the two counts
-static int extract_run(formgpu_ctx *ctx, const float4 *scan_dev, uint64_t scan_idx) {
+static int extract_run(formgpu_ctx *ctx, const float4 *scan_dev, uint64_t scan_idx,
+                       bool host_records) {
   ctx->cur_buf ^= 1;
   ctx->d_cur_planar = ctx->d_cur_planar_buf[ctx->cur_buf];
   ctx->d_cur_point = ctx->d_cur_point_buf[ctx->cur_buf];
-  const ExtractArgs a = make_extract_args(ctx, scan_dev, false);
+  // the pack kernel writes the counts (and, for host callers, the compact keypoint
+  // records) into mapped pinned memory and raises a flag: no memcpy, no stream sync
+  const ExtractArgs a = make_extract_args(ctx, scan_dev, false, host_records, true);
   extract_launch(a, 1, ctx->stream, ctx->prof);
   FORMGPU_CUDA(ctx, cudaGetLastError());
-  FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, ctx->d_cur_counts, 2 * sizeof(int),
-                                    cudaMemcpyDeviceToHost, ctx->stream));
-  FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int w = wait_flag(ctx, 2, a.seq);
+  if (w) return w;
   ctx->cur_n[0] = ctx->h_counts[0];
   ctx->cur_n[1] = ctx->h_counts[1];
   // a stale match set whose query buffer has just been overwritten is gone
@@ -336,7 +372,7 @@ int formgpu_extract(formgpu_ctx *ctx, const formgpu_point4f *scan, size_t n, uin
   ProfScope scope(ctx);
   FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_scan, scan, n * sizeof(float4), cudaMemcpyHostToDevice,
                                     ctx->stream));
-  const int rc = extract_run(ctx, ctx->d_scan, scan_idx);
+  const int rc = extract_run(ctx, ctx->d_scan, scan_idx, true);
   if (rc) return rc;
   ctx->cur_device_resident = false;
   const size_t np = (size_t)ctx->cur_n[0], nq = (size_t)ctx->cur_n[1];
@@ -344,14 +380,8 @@ int formgpu_extract(formgpu_ctx *ctx, const formgpu_point4f *scan, size_t n, uin
   *n_point = nq;
   if ((np && !planar_out) || (nq && !point_out) || np > planar_cap || nq > point_cap)
     return fail(ctx, FORMGPU_ERR_CAPACITY, "formgpu_extract: output buffers too small");
-  // compact lossless f32 records come back over PCIe; widen to the f64 API structs here
-  if (np)
-    FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_planar, ctx->d_cur_planar, np * sizeof(PlanarRec),
-                                      cudaMemcpyDeviceToHost, ctx->stream));
-  if (nq)
-    FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_point, ctx->d_cur_point, nq * sizeof(PointRec),
-                                      cudaMemcpyDeviceToHost, ctx->stream));
-  FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // the compact lossless f32 records already sit in mapped pinned memory (written by
+  // the pack kernel over PCIe); widen them to the f64 API structs here
   for (size_t i = 0; i < np; ++i) {
     const PlanarRec &r = ctx->h_planar[i];
     formgpu_planar_feat &o = planar_out[i];
@@ -379,7 +409,7 @@ int formgpu_extract_device(formgpu_ctx *ctx, const formgpu_point4f *scan_dev, si
   ProfScope scope(ctx);
   // the kernels read the caller's device buffer in place; extract_debug is only
   // available after formgpu_extract (which keeps its own copy)
-  const int rc = extract_run(ctx, reinterpret_cast<const float4 *>(scan_dev), scan_idx);
+  const int rc = extract_run(ctx, reinterpret_cast<const float4 *>(scan_dev), scan_idx, false);
   ctx->cur_device_resident = true;
   if (rc) return rc;
   *n_planar = (size_t)ctx->cur_n[0];

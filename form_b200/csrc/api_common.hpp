@@ -40,6 +40,10 @@ inline int find_slot(const formgpu_ctx *ctx, uint64_t scan) {
   return it == ctx->slot_of.end() ? -1 : it->second;
 }
 
+/// Spin until a kernel has published `seq` in the mapped flag.  Falls back to the
+/// stream state every few thousand polls so a faulted kernel cannot hang the caller.
+int wait_flag(formgpu_ctx *ctx, int which, unsigned long long seq);
+
 /// Ensure the pinned upload / result staging buffers are large enough.
 int ensure_upload(formgpu_ctx *ctx, size_t bytes);
 int ensure_out(formgpu_ctx *ctx, size_t pairs);

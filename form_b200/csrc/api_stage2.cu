@@ -174,15 +174,21 @@ int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k, formgpu_pair
       sa[t].block_hist = ctx->d_block_hist[t];
       sa[t].pair_off = ctx->d_pair + (size_t)(2 * t) * (W + 1);
       sa[t].pair_cnt = ctx->d_pair + (size_t)(2 * t + 1) * (W + 1);
+      sa[t].host_pair_off = ctx->h_pair + (size_t)(2 * t) * (W + 1);
+      sa[t].host_pair_cnt = ctx->h_pair + (size_t)(2 * t + 1) * (W + 1);
+      sa[t].done_counter = ctx->d_counters + ctx->counter_cap + 1;
+      sa[t].flag = ctx->h_flags + 1;
+      sa[t].seq = ctx->seq + 1;
       sa[t].seg = t == 0 ? ctx->d_seg_planar + (size_t)slot_k * 9 * kcap
                          : ctx->d_seg_point + (size_t)slot_k * 6 * kcap;
     }
     assoc_launch(aa[0], aa[1], ctx->stream, ctx->prof);
     segment_build_launch(sa[0], sa[1], ctx->stream, ctx->prof);
     FORMGPU_CUDA(ctx, cudaGetLastError());
-    FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_pair, ctx->d_pair, 4 * (W + 1) * sizeof(uint32_t),
-                                      cudaMemcpyDeviceToHost, ctx->stream));
-    FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // the counts arrive through mapped memory as soon as the scan kernel is done; the
+    // scatter kernel keeps running behind (later calls are ordered on the same stream)
+    const int w = wait_flag(ctx, 1, ++ctx->seq);
+    if (w) return w;
     for (int t = 0; t < 2; ++t) {
       if (nq[t] == 0) continue; // Matcher::match returns early, state stays (matcher.hpp:72-74)
       const uint32_t *off = ctx->h_pair + (size_t)(2 * t) * (W + 1);

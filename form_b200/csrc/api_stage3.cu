@@ -7,6 +7,9 @@ using namespace formgpu;
 
 namespace {
 
+// doubles per pair in the result buffer: 91 for blocks, 1 for errors
+inline size_t values_per_chunk_out(int values_per_chunk) { return values_per_chunk == 28 ? 91 : 1; }
+
 size_t next_pow2(size_t v) {
   size_t p = 1;
   while (p < v) p <<= 1;
@@ -104,7 +107,19 @@ int prepare(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
   a.n_chunks = (int)chunks.size();
   a.inv_sigma2 = 1.0 / (ctx->P.sigma * ctx->P.sigma);
   a.partials = ctx->d_partials;
-  a.out = ctx->d_out;
+  a.out = ctx->h_out; // mapped pinned: the kernel writes the results straight to the host
+  a.pair_counter = ctx->d_counters;
+  a.done_counter = ctx->d_counters + ctx->counter_cap;
+  int work = 0;
+  for (const LinPair &d : lp) work += (d.n_chunks_planar + d.n_chunks_point) > 0;
+  a.n_work_pairs = work;
+  a.flag = ctx->h_flags + 0;
+  a.seq = ++ctx->seq;
+  // pairs without correspondences are never touched by a CTA: zero them here
+  for (size_t p = 0; p < n_pairs; ++p)
+    if (lp[p].n_chunks_planar + lp[p].n_chunks_point == 0)
+      std::memset(ctx->h_out + p * (size_t)values_per_chunk_out(values_per_chunk), 0,
+                  values_per_chunk_out(values_per_chunk) * sizeof(double));
   return FORMGPU_OK;
 }
 
@@ -125,9 +140,11 @@ int formgpu_linearize(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pair
   if (rc) return rc;
   linearize_launch(a, ctx->stream, ctx->prof);
   FORMGPU_CUDA(ctx, cudaGetLastError());
-  FORMGPU_CUDA(ctx, cudaMemcpyAsync(out91, ctx->d_out, n_pairs * 91 * sizeof(double),
-                                    cudaMemcpyDeviceToHost, ctx->stream));
-  FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (a.n_chunks > 0) {
+    const int w = wait_flag(ctx, 0, a.seq);
+    if (w) return w;
+  }
+  std::memcpy(out91, ctx->h_out, n_pairs * 91 * sizeof(double));
   return FORMGPU_OK;
 }
 
@@ -144,9 +161,11 @@ int formgpu_error(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
   if (rc) return rc;
   error_launch(a, ctx->stream, ctx->prof);
   FORMGPU_CUDA(ctx, cudaGetLastError());
-  FORMGPU_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n_pairs * sizeof(double), cudaMemcpyDeviceToHost,
-                                    ctx->stream));
-  FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (a.n_chunks > 0) {
+    const int w = wait_flag(ctx, 0, a.seq);
+    if (w) return w;
+  }
+  std::memcpy(out, ctx->h_out, n_pairs * sizeof(double));
   return FORMGPU_OK;
 }
 

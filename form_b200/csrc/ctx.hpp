@@ -217,12 +217,18 @@ struct formgpu_ctx {
   uint32_t *h_pair = nullptr;     // pinned mirror of d_pair
   std::vector<formgpu::PairEntry> h_pair_table; // host mirror [W(k)][W(i)]
 
+  // ---- zero-copy completion signalling ----
+  // mapped pinned page the kernels write their completion sequence numbers to
+  volatile unsigned long long *h_flags = nullptr; // [8]: 0 lin/err, 1 assoc, 2 extract
+  unsigned long long seq = 0;
+  unsigned *d_counters = nullptr; // [pair tickets (cap) | done counters (8)]
+  size_t counter_cap = 0;
+
   // ---- linearisation scratch ----
   double *d_partials = nullptr;
   size_t partial_cap = 0; // chunks
   void *d_request = nullptr;
   size_t request_bytes = 0;
-  double *d_out = nullptr;
   size_t out_cap = 0; // pairs
 
   // ---- instrumentation ----

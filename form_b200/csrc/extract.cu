@@ -633,7 +633,9 @@ extract_pack_kernel(ExtractArgs a) {
         r.nx = nrm.x; r.ny = nrm.y; r.nz = nrm.z;
         r.pad0 = (uint32_t)(row * a.cols + c);
         r.pad1 = 0;
-        a.cur_planar[(size_t)b * a.kp_cap + base_out + __popc(bal & ((1u << lane) - 1u))] = r;
+        const size_t o = base_out + __popc(bal & ((1u << lane) - 1u));
+        a.cur_planar[(size_t)b * a.kp_cap + o] = r;
+        if (a.host_planar) a.host_planar[o] = r;
       }
       base_out += __popc(bal);
     }
@@ -647,6 +649,22 @@ extract_pack_kernel(ExtractArgs a) {
     r.x = p.x; r.y = p.y; r.z = p.z;
     r.w = 0.0f;
     a.cur_point[(size_t)b * a.kq_cap + s_off[1] + j] = r;
+    if (a.host_point) a.host_point[s_off[1] + j] = r;
+  }
+  // publish: the last CTA to finish writes the counts and raises the host-visible flag
+  if (a.flag) {
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned d = atomicAdd(a.done_counter, 1u);
+      if (d == gridDim.x * gridDim.y - 1u) {
+        *a.done_counter = 0u;
+        a.host_counts[0] = s_tot[0];
+        a.host_counts[1] = s_tot[1];
+        __threadfence_system();
+        *a.flag = a.seq;
+      }
+    }
   }
 }
 

@@ -27,6 +27,14 @@ struct ExtractArgs {
   int *cur_counts;         // [B][2]
   uint8_t *dbg_valid, *dbg_pvalid; // [B][rows*cols] or nullptr
   float *dbg_curv;                 // [B][rows*cols] or nullptr
+  // zero-copy results (mapped pinned host memory); host_planar/host_point may be null
+  // when the caller only needs the counts (device-resident mode)
+  PlanarRec *host_planar;
+  PointRec *host_point;
+  int *host_counts;                // [2]
+  unsigned *done_counter;          // zero on entry, self-cleaning
+  volatile unsigned long long *flag;
+  unsigned long long seq;
 };
 
 cudaError_t extract_configure(int cols, int cols_pad, int words, int pr_cap);
@@ -84,6 +92,11 @@ struct SegmentArgs {
   uint32_t *block_hist; // [blocks][W+1]
   uint32_t *pair_off;   // [W+1]
   uint32_t *pair_cnt;   // [W+1] (entry W = novel keypoints)
+  uint32_t *host_pair_off; // mapped pinned mirrors of the two arrays (zero-copy result)
+  uint32_t *host_pair_cnt;
+  unsigned *done_counter;  // zero on entry, self-cleaning
+  volatile unsigned long long *flag; // mapped pinned: set to `seq` once both types are written
+  unsigned long long seq;
   float *seg;           // segment base of the current slot: [9 or 6][kcap]
 };
 void segment_build_launch(const SegmentArgs &planar, const SegmentArgs &point, cudaStream_t stream, Profiler &prof);
@@ -139,7 +152,12 @@ struct LinArgs {
   int n_pairs, n_chunks;
   double inv_sigma2;
   double *partials; // [n_chunks][28] (linearize) or [n_chunks] (error)
-  double *out;      // [n_pairs][91] or [n_pairs]
+  double *out;      // [n_pairs][91] or [n_pairs]: mapped pinned host memory (zero-copy)
+  unsigned *pair_counter;          // [n_pairs] chunk tickets, zero on entry, self-cleaning
+  unsigned *done_counter;          // pairs finished, zero on entry, self-cleaning
+  int n_work_pairs;                // pairs with at least one chunk
+  volatile unsigned long long *flag; // mapped pinned: set to `seq` when everything is written
+  unsigned long long seq;
 };
 void linearize_launch(const LinArgs &a, cudaStream_t stream, Profiler &prof);
 void error_launch(const LinArgs &a, cudaStream_t stream, Profiler &prof);

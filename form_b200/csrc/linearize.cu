@@ -66,6 +66,105 @@ __device__ __forceinline__ double warp_sum(double v) {
 } // namespace
 
 // ---------------------------------------------------------------------------
+// finalize (run by the last chunk's CTA of a pair): sum the chunk partials in
+// index order and expand the two 7x7 moment matrices to the 13x13 block
+// ---------------------------------------------------------------------------
+__device__ void finalize_pair(const LinArgs &a, const LinPair &pr, int pair, const RelPose &rel) {
+  const int tid = threadIdx.x;
+  __shared__ double Wp[7][7], Wq[7][7];
+  __shared__ double Bp[7][13];    // plane-point basis rows
+  __shared__ double Bq[7][3][13]; // point-point basis (3 rows each)
+
+  if (tid < 28) {
+    double sp = 0.0, sq = 0.0;
+    for (int c = 0; c < pr.n_chunks_planar; ++c)
+      sp += __ldcg(&a.partials[(size_t)(pr.chunk_begin_planar + c) * 28 + tid]);
+    for (int c = 0; c < pr.n_chunks_point; ++c)
+      sq += __ldcg(&a.partials[(size_t)(pr.chunk_begin_point + c) * 28 + tid]);
+    // unpack upper-triangular index tid -> (p, q)
+    int p = 0, e = tid;
+    while (e >= 7 - p) {
+      e -= 7 - p;
+      ++p;
+    }
+    const int q = p + e;
+    Wp[p][q] = Wp[q][p] = sp;
+    Wq[p][q] = Wq[q][p] = sq;
+  }
+  for (int i = tid; i < 7 * 13; i += blockDim.x) (&Bp[0][0])[i] = 0.0;
+  for (int i = tid; i < 7 * 3 * 13; i += blockDim.x) (&Bq[0][0][0])[i] = 0.0;
+  __syncthreads();
+
+  const double *R = rel.R, *t = rel.t;
+  if (tid < 3) {
+    const int k = tid;
+    // ---- plane-point: row = [ u1, -u2, -R^T u1 - R^T [t]x u2, R^T u2, -r ] ----
+    const double K[3][3] = {{0, -t[2], t[1]}, {t[2], 0, -t[0]}, {-t[1], t[0], 0}}; // skew(t)
+    Bp[k][k] = 1.0;           // J_i rot  =  u1
+    Bp[3 + k][3 + k] = -1.0;  // J_i trans = -u2
+    for (int c = 0; c < 3; ++c) {
+      Bp[k][6 + c] = -R[3 * k + c];                 // -R^T u1
+      double bt = 0.0;                              // (R^T [t]x)[c][k]
+      for (int b = 0; b < 3; ++b) bt += R[3 * b + c] * K[b][k];
+      Bp[3 + k][6 + c] = -bt;                       // -R^T [t]x u2
+      Bp[3 + k][9 + c] = R[3 * k + c];              //  R^T u2
+    }
+    if (k == 0) {
+      Bp[6][12] = -1.0; // b = -r
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)   // +[t]x R, the constant part of -[c]x R
+          Bq[6][r][6 + c] = K[r][0] * R[c] + K[r][1] * R[3 + c] + K[r][2] * R[6 + c];
+    }
+    // ---- point-point: rows = [ [P]x, -I, -[c]x R, R, -e ],  c = P + e - t ----
+    double E[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+    E[k2][k1] = 1.0;  // skew(e_k): [k2][k1] = +1, [k1][k2] = -1
+    E[k1][k2] = -1.0;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        const double er = E[r][0] * R[c] + E[r][1] * R[3 + c] + E[r][2] * R[6 + c]; // (E_k R)[r][c]
+        Bq[k][r][c] = E[r][c];            // [P]x
+        Bq[k][r][6 + c] = -er;            // -[P]x R
+        Bq[3 + k][r][6 + c] = -er;        // -[e]x R
+      }
+    Bq[3 + k][k][12] = -1.0;              // -e
+    Bq[6][k][3 + k] = -1.0;               // -I
+    for (int c = 0; c < 3; ++c) Bq[6][k][9 + c] = R[3 * k + c]; // R
+  }
+  __syncthreads();
+
+  if (tid < 91) {
+    int x = 0, e = tid;
+    while (e >= 13 - x) {
+      e -= 13 - x;
+      ++x;
+    }
+    const int y = x + e;
+    double sum = 0.0;
+    if (pr.n_chunks_planar > 0) {
+      for (int k = 0; k < 7; ++k) {
+        const double bx = Bp[k][x];
+        if (bx == 0.0) continue;
+        double inner = 0.0;
+        for (int l = 0; l < 7; ++l) inner += Wp[k][l] * Bp[l][y];
+        sum += bx * inner;
+      }
+    }
+    if (pr.n_chunks_point > 0) {
+      for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 7; ++k) {
+          const double bx = Bq[k][r][x];
+          if (bx == 0.0) continue;
+          double inner = 0.0;
+          for (int l = 0; l < 7; ++l) inner += Wq[k][l] * Bq[l][r][y];
+          sum += bx * inner;
+        }
+    }
+    a.out[(size_t)pair * 91 + tid] = sum * a.inv_sigma2;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // chunk kernel: one CTA per chunk of one pair's correspondences
 // ---------------------------------------------------------------------------
 template <bool kErrorOnly>
@@ -124,6 +223,7 @@ __global__ void __launch_bounds__(kLinThreads) lin_chunk_kernel(LinArgs a) {
 
   constexpr int NV = kErrorOnly ? 1 : 28;
   __shared__ double s_part[kLinThreads / 32][NV];
+  __shared__ bool s_last;
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -137,146 +237,52 @@ __global__ void __launch_bounds__(kLinThreads) lin_chunk_kernel(LinArgs a) {
     for (int w = 0; w < kLinThreads / 32; ++w) v += s_part[w][tid];
     a.partials[(size_t)blockIdx.x * NV + tid] = v;
   }
-}
-
-// ---------------------------------------------------------------------------
-// finalize: per pair, sum the chunk partials in order and expand to 13x13
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(96) lin_finalize_kernel(LinArgs a) {
-  const LinPair pr = a.pairs[blockIdx.x];
-  const int tid = threadIdx.x;
-  __shared__ double Wp[7][7], Wq[7][7];
-  __shared__ double Bp[7][13];    // plane-point basis rows
-  __shared__ double Bq[7][3][13]; // point-point basis (3 rows each)
-  __shared__ RelPose s_rel;
-
-  if (tid < 28) {
-    double sp = 0.0, sq = 0.0;
-    for (int c = 0; c < pr.n_chunks_planar; ++c) sp += a.partials[(size_t)(pr.chunk_begin_planar + c) * 28 + tid];
-    for (int c = 0; c < pr.n_chunks_point; ++c) sq += a.partials[(size_t)(pr.chunk_begin_point + c) * 28 + tid];
-    // unpack upper-triangular index tid -> (p, q)
-    int p = 0, e = tid;
-    while (e >= 7 - p) {
-      e -= 7 - p;
-      ++p;
-    }
-    const int q = p + e;
-    Wp[p][q] = Wp[q][p] = sp;
-    Wq[p][q] = Wq[q][p] = sq;
-  }
-  if (tid == 32) s_rel = rel_pose(a.poses + 12 * pr.slot_i, a.poses + 12 * pr.slot_j);
-  for (int i = tid; i < 7 * 13; i += blockDim.x) (&Bp[0][0])[i] = 0.0;
-  for (int i = tid; i < 7 * 3 * 13; i += blockDim.x) (&Bq[0][0][0])[i] = 0.0;
+  // ---- last chunk of the pair finishes it (no second launch, no host memcpy) ----
+  __threadfence();
   __syncthreads();
-
   if (tid == 0) {
-    const double *R = s_rel.R, *t = s_rel.t;
-    // ---- plane-point: row = [ u1, -u2, -R^T u1 - R^T [t]x u2, R^T u2, -r ] ----
-    // skew(t)[b][a]
-    const double K[3][3] = {{0, -t[2], t[1]}, {t[2], 0, -t[0]}, {-t[1], t[0], 0}};
-    for (int k = 0; k < 3; ++k) {
-      Bp[k][k] = 1.0;           // J_i rot  =  u1
-      Bp[3 + k][3 + k] = -1.0;  // J_i trans = -u2
-      for (int c = 0; c < 3; ++c) {
-        Bp[k][6 + c] = -R[3 * k + c];                 // -R^T u1
-        double bt = 0.0;                              // (R^T [t]x)[c][k]
-        for (int b = 0; b < 3; ++b) bt += R[3 * b + c] * K[b][k];
-        Bp[3 + k][6 + c] = -bt;                       // -R^T [t]x u2
-        Bp[3 + k][9 + c] = R[3 * k + c];              //  R^T u2
-      }
-    }
-    Bp[6][12] = -1.0; // b = -r
-    // ---- point-point: rows = [ [P]x, -I, -[c]x R, R, -e ],  c = P + e - t ----
-    // E_a = skew(unit a): E_a[r][cc]
-    for (int k = 0; k < 3; ++k) {
-      double E[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-      const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
-      E[k2][k1] = 1.0;  // skew(e_k): [k2][k1] = +1, [k1][k2] = -1
-      E[k1][k2] = -1.0;
-      double ER[3][3]; // E_k * R
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) ER[r][c] = E[r][0] * R[c] + E[r][1] * R[3 + c] + E[r][2] * R[6 + c];
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) {
-          Bq[k][r][c] = E[r][c];            // [P]x
-          Bq[k][r][6 + c] = -ER[r][c];      // -[P]x R
-          Bq[3 + k][r][6 + c] = -ER[r][c];  // -[e]x R
-          Bq[6][r][6 + c] += t[k] * ER[r][c]; // +[t]x R
-        }
-      Bq[3 + k][k][12] = -1.0;              // -e
-    }
-    for (int r = 0; r < 3; ++r) {
-      Bq[6][r][3 + r] = -1.0;               // -I
-      for (int c = 0; c < 3; ++c) Bq[6][r][9 + c] = R[3 * r + c]; // R
-    }
+    const unsigned ticket = atomicAdd(&a.pair_counter[ch.pair], 1u);
+    s_last = ticket == (unsigned)(pr.n_chunks_planar + pr.n_chunks_point) - 1u;
   }
   __syncthreads();
-
-  if (tid < 91) {
-    int x = 0, e = tid;
-    while (e >= 13 - x) {
-      e -= 13 - x;
-      ++x;
+  if (!s_last) return;
+  __threadfence();
+  if (kErrorOnly) {
+    if (tid == 0) {
+      // chunks in index order: deterministic sum
+      double sum = 0.0;
+      for (int c = 0; c < pr.n_chunks_planar; ++c) sum += __ldcg(&a.partials[pr.chunk_begin_planar + c]);
+      for (int c = 0; c < pr.n_chunks_point; ++c) sum += __ldcg(&a.partials[pr.chunk_begin_point + c]);
+      a.out[ch.pair] = 0.5 * sum * a.inv_sigma2;
     }
-    const int y = x + e;
-    double sum = 0.0;
-    if (pr.n_chunks_planar > 0) {
-      for (int k = 0; k < 7; ++k) {
-        const double bx = Bp[k][x];
-        if (bx == 0.0) continue;
-        double inner = 0.0;
-        for (int l = 0; l < 7; ++l) inner += Wp[k][l] * Bp[l][y];
-        sum += bx * inner;
-      }
-    }
-    if (pr.n_chunks_point > 0) {
-      for (int r = 0; r < 3; ++r)
-        for (int k = 0; k < 7; ++k) {
-          const double bx = Bq[k][r][x];
-          if (bx == 0.0) continue;
-          double inner = 0.0;
-          for (int l = 0; l < 7; ++l) inner += Wq[k][l] * Bq[l][r][y];
-          sum += bx * inner;
-        }
-    }
-    a.out[(size_t)blockIdx.x * 91 + tid] = sum * a.inv_sigma2;
+  } else {
+    finalize_pair(a, pr, ch.pair, rel);
   }
-}
-
-__global__ void __launch_bounds__(128) err_finalize_kernel(LinArgs a) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= a.n_pairs) return;
-  const LinPair pr = a.pairs[p];
-  double s = 0.0;
-  for (int c = 0; c < pr.n_chunks_planar; ++c) s += a.partials[pr.chunk_begin_planar + c];
-  for (int c = 0; c < pr.n_chunks_point; ++c) s += a.partials[pr.chunk_begin_point + c];
-  a.out[p] = 0.5 * s * a.inv_sigma2;
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    a.pair_counter[ch.pair] = 0u;
+    const unsigned d = atomicAdd(a.done_counter, 1u);
+    if (d == (unsigned)a.n_work_pairs - 1u) {
+      *a.done_counter = 0u;
+      __threadfence_system();
+      *a.flag = a.seq;
+    }
+  }
 }
 
 void linearize_launch(const LinArgs &a, cudaStream_t stream, Profiler &prof) {
-  if (a.n_chunks > 0) {
-    prof.begin(FORMGPU_KG_LIN_CHUNK);
-    lin_chunk_kernel<false><<<a.n_chunks, kLinThreads, 0, stream>>>(a);
-    prof.end(FORMGPU_KG_LIN_CHUNK, 1);
-  }
-  if (a.n_pairs > 0) {
-    prof.begin(FORMGPU_KG_LIN_FINALIZE);
-    lin_finalize_kernel<<<a.n_pairs, 96, 0, stream>>>(a);
-    prof.end(FORMGPU_KG_LIN_FINALIZE, 1);
-  }
+  if (a.n_chunks <= 0) return;
+  prof.begin(FORMGPU_KG_LIN_CHUNK);
+  lin_chunk_kernel<false><<<a.n_chunks, kLinThreads, 0, stream>>>(a);
+  prof.end(FORMGPU_KG_LIN_CHUNK, 1);
 }
 
 void error_launch(const LinArgs &a, cudaStream_t stream, Profiler &prof) {
-  if (a.n_chunks > 0) {
-    prof.begin(FORMGPU_KG_ERR_CHUNK);
-    lin_chunk_kernel<true><<<a.n_chunks, kLinThreads, 0, stream>>>(a);
-    prof.end(FORMGPU_KG_ERR_CHUNK, 1);
-  }
-  if (a.n_pairs > 0) {
-    prof.begin(FORMGPU_KG_ERR_FINALIZE);
-    err_finalize_kernel<<<(a.n_pairs + 127) / 128, 128, 0, stream>>>(a);
-    prof.end(FORMGPU_KG_ERR_FINALIZE, 1);
-  }
+  if (a.n_chunks <= 0) return;
+  prof.begin(FORMGPU_KG_ERR_CHUNK);
+  lin_chunk_kernel<true><<<a.n_chunks, kLinThreads, 0, stream>>>(a);
+  prof.end(FORMGPU_KG_ERR_CHUNK, 1);
 }
 
 } // namespace formgpu

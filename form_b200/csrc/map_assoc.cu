@@ -171,13 +171,11 @@ __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs q
   const int cx = voxel_coord(wx, a.voxel_width), cy = voxel_coord(wy, a.voxel_width),
             cz = voxel_coord(wz, a.voxel_width);
 
-  double best = DBL_MAX;                     // Match::dist_sqrd default (map.hpp:55)
-  unsigned long long best_tie = ~0ull;
-  uint32_t best_src = kNoSlot;
+  // phase 1: lane l < 27 looks its neighbour voxel up (27 independent probes in flight)
+  uint32_t start = 0, count = 0;
   if (lane < 27 && a.n_map > 0) {
     const unsigned long long key = pack_key(cx + c_shift[lane][0], cy + c_shift[lane][1], cz + c_shift[lane][2]);
     uint32_t h = hash_key(key) & a.hash_mask;
-    uint32_t start = 0, count = 0;
     for (;;) {
       const HashSlot s = a.hash[h];
       if (s.key == key) {
@@ -188,40 +186,61 @@ __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs q
       if (s.key == kEmptyKey) break;
       h = (h + 1) & a.hash_mask;
     }
-    for (uint32_t i = 0; i < count; ++i) {
-      const WorldPoint p = a.world[start + i];
+  }
+  // phase 2: the whole warp scans each non-empty bucket together (32 consecutive
+  // 32-byte points per step = fully coalesced), instead of one lane per bucket
+  double best = DBL_MAX;                     // Match::dist_sqrd default (map.hpp:55)
+  unsigned long long best_tie = ~0ull;
+  int best_rank = 32;
+  uint32_t best_pos = kNoSlot;
+  unsigned nz = __ballot_sync(0xffffffffu, count > 0);
+  while (nz) {
+    const int b = __ffs(nz) - 1; // shift rank, ascending
+    nz &= nz - 1;
+    const uint32_t sb = __shfl_sync(0xffffffffu, start, b);
+    const uint32_t cb = __shfl_sync(0xffffffffu, count, b);
+    for (uint32_t i = lane; i < cb; i += 32) {
+      const WorldPoint p = a.world[sb + i];
       // 4-lane double squared norm, lane 3 = 0 padding: (d0^2 + d2^2) + (d1^2 + 0)
       const double d0 = p.x - wx, d1 = p.y - wy, d2 = p.z - wz;
       const double dist = (d0 * d0 + d2 * d2) + (d1 * d1 + 0.0);
-      if (dist < best || (dist == best && p.tie < best_tie)) {
+      // rule R5 key (dist, shift rank, tie); b only grows inside a lane
+      if (dist < best || (dist == best && (b < best_rank || (b == best_rank && p.tie < best_tie)))) {
         best = dist;
         best_tie = p.tie;
-        best_src = a.world_src[start + i];
+        best_rank = b;
+        best_pos = sb + i;
       }
     }
   }
-  // arg-min over lanes with key (dist, shift rank = lane, tie): rule R5
-  int best_lane = lane;
+  // arg-min over lanes with the same key
   for (int off = 16; off > 0; off >>= 1) {
     const double od = __shfl_xor_sync(0xffffffffu, best, off);
     const unsigned long long ot = __shfl_xor_sync(0xffffffffu, best_tie, off);
-    const uint32_t os = __shfl_xor_sync(0xffffffffu, best_src, off);
-    const int ol = __shfl_xor_sync(0xffffffffu, best_lane, off);
-    const bool take = (os != kNoSlot) &&
-                      (best_src == kNoSlot || od < best ||
-                       (od == best && (ol < best_lane || (ol == best_lane && ot < best_tie))));
+    const uint32_t op = __shfl_xor_sync(0xffffffffu, best_pos, off);
+    const int orank = __shfl_xor_sync(0xffffffffu, best_rank, off);
+    const bool take = (op != kNoSlot) &&
+                      (best_pos == kNoSlot || od < best ||
+                       (od == best && (orank < best_rank || (orank == best_rank && ot < best_tie))));
     if (take) {
       best = od;
       best_tie = ot;
-      best_src = os;
-      best_lane = ol;
+      best_pos = op;
+      best_rank = orank;
     }
   }
   if (lane == 0) {
     MatchRec m;
-    m.dist_sqrd = best_src == kNoSlot ? DBL_MAX : best;
-    m.slot = best_src == kNoSlot ? kNoSlot : (best_src >> 24);
-    m.k = best_src == kNoSlot ? 0u : (best_src & 0xFFFFFFu);
+    if (best_pos == kNoSlot) {
+      m.dist_sqrd = DBL_MAX;
+      m.slot = kNoSlot;
+      m.k = 0u;
+    } else {
+      const uint32_t src = a.world_src[best_pos];
+      m.dist_sqrd = best;
+      m.slot = src >> 24;
+      m.k = src & 0xFFFFFFu;
+    }
     a.match[q] = m;
   }
 }
@@ -288,6 +307,18 @@ __global__ void __launch_bounds__(256) segment_scan_kernel(SegmentArgs pa, Segme
     }
     a.pair_off[a.W] = off;        // total correspondences
     a.pair_cnt[a.W] = s_tot[a.W]; // novel keypoints
+    // publish the counts to the host without a memcpy: the caller spins on the flag
+    for (int b = 0; b <= a.W; ++b) {
+      a.host_pair_off[b] = a.pair_off[b];
+      a.host_pair_cnt[b] = a.pair_cnt[b];
+    }
+    __threadfence_system();
+    const unsigned d = atomicAdd(a.done_counter, 1u);
+    if (d == 1u) { // both types done
+      *a.done_counter = 0u;
+      __threadfence_system();
+      *a.flag = a.seq;
+    }
   }
 }
 

@@ -27,6 +27,8 @@ typedef struct formhost_est_params {
   int32_t num_threads;             /* 0 */
   int32_t device;                  /* 0 */
   int32_t record_trace;            /* 0 */
+  int32_t gtsam_lm_schedule;       /* 0: fused trial linearisation; 1: GTSAM's linearise + error calls */
+  int32_t reserved;
 } formhost_est_params;
 }
 
@@ -52,6 +54,7 @@ inline Estimator::Params to_estimator_params(const formhost_est_params &p) {
   e.matcher.max_num_rematches = (size_t)p.max_num_rematches;
   e.constraints.disable_smoothing = p.disable_smoothing != 0;
   e.constraints.planar_constraint_sigma = h.sigma;
+  e.constraints.fused_trial_linearization = p.gtsam_lm_schedule == 0;
   e.scans.max_num_keyscans = p.max_num_keyscans;
   e.scans.max_num_recent_scans = (size_t)p.max_num_recent_scans;
   e.scans.max_steps_unused_keyscan = p.max_steps_unused_keyscan;

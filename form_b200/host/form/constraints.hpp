@@ -110,6 +110,13 @@ public:
     double planar_constraint_sigma = 0.1;
     double pose_sigma = 1e-3; // Isotropic::Sigma(6, 1e-3), constraints.hpp:65
     LMParams opt_params;
+    /// Host scheduling of the hot-path calls inside LM.  false: GTSAM's schedule - one
+    /// linearisation per outer iteration plus one error evaluation per trial step.
+    /// true: every trial step is LINEARISED instead (its error is 0.5 * f of the returned
+    /// blocks, the same quantity), and an accepted trial's blocks are reused as the next
+    /// iteration's linearisation - one device round trip per LM step instead of two.
+    /// Same iterates either way (up to the rounding of 0.5 * f vs the error kernel).
+    bool fused_trial_linearization = true;
   };
   using PairCounts = std::map<uint64_t, std::pair<uint32_t, uint32_t>>; // i -> (planar, point)
 
@@ -482,11 +489,21 @@ private:
   /// DenseLMOptimizer::optimize (gtsam.hpp:40-54) with GTSAM's LM schedule.
   Values levenberg_marquardt(const Graph &g, const Values &initial) {
     const LMParams &P = m_params.opt_params;
+    const bool fused = m_params.fused_trial_linearization;
     Values values = initial;
     std::vector<uint64_t> order;
     for (const auto &kv : values) order.push_back(kv.first);
     const size_t n = 6 * order.size();
-    double error = graph_error(g, values);
+    dense::Quadratic lin;      // linearisation at `values` (valid when have_lin)
+    bool have_lin = false;
+    double error;
+    if (fused) {
+      lin = linearize_graph(g, values, order);
+      have_lin = true;
+      error = 0.5 * lin.f;
+    } else {
+      error = graph_error(g, values);
+    }
     double lambda = P.lambdaInitial;
     size_t iterations = 0;
 
@@ -502,7 +519,8 @@ private:
     do {
       current_error = new_error;
       // ---- iterate(): linearise once, then search lambda ----
-      const dense::Quadratic lin = linearize_graph(g, values, order);
+      if (!have_lin) lin = linearize_graph(g, values, order);
+      have_lin = true;
       for (;;) {
         // buildDampedSystem: + lambda * I (diagonalDamping = false)
         std::vector<double> A = lin.G;
@@ -511,6 +529,7 @@ private:
         bool step_ok = false, stop_search = false;
         double trial_error = std::numeric_limits<double>::infinity();
         Values trial;
+        dense::Quadratic trial_lin;
         double fidelity = 0.0;
         if (dense::cholesky(A, n)) {
           dense::cholesky_solve(A, n, delta.data());
@@ -524,7 +543,12 @@ private:
               for (int a = 0; a < 6; ++a) d[a] = delta[6 * k + a];
               trial[order[k]] = values.at(order[k]).retract(d);
             }
-            trial_error = graph_error(g, trial);
+            if (fused) {
+              trial_lin = linearize_graph(g, trial, order);
+              trial_error = 0.5 * trial_lin.f;
+            } else {
+              trial_error = graph_error(g, trial);
+            }
             const double cost_change = error - trial_error;
             if (lin_change > std::numeric_limits<double>::epsilon() * old_lin) {
               fidelity = cost_change / lin_change;
@@ -537,6 +561,8 @@ private:
         if (step_ok) {
           values = std::move(trial);
           error = trial_error;
+          if (fused) lin = std::move(trial_lin); // already the linearisation at the new values
+          else have_lin = false;
           lambda = std::max(P.lambdaLowerBound, lambda / P.lambdaFactor);
           ++iterations;
           ++m_stats.lm_iterations;
