@@ -38,13 +38,18 @@ int ensure_out(formgpu_ctx *ctx, size_t pairs) {
   if (pairs <= ctx->out_cap) return FORMGPU_OK;
   FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
+  if (ctx->h_pair_flags) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_pair_flags));
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   ctx->h_out = nullptr;
+  ctx->h_pair_flags = nullptr;
   ctx->d_counters = nullptr;
   const size_t cap = next_pow2(pairs);
   // results are written by the kernels straight into this mapped pinned buffer
   FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_out), cap * 91 * sizeof(double),
                                   cudaHostAllocMapped));
+  FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(const_cast<unsigned long long **>(&ctx->h_pair_flags)),
+                                  cap * sizeof(unsigned long long), cudaHostAllocMapped));
+  for (size_t i = 0; i < cap; ++i) ctx->h_pair_flags[i] = 0;
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_counters, cap + 8));
   FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, (cap + 8) * sizeof(unsigned), ctx->stream));
   FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -214,6 +219,7 @@ static int create_impl(formgpu_ctx *ctx) {
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_block_hist[0], ((ctx->kp_cap + 255) / 256 + 1) * (W + 1)));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_block_hist[1], ((ctx->kq_cap + 255) / 256 + 1) * (W + 1)));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_pair, 4 * (W + 1)));
+  FORMGPU_CUDA(ctx, map_assoc_configure((std::max(ctx->kp_cap, ctx->kq_cap) + 255) / 256 + 1, ctx->W));
   ctx->h_pair_table.assign(W * W, PairEntry{0, 0, 0, 0});
   FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pair), 4 * (W + 1) * sizeof(uint32_t),
                                   cudaHostAllocMapped));
@@ -276,6 +282,7 @@ void formgpu_destroy(formgpu_ctx *ctx) {
   F(ctx->d_seg_planar); F(ctx->d_seg_point); F(ctx->d_pair);
   F(ctx->d_partials); F(ctx->d_request); F(ctx->d_counters);
   if (ctx->h_flags) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_flags));
+  if (ctx->h_pair_flags) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_pair_flags));
   H(ctx->h_counts); H(ctx->h_planar); H(ctx->h_point); H(ctx->h_upload); H(ctx->h_out);
   H(ctx->h_pair);
   ctx->prof.destroy();

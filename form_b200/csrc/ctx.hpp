@@ -164,8 +164,9 @@ struct formgpu_ctx {
   formgpu::PointRec *h_point = nullptr;   // kq_cap
   void *h_upload = nullptr;              // request staging (poses, pairs, chunks)
   size_t h_upload_bytes = 0;
-  double *h_out = nullptr; // result staging (91 * pairs)
+  double *h_out = nullptr; // results (91 * pairs), mapped: written by the kernels
   size_t h_out_bytes = 0;
+  volatile unsigned long long *h_pair_flags = nullptr; // per-pair completion flags, mapped
 
   // ---- current scan ----
   bool have_current = false;

@@ -51,20 +51,32 @@ __device__ __forceinline__ void clear_bits(uint32_t *m, int lo, int hi) {
 // Resolve the sequential "take it if still unused, then suppress +-(np-1)"
 // rule inside a group of 32 candidates ordered by lane: lane l survives iff it
 // is a candidate and no surviving earlier lane lies within np-1 columns.
+// Each lane first collects the set of earlier candidate lanes it conflicts with (32
+// independent shuffles); the survivors are then found by a short fixed-point iteration
+// on ballots - the lowest undecided lane is always decidable, and in practice two or
+// three rounds settle the whole group - instead of a 31-step dependent shuffle chain.
 __device__ __forceinline__ bool resolve_group(bool cand, int col, int np, int lane) {
-  bool alive = cand;
-  const unsigned any = __ballot_sync(0xffffffffu, cand);
-  if (any == 0) return false;
-  const int last = 31 - __clz(any);
-  for (int k = 0; k < last; ++k) {
+  const unsigned cand_bits = __ballot_sync(0xffffffffu, cand);
+  if (cand_bits == 0) return false;
+  unsigned conf = 0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
     const int ck = __shfl_sync(0xffffffffu, col, k);
-    const int ak = __shfl_sync(0xffffffffu, (int)alive, k);
-    if (ak && lane > k) {
-      const int d = col - ck;
-      if (d < np && d > -np) alive = false;
-    }
+    const int d = col - ck;
+    if (d < np && d > -np) conf |= 1u << k;
   }
-  return alive;
+  conf &= cand_bits & ((1u << lane) - 1u); // earlier candidate lanes only
+  unsigned undecided = cand_bits, alive_bits = 0;
+  while (undecided) {
+    const bool me = (undecided >> lane) & 1u;
+    const bool kill = me && (conf & alive_bits);
+    const bool ok = me && !kill && !(conf & undecided);
+    const unsigned killb = __ballot_sync(0xffffffffu, kill);
+    const unsigned okb = __ballot_sync(0xffffffffu, ok);
+    alive_bits |= okb;
+    undecided &= ~(killb | okb);
+  }
+  return (alive_bits >> lane) & 1u;
 }
 
 } // namespace
@@ -305,30 +317,46 @@ __device__ __forceinline__ void neighbor_counts(const float4 *rowp, int c, int n
   if (n_minus > np) n_minus = np;
 }
 
-// find_closest (extraction.tpp:402-420), rule R2: arg-min (dist2, column) over
-// the valid points of one row.
-__device__ __forceinline__ int closest_in_row(const float4 *rowp, const uint32_t *valid,
-                                              const float4 p, int cols, int lane) {
-  float best = INFINITY;
-  int bc = 0x7fffffff;
+// find_closest (extraction.tpp:402-420), rule R2: arg-min (dist2, column) over the
+// valid points of one row, for kPicks query points at once: every row point is read
+// from shared memory once and compared with all kPicks queries, which divides the
+// shared-memory traffic - the limiter of this kernel - by kPicks.
+constexpr int kPicks = 4;
+__device__ __forceinline__ void closest_in_row_multi(const float4 *rowp, const uint32_t *valid,
+                                                     const float4 (&p)[kPicks], int cols, int lane,
+                                                     int (&out)[kPicks]) {
+  float best[kPicks];
+  int bc[kPicks];
+#pragma unroll
+  for (int k = 0; k < kPicks; ++k) {
+    best[k] = INFINITY;
+    bc[k] = 0x7fffffff;
+  }
   for (int c = lane; c < cols; c += 32) {
     if ((valid[c >> 5] >> (c & 31)) & 1u) {
-      const float d2 = diff_sqnorm4(rowp[c], p);
-      if (d2 < best) {
-        best = d2;
-        bc = c;
+      const float4 q = rowp[c];
+#pragma unroll
+      for (int k = 0; k < kPicks; ++k) {
+        const float d2 = diff_sqnorm4(q, p[k]);
+        if (d2 < best[k]) {
+          best[k] = d2;
+          bc[k] = c;
+        }
       }
     }
   }
-  for (int off = 16; off > 0; off >>= 1) {
-    const float od = __shfl_xor_sync(0xffffffffu, best, off);
-    const int oc = __shfl_xor_sync(0xffffffffu, bc, off);
-    if (od < best || (od == best && oc < bc)) {
-      best = od;
-      bc = oc;
+#pragma unroll
+  for (int k = 0; k < kPicks; ++k) {
+    for (int off = 16; off > 0; off >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, best[k], off);
+      const int oc = __shfl_xor_sync(0xffffffffu, bc[k], off);
+      if (od < best[k] || (od == best[k] && oc < bc[k])) {
+        best[k] = od;
+        bc[k] = oc;
+      }
     }
+    out[k] = bc[k] == 0x7fffffff ? -1 : bc[k];
   }
-  return bc == 0x7fffffff ? -1 : bc;
 }
 
 __device__ __forceinline__ float hypot_pos(float x, float y) {
@@ -500,29 +528,36 @@ extract_normals_kernel(ExtractArgs a) {
   const uint16_t *picks = a.planar_cols + rb * a.pr_cap;
   const double r2 = a.radius * a.radius;
 
-  // phase A: one warp per pick - neighbour counts and closest points
-  for (int pk = warp; pk < n_picks; pk += nwarps) {
-    const int c = picks[pk];
-    const float4 p = own[c];
-    int n_plus, n_minus, pp = 0, pm = 0, nq = 0, nm = 0;
-    neighbor_counts(own, c, np, r2, lane, n_plus, n_minus);
-    int cp = -1, cn = -1;
-    if (has_prev) {
-      cp = closest_in_row(prv, v_prv, p, cols, lane);
-      if (cp >= 0) neighbor_counts(prv, cp, np, r2, lane, pp, pm);
+  // phase A: one warp per group of kPicks picks - closest points, then neighbour counts
+  for (int g0 = warp * kPicks; g0 < n_picks; g0 += nwarps * kPicks) {
+    float4 pp[kPicks];
+    int cc[kPicks];
+#pragma unroll
+    for (int k = 0; k < kPicks; ++k) {
+      cc[k] = picks[min(g0 + k, n_picks - 1)]; // tail lanes repeat the last pick
+      pp[k] = own[cc[k]];
     }
-    if (has_next) {
-      cn = closest_in_row(nxt, v_nxt, p, cols, lane);
-      if (cn >= 0) neighbor_counts(nxt, cn, np, r2, lane, nq, nm);
-    }
-    if (lane == 0) {
-      PickDesc d;
-      d.c_prev = (short)cp; d.c_next = (short)cn;
-      d.n_plus = (unsigned char)n_plus; d.n_minus = (unsigned char)n_minus;
-      d.pp = (unsigned char)pp; d.pm = (unsigned char)pm;
-      d.np_ = (unsigned char)nq; d.nm = (unsigned char)nm;
-      d.pad[0] = d.pad[1] = 0;
-      desc[pk] = d;
+    int cprev[kPicks], cnext[kPicks];
+#pragma unroll
+    for (int k = 0; k < kPicks; ++k) cprev[k] = cnext[k] = -1;
+    if (has_prev) closest_in_row_multi(prv, v_prv, pp, cols, lane, cprev);
+    if (has_next) closest_in_row_multi(nxt, v_nxt, pp, cols, lane, cnext);
+#pragma unroll
+    for (int k = 0; k < kPicks; ++k) {
+      if (g0 + k >= n_picks) break;
+      int n_plus, n_minus, pp_ = 0, pm = 0, nq = 0, nm = 0;
+      neighbor_counts(own, cc[k], np, r2, lane, n_plus, n_minus);
+      if (cprev[k] >= 0) neighbor_counts(prv, cprev[k], np, r2, lane, pp_, pm);
+      if (cnext[k] >= 0) neighbor_counts(nxt, cnext[k], np, r2, lane, nq, nm);
+      if (lane == 0) {
+        PickDesc d;
+        d.c_prev = (short)cprev[k]; d.c_next = (short)cnext[k];
+        d.n_plus = (unsigned char)n_plus; d.n_minus = (unsigned char)n_minus;
+        d.pp = (unsigned char)pp_; d.pm = (unsigned char)pm;
+        d.np_ = (unsigned char)nq; d.nm = (unsigned char)nm;
+        d.pad[0] = d.pad[1] = 0;
+        desc[g0 + k] = d;
+      }
     }
   }
   __syncthreads();

@@ -99,6 +99,7 @@ struct SegmentArgs {
   unsigned long long seq;
   float *seg;           // segment base of the current slot: [9 or 6][kcap]
 };
+cudaError_t map_assoc_configure(size_t max_query_blocks, int W);
 void segment_build_launch(const SegmentArgs &planar, const SegmentArgs &point, cudaStream_t stream, Profiler &prof);
 
 struct CommitArgs {
@@ -129,37 +130,35 @@ struct WorldExportArgs {
 void world_export_launch(const WorldExportArgs &a, cudaStream_t stream, Profiler &prof);
 
 // ---- stage 3 (linearize.cu, FMA allowed: tolerance class) ----
-struct LinPair {   // one requested pair
-  int slot_i, slot_j;
-  uint32_t off_planar, n_planar, off_point, n_point;
-  int chunk_begin_planar, n_chunks_planar;
-  int chunk_begin_point, n_chunks_point;
+constexpr int kLinThreads = 256;   // threads per CTA
+constexpr int kLinCluster = 8;     // CTAs per cluster = per scan pair
+constexpr int kLinInlineTasks = 48; // pairs that travel in the kernel parameters (6 KB)
+
+struct LinTask { // one scan pair with at least one correspondence (128 B)
+  double rel[12];      // R_i^T R_j row-major, then R_i^T (t_j - t_i): precomputed by the host
+  uint32_t off_planar, n_planar, off_point, n_point; // ranges inside the segment of slot_j
+  int slot_j;
+  int out_index;       // position of the pair in the caller's list
+  uint32_t pad[2];
 };
-struct LinChunk {  // one block's work
-  int pair;
-  int type;        // 0 planar, 1 point
-  uint32_t start;  // offset inside the segment of slot_j
-  uint32_t len;
+static_assert(sizeof(LinTask) == 128, "LinTask size");
+
+struct LinInline {
+  LinTask tasks[kLinInlineTasks];
 };
+
 struct LinArgs {
-  int W;
   size_t kp_cap, kq_cap;
   const float *seg_planar; // [W][9][kp_cap]
   const float *seg_point;  // [W][6][kq_cap]
-  const double *poses;     // [W][12] poses of this request, by slot
-  const LinPair *pairs;
-  const LinChunk *chunks;
-  int n_pairs, n_chunks;
+  const LinTask *tasks;    // device copy of the request when it does not fit the parameters
+  int n_tasks;
   double inv_sigma2;
-  double *partials; // [n_chunks][28] (linearize) or [n_chunks] (error)
-  double *out;      // [n_pairs][91] or [n_pairs]: mapped pinned host memory (zero-copy)
-  unsigned *pair_counter;          // [n_pairs] chunk tickets, zero on entry, self-cleaning
-  unsigned *done_counter;          // pairs finished, zero on entry, self-cleaning
-  int n_work_pairs;                // pairs with at least one chunk
-  volatile unsigned long long *flag; // mapped pinned: set to `seq` when everything is written
+  double *out;             // [n_pairs][91] or [n_pairs]: mapped pinned host memory (zero-copy)
+  volatile unsigned long long *flags; // [n_pairs] mapped pinned: set to `seq` when the pair is written
   unsigned long long seq;
 };
-void linearize_launch(const LinArgs &a, cudaStream_t stream, Profiler &prof);
-void error_launch(const LinArgs &a, cudaStream_t stream, Profiler &prof);
+cudaError_t linearize_launch(const LinArgs &a, const LinInline *inline_req, bool error_only,
+                             cudaStream_t stream, Profiler &prof);
 
 } // namespace formgpu

@@ -7,54 +7,84 @@
 // (/root/reference/form/optimization/gtsam.hpp:59-140).  Tolerance class
 // (H/b rel <= 1e-5), so FMA contraction is allowed here.
 //
-// The reference materialises an (n+3m) x 13 dense Jacobian per pair and forms
-// A^T A.  Here each correspondence is streamed once from HBM (coalesced SoA
-// floats - the keypoints are float-exact) and reduced on the fly.  Working in
+// Arithmetic.  The reference materialises an (n+3m) x 13 dense Jacobian per pair
+// and forms A^T A.  Here each correspondence is streamed once from HBM (coalesced
+// SoA floats - the keypoints are float-exact) and reduced on the fly.  Working in
 // the frame of scan i,
-//     q = R_i^T (R_j p_j + t_j - t_i)           (p_j seen from scan i)
-// every row of [J_i J_j | -r] is LINEAR in a 7-vector that depends on the
-// correspondence, with coefficients that depend only on the pair's relative
-// pose (R_rel, t_rel):
+//     q = R_rel p_j + t_rel,   R_rel = R_i^T R_j,  t_rel = R_i^T (t_j - t_i)
+// every row of [J_i J_j | -r] is LINEAR in a 7-vector of the correspondence, with
+// coefficients that depend only on the pair's relative pose:
 //     plane-point:  s = [ n x q,  n,  n.(q - p_i) ]
-//     point-point:  z = [ p_i,  q - p_i,  1 ]         (3 rows, rotated by R_i^T,
-//                                                      which leaves A^T A unchanged)
-// so a thread only accumulates the 28 unique products of its 7-vector (56
-// registers instead of 182 for the 91 entries) and the 13x13 block is
-// recovered per pair in the finalize kernel as  sum_kl W_kl B_k^T B_l.
-// Reduction order is fixed (strided per thread, shuffle tree per warp, warps
-// and chunks in index order) so results are run-to-run deterministic.
+//     point-point:  z = [ p_i,  q - p_i,  1 ]     (3 rows, rotated by R_i^T, which
+//                                                  leaves A^T A unchanged)
+// so a thread accumulates only the 28 unique products of its 7-vector (56 registers
+// instead of 182 for the 91 entries) and the 13x13 block is recovered per pair as
+// sum_kl W_kl B_k^T B_l.
+//
+// Mapping.  One thread-block CLUSTER of 8 CTAs per scan pair: CTA r streams the r-th
+// eighth of the pair's planar and point correspondences, reduces its 2 x 28 moments
+// (butterfly-transpose warp reduction: 31 shuffles instead of 140), and leaves them
+// in its shared memory; after cluster.sync() CTA 0 gathers the eight partial sums
+// through distributed shared memory, expands the block and writes the 91 doubles
+// plus a per-pair sequence flag straight into mapped pinned host memory.  There
+// is no partial-sum traffic through global memory, no atomic, no second launch and
+// no device->host memcpy.  Small requests travel in the kernel parameters (with
+// the relative poses precomputed by the host), so the first instruction that
+// touches memory is already a correspondence load.  The partition and every
+// reduction order are fixed: results are run-to-run deterministic.
 #include "ctx.hpp"
 #include "kernels.hpp"
+
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace formgpu {
 
 namespace {
 
-constexpr int kLinThreads = 128;
+constexpr int kThreads = kLinThreads;
+constexpr int kWarps = kThreads / 32;
+constexpr int kCluster = kLinCluster;
 
-struct RelPose {
-  double R[9]; // R_i^T R_j, row-major
-  double t[3]; // R_i^T (t_j - t_i)
-};
-
-__device__ __forceinline__ RelPose rel_pose(const double *Ti, const double *Tj) {
-  RelPose r;
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int b = 0; b < 3; ++b)
-      r.R[3 * a + b] = Ti[a] * Tj[b] + Ti[3 + a] * Tj[3 + b] + Ti[6 + a] * Tj[6 + b];
-  const double dx = Tj[9] - Ti[9], dy = Tj[10] - Ti[10], dz = Tj[11] - Ti[11];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) r.t[a] = Ti[a] * dx + Ti[3 + a] * dy + Ti[6 + a] * dz;
-  return r;
+__device__ __forceinline__ void apply_rel(const double *rel, double x, double y, double z,
+                                          double &qx, double &qy, double &qz) {
+  qx = rel[0] * x + rel[1] * y + rel[2] * z + rel[9];
+  qy = rel[3] * x + rel[4] * y + rel[5] * z + rel[10];
+  qz = rel[6] * x + rel[7] * y + rel[8] * z + rel[11];
 }
 
-__device__ __forceinline__ void apply_rel(const RelPose &r, double x, double y, double z,
-                                          double &qx, double &qy, double &qz) {
-  qx = r.R[0] * x + r.R[1] * y + r.R[2] * z + r.t[0];
-  qy = r.R[3] * x + r.R[4] * y + r.R[5] * z + r.t[1];
-  qz = r.R[6] * x + r.R[7] * y + r.R[8] * z + r.t[2];
+// Butterfly-transpose reduction of 32 values per lane across the warp: at the step
+// with offset o a lane keeps the half of its values selected by (lane & o) and adds
+// the partner's copy of that half, so after 5 steps lane l holds the warp total of
+// element l.  16+8+4+2+1 = 31 exchanges instead of 32 * 5.
+template <int N> __device__ __forceinline__ void transpose_reduce(double (&v)[32], int lane) {
+  if constexpr (N >= 1) {
+    const bool upper = (lane & N) != 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double keep = upper ? v[i + N] : v[i];
+      const double send = upper ? v[i] : v[i + N];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, N);
+    }
+    transpose_reduce<N / 2>(v, lane);
+  }
+}
+
+// CTA-wide sum of the 28 moments of every thread into out[28] (shared memory).
+__device__ __forceinline__ void block_reduce28(double (&acc)[32], double (*s_warp)[28], double *out,
+                                               int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  transpose_reduce<16>(acc, lane);
+  if (lane < 28) s_warp[warp][lane] = acc[0];
+  __syncthreads();
+  if (tid < 28) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) v += s_warp[w][tid];
+    out[tid] = v;
+  }
+  __syncthreads();
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -63,72 +93,63 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-} // namespace
-
 // ---------------------------------------------------------------------------
-// finalize (run by the last chunk's CTA of a pair): sum the chunk partials in
-// index order and expand the two 7x7 moment matrices to the 13x13 block
+// expansion of the two 7x7 moment matrices to the 13x13 block (CTA 0 of a cluster)
 // ---------------------------------------------------------------------------
-__device__ void finalize_pair(const LinArgs &a, const LinPair &pr, int pair, const RelPose &rel) {
+__device__ void finalize_pair(const double *Wp28, const double *Wq28, bool has_planar,
+                              bool has_point, const double *rel, double inv_sigma2, double *out91) {
   const int tid = threadIdx.x;
   __shared__ double Wp[7][7], Wq[7][7];
   __shared__ double Bp[7][13];    // plane-point basis rows
   __shared__ double Bq[7][3][13]; // point-point basis (3 rows each)
-
   if (tid < 28) {
-    double sp = 0.0, sq = 0.0;
-    for (int c = 0; c < pr.n_chunks_planar; ++c)
-      sp += __ldcg(&a.partials[(size_t)(pr.chunk_begin_planar + c) * 28 + tid]);
-    for (int c = 0; c < pr.n_chunks_point; ++c)
-      sq += __ldcg(&a.partials[(size_t)(pr.chunk_begin_point + c) * 28 + tid]);
-    // unpack upper-triangular index tid -> (p, q)
-    int p = 0, e = tid;
+    int p = 0, e = tid; // upper-triangular index -> (p, q)
     while (e >= 7 - p) {
       e -= 7 - p;
       ++p;
     }
     const int q = p + e;
-    Wp[p][q] = Wp[q][p] = sp;
-    Wq[p][q] = Wq[q][p] = sq;
+    Wp[p][q] = Wp[q][p] = Wp28[tid];
+    Wq[p][q] = Wq[q][p] = Wq28[tid];
   }
   for (int i = tid; i < 7 * 13; i += blockDim.x) (&Bp[0][0])[i] = 0.0;
   for (int i = tid; i < 7 * 3 * 13; i += blockDim.x) (&Bq[0][0][0])[i] = 0.0;
   __syncthreads();
 
-  const double *R = rel.R, *t = rel.t;
+  const double *R = rel, *t = rel + 9;
   if (tid < 3) {
     const int k = tid;
     // ---- plane-point: row = [ u1, -u2, -R^T u1 - R^T [t]x u2, R^T u2, -r ] ----
     const double K[3][3] = {{0, -t[2], t[1]}, {t[2], 0, -t[0]}, {-t[1], t[0], 0}}; // skew(t)
-    Bp[k][k] = 1.0;           // J_i rot  =  u1
-    Bp[3 + k][3 + k] = -1.0;  // J_i trans = -u2
+    Bp[k][k] = 1.0;          // J_i rot   =  u1
+    Bp[3 + k][3 + k] = -1.0; // J_i trans = -u2
     for (int c = 0; c < 3; ++c) {
-      Bp[k][6 + c] = -R[3 * k + c];                 // -R^T u1
-      double bt = 0.0;                              // (R^T [t]x)[c][k]
+      Bp[k][6 + c] = -R[3 * k + c]; // -R^T u1
+      double bt = 0.0;              // (R^T [t]x)[c][k]
       for (int b = 0; b < 3; ++b) bt += R[3 * b + c] * K[b][k];
-      Bp[3 + k][6 + c] = -bt;                       // -R^T [t]x u2
-      Bp[3 + k][9 + c] = R[3 * k + c];              //  R^T u2
+      Bp[3 + k][6 + c] = -bt;          // -R^T [t]x u2
+      Bp[3 + k][9 + c] = R[3 * k + c]; //  R^T u2
     }
     if (k == 0) {
       Bp[6][12] = -1.0; // b = -r
       for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c)   // +[t]x R, the constant part of -[c]x R
+        for (int c = 0; c < 3; ++c) // +[t]x R, the constant part of -[c]x R
           Bq[6][r][6 + c] = K[r][0] * R[c] + K[r][1] * R[3 + c] + K[r][2] * R[6 + c];
     }
     // ---- point-point: rows = [ [P]x, -I, -[c]x R, R, -e ],  c = P + e - t ----
     double E[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
-    E[k2][k1] = 1.0;  // skew(e_k): [k2][k1] = +1, [k1][k2] = -1
+    E[k2][k1] = 1.0; // skew(e_k): [k2][k1] = +1, [k1][k2] = -1
     E[k1][k2] = -1.0;
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) {
         const double er = E[r][0] * R[c] + E[r][1] * R[3 + c] + E[r][2] * R[6 + c]; // (E_k R)[r][c]
-        Bq[k][r][c] = E[r][c];            // [P]x
-        Bq[k][r][6 + c] = -er;            // -[P]x R
-        Bq[3 + k][r][6 + c] = -er;        // -[e]x R
+        Bq[k][r][c] = E[r][c];     // [P]x
+        Bq[k][r][6 + c] = -er;     // -[P]x R
+        Bq[3 + k][r][6 + c] = -er; // -[e]x R
       }
-    Bq[3 + k][k][12] = -1.0;              // -e
-    Bq[6][k][3 + k] = -1.0;               // -I
+    Bq[3 + k][k][12] = -1.0; // -e
+    Bq[6][k][3 + k] = -1.0;  // -I
     for (int c = 0; c < 3; ++c) Bq[6][k][9 + c] = R[3 * k + c]; // R
   }
   __syncthreads();
@@ -141,7 +162,7 @@ __device__ void finalize_pair(const LinArgs &a, const LinPair &pr, int pair, con
     }
     const int y = x + e;
     double sum = 0.0;
-    if (pr.n_chunks_planar > 0) {
+    if (has_planar) {
       for (int k = 0; k < 7; ++k) {
         const double bx = Bp[k][x];
         if (bx == 0.0) continue;
@@ -150,7 +171,7 @@ __device__ void finalize_pair(const LinArgs &a, const LinPair &pr, int pair, con
         sum += bx * inner;
       }
     }
-    if (pr.n_chunks_point > 0) {
+    if (has_point) {
       for (int r = 0; r < 3; ++r)
         for (int k = 0; k < 7; ++k) {
           const double bx = Bq[k][r][x];
@@ -160,36 +181,43 @@ __device__ void finalize_pair(const LinArgs &a, const LinPair &pr, int pair, con
           sum += bx * inner;
         }
     }
-    a.out[(size_t)pair * 91 + tid] = sum * a.inv_sigma2;
+    out91[tid] = sum * inv_sigma2;
   }
 }
 
 // ---------------------------------------------------------------------------
-// chunk kernel: one CTA per chunk of one pair's correspondences
+// one cluster per pair
 // ---------------------------------------------------------------------------
 template <bool kErrorOnly>
-__global__ void __launch_bounds__(kLinThreads) lin_chunk_kernel(LinArgs a) {
-  const LinChunk ch = a.chunks[blockIdx.x];
-  const LinPair pr = a.pairs[ch.pair];
-  const RelPose rel = rel_pose(a.poses + 12 * pr.slot_i, a.poses + 12 * pr.slot_j);
+__device__ __forceinline__ void lin_cluster_body(const LinArgs &a, const LinTask &task) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x;
+  __shared__ double s_warp[kWarps][28];
+  __shared__ double s_sum[2][28];  // [planar | point] moments of this CTA (error: [0][0])
+  __shared__ double s_total[2][28];
 
-  double acc[kErrorOnly ? 1 : 28];
+  double acc[32];
 #pragma unroll
-  for (int k = 0; k < (kErrorOnly ? 1 : 28); ++k) acc[k] = 0.0;
+  for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+  double err_acc = 0.0;
 
-  if (ch.type == 0) {
-    const float *s = a.seg_planar + (size_t)pr.slot_j * 9 * a.kp_cap + ch.start;
+  // ---- plane-point correspondences of this CTA's slice ----
+  {
+    const uint32_t lo = (uint32_t)(((unsigned long long)task.n_planar * rank) / kCluster);
+    const uint32_t hi = (uint32_t)(((unsigned long long)task.n_planar * (rank + 1)) / kCluster);
+    const float *s = a.seg_planar + (size_t)task.slot_j * 9 * a.kp_cap + task.off_planar;
     const size_t st = a.kp_cap;
-    for (uint32_t c = tid; c < ch.len; c += kLinThreads) {
+#pragma unroll 2
+    for (uint32_t c = lo + tid; c < hi; c += kThreads) {
       const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
       const double nx = s[3 * st + c], ny = s[4 * st + c], nz = s[5 * st + c];
       const double pjx = s[6 * st + c], pjy = s[7 * st + c], pjz = s[8 * st + c];
       double qx, qy, qz;
-      apply_rel(rel, pjx, pjy, pjz, qx, qy, qz);
+      apply_rel(task.rel, pjx, pjy, pjz, qx, qy, qz);
       const double r = nx * (qx - pix) + ny * (qy - piy) + nz * (qz - piz);
       if (kErrorOnly) {
-        acc[0] += r * r;
+        err_acc += r * r;
       } else {
         const double v[7] = {ny * qz - nz * qy, nz * qx - nx * qz, nx * qy - ny * qx, nx, ny, nz, r};
         int e = 0;
@@ -199,17 +227,27 @@ __global__ void __launch_bounds__(kLinThreads) lin_chunk_kernel(LinArgs a) {
           for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
       }
     }
-  } else {
-    const float *s = a.seg_point + (size_t)pr.slot_j * 6 * a.kq_cap + ch.start;
+  }
+  if (!kErrorOnly) {
+    block_reduce28(acc, s_warp, s_sum[0], tid);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+  }
+  // ---- point-point correspondences ----
+  {
+    const uint32_t lo = (uint32_t)(((unsigned long long)task.n_point * rank) / kCluster);
+    const uint32_t hi = (uint32_t)(((unsigned long long)task.n_point * (rank + 1)) / kCluster);
+    const float *s = a.seg_point + (size_t)task.slot_j * 6 * a.kq_cap + task.off_point;
     const size_t st = a.kq_cap;
-    for (uint32_t c = tid; c < ch.len; c += kLinThreads) {
+#pragma unroll 2
+    for (uint32_t c = lo + tid; c < hi; c += kThreads) {
       const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
       const double pjx = s[3 * st + c], pjy = s[4 * st + c], pjz = s[5 * st + c];
       double qx, qy, qz;
-      apply_rel(rel, pjx, pjy, pjz, qx, qy, qz);
+      apply_rel(task.rel, pjx, pjy, pjz, qx, qy, qz);
       const double ex = qx - pix, ey = qy - piy, ez = qz - piz;
       if (kErrorOnly) {
-        acc[0] += ex * ex + ey * ey + ez * ez;
+        err_acc += ex * ex + ey * ey + ez * ez;
       } else {
         const double v[7] = {pix, piy, piz, ex, ey, ez, 1.0};
         int e = 0;
@@ -220,69 +258,102 @@ __global__ void __launch_bounds__(kLinThreads) lin_chunk_kernel(LinArgs a) {
       }
     }
   }
-
-  constexpr int NV = kErrorOnly ? 1 : 28;
-  __shared__ double s_part[kLinThreads / 32][NV];
-  __shared__ bool s_last;
-  const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const double v = warp_sum(acc[k]);
-    if (lane == 0) s_part[warp][k] = v;
-  }
-  __syncthreads();
-  if (tid < NV) {
-    double v = 0.0;
-#pragma unroll
-    for (int w = 0; w < kLinThreads / 32; ++w) v += s_part[w][tid];
-    a.partials[(size_t)blockIdx.x * NV + tid] = v;
-  }
-  // ---- last chunk of the pair finishes it (no second launch, no host memcpy) ----
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned ticket = atomicAdd(&a.pair_counter[ch.pair], 1u);
-    s_last = ticket == (unsigned)(pr.n_chunks_planar + pr.n_chunks_point) - 1u;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
   if (kErrorOnly) {
+    const double w = warp_sum(err_acc);
+    if ((tid & 31) == 0) s_warp[tid >> 5][0] = w;
+    __syncthreads();
     if (tid == 0) {
-      // chunks in index order: deterministic sum
-      double sum = 0.0;
-      for (int c = 0; c < pr.n_chunks_planar; ++c) sum += __ldcg(&a.partials[pr.chunk_begin_planar + c]);
-      for (int c = 0; c < pr.n_chunks_point; ++c) sum += __ldcg(&a.partials[pr.chunk_begin_point + c]);
-      a.out[ch.pair] = 0.5 * sum * a.inv_sigma2;
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < kWarps; ++k) v += s_warp[k][0];
+      s_sum[0][0] = v;
     }
   } else {
-    finalize_pair(a, pr, ch.pair, rel);
+    block_reduce28(acc, s_warp, s_sum[1], tid);
   }
-  __threadfence_system();
-  __syncthreads();
-  if (tid == 0) {
-    a.pair_counter[ch.pair] = 0u;
-    const unsigned d = atomicAdd(a.done_counter, 1u);
-    if (d == (unsigned)a.n_work_pairs - 1u) {
-      *a.done_counter = 0u;
-      __threadfence_system();
-      *a.flag = a.seq;
+
+  // ---- gather the eight CTA sums through distributed shared memory ----
+  cluster.sync();
+  if (rank == 0) {
+    if (kErrorOnly) {
+      if (tid == 0) {
+        double v = 0.0;
+        for (int r = 0; r < kCluster; ++r) v += *cluster.map_shared_rank(&s_sum[0][0], r);
+        a.out[task.out_index] = 0.5 * v * a.inv_sigma2;
+      }
+    } else {
+      if (tid < 56) {
+        const int which = tid / 28, e = tid % 28;
+        double v = 0.0;
+#pragma unroll
+        for (int r = 0; r < kCluster; ++r) v += *cluster.map_shared_rank(&s_sum[which][e], r);
+        s_total[which][e] = v;
+      }
+      __syncthreads();
+      finalize_pair(s_total[0], s_total[1], task.n_planar > 0, task.n_point > 0, task.rel,
+                    a.inv_sigma2, a.out + (size_t)task.out_index * 91);
     }
   }
+  cluster.sync(); // the other CTAs' shared memory must outlive CTA 0's remote reads
+  if (rank == 0) {
+    // publish: results first, then the pair's flag (the host polls it)
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) a.flags[task.out_index] = a.seq;
+  }
 }
 
-void linearize_launch(const LinArgs &a, cudaStream_t stream, Profiler &prof) {
-  if (a.n_chunks <= 0) return;
-  prof.begin(FORMGPU_KG_LIN_CHUNK);
-  lin_chunk_kernel<false><<<a.n_chunks, kLinThreads, 0, stream>>>(a);
-  prof.end(FORMGPU_KG_LIN_CHUNK, 1);
+} // namespace
+
+template <bool kErrorOnly>
+__global__ void __launch_bounds__(kLinThreads) lin_inline_kernel(LinArgs a, LinInline req) {
+  lin_cluster_body<kErrorOnly>(a, req.tasks[blockIdx.x / kLinCluster]);
 }
 
-void error_launch(const LinArgs &a, cudaStream_t stream, Profiler &prof) {
-  if (a.n_chunks <= 0) return;
-  prof.begin(FORMGPU_KG_ERR_CHUNK);
-  lin_chunk_kernel<true><<<a.n_chunks, kLinThreads, 0, stream>>>(a);
-  prof.end(FORMGPU_KG_ERR_CHUNK, 1);
+template <bool kErrorOnly>
+__global__ void __launch_bounds__(kLinThreads) lin_global_kernel(LinArgs a) {
+  __shared__ LinTask s_task;
+  if (threadIdx.x < sizeof(LinTask) / sizeof(unsigned long long))
+    reinterpret_cast<unsigned long long *>(&s_task)[threadIdx.x] =
+        reinterpret_cast<const unsigned long long *>(a.tasks + blockIdx.x / kLinCluster)[threadIdx.x];
+  __syncthreads();
+  lin_cluster_body<kErrorOnly>(a, s_task);
+}
+
+namespace {
+template <typename... Args>
+cudaError_t launch_cluster(void (*kernel)(Args...), int n_tasks, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_tasks * kLinCluster), 1, 1);
+  cfg.blockDim = dim3(kLinThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kLinCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+} // namespace
+
+cudaError_t linearize_launch(const LinArgs &a, const LinInline *inline_req, bool error_only,
+                             cudaStream_t stream, Profiler &prof) {
+  if (a.n_tasks <= 0) return cudaSuccess;
+  const int group = error_only ? FORMGPU_KG_ERR_CHUNK : FORMGPU_KG_LIN_CHUNK;
+  prof.begin(group);
+  cudaError_t e;
+  if (inline_req) {
+    e = error_only ? launch_cluster(lin_inline_kernel<true>, a.n_tasks, stream, a, *inline_req)
+                   : launch_cluster(lin_inline_kernel<false>, a.n_tasks, stream, a, *inline_req);
+  } else {
+    e = error_only ? launch_cluster(lin_global_kernel<true>, a.n_tasks, stream, a)
+                   : launch_cluster(lin_global_kernel<false>, a.n_tasks, stream, a);
+  }
+  prof.end(group, 1);
+  return e;
 }
 
 } // namespace formgpu

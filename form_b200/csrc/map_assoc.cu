@@ -26,12 +26,25 @@ namespace formgpu {
 
 namespace {
 
-// map.tpp:54-68 in the reference's order
-__constant__ int c_shift[27][3] = {
-    {0, 0, 0},   {1, 0, 0},   {-1, 0, 0},  {0, 1, 0},   {0, -1, 0},  {0, 0, 1},   {0, 0, -1},
-    {1, 1, 0},   {1, -1, 0},  {-1, 1, 0},  {-1, -1, 0}, {1, 0, 1},   {1, 0, -1},  {-1, 0, 1},
-    {-1, 0, -1}, {0, 1, 1},   {0, 1, -1},  {0, -1, 1},  {0, -1, -1}, {1, 1, 1},   {1, 1, -1},
-    {1, -1, 1},  {1, -1, -1}, {-1, 1, 1},  {-1, 1, -1}, {-1, -1, 1}, {-1, -1, -1}};
+// map.tpp:54-68: the 27 neighbour shifts in the reference's order.
+// Packed 2 bits per entry (0 -> 0, 1 -> +1, 2 -> -1) so a lane gets its shift with two
+// ALU ops instead of a lane-divergent (serialised) constant-memory load.
+constexpr unsigned long long pack_axis(int axis) {
+  constexpr int T[27][3] = {
+      {0, 0, 0},   {1, 0, 0},   {-1, 0, 0},  {0, 1, 0},   {0, -1, 0},  {0, 0, 1},   {0, 0, -1},
+      {1, 1, 0},   {1, -1, 0},  {-1, 1, 0},  {-1, -1, 0}, {1, 0, 1},   {1, 0, -1},  {-1, 0, 1},
+      {-1, 0, -1}, {0, 1, 1},   {0, 1, -1},  {0, -1, 1},  {0, -1, -1}, {1, 1, 1},   {1, 1, -1},
+      {1, -1, 1},  {1, -1, -1}, {-1, 1, 1},  {-1, 1, -1}, {-1, -1, 1}, {-1, -1, -1}};
+  unsigned long long v = 0;
+  for (int l = 0; l < 27; ++l) v |= (unsigned long long)(T[l][axis] == 0 ? 0 : T[l][axis] == 1 ? 1 : 2) << (2 * l);
+  return v;
+}
+constexpr unsigned long long kShiftX = pack_axis(0), kShiftY = pack_axis(1), kShiftZ = pack_axis(2);
+__device__ __forceinline__ int lane_shift(int lane, int axis) {
+  const unsigned long long bits = axis == 0 ? kShiftX : axis == 1 ? kShiftY : kShiftZ;
+  const int c = (int)((bits >> (2 * lane)) & 3ull);
+  return c == 2 ? -1 : c;
+}
 
 constexpr unsigned long long kEmptyKey = 0ull; // table is cleared with memset(0)
 
@@ -174,7 +187,7 @@ __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs q
   // phase 1: lane l < 27 looks its neighbour voxel up (27 independent probes in flight)
   uint32_t start = 0, count = 0;
   if (lane < 27 && a.n_map > 0) {
-    const unsigned long long key = pack_key(cx + c_shift[lane][0], cy + c_shift[lane][1], cz + c_shift[lane][2]);
+    const unsigned long long key = pack_key(cx + lane_shift(lane, 0), cy + lane_shift(lane, 1), cz + lane_shift(lane, 2));
     uint32_t h = hash_key(key) & a.hash_mask;
     for (;;) {
       const HashSlot s = a.hash[h];
@@ -187,18 +200,15 @@ __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs q
       h = (h + 1) & a.hash_mask;
     }
   }
-  // phase 2: the whole warp scans each non-empty bucket together (32 consecutive
-  // 32-byte points per step = fully coalesced), instead of one lane per bucket
+  // phase 2: the whole warp scans a bucket together (32 consecutive 32-byte points per
+  // step = fully coalesced).  The centre voxel goes first; a neighbour voxel is then
+  // scanned only if its box can still hold a point at least as close as the centre's
+  // best (exact pruning: a skipped voxel cannot change the arg-min).
   double best = DBL_MAX;                     // Match::dist_sqrd default (map.hpp:55)
   unsigned long long best_tie = ~0ull;
   int best_rank = 32;
   uint32_t best_pos = kNoSlot;
-  unsigned nz = __ballot_sync(0xffffffffu, count > 0);
-  while (nz) {
-    const int b = __ffs(nz) - 1; // shift rank, ascending
-    nz &= nz - 1;
-    const uint32_t sb = __shfl_sync(0xffffffffu, start, b);
-    const uint32_t cb = __shfl_sync(0xffffffffu, count, b);
+  auto scan_bucket = [&](int b, uint32_t sb, uint32_t cb) {
     for (uint32_t i = lane; i < cb; i += 32) {
       const WorldPoint p = a.world[sb + i];
       // 4-lane double squared norm, lane 3 = 0 padding: (d0^2 + d2^2) + (d1^2 + 0)
@@ -212,6 +222,34 @@ __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs q
         best_pos = sb + i;
       }
     }
+  };
+  const uint32_t c0 = __shfl_sync(0xffffffffu, count, 0);
+  if (c0) scan_bucket(0, __shfl_sync(0xffffffffu, start, 0), c0);
+  double bound = best;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) bound = fmin(bound, __shfl_xor_sync(0xffffffffu, bound, off));
+  // squared distance from the query to the box of this lane's voxel, shrunk by a safety
+  // margin that covers the rounding of floor(x / w) at the voxel faces
+  bool keep = false;
+  if (lane > 0 && lane < 27 && count > 0) {
+    const double w = a.voxel_width;
+    const double q[3] = {wx, wy, wz};
+    const int c[3] = {cx + lane_shift(lane, 0), cy + lane_shift(lane, 1), cz + lane_shift(lane, 2)};
+    double lb = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double lo = (double)c[k] * w, hi = lo + w;
+      double d = fmax(fmax(lo - q[k], q[k] - hi), 0.0);
+      d = fmax(d - 1e-9 * (1.0 + fabs(q[k])), 0.0);
+      lb += d * d;
+    }
+    keep = lb <= bound;
+  }
+  unsigned nz = __ballot_sync(0xffffffffu, keep);
+  while (nz) {
+    const int b = __ffs(nz) - 1; // shift rank, ascending
+    nz &= nz - 1;
+    scan_bucket(b, __shfl_sync(0xffffffffu, start, b), __shfl_sync(0xffffffffu, count, b));
   }
   // arg-min over lanes with the same key
   for (int off = 16; off > 0; off >>= 1) {
@@ -282,37 +320,58 @@ __global__ void __launch_bounds__(256) segment_hist_kernel(SegmentArgs pa, Segme
     a.block_hist[(size_t)blockIdx.x * nb + i] = s_hist[i];
 }
 
-// one block: per bin exclusive prefix over the query blocks, then the pair row
-__global__ void __launch_bounds__(256) segment_scan_kernel(SegmentArgs pa, SegmentArgs qa) {
+// one block per type: per bin exclusive prefix over the query blocks, then the pair row.
+// The [blocks][W+1] histogram is pulled into shared memory with coalesced loads first
+// (a read-modify-write loop over global memory serialises on every load).
+__global__ void __launch_bounds__(1024) segment_scan_kernel(SegmentArgs pa, SegmentArgs qa) {
   const SegmentArgs &a = blockIdx.x == 0 ? pa : qa;
+  extern __shared__ uint32_t s_hist[]; // [nblocks][nb]
   __shared__ uint32_t s_tot[kMaxWindow + 1];
   const int nb = a.W + 1;
   const int nblocks = (a.n_query + 255) / 256;
+  const int total = nblocks * nb;
+#pragma unroll 8
+  for (int i = threadIdx.x; i < total; i += blockDim.x) s_hist[i] = a.block_hist[i];
+  __syncthreads();
   for (int b = threadIdx.x; b < nb; b += blockDim.x) {
     uint32_t run = 0;
     for (int blk = 0; blk < nblocks; ++blk) {
-      const uint32_t c = a.block_hist[(size_t)blk * nb + b];
-      a.block_hist[(size_t)blk * nb + b] = run;
+      const uint32_t c = s_hist[blk * nb + b];
+      s_hist[blk * nb + b] = run;
       run += c;
     }
     s_tot[b] = run;
   }
   __syncthreads();
+  for (int i = threadIdx.x; i < total; i += blockDim.x) a.block_hist[i] = s_hist[i];
+  // exclusive prefix over the bins by one warp
+  __shared__ uint32_t s_off[kMaxWindow + 1];
+  if (threadIdx.x < 32) {
+    uint32_t run = 0;
+    for (int base = 0; base < a.W; base += 32) {
+      const int b = base + threadIdx.x;
+      const uint32_t c = b < a.W ? s_tot[b] : 0u;
+      uint32_t incl = c;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)threadIdx.x >= o) incl += t;
+      }
+      if (b < a.W) s_off[b] = run + incl - c;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (threadIdx.x == 0) s_off[a.W] = run; // total correspondences
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b <= a.W; b += blockDim.x) {
+    a.pair_off[b] = s_off[b];
+    a.pair_cnt[b] = s_tot[b]; // entry W = novel keypoints
+    a.host_pair_off[b] = s_off[b];
+    a.host_pair_cnt[b] = s_tot[b];
+  }
+  // the counts reach the host without a memcpy: the caller spins on the flag
+  __threadfence_system();
+  __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t off = 0;
-    for (int b = 0; b < a.W; ++b) {
-      a.pair_off[b] = off;
-      a.pair_cnt[b] = s_tot[b];
-      off += s_tot[b];
-    }
-    a.pair_off[a.W] = off;        // total correspondences
-    a.pair_cnt[a.W] = s_tot[a.W]; // novel keypoints
-    // publish the counts to the host without a memcpy: the caller spins on the flag
-    for (int b = 0; b <= a.W; ++b) {
-      a.host_pair_off[b] = a.pair_off[b];
-      a.host_pair_cnt[b] = a.pair_cnt[b];
-    }
-    __threadfence_system();
     const unsigned d = atomicAdd(a.done_counter, 1u);
     if (d == 1u) { // both types done
       *a.done_counter = 0u;
@@ -367,6 +426,11 @@ __global__ void __launch_bounds__(256) segment_scatter_kernel(SegmentArgs pa, Se
   }
 }
 
+cudaError_t map_assoc_configure(size_t max_query_blocks, int W) {
+  return cudaFuncSetAttribute(segment_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(max_query_blocks * (W + 1) * sizeof(uint32_t)));
+}
+
 void segment_build_launch(const SegmentArgs &pa, const SegmentArgs &qa, cudaStream_t stream,
                           Profiler &prof) {
   const int n = max(pa.n_query, qa.n_query);
@@ -374,7 +438,8 @@ void segment_build_launch(const SegmentArgs &pa, const SegmentArgs &qa, cudaStre
   prof.begin(FORMGPU_KG_SEGMENT);
   const dim3 g((n + 255) / 256, 2);
   segment_hist_kernel<<<g, 256, 0, stream>>>(pa, qa);
-  segment_scan_kernel<<<2, 256, 0, stream>>>(pa, qa);
+  const size_t scan_smem = (size_t)((n + 255) / 256) * (pa.W + 1) * sizeof(uint32_t);
+  segment_scan_kernel<<<2, 1024, scan_smem, stream>>>(pa, qa);
   segment_scatter_kernel<<<g, 256, 0, stream>>>(pa, qa);
   prof.end(FORMGPU_KG_SEGMENT, 3);
 }
