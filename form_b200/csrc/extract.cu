@@ -84,13 +84,15 @@ __device__ __forceinline__ bool resolve_group(bool cand, int col, int np, int la
 // ---------------------------------------------------------------------------
 // K1: validity masks, curvature, per-sector sort, greedy planar + point picks
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 extract_select_kernel(ExtractArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cols = a.cols, words = a.words, np = a.np;
   float4 *pts = reinterpret_cast<float4 *>(smem_raw);
-  unsigned long long *keys = reinterpret_cast<unsigned long long *>(pts + cols);
-  uint16_t *sorted = reinterpret_cast<uint16_t *>(keys + cols);
+  // sort key = curvature bits (non-negative floats order like unsigned ints); the column
+  // itself is the tie-break of rule R1, so 32 bits per point are enough
+  uint32_t *keys = reinterpret_cast<uint32_t *>(pts + cols);
+  uint16_t *sorted = reinterpret_cast<uint16_t *>(keys + a.cols_pad);
   uint16_t *ulist = sorted + a.cols_pad;
   uint32_t *m_range = reinterpret_cast<uint32_t *>(ulist + a.cols_pad);
   uint32_t *m_valid = m_range + words;
@@ -158,7 +160,7 @@ extract_select_kernel(ExtractArgs a) {
       }
       cf = (float)((dx * dx + dy * dy) + dz * dz);
     }
-    keys[c] = ((unsigned long long)__float_as_uint(cf) << 32) | (unsigned)c;
+    keys[c] = __float_as_uint(cf);
     if (a.dbg_curv) a.dbg_curv[row_base + c] = cf;
     if (a.dbg_valid) {
       a.dbg_valid[row_base + c] = get_bit(m_valid, c);
@@ -173,9 +175,13 @@ extract_select_kernel(ExtractArgs a) {
     const int s = min(c / pps, S - 1);
     const int start = s * pps;
     const int end = (s == S - 1) ? cols : start + pps;
-    const unsigned long long kc = keys[c];
+    const uint32_t kc = keys[c];
     int rank = 0;
-    for (int j = start; j < end; ++j) rank += (keys[j] < kc) ? 1 : 0;
+#pragma unroll 4
+    for (int j = start; j < end; ++j) {
+      const uint32_t kj = keys[j];
+      rank += (kj < kc || (kj == kc && j < c)) ? 1 : 0;
+    }
     sorted[start + rank] = (uint16_t)c;
   }
   __syncthreads();
@@ -195,7 +201,7 @@ extract_select_kernel(ExtractArgs a) {
       const int i = base + lane;
       const bool in = i < len;
       const int col = in ? (int)sorted[start + i] : 0;
-      const float curv = in ? __uint_as_float((unsigned)(keys[col] >> 32)) : FLT_MAX;
+      const float curv = in ? __uint_as_float(keys[col]) : FLT_MAX;
       const bool below = in && ((double)curv < a.planar_threshold);
       const bool cand = below && get_bit(m_used, col);
       const bool alive = resolve_group(cand, col, np, lane);
@@ -215,7 +221,10 @@ extract_select_kernel(ExtractArgs a) {
     }
     total += count;
   }
-  if (lane == 0) a.planar_cnt[(size_t)b * a.rows + row] = total;
+  if (lane == 0) {
+    a.planar_cnt[(size_t)b * a.rows + row] = total;
+    a.keep_cnt[(size_t)b * a.rows + row] = 0; // accumulated by the normals kernel
+  }
 
   // ---- point candidates (extraction.tpp:72-80): untouched by planar picks and
   // range-valid.  m_pvalid becomes the working mask of extract_point. ----
@@ -491,6 +500,11 @@ __device__ void smallest_eigvec3f(float m00, float m10, float m11, float m20, fl
 
 } // namespace
 
+// The search is arithmetic-bound (picks x 2 rows x cols distance evaluations) and a row
+// alone gives one CTA per SM at best, so every row is shared by kNormalSplit CTAs that
+// each stage the three rows and take a contiguous share of the row's picks.
+constexpr int kNormalSplit = 4;
+
 __global__ void __launch_bounds__(256)
 extract_normals_kernel(ExtractArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -503,15 +517,16 @@ extract_normals_kernel(ExtractArgs a) {
   PickDesc *desc = reinterpret_cast<PickDesc *>(v_nxt + words);
   __shared__ int s_keep;
 
-  const int row = blockIdx.x, b = blockIdx.y;
+  const int row = blockIdx.x / kNormalSplit, part = blockIdx.x % kNormalSplit, b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const size_t rb = (size_t)b * a.rows + row;
-  const int n_picks = a.planar_cnt[rb];
+  const int n_all = a.planar_cnt[rb];
+  // this CTA's share [p_lo, p_hi) of the row's picks, in multiples of kPicks
+  const int per = ((n_all + kNormalSplit * kPicks - 1) / (kNormalSplit * kPicks)) * kPicks;
+  const int p_lo = min(part * per, n_all), p_hi = min(p_lo + per, n_all);
+  const int n_picks = p_hi - p_lo;
   if (tid == 0) s_keep = 0;
-  if (n_picks == 0) {
-    if (tid == 0) a.keep_cnt[rb] = 0;
-    return;
-  }
+  if (n_picks == 0) return; // keep_cnt is zeroed by the select kernel and accumulated below
   const bool has_prev = row > 0, has_next = row < a.rows - 1;
   const float4 *g = a.scan + rb * cols;
   for (int c = tid; c < cols; c += blockDim.x) {
@@ -525,7 +540,7 @@ extract_normals_kernel(ExtractArgs a) {
   }
   __syncthreads();
 
-  const uint16_t *picks = a.planar_cols + rb * a.pr_cap;
+  const uint16_t *picks = a.planar_cols + rb * a.pr_cap + p_lo;
   const double r2 = a.radius * a.radius;
 
   // phase A: one warp per group of kPicks picks - closest points, then neighbour counts
@@ -600,14 +615,14 @@ extract_normals_kernel(ExtractArgs a) {
       out = make_float4(nrm[0], nrm[1], nrm[2], 1.0f);
       atomicAdd(&s_keep, 1);
     }
-    a.normals[rb * a.pr_cap + pk] = out;
+    a.normals[rb * a.pr_cap + p_lo + pk] = out;
     if (a.closest) {
-      a.closest[(rb * a.pr_cap + pk) * 2 + 0] = d.c_prev >= 0 ? (row - 1) * cols + d.c_prev : -1;
-      a.closest[(rb * a.pr_cap + pk) * 2 + 1] = d.c_next >= 0 ? (row + 1) * cols + d.c_next : -1;
+      a.closest[(rb * a.pr_cap + p_lo + pk) * 2 + 0] = d.c_prev >= 0 ? (row - 1) * cols + d.c_prev : -1;
+      a.closest[(rb * a.pr_cap + p_lo + pk) * 2 + 1] = d.c_next >= 0 ? (row + 1) * cols + d.c_next : -1;
     }
   }
   __syncthreads();
-  if (tid == 0) a.keep_cnt[rb] = s_keep;
+  if (tid == 0 && s_keep) atomicAdd(&a.keep_cnt[rb], s_keep); // integer count: order-free
 }
 
 // ---------------------------------------------------------------------------
@@ -688,7 +703,8 @@ extract_pack_kernel(ExtractArgs a) {
   }
   // publish: the last CTA to finish writes the counts and raises the host-visible flag
   if (a.flag) {
-    __threadfence_system();
+    if (a.host_planar || a.host_point) __threadfence_system(); // host records of this CTA first
+    else __threadfence();
     __syncthreads();
     if (tid == 0) {
       const unsigned d = atomicAdd(a.done_counter, 1u);
@@ -707,8 +723,8 @@ extract_pack_kernel(ExtractArgs a) {
 // host-side launcher
 // ---------------------------------------------------------------------------
 size_t extract_select_smem(int cols, int cols_pad, int words) {
-  return (size_t)cols * (sizeof(float4) + sizeof(unsigned long long)) +
-         (size_t)cols_pad * 2 * sizeof(uint16_t) + (size_t)words * 4 * sizeof(uint32_t);
+  return (size_t)cols * sizeof(float4) + (size_t)cols_pad * (sizeof(uint32_t) + 2 * sizeof(uint16_t)) +
+         (size_t)words * 4 * sizeof(uint32_t);
 }
 size_t extract_normals_smem(int cols, int words, int pr_cap) {
   return (size_t)cols * 3 * sizeof(float4) + (size_t)words * 2 * sizeof(uint32_t) +
@@ -727,10 +743,11 @@ cudaError_t extract_configure(int cols, int cols_pad, int words, int pr_cap) {
 void extract_launch(const ExtractArgs &a, int n_scans, cudaStream_t stream, Profiler &prof) {
   const dim3 grid(a.rows, n_scans);
   prof.begin(FORMGPU_KG_EXTRACT_SELECT);
-  extract_select_kernel<<<grid, 256, extract_select_smem(a.cols, a.cols_pad, a.words), stream>>>(a);
+  extract_select_kernel<<<grid, 512, extract_select_smem(a.cols, a.cols_pad, a.words), stream>>>(a);
   prof.end(FORMGPU_KG_EXTRACT_SELECT, 1);
   prof.begin(FORMGPU_KG_EXTRACT_NORMALS);
-  extract_normals_kernel<<<grid, 256, extract_normals_smem(a.cols, a.words, a.pr_cap), stream>>>(a);
+  extract_normals_kernel<<<dim3(a.rows * kNormalSplit, n_scans), 256,
+                           extract_normals_smem(a.cols, a.words, a.pr_cap), stream>>>(a);
   prof.end(FORMGPU_KG_EXTRACT_NORMALS, 1);
   prof.begin(FORMGPU_KG_EXTRACT_PACK);
   extract_pack_kernel<<<grid, 128, 0, stream>>>(a);

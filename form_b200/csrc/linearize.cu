@@ -154,6 +154,25 @@ __device__ void finalize_pair(const double *Wp28, const double *Wq28, bool has_p
   }
   __syncthreads();
 
+  // phase 1 (all threads): T = W B, 7 MACs per entry; phase 2 (91 threads): out = B^T T.
+  // Two short fully unrolled passes instead of one 49..147-term serial sum per entry.
+  __shared__ double Tp[7][13];    // W_p B_p
+  __shared__ double Tq[3][7][13]; // per residual row r: W_q B_q[.][r]
+  for (int idx = tid; idx < 91 + 273; idx += blockDim.x) {
+    double v = 0.0;
+    if (idx < 91) {
+      const int k = idx / 13, y = idx % 13;
+#pragma unroll
+      for (int l = 0; l < 7; ++l) v += Wp[k][l] * Bp[l][y];
+      Tp[k][y] = v;
+    } else {
+      const int j = idx - 91, r = j / 91, k = (j % 91) / 13, y = j % 13;
+#pragma unroll
+      for (int l = 0; l < 7; ++l) v += Wq[k][l] * Bq[l][r][y];
+      Tq[r][k][y] = v;
+    }
+  }
+  __syncthreads();
   if (tid < 91) {
     int x = 0, e = tid;
     while (e >= 13 - x) {
@@ -163,23 +182,14 @@ __device__ void finalize_pair(const double *Wp28, const double *Wq28, bool has_p
     const int y = x + e;
     double sum = 0.0;
     if (has_planar) {
-      for (int k = 0; k < 7; ++k) {
-        const double bx = Bp[k][x];
-        if (bx == 0.0) continue;
-        double inner = 0.0;
-        for (int l = 0; l < 7; ++l) inner += Wp[k][l] * Bp[l][y];
-        sum += bx * inner;
-      }
+#pragma unroll
+      for (int k = 0; k < 7; ++k) sum += Bp[k][x] * Tp[k][y];
     }
     if (has_point) {
+#pragma unroll
       for (int r = 0; r < 3; ++r)
-        for (int k = 0; k < 7; ++k) {
-          const double bx = Bq[k][r][x];
-          if (bx == 0.0) continue;
-          double inner = 0.0;
-          for (int l = 0; l < 7; ++l) inner += Wq[k][l] * Bq[l][r][y];
-          sum += bx * inner;
-        }
+#pragma unroll
+        for (int k = 0; k < 7; ++k) sum += Bq[k][r][x] * Tq[r][k][y];
     }
     out91[tid] = sum * inv_sigma2;
   }
