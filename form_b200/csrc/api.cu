@@ -219,7 +219,11 @@ static int create_impl(formgpu_ctx *ctx) {
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_block_hist[0], ((ctx->kp_cap + 255) / 256 + 1) * (W + 1)));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_block_hist[1], ((ctx->kq_cap + 255) / 256 + 1) * (W + 1)));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_pair, 4 * (W + 1)));
-  FORMGPU_CUDA(ctx, map_assoc_configure((std::max(ctx->kp_cap, ctx->kq_cap) + 255) / 256 + 1, ctx->W));
+  for (int t = 0; t < 2; ++t) {
+    const size_t n = ((t == 0 ? ctx->kp_cap : ctx->kq_cap) + 255) / 256 + 1;
+    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_hist_cnt[t], n * (W + 1)));
+    FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_hist_cnt[t], 0, n * (W + 1) * sizeof(uint32_t), ctx->stream));
+  }
   ctx->h_pair_table.assign(W * W, PairEntry{0, 0, 0, 0});
   FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pair), 4 * (W + 1) * sizeof(uint32_t),
                                   cudaHostAllocMapped));
@@ -270,7 +274,7 @@ void formgpu_destroy(formgpu_ctx *ctx) {
   F(ctx->d_scan); F(ctx->d_valid_bits); F(ctx->d_planar_cols); F(ctx->d_planar_cnt);
   F(ctx->d_point_cols); F(ctx->d_point_cnt); F(ctx->d_normals); F(ctx->d_closest);
   F(ctx->d_keep_cnt); F(ctx->d_cur_counts);
-  for (int i = 0; i < 2; ++i) { F(ctx->d_cur_planar_buf[i]); F(ctx->d_cur_point_buf[i]); F(ctx->d_block_hist[i]); }
+  for (int i = 0; i < 2; ++i) { F(ctx->d_cur_planar_buf[i]); F(ctx->d_cur_point_buf[i]); F(ctx->d_block_hist[i]); F(ctx->d_hist_cnt[i]); }
   F(ctx->d_dbg_valid); F(ctx->d_dbg_pvalid); F(ctx->d_dbg_curv);
   F(ctx->d_store_planar); F(ctx->d_store_point);
   for (int t = 0; t < 2; ++t) {

@@ -162,6 +162,19 @@ int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k, formgpu_pair
       aa[t].world = ctx->d_world[t];
       aa[t].world_src = ctx->d_world_src[t];
       aa[t].match = ctx->d_match[t];
+      aa[t].W = W;
+      aa[t].max_dist2 = ctx->P.max_dist_matching * ctx->P.max_dist_matching; // matcher.hpp:82
+      aa[t].min_dist2 = ctx->P.min_dist_map * ctx->P.min_dist_map;           // map.tpp:158
+      aa[t].hist_cnt = ctx->d_hist_cnt[t];
+      aa[t].block_hist = ctx->d_block_hist[t];
+      aa[t].pair_off = ctx->d_pair + (size_t)(2 * t) * (W + 1);
+      aa[t].pair_cnt = ctx->d_pair + (size_t)(2 * t + 1) * (W + 1);
+      aa[t].host_pair_off = ctx->h_pair + (size_t)(2 * t) * (W + 1);
+      aa[t].host_pair_cnt = ctx->h_pair + (size_t)(2 * t + 1) * (W + 1);
+      aa[t].type_ticket = ctx->d_counters + ctx->counter_cap + 3 + t;
+      aa[t].done_counter = ctx->d_counters + ctx->counter_cap + 1;
+      aa[t].flag = ctx->h_flags + 1;
+      aa[t].seq = ctx->seq + 1;
       sa[t].type = t;
       sa[t].W = W;
       sa[t].n_query = nq[t];
@@ -174,19 +187,15 @@ int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k, formgpu_pair
       sa[t].block_hist = ctx->d_block_hist[t];
       sa[t].pair_off = ctx->d_pair + (size_t)(2 * t) * (W + 1);
       sa[t].pair_cnt = ctx->d_pair + (size_t)(2 * t + 1) * (W + 1);
-      sa[t].host_pair_off = ctx->h_pair + (size_t)(2 * t) * (W + 1);
-      sa[t].host_pair_cnt = ctx->h_pair + (size_t)(2 * t + 1) * (W + 1);
-      sa[t].done_counter = ctx->d_counters + ctx->counter_cap + 1;
-      sa[t].flag = ctx->h_flags + 1;
-      sa[t].seq = ctx->seq + 1;
       sa[t].seg = t == 0 ? ctx->d_seg_planar + (size_t)slot_k * 9 * kcap
                          : ctx->d_seg_point + (size_t)slot_k * 6 * kcap;
     }
     assoc_launch(aa[0], aa[1], ctx->stream, ctx->prof);
     segment_build_launch(sa[0], sa[1], ctx->stream, ctx->prof);
     FORMGPU_CUDA(ctx, cudaGetLastError());
-    // the counts arrive through mapped memory as soon as the scan kernel is done; the
-    // scatter kernel keeps running behind (later calls are ordered on the same stream)
+    // the counts arrive through mapped memory as soon as the NN kernel's last CTA is
+    // done; the scatter kernel keeps running behind (later calls are ordered on the
+    // same stream)
     const int w = wait_flag(ctx, 1, ++ctx->seq);
     if (w) return w;
     for (int t = 0; t < 2; ++t) {

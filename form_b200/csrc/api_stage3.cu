@@ -62,6 +62,9 @@ int run(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs, const formg
   a.seg_planar = ctx->d_seg_planar;
   a.seg_point = ctx->d_seg_point;
   a.n_tasks = (int)tasks.size();
+  // CTAs per pair: as many as keep the launch within about one wave (2 CTAs per SM)
+  a.cluster = kLinCluster;
+  while (a.cluster > 1 && (size_t)a.cluster * tasks.size() > 2 * 148) a.cluster >>= 1;
   a.inv_sigma2 = 1.0 / (ctx->P.sigma * ctx->P.sigma);
   a.out = ctx->h_out;
   a.flags = ctx->h_pair_flags;

@@ -213,7 +213,8 @@ struct formgpu_ctx {
   uint32_t match_novel[2] = {0, 0};   // keypoints insert_matches would append
   float *d_seg_planar = nullptr; // [W][9][kp_cap]
   float *d_seg_point = nullptr;  // [W][6][kq_cap]
-  uint32_t *d_block_hist[2] = {nullptr, nullptr}; // [blocks][W+1]
+  uint32_t *d_block_hist[2] = {nullptr, nullptr}; // [blocks][W+1] prefix per 256-query block
+  uint32_t *d_hist_cnt[2] = {nullptr, nullptr};   // [blocks][W+1] atomic counters (self-cleaning)
   uint32_t *d_pair = nullptr;     // [type][off|cnt][W+1]
   uint32_t *h_pair = nullptr;     // pinned mirror of d_pair
   std::vector<formgpu::PairEntry> h_pair_table; // host mirror [W(k)][W(i)]

@@ -76,6 +76,20 @@ struct AssocArgs {
   const WorldPoint *world;
   const uint32_t *world_src;
   MatchRec *match;
+  // fused histogram + scan (the last CTA of a type turns the per-256-query bin counts
+  // into the offsets the scatter and commit kernels use, and publishes the pair row)
+  int W;
+  double max_dist2, min_dist2;
+  uint32_t *hist_cnt;      // [blocks256][W+1] atomic counters, zero on entry, self-cleaning
+  uint32_t *block_hist;    // [blocks256][W+1] exclusive prefix over the 256-query blocks
+  uint32_t *pair_off;      // [W+1]
+  uint32_t *pair_cnt;      // [W+1] (entry W = novel keypoints)
+  uint32_t *host_pair_off; // mapped pinned mirrors (zero-copy result)
+  uint32_t *host_pair_cnt;
+  unsigned *type_ticket;   // CTAs of this type that are done, zero on entry, self-cleaning
+  unsigned *done_counter;  // types that are done
+  volatile unsigned long long *flag;
+  unsigned long long seq;
 };
 void assoc_launch(const AssocArgs &planar, const AssocArgs &point, cudaStream_t stream, Profiler &prof);
 
@@ -92,14 +106,8 @@ struct SegmentArgs {
   uint32_t *block_hist; // [blocks][W+1]
   uint32_t *pair_off;   // [W+1]
   uint32_t *pair_cnt;   // [W+1] (entry W = novel keypoints)
-  uint32_t *host_pair_off; // mapped pinned mirrors of the two arrays (zero-copy result)
-  uint32_t *host_pair_cnt;
-  unsigned *done_counter;  // zero on entry, self-cleaning
-  volatile unsigned long long *flag; // mapped pinned: set to `seq` once both types are written
-  unsigned long long seq;
   float *seg;           // segment base of the current slot: [9 or 6][kcap]
 };
-cudaError_t map_assoc_configure(size_t max_query_blocks, int W);
 void segment_build_launch(const SegmentArgs &planar, const SegmentArgs &point, cudaStream_t stream, Profiler &prof);
 
 struct CommitArgs {
@@ -131,7 +139,7 @@ void world_export_launch(const WorldExportArgs &a, cudaStream_t stream, Profiler
 
 // ---- stage 3 (linearize.cu, FMA allowed: tolerance class) ----
 constexpr int kLinThreads = 256;   // threads per CTA
-constexpr int kLinCluster = 8;     // CTAs per cluster = per scan pair
+constexpr int kLinCluster = 8;     // largest cluster (CTAs per scan pair)
 constexpr int kLinInlineTasks = 48; // pairs that travel in the kernel parameters (6 KB)
 
 struct LinTask { // one scan pair with at least one correspondence (128 B)
@@ -153,6 +161,7 @@ struct LinArgs {
   const float *seg_point;  // [W][6][kq_cap]
   const LinTask *tasks;    // device copy of the request when it does not fit the parameters
   int n_tasks;
+  int cluster;             // CTAs per pair for this launch: 1, 2, 4 or 8
   double inv_sigma2;
   double *out;             // [n_pairs][91] or [n_pairs]: mapped pinned host memory (zero-copy)
   volatile unsigned long long *flags; // [n_pairs] mapped pinned: set to `seq` when the pair is written

@@ -21,10 +21,11 @@
 // instead of 182 for the 91 entries) and the 13x13 block is recovered per pair as
 // sum_kl W_kl B_k^T B_l.
 //
-// Mapping.  One thread-block CLUSTER of 8 CTAs per scan pair: CTA r streams the r-th
-// eighth of the pair's planar and point correspondences, reduces its 2 x 28 moments
+// Mapping.  One thread-block CLUSTER per scan pair (8 CTAs when the request has few
+// pairs, down to 1 when it has thousands, so that one launch is about one wave): CTA r
+// streams the r-th share of the pair's planar and point correspondences, reduces its 2 x 28 moments
 // (butterfly-transpose warp reduction: 31 shuffles instead of 140), and leaves them
-// in its shared memory; after cluster.sync() CTA 0 gathers the eight partial sums
+// in its shared memory; after cluster.sync() CTA 0 gathers the partial sums
 // through distributed shared memory, expands the block and writes the 91 doubles
 // plus a per-pair sequence flag straight into mapped pinned host memory.  There
 // is no partial-sum traffic through global memory, no atomic, no second launch and
@@ -45,7 +46,6 @@ namespace {
 
 constexpr int kThreads = kLinThreads;
 constexpr int kWarps = kThreads / 32;
-constexpr int kCluster = kLinCluster;
 
 __device__ __forceinline__ void apply_rel(const double *rel, double x, double y, double z,
                                           double &qx, double &qy, double &qz) {
@@ -202,6 +202,7 @@ template <bool kErrorOnly>
 __device__ __forceinline__ void lin_cluster_body(const LinArgs &a, const LinTask &task) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
+  const int kCluster = (int)cluster.num_blocks(); // 1, 2, 4 or 8: chosen per launch
   const int tid = threadIdx.x;
   __shared__ double s_warp[kWarps][28];
   __shared__ double s_sum[2][28];  // [planar | point] moments of this CTA (error: [0][0])
@@ -295,7 +296,6 @@ __device__ __forceinline__ void lin_cluster_body(const LinArgs &a, const LinTask
       if (tid < 56) {
         const int which = tid / 28, e = tid % 28;
         double v = 0.0;
-#pragma unroll
         for (int r = 0; r < kCluster; ++r) v += *cluster.map_shared_rank(&s_sum[which][e], r);
         s_total[which][e] = v;
       }
@@ -317,7 +317,7 @@ __device__ __forceinline__ void lin_cluster_body(const LinArgs &a, const LinTask
 
 template <bool kErrorOnly>
 __global__ void __launch_bounds__(kLinThreads) lin_inline_kernel(LinArgs a, LinInline req) {
-  lin_cluster_body<kErrorOnly>(a, req.tasks[blockIdx.x / kLinCluster]);
+  lin_cluster_body<kErrorOnly>(a, req.tasks[blockIdx.x / a.cluster]);
 }
 
 template <bool kErrorOnly>
@@ -325,22 +325,23 @@ __global__ void __launch_bounds__(kLinThreads) lin_global_kernel(LinArgs a) {
   __shared__ LinTask s_task;
   if (threadIdx.x < sizeof(LinTask) / sizeof(unsigned long long))
     reinterpret_cast<unsigned long long *>(&s_task)[threadIdx.x] =
-        reinterpret_cast<const unsigned long long *>(a.tasks + blockIdx.x / kLinCluster)[threadIdx.x];
+        reinterpret_cast<const unsigned long long *>(a.tasks + blockIdx.x / a.cluster)[threadIdx.x];
   __syncthreads();
   lin_cluster_body<kErrorOnly>(a, s_task);
 }
 
 namespace {
 template <typename... Args>
-cudaError_t launch_cluster(void (*kernel)(Args...), int n_tasks, cudaStream_t stream, Args... args) {
+cudaError_t launch_cluster(void (*kernel)(Args...), int n_tasks, int cluster, cudaStream_t stream,
+                           Args... args) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(n_tasks * kLinCluster), 1, 1);
+  cfg.gridDim = dim3((unsigned)(n_tasks * cluster), 1, 1);
   cfg.blockDim = dim3(kLinThreads, 1, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kLinCluster;
+  attr[0].val.clusterDim.x = (unsigned)cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -356,11 +357,11 @@ cudaError_t linearize_launch(const LinArgs &a, const LinInline *inline_req, bool
   prof.begin(group);
   cudaError_t e;
   if (inline_req) {
-    e = error_only ? launch_cluster(lin_inline_kernel<true>, a.n_tasks, stream, a, *inline_req)
-                   : launch_cluster(lin_inline_kernel<false>, a.n_tasks, stream, a, *inline_req);
+    e = error_only ? launch_cluster(lin_inline_kernel<true>, a.n_tasks, a.cluster, stream, a, *inline_req)
+                   : launch_cluster(lin_inline_kernel<false>, a.n_tasks, a.cluster, stream, a, *inline_req);
   } else {
-    e = error_only ? launch_cluster(lin_global_kernel<true>, a.n_tasks, stream, a)
-                   : launch_cluster(lin_global_kernel<false>, a.n_tasks, stream, a);
+    e = error_only ? launch_cluster(lin_global_kernel<true>, a.n_tasks, a.cluster, stream, a)
+                   : launch_cluster(lin_global_kernel<false>, a.n_tasks, a.cluster, stream, a);
   }
   prof.end(group, 1);
   return e;

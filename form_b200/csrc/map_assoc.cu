@@ -171,11 +171,19 @@ void map_build_launch(const MapArgs &pa, const MapArgs &qa, cudaStream_t stream,
 // ---------------------------------------------------------------------------
 // nearest neighbour: one warp per query keypoint
 // ---------------------------------------------------------------------------
+// bin of a query: matched slot if dist^2 < max_dist^2 (matcher.hpp:104), else none.
+// Bin W counts the keypoints that insert_matches would add (map.tpp:161).
+__device__ __forceinline__ int match_bin(const MatchRec &m, double max_d2) {
+  return (m.slot != kNoSlot && m.dist_sqrd < max_d2) ? (int)m.slot : -1;
+}
+
+
 __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs qa) {
   const AssocArgs &a = blockIdx.y == 0 ? pa : qa;
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (q >= a.n_query) return;
+  const int nb = a.W + 1;
+  if (q < a.n_query) {
   double x, y, z;
   if (a.type == 0) load_xyz(reinterpret_cast<const PlanarRec *>(a.queries) + q, x, y, z);
   else load_xyz(reinterpret_cast<const PointRec *>(a.queries) + q, x, y, z);
@@ -280,76 +288,48 @@ __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs q
       m.k = src & 0xFFFFFFu;
     }
     a.match[q] = m;
+    // per-256-query histogram of the accepted matches by matched scan (+ novel count)
+    const int bin = match_bin(m, a.max_dist2);
+    if (bin >= 0) atomicAdd(&a.hist_cnt[(size_t)(q >> 8) * nb + bin], 1u);
+    if (m.dist_sqrd > a.min_dist2) atomicAdd(&a.hist_cnt[(size_t)(q >> 8) * nb + a.W], 1u);
   }
-}
+  } // q < n_query
 
-void assoc_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream, Profiler &prof) {
-  const int n = max(pa.n_query, qa.n_query);
-  if (n <= 0) return;
-  prof.begin(FORMGPU_KG_ASSOC_NN);
-  assoc_nn_kernel<<<dim3((n + 7) / 8, 2), 256, 0, stream>>>(pa, qa);
-  prof.end(FORMGPU_KG_ASSOC_NN, 1);
-}
-
-// ---------------------------------------------------------------------------
-// correspondence segment of the current scan: stable counting sort of the
-// accepted matches by the matched scan's slot (rule R6 order inside a pair)
-// ---------------------------------------------------------------------------
-// bin of a query: matched slot if dist^2 < max_dist^2 (matcher.hpp:104), else none.
-// Bin W counts the keypoints that insert_matches would add (map.tpp:161).
-__device__ __forceinline__ int match_bin(const MatchRec &m, double max_d2) {
-  return (m.slot != kNoSlot && m.dist_sqrd < max_d2) ? (int)m.slot : -1;
-}
-
-__global__ void __launch_bounds__(256) segment_hist_kernel(SegmentArgs pa, SegmentArgs qa) {
-  const SegmentArgs &a = blockIdx.y == 0 ? pa : qa;
-  __shared__ uint32_t s_hist[kMaxWindow + 1];
-  const int nb = a.W + 1;
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) s_hist[i] = 0;
+  // ---- the last CTA of this type scans the histogram and publishes the pair row ----
+  __shared__ bool s_last;
+  __shared__ uint32_t s_tot[kMaxWindow + 1], s_off[kMaxWindow + 1];
+  __threadfence();
   __syncthreads();
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if ((int)(blockIdx.x * blockDim.x) >= a.n_query) return;
-  if (q < a.n_query) {
-    const MatchRec m = a.match[q];
-    const int b = match_bin(m, a.max_dist2);
-    if (b >= 0) atomicAdd(&s_hist[b], 1u);
-    if (m.dist_sqrd > a.min_dist2) atomicAdd(&s_hist[a.W], 1u);
-  }
+  if (threadIdx.x == 0) s_last = atomicAdd(a.type_ticket, 1u) == gridDim.x - 1u;
   __syncthreads();
-  for (int i = threadIdx.x; i < nb; i += blockDim.x)
-    a.block_hist[(size_t)blockIdx.x * nb + i] = s_hist[i];
-}
-
-// one block per type: per bin exclusive prefix over the query blocks, then the pair row.
-// The [blocks][W+1] histogram is pulled into shared memory with coalesced loads first
-// (a read-modify-write loop over global memory serialises on every load).
-__global__ void __launch_bounds__(1024) segment_scan_kernel(SegmentArgs pa, SegmentArgs qa) {
-  const SegmentArgs &a = blockIdx.x == 0 ? pa : qa;
-  extern __shared__ uint32_t s_hist[]; // [nblocks][nb]
-  __shared__ uint32_t s_tot[kMaxWindow + 1];
-  const int nb = a.W + 1;
+  if (!s_last) return;
+  __threadfence();
   const int nblocks = (a.n_query + 255) / 256;
-  const int total = nblocks * nb;
-#pragma unroll 8
-  for (int i = threadIdx.x; i < total; i += blockDim.x) s_hist[i] = a.block_hist[i];
-  __syncthreads();
   for (int b = threadIdx.x; b < nb; b += blockDim.x) {
     uint32_t run = 0;
-    for (int blk = 0; blk < nblocks; ++blk) {
-      const uint32_t c = s_hist[blk * nb + b];
-      s_hist[blk * nb + b] = run;
-      run += c;
+    // tiles of 16 blocks: all loads of a tile are issued before its stores, so they
+    // overlap instead of serialising on the read-modify-write of hist_cnt
+    for (int blk0 = 0; blk0 < nblocks; blk0 += 16) {
+      uint32_t c[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        c[i] = blk0 + i < nblocks ? __ldcg(&a.hist_cnt[(size_t)(blk0 + i) * nb + b]) : 0u;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (blk0 + i < nblocks) {
+          a.hist_cnt[(size_t)(blk0 + i) * nb + b] = 0u; // self-cleaning for the next association
+          a.block_hist[(size_t)(blk0 + i) * nb + b] = run;
+          run += c[i];
+        }
+      }
     }
     s_tot[b] = run;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < total; i += blockDim.x) a.block_hist[i] = s_hist[i];
-  // exclusive prefix over the bins by one warp
-  __shared__ uint32_t s_off[kMaxWindow + 1];
-  if (threadIdx.x < 32) {
+  if (threadIdx.x < 32) { // exclusive prefix over the bins by one warp
     uint32_t run = 0;
     for (int base = 0; base < a.W; base += 32) {
-      const int b = base + threadIdx.x;
+      const int b = base + (int)threadIdx.x;
       const uint32_t c = b < a.W ? s_tot[b] : 0u;
       uint32_t incl = c;
       for (int o = 1; o < 32; o <<= 1) {
@@ -368,10 +348,10 @@ __global__ void __launch_bounds__(1024) segment_scan_kernel(SegmentArgs pa, Segm
     a.host_pair_off[b] = s_off[b];
     a.host_pair_cnt[b] = s_tot[b];
   }
-  // the counts reach the host without a memcpy: the caller spins on the flag
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    *a.type_ticket = 0u;
     const unsigned d = atomicAdd(a.done_counter, 1u);
     if (d == 1u) { // both types done
       *a.done_counter = 0u;
@@ -381,6 +361,20 @@ __global__ void __launch_bounds__(1024) segment_scan_kernel(SegmentArgs pa, Segm
   }
 }
 
+void assoc_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream, Profiler &prof) {
+  const int n = max(pa.n_query, qa.n_query);
+  if (n <= 0) return;
+  prof.begin(FORMGPU_KG_ASSOC_NN);
+  assoc_nn_kernel<<<dim3((n + 7) / 8, 2), 256, 0, stream>>>(pa, qa);
+  prof.end(FORMGPU_KG_ASSOC_NN, 1);
+}
+
+// ---------------------------------------------------------------------------
+// correspondence segment of the current scan: stable counting sort of the
+// accepted matches by the matched scan's slot (rule R6 order inside a pair).
+// Counting and the prefix sums are fused into the NN kernel above; this kernel
+// recomputes each query's stable rank inside its 256-query block and scatters.
+// ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) segment_scatter_kernel(SegmentArgs pa, SegmentArgs qa) {
   const SegmentArgs &a = blockIdx.y == 0 ? pa : qa;
   __shared__ uint32_t s_warp[8][kMaxWindow];
@@ -426,22 +420,14 @@ __global__ void __launch_bounds__(256) segment_scatter_kernel(SegmentArgs pa, Se
   }
 }
 
-cudaError_t map_assoc_configure(size_t max_query_blocks, int W) {
-  return cudaFuncSetAttribute(segment_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)(max_query_blocks * (W + 1) * sizeof(uint32_t)));
-}
-
 void segment_build_launch(const SegmentArgs &pa, const SegmentArgs &qa, cudaStream_t stream,
                           Profiler &prof) {
   const int n = max(pa.n_query, qa.n_query);
   if (n <= 0) return;
   prof.begin(FORMGPU_KG_SEGMENT);
   const dim3 g((n + 255) / 256, 2);
-  segment_hist_kernel<<<g, 256, 0, stream>>>(pa, qa);
-  const size_t scan_smem = (size_t)((n + 255) / 256) * (pa.W + 1) * sizeof(uint32_t);
-  segment_scan_kernel<<<2, 1024, scan_smem, stream>>>(pa, qa);
   segment_scatter_kernel<<<g, 256, 0, stream>>>(pa, qa);
-  prof.end(FORMGPU_KG_SEGMENT, 3);
+  prof.end(FORMGPU_KG_SEGMENT, 1);
 }
 
 // ---------------------------------------------------------------------------

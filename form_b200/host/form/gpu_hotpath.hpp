@@ -66,6 +66,18 @@ public:
     point.assign(m_point.begin(), m_point.begin() + nq);
   }
 
+  /// formgpu_extract into the adapter's own buffers without building vectors (what a
+  /// caller that owns its buffers pays): returns the counts, data stays in planar_buffer().
+  void extract_raw(const PointXYZf *scan, size_t n, uint64_t scan_idx, size_t &n_planar,
+                   size_t &n_point) {
+    check(formgpu_extract(m_ctx, reinterpret_cast<const formgpu_point4f *>(scan), n, scan_idx,
+                          reinterpret_cast<formgpu_planar_feat *>(m_planar.data()), m_planar.size(),
+                          &n_planar, reinterpret_cast<formgpu_point_feat *>(m_point.data()),
+                          m_point.size(), &n_point));
+  }
+  const std::vector<PlanarFeat> &planar_buffer() const { return m_planar; }
+  const std::vector<PointFeat> &point_buffer() const { return m_point; }
+
   /// Scan already resident in device memory; nothing is copied back.
   void extract_device(const void *scan_dev, size_t n, uint64_t scan_idx, size_t &n_planar,
                       size_t &n_point) {

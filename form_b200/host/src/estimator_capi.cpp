@@ -86,8 +86,18 @@ void *formhost_replay_ctx(void *r) {
 /// keypoints back, as Estimator::register_scan does.  Returns seconds, < 0 on error.
 double formhost_replay_run_host(void *r, size_t first, size_t last,
                                 const formgpu_point4f *const *scans) {
+  auto *rh = static_cast<ReplayHandle *>(r);
+  auto *gpu = static_cast<GpuHotPath *>(rh->backend.get());
   try {
-    return replay_run_host(static_cast<ReplayHandle *>(r), first, last, scans);
+    const auto t0 = std::chrono::steady_clock::now();
+    replay(*rh->trace, *rh->backend, first, last,
+           [&](uint64_t scan_idx, size_t &np, size_t &nq) {
+             // straight through formgpu_extract: host scan in, f64 keypoint structs out
+             gpu->extract_raw(reinterpret_cast<const PointXYZf *>(scans[scan_idx]),
+                              rh->points_per_scan, scan_idx, np, nq);
+           },
+           rh->points_per_scan, rh->stats);
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   } catch (const std::exception &e) {
     g_error = e.what();
     return -1.0;
