@@ -139,6 +139,7 @@ FORMGPU_SYMBOLS = {
     "formgpu_extract_debug": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _psz, _vp, _psz]),
     "formgpu_map_rebuild": (_i, [_vp, _vp, _sz]),
     "formgpu_associate": (_i, [_vp, _vp, _vp, _sz, _psz]),
+    "formgpu_associate_linearize": (_i, [_vp, _vp, _sz, _vp, _sz, _psz, _vp]),
     "formgpu_get_matches": (_i, [_vp, _i, _vp, _sz, _psz]),
     "formgpu_commit_scan": (_i, [_vp, _psz, _psz]),
     "formgpu_remove_scans": (_i, [_vp, _vp, _sz]),

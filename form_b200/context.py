@@ -105,6 +105,18 @@ class Context:
                                                 C.byref(n)))
         return out[: n.value].copy()
 
+    def associate_linearize(self, poses: np.ndarray):
+        """One round trip: Matcher::match at the current scan's pose in `poses`, then the
+        blocks of every non-empty pair (i, current scan).  Returns (counts, blocks)."""
+        poses = np.ascontiguousarray(poses, dtype=_capi.SCAN_POSE)
+        cap = max(self.params.max_window_scans, 1)
+        out = np.zeros(cap, dtype=_capi.PAIR_COUNT)
+        blocks = np.zeros((cap, 91))
+        n = C.c_size_t()
+        self._check(self._lib.formgpu_associate_linearize(self._h, _capi.ptr(poses), poses.shape[0],
+                                                          _capi.ptr(out), cap, C.byref(n), _capi.ptr(blocks)))
+        return out[: n.value].copy(), blocks[: n.value].copy()
+
     def matches(self, type_: int) -> np.ndarray:
         cap = self.max_planar if type_ == 0 else self.max_point
         out = np.zeros(cap, dtype=_capi.MATCH)

@@ -37,25 +37,21 @@ int ensure_upload(formgpu_ctx *ctx, size_t bytes) {
 int ensure_out(formgpu_ctx *ctx, size_t pairs) {
   if (pairs <= ctx->out_cap) return FORMGPU_OK;
   FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (ctx->h_out) cudaFreeHost(ctx->h_out);
-  if (ctx->h_pair_flags) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_pair_flags));
+  if (ctx->h_out) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_out));
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   ctx->h_out = nullptr;
-  ctx->h_pair_flags = nullptr;
   ctx->d_counters = nullptr;
   const size_t cap = next_pow2(pairs);
   // results are written by the kernels straight into this mapped pinned buffer
-  FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_out), cap * 91 * sizeof(double),
-                                  cudaHostAllocMapped));
-  FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(const_cast<unsigned long long **>(&ctx->h_pair_flags)),
-                                  cap * sizeof(unsigned long long), cudaHostAllocMapped));
-  for (size_t i = 0; i < cap; ++i) ctx->h_pair_flags[i] = 0;
+  FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(const_cast<unsigned long long **>(&ctx->h_out)),
+                                  cap * 182 * sizeof(unsigned long long), cudaHostAllocMapped));
+  for (size_t i = 0; i < cap * 182; ++i) ctx->h_out[i] = 0; // tag 0 is never used (seq starts at 1)
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_counters, cap + 8));
   FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, (cap + 8) * sizeof(unsigned), ctx->stream));
   FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->counter_cap = cap;
   ctx->out_cap = cap;
-  ctx->h_out_bytes = cap * 91 * sizeof(double);
+  ctx->h_out_bytes = cap * 182 * sizeof(unsigned long long);
   return FORMGPU_OK;
 }
 
@@ -156,8 +152,8 @@ static int create_impl(formgpu_ctx *ctx) {
   }
   ctx->prof.stream = ctx->stream;
   FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(const_cast<unsigned long long **>(&ctx->h_flags)),
-                                  8 * sizeof(unsigned long long), cudaHostAllocMapped));
-  for (int i = 0; i < 8; ++i) ctx->h_flags[i] = 0;
+                                  24 * sizeof(unsigned long long), cudaHostAllocMapped));
+  for (int i = 0; i < 24; ++i) ctx->h_flags[i] = 0;
 
   const size_t B = ctx->B, R = ctx->rows, W = ctx->W;
   // stage 1
@@ -216,14 +212,16 @@ static int create_impl(formgpu_ctx *ctx) {
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_match[1], ctx->kq_cap));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_seg_planar, W * 9 * ctx->kp_cap));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_seg_point, W * 6 * ctx->kq_cap));
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_block_hist[0], ((ctx->kp_cap + 255) / 256 + 1) * (W + 1)));
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_block_hist[1], ((ctx->kq_cap + 255) / 256 + 1) * (W + 1)));
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_pair, 4 * (W + 1)));
   for (int t = 0; t < 2; ++t) {
     const size_t n = ((t == 0 ? ctx->kp_cap : ctx->kq_cap) + 255) / 256 + 1;
-    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_hist_cnt[t], n * (W + 1)));
-    FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_hist_cnt[t], 0, n * (W + 1) * sizeof(uint32_t), ctx->stream));
+    ctx->hist_bytes[t] = n * (W + 1) * sizeof(uint32_t);
+    for (int b = 0; b < 2; ++b) {
+      FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_hist_cnt[b][t], n * (W + 1)));
+      FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_hist_cnt[b][t], 0, ctx->hist_bytes[t], ctx->stream));
+    }
   }
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_pair, 4 * (W + 1)));
+  FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_pair, 0, 4 * (W + 1) * sizeof(uint32_t), ctx->stream));
   ctx->h_pair_table.assign(W * W, PairEntry{0, 0, 0, 0});
   FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pair), 4 * (W + 1) * sizeof(uint32_t),
                                   cudaHostAllocMapped));
@@ -274,7 +272,7 @@ void formgpu_destroy(formgpu_ctx *ctx) {
   F(ctx->d_scan); F(ctx->d_valid_bits); F(ctx->d_planar_cols); F(ctx->d_planar_cnt);
   F(ctx->d_point_cols); F(ctx->d_point_cnt); F(ctx->d_normals); F(ctx->d_closest);
   F(ctx->d_keep_cnt); F(ctx->d_cur_counts);
-  for (int i = 0; i < 2; ++i) { F(ctx->d_cur_planar_buf[i]); F(ctx->d_cur_point_buf[i]); F(ctx->d_block_hist[i]); F(ctx->d_hist_cnt[i]); }
+  for (int i = 0; i < 2; ++i) { F(ctx->d_cur_planar_buf[i]); F(ctx->d_cur_point_buf[i]); F(ctx->d_hist_cnt[i][0]); F(ctx->d_hist_cnt[i][1]); }
   F(ctx->d_dbg_valid); F(ctx->d_dbg_pvalid); F(ctx->d_dbg_curv);
   F(ctx->d_store_planar); F(ctx->d_store_point);
   for (int t = 0; t < 2; ++t) {
@@ -286,8 +284,8 @@ void formgpu_destroy(formgpu_ctx *ctx) {
   F(ctx->d_seg_planar); F(ctx->d_seg_point); F(ctx->d_pair);
   F(ctx->d_partials); F(ctx->d_request); F(ctx->d_counters);
   if (ctx->h_flags) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_flags));
-  if (ctx->h_pair_flags) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_pair_flags));
-  H(ctx->h_counts); H(ctx->h_planar); H(ctx->h_point); H(ctx->h_upload); H(ctx->h_out);
+  H(ctx->h_counts); H(ctx->h_planar); H(ctx->h_point); H(ctx->h_upload);
+  if (ctx->h_out) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_out));
   H(ctx->h_pair);
   ctx->prof.destroy();
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -498,6 +496,22 @@ int formgpu_profile_read(formgpu_ctx *ctx, double ms[FORMGPU_KG_COUNT],
     ctx->prof.group[g] = GroupProf();
   }
   return FORMGPU_OK;
+}
+
+/* not part of the public header: timing experiments (profiles/microbench_calls.py) */
+const unsigned long long *formgpu_debug_timestamps(const formgpu_ctx *ctx) {
+  return ctx ? const_cast<const unsigned long long *>(ctx->h_flags) + 8 : nullptr;
+}
+
+uint64_t formgpu_debug_host_times(formgpu_ctx *ctx, double out[8]) {
+  if (!ctx) return 0;
+  for (int i = 0; i < 8; ++i) {
+    out[i] = ctx->dbg_host_us[i];
+    ctx->dbg_host_us[i] = 0;
+  }
+  const uint64_t n = ctx->dbg_host_calls;
+  ctx->dbg_host_calls = 0;
+  return n;
 }
 
 uint64_t formgpu_launch_count(const formgpu_ctx *ctx) { return ctx ? ctx->prof.total_launches : 0; }

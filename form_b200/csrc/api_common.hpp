@@ -44,6 +44,16 @@ inline int find_slot(const formgpu_ctx *ctx, uint64_t scan) {
 /// stream state every few thousand polls so a faulted kernel cannot hang the caller.
 int wait_flag(formgpu_ctx *ctx, int which, unsigned long long seq);
 
+/// Stage 3 building blocks (api_stage3.cu), also used by the fused association call.
+void relative_pose(const formgpu_pose &Ti, const formgpu_pose &Tj, double rel[12]);
+/// Launch one cluster per task (no wait).  Assigns and returns the sequence number.
+int lin_launch(formgpu_ctx *ctx, const std::vector<LinTask> &tasks, bool error_only,
+               unsigned long long *seq_out);
+/// Spin until every word of the listed pairs carries the call's tag, decoding them into
+/// dst (per_pair = 91 doubles for blocks, 1 for errors; dst[k] belongs to out_indices[k]).
+int lin_wait(formgpu_ctx *ctx, const int *out_indices, size_t n, unsigned long long seq,
+             size_t per_pair, double *dst);
+
 /// Ensure the pinned upload / result staging buffers are large enough.
 int ensure_upload(formgpu_ctx *ctx, size_t bytes);
 int ensure_out(formgpu_ctx *ctx, size_t pairs);

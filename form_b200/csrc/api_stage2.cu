@@ -131,8 +131,13 @@ int formgpu_map_rebuild(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
   return FORMGPU_OK;
 }
 
-int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k, formgpu_pair_count *counts_out,
-                      size_t counts_cap, size_t *n_counts) {
+// Matcher::match for both types; when `poses` is given, the linearisation of every pair
+// (i, current scan) at those poses is queued right behind the association - its ranges are
+// read on the device from the pair row the scatter kernel has just written - so the caller
+// pays one device round trip instead of two per ICP iteration.
+static int associate_impl(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_scan_pose *poses,
+                          size_t n_poses, formgpu_pair_count *counts_out, size_t counts_cap,
+                          size_t *n_counts, double *out91) {
   if (!ctx) return FORMGPU_ERR_INVALID_ARG;
   if (!pose_k || !n_counts)
     return fail(ctx, FORMGPU_ERR_INVALID_ARG, "formgpu_associate: null argument");
@@ -145,9 +150,51 @@ int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k, formgpu_pair
   ProfScope scope(ctx);
 
   const int nq[2] = {ctx->cur_n[0], ctx->cur_n[1]};
+  // fused linearisation: one dynamic task per window scan that has a pose (ascending scan
+  // id = the order of the counts returned below)
+  const bool fused = poses != nullptr && out91 != nullptr && (nq[0] > 0 || nq[1] > 0);
+  static thread_local std::vector<LinTask> lin_tasks;
+  static thread_local std::vector<int> lin_slots;
+  unsigned long long lin_seq = 0;
+  lin_tasks.clear();
+  lin_slots.clear();
+  if (fused) {
+    int pk = -1;
+    std::vector<int> pose_idx(W, -1);
+    for (size_t p = 0; p < n_poses; ++p) {
+      const int s = find_slot(ctx, poses[p].scan);
+      if (s >= 0) pose_idx[s] = (int)p;
+      if (poses[p].scan == ctx->cur_scan) pk = (int)p;
+    }
+    if (pk < 0) return fail(ctx, FORMGPU_ERR_INVALID_ARG, "associate_linearize: no pose for the current scan");
+    std::vector<int> order;
+    for (int i = 0; i < W; ++i)
+      if (ctx->slot_used[i] && i != slot_k && pose_idx[i] >= 0) order.push_back(i);
+    std::sort(order.begin(), order.end(),
+              [&](int a, int b) { return ctx->slot_scan[a] < ctx->slot_scan[b]; });
+    const int rc = ensure_out(ctx, order.size() + 1);
+    if (rc) return rc;
+    for (size_t n = 0; n < order.size(); ++n) {
+      LinTask t{};
+      relative_pose(poses[pose_idx[order[n]]].pose, poses[pk].pose, t.rel);
+      t.slot_j = slot_k;
+      t.out_index = (int)n;
+      t.dyn_slot_i_plus1 = (uint32_t)order[n] + 1u;
+      lin_tasks.push_back(t);
+      lin_slots.push_back(order[n]);
+    }
+  }
   if (nq[0] > 0 || nq[1] > 0) {
+    // per type: the counter buffer of this association (already cleared).  A type without
+    // keypoints keeps its buffers untouched so that a stale match set stays committable.
+    int hbuf[2];
+    for (int t = 0; t < 2; ++t) {
+      hbuf[t] = nq[t] > 0 ? (ctx->hist_cur[t] ^ 1) : ctx->hist_cur[t];
+      ctx->hist_cur[t] = hbuf[t];
+    }
     AssocArgs aa[2];
     SegmentArgs sa[2];
+    const unsigned long long assoc_seq = ++ctx->seq; // published by the scatter kernel
     for (int t = 0; t < 2; ++t) {
       const void *queries = t == 0 ? (const void *)ctx->d_cur_planar : (const void *)ctx->d_cur_point;
       const size_t kcap = t == 0 ? ctx->kp_cap : ctx->kq_cap;
@@ -165,16 +212,7 @@ int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k, formgpu_pair
       aa[t].W = W;
       aa[t].max_dist2 = ctx->P.max_dist_matching * ctx->P.max_dist_matching; // matcher.hpp:82
       aa[t].min_dist2 = ctx->P.min_dist_map * ctx->P.min_dist_map;           // map.tpp:158
-      aa[t].hist_cnt = ctx->d_hist_cnt[t];
-      aa[t].block_hist = ctx->d_block_hist[t];
-      aa[t].pair_off = ctx->d_pair + (size_t)(2 * t) * (W + 1);
-      aa[t].pair_cnt = ctx->d_pair + (size_t)(2 * t + 1) * (W + 1);
-      aa[t].host_pair_off = ctx->h_pair + (size_t)(2 * t) * (W + 1);
-      aa[t].host_pair_cnt = ctx->h_pair + (size_t)(2 * t + 1) * (W + 1);
-      aa[t].type_ticket = ctx->d_counters + ctx->counter_cap + 3 + t;
-      aa[t].done_counter = ctx->d_counters + ctx->counter_cap + 1;
-      aa[t].flag = ctx->h_flags + 1;
-      aa[t].seq = ctx->seq + 1;
+      aa[t].hist_cnt = ctx->d_hist_cnt[hbuf[t]][t];
       sa[t].type = t;
       sa[t].W = W;
       sa[t].n_query = nq[t];
@@ -184,19 +222,30 @@ int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k, formgpu_pair
       sa[t].queries = queries;
       sa[t].store = t == 0 ? (const void *)ctx->d_store_planar : (const void *)ctx->d_store_point;
       sa[t].match = ctx->d_match[t];
-      sa[t].block_hist = ctx->d_block_hist[t];
-      sa[t].pair_off = ctx->d_pair + (size_t)(2 * t) * (W + 1);
-      sa[t].pair_cnt = ctx->d_pair + (size_t)(2 * t + 1) * (W + 1);
+      sa[t].hist_cnt = ctx->d_hist_cnt[hbuf[t]][t];
+      sa[t].hist_next = ctx->d_hist_cnt[hbuf[t] ^ 1][t];
+      sa[t].hist_bytes = nq[t] > 0 ? ctx->hist_bytes[t] : 0;
+      sa[t].host_pair_off = ctx->h_pair + (size_t)(2 * t) * (W + 1);
+      sa[t].host_pair_cnt = ctx->h_pair + (size_t)(2 * t + 1) * (W + 1);
+      sa[t].dev_pair_off = ctx->d_pair + (size_t)(2 * t) * (W + 1);
+      sa[t].dev_pair_cnt = ctx->d_pair + (size_t)(2 * t + 1) * (W + 1);
+      sa[t].done_counter = ctx->d_counters + ctx->counter_cap + 1;
+      sa[t].flag = ctx->h_flags + 1;
+      sa[t].seq = assoc_seq;
       sa[t].seg = t == 0 ? ctx->d_seg_planar + (size_t)slot_k * 9 * kcap
                          : ctx->d_seg_point + (size_t)slot_k * 6 * kcap;
     }
     assoc_launch(aa[0], aa[1], ctx->stream, ctx->prof);
     segment_build_launch(sa[0], sa[1], ctx->stream, ctx->prof);
     FORMGPU_CUDA(ctx, cudaGetLastError());
-    // the counts arrive through mapped memory as soon as the NN kernel's last CTA is
-    // done; the scatter kernel keeps running behind (later calls are ordered on the
-    // same stream)
-    const int w = wait_flag(ctx, 1, ++ctx->seq);
+    if (fused) {
+      const int rc = lin_launch(ctx, lin_tasks, false, &lin_seq);
+      if (rc) return rc;
+    }
+    // the counts arrive through mapped memory as soon as CTA 0 of the scatter kernel
+    // has summed the counters; the rest of the scatter keeps running behind (later
+    // calls are ordered on the same stream)
+    const int w = wait_flag(ctx, 1, assoc_seq);
     if (w) return w;
     for (int t = 0; t < 2; ++t) {
       if (nq[t] == 0) continue; // Matcher::match returns early, state stays (matcher.hpp:72-74)
@@ -216,6 +265,7 @@ int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k, formgpu_pair
       ctx->match_scan[t] = ctx->cur_scan;
       ctx->match_queries[t] = t == 0 ? (const void *)ctx->d_cur_planar : (const void *)ctx->d_cur_point;
       ctx->match_novel[t] = cnt[W];
+      ctx->match_hist[t] = ctx->d_hist_cnt[hbuf[t]][t];
     }
   }
   // non-empty pairs of the current scan, ascending scan id (rule R7)
@@ -231,7 +281,47 @@ int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k, formgpu_pair
   if (out.size() > counts_cap || (!counts_out && !out.empty()))
     return fail(ctx, FORMGPU_ERR_CAPACITY, "formgpu_associate: counts_out too small");
   if (!out.empty()) std::memcpy(counts_out, out.data(), out.size() * sizeof(formgpu_pair_count));
+  if (out91) {
+    if (fused) {
+      // the blocks of the non-empty pairs, in the order of `out`
+      std::vector<int> idx;
+      for (const auto &c : out) {
+        const int s = find_slot(ctx, c.i);
+        const auto it = std::find(lin_slots.begin(), lin_slots.end(), s);
+        if (it == lin_slots.end())
+          return fail(ctx, FORMGPU_ERR_INVALID_ARG, "associate_linearize: no pose for a matched scan");
+        idx.push_back((int)(it - lin_slots.begin()));
+      }
+      const int rc = lin_wait(ctx, idx.data(), idx.size(), lin_seq, 91, out91);
+      if (rc) return rc;
+    } else if (!out.empty()) {
+      // nothing was matched in this call (no keypoints): linearise what is there
+      std::vector<formgpu_pair> pairs;
+      for (const auto &c : out) pairs.push_back({c.i, ctx->cur_scan});
+      return formgpu_linearize(ctx, pairs.data(), pairs.size(), poses, n_poses, out91);
+    }
+  }
   return FORMGPU_OK;
+}
+
+int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k, formgpu_pair_count *counts_out,
+                      size_t counts_cap, size_t *n_counts) {
+  return associate_impl(ctx, pose_k, nullptr, 0, counts_out, counts_cap, n_counts, nullptr);
+}
+
+int formgpu_associate_linearize(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t n_poses,
+                                formgpu_pair_count *counts_out, size_t counts_cap, size_t *n_counts,
+                                double *out91) {
+  if (!ctx) return FORMGPU_ERR_INVALID_ARG;
+  if (!poses || !out91)
+    return fail(ctx, FORMGPU_ERR_INVALID_ARG, "formgpu_associate_linearize: null argument");
+  if (!ctx->have_current) return fail(ctx, FORMGPU_ERR_STATE, "formgpu_associate_linearize: no current scan");
+  const formgpu_pose *pose_k = nullptr;
+  for (size_t p = 0; p < n_poses; ++p)
+    if (poses[p].scan == ctx->cur_scan) pose_k = &poses[p].pose;
+  if (!pose_k)
+    return fail(ctx, FORMGPU_ERR_INVALID_ARG, "formgpu_associate_linearize: no pose for the current scan");
+  return associate_impl(ctx, pose_k, poses, n_poses, counts_out, counts_cap, n_counts, out91);
 }
 
 int formgpu_get_matches(formgpu_ctx *ctx, int type, formgpu_match *out, size_t cap, size_t *n) {
@@ -282,7 +372,7 @@ int formgpu_commit_scan(formgpu_ctx *ctx, size_t *n_planar_added, size_t *n_poin
     ca[t].min_dist2 = ctx->P.min_dist_map * ctx->P.min_dist_map;
     ca[t].queries = ctx->match_queries[t];
     ca[t].match = ctx->d_match[t];
-    ca[t].block_hist = ctx->d_block_hist[t];
+    ca[t].hist_cnt = ctx->match_hist[t];
     ca[t].store_dst = t == 0 ? (void *)(ctx->d_store_planar + (size_t)slot * kcap)
                              : (void *)(ctx->d_store_point + (size_t)slot * kcap);
     ca[t].dst_count = (uint32_t)ctx->store_n[t][slot];

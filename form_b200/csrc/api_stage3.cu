@@ -2,10 +2,12 @@
 #include "api_common.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 using namespace formgpu;
 
-namespace {
+namespace formgpu {
 
 // relative pose of scan j seen from scan i: R_i^T R_j and R_i^T (t_j - t_i)
 void relative_pose(const formgpu_pose &Ti, const formgpu_pose &Tj, double rel[12]) {
@@ -16,11 +18,96 @@ void relative_pose(const formgpu_pose &Ti, const formgpu_pose &Tj, double rel[12
   for (int a = 0; a < 3; ++a) rel[9 + a] = Ti.R[a] * d[0] + Ti.R[3 + a] * d[1] + Ti.R[6 + a] * d[2];
 }
 
-// Shared body of formgpu_linearize / formgpu_error.  Builds one task per pair that has
-// correspondences, launches one cluster per task, then polls the per-pair flags the
-// kernel raises in mapped host memory.
+int lin_launch(formgpu_ctx *ctx, const std::vector<LinTask> &tasks, bool error_only,
+               unsigned long long *seq_out) {
+  LinArgs a{};
+  a.kp_cap = ctx->kp_cap;
+  a.kq_cap = ctx->kq_cap;
+  a.seg_planar = ctx->d_seg_planar;
+  a.seg_point = ctx->d_seg_point;
+  a.pair_row = ctx->d_pair;
+  a.W = ctx->W;
+  a.n_tasks = (int)tasks.size();
+  // CTAs per pair: as many as keep the launch within about one wave (2 CTAs per SM)
+  a.cluster = kLinCluster;
+  while (a.cluster > 1 && (size_t)a.cluster * tasks.size() > 2 * 148) a.cluster >>= 1;
+  if (const char *dbg = std::getenv("FORMGPU_DEBUG_CLUSTER")) a.cluster = std::max(1, std::atoi(dbg));
+  a.debug_flags = 0;
+  if (const char *dbg = std::getenv("FORMGPU_DEBUG_FLAGS")) a.debug_flags = std::atoi(dbg);
+  a.debug_ts = const_cast<unsigned long long *>(ctx->h_flags) + 8; // [16] behind the flags
+  a.inv_sigma2 = 1.0 / (ctx->P.sigma * ctx->P.sigma);
+  a.out = ctx->h_out;
+  a.seq = ++ctx->seq;
+  *seq_out = a.seq;
+  if (tasks.empty()) return FORMGPU_OK;
+  if ((int)tasks.size() <= kLinInlineTasks) {
+    // the whole request rides in the kernel parameters: no upload, no dependent loads
+    static thread_local LinInline inl;
+    std::memcpy(inl.tasks, tasks.data(), tasks.size() * sizeof(LinTask));
+    FORMGPU_CUDA(ctx, linearize_launch(a, &inl, error_only, ctx->stream, ctx->prof));
+  } else {
+    const size_t bytes = tasks.size() * sizeof(LinTask);
+    FORMGPU_CUDA(ctx, cudaEventSynchronize(ctx->ev_upload));
+    const int rc = ensure_upload(ctx, bytes);
+    if (rc) return rc;
+    std::memcpy(ctx->h_upload, tasks.data(), bytes);
+    FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_request, ctx->h_upload, bytes, cudaMemcpyHostToDevice,
+                                      ctx->stream));
+    FORMGPU_CUDA(ctx, cudaEventRecord(ctx->ev_upload, ctx->stream));
+    a.tasks = static_cast<const LinTask *>(ctx->d_request);
+    FORMGPU_CUDA(ctx, linearize_launch(a, nullptr, error_only, ctx->stream, ctx->prof));
+  }
+  return FORMGPU_OK;
+}
+
+int lin_wait(formgpu_ctx *ctx, const int *out_indices, size_t n, unsigned long long seq,
+             size_t per_pair, double *dst) {
+  // Each 8-byte word = 32 bits of payload | tag << 32; a word is fresh once its tag is
+  // this call's.  Pairs (and words) complete in no particular order.
+  const unsigned long long tag = seq & 0xffffffffull;
+  const size_t words = 2 * per_pair; // words per pair in h_out: 182 (blocks) or 2 (errors)
+  unsigned spins = 0;
+  for (size_t k = 0; k < n; ++k) {
+    volatile unsigned long long *w = ctx->h_out + (size_t)out_indices[k] * words;
+    for (size_t e = 0; e < per_pair; ++e) {
+      unsigned long long lo, hi;
+      for (;;) {
+        lo = w[2 * e];
+        hi = w[2 * e + 1];
+        if ((lo >> 32) == tag && (hi >> 32) == tag) break;
+        if ((++spins & 0xfff) == 0) {
+          const cudaError_t err = cudaStreamQuery(ctx->stream);
+          if (err == cudaSuccess) {
+            lo = w[2 * e];
+            hi = w[2 * e + 1];
+            if ((lo >> 32) == tag && (hi >> 32) == tag) break;
+            return fail(ctx, FORMGPU_ERR_STATE, "linearize kernel finished without publishing a pair");
+          }
+          if (err != cudaErrorNotReady)
+            return fail(ctx, FORMGPU_ERR_CUDA, std::string("linearize kernel failed: ") + cudaGetErrorString(err));
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      const unsigned long long bits = (lo & 0xffffffffull) | (hi << 32);
+      std::memcpy(&dst[k * per_pair + e], &bits, sizeof(double));
+    }
+  }
+  return FORMGPU_OK;
+}
+
+} // namespace formgpu
+
+namespace {
+
+// Shared body of formgpu_linearize / formgpu_error: one task per pair that has
+// correspondences, one cluster per task, then poll the per-pair flags the kernel raises
+// in mapped host memory.
 int run(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs, const formgpu_scan_pose *poses,
         size_t n_poses, bool error_only, double *out) {
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
   const int W = ctx->W;
   const size_t per_pair = error_only ? 1 : 91;
   std::vector<int> pose_idx(W, -1);
@@ -32,13 +119,15 @@ int run(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs, const formg
   if (rc) return rc;
 
   static thread_local std::vector<LinTask> tasks;
+  static thread_local std::vector<int> indices;
   tasks.clear();
+  indices.clear();
   for (size_t p = 0; p < n_pairs; ++p) {
     const int si = find_slot(ctx, pairs[p].i), sj = find_slot(ctx, pairs[p].j);
     const PairEntry *e = (si >= 0 && sj >= 0) ? &ctx->h_pair_table[(size_t)sj * W + si] : nullptr;
     if (!e || (e->n_planar == 0 && e->n_point == 0)) {
       // no correspondences (or unknown scans): zero block, never touched by a CTA
-      std::memset(ctx->h_out + p * per_pair, 0, per_pair * sizeof(double));
+      std::memset(out + p * per_pair, 0, per_pair * sizeof(double));
       continue;
     }
     if (pose_idx[si] < 0 || pose_idx[sj] < 0)
@@ -54,60 +143,25 @@ int run(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs, const formg
     t.slot_j = sj;
     t.out_index = (int)p;
     tasks.push_back(t);
+    indices.push_back((int)p);
   }
-
-  LinArgs a{};
-  a.kp_cap = ctx->kp_cap;
-  a.kq_cap = ctx->kq_cap;
-  a.seg_planar = ctx->d_seg_planar;
-  a.seg_point = ctx->d_seg_point;
-  a.n_tasks = (int)tasks.size();
-  // CTAs per pair: as many as keep the launch within about one wave (2 CTAs per SM)
-  a.cluster = kLinCluster;
-  while (a.cluster > 1 && (size_t)a.cluster * tasks.size() > 2 * 148) a.cluster >>= 1;
-  a.inv_sigma2 = 1.0 / (ctx->P.sigma * ctx->P.sigma);
-  a.out = ctx->h_out;
-  a.flags = ctx->h_pair_flags;
-  a.seq = ++ctx->seq;
-  if (!tasks.empty()) {
-    if ((int)tasks.size() <= kLinInlineTasks) {
-      // the whole request rides in the kernel parameters: no upload, no dependent loads
-      static thread_local LinInline inl;
-      std::memcpy(inl.tasks, tasks.data(), tasks.size() * sizeof(LinTask));
-      FORMGPU_CUDA(ctx, linearize_launch(a, &inl, error_only, ctx->stream, ctx->prof));
-    } else {
-      const size_t bytes = tasks.size() * sizeof(LinTask);
-      FORMGPU_CUDA(ctx, cudaEventSynchronize(ctx->ev_upload));
-      rc = ensure_upload(ctx, bytes);
-      if (rc) return rc;
-      std::memcpy(ctx->h_upload, tasks.data(), bytes);
-      FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_request, ctx->h_upload, bytes, cudaMemcpyHostToDevice,
-                                        ctx->stream));
-      FORMGPU_CUDA(ctx, cudaEventRecord(ctx->ev_upload, ctx->stream));
-      a.tasks = static_cast<const LinTask *>(ctx->d_request);
-      FORMGPU_CUDA(ctx, linearize_launch(a, nullptr, error_only, ctx->stream, ctx->prof));
-    }
-    // wait for every pair's flag (they complete in no particular order)
-    unsigned spins = 0;
-    for (const LinTask &t : tasks) {
-      volatile unsigned long long *f = ctx->h_pair_flags + t.out_index;
-      while (*f != a.seq) {
-        if ((++spins & 0xfff) == 0) {
-          const cudaError_t e = cudaStreamQuery(ctx->stream);
-          if (e == cudaSuccess) {
-            if (*f == a.seq) break;
-            return fail(ctx, FORMGPU_ERR_STATE, "linearize kernel finished without publishing a pair");
-          }
-          if (e != cudaErrorNotReady)
-            return fail(ctx, FORMGPU_ERR_CUDA, std::string("linearize kernel failed: ") + cudaGetErrorString(e));
-        }
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
-      }
-    }
-  }
-  std::memcpy(out, ctx->h_out, n_pairs * per_pair * sizeof(double));
+  unsigned long long seq = 0;
+  const auto t1 = clk::now();
+  rc = lin_launch(ctx, tasks, error_only, &seq);
+  if (rc) return rc;
+  const auto t2 = clk::now();
+  // decode into a dense scratch, then scatter to the pairs' positions
+  static thread_local std::vector<double> dense;
+  dense.resize(indices.size() * per_pair);
+  rc = lin_wait(ctx, indices.data(), indices.size(), seq, per_pair, dense.data());
+  if (rc) return rc;
+  const auto t3 = clk::now();
+  ctx->dbg_host_us[0] += std::chrono::duration<double, std::micro>(t1 - t0).count(); // build
+  ctx->dbg_host_us[1] += std::chrono::duration<double, std::micro>(t2 - t1).count(); // launch API
+  ctx->dbg_host_us[2] += std::chrono::duration<double, std::micro>(t3 - t2).count(); // wait
+  ctx->dbg_host_calls += 1;
+  for (size_t k = 0; k < indices.size(); ++k)
+    std::memcpy(out + (size_t)indices[k] * per_pair, dense.data() + k * per_pair, per_pair * sizeof(double));
   return FORMGPU_OK;
 }
 

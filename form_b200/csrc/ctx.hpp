@@ -164,9 +164,9 @@ struct formgpu_ctx {
   formgpu::PointRec *h_point = nullptr;   // kq_cap
   void *h_upload = nullptr;              // request staging (poses, pairs, chunks)
   size_t h_upload_bytes = 0;
-  double *h_out = nullptr; // results (91 * pairs), mapped: written by the kernels
+  // results, mapped pinned, written by the kernels as sequence-tagged words (182 per pair)
+  volatile unsigned long long *h_out = nullptr;
   size_t h_out_bytes = 0;
-  volatile unsigned long long *h_pair_flags = nullptr; // per-pair completion flags, mapped
 
   // ---- current scan ----
   bool have_current = false;
@@ -213,10 +213,14 @@ struct formgpu_ctx {
   uint32_t match_novel[2] = {0, 0};   // keypoints insert_matches would append
   float *d_seg_planar = nullptr; // [W][9][kp_cap]
   float *d_seg_point = nullptr;  // [W][6][kq_cap]
-  uint32_t *d_block_hist[2] = {nullptr, nullptr}; // [blocks][W+1] prefix per 256-query block
-  uint32_t *d_hist_cnt[2] = {nullptr, nullptr};   // [blocks][W+1] atomic counters (self-cleaning)
-  uint32_t *d_pair = nullptr;     // [type][off|cnt][W+1]
-  uint32_t *h_pair = nullptr;     // pinned mirror of d_pair
+  // [ping-pong][blocks256][W+1] match counters per type: the NN kernel fills one buffer
+  // while the other is being cleared for the next association
+  uint32_t *d_hist_cnt[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  size_t hist_bytes[2] = {0, 0};
+  int hist_cur[2] = {0, 0};                        // per type: buffer used by its last association
+  const uint32_t *match_hist[2] = {nullptr, nullptr}; // counters the stored matches refer to
+  uint32_t *h_pair = nullptr;     // mapped pinned [type][off|cnt][W+1], written by the scatter kernel
+  uint32_t *d_pair = nullptr;     // device copy (read by a linearisation queued behind the association)
   std::vector<formgpu::PairEntry> h_pair_table; // host mirror [W(k)][W(i)]
 
   // ---- zero-copy completion signalling ----
@@ -235,4 +239,6 @@ struct formgpu_ctx {
 
   // ---- instrumentation ----
   formgpu::Profiler prof;
+  double dbg_host_us[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // host-side phase timers (experiments)
+  uint64_t dbg_host_calls = 0;
 };

@@ -76,20 +76,10 @@ struct AssocArgs {
   const WorldPoint *world;
   const uint32_t *world_src;
   MatchRec *match;
-  // fused histogram + scan (the last CTA of a type turns the per-256-query bin counts
-  // into the offsets the scatter and commit kernels use, and publishes the pair row)
+  // fused histogram: matches per (256-query block, matched slot), entry W = novel keypoints
   int W;
   double max_dist2, min_dist2;
-  uint32_t *hist_cnt;      // [blocks256][W+1] atomic counters, zero on entry, self-cleaning
-  uint32_t *block_hist;    // [blocks256][W+1] exclusive prefix over the 256-query blocks
-  uint32_t *pair_off;      // [W+1]
-  uint32_t *pair_cnt;      // [W+1] (entry W = novel keypoints)
-  uint32_t *host_pair_off; // mapped pinned mirrors (zero-copy result)
-  uint32_t *host_pair_cnt;
-  unsigned *type_ticket;   // CTAs of this type that are done, zero on entry, self-cleaning
-  unsigned *done_counter;  // types that are done
-  volatile unsigned long long *flag;
-  unsigned long long seq;
+  uint32_t *hist_cnt;      // [blocks256][W+1] atomic counters, zero on entry
 };
 void assoc_launch(const AssocArgs &planar, const AssocArgs &point, cudaStream_t stream, Profiler &prof);
 
@@ -103,9 +93,16 @@ struct SegmentArgs {
   const void *queries;  // current scan keypoints
   const void *store;    // keypoint store
   const MatchRec *match;
-  uint32_t *block_hist; // [blocks][W+1]
-  uint32_t *pair_off;   // [W+1]
-  uint32_t *pair_cnt;   // [W+1] (entry W = novel keypoints)
+  const uint32_t *hist_cnt; // [blocks256][W+1] counters filled by the NN kernel
+  uint32_t *hist_next;      // the other counter buffer, cleared after this launch
+  size_t hist_bytes;
+  uint32_t *host_pair_off;  // [W+1] mapped pinned: start of every pair in the segment
+  uint32_t *host_pair_cnt;  // [W+1] mapped pinned: counts (entry W = novel keypoints)
+  uint32_t *dev_pair_off;   // device copies for a linearisation queued right behind
+  uint32_t *dev_pair_cnt;
+  unsigned *done_counter;   // zero on entry, self-cleaning
+  volatile unsigned long long *flag; // mapped pinned: set to `seq` once both types are published
+  unsigned long long seq;
   float *seg;           // segment base of the current slot: [9 or 6][kcap]
 };
 void segment_build_launch(const SegmentArgs &planar, const SegmentArgs &point, cudaStream_t stream, Profiler &prof);
@@ -117,7 +114,7 @@ struct CommitArgs {
   double min_dist2;
   const void *queries;
   const MatchRec *match;
-  const uint32_t *block_hist;
+  const uint32_t *hist_cnt; // counters of the association the matches come from
   void *store_dst;   // store slot base of the scan being appended to
   uint32_t dst_count; // keypoints already stored there
 };
@@ -147,7 +144,9 @@ struct LinTask { // one scan pair with at least one correspondence (128 B)
   uint32_t off_planar, n_planar, off_point, n_point; // ranges inside the segment of slot_j
   int slot_j;
   int out_index;       // position of the pair in the caller's list
-  uint32_t pad[2];
+  uint32_t dyn_slot_i_plus1; // != 0: the ranges are read from the device pair row of slot_i
+                             // (association and linearisation queued back to back)
+  uint32_t pad;
 };
 static_assert(sizeof(LinTask) == 128, "LinTask size");
 
@@ -160,11 +159,17 @@ struct LinArgs {
   const float *seg_planar; // [W][9][kp_cap]
   const float *seg_point;  // [W][6][kq_cap]
   const LinTask *tasks;    // device copy of the request when it does not fit the parameters
+  const uint32_t *pair_row; // device [type][off|cnt][W+1] written by the last association
+  int W;
   int n_tasks;
   int cluster;             // CTAs per pair for this launch: 1, 2, 4 or 8
+  int debug_flags;         // timing experiments only: 1 = skip system fence, 2 = skip expansion,
+                           // 4 = record %globaltimer checkpoints of pair 0 into debug_ts
+  unsigned long long *debug_ts; // [16] mapped pinned
   double inv_sigma2;
-  double *out;             // [n_pairs][91] or [n_pairs]: mapped pinned host memory (zero-copy)
-  volatile unsigned long long *flags; // [n_pairs] mapped pinned: set to `seq` when the pair is written
+  // mapped pinned host memory (zero-copy), sequence-tagged words: [n_pairs][182] for
+  // blocks, [n_pairs][2] for errors; word = 32 bits of payload | (seq & 0xffffffff) << 32
+  volatile unsigned long long *out;
   unsigned long long seq;
 };
 cudaError_t linearize_launch(const LinArgs &a, const LinInline *inline_req, bool error_only,

@@ -27,9 +27,10 @@
 // (butterfly-transpose warp reduction: 31 shuffles instead of 140), and leaves them
 // in its shared memory; after cluster.sync() CTA 0 gathers the partial sums
 // through distributed shared memory, expands the block and writes the 91 doubles
-// plus a per-pair sequence flag straight into mapped pinned host memory.  There
-// is no partial-sum traffic through global memory, no atomic, no second launch and
-// no device->host memcpy.  Small requests travel in the kernel parameters (with
+// straight into mapped pinned host memory as sequence-tagged words (32 bits of payload
+// + 32 bits of tag per aligned 8-byte store), which the host polls.  There is no
+// partial-sum traffic through global memory, no atomic, no second launch, no
+// device->host memcpy and no system-wide fence.  Small requests travel in the kernel parameters (with
 // the relative poses precomputed by the host), so the first instruction that
 // touches memory is already a correspondence load.  The partition and every
 // reduction order are fixed: results are run-to-run deterministic.
@@ -43,6 +44,17 @@ namespace cg = cooperative_groups;
 namespace formgpu {
 
 namespace {
+
+__device__ __forceinline__ unsigned long long globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define LIN_TS(k)                                                                          \
+  do {                                                                                     \
+    if ((a.debug_flags & 4) && task.out_index == 0 && rank == 0 && tid == 0)               \
+      a.debug_ts[k] = globaltimer();                                                       \
+  } while (0)
 
 constexpr int kThreads = kLinThreads;
 constexpr int kWarps = kThreads / 32;
@@ -96,45 +108,41 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ---------------------------------------------------------------------------
 // expansion of the two 7x7 moment matrices to the 13x13 block (CTA 0 of a cluster)
 // ---------------------------------------------------------------------------
-__device__ void finalize_pair(const double *Wp28, const double *Wq28, bool has_planar,
-                              bool has_point, const double *rel, double inv_sigma2, double *out91) {
-  const int tid = threadIdx.x;
-  __shared__ double Wp[7][7], Wq[7][7];
-  __shared__ double Bp[7][13];    // plane-point basis rows
-  __shared__ double Bq[7][3][13]; // point-point basis (3 rows each)
-  if (tid < 28) {
-    int p = 0, e = tid; // upper-triangular index -> (p, q)
-    while (e >= 7 - p) {
-      e -= 7 - p;
-      ++p;
-    }
-    const int q = p + e;
-    Wp[p][q] = Wp[q][p] = Wp28[tid];
-    Wq[p][q] = Wq[q][p] = Wq28[tid];
-  }
-  for (int i = tid; i < 7 * 13; i += blockDim.x) (&Bp[0][0])[i] = 0.0;
-  for (int i = tid; i < 7 * 3 * 13; i += blockDim.x) (&Bq[0][0][0])[i] = 0.0;
-  __syncthreads();
+struct ExpandSmem {
+  double Wp[7][7], Wq[7][7];
+  double Bp[7][13];    // plane-point basis rows
+  double Bq[7][3][13]; // point-point basis (3 rows each)
+  double Tp[7][13];    // W_p B_p
+  double Tq[3][7][13]; // per residual row r: W_q B_q[.][r]
+};
 
+// The basis only depends on the relative pose, so CTA 0 builds it at kernel start:
+// three threads fill it while the rest of the CTA is already streaming correspondences
+// (the first __syncthreads of the reduction publishes it).
+__device__ __forceinline__ void build_basis(ExpandSmem &S, const double *rel) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 7 * 13; i += blockDim.x) (&S.Bp[0][0])[i] = 0.0;
+  for (int i = tid; i < 7 * 3 * 13; i += blockDim.x) (&S.Bq[0][0][0])[i] = 0.0;
+  __syncthreads();
   const double *R = rel, *t = rel + 9;
   if (tid < 3) {
     const int k = tid;
     // ---- plane-point: row = [ u1, -u2, -R^T u1 - R^T [t]x u2, R^T u2, -r ] ----
     const double K[3][3] = {{0, -t[2], t[1]}, {t[2], 0, -t[0]}, {-t[1], t[0], 0}}; // skew(t)
-    Bp[k][k] = 1.0;          // J_i rot   =  u1
-    Bp[3 + k][3 + k] = -1.0; // J_i trans = -u2
+    S.Bp[k][k] = 1.0;          // J_i rot   =  u1
+    S.Bp[3 + k][3 + k] = -1.0; // J_i trans = -u2
     for (int c = 0; c < 3; ++c) {
-      Bp[k][6 + c] = -R[3 * k + c]; // -R^T u1
-      double bt = 0.0;              // (R^T [t]x)[c][k]
+      S.Bp[k][6 + c] = -R[3 * k + c]; // -R^T u1
+      double bt = 0.0;                // (R^T [t]x)[c][k]
       for (int b = 0; b < 3; ++b) bt += R[3 * b + c] * K[b][k];
-      Bp[3 + k][6 + c] = -bt;          // -R^T [t]x u2
-      Bp[3 + k][9 + c] = R[3 * k + c]; //  R^T u2
+      S.Bp[3 + k][6 + c] = -bt;          // -R^T [t]x u2
+      S.Bp[3 + k][9 + c] = R[3 * k + c]; //  R^T u2
     }
     if (k == 0) {
-      Bp[6][12] = -1.0; // b = -r
+      S.Bp[6][12] = -1.0; // b = -r
       for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) // +[t]x R, the constant part of -[c]x R
-          Bq[6][r][6 + c] = K[r][0] * R[c] + K[r][1] * R[3 + c] + K[r][2] * R[6 + c];
+          S.Bq[6][r][6 + c] = K[r][0] * R[c] + K[r][1] * R[3 + c] + K[r][2] * R[6 + c];
     }
     // ---- point-point: rows = [ [P]x, -I, -[c]x R, R, -e ],  c = P + e - t ----
     double E[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
@@ -144,32 +152,54 @@ __device__ void finalize_pair(const double *Wp28, const double *Wq28, bool has_p
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) {
         const double er = E[r][0] * R[c] + E[r][1] * R[3 + c] + E[r][2] * R[6 + c]; // (E_k R)[r][c]
-        Bq[k][r][c] = E[r][c];     // [P]x
-        Bq[k][r][6 + c] = -er;     // -[P]x R
-        Bq[3 + k][r][6 + c] = -er; // -[e]x R
+        S.Bq[k][r][c] = E[r][c];     // [P]x
+        S.Bq[k][r][6 + c] = -er;     // -[P]x R
+        S.Bq[3 + k][r][6 + c] = -er; // -[e]x R
       }
-    Bq[3 + k][k][12] = -1.0; // -e
-    Bq[6][k][3 + k] = -1.0;  // -I
-    for (int c = 0; c < 3; ++c) Bq[6][k][9 + c] = R[3 * k + c]; // R
+    S.Bq[3 + k][k][12] = -1.0; // -e
+    S.Bq[6][k][3 + k] = -1.0;  // -I
+    for (int c = 0; c < 3; ++c) S.Bq[6][k][9 + c] = R[3 * k + c]; // R
+  }
+}
+
+// out = B^T W B in two short unrolled passes: T = W B (7 MACs per entry, all threads),
+// then B^T T (7 + 21 MACs per entry, 91 threads).  Every 8-byte word that leaves for the
+// host carries the call's sequence tag in its upper half (see publish_tagged).
+__device__ __forceinline__ void publish_tagged(volatile unsigned long long *dst, double v,
+                                               unsigned long long tag) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  dst[0] = (bits & 0xffffffffull) | (tag << 32);
+  dst[1] = (bits >> 32) | (tag << 32);
+}
+
+__device__ __forceinline__ void expand_and_publish(ExpandSmem &S, const double *Wp28, const double *Wq28,
+                                                   bool has_planar, bool has_point, double inv_sigma2,
+                                                   volatile unsigned long long *out182,
+                                                   unsigned long long tag) {
+  const int tid = threadIdx.x;
+  if (tid < 28) {
+    int p = 0, e = tid; // upper-triangular index -> (p, q)
+    while (e >= 7 - p) {
+      e -= 7 - p;
+      ++p;
+    }
+    const int q = p + e;
+    S.Wp[p][q] = S.Wp[q][p] = Wp28[tid];
+    S.Wq[p][q] = S.Wq[q][p] = Wq28[tid];
   }
   __syncthreads();
-
-  // phase 1 (all threads): T = W B, 7 MACs per entry; phase 2 (91 threads): out = B^T T.
-  // Two short fully unrolled passes instead of one 49..147-term serial sum per entry.
-  __shared__ double Tp[7][13];    // W_p B_p
-  __shared__ double Tq[3][7][13]; // per residual row r: W_q B_q[.][r]
   for (int idx = tid; idx < 91 + 273; idx += blockDim.x) {
     double v = 0.0;
     if (idx < 91) {
       const int k = idx / 13, y = idx % 13;
 #pragma unroll
-      for (int l = 0; l < 7; ++l) v += Wp[k][l] * Bp[l][y];
-      Tp[k][y] = v;
+      for (int l = 0; l < 7; ++l) v += S.Wp[k][l] * S.Bp[l][y];
+      S.Tp[k][y] = v;
     } else {
       const int j = idx - 91, r = j / 91, k = (j % 91) / 13, y = j % 13;
 #pragma unroll
-      for (int l = 0; l < 7; ++l) v += Wq[k][l] * Bq[l][r][y];
-      Tq[r][k][y] = v;
+      for (int l = 0; l < 7; ++l) v += S.Wq[k][l] * S.Bq[l][r][y];
+      S.Tq[r][k][y] = v;
     }
   }
   __syncthreads();
@@ -183,15 +213,15 @@ __device__ void finalize_pair(const double *Wp28, const double *Wq28, bool has_p
     double sum = 0.0;
     if (has_planar) {
 #pragma unroll
-      for (int k = 0; k < 7; ++k) sum += Bp[k][x] * Tp[k][y];
+      for (int k = 0; k < 7; ++k) sum += S.Bp[k][x] * S.Tp[k][y];
     }
     if (has_point) {
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int k = 0; k < 7; ++k) sum += Bq[k][r][x] * Tq[r][k][y];
+        for (int k = 0; k < 7; ++k) sum += S.Bq[k][r][x] * S.Tq[r][k][y];
     }
-    out91[tid] = sum * inv_sigma2;
+    publish_tagged(out182 + 2 * tid, sum * inv_sigma2, tag);
   }
 }
 
@@ -199,7 +229,23 @@ __device__ void finalize_pair(const double *Wp28, const double *Wq28, bool has_p
 // one cluster per pair
 // ---------------------------------------------------------------------------
 template <bool kErrorOnly>
-__device__ __forceinline__ void lin_cluster_body(const LinArgs &a, const LinTask &task) {
+__device__ __forceinline__ void lin_cluster_body(const LinArgs &a, const LinTask &task_in) {
+  // ranges of the pair: given by the host, or - when the linearisation was queued right
+  // behind the association that produces them - read from the device pair row
+  struct {
+    const double *rel;
+    uint32_t off_planar, n_planar, off_point, n_point;
+    int slot_j, out_index;
+  } task = {task_in.rel, task_in.off_planar, task_in.n_planar, task_in.off_point, task_in.n_point,
+            task_in.slot_j, task_in.out_index};
+  if (task_in.dyn_slot_i_plus1) {
+    const int si = (int)task_in.dyn_slot_i_plus1 - 1, nb = a.W + 1;
+    task.off_planar = a.pair_row[0 * nb + si];
+    task.n_planar = a.pair_row[1 * nb + si];
+    task.off_point = a.pair_row[2 * nb + si];
+    task.n_point = a.pair_row[3 * nb + si];
+    if (task.n_planar + task.n_point == 0) return; // empty pair: the whole cluster leaves
+  }
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int kCluster = (int)cluster.num_blocks(); // 1, 2, 4 or 8: chosen per launch
@@ -208,10 +254,13 @@ __device__ __forceinline__ void lin_cluster_body(const LinArgs &a, const LinTask
   __shared__ double s_sum[2][28];  // [planar | point] moments of this CTA (error: [0][0])
   __shared__ double s_total[2][28];
 
+  __shared__ ExpandSmem s_exp;
   double acc[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) acc[k] = 0.0;
   double err_acc = 0.0;
+  LIN_TS(0);
+  if (!kErrorOnly && rank == 0) build_basis(s_exp, task.rel);
 
   // ---- plane-point correspondences of this CTA's slice ----
   {
@@ -239,11 +288,13 @@ __device__ __forceinline__ void lin_cluster_body(const LinArgs &a, const LinTask
       }
     }
   }
+  LIN_TS(1);
   if (!kErrorOnly) {
     block_reduce28(acc, s_warp, s_sum[0], tid);
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc[k] = 0.0;
   }
+  LIN_TS(2);
   // ---- point-point correspondences ----
   {
     const uint32_t lo = (uint32_t)(((unsigned long long)task.n_point * rank) / kCluster);
@@ -283,34 +334,41 @@ __device__ __forceinline__ void lin_cluster_body(const LinArgs &a, const LinTask
     block_reduce28(acc, s_warp, s_sum[1], tid);
   }
 
-  // ---- gather the eight CTA sums through distributed shared memory ----
+  // ---- gather the CTA sums through distributed shared memory ----
+  LIN_TS(3);
   cluster.sync();
+  LIN_TS(4);
   if (rank == 0) {
     if (kErrorOnly) {
       if (tid == 0) {
         double v = 0.0;
         for (int r = 0; r < kCluster; ++r) v += *cluster.map_shared_rank(&s_sum[0][0], r);
-        a.out[task.out_index] = 0.5 * v * a.inv_sigma2;
+        s_total[0][0] = 0.5 * v * a.inv_sigma2;
       }
-    } else {
-      if (tid < 56) {
-        const int which = tid / 28, e = tid % 28;
-        double v = 0.0;
-        for (int r = 0; r < kCluster; ++r) v += *cluster.map_shared_rank(&s_sum[which][e], r);
-        s_total[which][e] = v;
-      }
-      __syncthreads();
-      finalize_pair(s_total[0], s_total[1], task.n_planar > 0, task.n_point > 0, task.rel,
-                    a.inv_sigma2, a.out + (size_t)task.out_index * 91);
+    } else if (tid < 56) {
+      const int which = tid / 28, e = tid % 28;
+      double v = 0.0;
+      for (int r = 0; r < kCluster; ++r) v += *cluster.map_shared_rank(&s_sum[which][e], r);
+      s_total[which][e] = v;
     }
   }
+  LIN_TS(5);
   cluster.sync(); // the other CTAs' shared memory must outlive CTA 0's remote reads
-  if (rank == 0) {
-    // publish: results first, then the pair's flag (the host polls it)
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) a.flags[task.out_index] = a.seq;
+  LIN_TS(6);
+  if (rank != 0) return;
+  __syncthreads();
+  // Publish straight into mapped pinned host memory.  Every 8-byte word carries the
+  // call's sequence tag next to 32 bits of payload, so the host can tell a fresh word
+  // from a stale one by itself: no system-wide fence (a ~3 us PCIe flush) and no
+  // separate flag are needed - an aligned 8-byte store is a single atomic PCIe write.
+  const unsigned long long tag = a.seq & 0xffffffffull;
+  if (kErrorOnly) {
+    if (tid == 0) publish_tagged(a.out + 2 * (size_t)task.out_index, s_total[0][0], tag);
+  } else if (!(a.debug_flags & 2)) {
+    expand_and_publish(s_exp, s_total[0], s_total[1], task.n_planar > 0, task.n_point > 0,
+                       a.inv_sigma2, a.out + 182 * (size_t)task.out_index, tag);
   }
+  LIN_TS(7);
 }
 
 } // namespace

@@ -295,70 +295,6 @@ __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs q
   }
   } // q < n_query
 
-  // ---- the last CTA of this type scans the histogram and publishes the pair row ----
-  __shared__ bool s_last;
-  __shared__ uint32_t s_tot[kMaxWindow + 1], s_off[kMaxWindow + 1];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(a.type_ticket, 1u) == gridDim.x - 1u;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const int nblocks = (a.n_query + 255) / 256;
-  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-    uint32_t run = 0;
-    // tiles of 16 blocks: all loads of a tile are issued before its stores, so they
-    // overlap instead of serialising on the read-modify-write of hist_cnt
-    for (int blk0 = 0; blk0 < nblocks; blk0 += 16) {
-      uint32_t c[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        c[i] = blk0 + i < nblocks ? __ldcg(&a.hist_cnt[(size_t)(blk0 + i) * nb + b]) : 0u;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (blk0 + i < nblocks) {
-          a.hist_cnt[(size_t)(blk0 + i) * nb + b] = 0u; // self-cleaning for the next association
-          a.block_hist[(size_t)(blk0 + i) * nb + b] = run;
-          run += c[i];
-        }
-      }
-    }
-    s_tot[b] = run;
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) { // exclusive prefix over the bins by one warp
-    uint32_t run = 0;
-    for (int base = 0; base < a.W; base += 32) {
-      const int b = base + (int)threadIdx.x;
-      const uint32_t c = b < a.W ? s_tot[b] : 0u;
-      uint32_t incl = c;
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)threadIdx.x >= o) incl += t;
-      }
-      if (b < a.W) s_off[b] = run + incl - c;
-      run += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (threadIdx.x == 0) s_off[a.W] = run; // total correspondences
-  }
-  __syncthreads();
-  for (int b = threadIdx.x; b <= a.W; b += blockDim.x) {
-    a.pair_off[b] = s_off[b];
-    a.pair_cnt[b] = s_tot[b]; // entry W = novel keypoints
-    a.host_pair_off[b] = s_off[b];
-    a.host_pair_cnt[b] = s_tot[b];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    *a.type_ticket = 0u;
-    const unsigned d = atomicAdd(a.done_counter, 1u);
-    if (d == 1u) { // both types done
-      *a.done_counter = 0u;
-      __threadfence_system();
-      *a.flag = a.seq;
-    }
-  }
 }
 
 void assoc_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream, Profiler &prof) {
@@ -372,17 +308,83 @@ void assoc_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream,
 // ---------------------------------------------------------------------------
 // correspondence segment of the current scan: stable counting sort of the
 // accepted matches by the matched scan's slot (rule R6 order inside a pair).
-// Counting and the prefix sums are fused into the NN kernel above; this kernel
-// recomputes each query's stable rank inside its 256-query block and scatters.
+// The NN kernel counts matches per (256-query block, matched slot) with integer atomics;
+// every CTA here derives its own exclusive prefix from those counters (a few KB from
+// L2), recomputes each query's stable rank inside its block and scatters.  CTA 0 also
+// publishes the pair row to the host.
 // ---------------------------------------------------------------------------
+// Sums the per-256-query bin counters the NN kernel left behind: s_pre[b] = matches of
+// bin b in earlier query blocks (exclusive prefix for this block), s_tot[b] = all of them.
+// Integer shared-memory atomics: order-free, so the result is deterministic.
+__device__ __forceinline__ void block_prefix(const uint32_t *hist_cnt, int nblocks, int nb, int blk,
+                                             uint32_t *s_pre, uint32_t *s_tot) {
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) s_pre[i] = s_tot[i] = 0u;
+  __syncthreads();
+  const int total = nblocks * nb;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const uint32_t c = __ldcg(&hist_cnt[i]);
+    if (c) {
+      const int bb = i / nb, b = i - bb * nb;
+      atomicAdd(&s_tot[b], c);
+      if (bb < blk) atomicAdd(&s_pre[b], c);
+    }
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) segment_scatter_kernel(SegmentArgs pa, SegmentArgs qa) {
   const SegmentArgs &a = blockIdx.y == 0 ? pa : qa;
   __shared__ uint32_t s_warp[8][kMaxWindow];
-  if ((int)(blockIdx.x * blockDim.x) >= a.n_query) return;
+  __shared__ uint32_t s_pre[kMaxWindow + 1], s_tot[kMaxWindow + 1], s_off[kMaxWindow + 1];
+  // clear the other counter buffer for this type's next association (grid-stride; saves
+  // a separate memset launch on the caller's critical path)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.hist_bytes / sizeof(uint32_t);
+       i += (size_t)gridDim.x * blockDim.x)
+    a.hist_next[i] = 0u;
+  const bool has_work = (int)(blockIdx.x * blockDim.x) < a.n_query;
+  if (!has_work && blockIdx.x != 0) return; // block 0 always publishes the pair row
   const int nb = a.W + 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nblocks = (a.n_query + 255) / 256;
   for (int i = threadIdx.x; i < 8 * kMaxWindow; i += blockDim.x) (&s_warp[0][0])[i] = 0;
+  block_prefix(a.hist_cnt, nblocks, nb, (int)blockIdx.x, s_pre, s_tot);
+  if (threadIdx.x < 32) { // exclusive prefix over the bins = start of every pair in the segment
+    uint32_t run = 0;
+    for (int base = 0; base < a.W; base += 32) {
+      const int b = base + lane;
+      const uint32_t c = b < a.W ? s_tot[b] : 0u;
+      uint32_t incl = c;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (b < a.W) s_off[b] = run + incl - c;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) s_off[a.W] = run; // total correspondences
+  }
   __syncthreads();
+  if (blockIdx.x == 0) {
+    // publish the pair row (offsets, counts, novel count) to the host without a memcpy
+    for (int b = threadIdx.x; b <= a.W; b += blockDim.x) {
+      a.host_pair_off[b] = s_off[b];
+      a.host_pair_cnt[b] = s_tot[b]; // entry W = novel keypoints
+      a.dev_pair_off[b] = s_off[b];
+      a.dev_pair_cnt[b] = s_tot[b];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned d = atomicAdd(a.done_counter, 1u);
+      if (d == 1u) { // both types published
+        *a.done_counter = 0u;
+        __threadfence_system();
+        *a.flag = a.seq;
+      }
+    }
+    if (!has_work) return;
+  }
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   MatchRec m;
   m.slot = kNoSlot;
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(256) segment_scatter_kernel(SegmentArgs pa, Se
   if (b >= 0 && rank_w == 0) s_warp[warp][b] = __popc(peers);
   __syncthreads();
   if (b < 0) return;
-  uint32_t pos = a.pair_off[b] + a.block_hist[(size_t)blockIdx.x * nb + b] + rank_w;
+  uint32_t pos = s_off[b] + s_pre[b] + rank_w;
   for (int w = 0; w < warp; ++w) pos += s_warp[w][b];
   // correspondence = (map point in its own scan frame, current keypoint):
   // PlanePoint/PointPoint::push_back (factor.hpp:71-75, :113-116).  The map point
@@ -428,6 +430,7 @@ void segment_build_launch(const SegmentArgs &pa, const SegmentArgs &qa, cudaStre
   const dim3 g((n + 255) / 256, 2);
   segment_scatter_kernel<<<g, 256, 0, stream>>>(pa, qa);
   prof.end(FORMGPU_KG_SEGMENT, 1);
+
 }
 
 // ---------------------------------------------------------------------------
@@ -438,15 +441,23 @@ __global__ void __launch_bounds__(256) commit_kernel(CommitArgs pa, CommitArgs q
   const CommitArgs &a = blockIdx.y == 0 ? pa : qa;
   if ((int)(blockIdx.x * blockDim.x) >= a.n_query) return;
   __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_before; // novel keypoints in earlier query blocks
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_before = 0u;
+  __syncthreads();
+  {
+    uint32_t mine = 0;
+    for (int blk = threadIdx.x; blk < (int)blockIdx.x; blk += blockDim.x)
+      mine += __ldcg(&a.hist_cnt[(size_t)blk * (a.W + 1) + a.W]);
+    if (mine) atomicAdd(&s_before, mine);
+  }
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const bool novel = q < a.n_query && a.match[q].dist_sqrd > a.min_dist2;
   const unsigned bal = __ballot_sync(0xffffffffu, novel);
   if (lane == 0) s_warp[warp] = __popc(bal);
   __syncthreads();
   if (!novel) return;
-  uint32_t pos = a.dst_count + a.block_hist[(size_t)blockIdx.x * (a.W + 1) + a.W] +
-                 __popc(bal & ((1u << lane) - 1u));
+  uint32_t pos = a.dst_count + s_before + __popc(bal & ((1u << lane) - 1u));
   for (int w = 0; w < warp; ++w) pos += s_warp[w];
   if (a.type == 0)
     reinterpret_cast<PlanarRec *>(a.store_dst)[pos] = reinterpret_cast<const PlanarRec *>(a.queries)[q];

@@ -159,14 +159,20 @@ public:
     for (const auto &c : counts) mine[c.i] = {c.n_planar, c.n_point};
   }
 
-  /// constraints.cpp:103-118
-  Values optimize(bool fast = false) {
+  bool fused_schedule() const noexcept { return m_params.fused_trial_linearization; }
+
+  /// constraints.cpp:103-118.  `first_blocks` (fused schedule only): the blocks of the
+  /// current scan's pairs at the current values, already obtained together with the
+  /// association (HotPath::associate_linearize), in ascending scan order.
+  Values optimize(bool fast = false, const std::vector<double> *first_blocks = nullptr) {
     ++m_stats.optimize_calls;
     Graph g = m_params.disable_smoothing ? get_single_graph() : get_graph(fast);
     Values init;
     if (m_params.disable_smoothing) init[m_scan] = m_values.at(m_scan);
     else init = m_values;
-    return levenberg_marquardt(g, init);
+    const bool usable = first_blocks && (fast || m_params.disable_smoothing) &&
+                        first_blocks->size() == 91 * g.pairs.size();
+    return levenberg_marquardt(g, init, usable ? first_blocks->data() : nullptr);
   }
 
   /// constraints.cpp:120-195
@@ -394,7 +400,8 @@ private:
 
   /// NonlinearFactorGraph::linearize + dense assembly in `order`.
   dense::Quadratic linearize_graph(const Graph &g, const Values &values,
-                                   const std::vector<uint64_t> &order) {
+                                   const std::vector<uint64_t> &order,
+                                   const double *preloaded_blocks = nullptr) {
     dense::Quadratic sys;
     const size_t n = 6 * order.size();
     sys.resize(n);
@@ -433,8 +440,12 @@ private:
     }
     if (!g.pairs.empty()) {
       std::vector<double> blocks(91 * g.pairs.size());
-      const std::vector<ScanPose> poses = merged_poses(values);
-      m_hotpath->linearize(g.pairs.data(), g.pairs.size(), poses.data(), poses.size(), blocks.data());
+      if (preloaded_blocks) {
+        std::copy(preloaded_blocks, preloaded_blocks + blocks.size(), blocks.begin());
+      } else {
+        const std::vector<ScanPose> poses = merged_poses(values);
+        m_hotpath->linearize(g.pairs.data(), g.pairs.size(), poses.data(), poses.size(), blocks.data());
+      }
       ++m_stats.linearize_calls;
       m_stats.linearized_pairs += g.pairs.size();
       for (size_t p = 0; p < g.pairs.size(); ++p) {
@@ -487,7 +498,8 @@ private:
   }
 
   /// DenseLMOptimizer::optimize (gtsam.hpp:40-54) with GTSAM's LM schedule.
-  Values levenberg_marquardt(const Graph &g, const Values &initial) {
+  Values levenberg_marquardt(const Graph &g, const Values &initial,
+                             const double *first_blocks = nullptr) {
     const LMParams &P = m_params.opt_params;
     const bool fused = m_params.fused_trial_linearization;
     Values values = initial;
@@ -498,7 +510,7 @@ private:
     bool have_lin = false;
     double error;
     if (fused) {
-      lin = linearize_graph(g, values, order);
+      lin = linearize_graph(g, values, order, first_blocks);
       have_lin = true;
       error = 0.5 * lin.f;
     } else {

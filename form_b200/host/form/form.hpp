@@ -210,9 +210,18 @@ struct Estimator {
       std::vector<PairCount> counts;
       for (size_t idx = 0; idx < m_params.matcher.max_num_rematches; ++idx) {
         const Pose3 before = m_constraints.get_current_pose();
-        m_hotpath->associate(before, counts);            // :75-79
-        m_constraints.set_current_counts(counts);
-        new_values = m_constraints.optimize(true);        // :82
+        if (m_constraints.fused_schedule()) {
+          // match (:75-79) and the first linearisation of optimize(true) (:82) in one
+          // hot-path call; the LM then starts from those blocks
+          const std::vector<ScanPose> now = m_constraints.scan_poses(m_constraints.get_values());
+          m_hotpath->associate_linearize(scan_idx, now.data(), now.size(), counts, m_first_blocks);
+          m_constraints.set_current_counts(counts);
+          new_values = m_constraints.optimize(true, &m_first_blocks);
+        } else {
+          m_hotpath->associate(before, counts);            // :75-79
+          m_constraints.set_current_counts(counts);
+          new_values = m_constraints.optimize(true);        // :82
+        }
         const Pose3 after = new_values.at(scan_idx);
         const double diff = norm6(before.localCoordinates(after));
         ++m_icp_iterations;
@@ -247,6 +256,7 @@ struct Estimator {
 private:
   std::string m_last_error;
   size_t m_icp_iterations = 0;
+  std::vector<double> m_first_blocks;
 };
 
 } // namespace form

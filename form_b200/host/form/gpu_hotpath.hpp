@@ -97,6 +97,18 @@ public:
     counts.resize(n);
   }
 
+  void associate_linearize(uint64_t, const ScanPose *poses, size_t n_poses,
+                           std::vector<PairCount> &counts, std::vector<double> &blocks) override {
+    counts.resize(256);
+    blocks.resize(91 * 256);
+    size_t n = 0;
+    check(formgpu_associate_linearize(m_ctx, reinterpret_cast<const formgpu_scan_pose *>(poses), n_poses,
+                                      reinterpret_cast<formgpu_pair_count *>(counts.data()), counts.size(),
+                                      &n, blocks.data()));
+    counts.resize(n);
+    blocks.resize(91 * n);
+  }
+
   void linearize(const PairKey *pairs, size_t n_pairs, const ScanPose *poses, size_t n_poses,
                  double *out91) override {
     check(formgpu_linearize(m_ctx, reinterpret_cast<const formgpu_pair *>(pairs), n_pairs,

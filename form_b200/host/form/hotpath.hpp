@@ -84,6 +84,23 @@ public:
   /// and reports the per-pair counts.
   virtual void associate(const Pose3 &pose_k, std::vector<PairCount> &counts) = 0;
 
+  /// associate() at the current scan's pose in `poses`, then linearize() of every non-empty
+  /// pair (i, current scan) at `poses`: the start of one ICP iteration (form.cpp:75-82).
+  /// blocks receives 91 doubles per entry of counts.  Implementations may fuse the two
+  /// into one device round trip; the default simply calls them in turn.
+  virtual void associate_linearize(uint64_t current_scan, const ScanPose *poses, size_t n_poses,
+                                   std::vector<PairCount> &counts, std::vector<double> &blocks) {
+    const Pose3 *pose_k = nullptr;
+    for (size_t p = 0; p < n_poses; ++p)
+      if (poses[p].scan == current_scan) pose_k = &poses[p].pose;
+    if (!pose_k) throw HotPathError("associate_linearize: no pose for the current scan");
+    associate(*pose_k, counts);
+    std::vector<PairKey> pairs;
+    for (const auto &c : counts) pairs.push_back({c.i, current_scan});
+    blocks.assign(91 * pairs.size(), 0.0);
+    if (!pairs.empty()) linearize(pairs.data(), pairs.size(), poses, n_poses, blocks.data());
+  }
+
   /// DenseFactor::linearize of FeatureFactor(X(i), X(j)) for each pair
   /// (gtsam.hpp:67-86, factor.cpp:141-186): 91 doubles per pair, the packed
   /// upper triangle of the 13x13 augmented information matrix.

@@ -16,7 +16,7 @@
 namespace form {
 
 struct TraceOp {
-  enum Kind : int { EXTRACT = 0, MAP_REBUILD, ASSOCIATE, LINEARIZE, ERROR, COMMIT, REMOVE };
+  enum Kind : int { EXTRACT = 0, MAP_REBUILD, ASSOCIATE, LINEARIZE, ERROR, COMMIT, REMOVE, ASSOC_LIN };
   Kind kind;
   uint64_t scan = 0;            // EXTRACT: scan index
   Pose3 pose;                   // ASSOCIATE
@@ -61,6 +61,15 @@ public:
     op.pose = pose_k;
     m_trace.ops.push_back(std::move(op));
     m_inner.associate(pose_k, counts);
+  }
+  void associate_linearize(uint64_t current_scan, const ScanPose *poses, size_t n_poses,
+                           std::vector<PairCount> &counts, std::vector<double> &blocks) override {
+    TraceOp op;
+    op.kind = TraceOp::ASSOC_LIN;
+    op.scan = current_scan;
+    op.poses.assign(poses, poses + n_poses);
+    m_trace.ops.push_back(std::move(op));
+    m_inner.associate_linearize(current_scan, poses, n_poses, counts, blocks);
   }
   void linearize(const PairKey *pairs, size_t n_pairs, const ScanPose *poses, size_t n_poses,
                  double *out91) override {
@@ -157,6 +166,23 @@ inline void replay(const Trace &trace, HotPath &hp, size_t first, size_t last,
                                    [&](const auto &e) { return e.first.j == cur_scan; }),
                     table.end());
         for (const auto &c : counts) table.push_back({{c.i, cur_scan}, {c.n_planar, c.n_point}});
+        break;
+      }
+      case TraceOp::ASSOC_LIN: {
+        hp.associate_linearize(op.scan, op.poses.data(), op.poses.size(), counts, out);
+        st.assoc_calls += 1;
+        st.assoc_queries += cur_np + cur_nq;
+        table.erase(std::remove_if(table.begin(), table.end(),
+                                   [&](const auto &e) { return e.first.j == cur_scan; }),
+                    table.end());
+        for (const auto &c : counts) table.push_back({{c.i, cur_scan}, {c.n_planar, c.n_point}});
+        st.lin_calls += 1;
+        st.lin_pairs += counts.size();
+        for (size_t p = 0; p < counts.size(); ++p) {
+          st.lin_planar += counts[p].n_planar;
+          st.lin_point += counts[p].n_point;
+          st.checksum += out[91 * p + 90];
+        }
         break;
       }
       case TraceOp::LINEARIZE: {

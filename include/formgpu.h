@@ -180,6 +180,18 @@ int formgpu_map_rebuild(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
 int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k,
                       formgpu_pair_count *counts_out, size_t counts_cap, size_t *n_counts);
 
+/* formgpu_associate followed by formgpu_linearize of every non-empty pair (i, current
+ * scan) at `poses` - what one ICP iteration does first (form/form.cpp:75-82: match, then
+ * optimize(true) whose first step linearises exactly those FeatureFactors,
+ * form/optimization/constraints.cpp:259-265) - as ONE device round trip: the
+ * linearisation is queued behind the association and reads its ranges on the device.
+ * The current scan is associated at its pose in `poses` (which must contain it).
+ * out91 receives 91 doubles per entry of counts_out, in the same order; it must hold
+ * 91 * counts_cap doubles. */
+int formgpu_associate_linearize(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t n_poses,
+                                formgpu_pair_count *counts_out, size_t counts_cap, size_t *n_counts,
+                                double *out91);
+
 /* Matcher::get_matches (matcher.hpp:114): per-keypoint results of the last
  * association; type 0 = planar, 1 = point. */
 int formgpu_get_matches(formgpu_ctx *ctx, int type, formgpu_match *out, size_t cap, size_t *n);

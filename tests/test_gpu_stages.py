@@ -61,6 +61,24 @@ def _run_sequence(sensor, n_scans, seq=0, remove_at=None, overrides=None, icp_it
                     er = ref.error(pairs, all_poses)
                     assert np.allclose(e, er, rtol=1e-9, atol=1e-12)
                     assert np.allclose(e, 0.5 * H[:, 90], rtol=1e-9, atol=1e-12)  # f = b^T b
+            # the fused entry point (association + linearisation of the current scan's pairs in
+            # one device round trip) against the two separate oracle calls
+            pose_k = perturbed(gt(seq, k), rng, 0.001, 0.01)
+            est[k] = pose_k
+            all_poses = scan_poses(window + [k], [est[s] for s in window + [k]])
+            fcounts, fH = ctx.associate_linearize(all_poses)
+            rcounts = ref.associate(pose_k)
+            assert fcounts.tobytes() == rcounts.tobytes(), f"scan {k} fused pair counts"
+            for t in (0, 1):
+                assert ctx.matches(t).tobytes() == ref.matches(t).tobytes(), f"scan {k} fused matches"
+            if len(rcounts):
+                pairs = np.zeros(len(rcounts), dtype=_capi.PAIR)
+                pairs["i"] = rcounts["i"]
+                pairs["j"] = k
+                Hr = ref.linearize(pairs, all_poses)
+                for a, b in zip(fH, Hr):
+                    worst = max(worst, block_rel_err(a, b))
+                assert np.array_equal(fH, ctx.linearize(pairs, all_poses))  # same kernel, same order
             added = ctx.commit_scan()
             radded = ref.commit_scan()
             assert added == radded, f"scan {k} novel keypoints"
