@@ -133,6 +133,8 @@ FORMGPU_SYMBOLS = {
     "formgpu_last_error": (C.c_char_p, [_vp]),
     "formgpu_abi_version": (_i, []),
     "formgpu_extract": (_i, [_vp, _vp, _sz, _u64, _vp, _sz, _psz, _vp, _sz, _psz]),
+    "formgpu_alloc_pinned": (_vp, [_sz]),
+    "formgpu_free_pinned": (None, [_vp]),
     "formgpu_extract_device": (_i, [_vp, _vp, _sz, _u64, _psz, _psz]),
     "formgpu_max_planar": (_sz, [_vp]),
     "formgpu_max_point": (_sz, [_vp]),

@@ -292,6 +292,19 @@ void formgpu_destroy(formgpu_ctx *ctx) {
   delete ctx;
 }
 
+void *formgpu_alloc_pinned(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void formgpu_free_pinned(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
 size_t formgpu_max_planar(const formgpu_ctx *ctx) { return ctx ? ctx->kp_cap : 0; }
 size_t formgpu_max_point(const formgpu_ctx *ctx) { return ctx ? ctx->kq_cap : 0; }
 
@@ -302,6 +315,9 @@ static ExtractArgs make_extract_args(formgpu_ctx *ctx, const float4 *scan_dev, b
                                      bool host_records = false, bool publish = false) {
   const formgpu_params &P = ctx->P;
   ExtractArgs a{};
+  a.host_planar_f64 = nullptr;
+  a.host_point_f64 = nullptr;
+  a.scan_idx = 0;
   a.rows = ctx->rows;
   a.cols = ctx->cols;
   a.words = ctx->words;
@@ -345,14 +361,30 @@ static ExtractArgs make_extract_args(formgpu_ctx *ctx, const float4 *scan_dev, b
 }
 
 // runs the kernels on a device-resident scan and fetches the two counts
+// device alias of a page-locked (cudaHostAlloc / cudaHostRegister, mapped) host pointer,
+// nullptr for pageable memory
+static void *mapped_alias(void *host_ptr) {
+  if (!host_ptr) return nullptr;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, host_ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
+}
+
 static int extract_run(formgpu_ctx *ctx, const float4 *scan_dev, uint64_t scan_idx,
-                       bool host_records) {
+                       bool host_records, formgpu_planar_feat *direct_planar = nullptr,
+                       formgpu_point_feat *direct_point = nullptr) {
   ctx->cur_buf ^= 1;
   ctx->d_cur_planar = ctx->d_cur_planar_buf[ctx->cur_buf];
   ctx->d_cur_point = ctx->d_cur_point_buf[ctx->cur_buf];
   // the pack kernel writes the counts (and, for host callers, the compact keypoint
   // records) into mapped pinned memory and raises a flag: no memcpy, no stream sync
-  const ExtractArgs a = make_extract_args(ctx, scan_dev, false, host_records, true);
+  ExtractArgs a = make_extract_args(ctx, scan_dev, false, host_records, true);
+  a.host_planar_f64 = direct_planar;
+  a.host_point_f64 = direct_point;
+  a.scan_idx = scan_idx;
   extract_launch(a, 1, ctx->stream, ctx->prof);
   FORMGPU_CUDA(ctx, cudaGetLastError());
   const int w = wait_flag(ctx, 2, a.seq);
@@ -381,12 +413,31 @@ int formgpu_extract(formgpu_ctx *ctx, const formgpu_point4f *scan, size_t n, uin
   ProfScope scope(ctx);
   FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_scan, scan, n * sizeof(float4), cudaMemcpyHostToDevice,
                                     ctx->stream));
-  const int rc = extract_run(ctx, ctx->d_scan, scan_idx, true);
+  // Page-locked caller buffers that can hold the worst case are written by the pack kernel
+  // itself (f64 API structs straight over PCIe); pageable ones go through the compact
+  // staging records and are widened here.
+  formgpu_planar_feat *dp = nullptr;
+  formgpu_point_feat *dq = nullptr;
+  if (planar_out && point_out && planar_cap >= ctx->kp_cap && point_cap >= ctx->kq_cap) {
+    if (ctx->direct_probe[0] != planar_out || ctx->direct_probe[1] != point_out) {
+      ctx->direct_probe[0] = planar_out;
+      ctx->direct_probe[1] = point_out;
+      ctx->direct_alias[0] = mapped_alias(planar_out);
+      ctx->direct_alias[1] = mapped_alias(point_out);
+    }
+    if (ctx->direct_alias[0] && ctx->direct_alias[1]) {
+      dp = static_cast<formgpu_planar_feat *>(ctx->direct_alias[0]);
+      dq = static_cast<formgpu_point_feat *>(ctx->direct_alias[1]);
+    }
+  }
+  const bool direct = dp != nullptr;
+  const int rc = extract_run(ctx, ctx->d_scan, scan_idx, !direct, dp, dq);
   if (rc) return rc;
   ctx->cur_device_resident = false;
   const size_t np = (size_t)ctx->cur_n[0], nq = (size_t)ctx->cur_n[1];
   *n_planar = np;
   *n_point = nq;
+  if (direct) return FORMGPU_OK;
   if ((np && !planar_out) || (nq && !point_out) || np > planar_cap || nq > point_cap)
     return fail(ctx, FORMGPU_ERR_CAPACITY, "formgpu_extract: output buffers too small");
   // the compact lossless f32 records already sit in mapped pinned memory (written by

@@ -168,6 +168,10 @@ struct formgpu_ctx {
   volatile unsigned long long *h_out = nullptr;
   size_t h_out_bytes = 0;
 
+  // caller output buffers last probed for page-locked-ness, and their device aliases
+  void *direct_probe[2] = {nullptr, nullptr};
+  void *direct_alias[2] = {nullptr, nullptr};
+
   // ---- current scan ----
   bool have_current = false;
   uint64_t cur_scan = 0;

@@ -665,29 +665,54 @@ extract_pack_kernel(ExtractArgs a) {
     a.cur_counts[2 * b + 0] = s_tot[0];
     a.cur_counts[2 * b + 1] = s_tot[1];
   }
-  // planar: stable compaction of the keep flags by warp 0
+  // planar: stable compaction of the keep flags by warp 0 into a list of kept picks
+  extern __shared__ uint16_t s_kept[]; // [pr_cap]
+  __shared__ int s_nkeep;
+  const int n_picks = a.planar_cnt[rb];
   if (tid < 32) {
-    const int n_picks = a.planar_cnt[rb];
-    int base_out = s_off[0];
+    int n = 0;
     for (int base = 0; base < n_picks; base += 32) {
       const int pk = base + lane;
-      float4 nrm = make_float4(0, 0, 0, 0);
-      if (pk < n_picks) nrm = a.normals[rb * a.pr_cap + pk];
-      const bool keep = pk < n_picks && nrm.w != 0.0f;
+      const bool keep = pk < n_picks && a.normals[rb * a.pr_cap + pk].w != 0.0f;
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
-      if (keep) {
-        const int c = a.planar_cols[rb * a.pr_cap + pk];
-        const float4 p = __ldg(&g[c]);
-        PlanarRec r;
-        r.x = p.x; r.y = p.y; r.z = p.z;
-        r.nx = nrm.x; r.ny = nrm.y; r.nz = nrm.z;
-        r.pad0 = (uint32_t)(row * a.cols + c);
-        r.pad1 = 0;
-        const size_t o = base_out + __popc(bal & ((1u << lane) - 1u));
-        a.cur_planar[(size_t)b * a.kp_cap + o] = r;
-        if (a.host_planar) a.host_planar[o] = r;
+      if (keep) s_kept[n + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)pk;
+      n += __popc(bal);
+    }
+    if (lane == 0) s_nkeep = n;
+  }
+  __syncthreads();
+  const int n_keep = s_nkeep;
+  for (int j = tid; j < n_keep; j += blockDim.x) {
+    const int pk = s_kept[j];
+    const float4 nrm = a.normals[rb * a.pr_cap + pk];
+    const int c = a.planar_cols[rb * a.pr_cap + pk];
+    const float4 p = __ldg(&g[c]);
+    PlanarRec r;
+    r.x = p.x; r.y = p.y; r.z = p.z;
+    r.nx = nrm.x; r.ny = nrm.y; r.nz = nrm.z;
+    r.pad0 = (uint32_t)(row * a.cols + c);
+    r.pad1 = 0;
+    a.cur_planar[(size_t)b * a.kp_cap + s_off[0] + j] = r;
+    if (a.host_planar) a.host_planar[s_off[0] + j] = r;
+  }
+  if (a.host_planar_f64) {
+    // the caller's (page-locked, mapped) buffer receives the API's f64 structs directly:
+    // consecutive threads write consecutive 8-byte words of the row's 72-byte records
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(a.host_planar_f64) + (size_t)s_off[0] * 9;
+    for (int i = tid; i < n_keep * 9; i += blockDim.x) {
+      const int j = i / 9, f = i - 9 * j;
+      const int pk = s_kept[j];
+      unsigned long long bits = 0ull; // pad / npad
+      if (f < 3) {
+        const float4 p = __ldg(&g[a.planar_cols[rb * a.pr_cap + pk]]);
+        bits = (unsigned long long)__double_as_longlong((double)(f == 0 ? p.x : f == 1 ? p.y : p.z));
+      } else if (f >= 4 && f < 7) {
+        const float4 nrm = a.normals[rb * a.pr_cap + pk];
+        bits = (unsigned long long)__double_as_longlong((double)(f == 4 ? nrm.x : f == 5 ? nrm.y : nrm.z));
+      } else if (f == 8) {
+        bits = a.scan_idx;
       }
-      base_out += __popc(bal);
+      dst[i] = bits;
     }
   }
   // points
@@ -701,9 +726,24 @@ extract_pack_kernel(ExtractArgs a) {
     a.cur_point[(size_t)b * a.kq_cap + s_off[1] + j] = r;
     if (a.host_point) a.host_point[s_off[1] + j] = r;
   }
+  if (a.host_point_f64) {
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(a.host_point_f64) + (size_t)s_off[1] * 5;
+    for (int i = tid; i < nq * 5; i += blockDim.x) {
+      const int j = i / 5, f = i - 5 * j;
+      unsigned long long bits = 0ull; // pad
+      if (f < 3) {
+        const float4 p = __ldg(&g[a.point_cols[rb * a.qr_cap + j]]);
+        bits = (unsigned long long)__double_as_longlong((double)(f == 0 ? p.x : f == 1 ? p.y : p.z));
+      } else if (f == 4) {
+        bits = a.scan_idx;
+      }
+      dst[i] = bits;
+    }
+  }
   // publish: the last CTA to finish writes the counts and raises the host-visible flag
   if (a.flag) {
-    if (a.host_planar || a.host_point) __threadfence_system(); // host records of this CTA first
+    if (a.host_planar || a.host_point || a.host_planar_f64 || a.host_point_f64)
+      __threadfence_system(); // host records of this CTA first
     else __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -750,7 +790,7 @@ void extract_launch(const ExtractArgs &a, int n_scans, cudaStream_t stream, Prof
                            extract_normals_smem(a.cols, a.words, a.pr_cap), stream>>>(a);
   prof.end(FORMGPU_KG_EXTRACT_NORMALS, 1);
   prof.begin(FORMGPU_KG_EXTRACT_PACK);
-  extract_pack_kernel<<<grid, 128, 0, stream>>>(a);
+  extract_pack_kernel<<<grid, 128, (size_t)a.pr_cap * sizeof(uint16_t), stream>>>(a);
   prof.end(FORMGPU_KG_EXTRACT_PACK, 1);
 }
 

@@ -31,6 +31,10 @@ struct ExtractArgs {
   // when the caller only needs the counts (device-resident mode)
   PlanarRec *host_planar;
   PointRec *host_point;
+  // ... or the caller's own page-locked buffers, filled with the API's f64 structs
+  formgpu_planar_feat *host_planar_f64;
+  formgpu_point_feat *host_point_f64;
+  unsigned long long scan_idx;
   int *host_counts;                // [2]
   unsigned *done_counter;          // zero on entry, self-cleaning
   volatile unsigned long long *flag;

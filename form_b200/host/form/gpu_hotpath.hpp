@@ -46,10 +46,23 @@ public:
     const int rc = formgpu_create(&g, device, stream, &m_ctx);
     if (rc != FORMGPU_OK)
       throw HotPathError(std::string("formgpu_create: ") + formgpu_last_error(nullptr));
-    m_planar.resize(formgpu_max_planar(m_ctx));
-    m_point.resize(formgpu_max_point(m_ctx));
+    // page-locked output buffers: the kernels write the keypoint structs straight into them
+    m_planar_cap = formgpu_max_planar(m_ctx);
+    m_point_cap = formgpu_max_point(m_ctx);
+    m_planar = static_cast<PlanarFeat *>(formgpu_alloc_pinned(m_planar_cap * sizeof(PlanarFeat)));
+    m_point = static_cast<PointFeat *>(formgpu_alloc_pinned(m_point_cap * sizeof(PointFeat)));
+    if (!m_planar || !m_point) {
+      formgpu_free_pinned(m_planar);
+      formgpu_free_pinned(m_point);
+      formgpu_destroy(m_ctx);
+      throw HotPathError("formgpu_alloc_pinned failed");
+    }
   }
-  ~GpuHotPath() override { formgpu_destroy(m_ctx); }
+  ~GpuHotPath() override {
+    formgpu_destroy(m_ctx);
+    formgpu_free_pinned(m_planar);
+    formgpu_free_pinned(m_point);
+  }
   GpuHotPath(const GpuHotPath &) = delete;
   GpuHotPath &operator=(const GpuHotPath &) = delete;
 
@@ -59,11 +72,10 @@ public:
                std::vector<PointFeat> &point) override {
     size_t np = 0, nq = 0;
     check(formgpu_extract(m_ctx, reinterpret_cast<const formgpu_point4f *>(scan), n, scan_idx,
-                          reinterpret_cast<formgpu_planar_feat *>(m_planar.data()), m_planar.size(),
-                          &np, reinterpret_cast<formgpu_point_feat *>(m_point.data()),
-                          m_point.size(), &nq));
-    planar.assign(m_planar.begin(), m_planar.begin() + np);
-    point.assign(m_point.begin(), m_point.begin() + nq);
+                          reinterpret_cast<formgpu_planar_feat *>(m_planar), m_planar_cap, &np,
+                          reinterpret_cast<formgpu_point_feat *>(m_point), m_point_cap, &nq));
+    planar.assign(m_planar, m_planar + np);
+    point.assign(m_point, m_point + nq);
   }
 
   /// formgpu_extract into the adapter's own buffers without building vectors (what a
@@ -71,12 +83,11 @@ public:
   void extract_raw(const PointXYZf *scan, size_t n, uint64_t scan_idx, size_t &n_planar,
                    size_t &n_point) {
     check(formgpu_extract(m_ctx, reinterpret_cast<const formgpu_point4f *>(scan), n, scan_idx,
-                          reinterpret_cast<formgpu_planar_feat *>(m_planar.data()), m_planar.size(),
-                          &n_planar, reinterpret_cast<formgpu_point_feat *>(m_point.data()),
-                          m_point.size(), &n_point));
+                          reinterpret_cast<formgpu_planar_feat *>(m_planar), m_planar_cap, &n_planar,
+                          reinterpret_cast<formgpu_point_feat *>(m_point), m_point_cap, &n_point));
   }
-  const std::vector<PlanarFeat> &planar_buffer() const { return m_planar; }
-  const std::vector<PointFeat> &point_buffer() const { return m_point; }
+  const PlanarFeat *planar_buffer() const { return m_planar; }
+  const PointFeat *point_buffer() const { return m_point; }
 
   /// Scan already resident in device memory; nothing is copied back.
   void extract_device(const void *scan_dev, size_t n, uint64_t scan_idx, size_t &n_planar,
@@ -151,8 +162,9 @@ private:
                          formgpu_last_error(m_ctx));
   }
   formgpu_ctx *m_ctx = nullptr;
-  std::vector<PlanarFeat> m_planar;
-  std::vector<PointFeat> m_point;
+  PlanarFeat *m_planar = nullptr; // page-locked, formgpu_max_planar entries
+  PointFeat *m_point = nullptr;
+  size_t m_planar_cap = 0, m_point_cap = 0;
 };
 
 } // namespace form

@@ -148,6 +148,14 @@ int formgpu_extract(formgpu_ctx *ctx, const formgpu_point4f *scan, size_t n, uin
                     formgpu_planar_feat *planar_out, size_t planar_cap, size_t *n_planar,
                     formgpu_point_feat *point_out, size_t point_cap, size_t *n_point);
 
+/* Page-locked, device-mapped host memory (cudaHostAlloc) for callers that do not link
+ * CUDA themselves.  Optional: when `scan` is page-locked the upload is a plain DMA, and
+ * when planar_out / point_out are page-locked and sized formgpu_max_planar / _point the
+ * kernels write the keypoint structs straight into them; pageable buffers work too and
+ * go through a staging copy. */
+void *formgpu_alloc_pinned(size_t bytes);
+void formgpu_free_pinned(void *p);
+
 /* Same, but `scan_dev` is a DEVICE pointer and nothing is copied back: only
  * the counts are returned (used to time the kernels with inputs resident). */
 int formgpu_extract_device(formgpu_ctx *ctx, const formgpu_point4f *scan_dev, size_t n,

@@ -106,3 +106,31 @@ def test_single_row_scan_drops_all_planar():
     rng = np.random.default_rng(5)
     pl, pt = _compare(params, _random_scan(rng, 1, 512, "smooth"))
     assert len(pl) == 0
+
+
+def test_extract_into_pinned_buffers_matches_pageable():
+    """Page-locked caller buffers are filled by the kernel itself (no staging copy): same bytes."""
+    import ctypes as C
+
+    lib = _capi.gpu_lib()
+    rows, cols = synth.shape("os1-64")
+    params = _capi.default_params(rows, cols)
+    scan = synth.scan("os1-64", 2, 5)
+    with _ctx(params) as ctx:
+        pl, pt = ctx.extract(scan, 9)  # pageable numpy buffers
+        capp, capq = ctx.max_planar, ctx.max_point
+        bp = lib.formgpu_alloc_pinned(capp * 72)
+        bq = lib.formgpu_alloc_pinned(capq * 40)
+        assert bp and bq
+        try:
+            a, b = C.c_size_t(), C.c_size_t()
+            rc = lib.formgpu_extract(ctx._h, _capi.ptr(scan), scan.shape[0], 9, C.c_void_p(bp), capp, C.byref(a),
+                                     C.c_void_p(bq), capq, C.byref(b))
+            assert rc == 0 and a.value == len(pl) and b.value == len(pt)
+            got_pl = np.ctypeslib.as_array((C.c_uint8 * (72 * a.value)).from_address(bp)).view(_capi.PLANAR_FEAT)
+            got_pt = np.ctypeslib.as_array((C.c_uint8 * (40 * b.value)).from_address(bq)).view(_capi.POINT_FEAT)
+            assert got_pl.tobytes() == pl.tobytes()
+            assert got_pt.tobytes() == pt.tobytes()
+        finally:
+            lib.formgpu_free_pinned(bp)
+            lib.formgpu_free_pinned(bq)
