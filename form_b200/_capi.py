@@ -197,6 +197,7 @@ FORMHOST_SYMBOLS = {
     "formhost_replay_create": (_vp, [_vp, _pest, _vp]),
     "formhost_replay_ctx": (_vp, [_vp]),
     "formhost_replay_run_device": (_d, [_vp, _sz, _sz, _vp]),
+    "formhost_replay_run_device_multi": (_d, [_vp, _sz, _sz, _sz, _vp]),
     **estimator_symbols("formhost_"),
 }
 

@@ -1,6 +1,9 @@
 // libformhost.so: form::Estimator and the trace replayer over the CUDA hot path.
 #include "form/capi_impl.hpp"
 
+#include <atomic>
+#include <thread>
+
 using namespace form;
 using namespace form::capi;
 
@@ -122,6 +125,45 @@ double formhost_replay_run_device(void *rv, size_t first, size_t last,
     g_error = e.what();
     return -1.0;
   }
+}
+
+/// Several independent sequences on ONE GPU: replay[i] (its own context and stream) is
+/// driven by its own host thread over scans_dev[i] (device pointers of its sequence).
+/// Returns the wall time in seconds from a common start to the last thread finishing
+/// (every replay call is synchronous, so all device work is done by then), < 0 on error.
+double formhost_replay_run_device_multi(void *const *replays, size_t n_replays, size_t first, size_t last,
+                                        const formgpu_point4f *const *const *scans_dev) {
+  std::vector<std::thread> threads;
+  std::vector<int> failed(n_replays, 0);
+  std::atomic<size_t> ready{0};
+  std::atomic<bool> go{false};
+  for (size_t i = 0; i < n_replays; ++i) {
+    threads.emplace_back([&, i] {
+      auto *r = static_cast<ReplayHandle *>(replays[i]);
+      auto *gpu = static_cast<GpuHotPath *>(r->backend.get());
+      ready.fetch_add(1);
+      while (!go.load(std::memory_order_acquire)) {
+      }
+      try {
+        replay(*r->trace, *r->backend, first, last,
+               [&](uint64_t scan_idx, size_t &np, size_t &nq) {
+                 gpu->extract_device(scans_dev[i][scan_idx], r->points_per_scan, scan_idx, np, nq);
+               },
+               r->points_per_scan, r->stats);
+      } catch (const std::exception &e) {
+        failed[i] = 1;
+      }
+    });
+  }
+  while (ready.load() < n_replays) {
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  go.store(true, std::memory_order_release);
+  for (auto &t : threads) t.join();
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  for (int f : failed)
+    if (f) return -1.0;
+  return dt;
 }
 
 void formhost_replay_stats(void *r, uint64_t out[20], double *checksum) {

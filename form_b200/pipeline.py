@@ -182,3 +182,16 @@ class Replay(ReplayBase):
 
     def launch_count(self) -> int:
         return int(_capi.gpu_lib().formgpu_launch_count(self.ctx()))
+
+
+def run_device_multi(replays, first: int, last: int, dev_ptrs_per_replay) -> float:
+    """Replay scans [first, last) of several sequences concurrently on one GPU (one host
+    thread, context and stream per sequence).  Returns the wall time in seconds."""
+    n = len(replays)
+    handles = (C.c_void_p * n)(*[r._h for r in replays])
+    arrays = [_scan_ptr_array(list(p)) for p in dev_ptrs_per_replay]
+    outer = (C.c_void_p * n)(*[C.cast(a, C.c_void_p) for a in arrays])
+    t = _capi.host_lib().formhost_replay_run_device_multi(handles, n, first, last, outer)
+    if t < 0:
+        raise RuntimeError("multi-sequence replay failed")
+    return t
