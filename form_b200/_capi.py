@@ -81,6 +81,26 @@ class EstParams(C.Structure):
     ]
 
 
+class Request(C.Structure):
+    """formgpu_request: one pending call of one sequence of a batch."""
+
+    _fields_ = [
+        ("sequence", C.c_uint32), ("op", C.c_uint32), ("flags", C.c_uint32), ("status", C.c_int32),
+        ("scan", C.c_void_p), ("n_points", C.c_size_t), ("scan_idx", C.c_uint64),
+        ("planar_out", C.c_void_p), ("planar_cap", C.c_size_t), ("n_planar", C.c_size_t),
+        ("point_out", C.c_void_p), ("point_cap", C.c_size_t), ("n_point", C.c_size_t),
+        ("poses", C.c_void_p), ("n_poses", C.c_size_t), ("pose_k", C.c_void_p),
+        ("pairs", C.c_void_p), ("n_pairs", C.c_size_t),
+        ("counts_out", C.c_void_p), ("counts_cap", C.c_size_t), ("n_counts", C.c_size_t),
+        ("out", C.c_void_p), ("scans", C.c_void_p), ("n_scans", C.c_size_t),
+    ]
+
+
+(OP_EXTRACT, OP_MAP_REBUILD, OP_ASSOCIATE, OP_ASSOC_LIN, OP_LINEARIZE, OP_ERROR, OP_COMMIT,
+ OP_REMOVE) = range(8)
+REQ_SCAN_ON_DEVICE = 1
+
+
 def default_est_params(rows: int = 64, cols: int = 1024, **overrides) -> EstParams:
     """Estimator::Params defaults (python/bindings.cpp:66-88 of FORM).  Keys of
     formgpu_params and of the estimator-level struct can both be overridden."""
@@ -153,6 +173,15 @@ FORMGPU_SYMBOLS = {
     "formgpu_profile_read": (_i, [_vp, _vp, _vp]),
     "formgpu_launch_count": (_u64, [_vp]),
     "formgpu_synchronize": (_i, [_vp]),
+    "formgpu_batch_create": (_i, [C.POINTER(Params), _i, _vp, _sz, C.POINTER(_vp)]),
+    "formgpu_batch_destroy": (None, [_vp]),
+    "formgpu_batch_size": (_sz, [_vp]),
+    "formgpu_batch_ctx": (_vp, [_vp, _sz]),
+    "formgpu_batch_submit": (_i, [_vp, _vp, _sz]),
+    "formgpu_batch_last_error": (C.c_char_p, [_vp]),
+    "formgpu_batch_profile_enable": (_i, [_vp, _i]),
+    "formgpu_batch_profile_read": (_i, [_vp, _vp, _vp]),
+    "formgpu_batch_launch_count": (_u64, [_vp]),
 }
 
 _pest = C.POINTER(EstParams)
@@ -198,6 +227,13 @@ FORMHOST_SYMBOLS = {
     "formhost_replay_ctx": (_vp, [_vp]),
     "formhost_replay_run_device": (_d, [_vp, _sz, _sz, _vp]),
     "formhost_replay_run_device_multi": (_d, [_vp, _sz, _sz, _sz, _vp]),
+    "formhost_batch_replay_create": (_vp, [_vp, _sz, _pest, _vp]),
+    "formhost_batch_replay_destroy": (None, [_vp]),
+    "formhost_batch_replay_batch": (_vp, [_vp]),
+    "formhost_batch_replay_run": (_d, [_vp, _sz, _sz, _vp, _i, _psz]),
+    "formhost_batch_replay_run_multi": (_d, [_vp, _sz, _sz, _sz, _vp, _i]),
+    "formhost_batch_replay_stats": (None, [_vp, _i, _vp, C.POINTER(_d)]),
+    "formhost_batch_replay_reset_stats": (None, [_vp]),
     **estimator_symbols("formhost_"),
 }
 

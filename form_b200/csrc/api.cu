@@ -159,6 +159,7 @@ static int create_impl(formgpu_ctx *ctx) {
   // stage 1
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_scan, B * ctx->n_points));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_valid_bits, B * R * ctx->words));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_row_box, B * R * ctx->words * 2));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_planar_cols, B * R * ctx->pr_cap));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_planar_cnt, B * R));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_point_cols, B * R * ctx->qr_cap));
@@ -269,7 +270,7 @@ void formgpu_destroy(formgpu_ctx *ctx) {
     if (p) cudaFreeHost(p);
     p = nullptr;
   };
-  F(ctx->d_scan); F(ctx->d_valid_bits); F(ctx->d_planar_cols); F(ctx->d_planar_cnt);
+  F(ctx->d_scan); F(ctx->d_valid_bits); F(ctx->d_row_box); F(ctx->d_planar_cols); F(ctx->d_planar_cnt);
   F(ctx->d_point_cols); F(ctx->d_point_cnt); F(ctx->d_normals); F(ctx->d_closest);
   F(ctx->d_keep_cnt); F(ctx->d_cur_counts);
   for (int i = 0; i < 2; ++i) { F(ctx->d_cur_planar_buf[i]); F(ctx->d_cur_point_buf[i]); F(ctx->d_hist_cnt[i][0]); F(ctx->d_hist_cnt[i][1]); }
@@ -338,6 +339,7 @@ static ExtractArgs make_extract_args(formgpu_ctx *ctx, const float4 *scan_dev, b
   a.radius = P.radius;
   a.scan = scan_dev;
   a.valid_bits = ctx->d_valid_bits;
+  a.row_box = ctx->d_row_box;
   a.planar_cols = ctx->d_planar_cols;
   a.planar_cnt = ctx->d_planar_cnt;
   a.point_cols = ctx->d_point_cols;
@@ -357,6 +359,7 @@ static ExtractArgs make_extract_args(formgpu_ctx *ctx, const float4 *scan_dev, b
   a.done_counter = ctx->d_counters + ctx->counter_cap + 2;
   a.flag = publish ? ctx->h_flags + 2 : nullptr;
   a.seq = publish ? ++ctx->seq : 0;
+  a.done_target = (unsigned)ctx->rows; // one scan per launch item
   return a;
 }
 
@@ -373,20 +376,27 @@ static void *mapped_alias(void *host_ptr) {
   return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
 }
 
-static int extract_run(formgpu_ctx *ctx, const float4 *scan_dev, uint64_t scan_idx,
-                       bool host_records, formgpu_planar_feat *direct_planar = nullptr,
-                       formgpu_point_feat *direct_point = nullptr) {
+} // extern "C"
+
+namespace formgpu {
+
+// stage 1, split so that a batched submit can build the argument blocks of several
+// contexts, launch once, and then complete each context
+void extract_prepare(formgpu_ctx *ctx, const float4 *scan_dev, uint64_t scan_idx, bool host_records,
+                     formgpu_planar_feat *direct_planar, formgpu_point_feat *direct_point,
+                     ExtractArgs &a) {
   ctx->cur_buf ^= 1;
   ctx->d_cur_planar = ctx->d_cur_planar_buf[ctx->cur_buf];
   ctx->d_cur_point = ctx->d_cur_point_buf[ctx->cur_buf];
   // the pack kernel writes the counts (and, for host callers, the compact keypoint
   // records) into mapped pinned memory and raises a flag: no memcpy, no stream sync
-  ExtractArgs a = make_extract_args(ctx, scan_dev, false, host_records, true);
+  a = make_extract_args(ctx, scan_dev, false, host_records, true);
   a.host_planar_f64 = direct_planar;
   a.host_point_f64 = direct_point;
   a.scan_idx = scan_idx;
-  extract_launch(a, 1, ctx->stream, ctx->prof);
-  FORMGPU_CUDA(ctx, cudaGetLastError());
+}
+
+int extract_finish(formgpu_ctx *ctx, const ExtractArgs &a, uint64_t scan_idx) {
   const int w = wait_flag(ctx, 2, a.seq);
   if (w) return w;
   ctx->cur_n[0] = ctx->h_counts[0];
@@ -398,6 +408,64 @@ static int extract_run(formgpu_ctx *ctx, const float4 *scan_dev, uint64_t scan_i
   ctx->have_current = true;
   return FORMGPU_OK;
 }
+
+// device aliases of page-locked caller buffers that can hold the worst case (the pack
+// kernel then writes the f64 API structs itself); nullptr otherwise
+void extract_direct_targets(formgpu_ctx *ctx, formgpu_planar_feat *planar_out, size_t planar_cap,
+                            formgpu_point_feat *point_out, size_t point_cap,
+                            formgpu_planar_feat *&dp, formgpu_point_feat *&dq) {
+  dp = nullptr;
+  dq = nullptr;
+  if (planar_out && point_out && planar_cap >= ctx->kp_cap && point_cap >= ctx->kq_cap) {
+    if (ctx->direct_probe[0] != planar_out || ctx->direct_probe[1] != point_out) {
+      ctx->direct_probe[0] = planar_out;
+      ctx->direct_probe[1] = point_out;
+      ctx->direct_alias[0] = mapped_alias(planar_out);
+      ctx->direct_alias[1] = mapped_alias(point_out);
+    }
+    if (ctx->direct_alias[0] && ctx->direct_alias[1]) {
+      dp = static_cast<formgpu_planar_feat *>(ctx->direct_alias[0]);
+      dq = static_cast<formgpu_point_feat *>(ctx->direct_alias[1]);
+    }
+  }
+}
+
+// widen the compact staging records (mapped pinned, written by the pack kernel) to the
+// API's f64 structs
+int extract_widen(formgpu_ctx *ctx, uint64_t scan_idx, formgpu_planar_feat *planar_out, size_t planar_cap,
+                  formgpu_point_feat *point_out, size_t point_cap) {
+  const size_t np = (size_t)ctx->cur_n[0], nq = (size_t)ctx->cur_n[1];
+  if ((np && !planar_out) || (nq && !point_out) || np > planar_cap || nq > point_cap)
+    return fail(ctx, FORMGPU_ERR_CAPACITY, "formgpu_extract: output buffers too small");
+  for (size_t i = 0; i < np; ++i) {
+    const PlanarRec &r = ctx->h_planar[i];
+    formgpu_planar_feat &o = planar_out[i];
+    o.x = r.x; o.y = r.y; o.z = r.z; o.pad = 0.0;
+    o.nx = r.nx; o.ny = r.ny; o.nz = r.nz; o.npad = 0.0;
+    o.scan = scan_idx;
+  }
+  for (size_t i = 0; i < nq; ++i) {
+    const PointRec &r = ctx->h_point[i];
+    formgpu_point_feat &o = point_out[i];
+    o.x = r.x; o.y = r.y; o.z = r.z; o.pad = 0.0;
+    o.scan = scan_idx;
+  }
+  return FORMGPU_OK;
+}
+
+} // namespace formgpu
+
+static int extract_run(formgpu_ctx *ctx, const float4 *scan_dev, uint64_t scan_idx,
+                       bool host_records, formgpu_planar_feat *direct_planar = nullptr,
+                       formgpu_point_feat *direct_point = nullptr) {
+  ExtractArgs a;
+  extract_prepare(ctx, scan_dev, scan_idx, host_records, direct_planar, direct_point, a);
+  extract_launch(a, 1, ctx->stream, ctx->prof);
+  FORMGPU_CUDA(ctx, cudaGetLastError());
+  return extract_finish(ctx, a, scan_idx);
+}
+
+extern "C" {
 
 int formgpu_extract(formgpu_ctx *ctx, const formgpu_point4f *scan, size_t n, uint64_t scan_idx,
                     formgpu_planar_feat *planar_out, size_t planar_cap, size_t *n_planar,
@@ -418,44 +486,15 @@ int formgpu_extract(formgpu_ctx *ctx, const formgpu_point4f *scan, size_t n, uin
   // staging records and are widened here.
   formgpu_planar_feat *dp = nullptr;
   formgpu_point_feat *dq = nullptr;
-  if (planar_out && point_out && planar_cap >= ctx->kp_cap && point_cap >= ctx->kq_cap) {
-    if (ctx->direct_probe[0] != planar_out || ctx->direct_probe[1] != point_out) {
-      ctx->direct_probe[0] = planar_out;
-      ctx->direct_probe[1] = point_out;
-      ctx->direct_alias[0] = mapped_alias(planar_out);
-      ctx->direct_alias[1] = mapped_alias(point_out);
-    }
-    if (ctx->direct_alias[0] && ctx->direct_alias[1]) {
-      dp = static_cast<formgpu_planar_feat *>(ctx->direct_alias[0]);
-      dq = static_cast<formgpu_point_feat *>(ctx->direct_alias[1]);
-    }
-  }
+  extract_direct_targets(ctx, planar_out, planar_cap, point_out, point_cap, dp, dq);
   const bool direct = dp != nullptr;
   const int rc = extract_run(ctx, ctx->d_scan, scan_idx, !direct, dp, dq);
   if (rc) return rc;
   ctx->cur_device_resident = false;
-  const size_t np = (size_t)ctx->cur_n[0], nq = (size_t)ctx->cur_n[1];
-  *n_planar = np;
-  *n_point = nq;
+  *n_planar = (size_t)ctx->cur_n[0];
+  *n_point = (size_t)ctx->cur_n[1];
   if (direct) return FORMGPU_OK;
-  if ((np && !planar_out) || (nq && !point_out) || np > planar_cap || nq > point_cap)
-    return fail(ctx, FORMGPU_ERR_CAPACITY, "formgpu_extract: output buffers too small");
-  // the compact lossless f32 records already sit in mapped pinned memory (written by
-  // the pack kernel over PCIe); widen them to the f64 API structs here
-  for (size_t i = 0; i < np; ++i) {
-    const PlanarRec &r = ctx->h_planar[i];
-    formgpu_planar_feat &o = planar_out[i];
-    o.x = r.x; o.y = r.y; o.z = r.z; o.pad = 0.0;
-    o.nx = r.nx; o.ny = r.ny; o.nz = r.nz; o.npad = 0.0;
-    o.scan = scan_idx;
-  }
-  for (size_t i = 0; i < nq; ++i) {
-    const PointRec &r = ctx->h_point[i];
-    formgpu_point_feat &o = point_out[i];
-    o.x = r.x; o.y = r.y; o.z = r.z; o.pad = 0.0;
-    o.scan = scan_idx;
-  }
-  return FORMGPU_OK;
+  return extract_widen(ctx, scan_idx, planar_out, planar_cap, point_out, point_cap);
 }
 
 int formgpu_extract_device(formgpu_ctx *ctx, const formgpu_point4f *scan_dev, size_t n,

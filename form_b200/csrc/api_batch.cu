@@ -1,0 +1,573 @@
+// C-ABI (include/formgpu.h): batched submit - the hot-path calls of MANY independent
+// sequences in one launch per kernel.
+//
+// One sequence alone cannot fill a B200: a per-scan request is < 1 MB and every call is
+// a dependent round trip.  A formgpu_batch owns S contexts (one per
+// sequence) on one stream; formgpu_batch_submit takes at most one pending call per
+// sequence, groups the calls by kind and issues ONE grid per kernel for each group -
+// blockIdx.z (or blockIdx.y for stage 1) selects the sequence, whose argument block the
+// CTA copies from a device array.  The kernel bodies are the single-sequence ones, so
+// the results are bit-identical to S separate contexts; only the launch is shared.
+// All groups are queued before the first wait, so the GPU runs them back to back while
+// the host collects results through the same mapped-memory flags as the single calls.
+#include "api_common.hpp"
+
+#include <algorithm>
+#include <functional>
+#include <new>
+
+using namespace formgpu;
+
+struct formgpu_batch {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::vector<formgpu_ctx *> ctx;
+  mutable std::string err;
+  // argument staging: pinned host ring + device mirror, bump-allocated per submit
+  unsigned char *h_args = nullptr, *d_args = nullptr;
+  size_t args_cap = 0, args_used = 0;
+  cudaEvent_t ev_args = nullptr;
+  Profiler prof;
+  // scratch reused across submits
+  std::vector<AssocPlan> assoc_plans;
+  std::vector<ExtractArgs> extract_args;
+  std::vector<CommitPlan> commit_plans;
+  std::vector<std::vector<int>> lin_indices;
+  std::vector<unsigned long long> lin_seqs;
+  std::vector<LinTask> tasks_scratch;
+};
+
+namespace {
+
+std::string g_batch_error;
+
+int bfail(formgpu_batch *b, int code, const std::string &msg) {
+  if (b) b->err = msg;
+  return code;
+}
+
+#define BATCH_CUDA(b, expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return bfail((b), FORMGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// make room for `bytes` more staged argument bytes (contents staged so far are kept)
+int ensure_args(formgpu_batch *b, size_t bytes) {
+  if (b->args_used + bytes <= b->args_cap) return FORMGPU_OK;
+  // no kernel of this submit has been queued yet (arguments are uploaded once, after the
+  // last group is staged) and the previous submit's were waited for at submit start
+  BATCH_CUDA(b, cudaStreamSynchronize(b->stream));
+  size_t cap = std::max<size_t>(b->args_cap * 2, 1 << 20);
+  while (cap < b->args_used + bytes) cap *= 2;
+  unsigned char *h = nullptr, *d = nullptr;
+  BATCH_CUDA(b, cudaHostAlloc(reinterpret_cast<void **>(&h), cap, cudaHostAllocDefault));
+  BATCH_CUDA(b, cudaMalloc(reinterpret_cast<void **>(&d), cap));
+  if (b->h_args) {
+    std::memcpy(h, b->h_args, b->args_used);
+    cudaFreeHost(b->h_args);
+  }
+  if (b->d_args) cudaFree(b->d_args);
+  b->h_args = h;
+  b->d_args = d;
+  b->args_cap = cap;
+  return FORMGPU_OK;
+}
+
+// stage `count` argument blocks; *offset = their position in the device mirror once the
+// submit's single upload has run
+template <typename T> int stage_args(formgpu_batch *b, const T *src, size_t count, size_t *offset) {
+  const size_t bytes = round_up(count * sizeof(T), 256);
+  const int rc = ensure_args(b, bytes);
+  if (rc) return rc;
+  std::memcpy(b->h_args + b->args_used, src, count * sizeof(T));
+  *offset = b->args_used;
+  b->args_used += bytes;
+  return FORMGPU_OK;
+}
+template <typename T> const T *staged(const formgpu_batch *b, size_t offset) {
+  return reinterpret_cast<const T *>(b->d_args + offset);
+}
+
+// Linearisation tasks of several contexts in up to two launches: pairs with many
+// correspondences get a cluster of 8 CTAs, the (many) small ones one or two, so that
+// neither the big pairs serialise on one SM nor the small ones waste seven CTAs.
+int stage_lin_groups(formgpu_batch *b, const std::vector<LinArgs> &ctx_args, const std::vector<LinTask> &tasks,
+                     const std::vector<uint32_t> &size_hint, bool error_only,
+                     std::vector<std::function<int()>> &launchers) {
+  if (tasks.empty()) return FORMGPU_OK;
+  size_t off_ctx = 0, off_tasks = 0;
+  int rc = stage_args(b, ctx_args.data(), ctx_args.size(), &off_ctx);
+  if (rc) return rc;
+  // stable partition: large tasks first
+  constexpr uint32_t kLarge = 4096;
+  std::vector<LinTask> ordered;
+  ordered.reserve(tasks.size());
+  size_t n_large = 0;
+  for (size_t i = 0; i < tasks.size(); ++i)
+    if (size_hint[i] >= kLarge) {
+      ordered.push_back(tasks[i]);
+      ++n_large;
+    }
+  for (size_t i = 0; i < tasks.size(); ++i)
+    if (size_hint[i] < kLarge) ordered.push_back(tasks[i]);
+  rc = stage_args(b, ordered.data(), ordered.size(), &off_tasks);
+  if (rc) return rc;
+  const size_t n_small = ordered.size() - n_large;
+  launchers.push_back([=]() -> int {
+    const LinArgs *d_ctx = staged<LinArgs>(b, off_ctx);
+    const LinTask *d_tasks = staged<LinTask>(b, off_tasks);
+    if (n_large)
+      BATCH_CUDA(b, linearize_batch_launch(d_ctx, d_tasks, (int)n_large, kLinCluster, error_only, b->stream, b->prof));
+    if (n_small) {
+      // few small tasks: still spread them (2 CTAs each) to keep the tail short
+      const int cluster = n_small * 2 <= 2 * 148 ? 2 : 1;
+      BATCH_CUDA(b, linearize_batch_launch(d_ctx, d_tasks + n_large, (int)n_small, cluster, error_only,
+                                           b->stream, b->prof));
+    }
+    return FORMGPU_OK;
+  });
+  return FORMGPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *formgpu_batch_last_error(const formgpu_batch *b) {
+  return b ? b->err.c_str() : g_batch_error.c_str();
+}
+
+int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size_t n_sequences,
+                         formgpu_batch **out) {
+  if (!p || !out || n_sequences == 0 || n_sequences > 4096) {
+    g_batch_error = "formgpu_batch_create: bad argument";
+    return FORMGPU_ERR_INVALID_ARG;
+  }
+  *out = nullptr;
+  formgpu_batch *b = new (std::nothrow) formgpu_batch();
+  if (!b) return FORMGPU_ERR_CAPACITY;
+  b->device = device;
+  b->stream = static_cast<cudaStream_t>(stream);
+  auto bail = [&](int rc, const std::string &msg) {
+    g_batch_error = msg;
+    formgpu_batch_destroy(b);
+    return rc;
+  };
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return bail(FORMGPU_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return bail(FORMGPU_ERR_INVALID_ARG, "device index out of range");
+  if (cudaSetDevice(device) != cudaSuccess) return bail(FORMGPU_ERR_CUDA, "cudaSetDevice failed");
+  if (!b->stream) {
+    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess)
+      return bail(FORMGPU_ERR_CUDA, "cudaStreamCreate failed");
+    b->own_stream = true;
+  }
+  b->prof.stream = b->stream;
+  if (cudaEventCreateWithFlags(&b->ev_args, cudaEventDisableTiming) != cudaSuccess)
+    return bail(FORMGPU_ERR_CUDA, "cudaEventCreate failed");
+  for (size_t i = 0; i < n_sequences; ++i) {
+    formgpu_ctx *c = nullptr;
+    const int rc = formgpu_create(p, device, b->stream, &c); // every context shares the batch stream
+    if (rc != FORMGPU_OK) return bail(rc, std::string("formgpu_create: ") + formgpu_last_error(nullptr));
+    b->ctx.push_back(c);
+  }
+  b->assoc_plans.resize(n_sequences);
+  b->extract_args.resize(n_sequences);
+  b->commit_plans.resize(n_sequences);
+  b->lin_indices.resize(n_sequences);
+  b->lin_seqs.resize(n_sequences);
+  *out = b;
+  return FORMGPU_OK;
+}
+
+void formgpu_batch_destroy(formgpu_batch *b) {
+  if (!b) return;
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (formgpu_ctx *c : b->ctx) formgpu_destroy(c);
+  if (b->h_args) cudaFreeHost(b->h_args);
+  if (b->d_args) cudaFree(b->d_args);
+  if (b->ev_args) cudaEventDestroy(b->ev_args);
+  b->prof.destroy();
+  if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+size_t formgpu_batch_size(const formgpu_batch *b) { return b ? b->ctx.size() : 0; }
+
+formgpu_ctx *formgpu_batch_ctx(formgpu_batch *b, size_t i) {
+  return (b && i < b->ctx.size()) ? b->ctx[i] : nullptr;
+}
+
+int formgpu_batch_profile_enable(formgpu_batch *b, int on) {
+  if (!b) return FORMGPU_ERR_INVALID_ARG;
+  b->prof.collect();
+  b->prof.timing = on != 0;
+  return FORMGPU_OK;
+}
+
+int formgpu_batch_profile_read(formgpu_batch *b, double ms[FORMGPU_KG_COUNT],
+                               uint64_t launches[FORMGPU_KG_COUNT]) {
+  if (!b) return FORMGPU_ERR_INVALID_ARG;
+  b->prof.collect();
+  for (int g = 0; g < FORMGPU_KG_COUNT; ++g) {
+    if (ms) ms[g] = b->prof.group[g].ms;
+    if (launches) launches[g] = b->prof.group[g].launches;
+    b->prof.group[g] = GroupProf();
+  }
+  return FORMGPU_OK;
+}
+
+uint64_t formgpu_batch_launch_count(const formgpu_batch *b) { return b ? b->prof.total_launches : 0; }
+
+int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
+  if (!b) return FORMGPU_ERR_INVALID_ARG;
+  if (n == 0) return FORMGPU_OK;
+  if (!reqs) return bfail(b, FORMGPU_ERR_INVALID_ARG, "formgpu_batch_submit: null requests");
+  BATCH_CUDA(b, cudaSetDevice(b->device));
+  const size_t S = b->ctx.size();
+
+  // ---- validate: known ops, one request per sequence ----
+  std::vector<uint8_t> seen(S, 0);
+  std::vector<size_t> by_op[FORMGPU_OP_COUNT];
+  for (size_t r = 0; r < n; ++r) {
+    formgpu_request &q = reqs[r];
+    q.status = FORMGPU_OK;
+    if (q.sequence >= S || q.op >= FORMGPU_OP_COUNT)
+      return bfail(b, FORMGPU_ERR_INVALID_ARG, "formgpu_batch_submit: bad sequence index or op");
+    if (seen[q.sequence])
+      return bfail(b, FORMGPU_ERR_INVALID_ARG, "formgpu_batch_submit: two requests for one sequence");
+    seen[q.sequence] = 1;
+    by_op[q.op].push_back(r);
+  }
+  // previous submit's argument uploads must have been consumed before the ring restarts
+  BATCH_CUDA(b, cudaEventSynchronize(b->ev_args));
+  b->args_used = 0;
+  int first_error = FORMGPU_OK;
+  auto set_status = [&](formgpu_request &q, int rc) {
+    q.status = rc;
+    if (rc != FORMGPU_OK && first_error == FORMGPU_OK) {
+      first_error = rc;
+      b->err = std::string("sequence ") + std::to_string(q.sequence) + ": " + formgpu_last_error(b->ctx[q.sequence]);
+    }
+  };
+
+  // =====================================================================================
+  // build phase: argument blocks of every group are staged in pinned memory; ONE upload
+  // and then every group's kernels go onto the stream before the first wait
+  // =====================================================================================
+  std::vector<std::function<int()>> launchers;
+
+  // ---- host-only: remove ----
+  for (size_t r : by_op[FORMGPU_OP_REMOVE]) {
+    formgpu_request &q = reqs[r];
+    set_status(q, formgpu_remove_scans(b->ctx[q.sequence], q.scans, q.n_scans));
+  }
+
+  // ---- stage 1 ----
+  std::vector<size_t> live_extract;
+  {
+    std::vector<ExtractArgs> items;
+    for (size_t r : by_op[FORMGPU_OP_EXTRACT]) {
+      formgpu_request &q = reqs[r];
+      formgpu_ctx *ctx = b->ctx[q.sequence];
+      if (!q.scan) {
+        set_status(q, fail(ctx, FORMGPU_ERR_INVALID_ARG, "extract: null scan"));
+        continue;
+      }
+      if (q.n_points != ctx->n_points) {
+        set_status(q, fail(ctx, FORMGPU_ERR_BAD_SCAN_SIZE,
+                           "Provided scan does not match the expected size " +
+                               std::to_string(ctx->n_points) + " != " + std::to_string(q.n_points)));
+        continue;
+      }
+      const bool on_device = (q.flags & FORMGPU_REQ_SCAN_ON_DEVICE) != 0;
+      const float4 *scan_dev = reinterpret_cast<const float4 *>(q.scan);
+      formgpu_planar_feat *dp = nullptr;
+      formgpu_point_feat *dq = nullptr;
+      bool host_records = false;
+      if (!on_device) {
+        BATCH_CUDA(b, cudaMemcpyAsync(ctx->d_scan, q.scan, q.n_points * sizeof(float4),
+                                      cudaMemcpyHostToDevice, b->stream));
+        scan_dev = ctx->d_scan;
+        extract_direct_targets(ctx, q.planar_out, q.planar_cap, q.point_out, q.point_cap, dp, dq);
+        host_records = dp == nullptr && (q.planar_out || q.point_out);
+      }
+      ExtractArgs &a = b->extract_args[q.sequence];
+      extract_prepare(ctx, scan_dev, q.scan_idx, host_records, dp, dq, a);
+      ctx->cur_device_resident = on_device;
+      items.push_back(a);
+      live_extract.push_back(r);
+    }
+    if (!items.empty()) {
+      size_t off = 0;
+      const int rc = stage_args(b, items.data(), items.size(), &off);
+      if (rc) return rc;
+      const ExtractArgs shape = items[0];
+      const int n_items = (int)items.size();
+      launchers.push_back([=]() -> int {
+        extract_batch_launch(shape, staged<ExtractArgs>(b, off), n_items, b->stream, b->prof);
+        BATCH_CUDA(b, cudaGetLastError());
+        return FORMGPU_OK;
+      });
+    }
+  }
+
+  // ---- reparative map rebuild ----
+  {
+    std::vector<MapArgs> items;
+    std::vector<MapClearRegion> regions;
+    int max_points = 0;
+    uint32_t max_hash = 0;
+    size_t max_clear = 0;
+    for (size_t r : by_op[FORMGPU_OP_MAP_REBUILD]) {
+      formgpu_request &q = reqs[r];
+      formgpu_ctx *ctx = b->ctx[q.sequence];
+      if (q.n_poses && !q.poses) {
+        set_status(q, fail(ctx, FORMGPU_ERR_INVALID_ARG, "map_rebuild: null poses"));
+        continue;
+      }
+      MapArgs a[2];
+      MapClearRegion clear;
+      const int rc = map_rebuild_prepare(ctx, q.poses, q.n_poses, b->stream, a, clear);
+      if (rc) {
+        set_status(q, rc);
+        continue;
+      }
+      items.push_back(a[0]);
+      items.push_back(a[1]);
+      regions.push_back(clear);
+      max_points = std::max(max_points, std::max(a[0].n_total, a[1].n_total));
+      max_hash = std::max(max_hash, std::max(a[0].hash_mask, a[1].hash_mask) + 1);
+      max_clear = std::max(max_clear, clear.bytes);
+    }
+    if (!regions.empty()) {
+      size_t off_items = 0, off_regions = 0;
+      int rc = stage_args(b, items.data(), items.size(), &off_items);
+      if (rc) return rc;
+      rc = stage_args(b, regions.data(), regions.size(), &off_regions);
+      if (rc) return rc;
+      const int n_items = (int)regions.size();
+      launchers.push_back([=]() -> int {
+        map_build_batch_launch(staged<MapArgs>(b, off_items), staged<MapClearRegion>(b, off_regions), n_items,
+                               max_points, max_hash, max_clear, b->stream, b->prof);
+        BATCH_CUDA(b, cudaGetLastError());
+        return FORMGPU_OK;
+      });
+    }
+  }
+
+  // ---- association (+ fused linearisation of the current scan's pairs) ----
+  std::vector<size_t> live_assoc;
+  {
+    std::vector<AssocArgs> aitems;
+    std::vector<SegmentArgs> sitems;
+    std::vector<LinArgs> lin_ctx;
+    std::vector<LinTask> &lin_tasks = b->tasks_scratch;
+    std::vector<uint32_t> hints;
+    lin_tasks.clear();
+    int max_query = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int op = pass == 0 ? FORMGPU_OP_ASSOCIATE : FORMGPU_OP_ASSOC_LIN;
+      for (size_t r : by_op[op]) {
+        formgpu_request &q = reqs[r];
+        formgpu_ctx *ctx = b->ctx[q.sequence];
+        const formgpu_pose *pose_k = q.pose_k;
+        if (op == FORMGPU_OP_ASSOC_LIN) {
+          pose_k = nullptr;
+          if (q.poses && q.out && ctx->have_current)
+            for (size_t p = 0; p < q.n_poses; ++p)
+              if (q.poses[p].scan == ctx->cur_scan) pose_k = &q.poses[p].pose;
+        }
+        if (!pose_k) {
+          set_status(q, fail(ctx, FORMGPU_ERR_INVALID_ARG, "associate: missing pose / output argument"));
+          continue;
+        }
+        AssocPlan &plan = b->assoc_plans[q.sequence];
+        const bool want_blocks = op == FORMGPU_OP_ASSOC_LIN;
+        const int rc = assoc_prepare(ctx, pose_k, want_blocks ? q.poses : nullptr, q.n_poses, want_blocks, plan);
+        if (rc) {
+          set_status(q, rc);
+          continue;
+        }
+        live_assoc.push_back(r);
+        if (!plan.any_query) continue;
+        aitems.push_back(plan.aa[0]);
+        aitems.push_back(plan.aa[1]);
+        sitems.push_back(plan.sa[0]);
+        sitems.push_back(plan.sa[1]);
+        max_query = std::max(max_query, std::max(plan.nq[0], plan.nq[1]));
+        if (plan.fused && !plan.lin_tasks.empty()) {
+          LinArgs la;
+          lin_make_args(ctx, (int)plan.lin_tasks.size(), la);
+          plan.lin_seq = la.seq;
+          const uint32_t ci = (uint32_t)lin_ctx.size();
+          lin_ctx.push_back(la);
+          for (size_t k = 0; k < plan.lin_tasks.size(); ++k) {
+            LinTask t = plan.lin_tasks[k];
+            t.ctx_index = ci;
+            lin_tasks.push_back(t);
+            // size estimate: the pair's count after the previous association of this scan
+            const PairEntry &e = ctx->h_pair_table[(size_t)plan.slot_k * ctx->W + plan.lin_slots[k]];
+            const uint32_t prev = e.n_planar + e.n_point;
+            hints.push_back(prev ? prev : (uint32_t)(plan.nq[0] + plan.nq[1]) / 4u);
+          }
+        } else if (plan.fused) {
+          LinArgs la;
+          lin_make_args(ctx, 0, la); // no other scan has a pose: nothing to linearise
+          plan.lin_seq = la.seq;
+        }
+      }
+    }
+    if (!aitems.empty()) {
+      size_t off_a = 0, off_s = 0;
+      int rc = stage_args(b, aitems.data(), aitems.size(), &off_a);
+      if (rc) return rc;
+      rc = stage_args(b, sitems.data(), sitems.size(), &off_s);
+      if (rc) return rc;
+      const int n_items = (int)aitems.size() / 2;
+      launchers.push_back([=]() -> int {
+        assoc_batch_launch(staged<AssocArgs>(b, off_a), n_items, max_query, b->stream, b->prof);
+        segment_build_batch_launch(staged<SegmentArgs>(b, off_s), n_items, max_query, b->stream, b->prof);
+        BATCH_CUDA(b, cudaGetLastError());
+        return FORMGPU_OK;
+      });
+      rc = stage_lin_groups(b, lin_ctx, lin_tasks, hints, false, launchers);
+      if (rc) return rc;
+    }
+  }
+
+  // ---- linearisation / error of listed pairs ----
+  std::vector<size_t> live_lin[2];
+  for (int eo = 0; eo < 2; ++eo) {
+    const int op = eo ? FORMGPU_OP_ERROR : FORMGPU_OP_LINEARIZE;
+    const size_t per_pair = eo ? 1 : 91;
+    std::vector<LinArgs> lin_ctx;
+    std::vector<LinTask> &lin_tasks = b->tasks_scratch;
+    std::vector<uint32_t> hints;
+    std::vector<LinTask> tasks;
+    lin_tasks.clear();
+    for (size_t r : by_op[op]) {
+      formgpu_request &q = reqs[r];
+      formgpu_ctx *ctx = b->ctx[q.sequence];
+      if (q.n_pairs == 0) {
+        b->lin_indices[q.sequence].clear();
+        live_lin[eo].push_back(r);
+        b->lin_seqs[q.sequence] = 0;
+        continue;
+      }
+      if (!q.pairs || !q.out || (q.n_poses && !q.poses)) {
+        set_status(q, fail(ctx, FORMGPU_ERR_INVALID_ARG, "linearize: null argument"));
+        continue;
+      }
+      const int rc = lin_build_tasks(ctx, q.pairs, q.n_pairs, q.poses, q.n_poses, per_pair, q.out, tasks,
+                                     b->lin_indices[q.sequence]);
+      if (rc) {
+        set_status(q, rc);
+        continue;
+      }
+      LinArgs la;
+      lin_make_args(ctx, (int)tasks.size(), la);
+      b->lin_seqs[q.sequence] = la.seq;
+      live_lin[eo].push_back(r);
+      if (tasks.empty()) continue;
+      const uint32_t ci = (uint32_t)lin_ctx.size();
+      lin_ctx.push_back(la);
+      for (LinTask &t : tasks) {
+        t.ctx_index = ci;
+        lin_tasks.push_back(t);
+        hints.push_back(t.n_planar + t.n_point);
+      }
+    }
+    const int rc = stage_lin_groups(b, lin_ctx, lin_tasks, hints, eo != 0, launchers);
+    if (rc) return rc;
+  }
+
+  // ---- commit ----
+  std::vector<size_t> live_commit;
+  {
+    std::vector<CommitArgs> items;
+    int max_query = 0;
+    for (size_t r : by_op[FORMGPU_OP_COMMIT]) {
+      formgpu_request &q = reqs[r];
+      formgpu_ctx *ctx = b->ctx[q.sequence];
+      CommitPlan &plan = b->commit_plans[q.sequence];
+      const int rc = commit_prepare(ctx, plan);
+      if (rc) {
+        set_status(q, rc);
+        continue;
+      }
+      live_commit.push_back(r);
+      items.push_back(plan.ca[0]);
+      items.push_back(plan.ca[1]);
+      max_query = std::max(max_query, std::max(plan.ca[0].n_query, plan.ca[1].n_query));
+    }
+    if (!items.empty() && max_query > 0) {
+      size_t off = 0;
+      const int rc = stage_args(b, items.data(), items.size(), &off);
+      if (rc) return rc;
+      const int n_items = (int)items.size() / 2;
+      launchers.push_back([=]() -> int {
+        commit_batch_launch(staged<CommitArgs>(b, off), n_items, max_query, b->stream, b->prof);
+        BATCH_CUDA(b, cudaGetLastError());
+        return FORMGPU_OK;
+      });
+    }
+  }
+  // one upload for the whole submit, then every group's kernels
+  if (b->args_used)
+    BATCH_CUDA(b, cudaMemcpyAsync(b->d_args, b->h_args, b->args_used, cudaMemcpyHostToDevice, b->stream));
+  for (auto &launch : launchers) {
+    const int rc = launch();
+    if (rc) return rc;
+  }
+  BATCH_CUDA(b, cudaEventRecord(b->ev_args, b->stream));
+
+  // =====================================================================================
+  // collect phase
+  // =====================================================================================
+  for (size_t r : live_extract) {
+    formgpu_request &q = reqs[r];
+    formgpu_ctx *ctx = b->ctx[q.sequence];
+    const ExtractArgs &a = b->extract_args[q.sequence];
+    int rc = extract_finish(ctx, a, q.scan_idx);
+    if (rc == FORMGPU_OK) {
+      q.n_planar = (size_t)ctx->cur_n[0];
+      q.n_point = (size_t)ctx->cur_n[1];
+      if (a.host_planar || a.host_point)
+        rc = extract_widen(ctx, q.scan_idx, q.planar_out, q.planar_cap, q.point_out, q.point_cap);
+    }
+    set_status(q, rc);
+  }
+  for (size_t r : live_assoc) {
+    formgpu_request &q = reqs[r];
+    formgpu_ctx *ctx = b->ctx[q.sequence];
+    AssocPlan &plan = b->assoc_plans[q.sequence];
+    const bool want_blocks = q.op == FORMGPU_OP_ASSOC_LIN;
+    set_status(q, assoc_finish(ctx, plan, q.poses, q.n_poses, q.counts_out, q.counts_cap, &q.n_counts,
+                               want_blocks ? q.out : nullptr));
+  }
+  for (int eo = 0; eo < 2; ++eo)
+    for (size_t r : live_lin[eo]) {
+      formgpu_request &q = reqs[r];
+      if (q.n_pairs == 0) continue;
+      set_status(q, lin_collect(b->ctx[q.sequence], b->lin_indices[q.sequence], b->lin_seqs[q.sequence],
+                                eo ? 1 : 91, q.out));
+    }
+  for (size_t r : live_commit) {
+    formgpu_request &q = reqs[r];
+    const CommitPlan &plan = b->commit_plans[q.sequence];
+    commit_finish(b->ctx[q.sequence], plan);
+    q.n_planar = plan.added[0];
+    q.n_point = plan.added[1];
+  }
+  if (b->prof.timing) b->prof.collect();
+  return first_error;
+}
+
+} // extern "C"

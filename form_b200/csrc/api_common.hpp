@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 namespace formgpu {
 
@@ -53,6 +54,65 @@ int lin_launch(formgpu_ctx *ctx, const std::vector<LinTask> &tasks, bool error_o
 /// dst (per_pair = 91 doubles for blocks, 1 for errors; dst[k] belongs to out_indices[k]).
 int lin_wait(formgpu_ctx *ctx, const int *out_indices, size_t n, unsigned long long seq,
              size_t per_pair, double *dst);
+
+// ---- prepare / finish halves of the API calls (shared with the batched submit) ----
+
+/// Stage 1: build the launch arguments of one scan (flips the keypoint ping-pong buffers,
+/// assigns the completion sequence number) / wait for the pack kernel's flag and adopt
+/// the scan as the context's current scan.
+void extract_prepare(formgpu_ctx *ctx, const float4 *scan_dev, uint64_t scan_idx, bool host_records,
+                     formgpu_planar_feat *direct_planar, formgpu_point_feat *direct_point,
+                     ExtractArgs &a);
+int extract_finish(formgpu_ctx *ctx, const ExtractArgs &a, uint64_t scan_idx);
+void extract_direct_targets(formgpu_ctx *ctx, formgpu_planar_feat *planar_out, size_t planar_cap,
+                            formgpu_point_feat *point_out, size_t point_cap,
+                            formgpu_planar_feat *&dp, formgpu_point_feat *&dq);
+int extract_widen(formgpu_ctx *ctx, uint64_t scan_idx, formgpu_planar_feat *planar_out, size_t planar_cap,
+                  formgpu_point_feat *point_out, size_t point_cap);
+
+/// Reparative rebuild: uploads the request of this context on `stream` and fills the two
+/// MapArgs and the region (cursor + hash tables) that must be zero before the build.
+int map_rebuild_prepare(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t n_poses,
+                        cudaStream_t stream, MapArgs a[2], MapClearRegion &clear);
+
+/// Association (+ optionally the fused linearisation of the current scan's pairs).
+struct AssocPlan {
+  bool any_query = false; // the current scan has keypoints: kernels must run
+  bool fused = false;     // lin_tasks are to be launched behind the scatter kernel
+  int slot_k = -1;
+  int nq[2] = {0, 0};
+  int hbuf[2] = {0, 0};
+  AssocArgs aa[2];
+  SegmentArgs sa[2];
+  unsigned long long assoc_seq = 0, lin_seq = 0;
+  std::vector<LinTask> lin_tasks;
+  std::vector<int> lin_slots;
+};
+int assoc_prepare(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_scan_pose *poses,
+                  size_t n_poses, bool want_blocks, AssocPlan &plan);
+int assoc_finish(formgpu_ctx *ctx, AssocPlan &plan, const formgpu_scan_pose *poses, size_t n_poses,
+                 formgpu_pair_count *counts_out, size_t counts_cap, size_t *n_counts, double *out91);
+
+/// Linearisation / error: argument block of a launch over `n_tasks` tasks of this context
+/// (assigns the sequence number that tags the results).
+void lin_make_args(formgpu_ctx *ctx, int n_tasks, LinArgs &a);
+/// Tasks of formgpu_linearize / formgpu_error: one per listed pair with correspondences;
+/// zero-fills the outputs of the others.  indices[k] = position of task k in `pairs`.
+int lin_build_tasks(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
+                    const formgpu_scan_pose *poses, size_t n_poses, size_t per_pair, double *out,
+                    std::vector<LinTask> &tasks, std::vector<int> &indices);
+/// Wait for the tagged results of `indices` and scatter them to their pairs' positions.
+int lin_collect(formgpu_ctx *ctx, const std::vector<int> &indices, unsigned long long seq,
+                size_t per_pair, double *out);
+
+/// Novel-keypoint commit.
+struct CommitPlan {
+  CommitArgs ca[2];
+  size_t added[2] = {0, 0};
+  int slots[2] = {-1, -1};
+};
+int commit_prepare(formgpu_ctx *ctx, CommitPlan &plan);
+void commit_finish(formgpu_ctx *ctx, const CommitPlan &plan);
 
 /// Ensure the pinned upload / result staging buffers are large enough.
 int ensure_upload(formgpu_ctx *ctx, size_t bytes);

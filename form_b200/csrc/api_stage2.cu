@@ -64,8 +64,24 @@ int formgpu_map_rebuild(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
   if (!ctx) return FORMGPU_ERR_INVALID_ARG;
   if (n_poses && !poses) return fail(ctx, FORMGPU_ERR_INVALID_ARG, "formgpu_map_rebuild: null poses");
   FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int W = ctx->W;
   ProfScope scope(ctx);
+  MapArgs a[2];
+  MapClearRegion clear;
+  const int rc = map_rebuild_prepare(ctx, poses, n_poses, ctx->stream, a, clear);
+  if (rc) return rc;
+  FORMGPU_CUDA(ctx, cudaMemsetAsync(clear.base, 0, clear.bytes, ctx->stream));
+  map_build_launch(a[0], a[1], ctx->stream, ctx->prof);
+  FORMGPU_CUDA(ctx, cudaGetLastError());
+  return FORMGPU_OK;
+}
+
+} // extern "C"
+
+namespace formgpu {
+
+int map_rebuild_prepare(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t n_poses,
+                        cudaStream_t stream, MapArgs a[2], MapClearRegion &clear) {
+  const int W = ctx->W;
   FORMGPU_CUDA(ctx, cudaEventSynchronize(ctx->ev_upload));
   MapReq h = map_req_view(ctx->h_map_req, W);
   std::vector<uint8_t> has_pose(W, 0);
@@ -92,10 +108,11 @@ int formgpu_map_rebuild(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
   }
   for (int s = 0; s < W; ++s) h.scan[s] = ctx->slot_scan[s];
   FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_map_req, ctx->h_map_req, ctx->map_req_bytes,
-                                    cudaMemcpyHostToDevice, ctx->stream));
-  FORMGPU_CUDA(ctx, cudaEventRecord(ctx->ev_upload, ctx->stream));
+                                    cudaMemcpyHostToDevice, stream));
+  FORMGPU_CUDA(ctx, cudaEventRecord(ctx->ev_upload, stream));
 
-  // size the tables for this rebuild (load factor <= 0.5) and clear them in one memset
+  // size the tables for this rebuild (load factor <= 0.5); cursor + both tables are one
+  // contiguous region, cleared in one go by the caller
   size_t hs[2];
   for (int t = 0; t < 2; ++t) {
     hs[t] = std::min(ctx->hash_cap[t], next_pow2(std::max<size_t>(2 * ctx->map_n[t], 1024)));
@@ -103,10 +120,9 @@ int formgpu_map_rebuild(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
   }
   ctx->d_hash[0] = reinterpret_cast<HashSlot *>(ctx->d_mapmem + 256);
   ctx->d_hash[1] = ctx->d_hash[0] + hs[0];
-  FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_mapmem, 0, 256 + (hs[0] + hs[1]) * sizeof(HashSlot),
-                                    ctx->stream));
+  clear.base = ctx->d_mapmem;
+  clear.bytes = 256 + (hs[0] + hs[1]) * sizeof(HashSlot);
   MapReq d = map_req_view(ctx->d_map_req, W);
-  MapArgs a[2];
   for (int t = 0; t < 2; ++t) {
     a[t].type = t;
     a[t].W = W;
@@ -125,8 +141,6 @@ int formgpu_map_rebuild(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
     a[t].world = ctx->d_world[t];
     a[t].cursor = reinterpret_cast<uint32_t *>(ctx->d_mapmem) + 16 * t;
   }
-  map_build_launch(a[0], a[1], ctx->stream, ctx->prof);
-  FORMGPU_CUDA(ctx, cudaGetLastError());
   ctx->map_built = true;
   return FORMGPU_OK;
 }
@@ -135,30 +149,24 @@ int formgpu_map_rebuild(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
 // (i, current scan) at those poses is queued right behind the association - its ranges are
 // read on the device from the pair row the scatter kernel has just written - so the caller
 // pays one device round trip instead of two per ICP iteration.
-static int associate_impl(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_scan_pose *poses,
-                          size_t n_poses, formgpu_pair_count *counts_out, size_t counts_cap,
-                          size_t *n_counts, double *out91) {
-  if (!ctx) return FORMGPU_ERR_INVALID_ARG;
-  if (!pose_k || !n_counts)
-    return fail(ctx, FORMGPU_ERR_INVALID_ARG, "formgpu_associate: null argument");
+int assoc_prepare(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_scan_pose *poses,
+                  size_t n_poses, bool want_blocks, AssocPlan &plan) {
   if (!ctx->have_current) return fail(ctx, FORMGPU_ERR_STATE, "formgpu_associate: no current scan");
   if (!ctx->map_built) return fail(ctx, FORMGPU_ERR_STATE, "formgpu_associate: map not built");
-  FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   const int W = ctx->W;
   const int slot_k = ensure_slot(ctx, ctx->cur_scan);
   if (slot_k < 0) return fail(ctx, FORMGPU_ERR_CAPACITY, "window is full (max_window_scans)");
-  ProfScope scope(ctx);
-
-  const int nq[2] = {ctx->cur_n[0], ctx->cur_n[1]};
+  plan.slot_k = slot_k;
+  plan.nq[0] = ctx->cur_n[0];
+  plan.nq[1] = ctx->cur_n[1];
+  const int *nq = plan.nq;
+  plan.any_query = nq[0] > 0 || nq[1] > 0;
   // fused linearisation: one dynamic task per window scan that has a pose (ascending scan
-  // id = the order of the counts returned below)
-  const bool fused = poses != nullptr && out91 != nullptr && (nq[0] > 0 || nq[1] > 0);
-  static thread_local std::vector<LinTask> lin_tasks;
-  static thread_local std::vector<int> lin_slots;
-  unsigned long long lin_seq = 0;
-  lin_tasks.clear();
-  lin_slots.clear();
-  if (fused) {
+  // id = the order of the counts returned by assoc_finish)
+  plan.fused = poses != nullptr && want_blocks && plan.any_query;
+  plan.lin_tasks.clear();
+  plan.lin_slots.clear();
+  if (plan.fused) {
     int pk = -1;
     std::vector<int> pose_idx(W, -1);
     for (size_t p = 0; p < n_poses; ++p) {
@@ -180,72 +188,74 @@ static int associate_impl(formgpu_ctx *ctx, const formgpu_pose *pose_k, const fo
       t.slot_j = slot_k;
       t.out_index = (int)n;
       t.dyn_slot_i_plus1 = (uint32_t)order[n] + 1u;
-      lin_tasks.push_back(t);
-      lin_slots.push_back(order[n]);
+      plan.lin_tasks.push_back(t);
+      plan.lin_slots.push_back(order[n]);
     }
   }
-  if (nq[0] > 0 || nq[1] > 0) {
-    // per type: the counter buffer of this association (already cleared).  A type without
-    // keypoints keeps its buffers untouched so that a stale match set stays committable.
-    int hbuf[2];
-    for (int t = 0; t < 2; ++t) {
-      hbuf[t] = nq[t] > 0 ? (ctx->hist_cur[t] ^ 1) : ctx->hist_cur[t];
-      ctx->hist_cur[t] = hbuf[t];
-    }
-    AssocArgs aa[2];
-    SegmentArgs sa[2];
-    const unsigned long long assoc_seq = ++ctx->seq; // published by the scatter kernel
-    for (int t = 0; t < 2; ++t) {
-      const void *queries = t == 0 ? (const void *)ctx->d_cur_planar : (const void *)ctx->d_cur_point;
-      const size_t kcap = t == 0 ? ctx->kp_cap : ctx->kq_cap;
-      aa[t].type = t;
-      aa[t].n_query = nq[t];
-      aa[t].n_map = (int)ctx->map_n[t];
-      aa[t].queries = queries;
-      std::memcpy(aa[t].pose, pose_k, 12 * sizeof(double));
-      aa[t].voxel_width = ctx->P.max_dist_matching;
-      aa[t].hash = ctx->d_hash[t];
-      aa[t].hash_mask = ctx->hash_mask[t];
-      aa[t].world = ctx->d_world[t];
-      aa[t].world_src = ctx->d_world_src[t];
-      aa[t].match = ctx->d_match[t];
-      aa[t].W = W;
-      aa[t].max_dist2 = ctx->P.max_dist_matching * ctx->P.max_dist_matching; // matcher.hpp:82
-      aa[t].min_dist2 = ctx->P.min_dist_map * ctx->P.min_dist_map;           // map.tpp:158
-      aa[t].hist_cnt = ctx->d_hist_cnt[hbuf[t]][t];
-      sa[t].type = t;
-      sa[t].W = W;
-      sa[t].n_query = nq[t];
-      sa[t].max_dist2 = ctx->P.max_dist_matching * ctx->P.max_dist_matching; // matcher.hpp:82
-      sa[t].min_dist2 = ctx->P.min_dist_map * ctx->P.min_dist_map;           // map.tpp:158
-      sa[t].kcap = kcap;
-      sa[t].queries = queries;
-      sa[t].store = t == 0 ? (const void *)ctx->d_store_planar : (const void *)ctx->d_store_point;
-      sa[t].match = ctx->d_match[t];
-      sa[t].hist_cnt = ctx->d_hist_cnt[hbuf[t]][t];
-      sa[t].hist_next = ctx->d_hist_cnt[hbuf[t] ^ 1][t];
-      sa[t].hist_bytes = nq[t] > 0 ? ctx->hist_bytes[t] : 0;
-      sa[t].host_pair_off = ctx->h_pair + (size_t)(2 * t) * (W + 1);
-      sa[t].host_pair_cnt = ctx->h_pair + (size_t)(2 * t + 1) * (W + 1);
-      sa[t].dev_pair_off = ctx->d_pair + (size_t)(2 * t) * (W + 1);
-      sa[t].dev_pair_cnt = ctx->d_pair + (size_t)(2 * t + 1) * (W + 1);
-      sa[t].done_counter = ctx->d_counters + ctx->counter_cap + 1;
-      sa[t].flag = ctx->h_flags + 1;
-      sa[t].seq = assoc_seq;
-      sa[t].seg = t == 0 ? ctx->d_seg_planar + (size_t)slot_k * 9 * kcap
-                         : ctx->d_seg_point + (size_t)slot_k * 6 * kcap;
-    }
-    assoc_launch(aa[0], aa[1], ctx->stream, ctx->prof);
-    segment_build_launch(sa[0], sa[1], ctx->stream, ctx->prof);
-    FORMGPU_CUDA(ctx, cudaGetLastError());
-    if (fused) {
-      const int rc = lin_launch(ctx, lin_tasks, false, &lin_seq);
-      if (rc) return rc;
-    }
+  if (!plan.any_query) return FORMGPU_OK;
+  // per type: the counter buffer of this association (already cleared).  A type without
+  // keypoints keeps its buffers untouched so that a stale match set stays committable.
+  for (int t = 0; t < 2; ++t) {
+    plan.hbuf[t] = nq[t] > 0 ? (ctx->hist_cur[t] ^ 1) : ctx->hist_cur[t];
+    ctx->hist_cur[t] = plan.hbuf[t];
+  }
+  const int *hbuf = plan.hbuf;
+  AssocArgs *aa = plan.aa;
+  SegmentArgs *sa = plan.sa;
+  plan.assoc_seq = ++ctx->seq; // published by the scatter kernel
+  for (int t = 0; t < 2; ++t) {
+    const void *queries = t == 0 ? (const void *)ctx->d_cur_planar : (const void *)ctx->d_cur_point;
+    const size_t kcap = t == 0 ? ctx->kp_cap : ctx->kq_cap;
+    aa[t].type = t;
+    aa[t].n_query = nq[t];
+    aa[t].n_map = (int)ctx->map_n[t];
+    aa[t].queries = queries;
+    std::memcpy(aa[t].pose, pose_k, 12 * sizeof(double));
+    aa[t].voxel_width = ctx->P.max_dist_matching;
+    aa[t].hash = ctx->d_hash[t];
+    aa[t].hash_mask = ctx->hash_mask[t];
+    aa[t].world = ctx->d_world[t];
+    aa[t].world_src = ctx->d_world_src[t];
+    aa[t].match = ctx->d_match[t];
+    aa[t].W = W;
+    aa[t].max_dist2 = ctx->P.max_dist_matching * ctx->P.max_dist_matching; // matcher.hpp:82
+    aa[t].min_dist2 = ctx->P.min_dist_map * ctx->P.min_dist_map;           // map.tpp:158
+    aa[t].hist_cnt = ctx->d_hist_cnt[hbuf[t]][t];
+    sa[t].type = t;
+    sa[t].W = W;
+    sa[t].n_query = nq[t];
+    sa[t].max_dist2 = ctx->P.max_dist_matching * ctx->P.max_dist_matching; // matcher.hpp:82
+    sa[t].min_dist2 = ctx->P.min_dist_map * ctx->P.min_dist_map;           // map.tpp:158
+    sa[t].kcap = kcap;
+    sa[t].queries = queries;
+    sa[t].store = t == 0 ? (const void *)ctx->d_store_planar : (const void *)ctx->d_store_point;
+    sa[t].match = ctx->d_match[t];
+    sa[t].hist_cnt = ctx->d_hist_cnt[hbuf[t]][t];
+    sa[t].hist_next = ctx->d_hist_cnt[hbuf[t] ^ 1][t];
+    sa[t].hist_bytes = nq[t] > 0 ? ctx->hist_bytes[t] : 0;
+    sa[t].host_pair_off = ctx->h_pair + (size_t)(2 * t) * (W + 1);
+    sa[t].host_pair_cnt = ctx->h_pair + (size_t)(2 * t + 1) * (W + 1);
+    sa[t].dev_pair_off = ctx->d_pair + (size_t)(2 * t) * (W + 1);
+    sa[t].dev_pair_cnt = ctx->d_pair + (size_t)(2 * t + 1) * (W + 1);
+    sa[t].done_counter = ctx->d_counters + ctx->counter_cap + 1;
+    sa[t].flag = ctx->h_flags + 1;
+    sa[t].seq = plan.assoc_seq;
+    sa[t].seg = t == 0 ? ctx->d_seg_planar + (size_t)slot_k * 9 * kcap
+                       : ctx->d_seg_point + (size_t)slot_k * 6 * kcap;
+  }
+  return FORMGPU_OK;
+}
+
+int assoc_finish(formgpu_ctx *ctx, AssocPlan &plan, const formgpu_scan_pose *poses, size_t n_poses,
+                 formgpu_pair_count *counts_out, size_t counts_cap, size_t *n_counts, double *out91) {
+  const int W = ctx->W;
+  const int slot_k = plan.slot_k;
+  const int *nq = plan.nq;
+  if (plan.any_query) {
     // the counts arrive through mapped memory as soon as CTA 0 of the scatter kernel
     // has summed the counters; the rest of the scatter keeps running behind (later
     // calls are ordered on the same stream)
-    const int w = wait_flag(ctx, 1, assoc_seq);
+    const int w = wait_flag(ctx, 1, plan.assoc_seq);
     if (w) return w;
     for (int t = 0; t < 2; ++t) {
       if (nq[t] == 0) continue; // Matcher::match returns early, state stays (matcher.hpp:72-74)
@@ -265,7 +275,7 @@ static int associate_impl(formgpu_ctx *ctx, const formgpu_pose *pose_k, const fo
       ctx->match_scan[t] = ctx->cur_scan;
       ctx->match_queries[t] = t == 0 ? (const void *)ctx->d_cur_planar : (const void *)ctx->d_cur_point;
       ctx->match_novel[t] = cnt[W];
-      ctx->match_hist[t] = ctx->d_hist_cnt[hbuf[t]][t];
+      ctx->match_hist[t] = ctx->d_hist_cnt[plan.hbuf[t]][t];
     }
   }
   // non-empty pairs of the current scan, ascending scan id (rule R7)
@@ -282,17 +292,17 @@ static int associate_impl(formgpu_ctx *ctx, const formgpu_pose *pose_k, const fo
     return fail(ctx, FORMGPU_ERR_CAPACITY, "formgpu_associate: counts_out too small");
   if (!out.empty()) std::memcpy(counts_out, out.data(), out.size() * sizeof(formgpu_pair_count));
   if (out91) {
-    if (fused) {
+    if (plan.fused) {
       // the blocks of the non-empty pairs, in the order of `out`
       std::vector<int> idx;
       for (const auto &c : out) {
         const int s = find_slot(ctx, c.i);
-        const auto it = std::find(lin_slots.begin(), lin_slots.end(), s);
-        if (it == lin_slots.end())
+        const auto it = std::find(plan.lin_slots.begin(), plan.lin_slots.end(), s);
+        if (it == plan.lin_slots.end())
           return fail(ctx, FORMGPU_ERR_INVALID_ARG, "associate_linearize: no pose for a matched scan");
-        idx.push_back((int)(it - lin_slots.begin()));
+        idx.push_back((int)(it - plan.lin_slots.begin()));
       }
-      const int rc = lin_wait(ctx, idx.data(), idx.size(), lin_seq, 91, out91);
+      const int rc = lin_wait(ctx, idx.data(), idx.size(), plan.lin_seq, 91, out91);
       if (rc) return rc;
     } else if (!out.empty()) {
       // nothing was matched in this call (no keypoints): linearise what is there
@@ -303,6 +313,33 @@ static int associate_impl(formgpu_ctx *ctx, const formgpu_pose *pose_k, const fo
   }
   return FORMGPU_OK;
 }
+
+} // namespace formgpu
+
+static int associate_impl(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_scan_pose *poses,
+                          size_t n_poses, formgpu_pair_count *counts_out, size_t counts_cap,
+                          size_t *n_counts, double *out91) {
+  if (!ctx) return FORMGPU_ERR_INVALID_ARG;
+  if (!pose_k || !n_counts)
+    return fail(ctx, FORMGPU_ERR_INVALID_ARG, "formgpu_associate: null argument");
+  FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  ProfScope scope(ctx);
+  static thread_local AssocPlan plan;
+  int rc = assoc_prepare(ctx, pose_k, poses, n_poses, out91 != nullptr, plan);
+  if (rc) return rc;
+  if (plan.any_query) {
+    assoc_launch(plan.aa[0], plan.aa[1], ctx->stream, ctx->prof);
+    segment_build_launch(plan.sa[0], plan.sa[1], ctx->stream, ctx->prof);
+    FORMGPU_CUDA(ctx, cudaGetLastError());
+    if (plan.fused) {
+      rc = lin_launch(ctx, plan.lin_tasks, false, &plan.lin_seq);
+      if (rc) return rc;
+    }
+  }
+  return assoc_finish(ctx, plan, poses, n_poses, counts_out, counts_cap, n_counts, out91);
+}
+
+extern "C" {
 
 int formgpu_associate(formgpu_ctx *ctx, const formgpu_pose *pose_k, formgpu_pair_count *counts_out,
                       size_t counts_cap, size_t *n_counts) {
@@ -351,10 +388,26 @@ int formgpu_commit_scan(formgpu_ctx *ctx, size_t *n_planar_added, size_t *n_poin
   if (!ctx) return FORMGPU_ERR_INVALID_ARG;
   FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
   ProfScope scope(ctx);
-  CommitArgs ca[2];
-  size_t added[2] = {0, 0};
-  int slots[2] = {-1, -1};
+  CommitPlan plan;
+  const int rc = commit_prepare(ctx, plan);
+  if (rc) return rc;
+  commit_launch(plan.ca[0], plan.ca[1], ctx->stream, ctx->prof);
+  FORMGPU_CUDA(ctx, cudaGetLastError());
+  commit_finish(ctx, plan);
+  if (n_planar_added) *n_planar_added = plan.added[0];
+  if (n_point_added) *n_point_added = plan.added[1];
+  return FORMGPU_OK;
+}
+
+} // extern "C"
+
+namespace formgpu {
+
+int commit_prepare(formgpu_ctx *ctx, CommitPlan &plan) {
+  CommitArgs *ca = plan.ca;
   for (int t = 0; t < 2; ++t) {
+    plan.added[t] = 0;
+    plan.slots[t] = -1;
     ca[t] = CommitArgs{};
     ca[t].type = t;
     ca[t].W = ctx->W;
@@ -366,8 +419,8 @@ int formgpu_commit_scan(formgpu_ctx *ctx, size_t *n_planar_added, size_t *n_poin
     const size_t kcap = t == 0 ? ctx->kp_cap : ctx->kq_cap;
     if ((size_t)ctx->store_n[t][slot] + ctx->match_novel[t] > kcap)
       return fail(ctx, FORMGPU_ERR_CAPACITY, "keypoint store of a scan is full");
-    slots[t] = slot;
-    added[t] = ctx->match_novel[t];
+    plan.slots[t] = slot;
+    plan.added[t] = ctx->match_novel[t];
     ca[t].n_query = ctx->match_n[t];
     ca[t].min_dist2 = ctx->P.min_dist_map * ctx->P.min_dist_map;
     ca[t].queries = ctx->match_queries[t];
@@ -377,14 +430,17 @@ int formgpu_commit_scan(formgpu_ctx *ctx, size_t *n_planar_added, size_t *n_poin
                              : (void *)(ctx->d_store_point + (size_t)slot * kcap);
     ca[t].dst_count = (uint32_t)ctx->store_n[t][slot];
   }
-  commit_launch(ca[0], ca[1], ctx->stream, ctx->prof);
-  FORMGPU_CUDA(ctx, cudaGetLastError());
-  for (int t = 0; t < 2; ++t)
-    if (slots[t] >= 0) ctx->store_n[t][slots[t]] += (int)added[t];
-  if (n_planar_added) *n_planar_added = added[0];
-  if (n_point_added) *n_point_added = added[1];
   return FORMGPU_OK;
 }
+
+void commit_finish(formgpu_ctx *ctx, const CommitPlan &plan) {
+  for (int t = 0; t < 2; ++t)
+    if (plan.slots[t] >= 0) ctx->store_n[t][plan.slots[t]] += (int)plan.added[t];
+}
+
+} // namespace formgpu
+
+extern "C" {
 
 int formgpu_remove_scans(formgpu_ctx *ctx, const uint64_t *scans, size_t n) {
   if (!ctx) return FORMGPU_ERR_INVALID_ARG;

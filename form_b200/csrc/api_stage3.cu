@@ -18,19 +18,18 @@ void relative_pose(const formgpu_pose &Ti, const formgpu_pose &Tj, double rel[12
   for (int a = 0; a < 3; ++a) rel[9 + a] = Ti.R[a] * d[0] + Ti.R[3 + a] * d[1] + Ti.R[6 + a] * d[2];
 }
 
-int lin_launch(formgpu_ctx *ctx, const std::vector<LinTask> &tasks, bool error_only,
-               unsigned long long *seq_out) {
-  LinArgs a{};
+void lin_make_args(formgpu_ctx *ctx, int n_tasks, LinArgs &a) {
+  a = LinArgs{};
   a.kp_cap = ctx->kp_cap;
   a.kq_cap = ctx->kq_cap;
   a.seg_planar = ctx->d_seg_planar;
   a.seg_point = ctx->d_seg_point;
   a.pair_row = ctx->d_pair;
   a.W = ctx->W;
-  a.n_tasks = (int)tasks.size();
+  a.n_tasks = n_tasks;
   // CTAs per pair: as many as keep the launch within about one wave (2 CTAs per SM)
   a.cluster = kLinCluster;
-  while (a.cluster > 1 && (size_t)a.cluster * tasks.size() > 2 * 148) a.cluster >>= 1;
+  while (a.cluster > 1 && (size_t)a.cluster * (size_t)n_tasks > 2 * 148) a.cluster >>= 1;
   if (const char *dbg = std::getenv("FORMGPU_DEBUG_CLUSTER")) a.cluster = std::max(1, std::atoi(dbg));
   a.debug_flags = 0;
   if (const char *dbg = std::getenv("FORMGPU_DEBUG_FLAGS")) a.debug_flags = std::atoi(dbg);
@@ -38,6 +37,12 @@ int lin_launch(formgpu_ctx *ctx, const std::vector<LinTask> &tasks, bool error_o
   a.inv_sigma2 = 1.0 / (ctx->P.sigma * ctx->P.sigma);
   a.out = ctx->h_out;
   a.seq = ++ctx->seq;
+}
+
+int lin_launch(formgpu_ctx *ctx, const std::vector<LinTask> &tasks, bool error_only,
+               unsigned long long *seq_out) {
+  LinArgs a;
+  lin_make_args(ctx, (int)tasks.size(), a);
   *seq_out = a.seq;
   if (tasks.empty()) return FORMGPU_OK;
   if ((int)tasks.size() <= kLinInlineTasks) {
@@ -97,29 +102,18 @@ int lin_wait(formgpu_ctx *ctx, const int *out_indices, size_t n, unsigned long l
   return FORMGPU_OK;
 }
 
-} // namespace formgpu
-
-namespace {
-
-// Shared body of formgpu_linearize / formgpu_error: one task per pair that has
-// correspondences, one cluster per task, then poll the per-pair flags the kernel raises
-// in mapped host memory.
-int run(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs, const formgpu_scan_pose *poses,
-        size_t n_poses, bool error_only, double *out) {
-  using clk = std::chrono::steady_clock;
-  const auto t0 = clk::now();
+int lin_build_tasks(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
+                    const formgpu_scan_pose *poses, size_t n_poses, size_t per_pair, double *out,
+                    std::vector<LinTask> &tasks, std::vector<int> &indices) {
   const int W = ctx->W;
-  const size_t per_pair = error_only ? 1 : 91;
-  std::vector<int> pose_idx(W, -1);
+  static thread_local std::vector<int> pose_idx;
+  pose_idx.assign(W, -1);
   for (size_t p = 0; p < n_poses; ++p) {
     const int s = find_slot(ctx, poses[p].scan);
     if (s >= 0) pose_idx[s] = (int)p;
   }
-  int rc = ensure_out(ctx, n_pairs);
+  const int rc = ensure_out(ctx, n_pairs);
   if (rc) return rc;
-
-  static thread_local std::vector<LinTask> tasks;
-  static thread_local std::vector<int> indices;
   tasks.clear();
   indices.clear();
   for (size_t p = 0; p < n_pairs; ++p) {
@@ -145,23 +139,49 @@ int run(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs, const formg
     tasks.push_back(t);
     indices.push_back((int)p);
   }
+  return FORMGPU_OK;
+}
+
+int lin_collect(formgpu_ctx *ctx, const std::vector<int> &indices, unsigned long long seq,
+                size_t per_pair, double *out) {
+  // decode into a dense scratch, then scatter to the pairs' positions
+  static thread_local std::vector<double> dense;
+  dense.resize(indices.size() * per_pair);
+  const int rc = lin_wait(ctx, indices.data(), indices.size(), seq, per_pair, dense.data());
+  if (rc) return rc;
+  for (size_t k = 0; k < indices.size(); ++k)
+    std::memcpy(out + (size_t)indices[k] * per_pair, dense.data() + k * per_pair, per_pair * sizeof(double));
+  return FORMGPU_OK;
+}
+
+} // namespace formgpu
+
+namespace {
+
+// Shared body of formgpu_linearize / formgpu_error: one task per pair that has
+// correspondences, one cluster per task, then poll the tagged words the kernel writes
+// into mapped host memory.
+int run(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs, const formgpu_scan_pose *poses,
+        size_t n_poses, bool error_only, double *out) {
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  const size_t per_pair = error_only ? 1 : 91;
+  static thread_local std::vector<LinTask> tasks;
+  static thread_local std::vector<int> indices;
+  int rc = lin_build_tasks(ctx, pairs, n_pairs, poses, n_poses, per_pair, out, tasks, indices);
+  if (rc) return rc;
   unsigned long long seq = 0;
   const auto t1 = clk::now();
   rc = lin_launch(ctx, tasks, error_only, &seq);
   if (rc) return rc;
   const auto t2 = clk::now();
-  // decode into a dense scratch, then scatter to the pairs' positions
-  static thread_local std::vector<double> dense;
-  dense.resize(indices.size() * per_pair);
-  rc = lin_wait(ctx, indices.data(), indices.size(), seq, per_pair, dense.data());
+  rc = lin_collect(ctx, indices, seq, per_pair, out);
   if (rc) return rc;
   const auto t3 = clk::now();
   ctx->dbg_host_us[0] += std::chrono::duration<double, std::micro>(t1 - t0).count(); // build
   ctx->dbg_host_us[1] += std::chrono::duration<double, std::micro>(t2 - t1).count(); // launch API
   ctx->dbg_host_us[2] += std::chrono::duration<double, std::micro>(t3 - t2).count(); // wait
   ctx->dbg_host_calls += 1;
-  for (size_t k = 0; k < indices.size(); ++k)
-    std::memcpy(out + (size_t)indices[k] * per_pair, dense.data() + k * per_pair, per_pair * sizeof(double));
   return FORMGPU_OK;
 }
 

@@ -138,6 +138,7 @@ struct formgpu_ctx {
   // ---- stage 1 ----
   float4 *d_scan = nullptr;
   uint32_t *d_valid_bits = nullptr;
+  float4 *d_row_box = nullptr; // [B][rows][words][2]
   uint16_t *d_planar_cols = nullptr;
   int *d_planar_cnt = nullptr;
   uint16_t *d_point_cols = nullptr;

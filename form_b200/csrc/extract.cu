@@ -84,8 +84,18 @@ __device__ __forceinline__ bool resolve_group(bool cand, int col, int np, int la
 // ---------------------------------------------------------------------------
 // K1: validity masks, curvature, per-sector sort, greedy planar + point picks
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(512)
-extract_select_kernel(ExtractArgs a) {
+namespace {
+
+// Batched launches (several sequences' scans in one grid) read the per-item argument
+// block from a device array: one cooperative copy into shared memory per CTA.
+__device__ __forceinline__ void load_item_args(ExtractArgs &dst, const ExtractArgs *src) {
+  static_assert(sizeof(ExtractArgs) % 8 == 0, "ExtractArgs is copied in 8-byte words");
+  for (int i = threadIdx.x; i < (int)(sizeof(ExtractArgs) / 8); i += blockDim.x)
+    reinterpret_cast<unsigned long long *>(&dst)[i] = reinterpret_cast<const unsigned long long *>(src)[i];
+  __syncthreads();
+}
+
+__device__ __forceinline__ void extract_select_body(const ExtractArgs &a, const int row, const int b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cols = a.cols, words = a.words, np = a.np;
   float4 *pts = reinterpret_cast<float4 *>(smem_raw);
@@ -99,7 +109,6 @@ extract_select_kernel(ExtractArgs a) {
   uint32_t *m_pvalid = m_valid + words;
   uint32_t *m_used = m_pvalid + words;
 
-  const int row = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31;
   const size_t row_base = ((size_t)b * a.rows + row) * cols;
   const float4 *g = a.scan + row_base;
@@ -143,6 +152,33 @@ extract_select_kernel(ExtractArgs a) {
     }
   }
   __syncthreads();
+
+  // bounding box of the VALID points of every 32-column chunk: lets the normals kernel
+  // prune its exact adjacent-row search (find_closest only considers valid points)
+  if (a.row_box) {
+    const int warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int w = warp; w < words; w += nwarps) {
+      const int c = w * 32 + lane;
+      const bool v = c < cols && get_bit(m_valid, c);
+      const float4 p = v ? pts[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float lo0 = v ? p.x : INFINITY, lo1 = v ? p.y : INFINITY, lo2 = v ? p.z : INFINITY;
+      float hi0 = v ? p.x : -INFINITY, hi1 = v ? p.y : -INFINITY, hi2 = v ? p.z : -INFINITY;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo0 = fminf(lo0, __shfl_xor_sync(0xffffffffu, lo0, o));
+        lo1 = fminf(lo1, __shfl_xor_sync(0xffffffffu, lo1, o));
+        lo2 = fminf(lo2, __shfl_xor_sync(0xffffffffu, lo2, o));
+        hi0 = fmaxf(hi0, __shfl_xor_sync(0xffffffffu, hi0, o));
+        hi1 = fmaxf(hi1, __shfl_xor_sync(0xffffffffu, hi1, o));
+        hi2 = fmaxf(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
+      }
+      if (lane == 0) {
+        float4 *dst = a.row_box + (((size_t)b * a.rows + row) * words + w) * 2;
+        dst[0] = make_float4(lo0, lo1, lo2, 0.f);
+        dst[1] = make_float4(hi0, hi1, hi2, 0.f);
+      }
+    }
+  }
 
   // curvature (extraction.tpp:226-261): double accumulation in the reference's
   // order, rounded to float; sort key = (float bits << 32) | column (rule R1)
@@ -300,6 +336,18 @@ extract_select_kernel(ExtractArgs a) {
   if (lane == 0) a.point_cnt[(size_t)b * a.rows + row] = ptotal;
 }
 
+} // namespace
+
+__global__ void __launch_bounds__(512) extract_select_kernel(ExtractArgs a) {
+  extract_select_body(a, blockIdx.x, blockIdx.y);
+}
+
+__global__ void __launch_bounds__(512) extract_select_batch_kernel(const ExtractArgs *items) {
+  __shared__ ExtractArgs s_a;
+  load_item_args(s_a, items + blockIdx.y);
+  extract_select_body(s_a, blockIdx.x, 0);
+}
+
 // ---------------------------------------------------------------------------
 // K2: PCA normals of the planar picks (compute_normal, extraction.tpp:263-329)
 // ---------------------------------------------------------------------------
@@ -326,46 +374,81 @@ __device__ __forceinline__ void neighbor_counts(const float4 *rowp, int c, int n
   if (n_minus > np) n_minus = np;
 }
 
-// find_closest (extraction.tpp:402-420), rule R2: arg-min (dist2, column) over the
-// valid points of one row, for kPicks query points at once: every row point is read
-// from shared memory once and compared with all kPicks queries, which divides the
-// shared-memory traffic - the limiter of this kernel - by kPicks.
-constexpr int kPicks = 4;
-__device__ __forceinline__ void closest_in_row_multi(const float4 *rowp, const uint32_t *valid,
-                                                     const float4 (&p)[kPicks], int cols, int lane,
-                                                     int (&out)[kPicks]) {
-  float best[kPicks];
-  int bc[kPicks];
-#pragma unroll
-  for (int k = 0; k < kPicks; ++k) {
-    best[k] = INFINITY;
-    bc[k] = 0x7fffffff;
-  }
-  for (int c = lane; c < cols; c += 32) {
-    if ((valid[c >> 5] >> (c & 31)) & 1u) {
-      const float4 q = rowp[c];
-#pragma unroll
-      for (int k = 0; k < kPicks; ++k) {
-        const float d2 = diff_sqnorm4(q, p[k]);
-        if (d2 < best[k]) {
-          best[k] = d2;
-          bc[k] = c;
-        }
-      }
+// find_closest (extraction.tpp:402-420), rule R2: arg-min (dist2, column) over the valid
+// points of one row.  The reference scans the whole row for every pick; here the row's
+// 32-column chunks carry the bounding box of their valid points (written by the select
+// kernel) and a chunk is evaluated only if its box can hold a point at least as close as
+// the best of the nearest chunk.  The pruning is exact: the float squared distance the
+// reference computes differs from the true one by a few ulp, the box distance computed
+// here likewise, and a chunk is skipped only when its bound exceeds the seed's best by a
+// 1e-5 relative margin - so every skipped point loses the (dist2, column) comparison.
+__device__ __forceinline__ float box_dist2(const float4 lo, const float4 hi, const float4 p) {
+  const float dx = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.0f);
+  const float dy = fmaxf(fmaxf(lo.y - p.y, p.y - hi.y), 0.0f);
+  const float dz = fmaxf(fmaxf(lo.z - p.z, p.z - hi.z), 0.0f);
+  return dx * dx + dy * dy + dz * dz; // +inf for an empty chunk (lo = +inf, hi = -inf)
+}
+
+__device__ __forceinline__ int closest_in_row_pruned(const float4 *rowp, const uint32_t *valid,
+                                                     const float4 *box, const float4 p, int words,
+                                                     int cols, int lane) {
+  // nearest chunk by box distance (ties: lowest chunk)
+  float lb_min = INFINITY;
+  int w_min = 0x7fffffff;
+  for (int w = lane; w < words; w += 32) {
+    const float lb = box_dist2(box[2 * w], box[2 * w + 1], p);
+    if (lb < lb_min) {
+      lb_min = lb;
+      w_min = w;
     }
   }
 #pragma unroll
-  for (int k = 0; k < kPicks; ++k) {
-    for (int off = 16; off > 0; off >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, best[k], off);
-      const int oc = __shfl_xor_sync(0xffffffffu, bc[k], off);
-      if (od < best[k] || (od == best[k] && oc < bc[k])) {
-        best[k] = od;
-        bc[k] = oc;
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ol = __shfl_xor_sync(0xffffffffu, lb_min, off);
+    const int ow = __shfl_xor_sync(0xffffffffu, w_min, off);
+    if (ol < lb_min || (ol == lb_min && ow < w_min)) {
+      lb_min = ol;
+      w_min = ow;
+    }
+  }
+  if (w_min == 0x7fffffff) return -1; // no valid point in the row
+  float best = INFINITY;
+  int bc = 0x7fffffff;
+  auto eval = [&](int w) {
+    const int c = w * 32 + lane;
+    if (c < cols && ((valid[w] >> lane) & 1u)) {
+      const float d2 = diff_sqnorm4(rowp[c], p);
+      if (d2 < best || (d2 == best && c < bc)) {
+        best = d2;
+        bc = c;
       }
     }
-    out[k] = bc[k] == 0x7fffffff ? -1 : bc[k];
+  };
+  eval(w_min);
+  float seed = best;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) seed = fminf(seed, __shfl_xor_sync(0xffffffffu, seed, off));
+  // every other chunk that the bound cannot exclude
+  for (int w0 = 0; w0 < words; w0 += 32) {
+    const int w = w0 + lane;
+    bool need = false;
+    if (w < words && w != w_min) need = box_dist2(box[2 * w], box[2 * w + 1], p) * (1.0f - 1e-5f) <= seed;
+    unsigned todo = __ballot_sync(0xffffffffu, need);
+    while (todo) {
+      eval(w0 + __ffs(todo) - 1);
+      todo &= todo - 1u;
+    }
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oc = __shfl_xor_sync(0xffffffffu, bc, off);
+    if (od < best || (od == best && oc < bc)) {
+      best = od;
+      bc = oc;
+    }
+  }
+  return bc == 0x7fffffff ? -1 : bc;
 }
 
 __device__ __forceinline__ float hypot_pos(float x, float y) {
@@ -505,24 +588,26 @@ __device__ void smallest_eigvec3f(float m00, float m10, float m11, float m20, fl
 // each stage the three rows and take a contiguous share of the row's picks.
 constexpr int kNormalSplit = 4;
 
-__global__ void __launch_bounds__(256)
-extract_normals_kernel(ExtractArgs a) {
+namespace {
+__device__ __forceinline__ void extract_normals_body(const ExtractArgs &a, const int bx, const int b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cols = a.cols, words = a.words, np = a.np;
   float4 *own = reinterpret_cast<float4 *>(smem_raw);
   float4 *prv = own + cols;
   float4 *nxt = prv + cols;
-  uint32_t *v_prv = reinterpret_cast<uint32_t *>(nxt + cols);
+  float4 *box_prv = nxt + cols;       // [words][2] chunk boxes of the adjacent rows
+  float4 *box_nxt = box_prv + 2 * words;
+  uint32_t *v_prv = reinterpret_cast<uint32_t *>(box_nxt + 2 * words);
   uint32_t *v_nxt = v_prv + words;
   PickDesc *desc = reinterpret_cast<PickDesc *>(v_nxt + words);
   __shared__ int s_keep;
 
-  const int row = blockIdx.x / kNormalSplit, part = blockIdx.x % kNormalSplit, b = blockIdx.y;
+  const int row = bx / kNormalSplit, part = bx % kNormalSplit;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const size_t rb = (size_t)b * a.rows + row;
   const int n_all = a.planar_cnt[rb];
-  // this CTA's share [p_lo, p_hi) of the row's picks, in multiples of kPicks
-  const int per = ((n_all + kNormalSplit * kPicks - 1) / (kNormalSplit * kPicks)) * kPicks;
+  // this CTA's contiguous share [p_lo, p_hi) of the row's picks
+  const int per = (n_all + kNormalSplit - 1) / kNormalSplit;
   const int p_lo = min(part * per, n_all), p_hi = min(p_lo + per, n_all);
   const int n_picks = p_hi - p_lo;
   if (tid == 0) s_keep = 0;
@@ -538,41 +623,33 @@ extract_normals_kernel(ExtractArgs a) {
     v_prv[w] = has_prev ? a.valid_bits[(rb - 1) * words + w] : 0u;
     v_nxt[w] = has_next ? a.valid_bits[(rb + 1) * words + w] : 0u;
   }
+  for (int i = tid; i < 2 * words; i += blockDim.x) {
+    if (has_prev) box_prv[i] = a.row_box[(rb - 1) * words * 2 + i];
+    if (has_next) box_nxt[i] = a.row_box[(rb + 1) * words * 2 + i];
+  }
   __syncthreads();
 
   const uint16_t *picks = a.planar_cols + rb * a.pr_cap + p_lo;
   const double r2 = a.radius * a.radius;
 
-  // phase A: one warp per group of kPicks picks - closest points, then neighbour counts
-  for (int g0 = warp * kPicks; g0 < n_picks; g0 += nwarps * kPicks) {
-    float4 pp[kPicks];
-    int cc[kPicks];
-#pragma unroll
-    for (int k = 0; k < kPicks; ++k) {
-      cc[k] = picks[min(g0 + k, n_picks - 1)]; // tail lanes repeat the last pick
-      pp[k] = own[cc[k]];
-    }
-    int cprev[kPicks], cnext[kPicks];
-#pragma unroll
-    for (int k = 0; k < kPicks; ++k) cprev[k] = cnext[k] = -1;
-    if (has_prev) closest_in_row_multi(prv, v_prv, pp, cols, lane, cprev);
-    if (has_next) closest_in_row_multi(nxt, v_nxt, pp, cols, lane, cnext);
-#pragma unroll
-    for (int k = 0; k < kPicks; ++k) {
-      if (g0 + k >= n_picks) break;
-      int n_plus, n_minus, pp_ = 0, pm = 0, nq = 0, nm = 0;
-      neighbor_counts(own, cc[k], np, r2, lane, n_plus, n_minus);
-      if (cprev[k] >= 0) neighbor_counts(prv, cprev[k], np, r2, lane, pp_, pm);
-      if (cnext[k] >= 0) neighbor_counts(nxt, cnext[k], np, r2, lane, nq, nm);
-      if (lane == 0) {
-        PickDesc d;
-        d.c_prev = (short)cprev[k]; d.c_next = (short)cnext[k];
-        d.n_plus = (unsigned char)n_plus; d.n_minus = (unsigned char)n_minus;
-        d.pp = (unsigned char)pp_; d.pm = (unsigned char)pm;
-        d.np_ = (unsigned char)nq; d.nm = (unsigned char)nm;
-        d.pad[0] = d.pad[1] = 0;
-        desc[g0 + k] = d;
-      }
+  // phase A: one warp per pick - closest points on the adjacent rows, then neighbour counts
+  for (int pk = warp; pk < n_picks; pk += nwarps) {
+    const int c = picks[pk];
+    const float4 pp = own[c];
+    const int cprev = has_prev ? closest_in_row_pruned(prv, v_prv, box_prv, pp, words, cols, lane) : -1;
+    const int cnext = has_next ? closest_in_row_pruned(nxt, v_nxt, box_nxt, pp, words, cols, lane) : -1;
+    int n_plus, n_minus, pp_ = 0, pm = 0, nq = 0, nm = 0;
+    neighbor_counts(own, c, np, r2, lane, n_plus, n_minus);
+    if (cprev >= 0) neighbor_counts(prv, cprev, np, r2, lane, pp_, pm);
+    if (cnext >= 0) neighbor_counts(nxt, cnext, np, r2, lane, nq, nm);
+    if (lane == 0) {
+      PickDesc d;
+      d.c_prev = (short)cprev; d.c_next = (short)cnext;
+      d.n_plus = (unsigned char)n_plus; d.n_minus = (unsigned char)n_minus;
+      d.pp = (unsigned char)pp_; d.pm = (unsigned char)pm;
+      d.np_ = (unsigned char)nq; d.nm = (unsigned char)nm;
+      d.pad[0] = d.pad[1] = 0;
+      desc[pk] = d;
     }
   }
   __syncthreads();
@@ -624,14 +701,24 @@ extract_normals_kernel(ExtractArgs a) {
   __syncthreads();
   if (tid == 0 && s_keep) atomicAdd(&a.keep_cnt[rb], s_keep); // integer count: order-free
 }
+} // namespace
+
+__global__ void __launch_bounds__(256) extract_normals_kernel(ExtractArgs a) {
+  extract_normals_body(a, blockIdx.x, blockIdx.y);
+}
+
+__global__ void __launch_bounds__(256) extract_normals_batch_kernel(const ExtractArgs *items) {
+  __shared__ ExtractArgs s_a;
+  load_item_args(s_a, items + blockIdx.y);
+  extract_normals_body(s_a, blockIdx.x, 0);
+}
 
 // ---------------------------------------------------------------------------
 // K3: pack kept planar picks and point picks into the current-scan keypoint
 // arrays in rule R3 order (row, sector, selection order; dropped normals removed)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-extract_pack_kernel(ExtractArgs a) {
-  const int row = blockIdx.x, b = blockIdx.y;
+namespace {
+__device__ __forceinline__ void extract_pack_body(const ExtractArgs &a, const int row, const int b) {
   const int tid = threadIdx.x, lane = tid & 31;
   const size_t rb0 = (size_t)b * a.rows;
   __shared__ int s_off[2];
@@ -748,7 +835,7 @@ extract_pack_kernel(ExtractArgs a) {
     __syncthreads();
     if (tid == 0) {
       const unsigned d = atomicAdd(a.done_counter, 1u);
-      if (d == gridDim.x * gridDim.y - 1u) {
+      if (d == a.done_target - 1u) {
         *a.done_counter = 0u;
         a.host_counts[0] = s_tot[0];
         a.host_counts[1] = s_tot[1];
@@ -757,6 +844,17 @@ extract_pack_kernel(ExtractArgs a) {
       }
     }
   }
+}
+} // namespace
+
+__global__ void __launch_bounds__(128) extract_pack_kernel(ExtractArgs a) {
+  extract_pack_body(a, blockIdx.x, blockIdx.y);
+}
+
+__global__ void __launch_bounds__(128) extract_pack_batch_kernel(const ExtractArgs *items) {
+  __shared__ ExtractArgs s_a;
+  load_item_args(s_a, items + blockIdx.y);
+  extract_pack_body(s_a, blockIdx.x, 0);
 }
 
 // ---------------------------------------------------------------------------
@@ -767,8 +865,8 @@ size_t extract_select_smem(int cols, int cols_pad, int words) {
          (size_t)words * 4 * sizeof(uint32_t);
 }
 size_t extract_normals_smem(int cols, int words, int pr_cap) {
-  return (size_t)cols * 3 * sizeof(float4) + (size_t)words * 2 * sizeof(uint32_t) +
-         (size_t)pr_cap * sizeof(PickDesc);
+  return (size_t)cols * 3 * sizeof(float4) + (size_t)words * 4 * sizeof(float4) +
+         (size_t)words * 2 * sizeof(uint32_t) + (size_t)pr_cap * sizeof(PickDesc);
 }
 
 cudaError_t extract_configure(int cols, int cols_pad, int words, int pr_cap) {
@@ -776,8 +874,30 @@ cudaError_t extract_configure(int cols, int cols_pad, int words, int pr_cap) {
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)extract_select_smem(cols, cols_pad, words));
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(extract_select_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)extract_select_smem(cols, cols_pad, words));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(extract_normals_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)extract_normals_smem(cols, words, pr_cap));
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(extract_normals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)extract_normals_smem(cols, words, pr_cap));
+}
+
+void extract_batch_launch(const ExtractArgs &shape, const ExtractArgs *items_dev, int n_items,
+                          cudaStream_t stream, Profiler &prof) {
+  const ExtractArgs &a = shape; // geometry (rows, cols, caps) is common to the batch
+  const dim3 grid(a.rows, n_items);
+  prof.begin(FORMGPU_KG_EXTRACT_SELECT);
+  extract_select_batch_kernel<<<grid, 512, extract_select_smem(a.cols, a.cols_pad, a.words), stream>>>(items_dev);
+  prof.end(FORMGPU_KG_EXTRACT_SELECT, 1);
+  prof.begin(FORMGPU_KG_EXTRACT_NORMALS);
+  extract_normals_batch_kernel<<<dim3(a.rows * kNormalSplit, n_items), 256,
+                                 extract_normals_smem(a.cols, a.words, a.pr_cap), stream>>>(items_dev);
+  prof.end(FORMGPU_KG_EXTRACT_NORMALS, 1);
+  prof.begin(FORMGPU_KG_EXTRACT_PACK);
+  extract_pack_batch_kernel<<<grid, 128, (size_t)a.pr_cap * sizeof(uint16_t), stream>>>(items_dev);
+  prof.end(FORMGPU_KG_EXTRACT_PACK, 1);
 }
 
 void extract_launch(const ExtractArgs &a, int n_scans, cudaStream_t stream, Profiler &prof) {

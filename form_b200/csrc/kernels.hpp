@@ -15,6 +15,7 @@ struct ExtractArgs {
   double min_norm2, max_norm2, planar_threshold, radius;
   const float4 *scan;      // [B][rows*cols]
   uint32_t *valid_bits;    // [B][rows][words]
+  float4 *row_box;         // [B][rows][words][2]  (lo, hi) of the valid points of a 32-column chunk
   uint16_t *planar_cols;   // [B][rows][pr_cap]
   int *planar_cnt;         // [B][rows]
   uint16_t *point_cols;    // [B][rows][qr_cap]
@@ -39,6 +40,8 @@ struct ExtractArgs {
   unsigned *done_counter;          // zero on entry, self-cleaning
   volatile unsigned long long *flag;
   unsigned long long seq;
+  unsigned done_target;            // pack CTAs that share done_counter (rows x scans of the launch)
+  unsigned pad_;
 };
 
 cudaError_t extract_configure(int cols, int cols_pad, int words, int pr_cap);
@@ -46,6 +49,10 @@ size_t extract_select_smem(int cols, int cols_pad, int words);
 size_t extract_normals_smem(int cols, int words, int pr_cap);
 /// Launches the three stage-1 kernels.
 void extract_launch(const ExtractArgs &a, int n_scans, cudaStream_t stream, Profiler &prof);
+/// Same three kernels for n_items scans of DIFFERENT contexts (one ExtractArgs each, in
+/// device memory); `shape` supplies the common geometry.
+void extract_batch_launch(const ExtractArgs &shape, const ExtractArgs *items_dev, int n_items,
+                          cudaStream_t stream, Profiler &prof);
 
 // ---- stage 2 (map_assoc.cu, compiled with -fmad=false) ----
 struct MapArgs {
@@ -67,6 +74,15 @@ struct MapArgs {
   uint32_t *cursor;      // allocation cursor (zeroed before the build)
 };
 void map_build_launch(const MapArgs &planar, const MapArgs &point, cudaStream_t stream, Profiler &prof);
+struct MapClearRegion {
+  void *base;   // 16-byte aligned
+  size_t bytes; // multiple of 16
+};
+/// Rebuild of n_items maps in one pass of four launches: items_dev = [item][type] MapArgs,
+/// regions_dev[item] = the cursor + hash tables to clear first.
+void map_build_batch_launch(const MapArgs *items_dev, const MapClearRegion *regions_dev, int n_items,
+                            int max_points, uint32_t max_hash, size_t max_clear_bytes,
+                            cudaStream_t stream, Profiler &prof);
 
 struct AssocArgs {
   int type;
@@ -86,6 +102,8 @@ struct AssocArgs {
   uint32_t *hist_cnt;      // [blocks256][W+1] atomic counters, zero on entry
 };
 void assoc_launch(const AssocArgs &planar, const AssocArgs &point, cudaStream_t stream, Profiler &prof);
+void assoc_batch_launch(const AssocArgs *items_dev, int n_items, int max_query, cudaStream_t stream,
+                        Profiler &prof);
 
 struct SegmentArgs {
   int type;
@@ -110,6 +128,8 @@ struct SegmentArgs {
   float *seg;           // segment base of the current slot: [9 or 6][kcap]
 };
 void segment_build_launch(const SegmentArgs &planar, const SegmentArgs &point, cudaStream_t stream, Profiler &prof);
+void segment_build_batch_launch(const SegmentArgs *items_dev, int n_items, int max_query,
+                                cudaStream_t stream, Profiler &prof);
 
 struct CommitArgs {
   int type;
@@ -123,6 +143,8 @@ struct CommitArgs {
   uint32_t dst_count; // keypoints already stored there
 };
 void commit_launch(const CommitArgs &planar, const CommitArgs &point, cudaStream_t stream, Profiler &prof);
+void commit_batch_launch(const CommitArgs *items_dev, int n_items, int max_query, cudaStream_t stream,
+                         Profiler &prof);
 
 struct WorldExportArgs {
   int type;
@@ -150,7 +172,7 @@ struct LinTask { // one scan pair with at least one correspondence (128 B)
   int out_index;       // position of the pair in the caller's list
   uint32_t dyn_slot_i_plus1; // != 0: the ranges are read from the device pair row of slot_i
                              // (association and linearisation queued back to back)
-  uint32_t pad;
+  uint32_t ctx_index;        // batched launches: which context's LinArgs the task uses
 };
 static_assert(sizeof(LinTask) == 128, "LinTask size");
 
@@ -178,5 +200,8 @@ struct LinArgs {
 };
 cudaError_t linearize_launch(const LinArgs &a, const LinInline *inline_req, bool error_only,
                              cudaStream_t stream, Profiler &prof);
+/// Tasks of several contexts in one launch: ctx_args_dev[task.ctx_index] is the task's context.
+cudaError_t linearize_batch_launch(const LinArgs *ctx_args_dev, const LinTask *tasks_dev, int n_tasks,
+                                   int cluster, bool error_only, cudaStream_t stream, Profiler &prof);
 
 } // namespace formgpu

@@ -388,6 +388,25 @@ __global__ void __launch_bounds__(kLinThreads) lin_global_kernel(LinArgs a) {
   lin_cluster_body<kErrorOnly>(a, s_task);
 }
 
+// Batched launch: the tasks of several contexts in one grid.  task.ctx_index selects the
+// context's argument block (segments, pair row, result buffer, sequence tag).
+template <bool kErrorOnly>
+__global__ void __launch_bounds__(kLinThreads)
+lin_batch_kernel(const LinArgs *ctx_args, const LinTask *tasks, int cluster) {
+  __shared__ LinTask s_task;
+  __shared__ LinArgs s_args;
+  static_assert(sizeof(LinArgs) % 8 == 0 && sizeof(LinArgs) / 8 <= 32, "LinArgs copy");
+  if (threadIdx.x < sizeof(LinTask) / sizeof(unsigned long long))
+    reinterpret_cast<unsigned long long *>(&s_task)[threadIdx.x] =
+        reinterpret_cast<const unsigned long long *>(tasks + blockIdx.x / cluster)[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x < sizeof(LinArgs) / sizeof(unsigned long long))
+    reinterpret_cast<unsigned long long *>(&s_args)[threadIdx.x] =
+        reinterpret_cast<const unsigned long long *>(ctx_args + s_task.ctx_index)[threadIdx.x];
+  __syncthreads();
+  lin_cluster_body<kErrorOnly>(s_args, s_task);
+}
+
 namespace {
 template <typename... Args>
 cudaError_t launch_cluster(void (*kernel)(Args...), int n_tasks, int cluster, cudaStream_t stream,
@@ -421,6 +440,18 @@ cudaError_t linearize_launch(const LinArgs &a, const LinInline *inline_req, bool
     e = error_only ? launch_cluster(lin_global_kernel<true>, a.n_tasks, a.cluster, stream, a)
                    : launch_cluster(lin_global_kernel<false>, a.n_tasks, a.cluster, stream, a);
   }
+  prof.end(group, 1);
+  return e;
+}
+
+cudaError_t linearize_batch_launch(const LinArgs *ctx_args_dev, const LinTask *tasks_dev, int n_tasks,
+                                   int cluster, bool error_only, cudaStream_t stream, Profiler &prof) {
+  if (n_tasks <= 0) return cudaSuccess;
+  const int group = error_only ? FORMGPU_KG_ERR_CHUNK : FORMGPU_KG_LIN_CHUNK;
+  prof.begin(group);
+  const cudaError_t e =
+      error_only ? launch_cluster(lin_batch_kernel<true>, n_tasks, cluster, stream, ctx_args_dev, tasks_dev, cluster)
+                 : launch_cluster(lin_batch_kernel<false>, n_tasks, cluster, stream, ctx_args_dev, tasks_dev, cluster);
   prof.end(group, 1);
   return e;
 }

@@ -20,6 +20,7 @@
 #include "ctx.hpp"
 #include "kernels.hpp"
 
+#include <algorithm>
 #include <cfloat>
 
 namespace formgpu {
@@ -93,13 +94,22 @@ __device__ __forceinline__ int find_slot_of(const int *off, int W, int g) {
   return lo;
 }
 
+// Batched launches (blockIdx.z = item = one sequence) read their argument block from a
+// device array [item][type]: one cooperative copy into shared memory per CTA.
+template <typename T> __device__ __forceinline__ void load_item_args(T &dst, const T *src) {
+  static_assert(sizeof(T) % 8 == 0, "argument blocks are copied in 8-byte words");
+  for (int i = threadIdx.x; i < (int)(sizeof(T) / 8); i += blockDim.x)
+    reinterpret_cast<unsigned long long *>(&dst)[i] = reinterpret_cast<const unsigned long long *>(src)[i];
+  __syncthreads();
+}
+
 } // namespace
 
 // ---------------------------------------------------------------------------
 // map build, pass 1: transform + key + hash insert + per-voxel count
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) map_insert_kernel(MapArgs pa, MapArgs qa) {
-  const MapArgs &a = blockIdx.y == 0 ? pa : qa;
+namespace {
+__device__ __forceinline__ void map_insert_body(const MapArgs &a) {
   __shared__ int s_off[kMaxWindow + 1];
   for (int i = threadIdx.x; i <= a.W; i += blockDim.x) s_off[i] = a.slot_off[i];
   __syncthreads();
@@ -130,20 +140,39 @@ __global__ void __launch_bounds__(256) map_insert_kernel(MapArgs pa, MapArgs qa)
   wp.tie = (a.slot_scan[slot] << 24) | (unsigned long long)k; // rule R4 id
   a.world_tmp[g] = wp;
 }
+} // namespace
+__global__ void __launch_bounds__(256) map_insert_kernel(MapArgs pa, MapArgs qa) {
+  map_insert_body(blockIdx.y == 0 ? pa : qa);
+}
+__global__ void __launch_bounds__(256) map_insert_batch_kernel(const MapArgs *items) {
+  __shared__ MapArgs s_a;
+  load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
+  map_insert_body(s_a);
+}
 
 // pass 2: give every occupied voxel a contiguous range; start is left pointing
 // one past the end and is walked down by the scatter pass
-__global__ void __launch_bounds__(256) map_alloc_kernel(MapArgs pa, MapArgs qa) {
-  const MapArgs &a = blockIdx.y == 0 ? pa : qa;
+namespace {
+__device__ __forceinline__ void map_alloc_body(const MapArgs &a) {
+  if (a.n_total <= 0) return;
   const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h > a.hash_mask) return;
   const uint32_t cnt = a.hash[h].count;
   if (cnt) a.hash[h].start = atomicAdd(a.cursor, cnt) + cnt;
 }
+} // namespace
+__global__ void __launch_bounds__(256) map_alloc_kernel(MapArgs pa, MapArgs qa) {
+  map_alloc_body(blockIdx.y == 0 ? pa : qa);
+}
+__global__ void __launch_bounds__(256) map_alloc_batch_kernel(const MapArgs *items) {
+  __shared__ MapArgs s_a;
+  load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
+  map_alloc_body(s_a);
+}
 
 // pass 3: scatter into voxel-contiguous order
-__global__ void __launch_bounds__(256) map_scatter_kernel(MapArgs pa, MapArgs qa) {
-  const MapArgs &a = blockIdx.y == 0 ? pa : qa;
+namespace {
+__device__ __forceinline__ void map_scatter_body(const MapArgs &a) {
   __shared__ int s_off[kMaxWindow + 1];
   for (int i = threadIdx.x; i <= a.W; i += blockDim.x) s_off[i] = a.slot_off[i];
   __syncthreads();
@@ -154,6 +183,25 @@ __global__ void __launch_bounds__(256) map_scatter_kernel(MapArgs pa, MapArgs qa
   a.world[pos] = a.world_tmp[g];
   const int slot = find_slot_of(s_off, a.W, g);
   a.world_src[pos] = ((uint32_t)slot << 24) | (uint32_t)(g - s_off[slot]);
+}
+} // namespace
+__global__ void __launch_bounds__(256) map_scatter_kernel(MapArgs pa, MapArgs qa) {
+  map_scatter_body(blockIdx.y == 0 ? pa : qa);
+}
+__global__ void __launch_bounds__(256) map_scatter_batch_kernel(const MapArgs *items) {
+  __shared__ MapArgs s_a;
+  load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
+  map_scatter_body(s_a);
+}
+
+// clears the hash tables (and allocation cursors) of every item of a batched rebuild:
+// regions[i] = {base, bytes}, bytes a multiple of 16
+__global__ void __launch_bounds__(256) map_clear_batch_kernel(const MapClearRegion *regions) {
+  const MapClearRegion r = regions[blockIdx.y];
+  uint4 *p = reinterpret_cast<uint4 *>(r.base);
+  const size_t n = r.bytes / sizeof(uint4);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 void map_build_launch(const MapArgs &pa, const MapArgs &qa, cudaStream_t stream, Profiler &prof) {
@@ -168,6 +216,24 @@ void map_build_launch(const MapArgs &pa, const MapArgs &qa, cudaStream_t stream,
   prof.end(FORMGPU_KG_MAP_BUILD, 3);
 }
 
+void map_build_batch_launch(const MapArgs *items_dev, const MapClearRegion *regions_dev, int n_items,
+                            int max_points, uint32_t max_hash, size_t max_clear_bytes,
+                            cudaStream_t stream, Profiler &prof) {
+  if (n_items <= 0) return;
+  prof.begin(FORMGPU_KG_MAP_BUILD);
+  const unsigned clear_blocks = (unsigned)std::min<size_t>((max_clear_bytes / 16 + 255) / 256, 592);
+  map_clear_batch_kernel<<<dim3(std::max(clear_blocks, 1u), n_items), 256, 0, stream>>>(regions_dev);
+  int launches = 1;
+  if (max_points > 0) {
+    const dim3 gp((max_points + 255) / 256, 2, n_items);
+    map_insert_batch_kernel<<<gp, 256, 0, stream>>>(items_dev);
+    map_alloc_batch_kernel<<<dim3((max_hash + 255) / 256, 2, n_items), 256, 0, stream>>>(items_dev);
+    map_scatter_batch_kernel<<<gp, 256, 0, stream>>>(items_dev);
+    launches += 3;
+  }
+  prof.end(FORMGPU_KG_MAP_BUILD, launches);
+}
+
 // ---------------------------------------------------------------------------
 // nearest neighbour: one warp per query keypoint
 // ---------------------------------------------------------------------------
@@ -178,51 +244,79 @@ __device__ __forceinline__ int match_bin(const MatchRec &m, double max_d2) {
 }
 
 
-__global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs qa) {
-  const AssocArgs &a = blockIdx.y == 0 ? pa : qa;
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// Eight lanes per query, four queries per warp.  Every instruction of the per-query setup
+// (f64 transform, three IEEE divisions for the voxel key, hashing) then serves four
+// queries instead of one - the one-warp-per-query version was issue-bound on exactly that
+// redundant work (ncu: 67 % issue-active, 420 warp instructions per query).  Lane s of a
+// group owns the neighbour voxels with the reference's shift ranks s, s+8, s+16, s+24
+// (map.tpp:54-68); its four home-slot loads are issued together, so the 27 probes are still
+// one memory round trip.  The arg-min key (dist^2, shift rank, scan, k) is rule R5.
+constexpr int kQueryLanes = 8;
+constexpr int kQueriesPerWarp = 32 / kQueryLanes;
+constexpr int kQueriesPerCta = 8 * kQueriesPerWarp; // 256 threads
+
+namespace {
+__device__ __forceinline__ void assoc_nn_body(const AssocArgs &a) {
+  const int lane = threadIdx.x & 31, sub = lane & (kQueryLanes - 1), grp = lane / kQueryLanes;
+  const int q = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kQueriesPerWarp + grp;
   const int nb = a.W + 1;
-  if (q < a.n_query) {
-  double x, y, z;
-  if (a.type == 0) load_xyz(reinterpret_cast<const PlanarRec *>(a.queries) + q, x, y, z);
-  else load_xyz(reinterpret_cast<const PointRec *>(a.queries) + q, x, y, z);
+  const bool active = q < a.n_query; // whole groups are active or not; shuffles need every lane
+  double x = 0.0, y = 0.0, z = 0.0;
+  if (active) {
+    if (a.type == 0) load_xyz(reinterpret_cast<const PlanarRec *>(a.queries) + q, x, y, z);
+    else load_xyz(reinterpret_cast<const PointRec *>(a.queries) + q, x, y, z);
+  }
   double wx, wy, wz;
   transform_point(a.pose, x, y, z, wx, wy, wz); // kp->transform(init), matcher.hpp:89
   const int cx = voxel_coord(wx, a.voxel_width), cy = voxel_coord(wy, a.voxel_width),
             cz = voxel_coord(wz, a.voxel_width);
 
-  // phase 1: lane l < 27 looks its neighbour voxel up (27 independent probes in flight)
-  uint32_t start = 0, count = 0;
-  if (lane < 27 && a.n_map > 0) {
-    const unsigned long long key = pack_key(cx + lane_shift(lane, 0), cy + lane_shift(lane, 1), cz + lane_shift(lane, 2));
-    uint32_t h = hash_key(key) & a.hash_mask;
-    for (;;) {
-      const HashSlot s = a.hash[h];
-      if (s.key == key) {
-        start = s.start;
-        count = s.count;
-        break;
+  // phase 1: up to four voxels per lane; the home slots are loaded back to back
+  uint32_t start[4] = {0u, 0u, 0u, 0u}, count[4] = {0u, 0u, 0u, 0u};
+  {
+    unsigned long long key[4];
+    uint32_t h[4];
+    HashSlot s[4];
+    bool live[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int v = sub + kQueryLanes * r;
+      live[r] = active && v < 27 && a.n_map > 0;
+      key[r] = pack_key(cx + lane_shift(v & 31, 0), cy + lane_shift(v & 31, 1), cz + lane_shift(v & 31, 2));
+      h[r] = hash_key(key[r]) & a.hash_mask;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (live[r]) s[r] = a.hash[h[r]];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (!live[r]) continue;
+      while (s[r].key != key[r] && s[r].key != kEmptyKey) { // linear probing (load <= 0.5)
+        h[r] = (h[r] + 1) & a.hash_mask;
+        s[r] = a.hash[h[r]];
       }
-      if (s.key == kEmptyKey) break;
-      h = (h + 1) & a.hash_mask;
+      if (s[r].key == key[r]) {
+        start[r] = s[r].start;
+        count[r] = s[r].count;
+      }
     }
   }
-  // phase 2: the whole warp scans a bucket together (32 consecutive 32-byte points per
-  // step = fully coalesced).  The centre voxel goes first; a neighbour voxel is then
-  // scanned only if its box can still hold a point at least as close as the centre's
-  // best (exact pruning: a skipped voxel cannot change the arg-min).
+
+  // phase 2: the group scans a bucket together (8 consecutive 32-byte points per step).
+  // The centre voxel goes first; a neighbour voxel is then scanned only if its box can still
+  // hold a point at least as close as the centre's best (exact pruning: a skipped voxel
+  // cannot change the arg-min).
   double best = DBL_MAX;                     // Match::dist_sqrd default (map.hpp:55)
   unsigned long long best_tie = ~0ull;
   int best_rank = 32;
   uint32_t best_pos = kNoSlot;
   auto scan_bucket = [&](int b, uint32_t sb, uint32_t cb) {
-    for (uint32_t i = lane; i < cb; i += 32) {
+    for (uint32_t i = sub; i < cb; i += kQueryLanes) {
       const WorldPoint p = a.world[sb + i];
       // 4-lane double squared norm, lane 3 = 0 padding: (d0^2 + d2^2) + (d1^2 + 0)
       const double d0 = p.x - wx, d1 = p.y - wy, d2 = p.z - wz;
       const double dist = (d0 * d0 + d2 * d2) + (d1 * d1 + 0.0);
-      // rule R5 key (dist, shift rank, tie); b only grows inside a lane
+      // rule R5 key (dist, shift rank, tie)
       if (dist < best || (dist == best && (b < best_rank || (b == best_rank && p.tie < best_tie)))) {
         best = dist;
         best_tie = p.tie;
@@ -231,36 +325,52 @@ __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs q
       }
     }
   };
-  const uint32_t c0 = __shfl_sync(0xffffffffu, count, 0);
-  if (c0) scan_bucket(0, __shfl_sync(0xffffffffu, start, 0), c0);
+  {
+    const uint32_t c0 = __shfl_sync(0xffffffffu, count[0], 0, kQueryLanes);
+    const uint32_t s0 = __shfl_sync(0xffffffffu, start[0], 0, kQueryLanes);
+    scan_bucket(0, s0, c0);
+  }
   double bound = best;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) bound = fmin(bound, __shfl_xor_sync(0xffffffffu, bound, off));
-  // squared distance from the query to the box of this lane's voxel, shrunk by a safety
-  // margin that covers the rounding of floor(x / w) at the voxel faces
-  bool keep = false;
-  if (lane > 0 && lane < 27 && count > 0) {
-    const double w = a.voxel_width;
-    const double q[3] = {wx, wy, wz};
-    const int c[3] = {cx + lane_shift(lane, 0), cy + lane_shift(lane, 1), cz + lane_shift(lane, 2)};
-    double lb = 0.0;
+  for (int off = kQueryLanes / 2; off > 0; off >>= 1)
+    bound = fmin(bound, __shfl_xor_sync(0xffffffffu, bound, off));
+  // squared distance from the query to the box of each of this lane's voxels, shrunk by a
+  // safety margin that covers the rounding of floor(x / w) at the voxel faces
+  unsigned survivors = 0; // bit v: voxel with shift rank v of this group's query must be scanned
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double lo = (double)c[k] * w, hi = lo + w;
-      double d = fmax(fmax(lo - q[k], q[k] - hi), 0.0);
-      d = fmax(d - 1e-9 * (1.0 + fabs(q[k])), 0.0);
-      lb += d * d;
+  for (int r = 0; r < 4; ++r) {
+    const int v = sub + kQueryLanes * r;
+    bool keep = false;
+    if (v > 0 && v < 27 && count[r] > 0) {
+      const double w = a.voxel_width;
+      const double qq[3] = {wx, wy, wz};
+      const int c[3] = {cx + lane_shift(v, 0), cy + lane_shift(v, 1), cz + lane_shift(v, 2)};
+      double lb = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double lo = (double)c[k] * w, hi = lo + w;
+        double d = fmax(fmax(lo - qq[k], qq[k] - hi), 0.0);
+        d = fmax(d - 1e-9 * (1.0 + fabs(qq[k])), 0.0);
+        lb += d * d;
+      }
+      keep = lb <= bound;
     }
-    keep = lb <= bound;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    survivors |= ((bal >> (grp * kQueryLanes)) & 0xffu) << (kQueryLanes * r);
   }
-  unsigned nz = __ballot_sync(0xffffffffu, keep);
-  while (nz) {
-    const int b = __ffs(nz) - 1; // shift rank, ascending
-    nz &= nz - 1;
-    scan_bucket(b, __shfl_sync(0xffffffffu, start, b), __shfl_sync(0xffffffffu, count, b));
+  while (__any_sync(0xffffffffu, survivors != 0u)) {
+    const int b = survivors ? __ffs(survivors) - 1 : 0; // shift rank, ascending
+    survivors &= survivors - 1u;
+    const int r = b >> 3;
+    const uint32_t my_start = r == 0 ? start[0] : r == 1 ? start[1] : r == 2 ? start[2] : start[3];
+    const uint32_t my_count = r == 0 ? count[0] : r == 1 ? count[1] : r == 2 ? count[2] : count[3];
+    const uint32_t sb = __shfl_sync(0xffffffffu, my_start, b & 7, kQueryLanes);
+    const uint32_t cb = __shfl_sync(0xffffffffu, my_count, b & 7, kQueryLanes);
+    if (b > 0) scan_bucket(b, sb, cb);
   }
-  // arg-min over lanes with the same key
-  for (int off = 16; off > 0; off >>= 1) {
+  // arg-min over the group's lanes with the same key
+#pragma unroll
+  for (int off = kQueryLanes / 2; off > 0; off >>= 1) {
     const double od = __shfl_xor_sync(0xffffffffu, best, off);
     const unsigned long long ot = __shfl_xor_sync(0xffffffffu, best_tie, off);
     const uint32_t op = __shfl_xor_sync(0xffffffffu, best_pos, off);
@@ -275,7 +385,7 @@ __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs q
       best_rank = orank;
     }
   }
-  if (lane == 0) {
+  if (active && sub == 0) {
     MatchRec m;
     if (best_pos == kNoSlot) {
       m.dist_sqrd = DBL_MAX;
@@ -293,15 +403,32 @@ __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs q
     if (bin >= 0) atomicAdd(&a.hist_cnt[(size_t)(q >> 8) * nb + bin], 1u);
     if (m.dist_sqrd > a.min_dist2) atomicAdd(&a.hist_cnt[(size_t)(q >> 8) * nb + a.W], 1u);
   }
-  } // q < n_query
-
+}
+} // namespace
+__global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs qa) {
+  assoc_nn_body(blockIdx.y == 0 ? pa : qa);
+}
+__global__ void __launch_bounds__(256) assoc_nn_batch_kernel(const AssocArgs *items) {
+  __shared__ AssocArgs s_a;
+  load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
+  if ((int)(blockIdx.x * kQueriesPerCta) >= s_a.n_query) return;
+  assoc_nn_body(s_a);
 }
 
 void assoc_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream, Profiler &prof) {
   const int n = max(pa.n_query, qa.n_query);
   if (n <= 0) return;
   prof.begin(FORMGPU_KG_ASSOC_NN);
-  assoc_nn_kernel<<<dim3((n + 7) / 8, 2), 256, 0, stream>>>(pa, qa);
+  assoc_nn_kernel<<<dim3((n + kQueriesPerCta - 1) / kQueriesPerCta, 2), 256, 0, stream>>>(pa, qa);
+  prof.end(FORMGPU_KG_ASSOC_NN, 1);
+}
+
+void assoc_batch_launch(const AssocArgs *items_dev, int n_items, int max_query, cudaStream_t stream,
+                        Profiler &prof) {
+  if (n_items <= 0 || max_query <= 0) return;
+  prof.begin(FORMGPU_KG_ASSOC_NN);
+  assoc_nn_batch_kernel<<<dim3((max_query + kQueriesPerCta - 1) / kQueriesPerCta, 2, n_items), 256, 0, stream>>>(
+      items_dev);
   prof.end(FORMGPU_KG_ASSOC_NN, 1);
 }
 
@@ -333,8 +460,8 @@ __device__ __forceinline__ void block_prefix(const uint32_t *hist_cnt, int nbloc
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) segment_scatter_kernel(SegmentArgs pa, SegmentArgs qa) {
-  const SegmentArgs &a = blockIdx.y == 0 ? pa : qa;
+namespace {
+__device__ __forceinline__ void segment_scatter_body(const SegmentArgs &a) {
   __shared__ uint32_t s_warp[8][kMaxWindow];
   __shared__ uint32_t s_pre[kMaxWindow + 1], s_tot[kMaxWindow + 1], s_off[kMaxWindow + 1];
   // clear the other counter buffer for this type's next association (grid-stride; saves
@@ -421,6 +548,15 @@ __global__ void __launch_bounds__(256) segment_scatter_kernel(SegmentArgs pa, Se
     s[3 * st + pos] = pj.x; s[4 * st + pos] = pj.y; s[5 * st + pos] = pj.z;
   }
 }
+} // namespace
+__global__ void __launch_bounds__(256) segment_scatter_kernel(SegmentArgs pa, SegmentArgs qa) {
+  segment_scatter_body(blockIdx.y == 0 ? pa : qa);
+}
+__global__ void __launch_bounds__(256) segment_scatter_batch_kernel(const SegmentArgs *items) {
+  __shared__ SegmentArgs s_a;
+  load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
+  segment_scatter_body(s_a);
+}
 
 void segment_build_launch(const SegmentArgs &pa, const SegmentArgs &qa, cudaStream_t stream,
                           Profiler &prof) {
@@ -430,15 +566,22 @@ void segment_build_launch(const SegmentArgs &pa, const SegmentArgs &qa, cudaStre
   const dim3 g((n + 255) / 256, 2);
   segment_scatter_kernel<<<g, 256, 0, stream>>>(pa, qa);
   prof.end(FORMGPU_KG_SEGMENT, 1);
+}
 
+void segment_build_batch_launch(const SegmentArgs *items_dev, int n_items, int max_query,
+                                cudaStream_t stream, Profiler &prof) {
+  if (n_items <= 0 || max_query <= 0) return;
+  prof.begin(FORMGPU_KG_SEGMENT);
+  segment_scatter_batch_kernel<<<dim3((max_query + 255) / 256, 2, n_items), 256, 0, stream>>>(items_dev);
+  prof.end(FORMGPU_KG_SEGMENT, 1);
 }
 
 // ---------------------------------------------------------------------------
 // commit: append the novel keypoints (dist^2 > min_dist_map^2, unmatched
 // included) to the scan's stored keypoints, in keypoint order (map.tpp:160-164)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) commit_kernel(CommitArgs pa, CommitArgs qa) {
-  const CommitArgs &a = blockIdx.y == 0 ? pa : qa;
+namespace {
+__device__ __forceinline__ void commit_body(const CommitArgs &a) {
   if ((int)(blockIdx.x * blockDim.x) >= a.n_query) return;
   __shared__ uint32_t s_warp[8];
   __shared__ uint32_t s_before; // novel keypoints in earlier query blocks
@@ -464,12 +607,29 @@ __global__ void __launch_bounds__(256) commit_kernel(CommitArgs pa, CommitArgs q
   else
     reinterpret_cast<PointRec *>(a.store_dst)[pos] = reinterpret_cast<const PointRec *>(a.queries)[q];
 }
+} // namespace
+__global__ void __launch_bounds__(256) commit_kernel(CommitArgs pa, CommitArgs qa) {
+  commit_body(blockIdx.y == 0 ? pa : qa);
+}
+__global__ void __launch_bounds__(256) commit_batch_kernel(const CommitArgs *items) {
+  __shared__ CommitArgs s_a;
+  load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
+  commit_body(s_a);
+}
 
 void commit_launch(const CommitArgs &pa, const CommitArgs &qa, cudaStream_t stream, Profiler &prof) {
   const int n = max(pa.n_query, qa.n_query);
   if (n <= 0) return;
   prof.begin(FORMGPU_KG_COMMIT);
   commit_kernel<<<dim3((n + 255) / 256, 2), 256, 0, stream>>>(pa, qa);
+  prof.end(FORMGPU_KG_COMMIT, 1);
+}
+
+void commit_batch_launch(const CommitArgs *items_dev, int n_items, int max_query, cudaStream_t stream,
+                         Profiler &prof) {
+  if (n_items <= 0 || max_query <= 0) return;
+  prof.begin(FORMGPU_KG_COMMIT);
+  commit_batch_kernel<<<dim3((max_query + 255) / 256, 2, n_items), 256, 0, stream>>>(items_dev);
   prof.end(FORMGPU_KG_COMMIT, 1);
 }
 

@@ -1,4 +1,5 @@
 // libformhost.so: form::Estimator and the trace replayer over the CUDA hot path.
+#include "form/batch_replay.hpp"
 #include "form/capi_impl.hpp"
 
 #include <atomic>
@@ -164,6 +165,97 @@ double formhost_replay_run_device_multi(void *const *replays, size_t n_replays, 
   for (int f : failed)
     if (f) return -1.0;
   return dt;
+}
+
+// ---- batched replay: many sequences per launch (formgpu_batch_submit) ----
+
+/// traces[s] (borrowed, from formhost_est_trace) drives sequence s of a fresh batch.
+void *formhost_batch_replay_create(const void *const *traces, size_t n, const formhost_est_params *p,
+                                   void *stream) {
+  try {
+    std::vector<const Trace *> tr;
+    for (size_t i = 0; i < n; ++i) tr.push_back(static_cast<const Trace *>(traces[i]));
+    const Estimator::Params ep = to_estimator_params(*p);
+    const int window = p->hot.max_window_scans > 0 ? p->hot.max_window_scans : 64;
+    return new BatchReplay(tr, Estimator::hotpath_params(ep), p->device, stream, window);
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return nullptr;
+  }
+}
+void formhost_batch_replay_destroy(void *r) { delete static_cast<BatchReplay *>(r); }
+void *formhost_batch_replay_batch(void *r) { return static_cast<BatchReplay *>(r)->batch(); }
+
+/// Replays scans [first, last) of every sequence in lock step; scans[s][k] = scan k of
+/// sequence s (device pointers when on_device != 0).  Returns seconds, < 0 on error.
+double formhost_batch_replay_run(void *r, size_t first, size_t last,
+                                 const formgpu_point4f *const *const *scans, int on_device,
+                                 size_t *rounds) {
+  try {
+    return static_cast<BatchReplay *>(r)->run(first, last, scans, on_device != 0, rounds);
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return -1.0;
+  }
+}
+
+/// Several batches on one GPU, one host thread (and stream) each: while one batch waits for
+/// its round, the others prepare and queue theirs.  scans[b] as for formhost_batch_replay_run.
+/// Returns the wall time from a common start to the last batch finishing, < 0 on error.
+double formhost_batch_replay_run_multi(void *const *replays, size_t n, size_t first, size_t last,
+                                       const formgpu_point4f *const *const *const *scans, int on_device) {
+  std::vector<std::thread> threads;
+  std::vector<int> failed(n, 0);
+  std::atomic<size_t> ready{0};
+  std::atomic<bool> go{false};
+  for (size_t i = 0; i < n; ++i) {
+    threads.emplace_back([&, i] {
+      ready.fetch_add(1);
+      while (!go.load(std::memory_order_acquire)) {
+      }
+      try {
+        static_cast<BatchReplay *>(replays[i])->run(first, last, scans[i], on_device != 0);
+      } catch (const std::exception &e) {
+        g_error = e.what();
+        failed[i] = 1;
+      }
+    });
+  }
+  while (ready.load() < n) {
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  go.store(true, std::memory_order_release);
+  for (auto &t : threads) t.join();
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  for (int f : failed)
+    if (f) return -1.0;
+  return dt;
+}
+
+/// Work counters of sequence `seq`, or summed over all sequences when seq < 0.
+void formhost_batch_replay_stats(void *r, int seq, uint64_t out[20], double *checksum) {
+  auto *b = static_cast<BatchReplay *>(r);
+  std::memset(out, 0, 20 * sizeof(uint64_t));
+  double cs = 0.0;
+  for (size_t s = 0; s < b->size(); ++s) {
+    if (seq >= 0 && (size_t)seq != s) continue;
+    ReplayHandle tmp;
+    tmp.stats = b->stats(s);
+    uint64_t v[20];
+    double c = 0.0;
+    replay_stats(&tmp, v, &c);
+    for (int k = 0; k < 20; ++k) out[k] += v[k];
+    cs += c;
+  }
+  if (checksum) *checksum = cs;
+}
+void formhost_batch_replay_reset_stats(void *r) {
+  auto *b = static_cast<BatchReplay *>(r);
+  for (size_t s = 0; s < b->size(); ++s) {
+    auto table = std::move(b->stats(s).table);
+    b->stats(s) = ReplayStats();
+    b->stats(s).table = std::move(table);
+  }
 }
 
 void formhost_replay_stats(void *r, uint64_t out[20], double *checksum) {

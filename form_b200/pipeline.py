@@ -195,3 +195,83 @@ def run_device_multi(replays, first: int, last: int, dev_ptrs_per_replay) -> flo
     if t < 0:
         raise RuntimeError("multi-sequence replay failed")
     return t
+
+
+class BatchReplay:
+    """Lock-step replay of the recorded traces of several sequences through
+    formgpu_batch_submit: calls of the same kind share one launch per kernel."""
+
+    def __init__(self, traces, params: _capi.EstParams, stream: int | None = None):
+        self._lib = _capi.host_lib()
+        self.n = len(traces)
+        arr = (C.c_void_p * self.n)(*traces)
+        self._h = self._lib.formhost_batch_replay_create(arr, self.n, C.byref(params), C.c_void_p(stream or 0))
+        if not self._h:
+            raise RuntimeError("formhost_batch_replay_create failed: " +
+                               (self._lib.formhost_last_error() or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.formhost_batch_replay_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _scan_table(ptrs_per_sequence):
+        inner = [_scan_ptr_array(list(p)) for p in ptrs_per_sequence]
+        outer = (C.c_void_p * len(inner))(*[C.cast(a, C.c_void_p) for a in inner])
+        return inner, outer
+
+    def run(self, first: int, last: int, ptrs_per_sequence, on_device: bool = True):
+        """Replay scans [first, last) of every sequence; returns (seconds, submits)."""
+        keep, outer = self._scan_table(ptrs_per_sequence)
+        rounds = C.c_size_t()
+        t = self._lib.formhost_batch_replay_run(self._h, first, last, outer, int(on_device), C.byref(rounds))
+        if t < 0:
+            raise RuntimeError("batched replay failed: " + (self._lib.formhost_last_error() or b"").decode())
+        return t, rounds.value
+
+    def batch(self):
+        return self._lib.formhost_batch_replay_batch(self._h)
+
+    def stats(self, seq: int = -1) -> dict:
+        out = np.zeros(20, np.uint64)
+        cs = C.c_double()
+        self._lib.formhost_batch_replay_stats(self._h, seq, _capi.ptr(out), C.byref(cs))
+        d = {k: int(v) for k, v in zip(_capi.REPLAY_STAT_NAMES, out)}
+        d["checksum"] = cs.value
+        return d
+
+    def reset_stats(self):
+        self._lib.formhost_batch_replay_reset_stats(self._h)
+
+    def profile_enable(self, on=True):
+        _capi.gpu_lib().formgpu_batch_profile_enable(self.batch(), int(on))
+
+    def profile_read(self):
+        ms = np.zeros(_capi.KG_COUNT)
+        launches = np.zeros(_capi.KG_COUNT, np.uint64)
+        _capi.gpu_lib().formgpu_batch_profile_read(self.batch(), _capi.ptr(ms), _capi.ptr(launches))
+        return {name: dict(ms=float(ms[i]), launches=int(launches[i]))
+                for i, name in enumerate(_capi.KG_NAMES)}
+
+    def launch_count(self) -> int:
+        return int(_capi.gpu_lib().formgpu_batch_launch_count(self.batch()))
+
+
+def run_batches(batch_replays, first: int, last: int, ptrs_per_batch, on_device: bool = True) -> float:
+    """Several BatchReplay objects concurrently on one GPU (one host thread and stream per
+    batch): while one batch waits for its round the others queue theirs."""
+    n = len(batch_replays)
+    handles = (C.c_void_p * n)(*[b._h for b in batch_replays])
+    keep = [BatchReplay._scan_table(p) for p in ptrs_per_batch]
+    outer = (C.c_void_p * n)(*[C.cast(k[1], C.c_void_p) for k in keep])
+    t = _capi.host_lib().formhost_batch_replay_run_multi(handles, n, first, last, outer, int(on_device))
+    if t < 0:
+        raise RuntimeError("batched replay failed: " + (_capi.host_lib().formhost_last_error() or b"").decode())
+    return t

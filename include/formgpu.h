@@ -240,6 +240,91 @@ int formgpu_linearize(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pair
 int formgpu_error(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
                   const formgpu_scan_pose *poses, size_t n_poses, double *out);
 
+/* ---- batched submit: many independent sequences per launch --------------- */
+#define FORMGPU_KG_COUNT 12 /* kernel groups, listed under "instrumentation" below */
+
+/* One sequence alone cannot fill a B200 (a per-scan request is < 1 MB and every call is a
+ * dependent round trip).  A formgpu_batch owns `n_sequences` contexts - one per
+ * independent sequence, i.e. one per form::Estimator - that share one CUDA stream.
+ * formgpu_batch_submit executes at most ONE pending call per sequence; calls of the same
+ * kind are executed by ONE launch per kernel (the grid's z / y index selects the
+ * sequence).  The arithmetic is that of the single-sequence entry points, so results are
+ * bit-identical to n separate contexts.  The call returns when every request has
+ * completed; request i's status lands in reqs[i].status and the first failure is the
+ * return value (the other requests still run).
+ *
+ * A request names the single-sequence call it stands for (the reference interfaces are
+ * the ones cited at those entry points) and uses the fields that call takes:
+ *   FORMGPU_OP_EXTRACT      formgpu_extract / formgpu_extract_device (flag
+ *                           FORMGPU_REQ_SCAN_ON_DEVICE): scan, n_points, scan_idx,
+ *                           planar_out/cap, point_out/cap -> n_planar, n_point
+ *   FORMGPU_OP_MAP_REBUILD  formgpu_map_rebuild: poses, n_poses
+ *   FORMGPU_OP_ASSOCIATE    formgpu_associate: pose_k, counts_out/cap -> n_counts
+ *   FORMGPU_OP_ASSOC_LIN    formgpu_associate_linearize: poses, n_poses, counts_out/cap,
+ *                           out (91 doubles per count) -> n_counts
+ *   FORMGPU_OP_LINEARIZE    formgpu_linearize: pairs, n_pairs, poses, n_poses, out
+ *   FORMGPU_OP_ERROR        formgpu_error: pairs, n_pairs, poses, n_poses, out
+ *   FORMGPU_OP_COMMIT       formgpu_commit_scan -> n_planar, n_point (keypoints added)
+ *   FORMGPU_OP_REMOVE       formgpu_remove_scans: scans, n_scans */
+#define FORMGPU_OP_EXTRACT 0
+#define FORMGPU_OP_MAP_REBUILD 1
+#define FORMGPU_OP_ASSOCIATE 2
+#define FORMGPU_OP_ASSOC_LIN 3
+#define FORMGPU_OP_LINEARIZE 4
+#define FORMGPU_OP_ERROR 5
+#define FORMGPU_OP_COMMIT 6
+#define FORMGPU_OP_REMOVE 7
+#define FORMGPU_OP_COUNT 8
+
+#define FORMGPU_REQ_SCAN_ON_DEVICE 1u /* `scan` is a device pointer; no keypoints copied back */
+
+typedef struct formgpu_request {
+  uint32_t sequence; /* index of the sequence inside the batch */
+  uint32_t op;       /* FORMGPU_OP_* */
+  uint32_t flags;    /* FORMGPU_REQ_* */
+  int32_t status;    /* out: FORMGPU_OK or the error of this request */
+  /* stage 1 */
+  const formgpu_point4f *scan;
+  size_t n_points;
+  uint64_t scan_idx;
+  formgpu_planar_feat *planar_out;
+  size_t planar_cap;
+  size_t n_planar; /* out */
+  formgpu_point_feat *point_out;
+  size_t point_cap;
+  size_t n_point; /* out */
+  /* stage 2 / 3 */
+  const formgpu_scan_pose *poses;
+  size_t n_poses;
+  const formgpu_pose *pose_k;
+  const formgpu_pair *pairs;
+  size_t n_pairs;
+  formgpu_pair_count *counts_out;
+  size_t counts_cap;
+  size_t n_counts; /* out */
+  double *out;     /* 91 doubles per pair (blocks) or 1 per pair (errors) */
+  const uint64_t *scans;
+  size_t n_scans;
+} formgpu_request;
+
+typedef struct formgpu_batch formgpu_batch;
+
+/* `stream`: cudaStream_t shared by all sequences of the batch, or NULL for a private one. */
+int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size_t n_sequences,
+                         formgpu_batch **out);
+void formgpu_batch_destroy(formgpu_batch *b);
+size_t formgpu_batch_size(const formgpu_batch *b);
+/* The context of sequence i, for the calls that are not batched (formgpu_get_matches,
+ * formgpu_get_keypoints, formgpu_world_keypoints, ...); it runs on the batch's stream. */
+formgpu_ctx *formgpu_batch_ctx(formgpu_batch *b, size_t i);
+int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n);
+const char *formgpu_batch_last_error(const formgpu_batch *b);
+/* As formgpu_profile_enable / _read / formgpu_launch_count, for the batched launches. */
+int formgpu_batch_profile_enable(formgpu_batch *b, int on);
+int formgpu_batch_profile_read(formgpu_batch *b, double ms[FORMGPU_KG_COUNT],
+                               uint64_t launches[FORMGPU_KG_COUNT]);
+uint64_t formgpu_batch_launch_count(const formgpu_batch *b);
+
 /* ---- instrumentation ---------------------------------------------------- */
 
 /* Kernel groups of the hot path (one or a few kernels each). */
@@ -255,7 +340,6 @@ int formgpu_error(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
 #define FORMGPU_KG_ERR_FINALIZE 9
 #define FORMGPU_KG_COMMIT 10         /* novel keypoint append                       */
 #define FORMGPU_KG_EXPORT 11         /* world-frame keypoint export                 */
-#define FORMGPU_KG_COUNT 12
 
 /* When enabled every kernel group is bracketed by CUDA events on the context's
  * stream (the calls then synchronise once more at their end).

@@ -13,6 +13,15 @@ from form_b200 import _capi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _has_gpu():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
 def header_symbols():
     text = open(os.path.join(ROOT, "include", "formgpu.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
@@ -38,6 +47,20 @@ def test_struct_sizes_match_reference_pods():
     assert _capi.POSE.itemsize == 96 and _capi.SCAN_POSE.itemsize == 104
     assert _capi.PAIR.itemsize == 16 and _capi.PAIR_COUNT.itemsize == 16 and _capi.MATCH.itemsize == 24
     assert C.sizeof(_capi.Params) == 96
+    assert C.sizeof(_capi.Request) == 176  # formgpu_request
+
+
+def test_batch_entry_points_fail_loudly_without_a_gpu_or_with_bad_arguments():
+    lib = _capi.gpu_lib()
+    h = C.c_void_p()
+    p = _capi.default_params(16, 1800)
+    assert lib.formgpu_batch_create(C.byref(p), 0, None, 0, C.byref(h)) == _capi.ERR_INVALID_ARG
+    assert lib.formgpu_batch_create(None, 0, None, 2, C.byref(h)) == _capi.ERR_INVALID_ARG
+    if not _has_gpu():
+        assert lib.formgpu_batch_create(C.byref(p), 0, None, 2, C.byref(h)) == _capi.ERR_CUDA
+        assert b"no CUDA device" in lib.formgpu_batch_last_error(None)
+    assert lib.formgpu_batch_submit(None, None, 0) == _capi.ERR_INVALID_ARG
+    assert lib.formgpu_batch_size(None) == 0 and not lib.formgpu_batch_ctx(None, 0)
 
 
 def test_default_params_are_the_reference_defaults():
@@ -50,15 +73,6 @@ def test_default_params_are_the_reference_defaults():
     assert (p.neighbor_points, p.num_sectors, p.planar_feats_per_sector, p.point_feats_per_sector) == (5, 6, 50, 3)
     assert (p.planar_threshold, p.radius, p.min_points) == (1.0, 1.0, 5)
     assert (p.max_dist_matching, p.min_dist_map, p.sigma) == (0.8, 0.1, 0.1)
-
-
-def _has_gpu():
-    try:
-        import torch
-
-        return torch.cuda.is_available()
-    except Exception:
-        return False
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")

@@ -1,0 +1,131 @@
+"""Batched submit (formgpu_batch_submit): the calls of several independent sequences share
+one launch per kernel.  The kernel bodies are the single-sequence ones, so all index work
+(keypoints, neighbour ids, pair counts, novel sets) must be BIT-identical to replaying each
+sequence on its own context - and therefore to the oracle-checked single-sequence path;
+normal-equation blocks agree to 1e-12 (summation order) and are run-to-run deterministic."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from form_b200 import _capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _record(sensor, seq, n_scans, **overrides):
+    from form_b200.pipeline import Estimator
+
+    rows, cols = synth.shape(sensor)
+    p = _capi.default_est_params(rows, cols, record_trace=1, **overrides)
+    scans = [synth.scan(sensor, seq, k) for k in range(n_scans)]
+    est = Estimator(p)
+    for s in scans:
+        est.register_scan(s)
+    return est, scans, p
+
+
+def test_batched_replay_is_bit_identical_to_single_contexts():
+    import torch
+
+    from form_b200.pipeline import BatchReplay, Replay
+
+    n = 14
+    runs = [_record("vlp-16", seq, n) for seq in (0, 3, 7)]
+    p = runs[0][2]
+    dev = [[torch.from_numpy(s.view(np.uint8)).cuda() for s in scans] for _, scans, _ in runs]
+    torch.cuda.synchronize()
+    ptrs = [[d.data_ptr() for d in seq] for seq in dev]
+    singles = []
+    for (est, scans, _), pp in zip(runs, ptrs):
+        r = Replay(est.trace(), p)
+        r.run_device(0, n, pp)
+        singles.append(r.stats())
+    br = BatchReplay([est.trace() for est, _, _ in runs], p)
+    t, rounds = br.run(0, n, ptrs, on_device=True)
+    assert rounds > 0 and br.launch_count() > 0
+    def same(got, ref, s):
+        for k in ref:
+            if k == "checksum":
+                # blocks are tolerance-class: a batched launch may split a pair over a different
+                # number of CTAs than a single-sequence launch, which reorders the fp64 sums
+                assert abs(got[k] - ref[k]) <= 1e-12 * abs(ref[k]), (s, k, got[k], ref[k])
+            else:
+                assert got[k] == ref[k], (s, k, got[k], ref[k])  # counts: bit-exact index work
+
+    for s, ref in enumerate(singles):
+        same(br.stats(s), ref, s)
+    # far fewer launches than three separate contexts would need
+    total = br.stats()
+    assert total["scans"] == 3 * n
+    # host-scan variant: scans uploaded and f64 keypoints written back inside the call
+    bh = BatchReplay([est.trace() for est, _, _ in runs], p)
+    host_ptrs = [[s.ctypes.data for s in scans] for _, scans, _ in runs]
+    bh.run(0, n, host_ptrs, on_device=False)
+    for s, ref in enumerate(singles):
+        same(bh.stats(s), ref, s)
+    # run to run the batched path is deterministic (fixed partition, fixed reduction trees)
+    b2 = BatchReplay([est.trace() for est, _, _ in runs], p)
+    b2.run(0, n, ptrs, on_device=True)
+    for s in range(3):
+        assert b2.stats(s) == br.stats(s)
+
+
+def test_batch_submit_extract_matches_oracle_and_reports_errors():
+    import oracle_lib
+
+    rows, cols = synth.shape("vlp-16")
+    params = _capi.default_params(rows, cols)
+    lib = _capi.gpu_lib()
+    h = C.c_void_p()
+    assert lib.formgpu_batch_create(C.byref(params), 0, None, 3, C.byref(h)) == 0
+    try:
+        assert lib.formgpu_batch_size(h) == 3
+        cap_p = lib.formgpu_max_planar(lib.formgpu_batch_ctx(h, 0))
+        cap_q = lib.formgpu_max_point(lib.formgpu_batch_ctx(h, 0))
+        scans = [synth.scan("vlp-16", s, 1) for s in range(3)]
+        planar = [np.zeros(cap_p, _capi.PLANAR_FEAT) for _ in range(3)]
+        point = [np.zeros(cap_q, _capi.POINT_FEAT) for _ in range(3)]
+        reqs = (_capi.Request * 3)()
+        for s in range(3):
+            reqs[s].sequence, reqs[s].op = s, _capi.OP_EXTRACT
+            reqs[s].scan, reqs[s].n_points, reqs[s].scan_idx = scans[s].ctypes.data, rows * cols, 5 + s
+            reqs[s].planar_out, reqs[s].planar_cap = planar[s].ctypes.data, cap_p
+            reqs[s].point_out, reqs[s].point_cap = point[s].ctypes.data, cap_q
+        assert lib.formgpu_batch_submit(h, reqs, 3) == 0
+        ref = oracle_lib.Oracle(params)
+        for s in range(3):
+            rp, rq = ref.extract(scans[s], 5 + s)
+            assert reqs[s].status == 0
+            assert planar[s][: reqs[s].n_planar].tobytes() == rp.tobytes()
+            assert point[s][: reqs[s].n_point].tobytes() == rq.tobytes()
+        # one bad request does not stop the others
+        reqs[1].n_points = 17
+        rc = lib.formgpu_batch_submit(h, reqs, 3)
+        assert rc == _capi.ERR_BAD_SCAN_SIZE
+        assert [reqs[s].status for s in range(3)] == [0, _capi.ERR_BAD_SCAN_SIZE, 0]
+        assert b"sequence 1" in lib.formgpu_batch_last_error(h)
+        # two requests for the same sequence are refused
+        reqs[1].n_points = rows * cols
+        reqs[1].sequence = 0
+        assert lib.formgpu_batch_submit(h, reqs, 3) == _capi.ERR_INVALID_ARG
+    finally:
+        lib.formgpu_batch_destroy(h)
+
+
+def test_batches_run_concurrently():
+    import torch
+
+    from form_b200.pipeline import BatchReplay, run_batches
+
+    n = 8
+    runs = [_record("vlp-16", seq, n) for seq in (1, 2)]
+    p = runs[0][2]
+    dev = [[torch.from_numpy(s.view(np.uint8)).cuda() for s in scans] for _, scans, _ in runs]
+    torch.cuda.synchronize()
+    ptrs = [[d.data_ptr() for d in seq] for seq in dev]
+    traces = [est.trace() for est, _, _ in runs]
+    a, b = BatchReplay(traces, p), BatchReplay(traces[::-1], p)
+    t = run_batches([a, b], 0, n, [ptrs, ptrs[::-1]])
+    assert t > 0
+    assert a.stats(0) == b.stats(1) and a.stats(1) == b.stats(0)
