@@ -36,6 +36,11 @@ struct formgpu_batch {
   std::vector<std::vector<int>> lin_indices;
   std::vector<unsigned long long> lin_seqs;
   std::vector<LinTask> tasks_scratch;
+  // sliced linearisation scratch: partial sums (56 doubles per CTA) and per-task tickets
+  double *d_partials = nullptr;
+  unsigned *d_tickets = nullptr;
+  size_t partial_cap = 0, ticket_cap = 0;
+  size_t partials_used = 0, tickets_used = 0; // within the current submit
 };
 
 namespace {
@@ -93,42 +98,85 @@ template <typename T> const T *staged(const formgpu_batch *b, size_t offset) {
   return reinterpret_cast<const T *>(b->d_args + offset);
 }
 
-// Linearisation tasks of several contexts in up to two launches: pairs with many
-// correspondences get a cluster of 8 CTAs, the (many) small ones one or two, so that
-// neither the big pairs serialise on one SM nor the small ones waste seven CTAs.
+// Scratch of the sliced linearisation launches: 56 doubles per CTA, one ticket per task.
+int ensure_lin_scratch(formgpu_batch *b, size_t n_ctas, size_t n_tasks) {
+  if (n_ctas > b->partial_cap) {
+    BATCH_CUDA(b, cudaStreamSynchronize(b->stream));
+    if (b->d_partials) cudaFree(b->d_partials);
+    b->d_partials = nullptr;
+    size_t cap = std::max<size_t>(b->partial_cap * 2, 4096);
+    while (cap < n_ctas) cap *= 2;
+    BATCH_CUDA(b, cudaMalloc(reinterpret_cast<void **>(&b->d_partials), cap * 56 * sizeof(double)));
+    b->partial_cap = cap;
+  }
+  if (n_tasks > b->ticket_cap) {
+    BATCH_CUDA(b, cudaStreamSynchronize(b->stream));
+    if (b->d_tickets) cudaFree(b->d_tickets);
+    b->d_tickets = nullptr;
+    size_t cap = std::max<size_t>(b->ticket_cap * 2, 4096);
+    while (cap < n_tasks) cap *= 2;
+    BATCH_CUDA(b, cudaMalloc(reinterpret_cast<void **>(&b->d_tickets), cap * sizeof(unsigned)));
+    BATCH_CUDA(b, cudaMemsetAsync(b->d_tickets, 0, cap * sizeof(unsigned), b->stream));
+    b->ticket_cap = cap;
+  }
+  return FORMGPU_OK;
+}
+
+// Linearisation tasks of several contexts in two launches: pairs of up to kLinWarpTask
+// correspondences are reduced by one warp each (eight per CTA); every larger pair is sliced
+// over ceil(size / kLinSlice) CTAs.  `size` is the host's estimate; the kernels divide the
+// TRUE range by the CTA count, so a wrong estimate costs balance, not correctness.
 int stage_lin_groups(formgpu_batch *b, const std::vector<LinArgs> &ctx_args, const std::vector<LinTask> &tasks,
                      const std::vector<uint32_t> &size_hint, bool error_only,
                      std::vector<std::function<int()>> &launchers) {
   if (tasks.empty()) return FORMGPU_OK;
-  size_t off_ctx = 0, off_tasks = 0;
-  int rc = stage_args(b, ctx_args.data(), ctx_args.size(), &off_ctx);
-  if (rc) return rc;
-  // stable partition: large tasks first
-  constexpr uint32_t kLarge = 4096;
-  std::vector<LinTask> ordered;
-  ordered.reserve(tasks.size());
-  size_t n_large = 0;
-  for (size_t i = 0; i < tasks.size(); ++i)
-    if (size_hint[i] >= kLarge) {
-      ordered.push_back(tasks[i]);
-      ++n_large;
+  std::vector<LinCta> ctas, warps;
+  ctas.reserve(tasks.size() * 2);
+  warps.reserve(tasks.size());
+  size_t n_sliced_tasks = 0;
+  for (size_t t = 0; t < tasks.size(); ++t) {
+    const LinArgs &ca = ctx_args[tasks[t].ctx_index];
+    if (size_hint[t] <= kLinWarpTask) {
+      warps.push_back(LinCta{(uint32_t)t, 0u, (uint16_t)0, (uint16_t)1, tasks[t].ctx_index, ca.pair_row,
+                             tasks[t].dyn_slot_i_plus1, (uint32_t)ca.W + 1u});
+      continue;
     }
-  for (size_t i = 0; i < tasks.size(); ++i)
-    if (size_hint[i] < kLarge) ordered.push_back(tasks[i]);
-  rc = stage_args(b, ordered.data(), ordered.size(), &off_tasks);
+    ++n_sliced_tasks;
+    const uint32_t n = std::min<uint32_t>(std::max<uint32_t>((size_hint[t] + kLinSlice - 1) / kLinSlice, 1u), 1024u);
+    const uint32_t first = (uint32_t)ctas.size();
+    for (uint32_t r = 0; r < n; ++r)
+      ctas.push_back(LinCta{(uint32_t)t, first, (uint16_t)r, (uint16_t)n, tasks[t].ctx_index, ca.pair_row,
+                            tasks[t].dyn_slot_i_plus1, (uint32_t)ca.W + 1u});
+  }
+  // every launch of a submit gets its own scratch range: launches of one submit run back
+  // to back and could otherwise overlap on the partial sums (tickets are indexed by task)
+  const size_t part_base = b->partials_used, ticket_base = b->tickets_used;
+  b->partials_used += ctas.size();
+  b->tickets_used += tasks.size();
+  int rc = ensure_lin_scratch(b, b->partials_used, b->tickets_used);
   if (rc) return rc;
-  const size_t n_small = ordered.size() - n_large;
+  size_t off_ctx = 0, off_tasks = 0, off_ctas = 0, off_warps = 0;
+  rc = stage_args(b, ctx_args.data(), ctx_args.size(), &off_ctx);
+  if (rc) return rc;
+  rc = stage_args(b, tasks.data(), tasks.size(), &off_tasks);
+  if (rc) return rc;
+  if (!ctas.empty()) {
+    rc = stage_args(b, ctas.data(), ctas.size(), &off_ctas);
+    if (rc) return rc;
+  }
+  if (!warps.empty()) {
+    rc = stage_args(b, warps.data(), warps.size(), &off_warps);
+    if (rc) return rc;
+  }
+  const int n_ctas = (int)ctas.size(), n_warps = (int)warps.size();
   launchers.push_back([=]() -> int {
-    const LinArgs *d_ctx = staged<LinArgs>(b, off_ctx);
-    const LinTask *d_tasks = staged<LinTask>(b, off_tasks);
-    if (n_large)
-      BATCH_CUDA(b, linearize_batch_launch(d_ctx, d_tasks, (int)n_large, kLinCluster, error_only, b->stream, b->prof));
-    if (n_small) {
-      // few small tasks: still spread them (2 CTAs each) to keep the tail short
-      const int cluster = n_small * 2 <= 2 * 148 ? 2 : 1;
-      BATCH_CUDA(b, linearize_batch_launch(d_ctx, d_tasks + n_large, (int)n_small, cluster, error_only,
-                                           b->stream, b->prof));
-    }
+    // big pairs first: they are the long pole; the warp-sized ones fill in behind
+    BATCH_CUDA(b, linearize_sliced_launch(staged<LinArgs>(b, off_ctx), staged<LinTask>(b, off_tasks),
+                                          staged<LinCta>(b, off_ctas), n_ctas,
+                                          b->d_partials + part_base * 56, b->d_tickets + ticket_base,
+                                          error_only, b->stream, b->prof));
+    BATCH_CUDA(b, linearize_warp_launch(staged<LinArgs>(b, off_ctx), staged<LinTask>(b, off_tasks),
+                                        staged<LinCta>(b, off_warps), n_warps, error_only, b->stream, b->prof));
     return FORMGPU_OK;
   });
   return FORMGPU_OK;
@@ -192,6 +240,8 @@ void formgpu_batch_destroy(formgpu_batch *b) {
   for (formgpu_ctx *c : b->ctx) formgpu_destroy(c);
   if (b->h_args) cudaFreeHost(b->h_args);
   if (b->d_args) cudaFree(b->d_args);
+  if (b->d_partials) cudaFree(b->d_partials);
+  if (b->d_tickets) cudaFree(b->d_tickets);
   if (b->ev_args) cudaEventDestroy(b->ev_args);
   b->prof.destroy();
   if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
@@ -248,6 +298,8 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
   // previous submit's argument uploads must have been consumed before the ring restarts
   BATCH_CUDA(b, cudaEventSynchronize(b->ev_args));
   b->args_used = 0;
+  b->partials_used = 0;
+  b->tickets_used = 0;
   int first_error = FORMGPU_OK;
   auto set_status = [&](formgpu_request &q, int rc) {
     q.status = rc;
@@ -413,8 +465,17 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
             t.ctx_index = ci;
             lin_tasks.push_back(t);
             // size estimate: the pair's count after the previous association of this scan
+            // size estimate: the pair's count after the previous association of this scan, else
+            // the count of the same map scan's pair with the previous scan
             const PairEntry &e = ctx->h_pair_table[(size_t)plan.slot_k * ctx->W + plan.lin_slots[k]];
-            const uint32_t prev = e.n_planar + e.n_point;
+            uint32_t prev = e.n_planar + e.n_point;
+            if (!prev && ctx->cur_scan > 0) {
+              const int sp = find_slot(ctx, ctx->cur_scan - 1);
+              if (sp >= 0) {
+                const PairEntry &e2 = ctx->h_pair_table[(size_t)sp * ctx->W + plan.lin_slots[k]];
+                prev = e2.n_planar + e2.n_point;
+              }
+            }
             hints.push_back(prev ? prev : (uint32_t)(plan.nq[0] + plan.nq[1]) / 4u);
           }
         } else if (plan.fused) {

@@ -119,11 +119,20 @@ struct ExpandSmem {
 // The basis only depends on the relative pose, so CTA 0 builds it at kernel start:
 // three threads fill it while the rest of the CTA is already streaming correspondences
 // (the first __syncthreads of the reduction publishes it).
+// kWarpScope: the cooperating group is one warp (small pairs of a batched launch) instead of
+// the CTA; `tid` / `nthreads` are then the lane and 32, and barriers are __syncwarp.
+template <bool kWarpScope> __device__ __forceinline__ void scope_sync() {
+  if (kWarpScope) __syncwarp();
+  else __syncthreads();
+}
+
+template <bool kWarpScope = false>
 __device__ __forceinline__ void build_basis(ExpandSmem &S, const double *rel) {
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 7 * 13; i += blockDim.x) (&S.Bp[0][0])[i] = 0.0;
-  for (int i = tid; i < 7 * 3 * 13; i += blockDim.x) (&S.Bq[0][0][0])[i] = 0.0;
-  __syncthreads();
+  const int tid = kWarpScope ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+  const int nthreads = kWarpScope ? 32 : (int)blockDim.x;
+  for (int i = tid; i < 7 * 13; i += nthreads) (&S.Bp[0][0])[i] = 0.0;
+  for (int i = tid; i < 7 * 3 * 13; i += nthreads) (&S.Bq[0][0][0])[i] = 0.0;
+  scope_sync<kWarpScope>();
   const double *R = rel, *t = rel + 9;
   if (tid < 3) {
     const int k = tid;
@@ -172,11 +181,13 @@ __device__ __forceinline__ void publish_tagged(volatile unsigned long long *dst,
   dst[1] = (bits >> 32) | (tag << 32);
 }
 
+template <bool kWarpScope = false>
 __device__ __forceinline__ void expand_and_publish(ExpandSmem &S, const double *Wp28, const double *Wq28,
                                                    bool has_planar, bool has_point, double inv_sigma2,
                                                    volatile unsigned long long *out182,
                                                    unsigned long long tag) {
-  const int tid = threadIdx.x;
+  const int tid = kWarpScope ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+  const int nthreads = kWarpScope ? 32 : (int)blockDim.x;
   if (tid < 28) {
     int p = 0, e = tid; // upper-triangular index -> (p, q)
     while (e >= 7 - p) {
@@ -187,8 +198,8 @@ __device__ __forceinline__ void expand_and_publish(ExpandSmem &S, const double *
     S.Wp[p][q] = S.Wp[q][p] = Wp28[tid];
     S.Wq[p][q] = S.Wq[q][p] = Wq28[tid];
   }
-  __syncthreads();
-  for (int idx = tid; idx < 91 + 273; idx += blockDim.x) {
+  scope_sync<kWarpScope>();
+  for (int idx = tid; idx < 91 + 273; idx += nthreads) {
     double v = 0.0;
     if (idx < 91) {
       const int k = idx / 13, y = idx % 13;
@@ -202,9 +213,9 @@ __device__ __forceinline__ void expand_and_publish(ExpandSmem &S, const double *
       S.Tq[r][k][y] = v;
     }
   }
-  __syncthreads();
-  if (tid < 91) {
-    int x = 0, e = tid;
+  scope_sync<kWarpScope>();
+  for (int o = tid; o < 91; o += nthreads) {
+    int x = 0, e = o;
     while (e >= 13 - x) {
       e -= 13 - x;
       ++x;
@@ -221,7 +232,7 @@ __device__ __forceinline__ void expand_and_publish(ExpandSmem &S, const double *
 #pragma unroll
         for (int k = 0; k < 7; ++k) sum += S.Bq[k][r][x] * S.Tq[r][k][y];
     }
-    publish_tagged(out182 + 2 * tid, sum * inv_sigma2, tag);
+    publish_tagged(out182 + 2 * o, sum * inv_sigma2, tag);
   }
 }
 
@@ -388,23 +399,286 @@ __global__ void __launch_bounds__(kLinThreads) lin_global_kernel(LinArgs a) {
   lin_cluster_body<kErrorOnly>(a, s_task);
 }
 
-// Batched launch: the tasks of several contexts in one grid.  task.ctx_index selects the
-// context's argument block (segments, pair row, result buffer, sequence tag).
+// ---------------------------------------------------------------------------
+// batched launches: the tasks of several contexts in ONE grid, sliced evenly
+// ---------------------------------------------------------------------------
+// A batched request holds hundreds of pairs of very different sizes (the pair with the
+// oldest key scan has ~15 k correspondences, most others a few hundred).  One cluster
+// per pair leaves the launch latency-bound on the big pairs (ncu: 16 warps per SM, 0.5
+// TB/s).  Here every pair gets n_cta = ceil(size / kLinSlice) CTAs chosen by the host;
+// CTA r streams the r-th share of the pair's planar and point ranges with its loads
+// issued four correspondences deep, leaves its 2 x 28 moments in global memory, and the
+// LAST CTA of the pair to arrive (ticket counter) adds the partial sums in rank order -
+// a fixed order, so the result does not depend on which CTA came last - expands the
+// block and publishes it.  task.ctx_index selects the context's argument block
+// (segments, pair row, result buffer, sequence tag).
 template <bool kErrorOnly>
 __global__ void __launch_bounds__(kLinThreads)
-lin_batch_kernel(const LinArgs *ctx_args, const LinTask *tasks, int cluster) {
+lin_sliced_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ctas, double *partials,
+                  unsigned *tickets) {
   __shared__ LinTask s_task;
   __shared__ LinArgs s_args;
+  __shared__ double s_warp[kWarps][28];
+  __shared__ double s_sum[2][28];
+  __shared__ ExpandSmem s_exp;
+  __shared__ unsigned s_ticket;
   static_assert(sizeof(LinArgs) % 8 == 0 && sizeof(LinArgs) / 8 <= 32, "LinArgs copy");
-  if (threadIdx.x < sizeof(LinTask) / sizeof(unsigned long long))
-    reinterpret_cast<unsigned long long *>(&s_task)[threadIdx.x] =
-        reinterpret_cast<const unsigned long long *>(tasks + blockIdx.x / cluster)[threadIdx.x];
+  const int tid = threadIdx.x;
+  const LinCta me = ctas[blockIdx.x];
+  // task, context block and (for dynamic ranges) the pair row are independent loads: one
+  // memory round trip instead of three dependent ones
+  __shared__ uint32_t s_dyn[4];
+  if (tid < (int)(sizeof(LinTask) / sizeof(unsigned long long)))
+    reinterpret_cast<unsigned long long *>(&s_task)[tid] =
+        reinterpret_cast<const unsigned long long *>(tasks + me.task)[tid];
+  else if (tid >= 32 && tid < 32 + (int)(sizeof(LinArgs) / sizeof(unsigned long long)))
+    reinterpret_cast<unsigned long long *>(&s_args)[tid - 32] =
+        reinterpret_cast<const unsigned long long *>(ctx_args + me.ctx_index)[tid - 32];
+  else if (tid >= 64 && tid < 68 && me.dyn_slot_i_plus1) // ranges written by the association queued just before
+    s_dyn[tid - 64] = __ldcg(&me.pair_row[(size_t)(tid - 64) * me.row_stride + (me.dyn_slot_i_plus1 - 1u)]);
   __syncthreads();
-  if (threadIdx.x < sizeof(LinArgs) / sizeof(unsigned long long))
-    reinterpret_cast<unsigned long long *>(&s_args)[threadIdx.x] =
-        reinterpret_cast<const unsigned long long *>(ctx_args + s_task.ctx_index)[threadIdx.x];
+  const LinArgs &a = s_args;
+  uint32_t off_planar = s_task.off_planar, n_planar = s_task.n_planar;
+  uint32_t off_point = s_task.off_point, n_point = s_task.n_point;
+  if (me.dyn_slot_i_plus1) {
+    off_planar = s_dyn[0];
+    n_planar = s_dyn[1];
+    off_point = s_dyn[2];
+    n_point = s_dyn[3];
+    if (n_planar + n_point == 0) return; // empty pair: all its CTAs leave, nothing is published
+  }
+  const double *rel = s_task.rel;
+  const int rank = me.rank, n_cta = me.n_cta;
+  double acc[32];
+  double err_acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+  // ---- plane-point correspondences of this CTA's slice ----
+  {
+    const uint32_t lo = (uint32_t)(((unsigned long long)n_planar * rank) / n_cta);
+    const uint32_t hi = (uint32_t)(((unsigned long long)n_planar * (rank + 1)) / n_cta);
+    const float *s = a.seg_planar + (size_t)s_task.slot_j * 9 * a.kp_cap + off_planar;
+    const size_t st = a.kp_cap;
+#pragma unroll 4
+    for (uint32_t c = lo + tid; c < hi; c += kThreads) {
+      const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
+      const double nx = s[3 * st + c], ny = s[4 * st + c], nz = s[5 * st + c];
+      const double pjx = s[6 * st + c], pjy = s[7 * st + c], pjz = s[8 * st + c];
+      double qx, qy, qz;
+      apply_rel(rel, pjx, pjy, pjz, qx, qy, qz);
+      const double r = nx * (qx - pix) + ny * (qy - piy) + nz * (qz - piz);
+      if (kErrorOnly) {
+        err_acc += r * r;
+      } else {
+        const double v[7] = {ny * qz - nz * qy, nz * qx - nx * qz, nx * qy - ny * qx, nx, ny, nz, r};
+        int e = 0;
+#pragma unroll
+        for (int p = 0; p < 7; ++p)
+#pragma unroll
+          for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
+      }
+    }
+  }
+  if (!kErrorOnly) {
+    block_reduce28(acc, s_warp, s_sum[0], tid);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+  }
+  // ---- point-point correspondences ----
+  if (n_point) {
+    const uint32_t lo = (uint32_t)(((unsigned long long)n_point * rank) / n_cta);
+    const uint32_t hi = (uint32_t)(((unsigned long long)n_point * (rank + 1)) / n_cta);
+    const float *s = a.seg_point + (size_t)s_task.slot_j * 6 * a.kq_cap + off_point;
+    const size_t st = a.kq_cap;
+#pragma unroll 4
+    for (uint32_t c = lo + tid; c < hi; c += kThreads) {
+      const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
+      const double pjx = s[3 * st + c], pjy = s[4 * st + c], pjz = s[5 * st + c];
+      double qx, qy, qz;
+      apply_rel(rel, pjx, pjy, pjz, qx, qy, qz);
+      const double ex = qx - pix, ey = qy - piy, ez = qz - piz;
+      if (kErrorOnly) {
+        err_acc += ex * ex + ey * ey + ez * ez;
+      } else {
+        const double v[7] = {pix, piy, piz, ex, ey, ez, 1.0};
+        int e = 0;
+#pragma unroll
+        for (int p = 0; p < 7; ++p)
+#pragma unroll
+          for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
+      }
+    }
+  }
+  if (kErrorOnly) {
+    const double w = warp_sum(err_acc);
+    if ((tid & 31) == 0) s_warp[tid >> 5][0] = w;
+    __syncthreads();
+    if (tid == 0) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < kWarps; ++k) v += s_warp[k][0];
+      s_sum[0][0] = v;
+    }
+    __syncthreads();
+  } else {
+    block_reduce28(acc, s_warp, s_sum[1], tid); // zeros when the pair has no point rows
+  }
+
+  // ---- leave the partial sums, take a ticket; the last CTA of the pair finishes it ----
+  double *mine = partials + (size_t)(me.first + rank) * 56;
+  if (kErrorOnly) {
+    if (tid == 0) mine[0] = s_sum[0][0];
+  } else if (tid < 56) {
+    mine[tid] = s_sum[tid / 28][tid % 28];
+  }
+  if (tid < 64) __threadfence(); // the writers' warps: their partial sums before the ticket
   __syncthreads();
-  lin_cluster_body<kErrorOnly>(s_args, s_task);
+  if (tid == 0) s_ticket = atomicAdd(&tickets[me.task], 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)(n_cta - 1)) return;
+  if (tid == 0) tickets[me.task] = 0u; // self-cleaning for the next launch
+  __threadfence();
+  const double *all = partials + (size_t)me.first * 56;
+  const unsigned long long tag = a.seq & 0xffffffffull;
+  if (kErrorOnly) {
+    if (tid == 0) {
+      double v = 0.0;
+      for (int r = 0; r < n_cta; ++r) v += __ldcg(&all[(size_t)r * 56]);
+      publish_tagged(a.out + 2 * (size_t)s_task.out_index, 0.5 * v * a.inv_sigma2, tag);
+    }
+    return;
+  }
+  if (tid < 56) {
+    double v = 0.0;
+    for (int r = 0; r < n_cta; ++r) v += __ldcg(&all[(size_t)r * 56 + tid]); // rank order: deterministic
+    s_sum[tid / 28][tid % 28] = v;
+  }
+  build_basis(s_exp, rel); // starts with a __syncthreads
+  __syncthreads();
+  expand_and_publish(s_exp, s_sum[0], s_sum[1], n_planar > 0, n_point > 0, a.inv_sigma2,
+                     a.out + 182 * (size_t)s_task.out_index, tag);
+}
+
+// Small pairs of a batched launch: ONE WARP per pair, eight pairs per CTA.  A few hundred
+// correspondences do not amortise a CTA's two block reductions and its partial-sum round
+// trip; a warp reduces its 28 moments with the butterfly transpose alone (no barrier, no
+// global scratch) and expands the block in its own slice of shared memory.
+constexpr int kLinWarpTasks = kLinThreads / 32;
+
+template <bool kErrorOnly>
+__global__ void __launch_bounds__(kLinThreads, 2)
+lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *entries, int n_entries) {
+  extern __shared__ __align__(16) unsigned char lin_warp_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ei = blockIdx.x * kLinWarpTasks + warp;
+  if (ei >= n_entries) return;
+  struct WarpSmem {
+    ExpandSmem exp;
+    LinTask task;
+    LinArgs args;
+    double sum[2][28];
+    uint32_t dyn[4];
+  };
+  WarpSmem &S = reinterpret_cast<WarpSmem *>(lin_warp_smem)[warp];
+  const LinCta me = entries[ei];
+  if (lane < (int)(sizeof(LinTask) / sizeof(unsigned long long)))
+    reinterpret_cast<unsigned long long *>(&S.task)[lane] =
+        reinterpret_cast<const unsigned long long *>(tasks + me.task)[lane];
+  if (lane >= 16 && lane < 16 + (int)(sizeof(LinArgs) / sizeof(unsigned long long)))
+    reinterpret_cast<unsigned long long *>(&S.args)[lane - 16] =
+        reinterpret_cast<const unsigned long long *>(ctx_args + me.ctx_index)[lane - 16];
+  if (lane < 4 && me.dyn_slot_i_plus1)
+    S.dyn[lane] = __ldcg(&me.pair_row[(size_t)lane * me.row_stride + (me.dyn_slot_i_plus1 - 1u)]);
+  __syncwarp();
+  const LinArgs &a = S.args;
+  uint32_t off_planar = S.task.off_planar, n_planar = S.task.n_planar;
+  uint32_t off_point = S.task.off_point, n_point = S.task.n_point;
+  if (me.dyn_slot_i_plus1) {
+    off_planar = S.dyn[0];
+    n_planar = S.dyn[1];
+    off_point = S.dyn[2];
+    n_point = S.dyn[3];
+    if (n_planar + n_point == 0) return;
+  }
+  const double *rel = S.task.rel;
+  double acc[32];
+  double err_acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+  {
+    const float *s = a.seg_planar + (size_t)S.task.slot_j * 9 * a.kp_cap + off_planar;
+    const size_t st = a.kp_cap;
+#pragma unroll 4
+    for (uint32_t c = lane; c < n_planar; c += 32) {
+      const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
+      const double nx = s[3 * st + c], ny = s[4 * st + c], nz = s[5 * st + c];
+      const double pjx = s[6 * st + c], pjy = s[7 * st + c], pjz = s[8 * st + c];
+      double qx, qy, qz;
+      apply_rel(rel, pjx, pjy, pjz, qx, qy, qz);
+      const double r = nx * (qx - pix) + ny * (qy - piy) + nz * (qz - piz);
+      if (kErrorOnly) {
+        err_acc += r * r;
+      } else {
+        const double v[7] = {ny * qz - nz * qy, nz * qx - nx * qz, nx * qy - ny * qx, nx, ny, nz, r};
+        int e = 0;
+#pragma unroll
+        for (int p = 0; p < 7; ++p)
+#pragma unroll
+          for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
+      }
+    }
+  }
+  if (!kErrorOnly) {
+    transpose_reduce<16>(acc, lane);
+    if (lane < 28) S.sum[0][lane] = acc[0];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+  }
+  if (n_point) {
+    const float *s = a.seg_point + (size_t)S.task.slot_j * 6 * a.kq_cap + off_point;
+    const size_t st = a.kq_cap;
+#pragma unroll 4
+    for (uint32_t c = lane; c < n_point; c += 32) {
+      const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
+      const double pjx = s[3 * st + c], pjy = s[4 * st + c], pjz = s[5 * st + c];
+      double qx, qy, qz;
+      apply_rel(rel, pjx, pjy, pjz, qx, qy, qz);
+      const double ex = qx - pix, ey = qy - piy, ez = qz - piz;
+      if (kErrorOnly) {
+        err_acc += ex * ex + ey * ey + ez * ez;
+      } else {
+        const double v[7] = {pix, piy, piz, ex, ey, ez, 1.0};
+        int e = 0;
+#pragma unroll
+        for (int p = 0; p < 7; ++p)
+#pragma unroll
+          for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
+      }
+    }
+  }
+  const unsigned long long tag = a.seq & 0xffffffffull;
+  if (kErrorOnly) {
+    const double w = warp_sum(err_acc);
+    if (lane == 0) publish_tagged(a.out + 2 * (size_t)S.task.out_index, 0.5 * w * a.inv_sigma2, tag);
+    return;
+  }
+  transpose_reduce<16>(acc, lane);
+  if (lane < 28) S.sum[1][lane] = acc[0];
+  build_basis<true>(S.exp, rel); // starts with a __syncwarp
+  __syncwarp();
+  expand_and_publish<true>(S.exp, S.sum[0], S.sum[1], n_planar > 0, n_point > 0, a.inv_sigma2,
+                           a.out + 182 * (size_t)S.task.out_index, tag);
+}
+
+size_t lin_warp_smem_bytes() {
+  struct WarpSmem {
+    ExpandSmem exp;
+    LinTask task;
+    LinArgs args;
+    double sum[2][28];
+    uint32_t dyn[4];
+  };
+  return sizeof(WarpSmem) * kLinWarpTasks;
 }
 
 namespace {
@@ -444,16 +718,42 @@ cudaError_t linearize_launch(const LinArgs &a, const LinInline *inline_req, bool
   return e;
 }
 
-cudaError_t linearize_batch_launch(const LinArgs *ctx_args_dev, const LinTask *tasks_dev, int n_tasks,
-                                   int cluster, bool error_only, cudaStream_t stream, Profiler &prof) {
-  if (n_tasks <= 0) return cudaSuccess;
+cudaError_t linearize_warp_launch(const LinArgs *ctx_args_dev, const LinTask *tasks_dev,
+                                  const LinCta *entries_dev, int n_entries, bool error_only,
+                                  cudaStream_t stream, Profiler &prof) {
+  if (n_entries <= 0) return cudaSuccess;
+  static bool configured = false;
+  const size_t smem = lin_warp_smem_bytes();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(lin_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(lin_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int group = error_only ? FORMGPU_KG_ERR_CHUNK : FORMGPU_KG_LIN_CHUNK;
+  const int grid = (n_entries + kLinWarpTasks - 1) / kLinWarpTasks;
+  prof.begin(group);
+  if (error_only)
+    lin_warp_kernel<true><<<grid, kLinThreads, smem, stream>>>(ctx_args_dev, tasks_dev, entries_dev, n_entries);
+  else
+    lin_warp_kernel<false><<<grid, kLinThreads, smem, stream>>>(ctx_args_dev, tasks_dev, entries_dev, n_entries);
+  prof.end(group, 1);
+  return cudaGetLastError();
+}
+
+cudaError_t linearize_sliced_launch(const LinArgs *ctx_args_dev, const LinTask *tasks_dev,
+                                    const LinCta *ctas_dev, int n_ctas, double *partials, unsigned *tickets,
+                                    bool error_only, cudaStream_t stream, Profiler &prof) {
+  if (n_ctas <= 0) return cudaSuccess;
   const int group = error_only ? FORMGPU_KG_ERR_CHUNK : FORMGPU_KG_LIN_CHUNK;
   prof.begin(group);
-  const cudaError_t e =
-      error_only ? launch_cluster(lin_batch_kernel<true>, n_tasks, cluster, stream, ctx_args_dev, tasks_dev, cluster)
-                 : launch_cluster(lin_batch_kernel<false>, n_tasks, cluster, stream, ctx_args_dev, tasks_dev, cluster);
+  if (error_only)
+    lin_sliced_kernel<true><<<n_ctas, kLinThreads, 0, stream>>>(ctx_args_dev, tasks_dev, ctas_dev, partials, tickets);
+  else
+    lin_sliced_kernel<false><<<n_ctas, kLinThreads, 0, stream>>>(ctx_args_dev, tasks_dev, ctas_dev, partials, tickets);
   prof.end(group, 1);
-  return e;
+  return cudaGetLastError();
 }
 
 } // namespace formgpu

@@ -251,12 +251,15 @@ __device__ __forceinline__ int match_bin(const MatchRec &m, double max_d2) {
 // group owns the neighbour voxels with the reference's shift ranks s, s+8, s+16, s+24
 // (map.tpp:54-68); its four home-slot loads are issued together, so the 27 probes are still
 // one memory round trip.  The arg-min key (dist^2, shift rank, scan, k) is rule R5.
-constexpr int kQueryLanes = 8;
-constexpr int kQueriesPerWarp = 32 / kQueryLanes;
-constexpr int kQueriesPerCta = 8 * kQueriesPerWarp; // 256 threads
+// A single sequence's call (20 k queries) cannot fill the GPU either way and is latency-
+// bound, so it keeps 32 lanes per query (shortest bucket scans); batched launches use 8.
+constexpr int kLanesSingle = 32, kLanesBatch = 8;
+__host__ __device__ constexpr int queries_per_cta(int lanes) { return 8 * (32 / lanes); } // 256 threads
 
 namespace {
-__device__ __forceinline__ void assoc_nn_body(const AssocArgs &a) {
+template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const AssocArgs &a) {
+  constexpr int kQueriesPerWarp = 32 / kQueryLanes;
+  constexpr int kVox = (27 + kQueryLanes - 1) / kQueryLanes; // voxels owned by a lane
   const int lane = threadIdx.x & 31, sub = lane & (kQueryLanes - 1), grp = lane / kQueryLanes;
   const int q = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kQueriesPerWarp + grp;
   const int nb = a.W + 1;
@@ -272,24 +275,26 @@ __device__ __forceinline__ void assoc_nn_body(const AssocArgs &a) {
             cz = voxel_coord(wz, a.voxel_width);
 
   // phase 1: up to four voxels per lane; the home slots are loaded back to back
-  uint32_t start[4] = {0u, 0u, 0u, 0u}, count[4] = {0u, 0u, 0u, 0u};
-  {
-    unsigned long long key[4];
-    uint32_t h[4];
-    HashSlot s[4];
-    bool live[4];
+  uint32_t start[kVox], count[kVox];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < kVox; ++r) start[r] = count[r] = 0u;
+  {
+    unsigned long long key[kVox];
+    uint32_t h[kVox];
+    HashSlot s[kVox];
+    bool live[kVox];
+#pragma unroll
+    for (int r = 0; r < kVox; ++r) {
       const int v = sub + kQueryLanes * r;
       live[r] = active && v < 27 && a.n_map > 0;
       key[r] = pack_key(cx + lane_shift(v & 31, 0), cy + lane_shift(v & 31, 1), cz + lane_shift(v & 31, 2));
       h[r] = hash_key(key[r]) & a.hash_mask;
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < kVox; ++r)
       if (live[r]) s[r] = a.hash[h[r]];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < kVox; ++r) {
       if (!live[r]) continue;
       while (s[r].key != key[r] && s[r].key != kEmptyKey) { // linear probing (load <= 0.5)
         h[r] = (h[r] + 1) & a.hash_mask;
@@ -337,8 +342,9 @@ __device__ __forceinline__ void assoc_nn_body(const AssocArgs &a) {
   // squared distance from the query to the box of each of this lane's voxels, shrunk by a
   // safety margin that covers the rounding of floor(x / w) at the voxel faces
   unsigned survivors = 0; // bit v: voxel with shift rank v of this group's query must be scanned
+  constexpr unsigned kGroupMask = kQueryLanes == 32 ? 0xffffffffu : ((1u << (kQueryLanes & 31)) - 1u);
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < kVox; ++r) {
     const int v = sub + kQueryLanes * r;
     bool keep = false;
     if (v > 0 && v < 27 && count[r] > 0) {
@@ -356,16 +362,21 @@ __device__ __forceinline__ void assoc_nn_body(const AssocArgs &a) {
       keep = lb <= bound;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    survivors |= ((bal >> (grp * kQueryLanes)) & 0xffu) << (kQueryLanes * r);
+    survivors |= ((bal >> (grp * kQueryLanes)) & kGroupMask) << ((kQueryLanes * r) & 31);
   }
   while (__any_sync(0xffffffffu, survivors != 0u)) {
     const int b = survivors ? __ffs(survivors) - 1 : 0; // shift rank, ascending
     survivors &= survivors - 1u;
-    const int r = b >> 3;
-    const uint32_t my_start = r == 0 ? start[0] : r == 1 ? start[1] : r == 2 ? start[2] : start[3];
-    const uint32_t my_count = r == 0 ? count[0] : r == 1 ? count[1] : r == 2 ? count[2] : count[3];
-    const uint32_t sb = __shfl_sync(0xffffffffu, my_start, b & 7, kQueryLanes);
-    const uint32_t cb = __shfl_sync(0xffffffffu, my_count, b & 7, kQueryLanes);
+    const int r = b / kQueryLanes;
+    uint32_t my_start = start[0], my_count = count[0];
+#pragma unroll
+    for (int rr = 1; rr < kVox; ++rr)
+      if (r == rr) {
+        my_start = start[rr];
+        my_count = count[rr];
+      }
+    const uint32_t sb = __shfl_sync(0xffffffffu, my_start, b % kQueryLanes, kQueryLanes);
+    const uint32_t cb = __shfl_sync(0xffffffffu, my_count, b % kQueryLanes, kQueryLanes);
     if (b > 0) scan_bucket(b, sb, cb);
   }
   // arg-min over the group's lanes with the same key
@@ -406,20 +417,21 @@ __device__ __forceinline__ void assoc_nn_body(const AssocArgs &a) {
 }
 } // namespace
 __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs qa) {
-  assoc_nn_body(blockIdx.y == 0 ? pa : qa);
+  assoc_nn_body<kLanesSingle>(blockIdx.y == 0 ? pa : qa);
 }
 __global__ void __launch_bounds__(256) assoc_nn_batch_kernel(const AssocArgs *items) {
   __shared__ AssocArgs s_a;
   load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
-  if ((int)(blockIdx.x * kQueriesPerCta) >= s_a.n_query) return;
-  assoc_nn_body(s_a);
+  if ((int)(blockIdx.x * queries_per_cta(kLanesBatch)) >= s_a.n_query) return;
+  assoc_nn_body<kLanesBatch>(s_a);
 }
 
 void assoc_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream, Profiler &prof) {
   const int n = max(pa.n_query, qa.n_query);
   if (n <= 0) return;
   prof.begin(FORMGPU_KG_ASSOC_NN);
-  assoc_nn_kernel<<<dim3((n + kQueriesPerCta - 1) / kQueriesPerCta, 2), 256, 0, stream>>>(pa, qa);
+  constexpr int per_cta = queries_per_cta(kLanesSingle);
+  assoc_nn_kernel<<<dim3((n + per_cta - 1) / per_cta, 2), 256, 0, stream>>>(pa, qa);
   prof.end(FORMGPU_KG_ASSOC_NN, 1);
 }
 
@@ -427,8 +439,8 @@ void assoc_batch_launch(const AssocArgs *items_dev, int n_items, int max_query, 
                         Profiler &prof) {
   if (n_items <= 0 || max_query <= 0) return;
   prof.begin(FORMGPU_KG_ASSOC_NN);
-  assoc_nn_batch_kernel<<<dim3((max_query + kQueriesPerCta - 1) / kQueriesPerCta, 2, n_items), 256, 0, stream>>>(
-      items_dev);
+  constexpr int per_cta = queries_per_cta(kLanesBatch);
+  assoc_nn_batch_kernel<<<dim3((max_query + per_cta - 1) / per_cta, 2, n_items), 256, 0, stream>>>(items_dev);
   prof.end(FORMGPU_KG_ASSOC_NN, 1);
 }
 
