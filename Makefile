@@ -2,7 +2,7 @@
 # snapshot):
 #   form_b200/lib/libformgpu.so   CUDA hot path + C-ABI (include/formgpu.h)
 #   form_b200/lib/libformhost.so  C++ host facade (form::Estimator, synthetic scans)
-# and, for tests / bench baselines only, oracle/_build/liboracle.so.
+# and, for tests / bench baselines only, oracle/_build/liboracle.so and oracle/_ref/libformref.so.
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       ?= g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
@@ -44,10 +44,13 @@ $(OBJDIR)/host_%.o: form_b200/host/src/%.cpp $(HOST_HDRS)
 $(LIBDIR)/libformhost.so: $(HOST_OBJS) $(LIBDIR)/libformgpu.so
 	$(CXX) -shared -pthread -o $@ $(HOST_OBJS) -L$(LIBDIR) -lformgpu -Wl,-rpath,'$$ORIGIN'
 
+# oracle/_ref: FORM's own stage-1/2 sources compiled from /root/reference against API
+# stand-ins (test infrastructure; skipped where the reference tree is absent)
 oracle: $(LIBDIR)/libformgpu.so
 	$(MAKE) -s -C oracle
+	$(MAKE) -s -C oracle/ref
 
 clean:
-	rm -rf build $(LIBDIR)/*.so oracle/_build
+	rm -rf build $(LIBDIR)/*.so oracle/_build oracle/_ref
 
 .PHONY: all oracle clean
