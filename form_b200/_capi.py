@@ -173,6 +173,9 @@ FORMGPU_SYMBOLS = {
     "formgpu_profile_read": (_i, [_vp, _vp, _vp]),
     "formgpu_launch_count": (_u64, [_vp]),
     "formgpu_synchronize": (_i, [_vp]),
+    "formgpu_set_shard": (_i, [_vp, _i, _i]),
+    "formgpu_linearize_device": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "formgpu_error_device": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "formgpu_batch_create": (_i, [C.POINTER(Params), _i, _vp, _sz, C.POINTER(_vp)]),
     "formgpu_batch_destroy": (None, [_vp]),
     "formgpu_batch_size": (_sz, [_vp]),

@@ -170,6 +170,26 @@ class Context:
                                             poses.shape[0], _capi.ptr(out)))
         return out
 
+    # -- point-sharded mode ----------------------------------------------------------
+    def set_shard(self, rank: int, world: int):
+        """Stage-3 calls reduce only the rank-th of `world` shares of every pair (the caller
+        sums the blocks over the ranks); (0, 1) switches the mode off."""
+        self._check(self._lib.formgpu_set_shard(self._h, rank, world))
+
+    def linearize_device(self, pairs: np.ndarray, poses: np.ndarray, out_dev_ptr: int):
+        """formgpu_linearize_device: blocks into device memory at out_dev_ptr (91 doubles per
+        pair), queued on the context's stream, nothing is waited for."""
+        pairs = np.ascontiguousarray(pairs, dtype=_capi.PAIR)
+        poses = np.ascontiguousarray(poses, dtype=_capi.SCAN_POSE)
+        self._check(self._lib.formgpu_linearize_device(self._h, _capi.ptr(pairs), pairs.shape[0],
+                                                       _capi.ptr(poses), poses.shape[0], C.c_void_p(out_dev_ptr)))
+
+    def error_device(self, pairs: np.ndarray, poses: np.ndarray, out_dev_ptr: int):
+        pairs = np.ascontiguousarray(pairs, dtype=_capi.PAIR)
+        poses = np.ascontiguousarray(poses, dtype=_capi.SCAN_POSE)
+        self._check(self._lib.formgpu_error_device(self._h, _capi.ptr(pairs), pairs.shape[0],
+                                                   _capi.ptr(poses), poses.shape[0], C.c_void_p(out_dev_ptr)))
+
     # -- instrumentation -----------------------------------------------------------
     def profile_enable(self, on: bool = True):
         self._check(self._lib.formgpu_profile_enable(self._h, int(on)))

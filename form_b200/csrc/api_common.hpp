@@ -49,7 +49,7 @@ int wait_flag(formgpu_ctx *ctx, int which, unsigned long long seq);
 void relative_pose(const formgpu_pose &Ti, const formgpu_pose &Tj, double rel[12]);
 /// Launch one cluster per task (no wait).  Assigns and returns the sequence number.
 int lin_launch(formgpu_ctx *ctx, const std::vector<LinTask> &tasks, bool error_only,
-               unsigned long long *seq_out);
+               unsigned long long *seq_out, double *out_plain = nullptr);
 /// Spin until every word of the listed pairs carries the call's tag, decoding them into
 /// dst (per_pair = 91 doubles for blocks, 1 for errors; dst[k] belongs to out_indices[k]).
 int lin_wait(formgpu_ctx *ctx, const int *out_indices, size_t n, unsigned long long seq,

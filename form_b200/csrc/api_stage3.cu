@@ -37,12 +37,16 @@ void lin_make_args(formgpu_ctx *ctx, int n_tasks, LinArgs &a) {
   a.inv_sigma2 = 1.0 / (ctx->P.sigma * ctx->P.sigma);
   a.out = ctx->h_out;
   a.seq = ++ctx->seq;
+  a.shard_rank = ctx->shard_rank;
+  a.shard_world = ctx->shard_world;
+  a.out_plain = nullptr;
 }
 
 int lin_launch(formgpu_ctx *ctx, const std::vector<LinTask> &tasks, bool error_only,
-               unsigned long long *seq_out) {
+               unsigned long long *seq_out, double *out_plain) {
   LinArgs a;
   lin_make_args(ctx, (int)tasks.size(), a);
+  a.out_plain = out_plain;
   *seq_out = a.seq;
   if (tasks.empty()) return FORMGPU_OK;
   if ((int)tasks.size() <= kLinInlineTasks) {
@@ -185,9 +189,56 @@ int run(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs, const formg
   return FORMGPU_OK;
 }
 
+// device-output variants: blocks stay in device memory (zero-filled for empty pairs) and
+// nothing is waited for - a collective queued on the same stream consumes them
+int run_device(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs, const formgpu_scan_pose *poses,
+               size_t n_poses, bool error_only, double *out_dev) {
+  const size_t per_pair = error_only ? 1 : 91;
+  static thread_local std::vector<LinTask> tasks;
+  static thread_local std::vector<int> indices;
+  static thread_local std::vector<double> sink;
+  sink.resize(n_pairs * per_pair); // lin_build_tasks zero-fills the host slots of empty pairs
+  int rc = lin_build_tasks(ctx, pairs, n_pairs, poses, n_poses, per_pair, sink.data(), tasks, indices);
+  if (rc) return rc;
+  FORMGPU_CUDA(ctx, cudaMemsetAsync(out_dev, 0, n_pairs * per_pair * sizeof(double), ctx->stream));
+  unsigned long long seq = 0;
+  return lin_launch(ctx, tasks, error_only, &seq, out_dev);
+}
+
 } // namespace
 
 extern "C" {
+
+int formgpu_set_shard(formgpu_ctx *ctx, int rank, int world) {
+  if (!ctx) return FORMGPU_ERR_INVALID_ARG;
+  if (world < 1 || rank < 0 || rank >= world)
+    return fail(ctx, FORMGPU_ERR_INVALID_ARG, "formgpu_set_shard: need 0 <= rank < world");
+  ctx->shard_rank = rank;
+  ctx->shard_world = world;
+  return FORMGPU_OK;
+}
+
+int formgpu_linearize_device(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
+                             const formgpu_scan_pose *poses, size_t n_poses, double *out91_dev) {
+  if (!ctx) return FORMGPU_ERR_INVALID_ARG;
+  if (n_pairs == 0) return FORMGPU_OK;
+  if (!pairs || !out91_dev || (n_poses && !poses))
+    return fail(ctx, FORMGPU_ERR_INVALID_ARG, "formgpu_linearize_device: null argument");
+  FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  ProfScope scope(ctx);
+  return run_device(ctx, pairs, n_pairs, poses, n_poses, false, out91_dev);
+}
+
+int formgpu_error_device(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
+                         const formgpu_scan_pose *poses, size_t n_poses, double *out_dev) {
+  if (!ctx) return FORMGPU_ERR_INVALID_ARG;
+  if (n_pairs == 0) return FORMGPU_OK;
+  if (!pairs || !out_dev || (n_poses && !poses))
+    return fail(ctx, FORMGPU_ERR_INVALID_ARG, "formgpu_error_device: null argument");
+  FORMGPU_CUDA(ctx, cudaSetDevice(ctx->device));
+  ProfScope scope(ctx);
+  return run_device(ctx, pairs, n_pairs, poses, n_poses, true, out_dev);
+}
 
 int formgpu_linearize(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
                       const formgpu_scan_pose *poses, size_t n_poses, double *out91) {

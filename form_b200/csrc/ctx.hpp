@@ -235,6 +235,9 @@ struct formgpu_ctx {
   unsigned *d_counters = nullptr; // [pair tickets (cap) | done counters (8)]
   size_t counter_cap = 0;
 
+  // ---- point-sharded mode (formgpu_set_shard) ----
+  int shard_rank = 0, shard_world = 1;
+
   // ---- linearisation scratch ----
   double *d_partials = nullptr;
   size_t partial_cap = 0; // chunks

@@ -197,6 +197,14 @@ struct LinArgs {
   // blocks, [n_pairs][2] for errors; word = 32 bits of payload | (seq & 0xffffffff) << 32
   volatile unsigned long long *out;
   unsigned long long seq;
+  // point-sharded mode: this context reduces only the shard_rank-th of
+  // shard_world contiguous shares of every pair's correspondences; the caller sums the
+  // per-pair blocks over the ranks (NCCL all-reduce of 91 * P doubles)
+  int shard_rank, shard_world;
+  // != nullptr: blocks / errors are written as plain doubles into DEVICE memory
+  // ([n_pairs][91] or [n_pairs]) instead of the tagged host words, so that a collective
+  // queued on the same stream can consume them without a host round trip
+  double *out_plain;
 };
 cudaError_t linearize_launch(const LinArgs &a, const LinInline *inline_req, bool error_only,
                              cudaStream_t stream, Profiler &prof);

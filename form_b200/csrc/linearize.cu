@@ -185,7 +185,7 @@ template <bool kWarpScope = false>
 __device__ __forceinline__ void expand_and_publish(ExpandSmem &S, const double *Wp28, const double *Wq28,
                                                    bool has_planar, bool has_point, double inv_sigma2,
                                                    volatile unsigned long long *out182,
-                                                   unsigned long long tag) {
+                                                   unsigned long long tag, double *plain91 = nullptr) {
   const int tid = kWarpScope ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
   const int nthreads = kWarpScope ? 32 : (int)blockDim.x;
   if (tid < 28) {
@@ -232,8 +232,19 @@ __device__ __forceinline__ void expand_and_publish(ExpandSmem &S, const double *
 #pragma unroll
         for (int k = 0; k < 7; ++k) sum += S.Bq[k][r][x] * S.Tq[r][k][y];
     }
-    publish_tagged(out182 + 2 * o, sum * inv_sigma2, tag);
+    if (plain91) plain91[o] = sum * inv_sigma2;
+    else publish_tagged(out182 + 2 * o, sum * inv_sigma2, tag);
   }
+}
+
+// this rank's contiguous share of a pair's n correspondences (point-sharded mode; the whole
+// range when shard_world == 1)
+__device__ __forceinline__ void shard_range(uint32_t n, int shard_rank, int shard_world, uint32_t &begin,
+                                            uint32_t &count) {
+  const uint32_t lo = (uint32_t)(((unsigned long long)n * (unsigned)shard_rank) / (unsigned)shard_world);
+  const uint32_t hi = (uint32_t)(((unsigned long long)n * (unsigned)(shard_rank + 1)) / (unsigned)shard_world);
+  begin = lo;
+  count = hi - lo;
 }
 
 // ---------------------------------------------------------------------------
@@ -256,6 +267,16 @@ __device__ __forceinline__ void lin_cluster_body(const LinArgs &a, const LinTask
     task.off_point = a.pair_row[2 * nb + si];
     task.n_point = a.pair_row[3 * nb + si];
     if (task.n_planar + task.n_point == 0) return; // empty pair: the whole cluster leaves
+  }
+  const bool has_planar = task.n_planar > 0, has_point = task.n_point > 0;
+  if (a.shard_world > 1) { // this rank's share of the pair
+    uint32_t b0, c0;
+    shard_range(task.n_planar, a.shard_rank, a.shard_world, b0, c0);
+    task.off_planar += b0;
+    task.n_planar = c0;
+    shard_range(task.n_point, a.shard_rank, a.shard_world, b0, c0);
+    task.off_point += b0;
+    task.n_point = c0;
   }
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -374,10 +395,14 @@ __device__ __forceinline__ void lin_cluster_body(const LinArgs &a, const LinTask
   // separate flag are needed - an aligned 8-byte store is a single atomic PCIe write.
   const unsigned long long tag = a.seq & 0xffffffffull;
   if (kErrorOnly) {
-    if (tid == 0) publish_tagged(a.out + 2 * (size_t)task.out_index, s_total[0][0], tag);
+    if (tid == 0) {
+      if (a.out_plain) a.out_plain[task.out_index] = s_total[0][0];
+      else publish_tagged(a.out + 2 * (size_t)task.out_index, s_total[0][0], tag);
+    }
   } else if (!(a.debug_flags & 2)) {
-    expand_and_publish(s_exp, s_total[0], s_total[1], task.n_planar > 0, task.n_point > 0,
-                       a.inv_sigma2, a.out + 182 * (size_t)task.out_index, tag);
+    expand_and_publish(s_exp, s_total[0], s_total[1], has_planar, has_point, a.inv_sigma2,
+                       a.out + 182 * (size_t)task.out_index, tag,
+                       a.out_plain ? a.out_plain + 91 * (size_t)task.out_index : nullptr);
   }
   LIN_TS(7);
 }

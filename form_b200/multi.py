@@ -48,3 +48,25 @@ def allreduce_blocks(blocks: np.ndarray, device=None) -> np.ndarray:
         t = t.to(device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.cpu().numpy()
+
+
+def sharded_linearize(ctx, pairs: np.ndarray, poses: np.ndarray, error_only: bool = False):
+    """Point-sharded stage 3 on the CUDA path (SURVEY 8e mode 2).  Every rank holds a replica
+    of the sequence's context (`ctx`, created on torch's current stream and switched to its
+    shard with ctx.set_shard(rank, world)); each linearises its share of every pair into
+    device memory and ONE NCCL all-reduce of 91 * P doubles (errors: P) over NVLink sums the
+    blocks - queued on the same stream, so there is no host round trip before the
+    collective.  Returns the full blocks (P x 91) / errors (P) on the host."""
+    import torch
+    import torch.distributed as dist
+
+    n = int(pairs.shape[0])
+    out = torch.empty(n * (1 if error_only else 91), dtype=torch.float64, device="cuda")
+    if error_only:
+        ctx.error_device(pairs, poses, out.data_ptr())
+    else:
+        ctx.linearize_device(pairs, poses, out.data_ptr())
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.SUM)
+    res = out.cpu().numpy()
+    return res if error_only else res.reshape(n, 91)

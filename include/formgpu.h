@@ -240,6 +240,26 @@ int formgpu_linearize(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pair
 int formgpu_error(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
                   const formgpu_scan_pose *poses, size_t n_poses, double *out);
 
+/* ---- point-sharded mode: one dense sequence over several GPUs ------------ */
+
+/* For very dense scans the correspondences of ONE sequence can be linearised by several
+ * GPUs (BASELINE.json configs[4]): every rank runs stages 1-2 on its own replica
+ * of the context (same inputs, bit-identical state) and formgpu_set_shard(rank, world)
+ * makes its stage-3 calls reduce only the rank-th of `world` contiguous shares of every
+ * pair's correspondences.  The 13x13 blocks are additive in the correspondences, so the
+ * block of a pair is the SUM of the ranks' blocks: the caller all-reduces 91 * n_pairs
+ * doubles (errors: n_pairs).  rank = 0, world = 1 (the default) switches the mode off. */
+int formgpu_set_shard(formgpu_ctx *ctx, int rank, int world);
+
+/* formgpu_linearize / formgpu_error with the result left in DEVICE memory (91 doubles
+ * per pair / one per pair, zeros for pairs without correspondences) and no wait: the work
+ * is queued on the context's stream, so a collective queued on the same stream (NCCL
+ * all-reduce over NVLink) consumes the blocks without a host round trip. */
+int formgpu_linearize_device(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
+                             const formgpu_scan_pose *poses, size_t n_poses, double *out91_dev);
+int formgpu_error_device(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
+                         const formgpu_scan_pose *poses, size_t n_poses, double *out_dev);
+
 /* ---- batched submit: many independent sequences per launch --------------- */
 #define FORMGPU_KG_COUNT 12 /* kernel groups, listed under "instrumentation" below */
 

@@ -1,0 +1,121 @@
+"""Point-sharded stage 3 (formgpu_set_shard, formgpu_linearize_device; SURVEY 8e mode 2,
+BASELINE.json configs[4]): the blocks of the shards add up to the block of the whole pair.
+One GPU plays every rank in turn; with two or more GPUs a real two-rank NCCL run sums the
+shard blocks with one all-reduce and compares them with the unsharded result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from form_b200 import _capi, synth
+from helpers import block_rel_err, gt, perturbed, scan_poses
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build_world(ctx, sensor, n_scans, seq=0):
+    """Replicated stages 1-2: the same inputs give every rank a bit-identical context."""
+    rng = np.random.default_rng(7)
+    est, window = {}, []
+    for k in range(n_scans):
+        ctx.extract(synth.scan(sensor, seq, k), k)
+        est[k] = perturbed(gt(seq, k), rng, 0.001, 0.01)
+        poses = scan_poses(window + [k], [est[s] for s in window + [k]])
+        ctx.map_rebuild(poses)
+        ctx.associate(est[k])
+        ctx.commit_scan()
+        window.append(k)
+    poses = scan_poses(window, [est[s] for s in window])
+    pairs = np.array([(i, j) for j in window for i in window if i < j], dtype=_capi.PAIR)
+    return pairs, poses
+
+
+def test_shard_blocks_sum_to_the_full_block_on_one_gpu():
+    import torch
+
+    from form_b200.context import Context
+
+    rows, cols = synth.shape("vlp-16")
+    params = _capi.default_params(rows, cols)
+    stream = torch.cuda.current_stream().cuda_stream
+    with Context(params, stream=stream) as ctx:
+        pairs, poses = _build_world(ctx, "vlp-16", 4)
+        full = ctx.linearize(pairs, poses)
+        full_err = ctx.error(pairs, poses)
+        assert np.abs(full).sum() > 0
+        for world in (2, 3, 8):
+            acc = torch.zeros(len(pairs) * 91, dtype=torch.float64, device="cuda")
+            acc_err = np.zeros(len(pairs))
+            acc_host = np.zeros_like(full)
+            for rank in range(world):
+                ctx.set_shard(rank, world)
+                part = torch.empty_like(acc)
+                ctx.linearize_device(pairs, poses, part.data_ptr())  # same stream as torch
+                acc += part
+                acc_host += ctx.linearize(pairs, poses)              # host-output path shards too
+                acc_err += ctx.error(pairs, poses)
+            ctx.set_shard(0, 1)
+            got = acc.cpu().numpy().reshape(len(pairs), 91)
+            for a, b, c in zip(got, full, acc_host):
+                assert block_rel_err(a, b) < 1e-12
+                assert block_rel_err(c, b) < 1e-12
+            assert np.allclose(acc_err, full_err, rtol=1e-12, atol=0)
+        assert ctx.linearize(pairs, poses).tobytes() == full.tobytes()  # mode off again: identical
+        with pytest.raises(Exception):
+            ctx.set_shard(2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _nccl_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    from form_b200 import multi
+    from form_b200.context import Context
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    rows, cols = synth.shape("vlp-16")
+    params = _capi.default_params(rows, cols)
+    with Context(params, device=rank, stream=torch.cuda.current_stream().cuda_stream) as ctx:
+        pairs, poses = _build_world(ctx, "vlp-16", 4)
+        full = ctx.linearize(pairs, poses)
+        ctx.set_shard(rank, world)
+        summed = multi.sharded_linearize(ctx, pairs, poses)
+        errs = multi.sharded_linearize(ctx, pairs, poses, error_only=True)
+        ctx.set_shard(0, 1)
+        full_err = ctx.error(pairs, poses)
+        worst = max(block_rel_err(a, b) for a, b in zip(summed, full))
+        ok = worst < 1e-12 and np.allclose(errs, full_err, rtol=1e-12, atol=0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        with open(out_path, "w") as f:
+            f.write("ok" if ok else f"mismatch {worst}")
+
+
+def test_two_rank_nccl_allreduce_of_shard_blocks():
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import tempfile
+
+    out = tempfile.mktemp()
+    mp.spawn(_nccl_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
