@@ -98,7 +98,7 @@ template <typename T> const T *staged(const formgpu_batch *b, size_t offset) {
   return reinterpret_cast<const T *>(b->d_args + offset);
 }
 
-// Scratch of the sliced linearisation launches: 56 doubles per CTA, one ticket per task.
+// Scratch of the batched linearisation launches: 56 doubles per slice, one ticket per task.
 int ensure_lin_scratch(formgpu_batch *b, size_t n_ctas, size_t n_tasks) {
   if (n_ctas > b->partial_cap) {
     BATCH_CUDA(b, cudaStreamSynchronize(b->stream));
@@ -122,61 +122,48 @@ int ensure_lin_scratch(formgpu_batch *b, size_t n_ctas, size_t n_tasks) {
   return FORMGPU_OK;
 }
 
-// Linearisation tasks of several contexts in two launches: pairs of up to kLinWarpTask
-// correspondences are reduced by one warp each (eight per CTA); every larger pair is sliced
-// over ceil(size / kLinSlice) CTAs.  `size` is the host's estimate; the kernels divide the
-// TRUE range by the CTA count, so a wrong estimate costs balance, not correctness.
+// Linearisation tasks of several contexts in ONE launch: every pair is cut into
+// ceil(size / kLinWarpSlice) warp-sized slices.  `size` is the host's estimate; the kernel
+// divides the TRUE range by the slice count, so a wrong estimate costs balance, not
+// correctness.  Slices of large pairs come first (they are the long pole).
 int stage_lin_groups(formgpu_batch *b, const std::vector<LinArgs> &ctx_args, const std::vector<LinTask> &tasks,
                      const std::vector<uint32_t> &size_hint, bool error_only,
                      std::vector<std::function<int()>> &launchers) {
   if (tasks.empty()) return FORMGPU_OK;
-  std::vector<LinCta> ctas, warps;
-  ctas.reserve(tasks.size() * 2);
-  warps.reserve(tasks.size());
-  size_t n_sliced_tasks = 0;
-  for (size_t t = 0; t < tasks.size(); ++t) {
+  std::vector<size_t> order(tasks.size());
+  for (size_t t = 0; t < order.size(); ++t) order[t] = t;
+  std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return size_hint[x] > size_hint[y]; });
+  std::vector<LinCta> slices;
+  slices.reserve(tasks.size() * 4);
+  for (size_t t : order) {
     const LinArgs &ca = ctx_args[tasks[t].ctx_index];
-    if (size_hint[t] <= kLinWarpTask) {
-      warps.push_back(LinCta{(uint32_t)t, 0u, (uint16_t)0, (uint16_t)1, tasks[t].ctx_index, ca.pair_row,
-                             tasks[t].dyn_slot_i_plus1, (uint32_t)ca.W + 1u});
-      continue;
-    }
-    ++n_sliced_tasks;
-    const uint32_t n = std::min<uint32_t>(std::max<uint32_t>((size_hint[t] + kLinSlice - 1) / kLinSlice, 1u), 1024u);
-    const uint32_t first = (uint32_t)ctas.size();
+    const uint32_t n =
+        std::min<uint32_t>(std::max<uint32_t>((size_hint[t] + kLinWarpSlice - 1) / kLinWarpSlice, 1u), 4096u);
+    const uint32_t first = (uint32_t)slices.size();
     for (uint32_t r = 0; r < n; ++r)
-      ctas.push_back(LinCta{(uint32_t)t, first, (uint16_t)r, (uint16_t)n, tasks[t].ctx_index, ca.pair_row,
-                            tasks[t].dyn_slot_i_plus1, (uint32_t)ca.W + 1u});
+      slices.push_back(LinCta{(uint32_t)t, first, (uint16_t)r, (uint16_t)n, tasks[t].ctx_index, ca.pair_row,
+                              tasks[t].dyn_slot_i_plus1, (uint32_t)ca.W + 1u});
   }
   // every launch of a submit gets its own scratch range: launches of one submit run back
   // to back and could otherwise overlap on the partial sums (tickets are indexed by task)
   const size_t part_base = b->partials_used, ticket_base = b->tickets_used;
-  b->partials_used += ctas.size();
+  b->partials_used += slices.size();
   b->tickets_used += tasks.size();
   int rc = ensure_lin_scratch(b, b->partials_used, b->tickets_used);
   if (rc) return rc;
-  size_t off_ctx = 0, off_tasks = 0, off_ctas = 0, off_warps = 0;
+  size_t off_ctx = 0, off_tasks = 0, off_slices = 0;
   rc = stage_args(b, ctx_args.data(), ctx_args.size(), &off_ctx);
   if (rc) return rc;
   rc = stage_args(b, tasks.data(), tasks.size(), &off_tasks);
   if (rc) return rc;
-  if (!ctas.empty()) {
-    rc = stage_args(b, ctas.data(), ctas.size(), &off_ctas);
-    if (rc) return rc;
-  }
-  if (!warps.empty()) {
-    rc = stage_args(b, warps.data(), warps.size(), &off_warps);
-    if (rc) return rc;
-  }
-  const int n_ctas = (int)ctas.size(), n_warps = (int)warps.size();
+  rc = stage_args(b, slices.data(), slices.size(), &off_slices);
+  if (rc) return rc;
+  const int n_slices = (int)slices.size();
   launchers.push_back([=]() -> int {
-    // big pairs first: they are the long pole; the warp-sized ones fill in behind
-    BATCH_CUDA(b, linearize_sliced_launch(staged<LinArgs>(b, off_ctx), staged<LinTask>(b, off_tasks),
-                                          staged<LinCta>(b, off_ctas), n_ctas,
-                                          b->d_partials + part_base * 56, b->d_tickets + ticket_base,
-                                          error_only, b->stream, b->prof));
     BATCH_CUDA(b, linearize_warp_launch(staged<LinArgs>(b, off_ctx), staged<LinTask>(b, off_tasks),
-                                        staged<LinCta>(b, off_warps), n_warps, error_only, b->stream, b->prof));
+                                        staged<LinCta>(b, off_slices), n_slices,
+                                        b->d_partials + part_base * 56, b->d_tickets + ticket_base,
+                                        error_only, b->stream, b->prof));
     return FORMGPU_OK;
   });
   return FORMGPU_OK;

@@ -208,28 +208,24 @@ struct LinArgs {
 };
 cudaError_t linearize_launch(const LinArgs &a, const LinInline *inline_req, bool error_only,
                              cudaStream_t stream, Profiler &prof);
-/// Batched launches: correspondences per CTA slice the host aims for, and the CTA table.
-constexpr uint32_t kLinSlice = 2048;
-constexpr uint32_t kLinWarpTask = 768; // pairs up to this size are reduced by a single warp
-struct LinCta { // one CTA of a batched linearisation launch (32 B)
+/// Batched launches: correspondences per warp slice the host aims for, and the slice table.
+constexpr uint32_t kLinWarpSlice = 512;
+struct LinCta { // one warp-sized slice of a pair in a batched linearisation launch (32 B)
   uint32_t task;  // index into the task array
-  uint32_t first; // index of the task's first CTA (= base of its partial sums)
-  uint16_t rank;  // this CTA's share of the pair: rank of n_cta
-  uint16_t n_cta;
+  uint32_t first; // index of the task's first slice (= base of its partial sums)
+  uint16_t rank;  // this slice's share of the pair: rank of n_cta
+  uint16_t n_cta; // slices of the pair
   uint32_t ctx_index;      // = tasks[task].ctx_index, so task and context load together
   const uint32_t *pair_row; // device [type][off|cnt][W+1] of the task's context (dynamic ranges)
   uint32_t dyn_slot_i_plus1; // = tasks[task].dyn_slot_i_plus1
   uint32_t row_stride;     // W + 1
 };
 static_assert(sizeof(LinCta) == 32, "LinCta size");
-/// Tasks of several contexts in one launch: ctx_args_dev[task.ctx_index] is the task's
-/// context; `partials` holds 56 doubles per CTA, `tickets` one zeroed counter per task.
-/// Small pairs: one warp per entry (entries as LinCta with rank 0 of 1), eight per CTA.
+/// Tasks of several contexts in one launch, one warp per slice (eight per CTA):
+/// ctx_args_dev[task.ctx_index] is the task's context; `partials` holds 56 doubles per
+/// slice, `tickets` one zeroed counter per task.
 cudaError_t linearize_warp_launch(const LinArgs *ctx_args_dev, const LinTask *tasks_dev,
-                                  const LinCta *entries_dev, int n_entries, bool error_only,
-                                  cudaStream_t stream, Profiler &prof);
-cudaError_t linearize_sliced_launch(const LinArgs *ctx_args_dev, const LinTask *tasks_dev,
-                                    const LinCta *ctas_dev, int n_ctas, double *partials, unsigned *tickets,
-                                    bool error_only, cudaStream_t stream, Profiler &prof);
+                                  const LinCta *entries_dev, int n_entries, double *partials,
+                                  unsigned *tickets, bool error_only, cudaStream_t stream, Profiler &prof);
 
 } // namespace formgpu

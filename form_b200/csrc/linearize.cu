@@ -425,174 +425,27 @@ __global__ void __launch_bounds__(kLinThreads) lin_global_kernel(LinArgs a) {
 }
 
 // ---------------------------------------------------------------------------
-// batched launches: the tasks of several contexts in ONE grid, sliced evenly
+// batched launches: the tasks of several contexts in ONE grid, one WARP per slice
 // ---------------------------------------------------------------------------
 // A batched request holds hundreds of pairs of very different sizes (the pair with the
-// oldest key scan has ~15 k correspondences, most others a few hundred).  One cluster
-// per pair leaves the launch latency-bound on the big pairs (ncu: 16 warps per SM, 0.5
-// TB/s).  Here every pair gets n_cta = ceil(size / kLinSlice) CTAs chosen by the host;
-// CTA r streams the r-th share of the pair's planar and point ranges with its loads
-// issued four correspondences deep, leaves its 2 x 28 moments in global memory, and the
-// LAST CTA of the pair to arrive (ticket counter) adds the partial sums in rank order -
-// a fixed order, so the result does not depend on which CTA came last - expands the
-// block and publishes it.  task.ctx_index selects the context's argument block
-// (segments, pair row, result buffer, sequence tag).
-template <bool kErrorOnly>
-__global__ void __launch_bounds__(kLinThreads)
-lin_sliced_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ctas, double *partials,
-                  unsigned *tickets) {
-  __shared__ LinTask s_task;
-  __shared__ LinArgs s_args;
-  __shared__ double s_warp[kWarps][28];
-  __shared__ double s_sum[2][28];
-  __shared__ ExpandSmem s_exp;
-  __shared__ unsigned s_ticket;
-  static_assert(sizeof(LinArgs) % 8 == 0 && sizeof(LinArgs) / 8 <= 32, "LinArgs copy");
-  const int tid = threadIdx.x;
-  const LinCta me = ctas[blockIdx.x];
-  // task, context block and (for dynamic ranges) the pair row are independent loads: one
-  // memory round trip instead of three dependent ones
-  __shared__ uint32_t s_dyn[4];
-  if (tid < (int)(sizeof(LinTask) / sizeof(unsigned long long)))
-    reinterpret_cast<unsigned long long *>(&s_task)[tid] =
-        reinterpret_cast<const unsigned long long *>(tasks + me.task)[tid];
-  else if (tid >= 32 && tid < 32 + (int)(sizeof(LinArgs) / sizeof(unsigned long long)))
-    reinterpret_cast<unsigned long long *>(&s_args)[tid - 32] =
-        reinterpret_cast<const unsigned long long *>(ctx_args + me.ctx_index)[tid - 32];
-  else if (tid >= 64 && tid < 68 && me.dyn_slot_i_plus1) // ranges written by the association queued just before
-    s_dyn[tid - 64] = __ldcg(&me.pair_row[(size_t)(tid - 64) * me.row_stride + (me.dyn_slot_i_plus1 - 1u)]);
-  __syncthreads();
-  const LinArgs &a = s_args;
-  uint32_t off_planar = s_task.off_planar, n_planar = s_task.n_planar;
-  uint32_t off_point = s_task.off_point, n_point = s_task.n_point;
-  if (me.dyn_slot_i_plus1) {
-    off_planar = s_dyn[0];
-    n_planar = s_dyn[1];
-    off_point = s_dyn[2];
-    n_point = s_dyn[3];
-    if (n_planar + n_point == 0) return; // empty pair: all its CTAs leave, nothing is published
-  }
-  const double *rel = s_task.rel;
-  const int rank = me.rank, n_cta = me.n_cta;
-  double acc[32];
-  double err_acc = 0.0;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) acc[k] = 0.0;
-  // ---- plane-point correspondences of this CTA's slice ----
-  {
-    const uint32_t lo = (uint32_t)(((unsigned long long)n_planar * rank) / n_cta);
-    const uint32_t hi = (uint32_t)(((unsigned long long)n_planar * (rank + 1)) / n_cta);
-    const float *s = a.seg_planar + (size_t)s_task.slot_j * 9 * a.kp_cap + off_planar;
-    const size_t st = a.kp_cap;
-#pragma unroll 4
-    for (uint32_t c = lo + tid; c < hi; c += kThreads) {
-      const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
-      const double nx = s[3 * st + c], ny = s[4 * st + c], nz = s[5 * st + c];
-      const double pjx = s[6 * st + c], pjy = s[7 * st + c], pjz = s[8 * st + c];
-      double qx, qy, qz;
-      apply_rel(rel, pjx, pjy, pjz, qx, qy, qz);
-      const double r = nx * (qx - pix) + ny * (qy - piy) + nz * (qz - piz);
-      if (kErrorOnly) {
-        err_acc += r * r;
-      } else {
-        const double v[7] = {ny * qz - nz * qy, nz * qx - nx * qz, nx * qy - ny * qx, nx, ny, nz, r};
-        int e = 0;
-#pragma unroll
-        for (int p = 0; p < 7; ++p)
-#pragma unroll
-          for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
-      }
-    }
-  }
-  if (!kErrorOnly) {
-    block_reduce28(acc, s_warp, s_sum[0], tid);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) acc[k] = 0.0;
-  }
-  // ---- point-point correspondences ----
-  if (n_point) {
-    const uint32_t lo = (uint32_t)(((unsigned long long)n_point * rank) / n_cta);
-    const uint32_t hi = (uint32_t)(((unsigned long long)n_point * (rank + 1)) / n_cta);
-    const float *s = a.seg_point + (size_t)s_task.slot_j * 6 * a.kq_cap + off_point;
-    const size_t st = a.kq_cap;
-#pragma unroll 4
-    for (uint32_t c = lo + tid; c < hi; c += kThreads) {
-      const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
-      const double pjx = s[3 * st + c], pjy = s[4 * st + c], pjz = s[5 * st + c];
-      double qx, qy, qz;
-      apply_rel(rel, pjx, pjy, pjz, qx, qy, qz);
-      const double ex = qx - pix, ey = qy - piy, ez = qz - piz;
-      if (kErrorOnly) {
-        err_acc += ex * ex + ey * ey + ez * ez;
-      } else {
-        const double v[7] = {pix, piy, piz, ex, ey, ez, 1.0};
-        int e = 0;
-#pragma unroll
-        for (int p = 0; p < 7; ++p)
-#pragma unroll
-          for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
-      }
-    }
-  }
-  if (kErrorOnly) {
-    const double w = warp_sum(err_acc);
-    if ((tid & 31) == 0) s_warp[tid >> 5][0] = w;
-    __syncthreads();
-    if (tid == 0) {
-      double v = 0.0;
-#pragma unroll
-      for (int k = 0; k < kWarps; ++k) v += s_warp[k][0];
-      s_sum[0][0] = v;
-    }
-    __syncthreads();
-  } else {
-    block_reduce28(acc, s_warp, s_sum[1], tid); // zeros when the pair has no point rows
-  }
-
-  // ---- leave the partial sums, take a ticket; the last CTA of the pair finishes it ----
-  double *mine = partials + (size_t)(me.first + rank) * 56;
-  if (kErrorOnly) {
-    if (tid == 0) mine[0] = s_sum[0][0];
-  } else if (tid < 56) {
-    mine[tid] = s_sum[tid / 28][tid % 28];
-  }
-  if (tid < 64) __threadfence(); // the writers' warps: their partial sums before the ticket
-  __syncthreads();
-  if (tid == 0) s_ticket = atomicAdd(&tickets[me.task], 1u);
-  __syncthreads();
-  if (s_ticket != (unsigned)(n_cta - 1)) return;
-  if (tid == 0) tickets[me.task] = 0u; // self-cleaning for the next launch
-  __threadfence();
-  const double *all = partials + (size_t)me.first * 56;
-  const unsigned long long tag = a.seq & 0xffffffffull;
-  if (kErrorOnly) {
-    if (tid == 0) {
-      double v = 0.0;
-      for (int r = 0; r < n_cta; ++r) v += __ldcg(&all[(size_t)r * 56]);
-      publish_tagged(a.out + 2 * (size_t)s_task.out_index, 0.5 * v * a.inv_sigma2, tag);
-    }
-    return;
-  }
-  if (tid < 56) {
-    double v = 0.0;
-    for (int r = 0; r < n_cta; ++r) v += __ldcg(&all[(size_t)r * 56 + tid]); // rank order: deterministic
-    s_sum[tid / 28][tid % 28] = v;
-  }
-  build_basis(s_exp, rel); // starts with a __syncthreads
-  __syncthreads();
-  expand_and_publish(s_exp, s_sum[0], s_sum[1], n_planar > 0, n_point > 0, a.inv_sigma2,
-                     a.out + 182 * (size_t)s_task.out_index, tag);
-}
-
-// Small pairs of a batched launch: ONE WARP per pair, eight pairs per CTA.  A few hundred
-// correspondences do not amortise a CTA's two block reductions and its partial-sum round
-// trip; a warp reduces its 28 moments with the butterfly transpose alone (no barrier, no
-// global scratch) and expands the block in its own slice of shared memory.
+// oldest key scan has ~15 k correspondences, most others a few hundred).  One cluster - or
+// one CTA - per pair leaves the launch latency-bound: ncu showed the CTAs waiting at the
+// barriers of their two block reductions (30 % of the stall samples) and on the partial-sum
+// fence, at 16 resident warps per SM.  Here the unit of work is a WARP: the host cuts every
+// pair into slices of about kLinWarpSlice correspondences (estimate; the kernel divides the
+// TRUE range by the slice count), a warp streams its slice with its loads issued four
+// correspondences deep, reduces its 2 x 28 moments with the butterfly transpose alone - no
+// barrier anywhere in the kernel - and, if the pair has several slices, leaves them in
+// global memory and takes a ticket; the LAST warp of the pair adds the partial sums in slice
+// order (a fixed order, so the result does not depend on which warp came last), expands the
+// block in its own slice of shared memory and publishes it.  task.ctx_index selects the
+// context's argument block (segments, pair row, result buffer, sequence tag).
 constexpr int kLinWarpTasks = kLinThreads / 32;
 
 template <bool kErrorOnly>
 __global__ void __launch_bounds__(kLinThreads, 2)
-lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *entries, int n_entries) {
+lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *entries, int n_entries,
+                double *partials, unsigned *tickets) {
   extern __shared__ __align__(16) unsigned char lin_warp_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ei = blockIdx.x * kLinWarpTasks + warp;
@@ -606,13 +459,14 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
   };
   WarpSmem &S = reinterpret_cast<WarpSmem *>(lin_warp_smem)[warp];
   const LinCta me = entries[ei];
+  // task, context block and (for dynamic ranges) the pair row are independent loads
   if (lane < (int)(sizeof(LinTask) / sizeof(unsigned long long)))
     reinterpret_cast<unsigned long long *>(&S.task)[lane] =
         reinterpret_cast<const unsigned long long *>(tasks + me.task)[lane];
   if (lane >= 16 && lane < 16 + (int)(sizeof(LinArgs) / sizeof(unsigned long long)))
     reinterpret_cast<unsigned long long *>(&S.args)[lane - 16] =
         reinterpret_cast<const unsigned long long *>(ctx_args + me.ctx_index)[lane - 16];
-  if (lane < 4 && me.dyn_slot_i_plus1)
+  if (lane < 4 && me.dyn_slot_i_plus1) // ranges written by the association queued just before
     S.dyn[lane] = __ldcg(&me.pair_row[(size_t)lane * me.row_stride + (me.dyn_slot_i_plus1 - 1u)]);
   __syncwarp();
   const LinArgs &a = S.args;
@@ -623,18 +477,21 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
     n_planar = S.dyn[1];
     off_point = S.dyn[2];
     n_point = S.dyn[3];
-    if (n_planar + n_point == 0) return;
+    if (n_planar + n_point == 0) return; // empty pair: all its warps leave, nothing is published
   }
   const double *rel = S.task.rel;
+  const int rank = me.rank, n_slices = me.n_cta;
   double acc[32];
   double err_acc = 0.0;
 #pragma unroll
   for (int k = 0; k < 32; ++k) acc[k] = 0.0;
   {
+    const uint32_t lo = (uint32_t)(((unsigned long long)n_planar * rank) / n_slices);
+    const uint32_t hi = (uint32_t)(((unsigned long long)n_planar * (rank + 1)) / n_slices);
     const float *s = a.seg_planar + (size_t)S.task.slot_j * 9 * a.kp_cap + off_planar;
     const size_t st = a.kp_cap;
 #pragma unroll 4
-    for (uint32_t c = lane; c < n_planar; c += 32) {
+    for (uint32_t c = lo + lane; c < hi; c += 32) {
       const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
       const double nx = s[3 * st + c], ny = s[4 * st + c], nz = s[5 * st + c];
       const double pjx = s[6 * st + c], pjy = s[7 * st + c], pjz = s[8 * st + c];
@@ -660,10 +517,12 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
     for (int k = 0; k < 32; ++k) acc[k] = 0.0;
   }
   if (n_point) {
+    const uint32_t lo = (uint32_t)(((unsigned long long)n_point * rank) / n_slices);
+    const uint32_t hi = (uint32_t)(((unsigned long long)n_point * (rank + 1)) / n_slices);
     const float *s = a.seg_point + (size_t)S.task.slot_j * 6 * a.kq_cap + off_point;
     const size_t st = a.kq_cap;
 #pragma unroll 4
-    for (uint32_t c = lane; c < n_point; c += 32) {
+    for (uint32_t c = lo + lane; c < hi; c += 32) {
       const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
       const double pjx = s[3 * st + c], pjy = s[4 * st + c], pjz = s[5 * st + c];
       double qx, qy, qz;
@@ -683,12 +542,50 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
   }
   const unsigned long long tag = a.seq & 0xffffffffull;
   if (kErrorOnly) {
-    const double w = warp_sum(err_acc);
+    double w = warp_sum(err_acc);
+    if (n_slices > 1) {
+      double *mine = partials + (size_t)(me.first + rank) * 56;
+      unsigned ticket = 0;
+      if (lane == 0) {
+        mine[0] = w;
+        __threadfence();
+        ticket = atomicAdd(&tickets[me.task], 1u);
+      }
+      ticket = __shfl_sync(0xffffffffu, ticket, 0);
+      if (ticket != (unsigned)(n_slices - 1)) return;
+      if (lane == 0) {
+        tickets[me.task] = 0u; // self-cleaning for the next launch
+        __threadfence();
+        const double *all = partials + (size_t)me.first * 56;
+        w = 0.0;
+        for (int r = 0; r < n_slices; ++r) w += __ldcg(&all[(size_t)r * 56]); // slice order
+      }
+    }
     if (lane == 0) publish_tagged(a.out + 2 * (size_t)S.task.out_index, 0.5 * w * a.inv_sigma2, tag);
     return;
   }
   transpose_reduce<16>(acc, lane);
-  if (lane < 28) S.sum[1][lane] = acc[0];
+  if (lane < 28) S.sum[1][lane] = acc[0]; // zeros when the pair has no point rows
+  if (n_slices > 1) {
+    // leave the partial sums, take a ticket; the last warp of the pair finishes it
+    __syncwarp();
+    double *mine = partials + (size_t)(me.first + rank) * 56;
+    for (int e = lane; e < 56; e += 32) mine[e] = S.sum[e / 28][e % 28];
+    __threadfence();
+    __syncwarp();
+    unsigned ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&tickets[me.task], 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket != (unsigned)(n_slices - 1)) return;
+    if (lane == 0) tickets[me.task] = 0u; // self-cleaning for the next launch
+    __threadfence();
+    const double *all = partials + (size_t)me.first * 56;
+    for (int e = lane; e < 56; e += 32) {
+      double v = 0.0;
+      for (int r = 0; r < n_slices; ++r) v += __ldcg(&all[(size_t)r * 56 + e]); // slice order: deterministic
+      S.sum[e / 28][e % 28] = v;
+    }
+  }
   build_basis<true>(S.exp, rel); // starts with a __syncwarp
   __syncwarp();
   expand_and_publish<true>(S.exp, S.sum[0], S.sum[1], n_planar > 0, n_point > 0, a.inv_sigma2,
@@ -744,8 +641,8 @@ cudaError_t linearize_launch(const LinArgs &a, const LinInline *inline_req, bool
 }
 
 cudaError_t linearize_warp_launch(const LinArgs *ctx_args_dev, const LinTask *tasks_dev,
-                                  const LinCta *entries_dev, int n_entries, bool error_only,
-                                  cudaStream_t stream, Profiler &prof) {
+                                  const LinCta *entries_dev, int n_entries, double *partials,
+                                  unsigned *tickets, bool error_only, cudaStream_t stream, Profiler &prof) {
   if (n_entries <= 0) return cudaSuccess;
   static bool configured = false;
   const size_t smem = lin_warp_smem_bytes();
@@ -760,23 +657,11 @@ cudaError_t linearize_warp_launch(const LinArgs *ctx_args_dev, const LinTask *ta
   const int grid = (n_entries + kLinWarpTasks - 1) / kLinWarpTasks;
   prof.begin(group);
   if (error_only)
-    lin_warp_kernel<true><<<grid, kLinThreads, smem, stream>>>(ctx_args_dev, tasks_dev, entries_dev, n_entries);
+    lin_warp_kernel<true><<<grid, kLinThreads, smem, stream>>>(ctx_args_dev, tasks_dev, entries_dev, n_entries,
+                                                               partials, tickets);
   else
-    lin_warp_kernel<false><<<grid, kLinThreads, smem, stream>>>(ctx_args_dev, tasks_dev, entries_dev, n_entries);
-  prof.end(group, 1);
-  return cudaGetLastError();
-}
-
-cudaError_t linearize_sliced_launch(const LinArgs *ctx_args_dev, const LinTask *tasks_dev,
-                                    const LinCta *ctas_dev, int n_ctas, double *partials, unsigned *tickets,
-                                    bool error_only, cudaStream_t stream, Profiler &prof) {
-  if (n_ctas <= 0) return cudaSuccess;
-  const int group = error_only ? FORMGPU_KG_ERR_CHUNK : FORMGPU_KG_LIN_CHUNK;
-  prof.begin(group);
-  if (error_only)
-    lin_sliced_kernel<true><<<n_ctas, kLinThreads, 0, stream>>>(ctx_args_dev, tasks_dev, ctas_dev, partials, tickets);
-  else
-    lin_sliced_kernel<false><<<n_ctas, kLinThreads, 0, stream>>>(ctx_args_dev, tasks_dev, ctas_dev, partials, tickets);
+    lin_warp_kernel<false><<<grid, kLinThreads, smem, stream>>>(ctx_args_dev, tasks_dev, entries_dev, n_entries,
+                                                                partials, tickets);
   prof.end(group, 1);
   return cudaGetLastError();
 }
