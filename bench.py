@@ -143,6 +143,14 @@ def algorithmic_bytes(s: dict, group: str) -> float:
     return 0.0  # map_build / commit: the replay does not count their units
 
 
+# DRAM bytes actually moved per algorithmic byte, from the committed `ncu --set full` capture
+# of the batched kernels (profiles/r01b_ncu_full_metrics.txt: dram__bytes_read.sum +
+# dram__bytes_write.sum of a launch / its algorithmic bytes).  assoc_nn: 58.2 MB for 700 416
+# queries (358.6 MB algorithmic) - hash slots and buckets are shared between queries and hit
+# L2; lin_chunk: 51.9 MB for 49.5 MB of correspondences (sector granularity at slice edges).
+NCU_TRAFFIC_RATIO = {"assoc_nn": 0.162, "lin_chunk": 1.05}
+
+
 def whole_step_bytes(s: dict) -> float:
     """SURVEY 8(d) B_scan with this implementation's record sizes."""
     return (16.0 * s["points"] + 32.0 * s["planar_kp"] + 16.0 * s["point_kp"]
@@ -254,6 +262,10 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     t_value, t_value_host, stats_d, gpu_launches = timed_batched(dev_ptrs, True)
+    if args.only_value:  # development aid (configuration sweeps): not a bench line
+        sampler.stop()
+        return {"sequences_per_gpu": M, "batches_per_gpu": G, "value": round(M * K / t_value, 2),
+                "setup_s": round(t_gen + t_record, 1)} if rank == 0 else None
     # ---- e2e: pinned host scans in, f64 keypoints + blocks out, through the same C-ABI ----
     t_e2e, _, stats_h, _ = timed_batched(host_ptrs, False)
     barrier()
@@ -302,7 +314,12 @@ def run_ours(args, rank, world, local_rank):
                      "share_of_gpu_time": round(ms / total_kernel_ms, 4)}
         roofline = {
             "bound": "hbm", "kernel": dom, "achieved": kg[dom]["achieved_GBps"], "peak": peak,
-            "unit": "GB/s", "frac": kg[dom]["frac"], "traffic": None, "peak_source": peak_src,
+            "unit": "GB/s", "frac": kg[dom]["frac"],
+            "traffic": (round(NCU_TRAFFIC_RATIO[dom] * kg[dom]["algorithmic_MB_per_launch"] * 1e6)
+                        if dom in NCU_TRAFFIC_RATIO else None),
+            "traffic_source": "ncu dram bytes per algorithmic byte of this kernel (profiles/"
+                              "r01b_ncu_full_metrics.txt) x this run's algorithmic bytes per launch",
+            "peak_source": peak_src,
             "algorithmic_bytes_per_launch": round(kg[dom]["algorithmic_MB_per_launch"] * 1e6),
             "avg_launch_us": kg[dom]["avg_launch_us"], "launches": kg[dom]["launches"],
             "kernel_share_of_gpu_time": kg[dom]["share_of_gpu_time"],
@@ -536,6 +553,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sequences-per-gpu", type=int, default=64,
                     help="independent sequences sharing one GPU")
+    ap.add_argument("--only-value", action="store_true", help="development: only the device-resident leg")
     ap.add_argument("--batches-per-gpu", type=int, default=8,
                     help="the sequences of a GPU are split over this many concurrent batches")
     args = ap.parse_args()

@@ -29,6 +29,8 @@ class Context:
         if rc != 0:
             raise FormGpuError(rc, (self._lib.formgpu_last_error(None) or b"").decode())
         self._h = h
+        # cudaStream_t the context's work is ordered on (None: a private stream of its own)
+        self.stream_handle = stream or None
         self.max_planar = self._lib.formgpu_max_planar(h)
         self.max_point = self._lib.formgpu_max_point(h)
         self._planar_buf = np.zeros(self.max_planar, dtype=_capi.PLANAR_FEAT)

@@ -251,6 +251,27 @@ __device__ __forceinline__ int match_bin(const MatchRec &m, double max_d2) {
 // group owns the neighbour voxels with the reference's shift ranks s, s+8, s+16, s+24
 // (map.tpp:54-68); its four home-slot loads are issued together, so the 27 probes are still
 // one memory round trip.  The arg-min key (dist^2, shift rank, scan, k) is rule R5.
+// read-only loads of the map through the non-coherent path (the argument block lives in
+// shared memory in the batched kernel, which hides from the compiler that these are global)
+__device__ __forceinline__ HashSlot load_slot(const HashSlot *p) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+  HashSlot s;
+  s.key = ((unsigned long long)v.y << 32) | v.x;
+  s.start = v.z;
+  s.count = v.w;
+  return s;
+}
+__device__ __forceinline__ WorldPoint load_world(const WorldPoint *p) {
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+  const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  WorldPoint w;
+  w.x = a.x;
+  w.y = a.y;
+  w.z = b.x;
+  w.tie = (unsigned long long)__double_as_longlong(b.y);
+  return w;
+}
+
 // A single sequence's call (20 k queries) cannot fill the GPU either way and is latency-
 // bound, so it keeps 32 lanes per query (shortest bucket scans); batched launches use 8.
 constexpr int kLanesSingle = 32, kLanesBatch = 8;
@@ -292,13 +313,13 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
     }
 #pragma unroll
     for (int r = 0; r < kVox; ++r)
-      if (live[r]) s[r] = a.hash[h[r]];
+      if (live[r]) s[r] = load_slot(a.hash + h[r]);
 #pragma unroll
     for (int r = 0; r < kVox; ++r) {
       if (!live[r]) continue;
       while (s[r].key != key[r] && s[r].key != kEmptyKey) { // linear probing (load <= 0.5)
         h[r] = (h[r] + 1) & a.hash_mask;
-        s[r] = a.hash[h[r]];
+        s[r] = load_slot(a.hash + h[r]);
       }
       if (s[r].key == key[r]) {
         start[r] = s[r].start;
@@ -317,7 +338,7 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
   uint32_t best_pos = kNoSlot;
   auto scan_bucket = [&](int b, uint32_t sb, uint32_t cb) {
     for (uint32_t i = sub; i < cb; i += kQueryLanes) {
-      const WorldPoint p = a.world[sb + i];
+      const WorldPoint p = load_world(a.world + sb + i);
       // 4-lane double squared norm, lane 3 = 0 padding: (d0^2 + d2^2) + (d1^2 + 0)
       const double d0 = p.x - wx, d1 = p.y - wy, d2 = p.z - wz;
       const double dist = (d0 * d0 + d2 * d2) + (d1 * d1 + 0.0);
@@ -340,24 +361,36 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
   for (int off = kQueryLanes / 2; off > 0; off >>= 1)
     bound = fmin(bound, __shfl_xor_sync(0xffffffffu, bound, off));
   // squared distance from the query to the box of each of this lane's voxels, shrunk by a
-  // safety margin that covers the rounding of floor(x / w) at the voxel faces
+  // safety margin that covers the rounding of floor(x / w) at the voxel faces.  All shifts
+  // are -1 / 0 / +1 per axis, so the per-axis terms are the distances to the two faces of
+  // the centre voxel - computed once per query, then three selects per voxel.
   unsigned survivors = 0; // bit v: voxel with shift rank v of this group's query must be scanned
   constexpr unsigned kGroupMask = kQueryLanes == 32 ? 0xffffffffu : ((1u << (kQueryLanes & 31)) - 1u);
+  double face2[3][2]; // [axis][0: towards -1, 1: towards +1], squared, margin applied
+  {
+    const double w = a.voxel_width;
+    const double qq[3] = {wx, wy, wz};
+    const int cc[3] = {cx, cy, cz};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double lo = (double)cc[k] * w, hi = lo + w;
+      const double margin = 1e-9 * (1.0 + fabs(qq[k])) + 4e-16 * fabs(lo);
+      const double dm = fmax(qq[k] - lo - margin, 0.0); // to the lower face (voxels with shift -1)
+      const double dp = fmax(hi - qq[k] - margin, 0.0); // to the upper face (voxels with shift +1)
+      face2[k][0] = dm * dm;
+      face2[k][1] = dp * dp;
+    }
+  }
 #pragma unroll
   for (int r = 0; r < kVox; ++r) {
     const int v = sub + kQueryLanes * r;
     bool keep = false;
     if (v > 0 && v < 27 && count[r] > 0) {
-      const double w = a.voxel_width;
-      const double qq[3] = {wx, wy, wz};
-      const int c[3] = {cx + lane_shift(v, 0), cy + lane_shift(v, 1), cz + lane_shift(v, 2)};
       double lb = 0.0;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const double lo = (double)c[k] * w, hi = lo + w;
-        double d = fmax(fmax(lo - qq[k], qq[k] - hi), 0.0);
-        d = fmax(d - 1e-9 * (1.0 + fabs(qq[k])), 0.0);
-        lb += d * d;
+        const int sh = lane_shift(v, k);
+        lb += sh == 0 ? 0.0 : sh < 0 ? face2[k][0] : face2[k][1];
       }
       keep = lb <= bound;
     }
@@ -419,7 +452,7 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
 __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs qa) {
   assoc_nn_body<kLanesSingle>(blockIdx.y == 0 ? pa : qa);
 }
-__global__ void __launch_bounds__(256) assoc_nn_batch_kernel(const AssocArgs *items) {
+__global__ void __launch_bounds__(256, 5) assoc_nn_batch_kernel(const AssocArgs *items) {
   __shared__ AssocArgs s_a;
   load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
   if ((int)(blockIdx.x * queries_per_cta(kLanesBatch)) >= s_a.n_query) return;

@@ -52,8 +52,9 @@ def allreduce_blocks(blocks: np.ndarray, device=None) -> np.ndarray:
 
 def sharded_linearize(ctx, pairs: np.ndarray, poses: np.ndarray, error_only: bool = False):
     """Point-sharded stage 3 on the CUDA path (SURVEY 8e mode 2).  Every rank holds a replica
-    of the sequence's context (`ctx`, created on torch's current stream and switched to its
-    shard with ctx.set_shard(rank, world)); each linearises its share of every pair into
+    of the sequence's context (`ctx`, created on torch's current NON-default stream -
+    `with torch.cuda.stream(torch.cuda.Stream()): Context(params, stream=...cuda_stream)` - and
+    switched to its shard with ctx.set_shard(rank, world)); each linearises its share of every pair into
     device memory and ONE NCCL all-reduce of 91 * P doubles (errors: P) over NVLink sums the
     blocks - queued on the same stream, so there is no host round trip before the
     collective.  Returns the full blocks (P x 91) / errors (P) on the host."""
@@ -61,11 +62,19 @@ def sharded_linearize(ctx, pairs: np.ndarray, poses: np.ndarray, error_only: boo
     import torch.distributed as dist
 
     n = int(pairs.shape[0])
+    cur = torch.cuda.current_stream()
+    same_stream = ctx.stream_handle is not None and ctx.stream_handle == cur.cuda_stream
     out = torch.empty(n * (1 if error_only else 91), dtype=torch.float64, device="cuda")
+    if not same_stream:
+        cur.synchronize()  # `out` must exist before a foreign stream writes it
     if error_only:
         ctx.error_device(pairs, poses, out.data_ptr())
     else:
         ctx.linearize_device(pairs, poses, out.data_ptr())
+    if not same_stream:
+        # the context runs on its own stream (e.g. it was created on the legacy default stream,
+        # whose handle is NULL = "private stream"): fall back to a host-side join
+        ctx.synchronize()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(out, op=dist.ReduceOp.SUM)
     res = out.cpu().numpy()

@@ -40,8 +40,10 @@ def test_shard_blocks_sum_to_the_full_block_on_one_gpu():
 
     rows, cols = synth.shape("vlp-16")
     params = _capi.default_params(rows, cols)
-    stream = torch.cuda.current_stream().cuda_stream
-    with Context(params, stream=stream) as ctx:
+    # a real (non-default) stream shared by torch and the context: the legacy default stream's
+    # handle is NULL, which formgpu_create reads as "create a private stream"
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side), Context(params, stream=side.cuda_stream) as ctx:
         pairs, poses = _build_world(ctx, "vlp-16", 4)
         full = ctx.linearize(pairs, poses)
         full_err = ctx.error(pairs, poses)
@@ -91,7 +93,8 @@ def _nccl_worker(rank, world, port, out_path):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     rows, cols = synth.shape("vlp-16")
     params = _capi.default_params(rows, cols)
-    with Context(params, device=rank, stream=torch.cuda.current_stream().cuda_stream) as ctx:
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side), Context(params, device=rank, stream=side.cuda_stream) as ctx:
         pairs, poses = _build_world(ctx, "vlp-16", 4)
         full = ctx.linearize(pairs, poses)
         ctx.set_shard(rank, world)
