@@ -230,6 +230,10 @@ FORMHOST_SYMBOLS = {
     "formhost_replay_ctx": (_vp, [_vp]),
     "formhost_replay_run_device": (_d, [_vp, _sz, _sz, _vp]),
     "formhost_replay_run_device_multi": (_d, [_vp, _sz, _sz, _sz, _vp]),
+    "formhost_pool_create": (_vp, [_pest, _sz, _i]),
+    "formhost_pool_destroy": (None, [_vp]),
+    "formhost_pool_stats": (None, [_vp, _vp]),
+    "formhost_pool_est_create": (_vp, [_vp, _pest, _sz]),
     "formhost_batch_replay_create": (_vp, [_vp, _sz, _pest, _vp]),
     "formhost_batch_replay_destroy": (None, [_vp]),
     "formhost_batch_replay_batch": (_vp, [_vp]),

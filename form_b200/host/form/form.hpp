@@ -192,6 +192,11 @@ struct Estimator {
   std::tuple<std::vector<PlanarFeat>, std::vector<PointFeat>>
   register_scan(const PointXYZf *scan, size_t n) noexcept {
     std::tuple<std::vector<PlanarFeat>, std::vector<PointFeat>> keypoints;
+    struct ScanBracket { // tells a pooled hot path that this sequence is inside register_scan
+      HotPath &hp;
+      explicit ScanBracket(HotPath &h) : hp(h) { hp.begin_scan(); }
+      ~ScanBracket() { hp.end_scan(); }
+    } bracket(*m_hotpath);
     try {
       // ---- initialisation (form.cpp:49-50) ----
       const Pose3 prediction = m_constraints.predict_next();

@@ -69,6 +69,12 @@ class HotPath {
 public:
   virtual ~HotPath() = default;
 
+  /// Brackets of one Estimator::register_scan.  A stand-alone context ignores them; the
+  /// pooled implementation (batch_dispatch.hpp) uses them to know which sequences to wait
+  /// for when it forms a batch.
+  virtual void begin_scan() {}
+  virtual void end_scan() {}
+
   /// FeatureExtractor::extract (extraction.hpp:99-101).  Also makes scan_idx the
   /// "current scan" whose keypoints later calls match and commit.
   virtual void extract(const PointXYZf *scan, size_t n, uint64_t scan_idx,

@@ -39,6 +39,8 @@ class RecordingHotPath : public HotPath {
 public:
   RecordingHotPath(HotPath &inner, Trace &trace) : m_inner(inner), m_trace(trace) {}
 
+  void begin_scan() override { m_inner.begin_scan(); }
+  void end_scan() override { m_inner.end_scan(); }
   void extract(const PointXYZf *scan, size_t n, uint64_t scan_idx, std::vector<PlanarFeat> &planar,
                std::vector<PointFeat> &point) override {
     m_trace.scan_begin.push_back(m_trace.ops.size());

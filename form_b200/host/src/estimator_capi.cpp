@@ -1,4 +1,5 @@
 // libformhost.so: form::Estimator and the trace replayer over the CUDA hot path.
+#include "form/batch_dispatch.hpp"
 #include "form/batch_replay.hpp"
 #include "form/capi_impl.hpp"
 
@@ -165,6 +166,42 @@ double formhost_replay_run_device_multi(void *const *replays, size_t n_replays, 
   for (int f : failed)
     if (f) return -1.0;
   return dt;
+}
+
+// ---- pool: many LIVE estimators on one GPU behind a batching dispatcher ----
+
+/// A pool of n sequences sharing one formgpu_batch; formhost_pool_est_create(pool, i) gives
+/// the form::Estimator of sequence i (same handle type as formhost_est_create: use the
+/// formhost_est_* calls on it, each sequence from its own host thread).
+void *formhost_pool_create(const formhost_est_params *p, size_t n_sequences, int linger_us) {
+  try {
+    const Estimator::Params ep = to_estimator_params(*p);
+    const int window = p->hot.max_window_scans > 0 ? p->hot.max_window_scans : 64;
+    auto *pool = new std::shared_ptr<BatchDispatcher>(std::make_shared<BatchDispatcher>(
+        Estimator::hotpath_params(ep), p->device, n_sequences, window,
+        std::chrono::microseconds(linger_us > 0 ? linger_us : 200)));
+    return pool;
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return nullptr;
+  }
+}
+void formhost_pool_destroy(void *pool) { delete static_cast<std::shared_ptr<BatchDispatcher> *>(pool); }
+void formhost_pool_stats(void *pool, uint64_t out[2]) {
+  auto &d = *static_cast<std::shared_ptr<BatchDispatcher> *>(pool);
+  out[0] = d->submits();
+  out[1] = d->requests();
+}
+void *formhost_pool_est_create(void *pool, const formhost_est_params *p, size_t seq) {
+  auto &d = *static_cast<std::shared_ptr<BatchDispatcher> *>(pool);
+  if (seq >= d->size()) {
+    g_error = "formhost_pool_est_create: sequence index outside the pool";
+    return nullptr;
+  }
+  auto make = [&](const HotPathParams &, const formhost_est_params &) -> std::shared_ptr<HotPath> {
+    return std::make_shared<BatchedHotPath>(d, seq);
+  };
+  return est_create(p, make, g_error);
 }
 
 // ---- batched replay: many sequences per launch (formgpu_batch_submit) ----

@@ -275,3 +275,58 @@ def run_batches(batch_replays, first: int, last: int, ptrs_per_batch, on_device:
     if t < 0:
         raise RuntimeError("batched replay failed: " + (_capi.host_lib().formhost_last_error() or b"").decode())
     return t
+
+
+class EstimatorPool:
+    """Many live form::Estimators on one GPU behind a batching dispatcher
+    (form/batch_dispatch.hpp): the hot-path calls of the pool's sequences are funnelled
+    through formgpu_batch_submit, so calls of the same kind share one launch per kernel.
+    Drive each estimator from its own thread (ctypes releases the GIL inside a call)."""
+
+    def __init__(self, params: _capi.EstParams, n_sequences: int, linger_us: int = 200):
+        self._lib = _capi.host_lib()
+        self.params = params
+        self.n = n_sequences
+        self._h = self._lib.formhost_pool_create(C.byref(params), n_sequences, linger_us)
+        if not self._h:
+            raise RuntimeError("formhost_pool_create failed: " + (self._lib.formhost_last_error() or b"").decode())
+        self.estimators = [PooledEstimator(self, i) for i in range(n_sequences)]
+
+    def stats(self) -> dict:
+        out = np.zeros(2, np.uint64)
+        self._lib.formhost_pool_stats(self._h, _capi.ptr(out))
+        return {"submits": int(out[0]), "requests": int(out[1])}
+
+    def close(self):
+        for e in getattr(self, "estimators", []):
+            e.close()
+        self.estimators = []
+        if getattr(self, "_h", None):
+            self._lib.formhost_pool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class PooledEstimator(EstimatorBase):
+    """form::Estimator of one sequence of an EstimatorPool (same calls as Estimator)."""
+
+    def __init__(self, pool: EstimatorPool, seq: int):
+        self.params = pool.params
+        self.rows, self.cols = pool.params.hot.num_rows, pool.params.hot.num_columns
+        self._h = pool._lib.formhost_pool_est_create(pool._h, C.byref(pool.params), seq)
+        if not self._h:
+            raise RuntimeError("formhost_pool_est_create failed: " + self._last_error())
+        cap = self.rows * self.cols
+        self._planar = np.zeros(cap, dtype=_capi.PLANAR_FEAT)
+        self._point = np.zeros(cap, dtype=_capi.POINT_FEAT)

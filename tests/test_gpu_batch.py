@@ -129,3 +129,40 @@ def test_batches_run_concurrently():
     t = run_batches([a, b], 0, n, [ptrs, ptrs[::-1]])
     assert t > 0
     assert a.stats(0) == b.stats(1) and a.stats(1) == b.stats(0)
+
+
+def test_pooled_live_estimators_match_standalone_estimators():
+    """Four LIVE form::Estimators (host smoother in the loop, one thread each) behind the
+    batching dispatcher: identical keypoints and control flow, poses equal to 1e-7, and far
+    fewer submits than requests."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from form_b200.pipeline import Estimator, EstimatorPool
+
+    sensor, n_scans, seqs = "vlp-16", 12, (0, 4, 5, 9)
+    rows, cols = synth.shape(sensor)
+    p = _capi.default_est_params(rows, cols)
+    scans = {s: [synth.scan(sensor, s, k) for k in range(n_scans)] for s in seqs}
+    alone = {}
+    for s in seqs:
+        with Estimator(p) as e:
+            kps = [e.register_scan(sc) for sc in scans[s]]
+            alone[s] = (kps, e.pose(), e.stats(), e.window())
+    with EstimatorPool(p, len(seqs)) as pool:
+        def drive(i):
+            e, s = pool.estimators[i], seqs[i]
+            kps = [e.register_scan(sc) for sc in scans[s]]
+            return kps, e.pose(), e.stats(), e.window()
+
+        with ThreadPoolExecutor(len(seqs)) as ex:
+            pooled = list(ex.map(drive, range(len(seqs))))
+        st = pool.stats()
+    for i, s in enumerate(seqs):
+        kps, pose, stats, window = pooled[i]
+        rk, rpose, rstats, rwindow = alone[s]
+        for (pl, pt), (rpl, rpt) in zip(kps, rk):
+            assert pl.tobytes() == rpl.tobytes() and pt.tobytes() == rpt.tobytes()
+        assert stats == rstats, (stats, rstats)          # same ICP / LM iterations, same calls
+        assert np.array_equal(window["scan"], rwindow["scan"])
+        assert np.max(np.abs(pose["t"] - rpose["t"])) < 1e-7 and np.max(np.abs(pose["R"] - rpose["R"])) < 1e-7
+    assert st["requests"] > st["submits"] > 0            # calls of different sequences shared submits
