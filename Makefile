@@ -19,7 +19,15 @@ HOST_OBJS := $(HOST_SRCS:form_b200/host/src/%.cpp=$(OBJDIR)/host_%.o)
 CSRC_HDRS := $(wildcard form_b200/csrc/*.hpp) include/formgpu.h
 HOST_HDRS := $(wildcard form_b200/host/form/*.hpp) include/formgpu.h
 
-all: $(LIBDIR)/libformgpu.so $(LIBDIR)/libformhost.so oracle
+PYTHON    ?= python3
+PYEXT     := python/form/_core$(shell $(PYTHON) -c "import sysconfig; print(sysconfig.get_config_var('EXT_SUFFIX'))")
+
+all: $(LIBDIR)/libformgpu.so $(LIBDIR)/libformhost.so $(PYEXT) oracle
+
+# form._core: the reference's Python surface (python/bindings.cpp) with pybind11
+$(PYEXT): python/bindings.cpp $(HOST_HDRS) $(LIBDIR)/libformgpu.so
+	$(CXX) -O2 -std=c++17 -fPIC -shared -pthread -ffp-contract=off -fvisibility=hidden -Iinclude -Iform_b200/host \
+	    $(shell $(PYTHON) -m pybind11 --includes) $< -o $@ -L$(LIBDIR) -lformgpu -Wl,-rpath,'$$ORIGIN/../../form_b200/lib'
 
 $(OBJDIR)/extract.o: form_b200/csrc/extract.cu $(CSRC_HDRS)
 	@mkdir -p $(OBJDIR)
@@ -51,6 +59,6 @@ oracle: $(LIBDIR)/libformgpu.so
 	$(MAKE) -s -C oracle/ref
 
 clean:
-	rm -rf build $(LIBDIR)/*.so oracle/_build oracle/_ref
+	rm -rf build $(LIBDIR)/*.so oracle/_build oracle/_ref python/form/_core*.so
 
 .PHONY: all oracle clean
