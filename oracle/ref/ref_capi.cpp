@@ -1,8 +1,8 @@
-// TEST INFRASTRUCTURE.  C entry points over FORM's own stage-1 / stage-2 translation units,
-// compiled UNMODIFIED from /root/reference (form/feature/extraction.{hpp,tpp},
-// form/feature/features.hpp, form/utils.hpp, form/mapping/map.{hpp,tpp},
-// form/optimization/matcher.hpp) against the API stand-ins in oracle/shim/ (Eigen, GTSAM,
-// oneTBB and tsl::robin_map are not in this image).  The result, oracle/_ref/libformref.so,
+// TEST INFRASTRUCTURE.  C entry points over FORM's own hot-path translation units, compiled
+// UNMODIFIED from /root/reference (form/feature/extraction.{hpp,tpp}, features.hpp,
+// form/utils.hpp, form/mapping/map.{hpp,tpp}, form/optimization/matcher.hpp,
+// form/feature/factor.{hpp,cpp}, form/optimization/gtsam.hpp) against the API stand-ins in
+// oracle/shim/ (Eigen, GTSAM, oneTBB and tsl::robin_map are not in this image).  The result, oracle/_ref/libformref.so,
 // is used by tests/test_reference_pins.py to pin the oracle restatement (and through it
 // the CUDA path) to the reference's real control flow.  It is never linked or loaded by
 // the product.  The structs exchanged are the C-ABI PODs of include/formgpu.h, which are
@@ -155,8 +155,32 @@ void formref_world_constraint_counts(void *wv, uint64_t scan, size_t *n_planar, 
   *n_planar = *n_point = 0;
   auto it = w.constraints.find((size_t)scan);
   if (it == w.constraints.end()) return;
-  *n_planar = std::get<0>(it.value())->map_points.size();
-  *n_point = std::get<1>(it.value())->map_points.size();
+  *n_planar = std::get<0>(it.value())->num_constraints();
+  *n_point = std::get<1>(it.value())->num_constraints();
+}
+
+/// DenseFactor::linearize of FeatureFactor(X(scan_i), X(cur_scan)) over the correspondences
+/// the last association appended for map scan `scan_i` (form/optimization/gtsam.hpp:67-86,
+/// form/feature/factor.cpp:131-186, constraints.cpp:259-265): the packed upper triangle of
+/// the 13x13 augmented information matrix.  Returns 1 when the pair has no correspondences.
+int formref_world_linearize(void *wv, uint64_t scan_i, uint64_t cur_scan, const formgpu_pose *Ti,
+                            const formgpu_pose *Tj, double sigma, double *out91) {
+  World &w = *static_cast<World *>(wv);
+  auto it = w.constraints.find((size_t)scan_i);
+  if (it == w.constraints.end()) return 1;
+  const auto &c = it.value();
+  if (std::get<0>(c)->num_constraints() + std::get<1>(c)->num_constraints() == 0) return 1;
+  form::FeatureFactor factor(X(scan_i), X(cur_scan), c, sigma);
+  gtsam::Values values;
+  values.insert(X(scan_i), to_pose(*Ti));
+  values.insert(X(cur_scan), to_pose(*Tj));
+  const auto gf = factor.linearize(values);
+  const auto *hf = dynamic_cast<const gtsam::HessianFactor *>(gf.get());
+  if (!hf || hf->info.rows() != 13) return 2;
+  size_t e = 0;
+  for (int r = 0; r < 13; ++r)
+    for (int col = r; col < 13; ++col) out91[e++] = hf->info(r, col);
+  return 0;
 }
 
 /// KeypointMap::insert_matches for both types (form/form.cpp:99-101).
@@ -185,6 +209,71 @@ size_t formref_world_keypoints(void *wv, int type, uint64_t scan, void *out, siz
   const auto &v = w.point_map.get((size_t)scan);
   if (out && v.size() <= cap && !v.empty()) std::memcpy(out, v.data(), v.size() * sizeof(form::PointFeat));
   return v.size();
+}
+
+} // extern "C"
+
+namespace {
+void copy_rows(const Eigen::MatrixXd &H, double *out) { // rows x 6, row-major out
+  for (size_t r = 0; r < H.rows(); ++r)
+    for (size_t c = 0; c < 6; ++c) out[6 * r + c] = H(r, c);
+}
+} // namespace
+
+extern "C" {
+
+/// PlanePoint::evaluateError (form/feature/factor.cpp:30-80) on n correspondences given as
+/// n x 3 row-major arrays: residual[n], H1 / H2 [n][6].
+void formref_plane_point(const double *p_i, const double *n_i, const double *p_j, size_t n,
+                         const formgpu_pose *Ti, const formgpu_pose *Tj, double *residual, double *H1,
+                         double *H2) {
+  form::PlanePoint pp;
+  pp.p_i.assign(p_i, p_i + 3 * n);
+  pp.n_i.assign(n_i, n_i + 3 * n);
+  pp.p_j.assign(p_j, p_j + 3 * n);
+  Eigen::MatrixXd A, B;
+  const gtsam::Vector r = pp.evaluateError(to_pose(*Ti), to_pose(*Tj), &A, &B);
+  for (size_t k = 0; k < n; ++k) residual[k] = r(k);
+  copy_rows(A, H1);
+  copy_rows(B, H2);
+}
+
+/// PointPoint::evaluateError (factor.cpp:82-128): residual[3m], H1 / H2 [3m][6].
+void formref_point_point(const double *p_i, const double *p_j, size_t m, const formgpu_pose *Ti,
+                         const formgpu_pose *Tj, double *residual, double *H1, double *H2) {
+  form::PointPoint pp;
+  pp.p_i.assign(p_i, p_i + 3 * m);
+  pp.p_j.assign(p_j, p_j + 3 * m);
+  Eigen::MatrixXd A, B;
+  const gtsam::Vector r = pp.evaluateError(to_pose(*Ti), to_pose(*Tj), &A, &B);
+  for (size_t k = 0; k < 3 * m; ++k) residual[k] = r(k);
+  copy_rows(A, H1);
+  copy_rows(B, H2);
+}
+
+/// FeatureFactor + DenseFactor::linearize (factor.cpp:131-186, gtsam.hpp:67-86) on raw
+/// correspondences: the packed upper triangle of the 13x13 augmented information matrix.
+int formref_linearize_raw(const double *p_i, const double *n_i, const double *p_j, size_t n,
+                          const double *q_i, const double *q_j, size_t m, const formgpu_pose *Ti,
+                          const formgpu_pose *Tj, double sigma, double *out91) {
+  auto planar = std::make_shared<form::PlanePoint>();
+  planar->p_i.assign(p_i, p_i + 3 * n);
+  planar->n_i.assign(n_i, n_i + 3 * n);
+  planar->p_j.assign(p_j, p_j + 3 * n);
+  auto point = std::make_shared<form::PointPoint>();
+  point->p_i.assign(q_i, q_i + 3 * m);
+  point->p_j.assign(q_j, q_j + 3 * m);
+  form::FeatureFactor factor(X(0), X(1), std::make_tuple(planar, point), sigma);
+  gtsam::Values values;
+  values.insert(X(0), to_pose(*Ti));
+  values.insert(X(1), to_pose(*Tj));
+  const auto gf = factor.linearize(values);
+  const auto *hf = dynamic_cast<const gtsam::HessianFactor *>(gf.get());
+  if (!hf || hf->info.rows() != 13) return 2;
+  size_t e = 0;
+  for (int r = 0; r < 13; ++r)
+    for (int col = r; col < 13; ++col) out91[e++] = hf->info(r, col);
+  return 0;
 }
 
 } // extern "C"

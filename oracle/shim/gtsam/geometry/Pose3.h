@@ -1,7 +1,7 @@
-// TEST INFRASTRUCTURE - not GTSAM.  gtsam::Pose3 / Rot3 as far as FORM's stage-1/2 sources
-// use them (transform of a point, rotation of a normal, inverse).  Arithmetic [external]:
-// T * p = R p + t with row-wise dot products ((r0 x + r1 y) + r2 z) + t;
-// inverse = (R^T, -(R^T t)) with the same dot-product order.
+// TEST INFRASTRUCTURE - not GTSAM.  gtsam::Pose3 / Rot3 as far as FORM's sources use them
+// (transform of a point, rotation of a normal, inverse, rotation().matrix() / transpose(),
+// translation()).  Arithmetic [external]: T * p = R p + t with row-wise dot products
+// ((r0 x + r1 y) + r2 z) + t; inverse = (R^T, -(R^T t)), same order.
 #pragma once
 
 #include <Eigen/Dense>
@@ -11,6 +11,8 @@ namespace gtsam {
 using Vector3 = Eigen::Vector3d;
 using Point3 = Eigen::Vector3d;
 using Key = unsigned long long;
+using Vector = Eigen::VectorXd;
+using Matrix = Eigen::MatrixXd;
 
 class Rot3 {
 public:
@@ -19,6 +21,13 @@ public:
     for (int i = 0; i < 9; ++i) m_r[i] = r[i];
   }
   const double *data() const { return m_r; } // row-major
+  Eigen::Matrix3d matrix() const {
+    Eigen::Matrix3d m;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) m(r, c) = m_r[3 * r + c];
+    return m;
+  }
+  Eigen::Matrix3d transpose() const { return matrix().transpose(); }
   template <typename V> Eigen::Vector3d operator*(const V &v) const {
     const double x = v(0), y = v(1), z = v(2);
     return Eigen::Vector3d((m_r[0] * x + m_r[1] * y) + m_r[2] * z, (m_r[3] * x + m_r[4] * y) + m_r[5] * z,

@@ -1,6 +1,6 @@
-"""CUDA path vs the REFERENCE'S OWN CODE (oracle/_ref/libformref.so: FORM's stage-1/2
+"""CUDA path vs the REFERENCE'S OWN CODE (oracle/_ref/libformref.so: FORM's hot-path
 sources compiled unmodified against API stand-ins, see tests/test_reference_pins.py),
-through the C-ABI, bit for bit.  The library is prebuilt where /root/reference exists and
+through the C-ABI: stages 1-2 bit for bit, stage-3 blocks to 1e-9 (tolerance 1e-5).  The library is prebuilt where /root/reference exists and
 travels to the GPU box with the snapshot."""
 import ctypes as C
 
@@ -9,7 +9,7 @@ import pytest
 
 from form_b200 import _capi, synth
 from form_b200.context import Context
-from helpers import perturbed, scan_poses
+from helpers import block_rel_err, perturbed, scan_poses
 import test_reference_pins as refpins
 
 pytestmark = pytest.mark.gpu
@@ -45,7 +45,9 @@ def test_cuda_extraction_matches_reference_on_random_scans_and_variants():
 
 def test_cuda_association_and_commit_match_reference_code():
     """Matcher::match + insert_matches of the reference vs formgpu_associate / _commit_scan:
-    matched scan, dist^2 bit pattern, per-pair counts, stored novel keypoints."""
+    matched scan, dist^2 bit pattern, per-pair counts, stored novel keypoints; and the
+    reference's DenseFactor::linearize over ITS correspondences vs formgpu_linearize."""
+    worst, checked = 0.0, 0
     rng = np.random.default_rng(29)
     sensor, n_scans = "vlp-16", 5
     rows, cols = synth.shape(sensor)
@@ -74,6 +76,20 @@ def test_cuda_association_and_commit_match_reference_code():
                     a, b = C.c_size_t(), C.c_size_t()
                     refpins.ref().formref_world_constraint_counts(world, s, C.byref(a), C.byref(b))
                     assert (a.value, b.value) == by_scan.get(s, (0, 0)), (k, s)
+                if len(counts):
+                    pairs = np.zeros(len(counts), dtype=_capi.PAIR)
+                    pairs["i"] = counts["i"]
+                    pairs["j"] = k
+                    H = ctx.linearize(pairs, sp)
+                    for c, h in zip(counts, H):
+                        got = np.zeros(91)
+                        Ti = np.array([poses[int(c["i"])]], dtype=_capi.POSE)
+                        Tj = np.array([poses[k]], dtype=_capi.POSE)
+                        rc = refpins.ref().formref_world_linearize(world, int(c["i"]), k, _capi.ptr(Ti), _capi.ptr(Tj),
+                                                                   params.sigma, _capi.ptr(got))
+                        assert rc == 0
+                        worst = max(worst, block_rel_err(h, got))
+                        checked += 1
                 ctx.commit_scan()
                 refpins.ref().formref_world_commit(world)
                 for t in (0, 1):
@@ -83,3 +99,4 @@ def test_cuda_association_and_commit_match_reference_code():
                     assert n == len(stored) and buf[:n].tobytes() == stored.tobytes()
     finally:
         refpins.ref().formref_world_destroy(world)
+    assert checked >= 4 and worst < 1e-9, (checked, worst)  # north-star tolerance: 1e-5

@@ -1,14 +1,19 @@
-"""Pins the oracle to the REFERENCE'S OWN CODE for the index-determining stages.
+"""Pins the oracle to the REFERENCE'S OWN CODE, all three stages of the hot path.
 
 oracle/_ref/libformref.so is FORM's form/feature/extraction.tpp, features.hpp, utils.hpp,
-form/mapping/map.tpp and form/optimization/matcher.hpp compiled UNMODIFIED from
-/root/reference (oracle/ref/Makefile) against API stand-ins for the libraries this image
-lacks (oracle/shim: Eigen, GTSAM Pose3/Values, oneTBB, tsl::robin_map).  Every decision
+form/mapping/map.tpp, form/optimization/matcher.hpp, form/feature/factor.{hpp,cpp} and
+form/optimization/gtsam.hpp compiled UNMODIFIED from /root/reference (oracle/ref/Makefile)
+against API stand-ins for the libraries this image lacks (oracle/shim: Eigen, GTSAM
+Pose3/Values/noise-model/factor base classes, oneTBB, tsl::robin_map).  Every decision
 FORM's own code takes - masks, dilation, thresholds, std::sort + greedy planar selection,
 the extract_point stride/break quirks, neighbour gathering, the dropped-normal rule, voxel
 keys, the strict-< bucket scans, the max_dist / min_dist_map gates, the world->local round
 trip - is therefore exercised as the reference wrote it, and must agree with the oracle
-restatement BIT FOR BIT (keypoints, match distances, pair counts, novel sets).
+restatement BIT FOR BIT (keypoints, match distances, pair counts, novel sets).  Stage 3 runs
+the reference's PlanePoint / PointPoint::evaluateError, FeatureFactor::evaluateError,
+FastIsotropic whitening and DenseFactor::linearize; residuals, Jacobians and the 13x13
+augmented information blocks must agree with the restatement to 1e-12 (tolerance class:
+the restatement reduces 7x7 moments instead of forming A^T A, so the bits differ).
 
 Only Eigen's/GTSAM's internal arithmetic order is still a stated rule, shared
 by shim and oracle.  The library is prebuilt in this container (the reference tree does
@@ -22,7 +27,7 @@ import pytest
 
 import oracle_lib
 from form_b200 import _capi, synth
-from helpers import perturbed, scan_poses
+from helpers import block_rel_err, perturbed, scan_poses
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libformref.so")
@@ -39,6 +44,10 @@ _SYMS = {
     "formref_world_commit": (None, [_vp]),
     "formref_world_remove": (None, [_vp, _u64]),
     "formref_world_keypoints": (_sz, [_vp, _i, _u64, _vp, _sz]),
+    "formref_world_linearize": (_i, [_vp, _u64, _u64, _vp, _vp, _d, _vp]),
+    "formref_plane_point": (None, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "formref_point_point": (None, [_vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "formref_linearize_raw": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _d, _vp]),
 }
 _ref = None
 
@@ -235,3 +244,106 @@ def test_association_commit_and_removal_match_reference(sensor, n_scans):
         assert sum(len(o.keypoints(0, k)) for k in poses) > 0
     finally:
         ref().formref_world_destroy(world)
+
+
+# ------------------------------------------------------------------ stage 3
+def _random_pose(rng, rot=0.6, trans=3.0):
+    ident = np.zeros((), dtype=_capi.POSE)
+    ident["R"] = np.eye(3).reshape(9)
+    return perturbed(ident, rng, rot, trans)
+
+
+def _random_correspondences(rng, n, m):
+    p_i, p_j = rng.normal(size=(n, 3)) * 6, rng.normal(size=(n, 3)) * 6
+    n_i = rng.normal(size=(n, 3))
+    n_i /= np.linalg.norm(n_i, axis=1, keepdims=True)
+    q_i, q_j = rng.normal(size=(m, 3)) * 6, rng.normal(size=(m, 3)) * 6
+    return p_i, n_i, p_j, q_i, q_j
+
+
+@pytest.mark.parametrize("n", [1, 7, 300])
+def test_plane_point_and_point_point_match_reference(n):
+    """PlanePoint / PointPoint::evaluateError (factor.cpp:30-128): residuals and both Jacobians."""
+    rng = np.random.default_rng(100 + n)
+    p_i, n_i, p_j, q_i, q_j = _random_correspondences(rng, n, n)
+    Ti, Tj = _random_pose(rng), _random_pose(rng)
+    a, b = np.array([Ti], dtype=_capi.POSE), np.array([Tj], dtype=_capi.POSE)
+    r, H1, H2 = np.zeros(n), np.zeros((n, 6)), np.zeros((n, 6))
+    ref().formref_plane_point(_capi.ptr(p_i), _capi.ptr(n_i), _capi.ptr(p_j), n, _capi.ptr(a), _capi.ptr(b),
+                              _capi.ptr(r), _capi.ptr(H1), _capi.ptr(H2))
+    o_r, o_H1, o_H2 = np.zeros(n), np.zeros((n, 6)), np.zeros((n, 6))
+    oracle_lib.lib().oracle_plane_point(_capi.ptr(p_i), _capi.ptr(n_i), _capi.ptr(p_j), n, _capi.ptr(a),
+                                        _capi.ptr(b), _capi.ptr(o_r), _capi.ptr(o_H1), _capi.ptr(o_H2))
+    scale = 1.0 + np.abs(H1).max()
+    assert np.abs(r - o_r).max() < 1e-12 * scale
+    assert np.abs(H1 - o_H1).max() < 1e-12 * scale and np.abs(H2 - o_H2).max() < 1e-12 * scale
+    assert np.abs(H1).max() > 0.1
+    r, H1, H2 = np.zeros(3 * n), np.zeros((3 * n, 6)), np.zeros((3 * n, 6))
+    ref().formref_point_point(_capi.ptr(q_i), _capi.ptr(q_j), n, _capi.ptr(a), _capi.ptr(b), _capi.ptr(r),
+                              _capi.ptr(H1), _capi.ptr(H2))
+    o_r, o_H1, o_H2 = np.zeros(3 * n), np.zeros((3 * n, 6)), np.zeros((3 * n, 6))
+    oracle_lib.lib().oracle_point_point(_capi.ptr(q_i), _capi.ptr(q_j), n, _capi.ptr(a), _capi.ptr(b),
+                                        _capi.ptr(o_r), _capi.ptr(o_H1), _capi.ptr(o_H2))
+    scale = 1.0 + np.abs(H1).max()
+    assert np.abs(r - o_r).max() < 1e-12 * scale
+    assert np.abs(H1 - o_H1).max() < 1e-12 * scale and np.abs(H2 - o_H2).max() < 1e-12 * scale
+
+
+@pytest.mark.parametrize("n,m", [(1, 0), (0, 1), (40, 9), (1001, 333)])
+def test_dense_factor_linearize_matches_reference(n, m):
+    """FeatureFactor + FastIsotropic + DenseFactor::linearize (factor.cpp:131-186,
+    gtsam.hpp:67-140) vs the restatement's 91-double block."""
+    rng = np.random.default_rng(7 * n + m)
+    p_i, n_i, p_j, q_i, q_j = _random_correspondences(rng, n, m)
+    Ti, Tj = _random_pose(rng), _random_pose(rng)
+    a, b = np.array([Ti], dtype=_capi.POSE), np.array([Tj], dtype=_capi.POSE)
+    got, want = np.zeros(91), np.zeros(91)
+    rc = ref().formref_linearize_raw(_capi.ptr(p_i), _capi.ptr(n_i), _capi.ptr(p_j), n, _capi.ptr(q_i),
+                                     _capi.ptr(q_j), m, _capi.ptr(a), _capi.ptr(b), 0.1, _capi.ptr(got))
+    assert rc == 0
+    oracle_lib.lib().oracle_linearize_raw(_capi.ptr(p_i), _capi.ptr(n_i), _capi.ptr(p_j), n, _capi.ptr(q_i),
+                                          _capi.ptr(q_j), m, _capi.ptr(a), _capi.ptr(b), 0.1, _capi.ptr(want), None)
+    assert np.abs(got).sum() > 0
+    assert block_rel_err(got, want) < 1e-12
+
+
+def test_whole_path_blocks_match_reference():
+    """Stages 1 -> 2 -> 3 end to end: the reference's own matcher builds the correspondences
+    of every pair (incl. its world->local round trip of the map point) and its own
+    DenseFactor::linearize forms the block; the restatement must agree to 1e-9."""
+    rng = np.random.default_rng(31)
+    sensor, n_scans = "vlp-16", 4
+    rows, cols = synth.shape(sensor)
+    params = _capi.default_params(rows, cols)
+    o = oracle_lib.Oracle(params, threads=2)
+    world = ref().formref_world_create(C.byref(params))
+    checked = 0
+    try:
+        poses = {}
+        for k in range(n_scans):
+            pl, pt = o.extract(synth.scan(sensor, 0, k), k)
+            gt = synth.gt_pose(0, k)
+            poses[k] = gt if k == 0 else perturbed(gt, rng, 0.002, 0.02)
+            sp = scan_poses(list(poses), [poses[s] for s in poses])
+            o.map_rebuild(sp)
+            counts = o.associate(poses[k])
+            _ref_associate(world, sp, k, pl, pt)
+            if len(counts):
+                pairs = np.zeros(len(counts), dtype=_capi.PAIR)
+                pairs["i"] = counts["i"]
+                pairs["j"] = k
+                H = o.linearize(pairs, sp)
+                for c, h in zip(counts, H):
+                    got = np.zeros(91)
+                    a = np.array([poses[int(c["i"])]], dtype=_capi.POSE)
+                    b = np.array([poses[k]], dtype=_capi.POSE)
+                    rc = ref().formref_world_linearize(world, int(c["i"]), k, _capi.ptr(a), _capi.ptr(b), params.sigma,
+                                                       _capi.ptr(got))
+                    assert rc == 0
+                    assert block_rel_err(got, h) < 1e-9, (k, int(c["i"]))
+                    checked += 1
+            o.commit_scan()
+            ref().formref_world_commit(world)
+    finally:
+        ref().formref_world_destroy(world)
+    assert checked >= 3
