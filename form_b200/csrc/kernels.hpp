@@ -209,7 +209,7 @@ struct LinArgs {
 cudaError_t linearize_launch(const LinArgs &a, const LinInline *inline_req, bool error_only,
                              cudaStream_t stream, Profiler &prof);
 /// Batched launches: correspondences per warp slice the host aims for, and the slice table.
-constexpr uint32_t kLinWarpSlice = 512;
+constexpr uint32_t kLinWarpSlice = 384;
 struct LinCta { // one warp-sized slice of a pair in a batched linearisation launch (32 B)
   uint32_t task;  // index into the task array
   uint32_t first; // index of the task's first slice (= base of its partial sums)

@@ -440,24 +440,57 @@ __global__ void __launch_bounds__(kLinThreads) lin_global_kernel(LinArgs a) {
 // order (a fixed order, so the result does not depend on which warp came last), expands the
 // block in its own slice of shared memory and publishes it.  task.ctx_index selects the
 // context's argument block (segments, pair row, result buffer, sequence tag).
-constexpr int kLinWarpTasks = kLinThreads / 32;
+constexpr int kLinWarpThreads = 128;              // 4 warps per CTA: three CTAs per SM by shared memory
+constexpr int kLinWarpTasks = kLinWarpThreads / 32;
+constexpr int kLinStage = 256;                    // correspondences staged per asynchronous batch
+
+// Shared memory of one warp.  The staging planes and the expansion scratch are never live at
+// the same time (a warp expands only after its last correspondence), so they share storage.
+struct LinWarpSmem {
+  union {
+    struct {
+      float planar[9][kLinStage]; // p_i, n_i, p_j planes of the staged planar correspondences
+      float point[6][kLinStage];  // p_i, p_j planes of the staged point correspondences
+    } stage;
+    ExpandSmem exp;
+  };
+  LinTask task;
+  LinArgs args;
+  double sum[2][28];
+  uint32_t dyn[4];
+};
+
+// 4-byte asynchronous global -> shared copies (LDGSTS): the whole batch of a warp is in
+// flight at once without holding registers.  Measured (profiles/r01b_lin_warp_launches.txt):
+// this did NOT move the kernel - launches below one wave cost a flat ~24 us (the serial
+// chain entry -> task -> batch -> reduce -> ticket -> merge -> expand -> publish of a warp),
+// and the large window-wide launches sit at 1.4 TB/s with 45 % of the issue slots busy, four
+// fifths of them address / copy / convert / expansion instructions rather than fp64 math.
+__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gmem_src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+template <int kPlanes>
+__device__ __forceinline__ void stage_planes(float (*dst)[kLinStage], const float *src, size_t plane_stride,
+                                             uint32_t begin, uint32_t count, int lane) {
+#pragma unroll
+  for (int pl = 0; pl < kPlanes; ++pl)
+    for (uint32_t i = lane; i < count; i += 32) cp_async4(&dst[pl][i], src + pl * plane_stride + begin + i);
+}
 
 template <bool kErrorOnly>
-__global__ void __launch_bounds__(kLinThreads, 2)
+__global__ void __launch_bounds__(kLinWarpThreads, 3)
 lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *entries, int n_entries,
                 double *partials, unsigned *tickets) {
   extern __shared__ __align__(16) unsigned char lin_warp_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ei = blockIdx.x * kLinWarpTasks + warp;
   if (ei >= n_entries) return;
-  struct WarpSmem {
-    ExpandSmem exp;
-    LinTask task;
-    LinArgs args;
-    double sum[2][28];
-    uint32_t dyn[4];
-  };
-  WarpSmem &S = reinterpret_cast<WarpSmem *>(lin_warp_smem)[warp];
+  LinWarpSmem &S = reinterpret_cast<LinWarpSmem *>(lin_warp_smem)[warp];
   const LinCta me = entries[ei];
   // task, context block and (for dynamic ranges) the pair row are independent loads
   if (lane < (int)(sizeof(LinTask) / sizeof(unsigned long long)))
@@ -479,22 +512,40 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
     n_point = S.dyn[3];
     if (n_planar + n_point == 0) return; // empty pair: all its warps leave, nothing is published
   }
-  const double *rel = S.task.rel;
+  const double *rel = S.task.rel; // outside the staging union
   const int rank = me.rank, n_slices = me.n_cta;
+  // this warp's slice of the planar and of the point range
+  const uint32_t p_lo = (uint32_t)(((unsigned long long)n_planar * rank) / n_slices);
+  const uint32_t p_hi = (uint32_t)(((unsigned long long)n_planar * (rank + 1)) / n_slices);
+  const uint32_t q_lo = (uint32_t)(((unsigned long long)n_point * rank) / n_slices);
+  const uint32_t q_hi = (uint32_t)(((unsigned long long)n_point * (rank + 1)) / n_slices);
+  const float *gp = a.seg_planar + (size_t)S.task.slot_j * 9 * a.kp_cap + off_planar;
+  const float *gq = a.seg_point + (size_t)S.task.slot_j * 6 * a.kq_cap + off_point;
+  const size_t stp = a.kp_cap, stq = a.kq_cap;
+  const double inv_sigma2 = a.inv_sigma2;
+  const unsigned long long tag = a.seq & 0xffffffffull;
+  volatile unsigned long long *out = a.out;
+  const int out_index = S.task.out_index;
+
   double acc[32];
   double err_acc = 0.0;
 #pragma unroll
   for (int k = 0; k < 32; ++k) acc[k] = 0.0;
-  {
-    const uint32_t lo = (uint32_t)(((unsigned long long)n_planar * rank) / n_slices);
-    const uint32_t hi = (uint32_t)(((unsigned long long)n_planar * (rank + 1)) / n_slices);
-    const float *s = a.seg_planar + (size_t)S.task.slot_j * 9 * a.kp_cap + off_planar;
-    const size_t st = a.kp_cap;
-#pragma unroll 4
-    for (uint32_t c = lo + lane; c < hi; c += 32) {
-      const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
-      const double nx = s[3 * st + c], ny = s[4 * st + c], nz = s[5 * st + c];
-      const double pjx = s[6 * st + c], pjy = s[7 * st + c], pjz = s[8 * st + c];
+  // Batches of up to kLinStage correspondences: all copies of a batch are issued, then
+  // awaited, then reduced from shared memory.  The first point batch is issued together with
+  // the first planar one, so a typical slice (<= kLinStage of each) has everything in flight
+  // at once.
+  const uint32_t q_first = min((uint32_t)kLinStage, q_hi - q_lo);
+  stage_planes<6>(S.stage.point, gq, stq, q_lo, q_first, lane);
+  for (uint32_t pb = p_lo; pb < p_hi || pb == p_lo; pb += kLinStage) {
+    const uint32_t pn = pb < p_hi ? min((uint32_t)kLinStage, p_hi - pb) : 0u;
+    stage_planes<9>(S.stage.planar, gp, stp, pb, pn, lane);
+    cp_async_wait_all();
+    __syncwarp();
+    for (uint32_t i = lane; i < pn; i += 32) {
+      const double pix = S.stage.planar[0][i], piy = S.stage.planar[1][i], piz = S.stage.planar[2][i];
+      const double nx = S.stage.planar[3][i], ny = S.stage.planar[4][i], nz = S.stage.planar[5][i];
+      const double pjx = S.stage.planar[6][i], pjy = S.stage.planar[7][i], pjz = S.stage.planar[8][i];
       double qx, qy, qz;
       apply_rel(rel, pjx, pjy, pjz, qx, qy, qz);
       const double r = nx * (qx - pix) + ny * (qy - piy) + nz * (qz - piz);
@@ -509,6 +560,8 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
           for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
       }
     }
+    __syncwarp(); // the planar planes are overwritten by the next batch
+    if (pb + kLinStage >= p_hi) break;
   }
   if (!kErrorOnly) {
     transpose_reduce<16>(acc, lane);
@@ -516,15 +569,16 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc[k] = 0.0;
   }
-  if (n_point) {
-    const uint32_t lo = (uint32_t)(((unsigned long long)n_point * rank) / n_slices);
-    const uint32_t hi = (uint32_t)(((unsigned long long)n_point * (rank + 1)) / n_slices);
-    const float *s = a.seg_point + (size_t)S.task.slot_j * 6 * a.kq_cap + off_point;
-    const size_t st = a.kq_cap;
-#pragma unroll 4
-    for (uint32_t c = lo + lane; c < hi; c += 32) {
-      const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
-      const double pjx = s[3 * st + c], pjy = s[4 * st + c], pjz = s[5 * st + c];
+  for (uint32_t qb = q_lo; qb < q_hi; qb += kLinStage) {
+    const uint32_t qn = min((uint32_t)kLinStage, q_hi - qb);
+    if (qb != q_lo) { // the first batch arrived with the planar one
+      stage_planes<6>(S.stage.point, gq, stq, qb, qn, lane);
+      cp_async_wait_all();
+      __syncwarp();
+    }
+    for (uint32_t i = lane; i < qn; i += 32) {
+      const double pix = S.stage.point[0][i], piy = S.stage.point[1][i], piz = S.stage.point[2][i];
+      const double pjx = S.stage.point[3][i], pjy = S.stage.point[4][i], pjz = S.stage.point[5][i];
       double qx, qy, qz;
       apply_rel(rel, pjx, pjy, pjz, qx, qy, qz);
       const double ex = qx - pix, ey = qy - piy, ez = qz - piz;
@@ -539,8 +593,8 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
           for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
       }
     }
+    __syncwarp();
   }
-  const unsigned long long tag = a.seq & 0xffffffffull;
   if (kErrorOnly) {
     double w = warp_sum(err_acc);
     if (n_slices > 1) {
@@ -561,11 +615,11 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
         for (int r = 0; r < n_slices; ++r) w += __ldcg(&all[(size_t)r * 56]); // slice order
       }
     }
-    if (lane == 0) publish_tagged(a.out + 2 * (size_t)S.task.out_index, 0.5 * w * a.inv_sigma2, tag);
+    if (lane == 0) publish_tagged(out + 2 * (size_t)out_index, 0.5 * w * inv_sigma2, tag);
     return;
   }
   transpose_reduce<16>(acc, lane);
-  if (lane < 28) S.sum[1][lane] = acc[0]; // zeros when the pair has no point rows
+  if (lane < 28) S.sum[1][lane] = acc[0]; // zeros when the slice has no point rows
   if (n_slices > 1) {
     // leave the partial sums, take a ticket; the last warp of the pair finishes it
     __syncwarp();
@@ -586,22 +640,14 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
       S.sum[e / 28][e % 28] = v;
     }
   }
+  __syncwarp();
   build_basis<true>(S.exp, rel); // starts with a __syncwarp
   __syncwarp();
-  expand_and_publish<true>(S.exp, S.sum[0], S.sum[1], n_planar > 0, n_point > 0, a.inv_sigma2,
-                           a.out + 182 * (size_t)S.task.out_index, tag);
+  expand_and_publish<true>(S.exp, S.sum[0], S.sum[1], n_planar > 0, n_point > 0, inv_sigma2,
+                           out + 182 * (size_t)out_index, tag);
 }
 
-size_t lin_warp_smem_bytes() {
-  struct WarpSmem {
-    ExpandSmem exp;
-    LinTask task;
-    LinArgs args;
-    double sum[2][28];
-    uint32_t dyn[4];
-  };
-  return sizeof(WarpSmem) * kLinWarpTasks;
-}
+size_t lin_warp_smem_bytes() { return sizeof(LinWarpSmem) * kLinWarpTasks; }
 
 namespace {
 template <typename... Args>
@@ -657,11 +703,11 @@ cudaError_t linearize_warp_launch(const LinArgs *ctx_args_dev, const LinTask *ta
   const int grid = (n_entries + kLinWarpTasks - 1) / kLinWarpTasks;
   prof.begin(group);
   if (error_only)
-    lin_warp_kernel<true><<<grid, kLinThreads, smem, stream>>>(ctx_args_dev, tasks_dev, entries_dev, n_entries,
-                                                               partials, tickets);
+    lin_warp_kernel<true><<<grid, kLinWarpThreads, smem, stream>>>(ctx_args_dev, tasks_dev, entries_dev, n_entries,
+                                                                   partials, tickets);
   else
-    lin_warp_kernel<false><<<grid, kLinThreads, smem, stream>>>(ctx_args_dev, tasks_dev, entries_dev, n_entries,
-                                                                partials, tickets);
+    lin_warp_kernel<false><<<grid, kLinWarpThreads, smem, stream>>>(ctx_args_dev, tasks_dev, entries_dev,
+                                                                    n_entries, partials, tickets);
   prof.end(group, 1);
   return cudaGetLastError();
 }
