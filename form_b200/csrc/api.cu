@@ -129,8 +129,9 @@ static int create_impl(formgpu_ctx *ctx) {
   ctx->n_points = (size_t)ctx->rows * ctx->cols;
   // picks in one row are pairwise >= neighbor_points apart (suppression +-(np-1))
   ctx->qr_cap = (ctx->cols + P.neighbor_points - 1) / P.neighbor_points + 1;
+  ctx->qr_cap = (ctx->qr_cap + 3) & ~3; // multiples of 4: every segment plane starts 16-byte aligned
   ctx->pr_cap = std::min(P.num_sectors * (P.planar_feats_per_sector + 1), ctx->qr_cap);
-  ctx->pr_cap = std::max(ctx->pr_cap, 1);
+  ctx->pr_cap = (std::max(ctx->pr_cap, 1) + 3) & ~3;
   ctx->kp_cap = (size_t)ctx->rows * ctx->pr_cap;
   ctx->kq_cap = (size_t)ctx->rows * ctx->qr_cap;
   if (ctx->kp_cap >= (1u << 24) || ctx->kq_cap >= (1u << 24))

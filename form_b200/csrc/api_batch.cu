@@ -13,6 +13,7 @@
 #include "api_common.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <functional>
 #include <new>
 
@@ -41,6 +42,9 @@ struct formgpu_batch {
   unsigned *d_tickets = nullptr;
   size_t partial_cap = 0, ticket_cap = 0;
   size_t partials_used = 0, tickets_used = 0; // within the current submit
+  // extraction launches with at least this many rows use the many-row kernel variants
+  // (kernels.hpp: kManyRowsMin; FORMGPU_MANY_ROWS_MIN overrides it, for tests and tuning)
+  int many_rows_min = kManyRowsMin;
 };
 
 namespace {
@@ -133,12 +137,19 @@ int stage_lin_groups(formgpu_batch *b, const std::vector<LinArgs> &ctx_args, con
   std::vector<size_t> order(tasks.size());
   for (size_t t = 0; t < order.size(); ++t) order[t] = t;
   std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return size_hint[x] > size_hint[y]; });
+  // Slice length: the per-slice cost (two butterfly reductions, partial sums, ticket) is
+  // worth ~250 correspondences, so slices grow with the launch - about kLinWarpTarget warps
+  // (two waves of resident warps) - between kLinWarpSlice and kLinWarpSliceMax.
+  unsigned long long total = 0;
+  for (uint32_t h : size_hint) total += h;
+  const uint32_t slice_len = (uint32_t)std::min<unsigned long long>(
+      std::max<unsigned long long>((total / kLinWarpTarget + 127) / 128 * 128, kLinWarpSlice), kLinWarpSliceMax);
   std::vector<LinCta> slices;
   slices.reserve(tasks.size() * 4);
   for (size_t t : order) {
     const LinArgs &ca = ctx_args[tasks[t].ctx_index];
     const uint32_t n =
-        std::min<uint32_t>(std::max<uint32_t>((size_hint[t] + kLinWarpSlice - 1) / kLinWarpSlice, 1u), 4096u);
+        std::min<uint32_t>(std::max<uint32_t>((size_hint[t] + slice_len - 1) / slice_len, 1u), 4096u);
     const uint32_t first = (uint32_t)slices.size();
     for (uint32_t r = 0; r < n; ++r)
       slices.push_back(LinCta{(uint32_t)t, first, (uint16_t)r, (uint16_t)n, tasks[t].ctx_index, ca.pair_row,
@@ -188,6 +199,7 @@ int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size
   if (!b) return FORMGPU_ERR_CAPACITY;
   b->device = device;
   b->stream = static_cast<cudaStream_t>(stream);
+  if (const char *env = std::getenv("FORMGPU_MANY_ROWS_MIN")) b->many_rows_min = std::atoi(env);
   auto bail = [&](int rc, const std::string &msg) {
     g_batch_error = msg;
     formgpu_batch_destroy(b);
@@ -350,7 +362,7 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       const ExtractArgs shape = items[0];
       const int n_items = (int)items.size();
       launchers.push_back([=]() -> int {
-        extract_batch_launch(shape, staged<ExtractArgs>(b, off), n_items, b->stream, b->prof);
+        extract_batch_launch(shape, staged<ExtractArgs>(b, off), n_items, b->many_rows_min, b->stream, b->prof);
         BATCH_CUDA(b, cudaGetLastError());
         return FORMGPU_OK;
       });

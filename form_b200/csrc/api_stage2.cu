@@ -133,6 +133,7 @@ int map_rebuild_prepare(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
     a[t].slot_scan = d.scan;
     a[t].n_total = (int)ctx->map_n[t];
     a[t].voxel_width = ctx->P.max_dist_matching; // form.cpp:61-65
+    a[t].inv_voxel_width = 1.0 / ctx->P.max_dist_matching;
     a[t].hash = ctx->d_hash[t];
     a[t].hash_mask = ctx->hash_mask[t];
     a[t].world_tmp = ctx->d_world_tmp[t];
@@ -212,6 +213,7 @@ int assoc_prepare(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_sc
     aa[t].queries = queries;
     std::memcpy(aa[t].pose, pose_k, 12 * sizeof(double));
     aa[t].voxel_width = ctx->P.max_dist_matching;
+    aa[t].inv_voxel_width = 1.0 / ctx->P.max_dist_matching;
     aa[t].hash = ctx->d_hash[t];
     aa[t].hash_mask = ctx->hash_mask[t];
     aa[t].world = ctx->d_world[t];

@@ -212,12 +212,12 @@ __device__ __forceinline__ void extract_select_body(const ExtractArgs &a, const 
     const int start = s * pps;
     const int end = (s == S - 1) ? cols : start + pps;
     const uint32_t kc = keys[c];
+    // rank under (key, column): columns before c count when <=, columns after c when <
     int rank = 0;
-#pragma unroll 4
-    for (int j = start; j < end; ++j) {
-      const uint32_t kj = keys[j];
-      rank += (kj < kc || (kj == kc && j < c)) ? 1 : 0;
-    }
+#pragma unroll 8
+    for (int j = start; j < c; ++j) rank += keys[j] <= kc ? 1 : 0;
+#pragma unroll 8
+    for (int j = c + 1; j < end; ++j) rank += keys[j] < kc ? 1 : 0;
     sorted[start + rank] = (uint16_t)c;
   }
   __syncthreads();
@@ -285,34 +285,59 @@ __device__ __forceinline__ void extract_select_body(const ExtractArgs &a, const 
     }
     __syncwarp();
     const int factor = 1 + U / pfps; // :379
-    int count = 0;
-    int offset = 0;
-    // Phase A: full strided passes while the pass starts with count <= pfps
-    while (offset < factor && count <= pfps) {
-      bool broken = false;
-      for (int m0 = 0; !broken; m0 += 32) {
-        const long long u = (long long)offset + (long long)(m0 + lane) * factor;
-        const bool in = u < U;
-        if (__ballot_sync(0xffffffffu, in) == 0) break;
-        const int col = in ? (int)ulist[u] : 0;
-        const bool cand = in && get_bit(m_pvalid, col);
-        const bool alive = resolve_group(cand, col, np, lane);
-        const unsigned sel = __ballot_sync(0xffffffffu, alive);
-        const int rank = __popc(sel & lt_mask);
-        // element m of a pass is visited iff m == 0 or the count after the
-        // earlier visits is still <= pfps (the break at :394-396 sits after the
-        // visit and leaves only the inner loop)
-        const bool visited = in && ((m0 + lane == 0) || (count + rank <= pfps));
-        const bool accept = alive && visited;
-        if (accept) {
-          out_pt[ptotal + count + rank] = (uint16_t)col;
-          clear_bits(m_pvalid, col - (np - 1), col + (np - 1));
-        }
-        count += __popc(__ballot_sync(0xffffffffu, accept));
-        if (count > pfps) broken = true;
-        __syncwarp();
+    // The reference visits u = offset + m * factor for offset = 0 .. factor-1 (outer) and
+    // m = 0, 1, .. (inner), leaving the inner loop once count > pfps (:394-396).  Equivalently,
+    // in that (offset, m) order: the first element of every pass is ALWAYS visited, a later
+    // element (m > 0) is visited iff the running count is still <= pfps.  A pass holds at most
+    // ceil(U / factor) <= pfps + 1 elements, so stepping pass by pass would keep 3-4 lanes of
+    // the warp busy; instead 32 consecutive elements of the whole visiting sequence (several
+    // passes) are resolved per step.  Pass `o` has n_full + 1 elements if o < rem, else n_full.
+    const int n_full = U / factor, rem = U - n_full * factor;
+    const int split = rem * (n_full + 1); // sequence index of the first element of pass `rem`
+    auto pass_of = [&](int t, int &o, int &m) {
+      if (t < split) {
+        o = t / (n_full + 1);
+        m = t - o * (n_full + 1);
+      } else {
+        const int t2 = t - split, d = t2 / n_full; // n_full > 0 whenever such a t exists
+        o = rem + d;
+        m = t2 - d * n_full;
       }
-      ++offset;
+    };
+    int count = 0;
+    int offset = factor; // first pass the strided phase has not touched when it stops
+    for (int base = 0; base < U && count <= pfps; base += 32) {
+      const int t = base + lane;
+      const bool in = t < U;
+      int o = 0, m = 0;
+      if (in) pass_of(t, o, m);
+      const int col = in ? (int)ulist[o + m * factor] : 0;
+      const bool cand = in && get_bit(m_pvalid, col);
+      bool alive = resolve_group(cand, col, np, lane);
+      unsigned sel = __ballot_sync(0xffffffffu, alive);
+      // lanes whose count-before already exceeds pfps (a suffix of the group): their m > 0
+      // candidates are not visited and must not suppress anything - resolve again without them
+      // (the outcome of the lanes before the suffix does not depend on later lanes)
+      const unsigned over_bits = __ballot_sync(0xffffffffu, count + __popc(sel & lt_mask) > pfps);
+      if (over_bits) {
+        const int first_over = __ffs(over_bits) - 1;
+        const bool dropped = cand && m > 0 && lane >= first_over;
+        if (__ballot_sync(0xffffffffu, dropped)) {
+          alive = resolve_group(cand && !dropped, col, np, lane);
+          sel = __ballot_sync(0xffffffffu, alive);
+        }
+      }
+      if (alive) {
+        out_pt[ptotal + count + __popc(sel & lt_mask)] = (uint16_t)col;
+        clear_bits(m_pvalid, col - (np - 1), col + (np - 1));
+      }
+      count += __popc(sel);
+      if (count > pfps) { // only the first element of every later pass is still visited
+        int o_last, m_last;
+        pass_of(min(base + 31, U - 1), o_last, m_last);
+        offset = o_last + 1;
+      }
+      __syncwarp();
     }
     // Phase B: count > pfps, so every remaining pass visits only u = offset
     for (int base = offset; base < factor; base += 32) {
@@ -391,27 +416,7 @@ __device__ __forceinline__ float box_dist2(const float4 lo, const float4 hi, con
 
 __device__ __forceinline__ int closest_in_row_pruned(const float4 *rowp, const uint32_t *valid,
                                                      const float4 *box, const float4 p, int words,
-                                                     int cols, int lane) {
-  // nearest chunk by box distance (ties: lowest chunk)
-  float lb_min = INFINITY;
-  int w_min = 0x7fffffff;
-  for (int w = lane; w < words; w += 32) {
-    const float lb = box_dist2(box[2 * w], box[2 * w + 1], p);
-    if (lb < lb_min) {
-      lb_min = lb;
-      w_min = w;
-    }
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const float ol = __shfl_xor_sync(0xffffffffu, lb_min, off);
-    const int ow = __shfl_xor_sync(0xffffffffu, w_min, off);
-    if (ol < lb_min || (ol == lb_min && ow < w_min)) {
-      lb_min = ol;
-      w_min = ow;
-    }
-  }
-  if (w_min == 0x7fffffff) return -1; // no valid point in the row
+                                                     int cols, int lane, int c_own) {
   float best = INFINITY;
   int bc = 0x7fffffff;
   auto eval = [&](int w) {
@@ -424,15 +429,50 @@ __device__ __forceinline__ int closest_in_row_pruned(const float4 *rowp, const u
       }
     }
   };
-  eval(w_min);
-  float seed = best;
+  auto warp_min = [](float v) {
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) seed = fminf(seed, __shfl_xor_sync(0xffffffffu, seed, off));
-  // every other chunk that the bound cannot exclude
+    for (int off = 16; off > 0; off >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+  };
+  // Seed: the chunk at the pick's own azimuth - on an organised scan the closest point of the
+  // adjacent row is nearly always there, so its best distance prunes almost every other chunk
+  // without first ranking all boxes.  (Any seed is valid: the pruning below is conservative.)
+  int w_seed = c_own >> 5;
+  eval(w_seed);
+  float seed = warp_min(best);
+  if (seed == INFINITY) {
+    // nothing valid at that azimuth: seed with the nearest chunk by box distance (ties: lowest)
+    float lb_min = INFINITY;
+    int w_min = 0x7fffffff;
+    for (int w = lane; w < words; w += 32) {
+      const float lb = box_dist2(box[2 * w], box[2 * w + 1], p);
+      if (lb < lb_min) {
+        lb_min = lb;
+        w_min = w;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ol = __shfl_xor_sync(0xffffffffu, lb_min, off);
+      const int ow = __shfl_xor_sync(0xffffffffu, w_min, off);
+      if (ol < lb_min || (ol == lb_min && ow < w_min)) {
+        lb_min = ol;
+        w_min = ow;
+      }
+    }
+    if (w_min == 0x7fffffff) return -1; // no valid point in the row
+    w_seed = w_min;
+    eval(w_seed);
+    seed = warp_min(best);
+  }
+  // every other chunk that the bound cannot exclude (empty chunks have an infinite bound)
   for (int w0 = 0; w0 < words; w0 += 32) {
     const int w = w0 + lane;
     bool need = false;
-    if (w < words && w != w_min) need = box_dist2(box[2 * w], box[2 * w + 1], p) * (1.0f - 1e-5f) <= seed;
+    if (w < words && w != w_seed) {
+      const float lb = box_dist2(box[2 * w], box[2 * w + 1], p);
+      need = lb < INFINITY && lb * (1.0f - 1e-5f) <= seed;
+    }
     unsigned todo = __ballot_sync(0xffffffffu, need);
     while (todo) {
       eval(w0 + __ffs(todo) - 1);
@@ -581,6 +621,47 @@ __device__ void smallest_eigvec3f(float m00, float m10, float m11, float m20, fl
   n[0] = n0; n[1] = n1; n[2] = n2;
 }
 
+// Covariance of the gathered neighbours (own row +-, closest point of each adjacent row and its
+// +-, extraction.tpp:275-305, :314-321) and the eigenvector of its smallest eigenvalue.
+// Returns {n, 1} or all zero when the feature is dropped (:308-310).
+__device__ __forceinline__ float4 pick_normal(const float4 *own, const float4 *prv, const float4 *nxt, int c,
+                                              const PickDesc d, int min_points) {
+  const float4 p = own[c];
+  const int n = d.n_plus + d.n_minus + (d.c_prev >= 0 ? 1 + d.pp + d.pm : 0) +
+                (d.c_next >= 0 ? 1 + d.np_ + d.nm : 0);
+  const bool other = d.c_prev >= 0 || d.c_next >= 0;
+  float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (other && n >= min_points) {
+    const float nf = (float)n;
+    float c00 = 0.f, c10 = 0.f, c11 = 0.f, c20 = 0.f, c21 = 0.f, c22 = 0.f;
+    auto acc = [&](const float4 q) {
+      const float a0 = (q.x - p.x) / nf, a1 = (q.y - p.y) / nf, a2 = (q.z - p.z) / nf;
+      c00 = c00 + a0 * a0;
+      c10 = c10 + a1 * a0;
+      c11 = c11 + a1 * a1;
+      c20 = c20 + a2 * a0;
+      c21 = c21 + a2 * a1;
+      c22 = c22 + a2 * a2;
+    };
+    for (int i = 1; i <= d.n_plus; ++i) acc(own[c + i]);
+    for (int i = 1; i <= d.n_minus; ++i) acc(own[c - i]);
+    if (d.c_prev >= 0) {
+      acc(prv[d.c_prev]);
+      for (int i = 1; i <= d.pp; ++i) acc(prv[d.c_prev + i]);
+      for (int i = 1; i <= d.pm; ++i) acc(prv[d.c_prev - i]);
+    }
+    if (d.c_next >= 0) {
+      acc(nxt[d.c_next]);
+      for (int i = 1; i <= d.np_; ++i) acc(nxt[d.c_next + i]);
+      for (int i = 1; i <= d.nm; ++i) acc(nxt[d.c_next - i]);
+    }
+    float nrm[3];
+    smallest_eigvec3f(c00, c10, c11, c20, c21, c22, nrm);
+    out = make_float4(nrm[0], nrm[1], nrm[2], 1.0f);
+  }
+  return out;
+}
+
 } // namespace
 
 // The search is arithmetic-bound (picks x 2 rows x cols distance evaluations) and a row
@@ -636,8 +717,8 @@ __device__ __forceinline__ void extract_normals_body(const ExtractArgs &a, const
   for (int pk = warp; pk < n_picks; pk += nwarps) {
     const int c = picks[pk];
     const float4 pp = own[c];
-    const int cprev = has_prev ? closest_in_row_pruned(prv, v_prv, box_prv, pp, words, cols, lane) : -1;
-    const int cnext = has_next ? closest_in_row_pruned(nxt, v_nxt, box_nxt, pp, words, cols, lane) : -1;
+    const int cprev = has_prev ? closest_in_row_pruned(prv, v_prv, box_prv, pp, words, cols, lane, c) : -1;
+    const int cnext = has_next ? closest_in_row_pruned(nxt, v_nxt, box_nxt, pp, words, cols, lane, c) : -1;
     int n_plus, n_minus, pp_ = 0, pm = 0, nq = 0, nm = 0;
     neighbor_counts(own, c, np, r2, lane, n_plus, n_minus);
     if (cprev >= 0) neighbor_counts(prv, cprev, np, r2, lane, pp_, pm);
@@ -654,44 +735,14 @@ __device__ __forceinline__ void extract_normals_body(const ExtractArgs &a, const
   }
   __syncthreads();
 
-  // phase B: one thread per pick - covariance + eigenvector
+  // phase B: one thread per pick - covariance + eigenvector (picks packed into as few warps as
+  // possible: spreading them over all warps was measured 40 % more instructions, the eigen
+  // solver being long and divergent)
   for (int pk = tid; pk < n_picks; pk += blockDim.x) {
     const int c = picks[pk];
-    const float4 p = own[c];
     const PickDesc d = desc[pk];
-    const int n = d.n_plus + d.n_minus + (d.c_prev >= 0 ? 1 + d.pp + d.pm : 0) +
-                  (d.c_next >= 0 ? 1 + d.np_ + d.nm : 0);
-    const bool other = d.c_prev >= 0 || d.c_next >= 0;
-    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (other && n >= a.min_points) {
-      const float nf = (float)n;
-      float c00 = 0.f, c10 = 0.f, c11 = 0.f, c20 = 0.f, c21 = 0.f, c22 = 0.f;
-      auto acc = [&](const float4 q) {
-        const float a0 = (q.x - p.x) / nf, a1 = (q.y - p.y) / nf, a2 = (q.z - p.z) / nf;
-        c00 = c00 + a0 * a0;
-        c10 = c10 + a1 * a0;
-        c11 = c11 + a1 * a1;
-        c20 = c20 + a2 * a0;
-        c21 = c21 + a2 * a1;
-        c22 = c22 + a2 * a2;
-      };
-      for (int i = 1; i <= d.n_plus; ++i) acc(own[c + i]);
-      for (int i = 1; i <= d.n_minus; ++i) acc(own[c - i]);
-      if (d.c_prev >= 0) {
-        acc(prv[d.c_prev]);
-        for (int i = 1; i <= d.pp; ++i) acc(prv[d.c_prev + i]);
-        for (int i = 1; i <= d.pm; ++i) acc(prv[d.c_prev - i]);
-      }
-      if (d.c_next >= 0) {
-        acc(nxt[d.c_next]);
-        for (int i = 1; i <= d.np_; ++i) acc(nxt[d.c_next + i]);
-        for (int i = 1; i <= d.nm; ++i) acc(nxt[d.c_next - i]);
-      }
-      float nrm[3];
-      smallest_eigvec3f(c00, c10, c11, c20, c21, c22, nrm);
-      out = make_float4(nrm[0], nrm[1], nrm[2], 1.0f);
-      atomicAdd(&s_keep, 1);
-    }
+    const float4 out = pick_normal(own, prv, nxt, c, d, a.min_points);
+    if (out.w != 0.0f) atomicAdd(&s_keep, 1);
     a.normals[rb * a.pr_cap + p_lo + pk] = out;
     if (a.closest) {
       a.closest[(rb * a.pr_cap + p_lo + pk) * 2 + 0] = d.c_prev >= 0 ? (row - 1) * cols + d.c_prev : -1;
@@ -707,10 +758,149 @@ __global__ void __launch_bounds__(256) extract_normals_kernel(ExtractArgs a) {
   extract_normals_body(a, blockIdx.x, blockIdx.y);
 }
 
+// ---------------------------------------------------------------------------
+// K2 for many-row (batched) launches: one THREAD per pick, one CTA per row.
+// The warp-per-pick search above spends ~450 warp instructions per pick, most of them the
+// five-step shuffle reductions and ballots that hold 32 lanes together around a search which,
+// after box pruning, touches one or two 32-column chunks (ncu: 620 warp instructions per pick,
+// 13 of 32 lanes active on average).  With thousands of rows in flight there is no need to
+// spread one pick over a warp: a thread walks the 32 chunk boxes (broadcast reads), evaluates
+// the chunk at its own azimuth and the few the bound cannot exclude, counts its neighbours and
+// goes straight on to its covariance and eigen solve - no shuffle, no barrier between the
+// phases, 32 picks per warp.  Same arithmetic per candidate and the same (dist2, column) /
+// first-miss rules, so the results are bit-identical to the warp-per-pick kernel.
+// ---------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ int closest_in_row_thread(const float4 *rowp, const uint32_t *valid,
+                                                     const float4 *box, const float4 p, int words, int c_own) {
+  float best = INFINITY;
+  int bc = 0x7fffffff;
+  auto eval = [&](int w) {
+    uint32_t m = valid[w];
+    while (m) {
+      const int c = w * 32 + __ffs(m) - 1;
+      m &= m - 1u;
+      const float d2 = diff_sqnorm4(rowp[c], p);
+      if (d2 < best || (d2 == best && c < bc)) {
+        best = d2;
+        bc = c;
+      }
+    }
+  };
+  int w_seed = c_own >> 5; // the chunk at the pick's own azimuth
+  eval(w_seed);
+  if (best == INFINITY) {
+    // nothing valid there: the nearest chunk by box distance (ties: lowest chunk)
+    float lb_min = INFINITY;
+    int w_min = -1;
+    for (int w = 0; w < words; ++w) {
+      const float lb = box_dist2(box[2 * w], box[2 * w + 1], p);
+      if (lb < lb_min) {
+        lb_min = lb;
+        w_min = w;
+      }
+    }
+    if (w_min < 0) return -1; // no valid point in the row
+    w_seed = w_min;
+    eval(w_seed);
+  }
+  // every other chunk the bound cannot exclude; the bound tightens as chunks are evaluated
+  // (still exact: a chunk is skipped only if each of its points loses to the current best)
+  for (int w = 0; w < words; ++w) {
+    if (w == w_seed) continue;
+    const float lb = box_dist2(box[2 * w], box[2 * w + 1], p);
+    if (lb < INFINITY && lb * (1.0f - 1e-5f) <= best) eval(w);
+  }
+  return bc == 0x7fffffff ? -1 : bc;
+}
+
+// find_neighbors (extraction.tpp:422-448) around column c of `rowp`, sequential form
+__device__ __forceinline__ void neighbor_counts_thread(const float4 *rowp, int c, int np, double r2,
+                                                       int &n_plus, int &n_minus) {
+  const float4 p = rowp[c];
+  n_plus = 0;
+  while (n_plus < np && (double)diff_sqnorm4(rowp[c + n_plus + 1], p) < r2) ++n_plus;
+  n_minus = 0;
+  while (n_minus < np && (double)diff_sqnorm4(rowp[c - n_minus - 1], p) < r2) ++n_minus;
+}
+
+__device__ __forceinline__ void extract_normals_thread_body(const ExtractArgs &a, const int row, const int b) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int cols = a.cols, words = a.words, np = a.np;
+  float4 *own = reinterpret_cast<float4 *>(smem_raw);
+  float4 *prv = own + cols;
+  float4 *nxt = prv + cols;
+  float4 *box_prv = nxt + cols; // [words][2] chunk boxes of the adjacent rows
+  float4 *box_nxt = box_prv + 2 * words;
+  uint32_t *v_prv = reinterpret_cast<uint32_t *>(box_nxt + 2 * words);
+  uint32_t *v_nxt = v_prv + words;
+  __shared__ int s_keep;
+
+  const int tid = threadIdx.x;
+  const size_t rb = (size_t)b * a.rows + row;
+  const int n_picks = a.planar_cnt[rb];
+  if (tid == 0) s_keep = 0;
+  if (n_picks == 0) return; // keep_cnt was zeroed by the select kernel
+  const bool has_prev = row > 0, has_next = row < a.rows - 1;
+  const float4 *g = a.scan + rb * cols;
+  for (int c = tid; c < cols; c += blockDim.x) {
+    own[c] = __ldg(&g[c]);
+    if (has_prev) prv[c] = __ldg(&g[c - cols]);
+    if (has_next) nxt[c] = __ldg(&g[c + cols]);
+  }
+  for (int w = tid; w < words; w += blockDim.x) {
+    v_prv[w] = has_prev ? a.valid_bits[(rb - 1) * words + w] : 0u;
+    v_nxt[w] = has_next ? a.valid_bits[(rb + 1) * words + w] : 0u;
+  }
+  for (int i = tid; i < 2 * words; i += blockDim.x) {
+    if (has_prev) box_prv[i] = a.row_box[(rb - 1) * words * 2 + i];
+    if (has_next) box_nxt[i] = a.row_box[(rb + 1) * words * 2 + i];
+  }
+  __syncthreads();
+
+  const uint16_t *picks = a.planar_cols + rb * a.pr_cap;
+  const double r2 = a.radius * a.radius;
+  int kept = 0;
+  for (int pk = tid; pk < n_picks; pk += blockDim.x) {
+    const int c = picks[pk];
+    const float4 pp = own[c];
+    const int cprev = has_prev ? closest_in_row_thread(prv, v_prv, box_prv, pp, words, c) : -1;
+    const int cnext = has_next ? closest_in_row_thread(nxt, v_nxt, box_nxt, pp, words, c) : -1;
+    int n_plus, n_minus, pp_ = 0, pm = 0, nq = 0, nm = 0;
+    neighbor_counts_thread(own, c, np, r2, n_plus, n_minus);
+    if (cprev >= 0) neighbor_counts_thread(prv, cprev, np, r2, pp_, pm);
+    if (cnext >= 0) neighbor_counts_thread(nxt, cnext, np, r2, nq, nm);
+    PickDesc d;
+    d.c_prev = (short)cprev; d.c_next = (short)cnext;
+    d.n_plus = (unsigned char)n_plus; d.n_minus = (unsigned char)n_minus;
+    d.pp = (unsigned char)pp_; d.pm = (unsigned char)pm;
+    d.np_ = (unsigned char)nq; d.nm = (unsigned char)nm;
+    d.pad[0] = d.pad[1] = 0;
+    const float4 out = pick_normal(own, prv, nxt, c, d, a.min_points);
+    if (out.w != 0.0f) ++kept;
+    a.normals[rb * a.pr_cap + pk] = out;
+    if (a.closest) {
+      a.closest[(rb * a.pr_cap + pk) * 2 + 0] = cprev >= 0 ? (row - 1) * cols + cprev : -1;
+      a.closest[(rb * a.pr_cap + pk) * 2 + 1] = cnext >= 0 ? (row + 1) * cols + cnext : -1;
+    }
+  }
+  if (kept) atomicAdd(&s_keep, kept);
+  __syncthreads();
+  if (tid == 0 && s_keep) atomicAdd(&a.keep_cnt[rb], s_keep); // integer count: order-free
+}
+} // namespace
+
 __global__ void __launch_bounds__(256) extract_normals_batch_kernel(const ExtractArgs *items) {
   __shared__ ExtractArgs s_a;
   load_item_args(s_a, items + blockIdx.y);
   extract_normals_body(s_a, blockIdx.x, 0);
+}
+
+__global__ void __launch_bounds__(256) extract_normals_rows_kernel(const ExtractArgs *items) {
+  __shared__ ExtractArgs s_a;
+  load_item_args(s_a, items + blockIdx.y);
+  extract_normals_thread_body(s_a, blockIdx.x, 0);
 }
 
 // ---------------------------------------------------------------------------
@@ -880,20 +1070,35 @@ cudaError_t extract_configure(int cols, int cols_pad, int words, int pr_cap) {
   e = cudaFuncSetAttribute(extract_normals_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)extract_normals_smem(cols, words, pr_cap));
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(extract_normals_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)extract_normals_smem(cols, words, pr_cap));
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(extract_normals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)extract_normals_smem(cols, words, pr_cap));
 }
 
 void extract_batch_launch(const ExtractArgs &shape, const ExtractArgs *items_dev, int n_items,
-                          cudaStream_t stream, Profiler &prof) {
+                          int many_rows_min, cudaStream_t stream, Profiler &prof) {
   const ExtractArgs &a = shape; // geometry (rows, cols, caps) is common to the batch
   const dim3 grid(a.rows, n_items);
   prof.begin(FORMGPU_KG_EXTRACT_SELECT);
-  extract_select_batch_kernel<<<grid, 512, extract_select_smem(a.cols, a.cols_pad, a.words), stream>>>(items_dev);
+  // One warp of every CTA ends up walking the row's greedy selections alone, so what bounds a
+  // many-row launch is how many rows are RESIDENT (registers: 2 CTAs of 512 threads per SM, 10
+  // of 128).  Launches with more rows than fit at 512 threads use 128-thread CTAs: the parallel
+  // part of a row takes four times longer, but five times as many serial walks overlap it.
+  const bool many_rows = a.rows * n_items >= many_rows_min;
+  const int select_threads = many_rows ? 128 : 512;
+  extract_select_batch_kernel<<<grid, select_threads, extract_select_smem(a.cols, a.cols_pad, a.words),
+                                stream>>>(items_dev);
   prof.end(FORMGPU_KG_EXTRACT_SELECT, 1);
   prof.begin(FORMGPU_KG_EXTRACT_NORMALS);
-  extract_normals_batch_kernel<<<dim3(a.rows * kNormalSplit, n_items), 256,
-                                 extract_normals_smem(a.cols, a.words, a.pr_cap), stream>>>(items_dev);
+  // many rows: one thread per pick (one CTA per row); few rows: one warp per pick, four CTAs
+  // per row, which spreads a small launch over the whole GPU
+  if (many_rows)
+    extract_normals_rows_kernel<<<grid, 256, extract_normals_smem(a.cols, a.words, a.pr_cap), stream>>>(items_dev);
+  else
+    extract_normals_batch_kernel<<<dim3(a.rows * kNormalSplit, n_items), 256,
+                                   extract_normals_smem(a.cols, a.words, a.pr_cap), stream>>>(items_dev);
   prof.end(FORMGPU_KG_EXTRACT_NORMALS, 1);
   prof.begin(FORMGPU_KG_EXTRACT_PACK);
   extract_pack_batch_kernel<<<grid, 128, (size_t)a.pr_cap * sizeof(uint16_t), stream>>>(items_dev);

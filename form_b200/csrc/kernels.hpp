@@ -51,8 +51,11 @@ size_t extract_normals_smem(int cols, int words, int pr_cap);
 void extract_launch(const ExtractArgs &a, int n_scans, cudaStream_t stream, Profiler &prof);
 /// Same three kernels for n_items scans of DIFFERENT contexts (one ExtractArgs each, in
 /// device memory); `shape` supplies the common geometry.
+/// Launches with at least `many_rows_min` rows (rows x items) use the many-row variants: 128-thread
+/// select CTAs and the thread-per-pick normals kernel, which trade per-row latency for rows in flight.
+constexpr int kManyRowsMin = 2 * 148 + 1;
 void extract_batch_launch(const ExtractArgs &shape, const ExtractArgs *items_dev, int n_items,
-                          cudaStream_t stream, Profiler &prof);
+                          int many_rows_min, cudaStream_t stream, Profiler &prof);
 
 // ---- stage 2 (map_assoc.cu, compiled with -fmad=false) ----
 struct MapArgs {
@@ -65,6 +68,7 @@ struct MapArgs {
   const uint64_t *slot_scan; // [W]
   int n_total;
   double voxel_width;
+  double inv_voxel_width; // 1 / voxel_width (host, IEEE): fast path of voxel_coord
   HashSlot *hash;
   uint32_t hash_mask;
   WorldPoint *world_tmp; // store order
@@ -91,6 +95,7 @@ struct AssocArgs {
   const void *queries; // PlanarRec* / PointRec* of the current scan
   double pose[12];     // pose of the current scan
   double voxel_width;
+  double inv_voxel_width; // 1 / voxel_width (host, IEEE): fast path of voxel_coord
   const HashSlot *hash;
   uint32_t hash_mask;
   const WorldPoint *world;
@@ -209,7 +214,9 @@ struct LinArgs {
 cudaError_t linearize_launch(const LinArgs &a, const LinInline *inline_req, bool error_only,
                              cudaStream_t stream, Profiler &prof);
 /// Batched launches: correspondences per warp slice the host aims for, and the slice table.
-constexpr uint32_t kLinWarpSlice = 384;
+constexpr uint32_t kLinWarpSlice = 384;     // shortest slice
+constexpr uint32_t kLinWarpSliceMax = 1536; // longest slice
+constexpr uint32_t kLinWarpTarget = 3552;   // warps aimed for: 2 x 148 SMs x 12 resident warps
 struct LinCta { // one warp-sized slice of a pair in a batched linearisation launch (32 B)
   uint32_t task;  // index into the task array
   uint32_t first; // index of the task's first slice (= base of its partial sums)

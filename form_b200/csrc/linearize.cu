@@ -433,53 +433,74 @@ __global__ void __launch_bounds__(kLinThreads) lin_global_kernel(LinArgs a) {
 // barriers of their two block reductions (30 % of the stall samples) and on the partial-sum
 // fence, at 16 resident warps per SM.  Here the unit of work is a WARP: the host cuts every
 // pair into slices of about kLinWarpSlice correspondences (estimate; the kernel divides the
-// TRUE range by the slice count), a warp streams its slice with its loads issued four
-// correspondences deep, reduces its 2 x 28 moments with the butterfly transpose alone - no
+// TRUE range by the slice count), a warp streams its slice as aligned 128-bit loads straight
+// into registers, two quads per plane in flight, reduces its 2 x 28 moments with the butterfly transpose alone - no
 // barrier anywhere in the kernel - and, if the pair has several slices, leaves them in
 // global memory and takes a ticket; the LAST warp of the pair adds the partial sums in slice
 // order (a fixed order, so the result does not depend on which warp came last), expands the
 // block in its own slice of shared memory and publishes it.  task.ctx_index selects the
 // context's argument block (segments, pair row, result buffer, sequence tag).
-constexpr int kLinWarpThreads = 128;              // 4 warps per CTA: three CTAs per SM by shared memory
+constexpr int kLinWarpThreads = 128;              // 4 warps per CTA
 constexpr int kLinWarpTasks = kLinWarpThreads / 32;
-constexpr int kLinStage = 256;                    // correspondences staged per asynchronous batch
 
-// Shared memory of one warp.  The staging planes and the expansion scratch are never live at
-// the same time (a warp expands only after its last correspondence), so they share storage.
+// Shared memory of one warp: its task / context blocks, the two moment vectors and the
+// expansion scratch of the pair's last warp.
 struct LinWarpSmem {
-  union {
-    struct {
-      float planar[9][kLinStage]; // p_i, n_i, p_j planes of the staged planar correspondences
-      float point[6][kLinStage];  // p_i, p_j planes of the staged point correspondences
-    } stage;
-    ExpandSmem exp;
-  };
+  ExpandSmem exp;
   LinTask task;
   LinArgs args;
   double sum[2][28];
   uint32_t dyn[4];
 };
 
-// 4-byte asynchronous global -> shared copies (LDGSTS): the whole batch of a warp is in
-// flight at once without holding registers.  Measured (profiles/r01b_lin_warp_launches.txt):
-// this did NOT move the kernel - launches below one wave cost a flat ~24 us (the serial
-// chain entry -> task -> batch -> reduce -> ticket -> merge -> expand -> publish of a warp),
-// and the large window-wide launches sit at 1.4 TB/s with 45 % of the issue slots busy, four
-// fifths of them address / copy / convert / expansion instructions rather than fp64 math.
-__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gmem_src) {
-  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+// Streaming 128-bit loads of the correspondence planes: read once, so they bypass L1
+// allocation; the data were written by an earlier kernel (segment scatter), hence .nc.
+__device__ __forceinline__ float4 ld_stream4(const float *p) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p));
+  return v;
 }
 
-template <int kPlanes>
-__device__ __forceinline__ void stage_planes(float (*dst)[kLinStage], const float *src, size_t plane_stride,
-                                             uint32_t begin, uint32_t count, int lane) {
+#define LIN_COMP(v, k) ((k) == 0 ? (v).x : (k) == 1 ? (v).y : (k) == 2 ? (v).z : (v).w)
+
+// A warp streams the elements [lo, hi) of kPlanes SoA planes (`stride` floats apart, every
+// plane 16-byte aligned: the capacities are multiples of 4) as aligned float4 quads: lane l
+// owns the quads at a0 + 4 l + 128 c, a0 = lo rounded down to a quad.  The quad of the next
+// step is requested before the current one is reduced, so each lane keeps two 16-byte loads
+// per plane in flight (9 + 9 LDG.128 for plane-point rows) without staging through shared
+// memory; the first and last quad of a range are masked element by element.
+template <int kPlanes, typename Term>
+__device__ __forceinline__ void stream_quads(const float *base, size_t stride, uint32_t lo, uint32_t hi,
+                                             int lane, Term &&term) {
+  if (hi <= lo) return;
+  float4 cur[kPlanes], nxt[kPlanes];
+  uint32_t idx = (lo & ~3u) + 4u * (uint32_t)lane;
+  if (idx < hi) {
 #pragma unroll
-  for (int pl = 0; pl < kPlanes; ++pl)
-    for (uint32_t i = lane; i < count; i += 32) cp_async4(&dst[pl][i], src + pl * plane_stride + begin + i);
+    for (int pl = 0; pl < kPlanes; ++pl) cur[pl] = ld_stream4(base + pl * stride + idx);
+  }
+#pragma unroll 1
+  for (; idx < hi; idx += 128u) {
+    const uint32_t nidx = idx + 128u;
+    if (nidx < hi) {
+#pragma unroll
+      for (int pl = 0; pl < kPlanes; ++pl) nxt[pl] = ld_stream4(base + pl * stride + nidx);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t e = idx + (uint32_t)k;
+      if (e >= lo && e < hi) {
+        float c[kPlanes];
+#pragma unroll
+        for (int pl = 0; pl < kPlanes; ++pl) c[pl] = LIN_COMP(cur[pl], k);
+        term(c);
+      }
+    }
+#pragma unroll
+    for (int pl = 0; pl < kPlanes; ++pl) cur[pl] = nxt[pl];
+  }
 }
 
 template <bool kErrorOnly>
@@ -512,15 +533,16 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
     n_point = S.dyn[3];
     if (n_planar + n_point == 0) return; // empty pair: all its warps leave, nothing is published
   }
-  const double *rel = S.task.rel; // outside the staging union
+  const double *rel = S.task.rel; // relative pose of the pair (shared memory)
   const int rank = me.rank, n_slices = me.n_cta;
   // this warp's slice of the planar and of the point range
   const uint32_t p_lo = (uint32_t)(((unsigned long long)n_planar * rank) / n_slices);
   const uint32_t p_hi = (uint32_t)(((unsigned long long)n_planar * (rank + 1)) / n_slices);
   const uint32_t q_lo = (uint32_t)(((unsigned long long)n_point * rank) / n_slices);
   const uint32_t q_hi = (uint32_t)(((unsigned long long)n_point * (rank + 1)) / n_slices);
-  const float *gp = a.seg_planar + (size_t)S.task.slot_j * 9 * a.kp_cap + off_planar;
-  const float *gq = a.seg_point + (size_t)S.task.slot_j * 6 * a.kq_cap + off_point;
+  // plane 0 of the segment of slot_j; element indices below are relative to it
+  const float *gp = a.seg_planar + (size_t)S.task.slot_j * 9 * a.kp_cap;
+  const float *gq = a.seg_point + (size_t)S.task.slot_j * 6 * a.kq_cap;
   const size_t stp = a.kp_cap, stq = a.kq_cap;
   const double inv_sigma2 = a.inv_sigma2;
   const unsigned long long tag = a.seq & 0xffffffffull;
@@ -531,70 +553,45 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
   double err_acc = 0.0;
 #pragma unroll
   for (int k = 0; k < 32; ++k) acc[k] = 0.0;
-  // Batches of up to kLinStage correspondences: all copies of a batch are issued, then
-  // awaited, then reduced from shared memory.  The first point batch is issued together with
-  // the first planar one, so a typical slice (<= kLinStage of each) has everything in flight
-  // at once.
-  const uint32_t q_first = min((uint32_t)kLinStage, q_hi - q_lo);
-  stage_planes<6>(S.stage.point, gq, stq, q_lo, q_first, lane);
-  for (uint32_t pb = p_lo; pb < p_hi || pb == p_lo; pb += kLinStage) {
-    const uint32_t pn = pb < p_hi ? min((uint32_t)kLinStage, p_hi - pb) : 0u;
-    stage_planes<9>(S.stage.planar, gp, stp, pb, pn, lane);
-    cp_async_wait_all();
-    __syncwarp();
-    for (uint32_t i = lane; i < pn; i += 32) {
-      const double pix = S.stage.planar[0][i], piy = S.stage.planar[1][i], piz = S.stage.planar[2][i];
-      const double nx = S.stage.planar[3][i], ny = S.stage.planar[4][i], nz = S.stage.planar[5][i];
-      const double pjx = S.stage.planar[6][i], pjy = S.stage.planar[7][i], pjz = S.stage.planar[8][i];
-      double qx, qy, qz;
-      apply_rel(rel, pjx, pjy, pjz, qx, qy, qz);
-      const double r = nx * (qx - pix) + ny * (qy - piy) + nz * (qz - piz);
-      if (kErrorOnly) {
-        err_acc += r * r;
-      } else {
-        const double v[7] = {ny * qz - nz * qy, nz * qx - nx * qz, nx * qy - ny * qx, nx, ny, nz, r};
-        int e = 0;
+  stream_quads<9>(gp, stp, off_planar + p_lo, off_planar + p_hi, lane, [&](const float(&c)[9]) {
+    const double pix = c[0], piy = c[1], piz = c[2];
+    const double nx = c[3], ny = c[4], nz = c[5];
+    double qx, qy, qz;
+    apply_rel(rel, (double)c[6], (double)c[7], (double)c[8], qx, qy, qz);
+    const double r = nx * (qx - pix) + ny * (qy - piy) + nz * (qz - piz);
+    if (kErrorOnly) {
+      err_acc += r * r;
+    } else {
+      const double v[7] = {ny * qz - nz * qy, nz * qx - nx * qz, nx * qy - ny * qx, nx, ny, nz, r};
+      int e = 0;
 #pragma unroll
-        for (int p = 0; p < 7; ++p)
+      for (int p = 0; p < 7; ++p)
 #pragma unroll
-          for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
-      }
+        for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
     }
-    __syncwarp(); // the planar planes are overwritten by the next batch
-    if (pb + kLinStage >= p_hi) break;
-  }
+  });
   if (!kErrorOnly) {
     transpose_reduce<16>(acc, lane);
     if (lane < 28) S.sum[0][lane] = acc[0];
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc[k] = 0.0;
   }
-  for (uint32_t qb = q_lo; qb < q_hi; qb += kLinStage) {
-    const uint32_t qn = min((uint32_t)kLinStage, q_hi - qb);
-    if (qb != q_lo) { // the first batch arrived with the planar one
-      stage_planes<6>(S.stage.point, gq, stq, qb, qn, lane);
-      cp_async_wait_all();
-      __syncwarp();
-    }
-    for (uint32_t i = lane; i < qn; i += 32) {
-      const double pix = S.stage.point[0][i], piy = S.stage.point[1][i], piz = S.stage.point[2][i];
-      const double pjx = S.stage.point[3][i], pjy = S.stage.point[4][i], pjz = S.stage.point[5][i];
-      double qx, qy, qz;
-      apply_rel(rel, pjx, pjy, pjz, qx, qy, qz);
-      const double ex = qx - pix, ey = qy - piy, ez = qz - piz;
-      if (kErrorOnly) {
-        err_acc += ex * ex + ey * ey + ez * ez;
-      } else {
-        const double v[7] = {pix, piy, piz, ex, ey, ez, 1.0};
-        int e = 0;
+  stream_quads<6>(gq, stq, off_point + q_lo, off_point + q_hi, lane, [&](const float(&c)[6]) {
+    const double pix = c[0], piy = c[1], piz = c[2];
+    double qx, qy, qz;
+    apply_rel(rel, (double)c[3], (double)c[4], (double)c[5], qx, qy, qz);
+    const double ex = qx - pix, ey = qy - piy, ez = qz - piz;
+    if (kErrorOnly) {
+      err_acc += ex * ex + ey * ey + ez * ez;
+    } else {
+      const double v[7] = {pix, piy, piz, ex, ey, ez, 1.0};
+      int e = 0;
 #pragma unroll
-        for (int p = 0; p < 7; ++p)
+      for (int p = 0; p < 7; ++p)
 #pragma unroll
-          for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
-      }
+        for (int q = p; q < 7; ++q) acc[e++] += v[p] * v[q];
     }
-    __syncwarp();
-  }
+  });
   if (kErrorOnly) {
     double w = warp_sum(err_acc);
     if (n_slices > 1) {
@@ -618,8 +615,8 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
     if (lane == 0) publish_tagged(out + 2 * (size_t)out_index, 0.5 * w * inv_sigma2, tag);
     return;
   }
-  transpose_reduce<16>(acc, lane);
-  if (lane < 28) S.sum[1][lane] = acc[0]; // zeros when the slice has no point rows
+  if (q_hi > q_lo) transpose_reduce<16>(acc, lane); // warp-uniform; acc is all zero otherwise
+  if (lane < 28) S.sum[1][lane] = acc[0];
   if (n_slices > 1) {
     // leave the partial sums, take a ticket; the last warp of the pair finishes it
     __syncwarp();

@@ -28,23 +28,28 @@ namespace formgpu {
 namespace {
 
 // map.tpp:54-68: the 27 neighbour shifts in the reference's order.
-// Packed 2 bits per entry (0 -> 0, 1 -> +1, 2 -> -1) so a lane gets its shift with two
-// ALU ops instead of a lane-divergent (serialised) constant-memory load.
-constexpr unsigned long long pack_axis(int axis) {
+// Packed 2 bits per entry as two's complement (0 -> 00, +1 -> 01, -1 -> 11), 16 voxels per
+// 32-bit word, so a lane decodes a shift with a select, a left shift and an arithmetic right
+// shift instead of a lane-divergent (serialised) constant-memory load.
+constexpr uint32_t pack_axis(int axis, int half) {
   constexpr int T[27][3] = {
       {0, 0, 0},   {1, 0, 0},   {-1, 0, 0},  {0, 1, 0},   {0, -1, 0},  {0, 0, 1},   {0, 0, -1},
       {1, 1, 0},   {1, -1, 0},  {-1, 1, 0},  {-1, -1, 0}, {1, 0, 1},   {1, 0, -1},  {-1, 0, 1},
       {-1, 0, -1}, {0, 1, 1},   {0, 1, -1},  {0, -1, 1},  {0, -1, -1}, {1, 1, 1},   {1, 1, -1},
       {1, -1, 1},  {1, -1, -1}, {-1, 1, 1},  {-1, 1, -1}, {-1, -1, 1}, {-1, -1, -1}};
-  unsigned long long v = 0;
-  for (int l = 0; l < 27; ++l) v |= (unsigned long long)(T[l][axis] == 0 ? 0 : T[l][axis] == 1 ? 1 : 2) << (2 * l);
+  uint32_t v = 0;
+  for (int l = 0; l < 16; ++l)
+    if (16 * half + l < 27) v |= ((uint32_t)T[16 * half + l][axis] & 3u) << (2 * l);
   return v;
 }
-constexpr unsigned long long kShiftX = pack_axis(0), kShiftY = pack_axis(1), kShiftZ = pack_axis(2);
-__device__ __forceinline__ int lane_shift(int lane, int axis) {
-  const unsigned long long bits = axis == 0 ? kShiftX : axis == 1 ? kShiftY : kShiftZ;
-  const int c = (int)((bits >> (2 * lane)) & 3ull);
-  return c == 2 ? -1 : c;
+constexpr uint32_t kShX0 = pack_axis(0, 0), kShX1 = pack_axis(0, 1), kShY0 = pack_axis(1, 0),
+                   kShY1 = pack_axis(1, 1), kShZ0 = pack_axis(2, 0), kShZ1 = pack_axis(2, 1);
+// shift of the voxel with rank v (0..31; ranks >= 27 decode to 0) along `axis` (compile-time)
+__device__ __forceinline__ int lane_shift(int v, int axis) {
+  const uint32_t lo = axis == 0 ? kShX0 : axis == 1 ? kShY0 : kShZ0;
+  const uint32_t hi = axis == 0 ? kShX1 : axis == 1 ? kShY1 : kShZ1;
+  const uint32_t w = (v & 16) ? hi : lo;
+  return (int)(w << (30 - 2 * (v & 15))) >> 30;
 }
 
 constexpr unsigned long long kEmptyKey = 0ull; // table is cleared with memset(0)
@@ -64,9 +69,18 @@ __device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
   return (uint32_t)k;
 }
 
-// VoxelMap::computeCoords (map.tpp:34-38): floor(p / width), IEEE division
-__device__ __forceinline__ int voxel_coord(double v, double width) {
-  return (int)floor(v / width);
+// VoxelMap::computeCoords (map.tpp:34-38): floor(p / width) with an IEEE division.
+// q = v * fl(1 / width) differs from the correctly rounded quotient by less than 3.4e-16 |q|
+// (three roundings), so both have the same floor unless q lies within that distance of an
+// integer; only then (about one coordinate in 1e13) is the division carried out.  Exact by
+// construction: the result is always floor(fl(v / width)).
+__device__ __forceinline__ int voxel_coord(double v, double width, double inv_width) {
+  const double q = v * inv_width;
+  const double f = floor(q);
+  const double fr = q - f; // exact, in [0, 1)
+  const double tol = 8.9e-16 * (fabs(q) + 1.0);
+  if (fr < tol || fr > 1.0 - tol) return (int)floor(v / width);
+  return (int)f;
 }
 
 // R p + t in the oracle's order ((r0 x + r1 y) + r2 z) + t
@@ -123,8 +137,9 @@ __device__ __forceinline__ void map_insert_body(const MapArgs &a) {
   const double *T = a.slot_pose + 12 * slot;
   double wx, wy, wz;
   transform_point(T, x, y, z, wx, wy, wz);
-  const unsigned long long key = pack_key(voxel_coord(wx, a.voxel_width), voxel_coord(wy, a.voxel_width),
-                                          voxel_coord(wz, a.voxel_width));
+  const unsigned long long key = pack_key(voxel_coord(wx, a.voxel_width, a.inv_voxel_width),
+                                          voxel_coord(wy, a.voxel_width, a.inv_voxel_width),
+                                          voxel_coord(wz, a.voxel_width, a.inv_voxel_width));
   uint32_t h = hash_key(key) & a.hash_mask;
   for (;;) {
     unsigned long long *kp = &a.hash[h].key;
@@ -245,14 +260,21 @@ __device__ __forceinline__ int match_bin(const MatchRec &m, double max_d2) {
 
 
 // Eight lanes per query, four queries per warp.  Every instruction of the per-query setup
-// (f64 transform, three IEEE divisions for the voxel key, hashing) then serves four
-// queries instead of one - the one-warp-per-query version was issue-bound on exactly that
-// redundant work (ncu: 67 % issue-active, 420 warp instructions per query).  Lane s of a
-// group owns the neighbour voxels with the reference's shift ranks s, s+8, s+16, s+24
-// (map.tpp:54-68); its four home-slot loads are issued together, so the 27 probes are still
-// one memory round trip.  The arg-min key (dist^2, shift rank, scan, k) is rule R5.
-// read-only loads of the map through the non-coherent path (the argument block lives in
-// shared memory in the batched kernel, which hides from the compiler that these are global)
+// (f64 transform, voxel key, hashing) then serves four queries instead of one - the
+// one-warp-per-query version was issue-bound on exactly that redundant work (ncu: 67 %
+// issue-active, 420 warp instructions per query).
+//
+// Order of the search: (1) the group probes the CENTRE voxel and scans its bucket together;
+// (2) every lane bounds the squared distance from the query to the boxes of its share of the 26
+// neighbour voxels (pure arithmetic on the distances to the six faces of the centre voxel) and
+// keeps those that can still hold a point at least as close as the centre's best - exact
+// pruning: a skipped voxel cannot change the arg-min; (3) the surviving voxel ranks (typically
+// one to four of 26) are compacted through shared memory so that lane s of the group probes the
+// s-th survivor - one hash probe per lane instead of four; (4) the group scans the survivors'
+// buckets one after the other.  The arg-min key (dist^2, shift rank, scan, k) is rule R5, so
+// neither the scan order nor the split over lanes matters.
+// Read-only loads of the map go through the non-coherent path (the argument block lives in
+// shared memory in the batched kernel, which hides from the compiler that these are global).
 __device__ __forceinline__ HashSlot load_slot(const HashSlot *p) {
   const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
   HashSlot s;
@@ -271,20 +293,39 @@ __device__ __forceinline__ WorldPoint load_world(const WorldPoint *p) {
   w.tie = (unsigned long long)__double_as_longlong(b.y);
   return w;
 }
+// bucket of the voxel `key`: linear probing (load <= 0.5); absent -> count stays 0
+__device__ __forceinline__ void probe_voxel(const HashSlot *hash, uint32_t mask, unsigned long long key,
+                                            uint32_t &start, uint32_t &count) {
+  uint32_t h = hash_key(key) & mask;
+  HashSlot s = load_slot(hash + h);
+  while (s.key != key && s.key != kEmptyKey) {
+    h = (h + 1) & mask;
+    s = load_slot(hash + h);
+  }
+  if (s.key == key) {
+    start = s.start;
+    count = s.count;
+  }
+}
 
 // A single sequence's call (20 k queries) cannot fill the GPU either way and is latency-
 // bound, so it keeps 32 lanes per query (shortest bucket scans); batched launches use 8.
-constexpr int kLanesSingle = 32, kLanesBatch = 8;
+constexpr int kLanesSingle = 32, kLanesBatch = 4;
 __host__ __device__ constexpr int queries_per_cta(int lanes) { return 8 * (32 / lanes); } // 256 threads
 
 namespace {
 template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const AssocArgs &a) {
-  constexpr int kQueriesPerWarp = 32 / kQueryLanes;
-  constexpr int kVox = (27 + kQueryLanes - 1) / kQueryLanes; // voxels owned by a lane
+  constexpr int kGroups = 32 / kQueryLanes;                  // queries per warp
+  constexpr int kVox = (27 + kQueryLanes - 1) / kQueryLanes; // voxel ranks owned by a lane
+  constexpr int kDepth = kQueryLanes >= 32 ? 2 : 3;          // bucket points a lane keeps in flight
+  __shared__ unsigned char s_list[8][kGroups][28];           // compacted surviving voxel ranks
+  __shared__ uint2 s_bucket[8][kGroups][27];                 // their buckets {start, count}
   const int lane = threadIdx.x & 31, sub = lane & (kQueryLanes - 1), grp = lane / kQueryLanes;
-  const int q = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kQueriesPerWarp + grp;
+  const int warp = threadIdx.x >> 5;
+  const int q = (blockIdx.x * (blockDim.x >> 5) + warp) * kGroups + grp;
   const int nb = a.W + 1;
   const bool active = q < a.n_query; // whole groups are active or not; shuffles need every lane
+  const bool searchable = active && a.n_map > 0;
   double x = 0.0, y = 0.0, z = 0.0;
   if (active) {
     if (a.type == 0) load_xyz(reinterpret_cast<const PlanarRec *>(a.queries) + q, x, y, z);
@@ -292,83 +333,61 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
   }
   double wx, wy, wz;
   transform_point(a.pose, x, y, z, wx, wy, wz); // kp->transform(init), matcher.hpp:89
-  const int cx = voxel_coord(wx, a.voxel_width), cy = voxel_coord(wy, a.voxel_width),
-            cz = voxel_coord(wz, a.voxel_width);
+  const double w = a.voxel_width, iw = a.inv_voxel_width;
+  const int cx = voxel_coord(wx, w, iw), cy = voxel_coord(wy, w, iw), cz = voxel_coord(wz, w, iw);
 
-  // phase 1: up to four voxels per lane; the home slots are loaded back to back
-  uint32_t start[kVox], count[kVox];
-#pragma unroll
-  for (int r = 0; r < kVox; ++r) start[r] = count[r] = 0u;
-  {
-    unsigned long long key[kVox];
-    uint32_t h[kVox];
-    HashSlot s[kVox];
-    bool live[kVox];
-#pragma unroll
-    for (int r = 0; r < kVox; ++r) {
-      const int v = sub + kQueryLanes * r;
-      live[r] = active && v < 27 && a.n_map > 0;
-      key[r] = pack_key(cx + lane_shift(v & 31, 0), cy + lane_shift(v & 31, 1), cz + lane_shift(v & 31, 2));
-      h[r] = hash_key(key[r]) & a.hash_mask;
-    }
-#pragma unroll
-    for (int r = 0; r < kVox; ++r)
-      if (live[r]) s[r] = load_slot(a.hash + h[r]);
-#pragma unroll
-    for (int r = 0; r < kVox; ++r) {
-      if (!live[r]) continue;
-      while (s[r].key != key[r] && s[r].key != kEmptyKey) { // linear probing (load <= 0.5)
-        h[r] = (h[r] + 1) & a.hash_mask;
-        s[r] = load_slot(a.hash + h[r]);
-      }
-      if (s[r].key == key[r]) {
-        start[r] = s[r].start;
-        count[r] = s[r].count;
-      }
-    }
-  }
-
-  // phase 2: the group scans a bucket together (8 consecutive 32-byte points per step).
-  // The centre voxel goes first; a neighbour voxel is then scanned only if its box can still
-  // hold a point at least as close as the centre's best (exact pruning: a skipped voxel
-  // cannot change the arg-min).
   double best = DBL_MAX;                     // Match::dist_sqrd default (map.hpp:55)
   unsigned long long best_tie = ~0ull;
   int best_rank = 32;
   uint32_t best_pos = kNoSlot;
+  auto consider = [&](const WorldPoint &p, uint32_t pos, int b) {
+    // 4-lane double squared norm, lane 3 = 0 padding: (d0^2 + d2^2) + (d1^2 + 0)
+    const double d0 = p.x - wx, d1 = p.y - wy, d2 = p.z - wz;
+    const double dist = (d0 * d0 + d2 * d2) + (d1 * d1 + 0.0);
+    // rule R5 key (dist, shift rank, tie)
+    if (dist < best || (dist == best && (b < best_rank || (b == best_rank && p.tie < best_tie)))) {
+      best = dist;
+      best_tie = p.tie;
+      best_rank = b;
+      best_pos = pos;
+    }
+  };
+  // the group scans a bucket together, kQueryLanes consecutive 32-byte points per step; a lane
+  // requests its next kDepth points before it looks at the first
   auto scan_bucket = [&](int b, uint32_t sb, uint32_t cb) {
-    for (uint32_t i = sub; i < cb; i += kQueryLanes) {
-      const WorldPoint p = load_world(a.world + sb + i);
-      // 4-lane double squared norm, lane 3 = 0 padding: (d0^2 + d2^2) + (d1^2 + 0)
-      const double d0 = p.x - wx, d1 = p.y - wy, d2 = p.z - wz;
-      const double dist = (d0 * d0 + d2 * d2) + (d1 * d1 + 0.0);
-      // rule R5 key (dist, shift rank, tie)
-      if (dist < best || (dist == best && (b < best_rank || (b == best_rank && p.tie < best_tie)))) {
-        best = dist;
-        best_tie = p.tie;
-        best_rank = b;
-        best_pos = sb + i;
+    for (uint32_t i = sub; i < cb; i += kDepth * kQueryLanes) {
+      WorldPoint p[kDepth];
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u) {
+        const uint32_t iu = i + u * kQueryLanes;
+        p[u] = load_world(a.world + sb + (iu < cb ? iu : i));
+      }
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u) {
+        const uint32_t iu = i + u * kQueryLanes;
+        if (u == 0 || iu < cb) consider(p[u], sb + iu, b);
       }
     }
   };
+
+  // (1) centre voxel: every lane of the group probes the same slot (one broadcast load)
   {
-    const uint32_t c0 = __shfl_sync(0xffffffffu, count[0], 0, kQueryLanes);
-    const uint32_t s0 = __shfl_sync(0xffffffffu, start[0], 0, kQueryLanes);
+    uint32_t s0 = 0u, c0 = 0u;
+    if (searchable) probe_voxel(a.hash, a.hash_mask, pack_key(cx, cy, cz), s0, c0);
     scan_bucket(0, s0, c0);
   }
   double bound = best;
 #pragma unroll
   for (int off = kQueryLanes / 2; off > 0; off >>= 1)
     bound = fmin(bound, __shfl_xor_sync(0xffffffffu, bound, off));
-  // squared distance from the query to the box of each of this lane's voxels, shrunk by a
+
+  // (2) squared distance from the query to the box of each of this lane's voxels, shrunk by a
   // safety margin that covers the rounding of floor(x / w) at the voxel faces.  All shifts
   // are -1 / 0 / +1 per axis, so the per-axis terms are the distances to the two faces of
   // the centre voxel - computed once per query, then three selects per voxel.
-  unsigned survivors = 0; // bit v: voxel with shift rank v of this group's query must be scanned
   constexpr unsigned kGroupMask = kQueryLanes == 32 ? 0xffffffffu : ((1u << (kQueryLanes & 31)) - 1u);
   double face2[3][2]; // [axis][0: towards -1, 1: towards +1], squared, margin applied
   {
-    const double w = a.voxel_width;
     const double qq[3] = {wx, wy, wz};
     const int cc[3] = {cx, cy, cz};
 #pragma unroll
@@ -381,36 +400,48 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
       face2[k][1] = dp * dp;
     }
   }
+  unsigned survivors = 0; // bit v: the voxel with shift rank v of this group's query must be searched
+  bool keep[kVox];
 #pragma unroll
   for (int r = 0; r < kVox; ++r) {
-    const int v = sub + kQueryLanes * r;
-    bool keep = false;
-    if (v > 0 && v < 27 && count[r] > 0) {
+    const int v = sub | (kQueryLanes * r);
+    keep[r] = false;
+    if (searchable && v > 0 && v < 27) {
       double lb = 0.0;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const int sh = lane_shift(v, k);
         lb += sh == 0 ? 0.0 : sh < 0 ? face2[k][0] : face2[k][1];
       }
-      keep = lb <= bound;
+      keep[r] = lb <= bound;
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const unsigned bal = __ballot_sync(0xffffffffu, keep[r]);
     survivors |= ((bal >> (grp * kQueryLanes)) & kGroupMask) << ((kQueryLanes * r) & 31);
   }
-  while (__any_sync(0xffffffffu, survivors != 0u)) {
-    const int b = survivors ? __ffs(survivors) - 1 : 0; // shift rank, ascending
-    survivors &= survivors - 1u;
-    const int r = b / kQueryLanes;
-    uint32_t my_start = start[0], my_count = count[0];
+
+  // (3) compaction: the i-th surviving rank is probed by lane i % kQueryLanes, which leaves the
+  // bucket's {start, count} in shared memory for the whole group
+  const int n_surv = __popc(survivors);
 #pragma unroll
-    for (int rr = 1; rr < kVox; ++rr)
-      if (r == rr) {
-        my_start = start[rr];
-        my_count = count[rr];
-      }
-    const uint32_t sb = __shfl_sync(0xffffffffu, my_start, b % kQueryLanes, kQueryLanes);
-    const uint32_t cb = __shfl_sync(0xffffffffu, my_count, b % kQueryLanes, kQueryLanes);
-    if (b > 0) scan_bucket(b, sb, cb);
+  for (int r = 0; r < kVox; ++r) {
+    const int v = sub | (kQueryLanes * r);
+    if (keep[r]) s_list[warp][grp][__popc(survivors & ((1u << v) - 1u))] = (unsigned char)v;
+  }
+  __syncwarp();
+  for (int i = sub; i < n_surv; i += kQueryLanes) {
+    const int v = s_list[warp][grp][i];
+    uint32_t st = 0u, ct = 0u;
+    probe_voxel(a.hash, a.hash_mask,
+                pack_key(cx + lane_shift(v, 0), cy + lane_shift(v, 1), cz + lane_shift(v, 2)), st, ct);
+    s_bucket[warp][grp][i] = make_uint2(st, ct);
+  }
+  __syncwarp();
+
+  // (4) the survivors' non-empty buckets, one after the other (no warp-wide operation inside:
+  // every group runs its own trip count)
+  for (int i = 0; i < n_surv; ++i) {
+    const uint2 bk = s_bucket[warp][grp][i];
+    if (bk.y) scan_bucket(s_list[warp][grp][i], bk.x, bk.y);
   }
   // arg-min over the group's lanes with the same key
 #pragma unroll
@@ -452,7 +483,7 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
 __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs qa) {
   assoc_nn_body<kLanesSingle>(blockIdx.y == 0 ? pa : qa);
 }
-__global__ void __launch_bounds__(256, 5) assoc_nn_batch_kernel(const AssocArgs *items) {
+__global__ void __launch_bounds__(256, 4) assoc_nn_batch_kernel(const AssocArgs *items) {
   __shared__ AssocArgs s_a;
   load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
   if ((int)(blockIdx.x * queries_per_cta(kLanesBatch)) >= s_a.n_query) return;
