@@ -29,6 +29,10 @@ struct formgpu_batch {
   unsigned char *h_args = nullptr, *d_args = nullptr;
   size_t args_cap = 0, args_used = 0;
   cudaEvent_t ev_args = nullptr;
+  // host scans are uploaded on a side stream while the other groups' kernels of the same
+  // submit run; the extraction kernels (queued last) wait for ev_copy
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr;
   Profiler prof;
   // scratch reused across submits
   std::vector<AssocPlan> assoc_plans;
@@ -45,6 +49,7 @@ struct formgpu_batch {
   // extraction launches with at least this many rows use the many-row kernel variants
   // (kernels.hpp: kManyRowsMin; FORMGPU_MANY_ROWS_MIN overrides it, for tests and tuning)
   int many_rows_min = kManyRowsMin;
+  int assoc_lanes = kAssocLanes; // lanes per query of the batched association kernel (FORMGPU_ASSOC_LANES)
 };
 
 namespace {
@@ -200,6 +205,7 @@ int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size
   b->device = device;
   b->stream = static_cast<cudaStream_t>(stream);
   if (const char *env = std::getenv("FORMGPU_MANY_ROWS_MIN")) b->many_rows_min = std::atoi(env);
+  if (const char *env = std::getenv("FORMGPU_ASSOC_LANES")) b->assoc_lanes = std::atoi(env);
   auto bail = [&](int rc, const std::string &msg) {
     g_batch_error = msg;
     formgpu_batch_destroy(b);
@@ -216,8 +222,11 @@ int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size
     b->own_stream = true;
   }
   b->prof.stream = b->stream;
-  if (cudaEventCreateWithFlags(&b->ev_args, cudaEventDisableTiming) != cudaSuccess)
+  if (cudaEventCreateWithFlags(&b->ev_args, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&b->ev_copy, cudaEventDisableTiming) != cudaSuccess)
     return bail(FORMGPU_ERR_CUDA, "cudaEventCreate failed");
+  if (cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+    return bail(FORMGPU_ERR_CUDA, "cudaStreamCreate failed");
   for (size_t i = 0; i < n_sequences; ++i) {
     formgpu_ctx *c = nullptr;
     const int rc = formgpu_create(p, device, b->stream, &c); // every context shares the batch stream
@@ -242,6 +251,11 @@ void formgpu_batch_destroy(formgpu_batch *b) {
   if (b->d_partials) cudaFree(b->d_partials);
   if (b->d_tickets) cudaFree(b->d_tickets);
   if (b->ev_args) cudaEventDestroy(b->ev_args);
+  if (b->ev_copy) cudaEventDestroy(b->ev_copy);
+  if (b->copy_stream) {
+    cudaStreamSynchronize(b->copy_stream);
+    cudaStreamDestroy(b->copy_stream);
+  }
   b->prof.destroy();
   if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -322,6 +336,8 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
 
   // ---- stage 1 ----
   std::vector<size_t> live_extract;
+  std::function<int()> extract_launcher; // queued after every other group (see copy_stream)
+  bool scans_uploading = false;
   {
     std::vector<ExtractArgs> items;
     for (size_t r : by_op[FORMGPU_OP_EXTRACT]) {
@@ -344,7 +360,8 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       bool host_records = false;
       if (!on_device) {
         BATCH_CUDA(b, cudaMemcpyAsync(ctx->d_scan, q.scan, q.n_points * sizeof(float4),
-                                      cudaMemcpyHostToDevice, b->stream));
+                                      cudaMemcpyHostToDevice, b->copy_stream));
+        scans_uploading = true;
         scan_dev = ctx->d_scan;
         extract_direct_targets(ctx, q.planar_out, q.planar_cap, q.point_out, q.point_cap, dp, dq);
         host_records = dp == nullptr && (q.planar_out || q.point_out);
@@ -361,11 +378,13 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       if (rc) return rc;
       const ExtractArgs shape = items[0];
       const int n_items = (int)items.size();
-      launchers.push_back([=]() -> int {
+      if (scans_uploading) BATCH_CUDA(b, cudaEventRecord(b->ev_copy, b->copy_stream));
+      extract_launcher = [=]() -> int {
+        if (scans_uploading) BATCH_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_copy, 0));
         extract_batch_launch(shape, staged<ExtractArgs>(b, off), n_items, b->many_rows_min, b->stream, b->prof);
         BATCH_CUDA(b, cudaGetLastError());
         return FORMGPU_OK;
-      });
+      };
     }
   }
 
@@ -492,7 +511,7 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       if (rc) return rc;
       const int n_items = (int)aitems.size() / 2;
       launchers.push_back([=]() -> int {
-        assoc_batch_launch(staged<AssocArgs>(b, off_a), n_items, max_query, b->stream, b->prof);
+        assoc_batch_launch(staged<AssocArgs>(b, off_a), n_items, max_query, b->assoc_lanes, b->stream, b->prof);
         segment_build_batch_launch(staged<SegmentArgs>(b, off_s), n_items, max_query, b->stream, b->prof);
         BATCH_CUDA(b, cudaGetLastError());
         return FORMGPU_OK;
@@ -584,6 +603,10 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
     BATCH_CUDA(b, cudaMemcpyAsync(b->d_args, b->h_args, b->args_used, cudaMemcpyHostToDevice, b->stream));
   for (auto &launch : launchers) {
     const int rc = launch();
+    if (rc) return rc;
+  }
+  if (extract_launcher) {
+    const int rc = extract_launcher();
     if (rc) return rc;
   }
   BATCH_CUDA(b, cudaEventRecord(b->ev_args, b->stream));

@@ -53,7 +53,7 @@ void extract_launch(const ExtractArgs &a, int n_scans, cudaStream_t stream, Prof
 /// device memory); `shape` supplies the common geometry.
 /// Launches with at least `many_rows_min` rows (rows x items) use the many-row variants: 128-thread
 /// select CTAs and the thread-per-pick normals kernel, which trade per-row latency for rows in flight.
-constexpr int kManyRowsMin = 2 * 148 + 1;
+constexpr int kManyRowsMin = 1; // measured: +5 % batched throughput over switching at 2 x 148 rows
 void extract_batch_launch(const ExtractArgs &shape, const ExtractArgs *items_dev, int n_items,
                           int many_rows_min, cudaStream_t stream, Profiler &prof);
 
@@ -107,7 +107,10 @@ struct AssocArgs {
   uint32_t *hist_cnt;      // [blocks256][W+1] atomic counters, zero on entry
 };
 void assoc_launch(const AssocArgs &planar, const AssocArgs &point, cudaStream_t stream, Profiler &prof);
-void assoc_batch_launch(const AssocArgs *items_dev, int n_items, int max_query, cudaStream_t stream,
+/// `lanes` = lanes that share one query in the batched kernel (2, 4 or 8; kAssocLanes by default,
+/// FORMGPU_ASSOC_LANES overrides it per batch for tuning).
+constexpr int kAssocLanes = 4;
+void assoc_batch_launch(const AssocArgs *items_dev, int n_items, int max_query, int lanes, cudaStream_t stream,
                         Profiler &prof);
 
 struct SegmentArgs {

@@ -631,11 +631,29 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
     if (lane == 0) tickets[me.task] = 0u; // self-cleaning for the next launch
     __threadfence();
     const double *all = partials + (size_t)me.first * 56;
-    for (int e = lane; e < 56; e += 32) {
-      double v = 0.0;
-      for (int r = 0; r < n_slices; ++r) v += __ldcg(&all[(size_t)r * 56 + e]); // slice order: deterministic
-      S.sum[e / 28][e % 28] = v;
+    // slice order (deterministic); eight loads in flight per step - a pair of 40 slices is 5
+    // L2 round trips on the launch's critical path instead of 40
+    double v0 = 0.0, v1 = 0.0; // elements lane and lane + 32
+    int r = 0;
+    for (; r + 8 <= n_slices; r += 8) {
+      double t0[8], t1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        t0[u] = __ldcg(&all[(size_t)(r + u) * 56 + lane]);
+        t1[u] = lane < 24 ? __ldcg(&all[(size_t)(r + u) * 56 + 32 + lane]) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        v0 += t0[u];
+        v1 += t1[u];
+      }
     }
+    for (; r < n_slices; ++r) {
+      v0 += __ldcg(&all[(size_t)r * 56 + lane]);
+      if (lane < 24) v1 += __ldcg(&all[(size_t)r * 56 + 32 + lane]);
+    }
+    S.sum[lane / 28][lane % 28] = v0;
+    if (lane < 24) S.sum[(32 + lane) / 28][(32 + lane) % 28] = v1;
   }
   __syncwarp();
   build_basis<true>(S.exp, rel); // starts with a __syncwarp

@@ -310,7 +310,7 @@ __device__ __forceinline__ void probe_voxel(const HashSlot *hash, uint32_t mask,
 
 // A single sequence's call (20 k queries) cannot fill the GPU either way and is latency-
 // bound, so it keeps 32 lanes per query (shortest bucket scans); batched launches use 8.
-constexpr int kLanesSingle = 32, kLanesBatch = 4;
+constexpr int kLanesSingle = 32;
 __host__ __device__ constexpr int queries_per_cta(int lanes) { return 8 * (32 / lanes); } // 256 threads
 
 namespace {
@@ -355,19 +355,15 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
   // the group scans a bucket together, kQueryLanes consecutive 32-byte points per step; a lane
   // requests its next kDepth points before it looks at the first
   auto scan_bucket = [&](int b, uint32_t sb, uint32_t cb) {
-    for (uint32_t i = sub; i < cb; i += kDepth * kQueryLanes) {
+    uint32_t i = sub;
+    for (; i + (kDepth - 1) * kQueryLanes < cb; i += kDepth * kQueryLanes) {
       WorldPoint p[kDepth];
 #pragma unroll
-      for (int u = 0; u < kDepth; ++u) {
-        const uint32_t iu = i + u * kQueryLanes;
-        p[u] = load_world(a.world + sb + (iu < cb ? iu : i));
-      }
+      for (int u = 0; u < kDepth; ++u) p[u] = load_world(a.world + sb + i + u * kQueryLanes);
 #pragma unroll
-      for (int u = 0; u < kDepth; ++u) {
-        const uint32_t iu = i + u * kQueryLanes;
-        if (u == 0 || iu < cb) consider(p[u], sb + iu, b);
-      }
+      for (int u = 0; u < kDepth; ++u) consider(p[u], sb + i + u * kQueryLanes, b);
     }
+    for (; i < cb; i += kQueryLanes) consider(load_world(a.world + sb + i), sb + i, b);
   };
 
   // (1) centre voxel: every lane of the group probes the same slot (one broadcast load)
@@ -483,11 +479,12 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
 __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs qa) {
   assoc_nn_body<kLanesSingle>(blockIdx.y == 0 ? pa : qa);
 }
+template <int kQueryLanes>
 __global__ void __launch_bounds__(256, 4) assoc_nn_batch_kernel(const AssocArgs *items) {
   __shared__ AssocArgs s_a;
   load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
-  if ((int)(blockIdx.x * queries_per_cta(kLanesBatch)) >= s_a.n_query) return;
-  assoc_nn_body<kLanesBatch>(s_a);
+  if ((int)(blockIdx.x * queries_per_cta(kQueryLanes)) >= s_a.n_query) return;
+  assoc_nn_body<kQueryLanes>(s_a);
 }
 
 void assoc_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream, Profiler &prof) {
@@ -499,12 +496,16 @@ void assoc_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream,
   prof.end(FORMGPU_KG_ASSOC_NN, 1);
 }
 
-void assoc_batch_launch(const AssocArgs *items_dev, int n_items, int max_query, cudaStream_t stream,
+void assoc_batch_launch(const AssocArgs *items_dev, int n_items, int max_query, int lanes, cudaStream_t stream,
                         Profiler &prof) {
   if (n_items <= 0 || max_query <= 0) return;
   prof.begin(FORMGPU_KG_ASSOC_NN);
-  constexpr int per_cta = queries_per_cta(kLanesBatch);
-  assoc_nn_batch_kernel<<<dim3((max_query + per_cta - 1) / per_cta, 2, n_items), 256, 0, stream>>>(items_dev);
+  const auto grid = [&](int per_cta) { return dim3((max_query + per_cta - 1) / per_cta, 2, n_items); };
+  switch (lanes) {
+  case 2: assoc_nn_batch_kernel<2><<<grid(queries_per_cta(2)), 256, 0, stream>>>(items_dev); break;
+  case 8: assoc_nn_batch_kernel<8><<<grid(queries_per_cta(8)), 256, 0, stream>>>(items_dev); break;
+  default: assoc_nn_batch_kernel<4><<<grid(queries_per_cta(4)), 256, 0, stream>>>(items_dev); break;
+  }
   prof.end(FORMGPU_KG_ASSOC_NN, 1);
 }
 
