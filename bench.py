@@ -143,12 +143,14 @@ def algorithmic_bytes(s: dict, group: str) -> float:
     return 0.0  # map_build / commit: the replay does not count their units
 
 
-# DRAM bytes actually moved per algorithmic byte, from the committed `ncu --set full` capture
-# of the batched kernels (profiles/r01b_ncu_full_metrics.txt: dram__bytes_read.sum +
-# dram__bytes_write.sum of a launch / its algorithmic bytes).  assoc_nn: 58.2 MB for 700 416
-# queries (358.6 MB algorithmic) - hash slots and buckets are shared between queries and hit
-# L2; lin_chunk: 51.9 MB for 49.5 MB of correspondences (sector granularity at slice edges).
-NCU_TRAFFIC_RATIO = {"assoc_nn": 0.162, "lin_chunk": 1.05}
+# DRAM bytes actually moved per algorithmic byte, from the committed `ncu --set full` captures
+# of the batched kernels (dram__bytes_read.sum + dram__bytes_write.sum of a launch / its
+# algorithmic bytes).  assoc_nn (profiles/r02_ncu_full_metrics.txt): 9.06 MB for 147 456
+# queries (75.5 MB algorithmic) - hash slots and buckets are shared between queries and hit
+# L1/L2, and only the centre voxel plus the few unpruned neighbours are probed at all;
+# lin_chunk (profiles/r01b_ncu_full_metrics.txt): 51.9 MB for 49.5 MB of correspondences
+# (sector granularity at slice edges).
+NCU_TRAFFIC_RATIO = {"assoc_nn": 0.120, "lin_chunk": 1.05}
 
 
 def whole_step_bytes(s: dict) -> float:
@@ -330,7 +332,8 @@ def run_ours(args, rank, world, local_rank):
             "traffic": (round(NCU_TRAFFIC_RATIO[dom] * kg[dom]["algorithmic_MB_per_launch"] * 1e6)
                         if dom in NCU_TRAFFIC_RATIO else None),
             "traffic_source": "ncu dram bytes per algorithmic byte of this kernel (profiles/"
-                              "r01b_ncu_full_metrics.txt) x this run's algorithmic bytes per launch",
+                              "r02_ncu_full_metrics.txt, r01b_ncu_full_metrics.txt) x this run's "
+                              "algorithmic bytes per launch",
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": round(kg[dom]["algorithmic_MB_per_launch"] * 1e6),
             "avg_launch_us": kg[dom]["avg_launch_us"], "launches": kg[dom]["launches"],

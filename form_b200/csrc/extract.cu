@@ -402,10 +402,11 @@ __device__ __forceinline__ void neighbor_counts(const float4 *rowp, int c, int n
 // find_closest (extraction.tpp:402-420), rule R2: arg-min (dist2, column) over the valid
 // points of one row.  The reference scans the whole row for every pick; here the row's
 // 32-column chunks carry the bounding box of their valid points (written by the select
-// kernel) and a chunk is evaluated only if its box can hold a point at least as close as
-// the best of the nearest chunk.  The pruning is exact: the float squared distance the
+// kernel).  The chunk at the pick's own azimuth is evaluated first (on an organised scan the
+// closest point is nearly always there); any other chunk is evaluated only if its box can hold
+// a point at least as close.  The pruning is exact: the float squared distance the
 // reference computes differs from the true one by a few ulp, the box distance computed
-// here likewise, and a chunk is skipped only when its bound exceeds the seed's best by a
+// here likewise, and a chunk is skipped only when its bound exceeds the best so far by a
 // 1e-5 relative margin - so every skipped point loses the (dist2, column) comparison.
 __device__ __forceinline__ float box_dist2(const float4 lo, const float4 hi, const float4 p) {
   const float dx = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.0f);

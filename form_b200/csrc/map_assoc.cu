@@ -13,10 +13,12 @@
 //     (linear probing, 64-bit CAS insert, load factor <= 0.5), and
 //   * the world points (32 B: x, y, z f64 + tie-break id) stored contiguously
 //     per voxel (CSR), so a bucket scan is a run of whole 32-byte sectors.
-// Search is warp-cooperative: one warp per query, lane l < 27 probes the
-// neighbour voxel with the reference's shift l (map.tpp:54-68) and scans its
-// bucket; a shuffle arg-min with the key (dist^2, shift rank, scan, k)
-// implements rule R5 (identical to the reference's strict-< visiting order).
+// Search is cooperative: a group of lanes (32 for a single sequence, 4 by default in batched
+// submits) shares one query - it scans the centre voxel's bucket together, bounds the distance to
+// the 26 neighbour voxels of the reference's shift table (map.tpp:54-68) from the six faces of
+// the centre voxel, probes only the voxels that can still hold a closer point and scans their
+// buckets; a shuffle arg-min with the key (dist^2, shift rank, scan, k) implements rule R5
+// (identical to the reference's strict-< visiting order).
 #include "ctx.hpp"
 #include "kernels.hpp"
 

@@ -15,17 +15,21 @@ for r in rows[1:]:
 agg = collections.defaultdict(list)
 for (_, name), m in launches.items():
     agg[name].append(m)
-print(f"{'kernel':34s} {'n':>4s} {'us/launch':>9s} {'tot_ms':>7s} {'Minst':>7s} {'inst/thr-blk':>10s} {'issue%':>6s} {'warps%':>6s} {'lanes':>5s} {'fp64%':>5s} {'L1hit':>5s} {'L2hit':>5s} {'dramMB':>7s}")
+have_mem = any("dram__bytes_read.sum" in m for ms in agg.values() for m in ms)
+print(f"{'kernel':34s} {'n':>4s} {'us/launch':>9s} {'tot_ms':>7s} {'Minst':>7s} {'inst/CTA':>9s} {'issue%':>6s} {'warps%':>6s} {'lanes':>5s}"
+      + (f" {'fp64%':>5s} {'L1hit':>5s} {'L2hit':>5s} {'dramMB':>7s}" if have_mem else ""))
 for name, ms in sorted(agg.items(), key=lambda kv: -sum(m["gpu__time_duration.sum"] for m in kv[1])):
     n = len(ms)
     t = sum(m["gpu__time_duration.sum"] for m in ms)
-    unit_ns = t > 1e5  # ncu reports ns or us depending on version
-    tus = t / 1e3 if unit_ns else t
+    tus = t / 1e3  # ncu reports gpu__time_duration in ns in --csv mode
     inst = sum(m["smsp__inst_executed.sum"] for m in ms)
     blocks = sum(m["launch__grid_size"] for m in ms)
     w = lambda key: sum(m.get(key, 0) * m["gpu__time_duration.sum"] for m in ms) / t
-    dram = sum(m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0) for m in ms)
-    print(f"{name[:34]:34s} {n:4d} {tus / n:9.1f} {tus / 1e3:7.2f} {inst / 1e6:7.1f} {inst / blocks:10.0f} "
-          f"{w('smsp__issue_active.avg.pct_of_peak_sustained_active'):6.1f} {w('sm__warps_active.avg.pct_of_peak_sustained_active'):6.1f} "
-          f"{w('smsp__thread_inst_executed_per_inst_executed.ratio'):5.1f} {w('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active'):5.1f} "
-          f"{w('l1tex__t_sector_hit_rate.pct'):5.1f} {w('lts__t_sector_hit_rate.pct'):5.1f} {dram / n / 1e6:7.2f}")
+    line = (f"{name[:34]:34s} {n:4d} {tus / n:9.1f} {tus / 1e3:7.2f} {inst / 1e6:7.1f} {inst / blocks:9.0f} "
+            f"{w('smsp__issue_active.avg.pct_of_peak_sustained_active'):6.1f} {w('sm__warps_active.avg.pct_of_peak_sustained_active'):6.1f} "
+            f"{w('smsp__thread_inst_executed_per_inst_executed.ratio'):5.1f}")
+    if have_mem:
+        dram = sum(m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0) for m in ms)
+        line += (f" {w('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active'):5.1f} {w('l1tex__t_sector_hit_rate.pct'):5.1f} "
+                 f"{w('lts__t_sector_hit_rate.pct'):5.1f} {dram / n / 1e6:7.2f}")
+    print(line)
