@@ -55,6 +55,15 @@ METRIC = "scans/sec (feature+assoc+linearize hot path)"
 DTYPE = "f32 index arithmetic, f64 transforms/normal equations"
 
 
+def host_cores() -> int:
+    """Host cores this process may run on (affinity-aware: a rank pinned to a share of the box,
+    or `taskset`, sees that share)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -191,7 +200,8 @@ def run_ours(args, rank, world, local_rank):
     n_points = rows * cols
     W, K = args.warmup, args.steps
     S = W + K
-    cores = os.cpu_count() or 1
+    cores = host_cores()
+    sched_cores = args.emulate_cores if args.emulate_cores > 0 else cores  # cores of the timed region
     M = args.sequences_per_gpu
     if M <= 0:
         # auto: 128 sequences keep the GPU ~8 % busier than 64 (measured), but their scans take
@@ -200,7 +210,16 @@ def run_ours(args, rank, world, local_rank):
 
         need_128 = 128 * S * n_points * 16
         M = 128 if psutil.virtual_memory().available / max(world, 1) >= 4 * need_128 else 64
-    G = max(1, min(args.batches_per_gpu, M, max(1, cores // max(world, 1) - 1)))
+    # one host thread per batch, each mostly polling for its round's results: with a core per
+    # thread they spin; when a rank has fewer than 4 spare cores (8 ranks on a 16-core box) it
+    # still runs --yield-batches batches and the polling loops yield (FORMGPU_YIELD_WAIT, api.cu
+    # poll_relax); measured on 2 cores, 32 sequences: 1 spinning batch 2227 scans/s, 4 yielding
+    # batches 4280, 8 yielding batches 4807
+    spare = max(1, sched_cores // max(world, 1) - 1)
+    yield_wait = spare < 4
+    if yield_wait:
+        os.environ["FORMGPU_YIELD_WAIT"] = "1"  # read at the library's first poll
+    G = max(1, min(args.batches_per_gpu, M, spare if not yield_wait else args.yield_batches))
     p = _capi.default_est_params(rows, cols, record_trace=1, device=local_rank)
     pool = ThreadPoolExecutor(max_workers=max(1, min(16, cores // max(world, 1))))
 
@@ -272,6 +291,8 @@ def run_ours(args, rank, world, local_rank):
             r_.close()
         return t_dev, t_host, st, launches
 
+    if args.emulate_cores > 0:  # development aid: the timed legs run on a share of the box's cores
+        os.sched_setaffinity(0, sorted(os.sched_getaffinity(0))[: args.emulate_cores])
     # ---- value: scans resident in HBM ----
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -362,6 +383,7 @@ def run_ours(args, rank, world, local_rank):
                             f"advanced in lock step (formgpu_batch_submit), {G} concurrent batches",
                 "sensor": args.sensor, "rows": rows, "cols": cols, "scans_per_sequence": S,
                 "sequences_per_gpu": M, "batches_per_gpu": G, "sequences": world * M,
+                "host_wait": "yield (fewer spare host cores than batches)" if yield_wait else "spin",
                 "step": "hot-path calls of one scan of one sequence, replayed from the recorded pipeline "
                         "trace; `steps` timed scans per sequence after `warmup` untimed ones",
                 "l2": f"inputs larger than L2: every round touches {M} scans + {M} maps (> 126 MB); no flush",
@@ -502,7 +524,7 @@ def cpu_single_sequence(rows, cols, W, last, scans):
 
 
 def cpu_baseline_multi(args, rows, cols, W, S, host_np):
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     last = min(S, W + max(1, args.cpu_sample))
     n = last - W
     workers = min(cores, len(host_np))
@@ -528,7 +550,7 @@ def run_reference(args, rank, world):
     rows, cols = synth.shape(args.sensor)
     W, K = args.warmup, args.steps
     S = W + K
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     workers = cores if args.sequences_per_gpu <= 0 else min(cores, args.sequences_per_gpu)
     # bounded sample: the CPU needs ~0.2 s per scan and core
     last = min(S, W + max(1, min(K, args.cpu_sample)))
@@ -570,6 +592,11 @@ def main():
     ap.add_argument("--sequences-per-gpu", type=int, default=0,
                     help="independent sequences sharing one GPU (0 = 128 if host memory allows, else 64)")
     ap.add_argument("--only-value", action="store_true", help="development: only the device-resident leg")
+    ap.add_argument("--yield-batches", type=int, default=8,
+                    help="batches per GPU when the rank has fewer than 4 spare host cores (yielding waits)")
+    ap.add_argument("--emulate-cores", type=int, default=0,
+                    help="development: restrict the timed legs to this many host cores (what a rank "
+                         "gets on a box with few cores per GPU)")
     ap.add_argument("--batches-per-gpu", type=int, default=16,
                     help="the sequences of a GPU are split over this many concurrent batches")
     args = ap.parse_args()

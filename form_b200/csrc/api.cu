@@ -1,6 +1,9 @@
 // C-ABI (include/formgpu.h): lifecycle, instrumentation and stage 1.
 #include "api_common.hpp"
 
+#include <sched.h>
+#include <cstdlib>
+
 #include <algorithm>
 #include <new>
 
@@ -68,10 +71,19 @@ int wait_flag(formgpu_ctx *ctx, int which, unsigned long long seq) {
       if (e != cudaErrorNotReady)
         return fail(ctx, FORMGPU_ERR_CUDA, std::string("kernel failed: ") + cudaGetErrorString(e));
     }
-#if defined(__x86_64__)
-    __builtin_ia32_pause();
-#endif
+    poll_relax(spins);
   }
+}
+
+void poll_relax(unsigned spins) {
+  static const bool yield_wait = [] {
+    const char *e = std::getenv("FORMGPU_YIELD_WAIT");
+    return e && e[0] == '1';
+  }();
+  if (yield_wait && (spins & 63u) == 63u) sched_yield();
+#if defined(__x86_64__)
+  __builtin_ia32_pause();
+#endif
 }
 
 } // namespace formgpu

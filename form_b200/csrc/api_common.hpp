@@ -45,6 +45,12 @@ inline int find_slot(const formgpu_ctx *ctx, uint64_t scan) {
 /// stream state every few thousand polls so a faulted kernel cannot hang the caller.
 int wait_flag(formgpu_ctx *ctx, int which, unsigned long long seq);
 
+/// One step of a result-polling loop: a pause, and - when FORMGPU_YIELD_WAIT=1 (more polling
+/// host threads than cores, e.g. several batches per GPU on a box with two cores per GPU) - a
+/// sched_yield() every 64 polls, so that a thread which is only waiting hands its core to one
+/// that has a submit to build.  Without the variable the loop never enters the kernel.
+void poll_relax(unsigned spins);
+
 /// Stage 3 building blocks (api_stage3.cu), also used by the fused association call.
 void relative_pose(const formgpu_pose &Ti, const formgpu_pose &Tj, double rel[12]);
 /// Launch one cluster per task (no wait).  Assigns and returns the sequence number.

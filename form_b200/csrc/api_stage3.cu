@@ -95,9 +95,7 @@ int lin_wait(formgpu_ctx *ctx, const int *out_indices, size_t n, unsigned long l
           if (err != cudaErrorNotReady)
             return fail(ctx, FORMGPU_ERR_CUDA, std::string("linearize kernel failed: ") + cudaGetErrorString(err));
         }
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
+        poll_relax(spins);
       }
       const unsigned long long bits = (lo & 0xffffffffull) | (hi << 32);
       std::memcpy(&dst[k * per_pair + e], &bits, sizeof(double));
