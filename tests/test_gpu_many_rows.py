@@ -1,8 +1,9 @@
-"""Many-row extraction kernels (128-thread select CTAs, thread-per-pick normals): batched
-launches with hundreds of rows switch to them (kernels.hpp: kManyRowsMin).  The batch tests use
-small scans, so here FORMGPU_MANY_ROWS_MIN=1 forces the variants for every launch and the
-keypoints - normals included - are compared bit for bit with the CPU oracle on the synthetic
-sensor shapes, parameter variants and the edge-case scans of test_gpu_extract."""
+"""Kernel variants that only batched submits use.  Many-row extraction kernels (128-thread select
+CTAs, thread-per-pick normals; kernels.hpp: kManyRowsMin, FORMGPU_MANY_ROWS_MIN) and the lanes
+per query of the batched association kernel (kAssocLanes, FORMGPU_ASSOC_LANES): keypoints -
+normals included - are compared bit for bit with the CPU oracle on the synthetic sensor shapes,
+parameter variants and the edge-case scans of test_gpu_extract; association counters with the
+single-sequence path."""
 import ctypes as C
 import zlib
 
@@ -86,9 +87,9 @@ def test_many_row_kernels_edge_cases(many_rows, shape):
     _batch_extract_vs_oracle(params, scans, rows, cols)
 
 
-def test_default_threshold_switches_on_a_large_batch():
-    """Without the override a 5 x 64-row batch (320 rows) takes the many-row kernels and a single
-    scan the few-row ones: both must give the oracle's bytes."""
+def test_large_and_single_scan_batches_match_oracle():
+    """Default threshold (kManyRowsMin): a 5 x 64-row batch and a single-scan batch both give the
+    oracle's bytes."""
     rows, cols = synth.shape("os1-64")
     params = _capi.default_params(rows, cols)
     scans = [synth.scan("os1-64", s, 9) for s in range(5)]
@@ -124,3 +125,15 @@ def test_association_lane_variants_match_single_contexts(monkeypatch, lanes):
                 assert abs(got[k] - ref[k]) <= 1e-12 * abs(ref[k]), (lanes, s, k, got[k], ref[k])
             else:
                 assert got[k] == ref[k], (lanes, s, k, got[k], ref[k])
+
+
+def test_few_row_variants_still_match_oracle(monkeypatch):
+    """FORMGPU_MANY_ROWS_MIN above the launch's row count selects the latency-shaped variants
+    (512-thread select CTAs, warp-per-pick normals on four CTAs per row) for a batched submit."""
+    monkeypatch.setenv("FORMGPU_MANY_ROWS_MIN", "1000000")
+    rows, cols = synth.shape("os1-64")
+    params = _capi.default_params(rows, cols)
+    _batch_extract_vs_oracle(params, [synth.scan("os1-64", s, 9) for s in range(3)], rows, cols)
+    rng = np.random.default_rng(11)
+    params = _capi.default_params(7, 333)
+    _batch_extract_vs_oracle(params, [_random_scan(rng, 7, 333, k) for k in ("ties", "dropouts", "noise")], 7, 333)
