@@ -261,10 +261,12 @@ __device__ __forceinline__ int match_bin(const MatchRec &m, double max_d2) {
 }
 
 
-// Eight lanes per query, four queries per warp.  Every instruction of the per-query setup
-// (f64 transform, voxel key, hashing) then serves four queries instead of one - the
-// one-warp-per-query version was issue-bound on exactly that redundant work (ncu: 67 %
-// issue-active, 420 warp instructions per query).
+// A few lanes per query (kQueryLanes: 4 by default in batched submits, i.e. eight queries per
+// warp).  Every instruction of the per-query setup (f64 transform, voxel key, hashing, face
+// distances, arg-min) then serves several queries instead of one - the one-warp-per-query
+// version was issue-bound on exactly that redundant work (ncu: 67 % issue-active, 420 warp
+// instructions per query; 121 with four lanes).  Fewer lanes also mean longer per-lane bucket
+// scans whose lengths diverge across the warp: two lanes measured 2 % slower than four.
 //
 // Order of the search: (1) the group probes the CENTRE voxel and scans its bucket together;
 // (2) every lane bounds the squared distance from the query to the boxes of its share of the 26
@@ -311,7 +313,7 @@ __device__ __forceinline__ void probe_voxel(const HashSlot *hash, uint32_t mask,
 }
 
 // A single sequence's call (20 k queries) cannot fill the GPU either way and is latency-
-// bound, so it keeps 32 lanes per query (shortest bucket scans); batched launches use 8.
+// bound, so it keeps 32 lanes per query (shortest bucket scans); batched launches use kAssocLanes.
 constexpr int kLanesSingle = 32;
 __host__ __device__ constexpr int queries_per_cta(int lanes) { return 8 * (32 / lanes); } // 256 threads
 
