@@ -86,6 +86,49 @@ def stats_for(name, map_pts, queries, w):
           f"{np.median(best_d) * 100:.1f} cm, p90 {np.percentile(best_d, 90) * 100:.1f} cm")
 
 
+def subcell_model(name, map_pts, queries, w, n_sub=4):
+    """What a sub-voxel ordering of the buckets would buy: every voxel's points grouped by an
+    n_sub^3 cell code; a query scans its own cell, then every cell (of the 27 voxels) whose box is
+    at most as far as the best so far, nearest first.  Reports candidates and cells per query and
+    checks that the result is the brute-force nearest neighbour of the 27 voxels."""
+    cw = w / n_sub
+    vox = np.floor(map_pts / w).astype(np.int64)
+    cell = np.clip(np.floor((map_pts - vox * w) / cw).astype(np.int64), 0, n_sub - 1)
+    fine = vox * n_sub + cell  # global fine-cell coordinates
+    cells = {}
+    for i, f in enumerate(map(tuple, fine)):
+        cells.setdefault(f, []).append(i)
+    cells = {f: map_pts[np.array(ix)] for f, ix in cells.items()}
+    rng = np.arange(-n_sub, 2 * n_sub)  # fine cells of the 3x3x3 voxel block, relative to the voxel
+    rel = np.stack(np.meshgrid(rng, rng, rng, indexing="ij"), axis=-1).reshape(-1, 3)
+    cand, visited, wrong = [], [], 0
+    for q in queries:
+        k = np.floor(q / w).astype(np.int64)
+        base = k * n_sub
+        lo = (base + rel) * cw
+        d = np.maximum(np.maximum(lo - q, q - (lo + cw)), 0.0)
+        lb = (d * d).sum(axis=1)
+        best, n_c, n_v = np.inf, 0, 0
+        for j in np.argsort(lb, kind="stable"):
+            if lb[j] > best:
+                break
+            pts = cells.get(tuple(base + rel[j]))
+            if pts is None:
+                continue
+            n_v += 1
+            n_c += len(pts)
+            best = min(best, ((pts - q) ** 2).sum(axis=1).min())
+        # brute force over the 27 voxels
+        m = np.all(np.abs(vox - k) <= 1, axis=1)
+        ref = ((map_pts[m] - q) ** 2).sum(axis=1).min() if m.any() else np.inf
+        wrong += int(best != ref)
+        cand.append(n_c)
+        visited.append(n_v)
+    print(f"[{name}] with {n_sub}^3 sub-cells of {cw * 100:.0f} cm: candidates per query {np.mean(cand):.1f} "
+          f"(p90 {np.percentile(cand, 90):.0f}), non-empty cells visited {np.mean(visited):.2f} "
+          f"(p90 {np.percentile(visited, 90):.0f}); results differing from brute force: {wrong}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sensor", default="os0-128")
@@ -117,6 +160,8 @@ def main():
                 if len(q) > args.sample:
                     q = q[rng.choice(len(q), args.sample, replace=False)]
                 stats_for(("planar", "point")[t], mp, q, w)
+                for n_sub in (2, 4):
+                    subcell_model(("planar", "point")[t], mp, q[: args.sample // 4], w, n_sub)
         o.commit_scan()
 
 
