@@ -1,4 +1,4 @@
-"""CPU models of two transformations the CUDA kernels apply to the reference's algorithm,
+"""CPU models of transformations the CUDA kernels apply to the reference's algorithm,
 checked against the reference's own sequential form on random and adversarial inputs
 (the GPU parity tests check the kernels themselves; these pin the REASONING they rest on):
 
@@ -9,7 +9,12 @@ checked against the reference's own sequential form on random and adversarial in
 * map_assoc.cu, voxel_coord: floor(v * fl(1 / w)) with a fall-back to the IEEE division when the
   product is within 8.9e-16 (|q| + 1) of an integer must equal floor(fl(v / w)) always
   (/root/reference/form/mapping/map.tpp:34-38).
+* blueprint of the NEXT association kernel (not built yet): buckets ordered by a 4x4x4 cell
+  code, own cell + adjacent cells by box bound, whole-voxel fall-back - must give the rule-R5
+  arg-min of the 27-voxel search (/root/reference/form/mapping/map.tpp:54-91) exactly.
 """
+import zlib
+
 import numpy as np
 import pytest
 
@@ -187,3 +192,153 @@ def test_voxel_coord_fast_path_is_exact(w):
     # the fall-back really is rare away from the faces
     rnd = rng.uniform(-1e5, 1e5, 1_000_000)
     assert voxel_coord_fast(rnd, w)[1].mean() < 1e-6
+
+
+# --------------------------------------------------------------------------- cell-ordered buckets
+# Blueprint of the next association kernel (profiles/assoc_stats.py): every voxel's
+# bucket is ordered by a 4x4x4 cell code; a query scans its own cell, then the adjacent fine cells
+# whose box bound does not exceed the best so far, and falls back to the whole-voxel search (the
+# current kernel) only when the best is not inside the adjacency radius.  The model carries the
+# full rule-R5 key (dist^2, shift rank, tie) and must reproduce the brute-force search of the 27
+# voxels exactly - including ties, points on voxel / cell faces and voxels too small for a table.
+SHIFTS27 = [(0, 0, 0), (1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1),
+            (1, 1, 0), (1, -1, 0), (-1, 1, 0), (-1, -1, 0), (1, 0, 1), (1, 0, -1), (-1, 0, 1),
+            (-1, 0, -1), (0, 1, 1), (0, 1, -1), (0, -1, 1), (0, -1, -1), (1, 1, 1), (1, 1, -1),
+            (1, -1, 1), (1, -1, -1), (-1, 1, 1), (-1, 1, -1), (-1, -1, 1), (-1, -1, -1)]
+RANK = {s: r for r, s in enumerate(SHIFTS27)}
+N_SUB, TABLE_MIN = 4, 16
+
+
+def _dist2(p, q):  # (d0^2 + d2^2) + (d1^2 + 0), the reference's 4-lane order
+    d = p - q
+    return (d[0] * d[0] + d[2] * d[2]) + (d[1] * d[1] + 0.0)
+
+
+def build_cell_map(points, w):
+    """voxel -> {'pts': [(xyz, tie)] ordered by cell code, 'off': 65 offsets or None}."""
+    cw = w / N_SUB
+    vox = {}
+    for tie, p in enumerate(points):
+        v = tuple(int(np.floor(c / w)) for c in p)
+        vox.setdefault(v, []).append((p, tie))
+    out = {}
+    for v, pts in vox.items():
+        if len(pts) < TABLE_MIN:
+            out[v] = dict(pts=pts, off=None)
+            continue
+        code = []
+        for p, _ in pts:
+            rel = p - np.array(v, dtype=np.float64) * w
+            c = [min(max(int(np.floor(r / cw)), 0), N_SUB - 1) for r in rel]
+            code.append((c[0] * N_SUB + c[1]) * N_SUB + c[2])
+        order = sorted(range(len(pts)), key=lambda i: code[i])  # stable: any order inside a cell is fine
+        cnt = np.bincount([code[i] for i in order], minlength=N_SUB ** 3)
+        out[v] = dict(pts=[pts[i] for i in order], off=np.concatenate([[0], np.cumsum(cnt)]))
+    return out
+
+
+def brute_force_r5(cmap, q, w):
+    c = tuple(int(np.floor(x / w)) for x in q)
+    best = (np.inf, 99, 1 << 62)
+    for s in SHIFTS27:
+        b = cmap.get(tuple(c[a] + s[a] for a in range(3)))
+        if b:
+            for p, tie in b["pts"]:
+                best = min(best, (_dist2(p, q), RANK[s], tie))
+    return best
+
+
+def cell_search_r5(cmap, q, w, stats=None):
+    cw = w / N_SUB
+    c = tuple(int(np.floor(x / w)) for x in q)
+    margin = [1e-9 * (1.0 + abs(x)) for x in q]
+    best = (np.inf, 99, 1 << 62)
+    seen_whole = set()  # voxels without a table that were scanned entirely
+    n_cand = 0
+
+    def scan(v, lo, hi):
+        nonlocal best, n_cand
+        s = tuple(v[a] - c[a] for a in range(3))
+        for p, tie in cmap[v]["pts"][lo:hi]:
+            n_cand += 1
+            best = min(best, (_dist2(p, q), RANK[s], tie))
+
+    def visit_cell(f):  # f = global fine-cell coordinates
+        v = tuple(x // N_SUB for x in f)  # floor division: the voxel that holds the fine cell
+        b = cmap.get(v)
+        if b is None:
+            return
+        if b["off"] is None:
+            if v not in seen_whole:
+                seen_whole.add(v)
+                scan(v, 0, len(b["pts"]))
+            return
+        i = [f[a] - v[a] * N_SUB for a in range(3)]
+        code = (i[0] * N_SUB + i[1]) * N_SUB + i[2]
+        scan(v, b["off"][code], b["off"][code + 1])
+
+    def cell_bound(f):
+        lb = 0.0
+        for a in range(3):
+            lo = f[a] * cw
+            gap = max(lo - q[a] - margin[a], q[a] - (lo + cw) - margin[a], 0.0)
+            lb += gap * gap
+        return lb
+
+    rel = [q[a] - c[a] * w for a in range(3)]
+    f0 = tuple(c[a] * N_SUB + min(max(int(np.floor(rel[a] / cw)), 0), N_SUB - 1) for a in range(3))
+    visit_cell(f0)
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dz in (-1, 0, 1):
+                if (dx, dy, dz) == (0, 0, 0):
+                    continue
+                f = (f0[0] + dx, f0[1] + dy, f0[2] + dz)
+                if cell_bound(f) <= best[0]:
+                    visit_cell(f)
+    # every fine cell that is not adjacent to f0 is at least one cell width away along some axis
+    reach = cw - max(margin)
+    if not best[0] < reach * reach:  # fall back to the whole-voxel search of today's kernel
+        if stats is not None:
+            stats["fallback"] = stats.get("fallback", 0) + 1
+        for s in SHIFTS27:
+            v = tuple(c[a] + s[a] for a in range(3))
+            if v in cmap:
+                scan(v, 0, len(cmap[v]["pts"]))
+    if stats is not None:
+        stats["cand"] = stats.get("cand", 0) + n_cand
+        stats["n"] = stats.get("n", 0) + 1
+    return best
+
+
+def _cloud(rng, kind, w):
+    if kind == "surface":  # a wall and a floor through a block of voxels, 3-8 cm spacing
+        n = 3000
+        a = rng.uniform(-1.5 * w, 2.5 * w, (n, 2))
+        wall = np.stack([a[:, 0], np.full(n, 0.31) + 0.01 * rng.standard_normal(n), a[:, 1]], axis=1)
+        floor = np.stack([a[:, 0], a[:, 1], np.full(n, -0.52) + 0.01 * rng.standard_normal(n)], axis=1)
+        return np.concatenate([wall, floor])
+    if kind == "sparse":
+        return rng.uniform(-2 * w, 3 * w, (150, 3))
+    if kind == "lattice":  # points ON voxel and cell faces, many exact distance ties
+        g = np.arange(-8, 13) * (w / 4)
+        x, y, z = np.meshgrid(g, g, g, indexing="ij")
+        pts = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)
+        return np.concatenate([pts, pts[::7]])  # duplicates: the tie id decides
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["surface", "sparse", "lattice"])
+@pytest.mark.parametrize("w", [0.8, 0.3])
+def test_cell_ordered_search_equals_brute_force_r5(kind, w):
+    rng = np.random.default_rng(zlib.crc32(f"{kind}-{w}".encode()))
+    pts = _cloud(rng, kind, w)
+    cmap = build_cell_map(pts, w)
+    stats = {}
+    queries = list(rng.uniform(-1.2 * w, 2.2 * w, (250, 3)))
+    queries += [p + rng.normal(scale=0.03, size=3) for p in pts[rng.choice(len(pts), 250)]]
+    queries += [pts[i].copy() for i in rng.choice(len(pts), 60)]  # exactly on map points / faces
+    for q in queries:
+        assert cell_search_r5(cmap, q, w, stats) == brute_force_r5(cmap, q, w), (kind, w, q)
+    if kind == "surface":  # the point of the exercise: far fewer candidates, rare fall-backs
+        assert stats["fallback"] < 0.45 * stats["n"]
