@@ -342,3 +342,52 @@ def test_cell_ordered_search_equals_brute_force_r5(kind, w):
         assert cell_search_r5(cmap, q, w, stats) == brute_force_r5(cmap, q, w), (kind, w, q)
     if kind == "surface":  # the point of the exercise: far fewer candidates, rare fall-backs
         assert stats["fallback"] < 0.45 * stats["n"]
+
+
+# --------------------------------------------------------------------------- face pruning (today's kernel)
+def face_pruned_search_r5(cmap, q, w):
+    """map_assoc.cu assoc_nn_body as built today: the centre voxel's bucket first, then only the
+    neighbour voxels whose box (bounded from the six face distances of the centre voxel, shrunk by
+    the rounding margin) can still hold a point at least as close."""
+    c = tuple(int(np.floor(x / w)) for x in q)
+    best = (np.inf, 99, 1 << 62)
+
+    def scan(s):
+        nonlocal best
+        b = cmap.get(tuple(c[a] + s[a] for a in range(3)))
+        for p, tie in (b["pts"] if b else []):
+            best = min(best, (_dist2(p, q), RANK[s], tie))
+
+    scan((0, 0, 0))
+    bound = best[0]
+    face2 = []
+    for a in range(3):
+        lo = c[a] * w
+        margin = 1e-9 * (1.0 + abs(q[a])) + 4e-16 * abs(lo)
+        dm, dp = max(q[a] - lo - margin, 0.0), max(lo + w - q[a] - margin, 0.0)
+        face2.append((dm * dm, dp * dp))
+    n_scanned = 0
+    for s in SHIFTS27[1:]:
+        lb = sum(0.0 if s[a] == 0 else face2[a][0] if s[a] < 0 else face2[a][1] for a in range(3))
+        if lb <= bound:  # the bound is the centre's best: it is not tightened between voxels
+            n_scanned += 1
+            scan(s)
+    return best, n_scanned
+
+
+@pytest.mark.parametrize("kind", ["surface", "sparse", "lattice"])
+def test_face_pruned_search_equals_brute_force_r5(kind):
+    w = 0.8
+    rng = np.random.default_rng(zlib.crc32(f"face-{kind}".encode()))
+    pts = _cloud(rng, kind, w)
+    cmap = build_cell_map(pts, w)
+    queries = list(rng.uniform(-1.2 * w, 2.2 * w, (300, 3)))
+    queries += [p + rng.normal(scale=0.03, size=3) for p in pts[rng.choice(len(pts), 300)]]
+    queries += [pts[i].copy() for i in rng.choice(len(pts), 80)]
+    scanned = []
+    for q in queries:
+        got, n = face_pruned_search_r5(cmap, q, w)
+        assert got == brute_force_r5(cmap, q, w), (kind, q)
+        scanned.append(n)
+    if kind == "surface":  # queries near the surfaces (the second group) touch few of the 26 neighbours
+        assert np.mean(scanned[300:600]) < 4
