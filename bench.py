@@ -209,7 +209,8 @@ def run_ours(args, rank, world, local_rank):
         import psutil
 
         need_128 = 128 * S * n_points * 16
-        M = 128 if psutil.virtual_memory().available / max(world, 1) >= 4 * need_128 else 64
+        # (x3 headroom: on a 196 GB box one or two ranks take 128 sequences, four or eight take 64)
+        M = 128 if psutil.virtual_memory().available / max(world, 1) >= 3 * need_128 else 64
     # one host thread per batch, each mostly polling for its round's results: with a core per
     # thread they spin; when a rank has fewer than 4 spare cores (8 ranks on a 16-core box) it
     # still runs --yield-batches batches and the polling loops yield (FORMGPU_YIELD_WAIT, api.cu
