@@ -13,10 +13,10 @@ CXXFLAGS  := -O3 -std=c++17 -fPIC -pthread -ffp-contract=off -Wall -Iinclude -If
 LIBDIR    := form_b200/lib
 OBJDIR    := build/obj
 
-GPU_OBJS  := $(OBJDIR)/extract.o $(OBJDIR)/map_assoc.o $(OBJDIR)/linearize.o $(OBJDIR)/api.o $(OBJDIR)/api_stage2.o $(OBJDIR)/api_stage3.o $(OBJDIR)/api_batch.o
+GPU_OBJS  := $(OBJDIR)/extract.o $(OBJDIR)/map_assoc.o $(OBJDIR)/linearize.o $(OBJDIR)/moments.o $(OBJDIR)/api.o $(OBJDIR)/api_stage2.o $(OBJDIR)/api_stage3.o $(OBJDIR)/api_batch.o
 HOST_SRCS := $(wildcard form_b200/host/src/*.cpp)
 HOST_OBJS := $(HOST_SRCS:form_b200/host/src/%.cpp=$(OBJDIR)/host_%.o)
-CSRC_HDRS := $(wildcard form_b200/csrc/*.hpp) include/formgpu.h
+CSRC_HDRS := $(wildcard form_b200/csrc/*.hpp) $(wildcard form_b200/csrc/*.cuh) include/formgpu.h
 HOST_HDRS := $(wildcard form_b200/host/form/*.hpp) include/formgpu.h
 
 PYTHON    ?= python3

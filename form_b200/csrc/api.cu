@@ -236,6 +236,14 @@ static int create_impl(formgpu_ctx *ctx) {
   }
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_pair, 4 * (W + 1)));
   FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_pair, 0, 4 * (W + 1) * sizeof(uint32_t), ctx->stream));
+  // pair-moment cache + the scratch of the kernel that fills it
+  if (const char *env = std::getenv("FORMGPU_STREAM_LINEARIZE")) ctx->moment_cache = env[0] != '1';
+  ctx->mom_max_units = moment_max_units(ctx->kp_cap + ctx->kq_cap, W);
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_moments, (size_t)W * W * kMomentStride));
+  FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_moments, 0, (size_t)W * W * kMomentStride * sizeof(double), ctx->stream));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_mom_partials, (size_t)ctx->mom_max_units * kMomentPartial));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_mom_tickets, (size_t)W));
+  FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_mom_tickets, 0, W * sizeof(unsigned), ctx->stream));
   ctx->h_pair_table.assign(W * W, PairEntry{0, 0, 0, 0});
   FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_pair), 4 * (W + 1) * sizeof(uint32_t),
                                   cudaHostAllocMapped));
@@ -297,6 +305,7 @@ void formgpu_destroy(formgpu_ctx *ctx) {
   if (ctx->ev_upload) cudaEventDestroy(ctx->ev_upload);
   F(ctx->d_seg_planar); F(ctx->d_seg_point); F(ctx->d_pair);
   F(ctx->d_partials); F(ctx->d_request); F(ctx->d_counters);
+  F(ctx->d_moments); F(ctx->d_mom_partials); F(ctx->d_mom_tickets);
   if (ctx->h_flags) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_flags));
   H(ctx->h_counts); H(ctx->h_planar); H(ctx->h_point); H(ctx->h_upload);
   if (ctx->h_out) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_out));

@@ -50,6 +50,8 @@ struct formgpu_batch {
   // (kernels.hpp: kManyRowsMin; FORMGPU_MANY_ROWS_MIN overrides it, for tests and tuning)
   int many_rows_min = kManyRowsMin;
   int assoc_lanes = kAssocLanes; // lanes per query of the batched association kernel (FORMGPU_ASSOC_LANES)
+  // stage 3 from the pair-moment cache (moments.cu); FORMGPU_STREAM_LINEARIZE=1 streams instead
+  bool moment_cache = true;
 };
 
 namespace {
@@ -139,6 +141,21 @@ int stage_lin_groups(formgpu_batch *b, const std::vector<LinArgs> &ctx_args, con
                      const std::vector<uint32_t> &size_hint, bool error_only,
                      std::vector<std::function<int()>> &launchers) {
   if (tasks.empty()) return FORMGPU_OK;
+  if (b->moment_cache) {
+    // evaluation from the pair-moment cache: one warp per task, nothing is streamed
+    size_t off_ctx = 0, off_tasks = 0;
+    int rc = stage_args(b, ctx_args.data(), ctx_args.size(), &off_ctx);
+    if (rc) return rc;
+    rc = stage_args(b, tasks.data(), tasks.size(), &off_tasks);
+    if (rc) return rc;
+    const int n_tasks = (int)tasks.size();
+    launchers.push_back([=]() -> int {
+      BATCH_CUDA(b, eval_batch_launch(staged<LinArgs>(b, off_ctx), staged<LinTask>(b, off_tasks), n_tasks,
+                                      error_only, b->stream, b->prof));
+      return FORMGPU_OK;
+    });
+    return FORMGPU_OK;
+  }
   std::vector<size_t> order(tasks.size());
   for (size_t t = 0; t < order.size(); ++t) order[t] = t;
   std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return size_hint[x] > size_hint[y]; });
@@ -233,6 +250,7 @@ int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size
     if (rc != FORMGPU_OK) return bail(rc, std::string("formgpu_create: ") + formgpu_last_error(nullptr));
     b->ctx.push_back(c);
   }
+  b->moment_cache = b->ctx[0]->moment_cache;
   b->assoc_plans.resize(n_sequences);
   b->extract_args.resize(n_sequences);
   b->commit_plans.resize(n_sequences);
@@ -305,6 +323,9 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       return bfail(b, FORMGPU_ERR_INVALID_ARG, "formgpu_batch_submit: bad sequence index or op");
     if (seen[q.sequence])
       return bfail(b, FORMGPU_ERR_INVALID_ARG, "formgpu_batch_submit: two requests for one sequence");
+    if (b->ctx[q.sequence]->shard_world > 1)
+      return bfail(b, FORMGPU_ERR_UNSUPPORTED,
+                   "formgpu_batch_submit: point-sharded contexts (formgpu_set_shard) are not batched");
     seen[q.sequence] = 1;
     by_op[q.op].push_back(r);
   }
@@ -437,6 +458,8 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
   {
     std::vector<AssocArgs> aitems;
     std::vector<SegmentArgs> sitems;
+    std::vector<MomentArgs> mitems;
+    int max_units = 0;
     std::vector<LinArgs> lin_ctx;
     std::vector<LinTask> &lin_tasks = b->tasks_scratch;
     std::vector<uint32_t> hints;
@@ -471,6 +494,8 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
         aitems.push_back(plan.aa[1]);
         sitems.push_back(plan.sa[0]);
         sitems.push_back(plan.sa[1]);
+        mitems.push_back(plan.ma);
+        max_units = std::max(max_units, plan.mom_units);
         max_query = std::max(max_query, std::max(plan.nq[0], plan.nq[1]));
         if (plan.fused && !plan.lin_tasks.empty()) {
           LinArgs la;
@@ -504,15 +529,19 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       }
     }
     if (!aitems.empty()) {
-      size_t off_a = 0, off_s = 0;
+      size_t off_a = 0, off_s = 0, off_m = 0;
       int rc = stage_args(b, aitems.data(), aitems.size(), &off_a);
       if (rc) return rc;
       rc = stage_args(b, sitems.data(), sitems.size(), &off_s);
       if (rc) return rc;
+      rc = stage_args(b, mitems.data(), mitems.size(), &off_m);
+      if (rc) return rc;
       const int n_items = (int)aitems.size() / 2;
+      const bool moments = b->moment_cache;
       launchers.push_back([=]() -> int {
         assoc_batch_launch(staged<AssocArgs>(b, off_a), n_items, max_query, b->assoc_lanes, b->stream, b->prof);
         segment_build_batch_launch(staged<SegmentArgs>(b, off_s), n_items, max_query, b->stream, b->prof);
+        if (moments) moments_batch_launch(staged<MomentArgs>(b, off_m), n_items, max_units, b->stream, b->prof);
         BATCH_CUDA(b, cudaGetLastError());
         return FORMGPU_OK;
       });

@@ -53,7 +53,10 @@ void poll_relax(unsigned spins);
 
 /// Stage 3 building blocks (api_stage3.cu), also used by the fused association call.
 void relative_pose(const formgpu_pose &Ti, const formgpu_pose &Tj, double rel[12]);
-/// Launch one cluster per task (no wait).  Assigns and returns the sequence number.
+/// true: linearize / error of this context are evaluated from the pair-moment cache
+inline bool use_moment_cache(const formgpu_ctx *ctx) { return ctx->moment_cache && ctx->shard_world == 1; }
+/// Launch one cluster per task - or, from the moment cache, one warp per task (no wait).
+/// Assigns and returns the sequence number.
 int lin_launch(formgpu_ctx *ctx, const std::vector<LinTask> &tasks, bool error_only,
                unsigned long long *seq_out, double *out_plain = nullptr);
 /// Spin until every word of the listed pairs carries the call's tag, decoding them into
@@ -91,6 +94,8 @@ struct AssocPlan {
   AssocArgs aa[2];
   SegmentArgs sa[2];
   unsigned long long assoc_seq = 0, lin_seq = 0;
+  MomentArgs ma;      // pair moments of this association (queued behind the scatter kernel)
+  int mom_units = 0;  // upper bound of the units (warps) the moment kernel needs
   std::vector<LinTask> lin_tasks;
   std::vector<int> lin_slots;
 };

@@ -187,6 +187,7 @@ int assoc_prepare(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_sc
       LinTask t{};
       relative_pose(poses[pose_idx[order[n]]].pose, poses[pk].pose, t.rel);
       t.slot_j = slot_k;
+      t.slot_i = order[n];
       t.out_index = (int)n;
       t.dyn_slot_i_plus1 = (uint32_t)order[n] + 1u;
       plan.lin_tasks.push_back(t);
@@ -245,6 +246,26 @@ int assoc_prepare(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_sc
     sa[t].seg = t == 0 ? ctx->d_seg_planar + (size_t)slot_k * 9 * kcap
                        : ctx->d_seg_point + (size_t)slot_k * 6 * kcap;
   }
+  // pair moments of (every map slot, current scan) at the poses of this association
+  // (moments.cu): the kernel reads the pair row the scatter kernel leaves on the device
+  MomentArgs &m = plan.ma;
+  m = MomentArgs{};
+  m.kp_cap = ctx->kp_cap;
+  m.kq_cap = ctx->kq_cap;
+  m.seg_planar = sa[0].seg;
+  m.seg_point = sa[1].seg;
+  m.pair_row = ctx->d_pair;
+  m.slot_pose = reinterpret_cast<const double *>(ctx->d_map_req); // MapReq::pose, [W][12]
+  std::memcpy(m.pose_k, pose_k, 12 * sizeof(double));
+  m.moments = ctx->d_moments + (size_t)slot_k * W * kMomentStride;
+  m.partials = ctx->d_mom_partials;
+  m.tickets = ctx->d_mom_tickets;
+  m.W = W;
+  m.n_pairs = W;
+  m.shard_rank = 0; // the cache always holds the whole pair; sharded contexts stream (lin_launch)
+  m.shard_world = 1;
+  for (int i = 0; i < W; ++i) m.slots[i] = (unsigned char)i;
+  plan.mom_units = std::min(ctx->mom_max_units, moment_max_units((size_t)nq[0] + (size_t)nq[1], W));
   return FORMGPU_OK;
 }
 
@@ -332,6 +353,7 @@ static int associate_impl(formgpu_ctx *ctx, const formgpu_pose *pose_k, const fo
   if (plan.any_query) {
     assoc_launch(plan.aa[0], plan.aa[1], ctx->stream, ctx->prof);
     segment_build_launch(plan.sa[0], plan.sa[1], ctx->stream, ctx->prof);
+    if (ctx->moment_cache) moments_launch(plan.ma, plan.mom_units, ctx->stream, ctx->prof);
     FORMGPU_CUDA(ctx, cudaGetLastError());
     if (plan.fused) {
       rc = lin_launch(ctx, plan.lin_tasks, false, &plan.lin_seq);

@@ -40,6 +40,7 @@ void lin_make_args(formgpu_ctx *ctx, int n_tasks, LinArgs &a) {
   a.shard_rank = ctx->shard_rank;
   a.shard_world = ctx->shard_world;
   a.out_plain = nullptr;
+  a.moments = ctx->d_moments;
 }
 
 int lin_launch(formgpu_ctx *ctx, const std::vector<LinTask> &tasks, bool error_only,
@@ -49,22 +50,28 @@ int lin_launch(formgpu_ctx *ctx, const std::vector<LinTask> &tasks, bool error_o
   a.out_plain = out_plain;
   *seq_out = a.seq;
   if (tasks.empty()) return FORMGPU_OK;
+  const bool cached = use_moment_cache(ctx);
   if ((int)tasks.size() <= kLinInlineTasks) {
     // the whole request rides in the kernel parameters: no upload, no dependent loads
     static thread_local LinInline inl;
     std::memcpy(inl.tasks, tasks.data(), tasks.size() * sizeof(LinTask));
-    FORMGPU_CUDA(ctx, linearize_launch(a, &inl, error_only, ctx->stream, ctx->prof));
+    if (cached) FORMGPU_CUDA(ctx, eval_launch(a, &inl, error_only, ctx->stream, ctx->prof));
+    else FORMGPU_CUDA(ctx, linearize_launch(a, &inl, error_only, ctx->stream, ctx->prof));
   } else {
+    // tasks, then (for the cached evaluation, whose kernel takes its argument block from
+    // device memory) the argument block itself
     const size_t bytes = tasks.size() * sizeof(LinTask);
     FORMGPU_CUDA(ctx, cudaEventSynchronize(ctx->ev_upload));
-    const int rc = ensure_upload(ctx, bytes);
+    const int rc = ensure_upload(ctx, bytes + sizeof(LinArgs));
     if (rc) return rc;
-    std::memcpy(ctx->h_upload, tasks.data(), bytes);
-    FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_request, ctx->h_upload, bytes, cudaMemcpyHostToDevice,
-                                      ctx->stream));
-    FORMGPU_CUDA(ctx, cudaEventRecord(ctx->ev_upload, ctx->stream));
     a.tasks = static_cast<const LinTask *>(ctx->d_request);
-    FORMGPU_CUDA(ctx, linearize_launch(a, nullptr, error_only, ctx->stream, ctx->prof));
+    std::memcpy(ctx->h_upload, tasks.data(), bytes);
+    std::memcpy(static_cast<unsigned char *>(ctx->h_upload) + bytes, &a, sizeof(LinArgs));
+    FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_request, ctx->h_upload, bytes + sizeof(LinArgs),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    FORMGPU_CUDA(ctx, cudaEventRecord(ctx->ev_upload, ctx->stream));
+    if (cached) FORMGPU_CUDA(ctx, eval_launch(a, nullptr, error_only, ctx->stream, ctx->prof));
+    else FORMGPU_CUDA(ctx, linearize_launch(a, nullptr, error_only, ctx->stream, ctx->prof));
   }
   return FORMGPU_OK;
 }
@@ -137,6 +144,7 @@ int lin_build_tasks(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
     t.off_point = e->off_point;
     t.n_point = e->n_point;
     t.slot_j = sj;
+    t.slot_i = si;
     t.out_index = (int)p;
     tasks.push_back(t);
     indices.push_back((int)p);

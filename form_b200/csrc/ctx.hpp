@@ -238,6 +238,16 @@ struct formgpu_ctx {
   // ---- point-sharded mode (formgpu_set_shard) ----
   int shard_rank = 0, shard_world = 1;
 
+  // ---- pair-moment cache (moments.cu) ----
+  // [W(j)][W(i)][kMomentStride] doubles: moments of pair (i, j) left by scan j's last association
+  double *d_moments = nullptr;
+  double *d_mom_partials = nullptr; // [mom_max_units][kMomentPartial]
+  unsigned *d_mom_tickets = nullptr; // [W], self-cleaning
+  int mom_max_units = 0;
+  // linearize / error are evaluated from the cache (default) or, with
+  // FORMGPU_STREAM_LINEARIZE=1 and always in point-sharded mode, by streaming the correspondences
+  bool moment_cache = true;
+
   // ---- linearisation scratch ----
   double *d_partials = nullptr;
   size_t partial_cap = 0; // chunks

@@ -173,7 +173,7 @@ constexpr int kLinThreads = 256;   // threads per CTA
 constexpr int kLinCluster = 8;     // largest cluster (CTAs per scan pair)
 constexpr int kLinInlineTasks = 48; // pairs that travel in the kernel parameters (6 KB)
 
-struct LinTask { // one scan pair with at least one correspondence (128 B)
+struct LinTask { // one scan pair with at least one correspondence (144 B)
   double rel[12];      // R_i^T R_j row-major, then R_i^T (t_j - t_i): precomputed by the host
   uint32_t off_planar, n_planar, off_point, n_point; // ranges inside the segment of slot_j
   int slot_j;
@@ -181,8 +181,10 @@ struct LinTask { // one scan pair with at least one correspondence (128 B)
   uint32_t dyn_slot_i_plus1; // != 0: the ranges are read from the device pair row of slot_i
                              // (association and linearisation queued back to back)
   uint32_t ctx_index;        // batched launches: which context's LinArgs the task uses
+  int slot_i;                // window slot of scan i: the pair's entry in the moment cache
+  int pad_[3];
 };
-static_assert(sizeof(LinTask) == 128, "LinTask size");
+static_assert(sizeof(LinTask) == 144, "LinTask size");
 
 struct LinInline {
   LinTask tasks[kLinInlineTasks];
@@ -213,7 +215,10 @@ struct LinArgs {
   // ([n_pairs][91] or [n_pairs]) instead of the tagged host words, so that a collective
   // queued on the same stream can consume them without a host round trip
   double *out_plain;
+  // pair-moment cache of the context (moments.cu): [W(j)][W(i)][kMomentStride] doubles
+  const double *moments;
 };
+static_assert(sizeof(LinArgs) <= 128 && sizeof(LinArgs) % 8 == 0, "LinArgs: lin_warp_kernel copies it with lanes 16..31");
 cudaError_t linearize_launch(const LinArgs &a, const LinInline *inline_req, bool error_only,
                              cudaStream_t stream, Profiler &prof);
 /// Batched launches: correspondences per warp slice the host aims for, and the slice table.
@@ -237,5 +242,45 @@ static_assert(sizeof(LinCta) == 32, "LinCta size");
 cudaError_t linearize_warp_launch(const LinArgs *ctx_args_dev, const LinTask *tasks_dev,
                                   const LinCta *entries_dev, int n_entries, double *partials,
                                   unsigned *tickets, bool error_only, cudaStream_t stream, Profiler &prof);
+
+// ---- stage 3, cached form (moments.cu, FMA allowed: tolerance class) ----
+// Every association leaves, per pair (i, current scan), the POSE-INDEPENDENT second moments of
+// its correspondences at a reference relative pose rel0 (header of moments.cu); a later
+// linearisation / error evaluation at any poses is a 13x13 congruence of those moments - no
+// correspondence is streamed again.
+constexpr int kMomentPlanar = 91;    // packed upper triangle of sum phi phi^T, phi in R^13
+constexpr int kMomentPoint = 28;     // packed upper triangle of sum zeta zeta^T, zeta in R^7
+constexpr int kMomentStride = 132;   // doubles per entry: M_p[91] | M_q[28] | rel0[12] | counts (2 x u32)
+constexpr int kMomentAcc = 73;       // distinct planar sums a thread accumulates
+constexpr int kMomentPartial = 104;  // doubles per unit partial: 73 planar | 28 point | pad
+constexpr uint32_t kMomentUnit = 512; // correspondences per warp-sized unit of work
+
+struct MomentArgs { // one association of one context
+  size_t kp_cap, kq_cap;
+  const float *seg_planar;   // segment of the current slot: [9][kp_cap]
+  const float *seg_point;    // [6][kq_cap]
+  const uint32_t *pair_row;  // device [type][off|cnt][W+1] written by the scatter kernel just before
+  const double *slot_pose;   // [W][12] poses of the last map rebuild (device)
+  double pose_k[12];         // pose the current scan was associated at
+  double *moments;           // cache row of the current slot: [W][kMomentStride]
+  double *partials;          // [max_units][kMomentPartial]
+  unsigned *tickets;         // [W], zero on entry, self-cleaning
+  int W;
+  int n_pairs;               // map slots listed in `slots`
+  int shard_rank, shard_world;
+  unsigned char slots[kMaxWindow];
+};
+/// Upper bound of the units (= warps) one association with n_corr accepted matches over n_pairs
+/// pairs can need.
+inline int moment_max_units(size_t n_corr, int n_pairs) { return (int)(n_corr / kMomentUnit) + n_pairs; }
+void moments_launch(const MomentArgs &a, int max_units, cudaStream_t stream, Profiler &prof);
+void moments_batch_launch(const MomentArgs *items_dev, int n_items, int max_units, cudaStream_t stream,
+                          Profiler &prof);
+/// Blocks / errors of the listed tasks from the moment cache: one warp per task.  Tasks travel in
+/// the kernel parameters (inline_req, <= kLinInlineTasks) or in a.tasks (device memory).
+cudaError_t eval_launch(const LinArgs &a, const LinInline *inline_req, bool error_only, cudaStream_t stream,
+                        Profiler &prof);
+cudaError_t eval_batch_launch(const LinArgs *ctx_args_dev, const LinTask *tasks_dev, int n_tasks,
+                              bool error_only, cudaStream_t stream, Profiler &prof);
 
 } // namespace formgpu
