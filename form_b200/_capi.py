@@ -181,6 +181,9 @@ FORMGPU_SYMBOLS = {
     "formgpu_batch_size": (_sz, [_vp]),
     "formgpu_batch_ctx": (_vp, [_vp, _sz]),
     "formgpu_batch_submit": (_i, [_vp, _vp, _sz]),
+    "formgpu_batch_submit_async": (_i, [_vp, _vp, _sz]),
+    "formgpu_batch_wait": (_i, [_vp]),
+    "formgpu_batch_done": (_i, [_vp]),
     "formgpu_batch_last_error": (C.c_char_p, [_vp]),
     "formgpu_batch_profile_enable": (_i, [_vp, _i]),
     "formgpu_batch_profile_read": (_i, [_vp, _vp, _vp]),
@@ -214,6 +217,8 @@ FORMHOST_SYMBOLS = {
     "formhost_synth_shape": (_sz, [_i, C.POINTER(_i), C.POINTER(_i)]),
     "formhost_synth_scan": (_i, [_i, _u64, _u64, _vp, _i]),
     "formhost_synth_gt_pose": (None, [_u64, _u64, _vp]),
+    "formhost_synth_stress_scan": (None, [_u64, _u64, _vp, _i]),
+    "formhost_synth_stress_pose": (None, [_u64, _u64, _vp]),
     "formhost_pose_expmap": (None, [_vp, _vp]),
     "formhost_pose_logmap": (None, [_vp, _vp]),
     "formhost_pose_logmap_derivative": (None, [_vp, _vp]),
@@ -239,6 +244,7 @@ FORMHOST_SYMBOLS = {
     "formhost_batch_replay_batch": (_vp, [_vp]),
     "formhost_batch_replay_run": (_d, [_vp, _sz, _sz, _vp, _i, _psz]),
     "formhost_batch_replay_run_multi": (_d, [_vp, _sz, _sz, _sz, _vp, _i]),
+    "formhost_batch_replay_run_pipelined": (_d, [_vp, _sz, _sz, _sz, _sz, _vp, _i]),
     "formhost_batch_replay_stats": (None, [_vp, _i, _vp, C.POINTER(_d)]),
     "formhost_batch_replay_reset_stats": (None, [_vp]),
     **estimator_symbols("formhost_"),

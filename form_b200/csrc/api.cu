@@ -193,6 +193,7 @@ static int create_impl(formgpu_ctx *ctx) {
   FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_point),
                                   ctx->kq_cap * sizeof(PointRec), cudaHostAllocMapped));
   FORMGPU_CUDA(ctx, extract_configure(ctx->cols, ctx->words * 32, ctx->words, ctx->pr_cap));
+  FORMGPU_CUDA(ctx, linearize_configure());
 
   // window / keypoint store
   ctx->slot_scan.assign(W, 0);
@@ -439,12 +440,13 @@ void extract_direct_targets(formgpu_ctx *ctx, formgpu_planar_feat *planar_out, s
   dp = nullptr;
   dq = nullptr;
   if (planar_out && point_out && planar_cap >= ctx->kp_cap && point_cap >= ctx->kq_cap) {
-    if (ctx->direct_probe[0] != planar_out || ctx->direct_probe[1] != point_out) {
-      ctx->direct_probe[0] = planar_out;
-      ctx->direct_probe[1] = point_out;
-      ctx->direct_alias[0] = mapped_alias(planar_out);
-      ctx->direct_alias[1] = mapped_alias(point_out);
-    }
+    // probed on EVERY call (cudaPointerGetAttributes is a table lookup): a cached answer keyed
+    // on the address would go stale when the caller frees its page-locked buffers and a
+    // pageable allocation later lands at the same address
+    ctx->direct_probe[0] = planar_out;
+    ctx->direct_probe[1] = point_out;
+    ctx->direct_alias[0] = mapped_alias(planar_out);
+    ctx->direct_alias[1] = mapped_alias(point_out);
     if (ctx->direct_alias[0] && ctx->direct_alias[1]) {
       dp = static_cast<formgpu_planar_feat *>(ctx->direct_alias[0]);
       dq = static_cast<formgpu_point_feat *>(ctx->direct_alias[1]);

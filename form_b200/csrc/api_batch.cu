@@ -52,6 +52,14 @@ struct formgpu_batch {
   int assoc_lanes = kAssocLanes; // lanes per query of the batched association kernel (FORMGPU_ASSOC_LANES)
   // stage 3 from the pair-moment cache (moments.cu); FORMGPU_STREAM_LINEARIZE=1 streams instead
   bool moment_cache = true;
+  // the submission in flight (formgpu_batch_submit_async ... formgpu_batch_wait)
+  struct Pending {
+    bool active = false;
+    formgpu_request *reqs = nullptr;
+    size_t n = 0;
+    int first_error = FORMGPU_OK;
+    std::vector<size_t> live_extract, live_assoc, live_lin[2], live_commit;
+  } pend;
 };
 
 namespace {
@@ -306,12 +314,29 @@ int formgpu_batch_profile_read(formgpu_batch *b, double ms[FORMGPU_KG_COUNT],
 
 uint64_t formgpu_batch_launch_count(const formgpu_batch *b) { return b ? b->prof.total_launches : 0; }
 
-int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
-  if (!b) return FORMGPU_ERR_INVALID_ARG;
-  if (n == 0) return FORMGPU_OK;
-  if (!reqs) return bfail(b, FORMGPU_ERR_INVALID_ARG, "formgpu_batch_submit: null requests");
+} // extern "C"
+
+namespace {
+
+// Build phase of a submission: validate, stage every group's argument blocks, ONE upload, queue
+// every group's kernels.  Nothing is waited for.  An early return (bad request list, CUDA error)
+// leaves the requests it did not reach untouched - the caller stamps them.
+int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
   BATCH_CUDA(b, cudaSetDevice(b->device));
   const size_t S = b->ctx.size();
+  formgpu_batch::Pending &pend = b->pend;
+  pend.reqs = reqs;
+  pend.n = n;
+  pend.first_error = FORMGPU_OK;
+  pend.live_extract.clear();
+  pend.live_assoc.clear();
+  pend.live_lin[0].clear();
+  pend.live_lin[1].clear();
+  pend.live_commit.clear();
+  std::vector<size_t> &live_extract = pend.live_extract, &live_assoc = pend.live_assoc,
+                      &live_commit = pend.live_commit;
+  std::vector<size_t>(&live_lin)[2] = pend.live_lin;
+  int &first_error = pend.first_error;
 
   // ---- validate: known ops, one request per sequence ----
   std::vector<uint8_t> seen(S, 0);
@@ -334,7 +359,6 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
   b->args_used = 0;
   b->partials_used = 0;
   b->tickets_used = 0;
-  int first_error = FORMGPU_OK;
   auto set_status = [&](formgpu_request &q, int rc) {
     q.status = rc;
     if (rc != FORMGPU_OK && first_error == FORMGPU_OK) {
@@ -356,7 +380,6 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
   }
 
   // ---- stage 1 ----
-  std::vector<size_t> live_extract;
   std::function<int()> extract_launcher; // queued after every other group (see copy_stream)
   bool scans_uploading = false;
   {
@@ -454,7 +477,6 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
   }
 
   // ---- association (+ fused linearisation of the current scan's pairs) ----
-  std::vector<size_t> live_assoc;
   {
     std::vector<AssocArgs> aitems;
     std::vector<SegmentArgs> sitems;
@@ -551,7 +573,6 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
   }
 
   // ---- linearisation / error of listed pairs ----
-  std::vector<size_t> live_lin[2];
   for (int eo = 0; eo < 2; ++eo) {
     const int op = eo ? FORMGPU_OP_ERROR : FORMGPU_OP_LINEARIZE;
     const size_t per_pair = eo ? 1 : 91;
@@ -597,7 +618,6 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
   }
 
   // ---- commit ----
-  std::vector<size_t> live_commit;
   {
     std::vector<CommitArgs> items;
     int max_query = 0;
@@ -639,10 +659,25 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
     if (rc) return rc;
   }
   BATCH_CUDA(b, cudaEventRecord(b->ev_args, b->stream));
+  return FORMGPU_OK;
+}
 
-  // =====================================================================================
-  // collect phase
-  // =====================================================================================
+// Collect phase: wait for the results of the submission in flight (mapped-memory flags and
+// tagged words, as the single-sequence calls) and fill the requests' output fields.
+int submit_collect(formgpu_batch *b) {
+  formgpu_batch::Pending &pend = b->pend;
+  formgpu_request *reqs = pend.reqs;
+  int &first_error = pend.first_error;
+  auto set_status = [&](formgpu_request &q, int rc) {
+    q.status = rc;
+    if (rc != FORMGPU_OK && first_error == FORMGPU_OK) {
+      first_error = rc;
+      b->err = std::string("sequence ") + std::to_string(q.sequence) + ": " + formgpu_last_error(b->ctx[q.sequence]);
+    }
+  };
+  const std::vector<size_t> &live_extract = pend.live_extract, &live_assoc = pend.live_assoc,
+                            &live_commit = pend.live_commit;
+  const std::vector<size_t>(&live_lin)[2] = pend.live_lin;
   for (size_t r : live_extract) {
     formgpu_request &q = reqs[r];
     formgpu_ctx *ctx = b->ctx[q.sequence];
@@ -680,6 +715,53 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
   }
   if (b->prof.timing) b->prof.collect();
   return first_error;
+}
+
+} // namespace
+
+extern "C" {
+
+int formgpu_batch_submit_async(formgpu_batch *b, formgpu_request *reqs, size_t n) {
+  if (!b) return FORMGPU_ERR_INVALID_ARG;
+  if (b->pend.active)
+    return bfail(b, FORMGPU_ERR_STATE, "formgpu_batch_submit_async: the previous submission has not been waited for");
+  if (n == 0) return FORMGPU_OK;
+  if (!reqs) return bfail(b, FORMGPU_ERR_INVALID_ARG, "formgpu_batch_submit: null requests");
+  for (size_t r = 0; r < n; ++r) reqs[r].status = FORMGPU_OK;
+  const int rc = submit_build(b, reqs, n);
+  if (rc != FORMGPU_OK) {
+    // aborted before the collect phase: no request may be taken for completed.  Whatever was
+    // already queued is drained so that the caller can reuse its buffers.
+    cudaStreamSynchronize(b->stream);
+    for (size_t r = 0; r < n; ++r)
+      if (reqs[r].status == FORMGPU_OK) reqs[r].status = rc;
+    return rc;
+  }
+  b->pend.active = true;
+  return FORMGPU_OK;
+}
+
+int formgpu_batch_wait(formgpu_batch *b) {
+  if (!b) return FORMGPU_ERR_INVALID_ARG;
+  if (!b->pend.active) return FORMGPU_OK;
+  b->pend.active = false;
+  return submit_collect(b);
+}
+
+int formgpu_batch_done(formgpu_batch *b) {
+  if (!b) return -FORMGPU_ERR_INVALID_ARG;
+  if (!b->pend.active) return 1;
+  const cudaError_t e = cudaEventQuery(b->ev_args);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) return 0;
+  b->err = std::string("cudaEventQuery: ") + cudaGetErrorString(e);
+  return -FORMGPU_ERR_CUDA;
+}
+
+int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {
+  const int rc = formgpu_batch_submit_async(b, reqs, n);
+  if (rc != FORMGPU_OK) return rc;
+  return formgpu_batch_wait(b);
 }
 
 } // extern "C"

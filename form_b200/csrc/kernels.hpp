@@ -219,6 +219,8 @@ struct LinArgs {
   const double *moments;
 };
 static_assert(sizeof(LinArgs) <= 128 && sizeof(LinArgs) % 8 == 0, "LinArgs: lin_warp_kernel copies it with lanes 16..31");
+/// Per-device attributes of the stage-3 kernels (formgpu_create, with the device current).
+cudaError_t linearize_configure();
 cudaError_t linearize_launch(const LinArgs &a, const LinInline *inline_req, bool error_only,
                              cudaStream_t stream, Profiler &prof);
 /// Batched launches: correspondences per warp slice the host aims for, and the slice table.

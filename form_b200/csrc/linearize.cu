@@ -411,6 +411,15 @@ lin_warp_kernel(const LinArgs *ctx_args, const LinTask *tasks, const LinCta *ent
 
 size_t lin_warp_smem_bytes() { return sizeof(LinWarpSmem) * kLinWarpTasks; }
 
+// Per-device kernel attributes: called by formgpu_create with the context's device current, so
+// every device a process drives is configured (no process-wide "done" flag).
+cudaError_t linearize_configure() {
+  const int smem = (int)lin_warp_smem_bytes();
+  cudaError_t e = cudaFuncSetAttribute(lin_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(lin_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
 namespace {
 template <typename... Args>
 cudaError_t launch_cluster(void (*kernel)(Args...), int n_tasks, int cluster, cudaStream_t stream,
@@ -452,15 +461,7 @@ cudaError_t linearize_warp_launch(const LinArgs *ctx_args_dev, const LinTask *ta
                                   const LinCta *entries_dev, int n_entries, double *partials,
                                   unsigned *tickets, bool error_only, cudaStream_t stream, Profiler &prof) {
   if (n_entries <= 0) return cudaSuccess;
-  static bool configured = false;
   const size_t smem = lin_warp_smem_bytes();
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(lin_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(lin_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   const int group = error_only ? FORMGPU_KG_ERR_CHUNK : FORMGPU_KG_LIN_CHUNK;
   const int grid = (n_entries + kLinWarpTasks - 1) / kLinWarpTasks;
   prof.begin(group);

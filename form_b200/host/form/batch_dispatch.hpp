@@ -19,6 +19,7 @@
 #include <condition_variable>
 #include <memory>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -65,6 +66,12 @@ public:
     m_cv_work.notify_all();
   }
 
+  /// Message of the last submission that failed as a whole ("" if none).
+  std::string batch_error() {
+    std::lock_guard<std::mutex> lk(m_mu);
+    return m_batch_error;
+  }
+
   /// Execute one request of sequence `seq` (blocking).  Returns the request's status; the
   /// message of a failure is formgpu_last_error(ctx(seq)).
   int execute(size_t seq, formgpu_request &req) {
@@ -109,8 +116,15 @@ private:
         }
       m_pending = 0;
       lk.unlock();
-      formgpu_batch_submit(m_batch, reqs.data(), reqs.size()); // per-request status is in reqs[k]
+      // per-request status is in reqs[k]; a submission that aborts as a whole (bad request list,
+      // CUDA error while queueing) stamps its code on every request it did not reject individually
+      const int rc = formgpu_batch_submit(m_batch, reqs.data(), reqs.size());
       lk.lock();
+      if (rc != FORMGPU_OK) {
+        m_batch_error = formgpu_batch_last_error(m_batch);
+        for (auto &q : reqs)
+          if (q.status == FORMGPU_OK) q.status = rc; // belt and braces: never report an unprocessed request as done
+      }
       for (size_t k = 0; k < reqs.size(); ++k) {
         Slot &s = m_slots[owner[k]];
         *s.req = reqs[k];
@@ -132,6 +146,7 @@ private:
   std::chrono::steady_clock::time_point m_first_post;
   bool m_stop = false;
   uint64_t m_submits = 0, m_requests = 0;
+  std::string m_batch_error; // message of the last submission that failed as a whole
   std::thread m_thread;
 };
 
@@ -269,8 +284,10 @@ private:
     if (rc != FORMGPU_OK) fail(rc);
   }
   [[noreturn]] void fail(int rc) const {
-    throw HotPathError(std::string("formgpu error ") + std::to_string(rc) + ": " +
-                       formgpu_last_error(m_pool->ctx(m_seq)));
+    std::string msg = formgpu_last_error(m_pool->ctx(m_seq));
+    const std::string batch = m_pool->batch_error();
+    if (!batch.empty()) msg += (msg.empty() ? "" : "; ") + std::string("batch: ") + batch;
+    throw HotPathError(std::string("formgpu error ") + std::to_string(rc) + ": " + msg);
   }
 
   std::shared_ptr<BatchDispatcher> m_pool;

@@ -44,6 +44,16 @@ public:
   /// wall time in seconds; `rounds` (optional) receives the number of submits.
   double run(size_t first, size_t last, const formgpu_point4f *const *const *scans, bool on_device,
              size_t *rounds = nullptr) {
+    begin(first, last, on_device);
+    const auto t0 = std::chrono::steady_clock::now();
+    while (submit_next(scans)) finish_round();
+    if (rounds) *rounds = m_rounds;
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+
+  // ---- the same replay in three steps, for a host thread that drives several batches ----
+  /// Positions every sequence at scan `first`.
+  void begin(size_t first, size_t last, bool on_device) {
     const size_t S = m_traces.size();
     if (!on_device) ensure_host_buffers();
     for (size_t s = 0; s < S; ++s) {
@@ -52,32 +62,62 @@ public:
       m_seq[s].op = lo < hi ? t.scan_begin[lo] : 0;
       m_seq[s].end = lo < hi ? t.op_end(hi - 1) : 0;
     }
-    std::vector<formgpu_request> reqs;
-    std::vector<size_t> owner;
-    reqs.reserve(S);
-    size_t n_rounds = 0;
-    const auto t0 = std::chrono::steady_clock::now();
-    for (;;) {
-      reqs.clear();
-      owner.clear();
-      for (size_t s = 0; s < S; ++s) {
-        Seq &q = m_seq[s];
-        if (q.op >= q.end) continue;
-        reqs.push_back(make_request(s, (*m_traces[s]).ops[q.op], scans[s], on_device));
-        owner.push_back(s);
-      }
-      if (reqs.empty()) break;
-      const int rc = formgpu_batch_submit(m_batch, reqs.data(), reqs.size());
-      if (rc != FORMGPU_OK)
-        throw HotPathError(std::string("formgpu_batch_submit: ") + formgpu_batch_last_error(m_batch));
-      for (size_t r = 0; r < reqs.size(); ++r) {
-        const size_t s = owner[r];
-        account(s, (*m_traces[s]).ops[m_seq[s].op], reqs[r]);
-        m_seq[s].op += 1;
-      }
-      ++n_rounds;
+    m_on_device = on_device;
+    m_rounds = 0;
+    m_reqs.reserve(S);
+  }
+  /// Queues the next pending call of every sequence (formgpu_batch_submit_async); false when
+  /// every sequence has reached its end.
+  bool submit_next(const formgpu_point4f *const *const *scans) {
+    m_reqs.clear();
+    m_owner.clear();
+    for (size_t s = 0; s < m_traces.size(); ++s) {
+      Seq &q = m_seq[s];
+      if (q.op >= q.end) continue;
+      m_reqs.push_back(make_request(s, (*m_traces[s]).ops[q.op], scans[s], m_on_device));
+      m_owner.push_back(s);
     }
-    if (rounds) *rounds = n_rounds;
+    if (m_reqs.empty()) return false;
+    const int rc = formgpu_batch_submit_async(m_batch, m_reqs.data(), m_reqs.size());
+    if (rc != FORMGPU_OK)
+      throw HotPathError(std::string("formgpu_batch_submit: ") + formgpu_batch_last_error(m_batch));
+    return true;
+  }
+  /// Waits for the round queued by submit_next and advances the sequences.
+  void finish_round() {
+    const int rc = formgpu_batch_wait(m_batch);
+    if (rc != FORMGPU_OK)
+      throw HotPathError(std::string("formgpu_batch_submit: ") + formgpu_batch_last_error(m_batch));
+    for (size_t r = 0; r < m_reqs.size(); ++r) {
+      const size_t s = m_owner[r];
+      account(s, (*m_traces[s]).ops[m_seq[s].op], m_reqs[r]);
+      m_seq[s].op += 1;
+    }
+    ++m_rounds;
+  }
+  size_t rounds() const { return m_rounds; }
+
+  /// One host thread, several batches (one stream each) on the same GPU: the thread queues a
+  /// round on every batch before it waits for the first, so reps.size() rounds are in flight
+  /// while it builds the next ones.  Returns the wall time in seconds.
+  static double run_pipelined(const std::vector<BatchReplay *> &reps, size_t first, size_t last,
+                              const formgpu_point4f *const *const *const *scans, bool on_device) {
+    std::vector<uint8_t> flying(reps.size(), 0);
+    for (BatchReplay *r : reps) r->begin(first, last, on_device);
+    const auto t0 = std::chrono::steady_clock::now();
+    size_t n_flying = 0;
+    for (size_t i = 0; i < reps.size(); ++i) {
+      flying[i] = reps[i]->submit_next(scans[i]);
+      n_flying += flying[i];
+    }
+    while (n_flying) {
+      for (size_t i = 0; i < reps.size(); ++i) {
+        if (!flying[i]) continue;
+        reps[i]->finish_round();
+        flying[i] = reps[i]->submit_next(scans[i]);
+        if (!flying[i]) --n_flying;
+      }
+    }
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   }
 
@@ -261,6 +301,10 @@ private:
   size_t m_points = 0;
   size_t m_planar_cap = 0, m_point_cap = 0;
   bool m_host_ready = false;
+  bool m_on_device = false;
+  size_t m_rounds = 0;
+  std::vector<formgpu_request> m_reqs; // the round in flight (must outlive formgpu_batch_wait)
+  std::vector<size_t> m_owner;
   std::vector<std::unique_ptr<void, void (*)(void *)>> m_pinned;
 };
 

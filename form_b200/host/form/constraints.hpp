@@ -565,9 +565,10 @@ private:
             if (lin_change > std::numeric_limits<double>::epsilon() * old_lin) {
               fidelity = cost_change / lin_change;
               step_ok = fidelity > P.minModelFidelity;
-            } else if (std::fabs(cost_change) < P.relativeErrorTol * error) {
-              stop_search = true;
             }
+            // GTSAM's tryLambda tests this after (not instead of) the fidelity block: a
+            // REJECTED step whose cost change is tiny ends the lambda search
+            if (std::fabs(cost_change) < P.relativeErrorTol * error) stop_search = true;
           }
         }
         if (step_ok) {

@@ -13,6 +13,12 @@
 //     returns beyond 100 m -> (0,0,0); never NaN/Inf,
 //   * RNG xoshiro256** seeded through splitmix64 with
 //     0xF0A30000 + sequence_id*1000003 + k, one stream per scan.
+// Stress configuration (BASELINE.json configs[4]: 128x2048 scans against a ~1 M-voxel map): the
+// world is a TILED hall - the same 160 x 160 x 40 m hall repeated every 400 m in x and y, each
+// tile with its own jittered pillars and wall slabs (World::hall(tile)).  A 128x2048 scan of one
+// tile leaves ~58 k keypoints spread over tens of thousands of 0.8 m voxels; seeding the map with
+// one scan per tile (stress_pose(tile, k) = tile offset + a short local trajectory) reaches a
+// million occupied voxels with a few dozen map scans.
 #pragma once
 
 #include "form/pose3.hpp"
@@ -95,6 +101,33 @@ struct World {
     for (auto &c : cxy) cyls.push_back({c[0], c[1], 0.3, -1.5, 4.5});
   }
 
+  /// Tile `tile` of the stress world: a 160 x 160 x 40 m hall with a jittered 6 x 6 grid of
+  /// pillars (r = 1.5 m) and 8 jittered wall slabs, in tile-local coordinates.
+  static World hall(uint64_t tile) {
+    World w;
+    w.room = Box{{-80, -80, -20}, {80, 80, 20}};
+    w.slabs.clear();
+    w.cyls.clear();
+    uint64_t seed = 0x5EED7113ull + tile * 7919ull;
+    Rng rng(seed);
+    for (int gx = 0; gx < 6; ++gx)
+      for (int gy = 0; gy < 6; ++gy) {
+        const double cx = -62.5 + 25.0 * gx + 6.0 * (rng.uniform() - 0.5);
+        const double cy = -62.5 + 25.0 * gy + 6.0 * (rng.uniform() - 0.5);
+        if (cx * cx + cy * cy < 100.0) continue; // keep the sensor's neighbourhood free
+        w.cyls.push_back({cx, cy, 1.5, -20.0, 20.0});
+      }
+    for (int k = 0; k < 8; ++k) {
+      const double ang = 0.785398163397448 * k + 0.3 * (rng.uniform() - 0.5);
+      const double r = 35.0 + 25.0 * rng.uniform();
+      const double cx = r * std::cos(ang), cy = r * std::sin(ang);
+      const double half = 6.0 + 6.0 * rng.uniform(), top = -20.0 + 12.0 + 20.0 * rng.uniform();
+      if (k % 2 == 0) w.slabs.push_back({{cx - half, cy - 0.2, -20.0}, {cx + half, cy + 0.2, top}});
+      else w.slabs.push_back({{cx - 0.2, cy - half, -20.0}, {cx + 0.2, cy + half, top}});
+    }
+    return w;
+  }
+
   // distance along the ray to the inside of the room box (origin is inside)
   static double exit_box(const Box &b, const double o[3], const double d[3]) {
     double tmax = 1e300;
@@ -156,11 +189,42 @@ inline uint64_t scan_seed(uint64_t sequence_id, size_t k) {
   return 0xF0A30000ull + sequence_id * 1000003ull + (uint64_t)k;
 }
 
+/// Fill `out` (rows*cols points, row-major) with the scan of `world` seen from pose T (in the
+/// world's own frame); `seed` drives the range noise and the dropouts.
+inline void generate_scan_in(const World &world, const SensorModel &sm, const Pose3 &T, uint64_t seed,
+                             PointXYZf *out, int num_threads = 0);
+
 /// Fill `out` (rows*cols points, row-major) with scan k of sequence_id.
 inline void generate_scan(const SensorModel &sm, uint64_t sequence_id, size_t k,
                           PointXYZf *out, int num_threads = 0) {
   static const World world;
-  const Pose3 T = gt_pose(sequence_id, k);
+  generate_scan_in(world, sm, gt_pose(sequence_id, k), scan_seed(sequence_id, k), out, num_threads);
+}
+
+// ---- stress configuration: tiled hall ----
+/// Sensor pose of scan k inside its tile (tile-local frame).
+inline Pose3 stress_local_pose(uint64_t tile, size_t k) {
+  const double kk = (double)k;
+  const double yaw = 0.15 * std::sin(0.07 * kk) + 0.05 * (double)(tile % 7);
+  const double c = std::cos(yaw), s = std::sin(yaw);
+  return Pose3({c, -s, 0, s, c, 0, 0, 0, 1},
+               {-3.0 + 0.1 * kk, 0.35 * (double)(tile % 5), 0.04 * std::sin(0.1 * kk)});
+}
+/// World pose of scan k of tile `tile`: tiles repeat every 400 m on an 8-wide grid.
+inline Pose3 stress_pose(uint64_t tile, size_t k) {
+  Pose3 T = stress_local_pose(tile, k);
+  T.t[0] += 400.0 * (double)(tile % 8);
+  T.t[1] += 400.0 * (double)(tile / 8);
+  return T;
+}
+inline void generate_stress_scan(uint64_t tile, size_t k, PointXYZf *out, int num_threads = 0) {
+  const World world = World::hall(tile);
+  generate_scan_in(world, SensorModel::Stress_128x2048(), stress_local_pose(tile, k),
+                   0x57E55000ull + tile * 1000003ull + (uint64_t)k, out, num_threads);
+}
+
+inline void generate_scan_in(const World &world, const SensorModel &sm, const Pose3 &T, uint64_t seed,
+                             PointXYZf *out, int num_threads) {
   const double o[3] = {T.t[0], T.t[1], T.t[2]};
   const size_t n = (size_t)sm.rows * sm.cols;
   // the noise / dropout stream is consumed in index order so the scan does not
@@ -168,7 +232,7 @@ inline void generate_scan(const SensorModel &sm, uint64_t sequence_id, size_t k,
   std::vector<float> noise(n);
   std::vector<uint8_t> drop(n);
   {
-    Rng rng(scan_seed(sequence_id, k));
+    Rng rng(seed);
     for (size_t i = 0; i < n; ++i) {
       noise[i] = (float)(sm.noise_sigma * rng.gauss());
       drop[i] = rng.uniform() < sm.dropout;

@@ -269,6 +269,49 @@ double formhost_batch_replay_run_multi(void *const *replays, size_t n, size_t fi
   return dt;
 }
 
+/// The same job with `n_threads` host threads, each driving its share of the batches in a
+/// software pipeline (BatchReplay::run_pipelined): a thread queues one round on each of its
+/// batches before it waits for the first, so n / n_threads rounds per thread are in flight.
+/// n_threads = 0 or >= n: one thread per batch.  Returns seconds, < 0 on error.
+double formhost_batch_replay_run_pipelined(void *const *replays, size_t n, size_t n_threads, size_t first,
+                                           size_t last, const formgpu_point4f *const *const *const *scans,
+                                           int on_device) {
+  if (n == 0) return 0.0;
+  if (n_threads == 0 || n_threads > n) n_threads = n;
+  std::vector<std::thread> threads;
+  std::vector<int> failed(n_threads, 0);
+  std::atomic<size_t> ready{0};
+  std::atomic<bool> go{false};
+  for (size_t t = 0; t < n_threads; ++t) {
+    threads.emplace_back([&, t] {
+      std::vector<BatchReplay *> mine;
+      std::vector<const formgpu_point4f *const *const *> my_scans;
+      for (size_t i = t; i < n; i += n_threads) {
+        mine.push_back(static_cast<BatchReplay *>(replays[i]));
+        my_scans.push_back(scans[i]);
+      }
+      ready.fetch_add(1);
+      while (!go.load(std::memory_order_acquire)) {
+      }
+      try {
+        BatchReplay::run_pipelined(mine, first, last, my_scans.data(), on_device != 0);
+      } catch (const std::exception &e) {
+        g_error = e.what();
+        failed[t] = 1;
+      }
+    });
+  }
+  while (ready.load() < n_threads) {
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  go.store(true, std::memory_order_release);
+  for (auto &t : threads) t.join();
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  for (int f : failed)
+    if (f) return -1.0;
+  return dt;
+}
+
 /// Work counters of sequence `seq`, or summed over all sequences when seq < 0.
 void formhost_batch_replay_stats(void *r, int seq, uint64_t out[20], double *checksum) {
   auto *b = static_cast<BatchReplay *>(r);

@@ -39,6 +39,17 @@ int formhost_synth_scan(int sensor, uint64_t sequence_id, uint64_t k, formgpu_po
   return 0;
 }
 
+/// Stress configuration (BASELINE.json configs[4]): 128x2048 scan k of tile `tile` of the tiled
+/// hall, and its world pose.
+void formhost_synth_stress_scan(uint64_t tile, uint64_t k, formgpu_point4f *out, int threads) {
+  form::synth::generate_stress_scan(tile, (size_t)k, reinterpret_cast<form::PointXYZf *>(out), threads);
+}
+void formhost_synth_stress_pose(uint64_t tile, uint64_t k, formgpu_pose *out) {
+  const form::Pose3 T = form::synth::stress_pose(tile, (size_t)k);
+  for (int i = 0; i < 9; ++i) out->R[i] = T.R[i];
+  for (int i = 0; i < 3; ++i) out->t[i] = T.t[i];
+}
+
 /// Ground-truth sensor pose of scan k.
 void formhost_synth_gt_pose(uint64_t sequence_id, uint64_t k, formgpu_pose *out) {
   const form::Pose3 T = form::synth::gt_pose(sequence_id, (size_t)k);

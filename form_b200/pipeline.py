@@ -264,14 +264,17 @@ class BatchReplay:
         return int(_capi.gpu_lib().formgpu_batch_launch_count(self.batch()))
 
 
-def run_batches(batch_replays, first: int, last: int, ptrs_per_batch, on_device: bool = True) -> float:
-    """Several BatchReplay objects concurrently on one GPU (one host thread and stream per
-    batch): while one batch waits for its round the others queue theirs."""
+def run_batches(batch_replays, first: int, last: int, ptrs_per_batch, on_device: bool = True,
+                threads: int = 0) -> float:
+    """Several BatchReplay objects concurrently on one GPU (one stream per batch), driven by
+    `threads` host threads (0: one per batch).  A thread that owns several batches queues a
+    round on each of them (formgpu_batch_submit_async) before it waits for the first."""
     n = len(batch_replays)
     handles = (C.c_void_p * n)(*[b._h for b in batch_replays])
     keep = [BatchReplay._scan_table(p) for p in ptrs_per_batch]
     outer = (C.c_void_p * n)(*[C.cast(k[1], C.c_void_p) for k in keep])
-    t = _capi.host_lib().formhost_batch_replay_run_multi(handles, n, first, last, outer, int(on_device))
+    t = _capi.host_lib().formhost_batch_replay_run_pipelined(handles, n, threads, first, last, outer,
+                                                             int(on_device))
     if t < 0:
         raise RuntimeError("batched replay failed: " + (_capi.host_lib().formhost_last_error() or b"").decode())
     return t

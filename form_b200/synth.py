@@ -32,3 +32,18 @@ def gt_pose(sequence_id: int, k: int) -> np.ndarray:
     out = np.zeros(1, dtype=_capi.POSE)
     _capi.host_lib().formhost_synth_gt_pose(sequence_id, k, _capi.ptr(out))
     return out[0]
+
+
+def stress_scan(tile: int, k: int, threads: int = 0) -> np.ndarray:
+    """128x2048 scan k of tile `tile` of the tiled-hall stress world (BASELINE.json configs[4])."""
+    rows, cols = shape("stress-128x2048")
+    out = np.zeros(rows * cols, dtype=_capi.POINT4F)
+    _capi.host_lib().formhost_synth_stress_scan(tile, k, _capi.ptr(out), threads)
+    return out
+
+
+def stress_pose(tile: int, k: int) -> np.ndarray:
+    """World pose of scan k of tile `tile` (tiles repeat every 400 m)."""
+    out = np.zeros(1, dtype=_capi.POSE)
+    _capi.host_lib().formhost_synth_stress_pose(tile, k, _capi.ptr(out))
+    return out[0]

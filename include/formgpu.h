@@ -338,6 +338,20 @@ size_t formgpu_batch_size(const formgpu_batch *b);
  * formgpu_get_keypoints, formgpu_world_keypoints, ...); it runs on the batch's stream. */
 formgpu_ctx *formgpu_batch_ctx(formgpu_batch *b, size_t i);
 int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n);
+/* The two halves of formgpu_batch_submit, for a host thread that drives SEVERAL batches (one
+ * stream each) on one GPU: formgpu_batch_submit_async validates the requests, uploads their
+ * arguments and queues every kernel, then returns; formgpu_batch_wait blocks until the results
+ * have arrived and fills the output fields of the SAME reqs array (which, with every buffer it
+ * points to, must stay alive and untouched in between).  One submission may be in flight per
+ * batch (FORMGPU_ERR_STATE otherwise).  A thread that submits to each of its batches before it
+ * waits for the first keeps as many rounds in flight as it owns batches.  If the build half fails
+ * (bad request list, CUDA error) nothing stays in flight, and every request that was not
+ * individually rejected carries the returned code in `status`.
+ * formgpu_batch_done: 1 when formgpu_batch_wait would not block (or nothing is in flight), 0
+ * while the submission is still running, < 0 (= -status code) on error. */
+int formgpu_batch_submit_async(formgpu_batch *b, formgpu_request *reqs, size_t n);
+int formgpu_batch_wait(formgpu_batch *b);
+int formgpu_batch_done(formgpu_batch *b);
 const char *formgpu_batch_last_error(const formgpu_batch *b);
 /* As formgpu_profile_enable / _read / formgpu_launch_count, for the batched launches. */
 int formgpu_batch_profile_enable(formgpu_batch *b, int on);

@@ -131,6 +131,64 @@ def test_batches_run_concurrently():
     assert a.stats(0) == b.stats(1) and a.stats(1) == b.stats(0)
 
 
+def test_one_host_thread_pipelines_several_batches():
+    """formgpu_batch_submit_async / formgpu_batch_wait: ONE host thread keeps a round in flight on
+    each of its batches; results are those of the blocking submits."""
+    import torch
+
+    from form_b200.pipeline import BatchReplay, run_batches
+
+    n = 8
+    runs = [_record("vlp-16", seq, n) for seq in (1, 2, 6)]
+    p = runs[0][2]
+    dev = [[torch.from_numpy(s.view(np.uint8)).cuda() for s in scans] for _, scans, _ in runs]
+    torch.cuda.synchronize()
+    ptrs = [[d.data_ptr() for d in seq] for seq in dev]
+    traces = [est.trace() for est, _, _ in runs]
+    ref = BatchReplay(traces, p)
+    ref.run(0, n, ptrs)
+    reps = [BatchReplay([traces[i]], p) for i in range(3)]
+    t = run_batches(reps, 0, n, [[ptrs[i]] for i in range(3)], threads=1)
+    assert t > 0
+    for i in range(3):
+        got, want = reps[i].stats(0), ref.stats(i)
+        assert {k: v for k, v in got.items() if k != "checksum"} == {k: v for k, v in want.items() if k != "checksum"}
+        assert abs(got["checksum"] - want["checksum"]) <= 1e-12 * abs(want["checksum"])
+
+
+def test_async_submit_state_and_failure_stamping():
+    rows, cols = synth.shape("vlp-16")
+    params = _capi.default_params(rows, cols)
+    lib = _capi.gpu_lib()
+    h = C.c_void_p()
+    assert lib.formgpu_batch_create(C.byref(params), 0, None, 2, C.byref(h)) == 0
+    try:
+        scans = [synth.scan("vlp-16", s, 0) for s in range(2)]
+        reqs = (_capi.Request * 2)()
+        for s in range(2):
+            reqs[s].sequence, reqs[s].op, reqs[s].flags = s, _capi.OP_EXTRACT, 0
+            reqs[s].scan, reqs[s].n_points, reqs[s].scan_idx = scans[s].ctypes.data, rows * cols, s
+        assert lib.formgpu_batch_done(h) == 1  # nothing in flight
+        assert lib.formgpu_batch_submit_async(h, reqs, 2) == 0
+        # a second submission before the wait is refused and does not disturb the first
+        other = (_capi.Request * 1)()
+        other[0].sequence, other[0].op = 0, _capi.OP_COMMIT
+        assert lib.formgpu_batch_submit_async(h, other, 1) == _capi.ERR_STATE
+        assert lib.formgpu_batch_wait(h) == 0
+        assert lib.formgpu_batch_done(h) == 1
+        assert reqs[0].n_planar > 0 and reqs[1].n_planar > 0
+        assert lib.formgpu_batch_wait(h) == 0  # idempotent
+        # a submission that aborts in its build phase stamps every request (ADVICE r1: a pooled
+        # Estimator must not mistake an unprocessed request for a completed one)
+        reqs[1].op = 99
+        rc = lib.formgpu_batch_submit(h, reqs, 2)
+        assert rc == _capi.ERR_INVALID_ARG
+        assert [reqs[s].status for s in range(2)] == [rc, rc]
+        assert lib.formgpu_batch_done(h) == 1
+    finally:
+        lib.formgpu_batch_destroy(h)
+
+
 def test_pooled_live_estimators_match_standalone_estimators():
     """Four LIVE form::Estimators (host smoother in the loop, one thread each) behind the
     batching dispatcher: identical keypoints and control flow, poses equal to 1e-7, and far
