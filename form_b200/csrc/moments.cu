@@ -34,7 +34,7 @@
 //                      last warp in unit order (ticket), which expands the 73 sums to the packed
 //                      13x13 and stores the cache entry.  Fixed partition + fixed order =>
 //                      run-to-run deterministic.
-//   eval_kernel        one warp per pair: two small congruences, basis expansion, 91 tagged words
+//   eval_kernel        one 128-thread CTA per pair: two small congruences, basis expansion, 91 tagged words
 //                      to mapped host memory (or plain doubles to device memory); error-only
 //                      variant: 0.5 (W_p[6][6] + tr W_q[3:6]) / sigma^2.
 // model: tests/test_moment_model.py mirrors the index conventions below one to one.
@@ -313,24 +313,35 @@ __global__ void __launch_bounds__(kMomentThreads, 2) moment_batch_kernel(const M
 }
 
 // ---------------------------------------------------------------------------
-// evaluation: one warp per pair
+// evaluation: one CTA of 128 threads per pair
 // ---------------------------------------------------------------------------
+// The work of a pair is ~7 k multiply-adds in six dependent phases (S M, (S M) S^T, W B,
+// B^T (W B), twice).  One warp per pair left every phase several rounds deep and the launch
+// latency-bound (r2 profile: 64 us for 10 k pairs, 17 us for 12); with 128 threads every phase
+// is one to three rounds, and the inputs of the two congruences share their shared memory with
+// the expansion scratch (7.5 KB per pair, 16 pairs resident per SM).
 namespace {
 
-constexpr int kEvalThreads = 64; // 2 warps = 2 pairs per CTA
-constexpr int kEvalWarps = kEvalThreads / 32;
+constexpr int kEvalThreads = 128;
 
-struct EvalWarpSmem {
-  ExpandSmem exp;
+struct EvalCongruence { // phase 1-2 operands; dead once Wp28 / Wq28 exist
   double M[13][13];  // sum phi phi^T
   double Mq[7][7];   // sum zeta zeta^T
   double Sc[7][13];  // s = Sc phi
   double Zc[7][7];   // z = Zc zeta
   double T[7][13];   // Sc M
   double TZ[7][7];   // Zc Mq
+};
+struct EvalSmem {
+  union {
+    EvalCongruence c;
+    ExpandSmem exp;
+  };
   double Wp28[28], Wq28[28];
   double rel[12], rel0[12];
   double dR[9], dt[3];
+  LinTask task; // eval_global_kernel: the task / context blocks of this CTA
+  LinArgs args;
 };
 
 __device__ __forceinline__ int eps3(int k, int a, int b) { // Levi-Civita symbol
@@ -338,103 +349,102 @@ __device__ __forceinline__ int eps3(int k, int a, int b) { // Levi-Civita symbol
 }
 
 template <bool kErrorOnly>
-__device__ __forceinline__ void eval_body(const LinArgs &a, const LinTask &task, EvalWarpSmem &S, int lane) {
+__device__ __forceinline__ void eval_body(const LinArgs &a, const LinTask &task, EvalSmem &S) {
+  const int tid = threadIdx.x;
   if (task.dyn_slot_i_plus1) {
     // queued right behind the association: an empty pair publishes nothing (the host learns
     // the counts from the association and does not wait for it)
     const int nb = a.W + 1, si = (int)task.dyn_slot_i_plus1 - 1;
     const uint32_t n = __ldcg(&a.pair_row[1 * nb + si]) + __ldcg(&a.pair_row[3 * nb + si]);
-    if (n == 0) return;
+    if (n == 0) return; // CTA-uniform
   }
+  EvalCongruence &C = S.c;
   const double *entry = a.moments + ((size_t)task.slot_j * a.W + task.slot_i) * kMomentStride;
-  for (int o = lane; o < kMomentPlanar; o += 32) {
-    int x = 0, e = o;
+  if (tid < kMomentPlanar) {
+    int x = 0, e = tid;
     while (e >= 13 - x) {
       e -= 13 - x;
       ++x;
     }
-    const double v = entry[o];
-    S.M[x][x + e] = v;
-    S.M[x + e][x] = v;
-  }
-  if (lane < kMomentPoint) {
-    int p = 0, e = lane;
+    const double v = entry[tid];
+    C.M[x][x + e] = v;
+    C.M[x + e][x] = v;
+  } else if (tid < kMomentPlanar + kMomentPoint) {
+    int p = 0, e = tid - kMomentPlanar;
     while (e >= 7 - p) {
       e -= 7 - p;
       ++p;
     }
-    const double v = entry[kMomentPlanar + lane];
-    S.Mq[p][p + e] = v;
-    S.Mq[p + e][p] = v;
+    const double v = entry[tid];
+    C.Mq[p][p + e] = v;
+    C.Mq[p + e][p] = v;
   }
-  if (lane < 12) {
-    S.rel0[lane] = entry[kMomentPlanar + kMomentPoint + lane];
-    S.rel[lane] = task.rel[lane];
+  if (tid < 12) {
+    S.rel0[tid] = entry[kMomentPlanar + kMomentPoint + tid];
+    S.rel[tid] = task.rel[tid];
   }
-  for (int i = lane; i < 7 * 13; i += 32) (&S.Sc[0][0])[i] = 0.0;
-  for (int i = lane; i < 7 * 7; i += 32) (&S.Zc[0][0])[i] = 0.0;
-  __syncwarp();
+  for (int i = tid; i < 7 * 13; i += kEvalThreads) (&C.Sc[0][0])[i] = 0.0;
+  for (int i = tid; i < 7 * 7; i += kEvalThreads) (&C.Zc[0][0])[i] = 0.0;
+  __syncthreads();
   // dR = R R0^T, dt = t - dR t0
-  if (lane < 9) {
-    const int r = lane / 3, c = lane % 3;
-    S.dR[lane] = S.rel[3 * r] * S.rel0[3 * c] + S.rel[3 * r + 1] * S.rel0[3 * c + 1] +
-                 S.rel[3 * r + 2] * S.rel0[3 * c + 2];
+  if (tid < 9) {
+    const int r = tid / 3, c = tid % 3;
+    S.dR[tid] = S.rel[3 * r] * S.rel0[3 * c] + S.rel[3 * r + 1] * S.rel0[3 * c + 1] +
+                S.rel[3 * r + 2] * S.rel0[3 * c + 2];
   }
-  __syncwarp();
-  if (lane < 3)
-    S.dt[lane] = S.rel[9 + lane] - (S.dR[3 * lane] * S.rel0[9] + S.dR[3 * lane + 1] * S.rel0[10] +
-                                    S.dR[3 * lane + 2] * S.rel0[11]);
-  __syncwarp();
+  __syncthreads();
+  if (tid < 3)
+    S.dt[tid] = S.rel[9 + tid] - (S.dR[3 * tid] * S.rel0[9] + S.dR[3 * tid + 1] * S.rel0[10] +
+                                  S.dR[3 * tid + 2] * S.rel0[11]);
+  __syncthreads();
   // coefficient matrices (tests/test_moment_model.py: coeff_S, coeff_Z)
-  if (lane < 27) { // (k, a, c): rows n x (dR q0)
-    const int k = lane / 9, a_ = (lane / 3) % 3, c = lane % 3;
+  if (tid < 27) { // (k, a, c): rows n x (dR q0)
+    const int k = tid / 9, a_ = (tid / 3) % 3, c = tid % 3;
     double v = 0.0;
 #pragma unroll
     for (int b = 0; b < 3; ++b) v += (double)eps3(k, a_, b) * S.dR[3 * b + c];
-    S.Sc[k][3 * a_ + c] = v;
-  }
-  if (lane < 9) { // (k, a): rows n x dt, and the residual row
-    const int k = lane / 3, a_ = lane % 3;
+    C.Sc[k][3 * a_ + c] = v;
+  } else if (tid >= 32 && tid < 41) { // (k, a): rows n x dt, and the residual row
+    const int k = (tid - 32) / 3, a_ = (tid - 32) % 3;
     double v = 0.0;
 #pragma unroll
     for (int b = 0; b < 3; ++b) v += (double)eps3(k, a_, b) * S.dt[b];
-    S.Sc[k][9 + a_] = v;
-    S.Sc[6][3 * k + a_] = S.dR[3 * k + a_] - (k == a_ ? 1.0 : 0.0);
-    S.Zc[3 + k][a_] = S.dR[3 * k + a_] - (k == a_ ? 1.0 : 0.0);
+    C.Sc[k][9 + a_] = v;
+    C.Sc[6][3 * k + a_] = S.dR[3 * k + a_] - (k == a_ ? 1.0 : 0.0);
+    C.Zc[3 + k][a_] = S.dR[3 * k + a_] - (k == a_ ? 1.0 : 0.0);
+  } else if (tid >= 64 && tid < 67) {
+    const int k = tid - 64;
+    C.Sc[3 + k][9 + k] = 1.0;
+    C.Sc[6][9 + k] = S.dt[k];
+    C.Zc[k][k] = 1.0;
+    C.Zc[k][3 + k] = -1.0;
+    C.Zc[3 + k][3 + k] = 1.0;
+    C.Zc[3 + k][6] = S.dt[k];
+  } else if (tid == 96) {
+    C.Sc[6][12] = 1.0;
+    C.Zc[6][6] = 1.0;
   }
-  if (lane < 3) {
-    S.Sc[3 + lane][9 + lane] = 1.0;
-    S.Sc[6][9 + lane] = S.dt[lane];
-    S.Zc[lane][lane] = 1.0;
-    S.Zc[lane][3 + lane] = -1.0;
-    S.Zc[3 + lane][3 + lane] = 1.0;
-    S.Zc[3 + lane][6] = S.dt[lane];
-  }
-  if (lane == 3) {
-    S.Sc[6][12] = 1.0;
-    S.Zc[6][6] = 1.0;
-  }
-  __syncwarp();
-  // T = Sc M, TZ = Zc Mq
-  for (int idx = lane; idx < 7 * 13 + 7 * 7; idx += 32) {
+  __syncthreads();
+  // T = Sc M (91 entries), TZ = Zc Mq (49 entries)
+  for (int idx = tid; idx < 7 * 13 + 7 * 7; idx += kEvalThreads) {
     double v = 0.0;
     if (idx < 91) {
       const int k = idx / 13, y = idx % 13;
 #pragma unroll
-      for (int l = 0; l < 13; ++l) v += S.Sc[k][l] * S.M[l][y];
-      S.T[k][y] = v;
+      for (int l = 0; l < 13; ++l) v += C.Sc[k][l] * C.M[l][y];
+      C.T[k][y] = v;
     } else {
       const int j = idx - 91, k = j / 7, y = j % 7;
 #pragma unroll
-      for (int l = 0; l < 7; ++l) v += S.Zc[k][l] * S.Mq[l][y];
-      S.TZ[k][y] = v;
+      for (int l = 0; l < 7; ++l) v += C.Zc[k][l] * C.Mq[l][y];
+      C.TZ[k][y] = v;
     }
   }
-  __syncwarp();
+  __syncthreads();
   // W_p = T Sc^T, W_q = TZ Zc^T (packed upper triangles, the order expand_and_publish expects)
-  for (int idx = lane; idx < 56; idx += 32) {
-    const int which = idx / 28;
-    int p = 0, e = idx % 28;
+  if (tid < 56) {
+    const int which = tid / 28;
+    int p = 0, e = tid % 28;
     while (e >= 7 - p) {
       e -= 7 - p;
       ++p;
@@ -443,18 +453,18 @@ __device__ __forceinline__ void eval_body(const LinArgs &a, const LinTask &task,
     double v = 0.0;
     if (which == 0) {
 #pragma unroll
-      for (int y = 0; y < 13; ++y) v += S.T[p][y] * S.Sc[q][y];
-      S.Wp28[idx] = v;
+      for (int y = 0; y < 13; ++y) v += C.T[p][y] * C.Sc[q][y];
+      S.Wp28[tid] = v;
     } else {
 #pragma unroll
-      for (int y = 0; y < 7; ++y) v += S.TZ[p][y] * S.Zc[q][y];
-      S.Wq28[idx - 28] = v;
+      for (int y = 0; y < 7; ++y) v += C.TZ[p][y] * C.Zc[q][y];
+      S.Wq28[tid - 28] = v;
     }
   }
-  __syncwarp();
+  __syncthreads(); // the congruence operands are dead from here on: S.exp reuses their memory
   const unsigned long long tag = a.seq & 0xffffffffull;
   if (kErrorOnly) {
-    if (lane == 0) {
+    if (tid == 0) {
       // W_p[6][6] = sum r^2 (packed index 27), W_q[3][3], [4][4], [5][5] = sum |e|^2 (18, 22, 25)
       const double err = 0.5 * a.inv_sigma2 * (S.Wp28[27] + S.Wq28[18] + S.Wq28[22] + S.Wq28[25]);
       if (a.out_plain) a.out_plain[task.out_index] = err;
@@ -462,44 +472,36 @@ __device__ __forceinline__ void eval_body(const LinArgs &a, const LinTask &task,
     }
     return;
   }
-  build_basis<true>(S.exp, S.rel); // starts with a __syncwarp
-  __syncwarp();
-  expand_and_publish<true>(S.exp, S.Wp28, S.Wq28, true, true, a.inv_sigma2,
-                           a.out + 182 * (size_t)task.out_index, tag,
-                           a.out_plain ? a.out_plain + 91 * (size_t)task.out_index : nullptr);
+  build_basis<false>(S.exp, S.rel); // zero-fills, then three threads write the entries
+  __syncthreads();
+  expand_and_publish<false>(S.exp, S.Wp28, S.Wq28, true, true, a.inv_sigma2,
+                            a.out + 182 * (size_t)task.out_index, tag,
+                            a.out_plain ? a.out_plain + 91 * (size_t)task.out_index : nullptr);
 }
 
 } // namespace
 
 template <bool kErrorOnly>
 __global__ void __launch_bounds__(kEvalThreads) eval_inline_kernel(LinArgs a, LinInline req) {
-  __shared__ EvalWarpSmem s_w[kEvalWarps];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ti = (int)blockIdx.x * kEvalWarps + warp;
-  if (ti >= a.n_tasks) return;
-  eval_body<kErrorOnly>(a, req.tasks[ti], s_w[warp], lane);
+  __shared__ EvalSmem s;
+  eval_body<kErrorOnly>(a, req.tasks[blockIdx.x], s);
 }
 
 // tasks (and, for batched launches, the contexts' argument blocks) in device memory
 template <bool kErrorOnly>
 __global__ void __launch_bounds__(kEvalThreads)
 eval_global_kernel(const LinArgs *ctx_args, const LinTask *tasks, int n_tasks) {
-  __shared__ EvalWarpSmem s_w[kEvalWarps];
-  __shared__ LinTask s_task[kEvalWarps];
-  __shared__ LinArgs s_args[kEvalWarps];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ti = (int)blockIdx.x * kEvalWarps + warp;
-  if (ti >= n_tasks) return;
-  for (int i = lane; i < (int)(sizeof(LinTask) / 8); i += 32)
-    reinterpret_cast<unsigned long long *>(&s_task[warp])[i] =
-        reinterpret_cast<const unsigned long long *>(tasks + ti)[i];
-  __syncwarp();
-  const LinArgs *src = ctx_args + s_task[warp].ctx_index;
-  for (int i = lane; i < (int)(sizeof(LinArgs) / 8); i += 32)
-    reinterpret_cast<unsigned long long *>(&s_args[warp])[i] =
-        reinterpret_cast<const unsigned long long *>(src)[i];
-  __syncwarp();
-  eval_body<kErrorOnly>(s_args[warp], s_task[warp], s_w[warp], lane);
+  __shared__ EvalSmem s;
+  const int tid = threadIdx.x;
+  if (tid < (int)(sizeof(LinTask) / 8))
+    reinterpret_cast<unsigned long long *>(&s.task)[tid] =
+        reinterpret_cast<const unsigned long long *>(tasks + blockIdx.x)[tid];
+  __syncthreads();
+  if (tid < (int)(sizeof(LinArgs) / 8))
+    reinterpret_cast<unsigned long long *>(&s.args)[tid] =
+        reinterpret_cast<const unsigned long long *>(ctx_args + s.task.ctx_index)[tid];
+  __syncthreads();
+  eval_body<kErrorOnly>(s.args, s.task, s);
 }
 
 void moments_launch(const MomentArgs &a, int max_units, cudaStream_t stream, Profiler &prof) {
@@ -522,7 +524,7 @@ cudaError_t eval_launch(const LinArgs &a, const LinInline *inline_req, bool erro
                         Profiler &prof) {
   if (a.n_tasks <= 0) return cudaSuccess;
   const int group = error_only ? FORMGPU_KG_ERR_FINALIZE : FORMGPU_KG_LIN_FINALIZE;
-  const int grid = (a.n_tasks + kEvalWarps - 1) / kEvalWarps;
+  const int grid = a.n_tasks;
   prof.begin(group);
   if (inline_req) {
     if (error_only) eval_inline_kernel<true><<<grid, kEvalThreads, 0, stream>>>(a, *inline_req);
@@ -541,7 +543,7 @@ cudaError_t eval_batch_launch(const LinArgs *ctx_args_dev, const LinTask *tasks_
                               bool error_only, cudaStream_t stream, Profiler &prof) {
   if (n_tasks <= 0) return cudaSuccess;
   const int group = error_only ? FORMGPU_KG_ERR_FINALIZE : FORMGPU_KG_LIN_FINALIZE;
-  const int grid = (n_tasks + kEvalWarps - 1) / kEvalWarps;
+  const int grid = n_tasks;
   prof.begin(group);
   if (error_only) eval_global_kernel<true><<<grid, kEvalThreads, 0, stream>>>(ctx_args_dev, tasks_dev, n_tasks);
   else eval_global_kernel<false><<<grid, kEvalThreads, 0, stream>>>(ctx_args_dev, tasks_dev, n_tasks);
