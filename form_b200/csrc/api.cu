@@ -194,6 +194,7 @@ static int create_impl(formgpu_ctx *ctx) {
                                   ctx->kq_cap * sizeof(PointRec), cudaHostAllocMapped));
   FORMGPU_CUDA(ctx, extract_configure(ctx->cols, ctx->words * 32, ctx->words, ctx->pr_cap));
   FORMGPU_CUDA(ctx, linearize_configure());
+  if (const char *env = std::getenv("FORMGPU_CELL_BUCKETS")) ctx->cell_buckets = env[0] != '0';
 
   // window / keypoint store
   ctx->slot_scan.assign(W, 0);

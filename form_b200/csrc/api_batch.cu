@@ -467,9 +467,10 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       rc = stage_args(b, regions.data(), regions.size(), &off_regions);
       if (rc) return rc;
       const int n_items = (int)regions.size();
+      const bool cells = items[0].cells != 0; // one switch per process (FORMGPU_CELL_BUCKETS)
       launchers.push_back([=]() -> int {
         map_build_batch_launch(staged<MapArgs>(b, off_items), staged<MapClearRegion>(b, off_regions), n_items,
-                               max_points, max_hash, max_clear, b->stream, b->prof);
+                               max_points, max_hash, max_clear, cells, b->stream, b->prof);
         BATCH_CUDA(b, cudaGetLastError());
         return FORMGPU_OK;
       });

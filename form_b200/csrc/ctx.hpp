@@ -207,6 +207,9 @@ struct formgpu_ctx {
   size_t map_req_bytes = 0;
   cudaEvent_t ev_upload = nullptr;    // guards reuse of the pinned request buffers
   bool map_built = false;
+  // voxel buckets ordered by 4x4x4 sub-cells, association searches cell by cell (default);
+  // FORMGPU_CELL_BUCKETS=0 at formgpu_create keeps the whole-bucket scans
+  bool cell_buckets = true;
   void *d_export = nullptr;           // lazily allocated world export buffer
   size_t export_bytes = 0;
 

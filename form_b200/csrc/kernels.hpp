@@ -69,14 +69,22 @@ struct MapArgs {
   int n_total;
   double voxel_width;
   double inv_voxel_width; // 1 / voxel_width (host, IEEE): fast path of voxel_coord
+  int cells;              // != 0: pass 4 orders the buckets of >= kCellMin points by cell code
+  int pad_cells;
   HashSlot *hash;
   uint32_t hash_mask;
-  WorldPoint *world_tmp; // store order
-  uint32_t *world_slot;  // hash slot per store-order point
+  WorldPoint *world_tmp; // store order; with cells: the FINAL voxel- and cell-sorted points
+  uint32_t *world_slot;  // hash slot per store-order point; with cells: the final world_src
   uint32_t *world_src;   // voxel-sorted -> (window slot << 24 | k)
-  WorldPoint *world;     // voxel-sorted
+  WorldPoint *world;     // voxel-sorted; with cells: the per-voxel cell tables (pass 4)
   uint32_t *cursor;      // allocation cursor (zeroed before the build)
 };
+/// Cell-ordered buckets (map_assoc.cu, pass 4): a voxel holding kCellMin..kCellMax points gets
+/// kCellFlag in its slot's count; its bucket is ordered by a kCellSub^3 cell code and carries a
+/// table of 64 u16 end offsets.
+constexpr uint32_t kCellFlag = 0x80000000u;
+constexpr uint32_t kCellMin = 16, kCellMax = 65535;
+constexpr int kCellSub = 4;
 void map_build_launch(const MapArgs &planar, const MapArgs &point, cudaStream_t stream, Profiler &prof);
 struct MapClearRegion {
   void *base;   // 16-byte aligned
@@ -85,7 +93,7 @@ struct MapClearRegion {
 /// Rebuild of n_items maps in one pass of four launches: items_dev = [item][type] MapArgs,
 /// regions_dev[item] = the cursor + hash tables to clear first.
 void map_build_batch_launch(const MapArgs *items_dev, const MapClearRegion *regions_dev, int n_items,
-                            int max_points, uint32_t max_hash, size_t max_clear_bytes,
+                            int max_points, uint32_t max_hash, size_t max_clear_bytes, bool cells,
                             cudaStream_t stream, Profiler &prof);
 
 struct AssocArgs {
@@ -96,6 +104,9 @@ struct AssocArgs {
   double pose[12];     // pose of the current scan
   double voxel_width;
   double inv_voxel_width; // 1 / voxel_width (host, IEEE): fast path of voxel_coord
+  // cell-ordered buckets: the offset table of a flagged voxel whose bucket starts at `start` lives
+  // in cell_tab[start .. start+3] (64 x u16 end offsets); nullptr = buckets are not cell-ordered
+  const WorldPoint *cell_tab;
   const HashSlot *hash;
   uint32_t hash_mask;
   const WorldPoint *world;

@@ -54,6 +54,27 @@ __device__ __forceinline__ int lane_shift(int v, int axis) {
   return (int)(w << (30 - 2 * (v & 15))) >> 30;
 }
 
+// inverse of the table: rank of the shift (sx, sy, sz), 5 bits per entry, 12 entries per word
+constexpr unsigned long long pack_rank(int word) {
+  constexpr int T[27][3] = {
+      {0, 0, 0},   {1, 0, 0},   {-1, 0, 0},  {0, 1, 0},   {0, -1, 0},  {0, 0, 1},   {0, 0, -1},
+      {1, 1, 0},   {1, -1, 0},  {-1, 1, 0},  {-1, -1, 0}, {1, 0, 1},   {1, 0, -1},  {-1, 0, 1},
+      {-1, 0, -1}, {0, 1, 1},   {0, 1, -1},  {0, -1, 1},  {0, -1, -1}, {1, 1, 1},   {1, 1, -1},
+      {1, -1, 1},  {1, -1, -1}, {-1, 1, 1},  {-1, 1, -1}, {-1, -1, 1}, {-1, -1, -1}};
+  unsigned long long v = 0;
+  for (int r = 0; r < 27; ++r) {
+    const int idx = (T[r][0] + 1) * 9 + (T[r][1] + 1) * 3 + (T[r][2] + 1);
+    if (idx / 12 == word) v |= (unsigned long long)r << (5 * (idx % 12));
+  }
+  return v;
+}
+constexpr unsigned long long kRank0 = pack_rank(0), kRank1 = pack_rank(1), kRank2 = pack_rank(2);
+__device__ __forceinline__ int shift_rank(int sx, int sy, int sz) {
+  const int idx = (sx + 1) * 9 + (sy + 1) * 3 + (sz + 1);
+  const unsigned long long wd = idx < 12 ? kRank0 : idx < 24 ? kRank1 : kRank2;
+  return (int)((wd >> (5 * (idx % 12))) & 31ull);
+}
+
 constexpr unsigned long long kEmptyKey = 0ull; // table is cleared with memset(0)
 
 // 21 bits per axis (two's complement wrap), bit 63 marks "occupied".
@@ -175,7 +196,11 @@ __device__ __forceinline__ void map_alloc_body(const MapArgs &a) {
   const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h > a.hash_mask) return;
   const uint32_t cnt = a.hash[h].count;
-  if (cnt) a.hash[h].start = atomicAdd(a.cursor, cnt) + cnt;
+  if (cnt) {
+    a.hash[h].start = atomicAdd(a.cursor, cnt) + cnt;
+    // cell-ordered bucket (map_cells_body): the flag travels in the count's top bit
+    if (a.cells && cnt >= kCellMin && cnt <= kCellMax) a.hash[h].count = cnt | kCellFlag;
+  }
 }
 } // namespace
 __global__ void __launch_bounds__(256) map_alloc_kernel(MapArgs pa, MapArgs qa) {
@@ -211,6 +236,108 @@ __global__ void __launch_bounds__(256) map_scatter_batch_kernel(const MapArgs *i
   map_scatter_body(s_a);
 }
 
+// pass 4 (cell-ordered buckets): copy every bucket from the scatter pass's output (`world`,
+// `world_src`) into the final arrays (`world_tmp`, `world_slot` - both dead once the scatter pass
+// has run), ordering the buckets of kCellMin..kCellMax points by the kCellSub^3 cell code of
+// their points, and leave the table of the cells' END offsets (64 x u16 = 128 B) in the first
+// four records of `world` at the bucket's position - the source copy is dead by then, and a
+// flagged bucket has at least kCellMin >= 4 records, so every voxel owns its table slot without
+// any allocation.  One warp per voxel, any bucket size: histogram over the 64 cells (integer
+// shared-memory atomics), exclusive prefix, scatter.  The order inside a cell is arbitrary, like
+// the order inside a bucket before - rule R5's key does not depend on it.
+namespace {
+constexpr int kCellWarps = 8;
+struct CellSmem { // one warp's voxel
+  uint32_t hist[kCellSub * kCellSub * kCellSub];
+  uint32_t cur[kCellSub * kCellSub * kCellSub];
+};
+static_assert(kCellSub * kCellSub * kCellSub == 64, "the table layout assumes 64 cells (two per lane)");
+
+// cell of a coordinate relative to its voxel's lower corner (clamped: a point a rounding error
+// outside its voxel lands in the edge cell, which the query-side margins cover)
+__device__ __forceinline__ int cell_index(double rel, double inv_cw) {
+  const int i = (int)floor(rel * inv_cw);
+  return min(max(i, 0), kCellSub - 1);
+}
+__device__ __forceinline__ int unpack_coord(unsigned long long key, int shift) {
+  const uint32_t v = (uint32_t)(key >> shift) & 0x1FFFFFu;
+  return (int)(v << 11) >> 11; // sign-extend 21 bits
+}
+
+__device__ __forceinline__ void map_cells_body(const MapArgs &a) {
+  __shared__ CellSmem s_cells[kCellWarps];
+  if (!a.cells || a.n_total <= 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  CellSmem &S = s_cells[warp];
+  const uint32_t n_slots = a.hash_mask + 1u;
+  const uint32_t stride = gridDim.x * kCellWarps * 32u;
+  const double w = a.voxel_width, inv_cw = (double)kCellSub * a.inv_voxel_width;
+  for (uint32_t base = (blockIdx.x * kCellWarps + warp) * 32u; base < n_slots; base += stride) {
+    const uint32_t h = base + lane;
+    HashSlot s;
+    s.key = 0ull;
+    s.start = s.count = 0u;
+    if (h < n_slots) s = a.hash[h];
+    // small buckets: copied as they are, one lane per voxel
+    if (s.count != 0u && (s.count & kCellFlag) == 0u) {
+      for (uint32_t i = 0; i < s.count; ++i) {
+        a.world_tmp[s.start + i] = a.world[s.start + i];
+        a.world_slot[s.start + i] = a.world_src[s.start + i];
+      }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, (s.count & kCellFlag) != 0u);
+    while (todo) {
+      const int owner = __ffs(todo) - 1;
+      todo &= todo - 1u;
+      const uint32_t start = __shfl_sync(0xffffffffu, s.start, owner);
+      const uint32_t cnt = __shfl_sync(0xffffffffu, s.count, owner) & ~kCellFlag;
+      const unsigned long long key = __shfl_sync(0xffffffffu, s.key, owner);
+      const double lx = (double)unpack_coord(key, 42) * w, ly = (double)unpack_coord(key, 21) * w,
+                   lz = (double)unpack_coord(key, 0) * w;
+      S.hist[lane] = 0u;
+      S.hist[lane + 32] = 0u;
+      __syncwarp();
+      auto code_of = [&](const WorldPoint &p) {
+        return (cell_index(p.x - lx, inv_cw) * kCellSub + cell_index(p.y - ly, inv_cw)) * kCellSub +
+               cell_index(p.z - lz, inv_cw);
+      };
+      for (uint32_t i = lane; i < cnt; i += 32) atomicAdd(&S.hist[code_of(a.world[start + i])], 1u);
+      __syncwarp();
+      // exclusive prefix over the 64 bins, two per lane
+      const uint32_t c0 = S.hist[2 * lane], c1 = S.hist[2 * lane + 1];
+      uint32_t incl = c0 + c1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t excl = incl - (c0 + c1);
+      S.cur[2 * lane] = excl;
+      S.cur[2 * lane + 1] = excl + c0;
+      __syncwarp();
+      for (uint32_t i = lane; i < cnt; i += 32) {
+        const WorldPoint p = a.world[start + i];
+        const uint32_t pos = atomicAdd(&S.cur[code_of(p)], 1u);
+        a.world_tmp[start + pos] = p;
+        a.world_slot[start + pos] = a.world_src[start + i];
+      }
+      __syncwarp(); // every read of the source bucket is done: its head becomes the table
+      // END offsets of cells 2 lane and 2 lane + 1 as one 32-bit word
+      reinterpret_cast<uint32_t *>(a.world + start)[lane] = (excl + c0) | ((excl + c0 + c1) << 16);
+      __syncwarp();
+    }
+  }
+}
+} // namespace
+__global__ void __launch_bounds__(kCellWarps * 32) map_cells_kernel(MapArgs pa, MapArgs qa) {
+  map_cells_body(blockIdx.y == 0 ? pa : qa);
+}
+__global__ void __launch_bounds__(kCellWarps * 32) map_cells_batch_kernel(const MapArgs *items) {
+  __shared__ MapArgs s_a;
+  load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
+  map_cells_body(s_a);
+}
+
 // clears the hash tables (and allocation cursors) of every item of a batched rebuild:
 // regions[i] = {base, bytes}, bytes a multiple of 16
 __global__ void __launch_bounds__(256) map_clear_batch_kernel(const MapClearRegion *regions) {
@@ -230,11 +357,17 @@ void map_build_launch(const MapArgs &pa, const MapArgs &qa, cudaStream_t stream,
   const uint32_t hs = max(pa.hash_mask, qa.hash_mask) + 1;
   map_alloc_kernel<<<dim3((hs + 255) / 256, 2), 256, 0, stream>>>(pa, qa);
   map_scatter_kernel<<<gp, 256, 0, stream>>>(pa, qa);
-  prof.end(FORMGPU_KG_MAP_BUILD, 3);
+  int launches = 3;
+  if (pa.cells || qa.cells) {
+    const unsigned blocks = std::min<unsigned>((hs + kCellWarps * 32 - 1) / (kCellWarps * 32), 4 * 148);
+    map_cells_kernel<<<dim3(blocks, 2), kCellWarps * 32, 0, stream>>>(pa, qa);
+    ++launches;
+  }
+  prof.end(FORMGPU_KG_MAP_BUILD, launches);
 }
 
 void map_build_batch_launch(const MapArgs *items_dev, const MapClearRegion *regions_dev, int n_items,
-                            int max_points, uint32_t max_hash, size_t max_clear_bytes,
+                            int max_points, uint32_t max_hash, size_t max_clear_bytes, bool cells,
                             cudaStream_t stream, Profiler &prof) {
   if (n_items <= 0) return;
   prof.begin(FORMGPU_KG_MAP_BUILD);
@@ -247,6 +380,11 @@ void map_build_batch_launch(const MapArgs *items_dev, const MapClearRegion *regi
     map_alloc_batch_kernel<<<dim3((max_hash + 255) / 256, 2, n_items), 256, 0, stream>>>(items_dev);
     map_scatter_batch_kernel<<<gp, 256, 0, stream>>>(items_dev);
     launches += 3;
+    if (cells) {
+      const unsigned blocks = std::max(1u, std::min<unsigned>((max_hash + kCellWarps * 32 - 1) / (kCellWarps * 32), 32u));
+      map_cells_batch_kernel<<<dim3(blocks, 2, n_items), kCellWarps * 32, 0, stream>>>(items_dev);
+      ++launches;
+    }
   }
   prof.end(FORMGPU_KG_MAP_BUILD, launches);
 }
@@ -370,78 +508,155 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
     for (; i < cb; i += kQueryLanes) consider(load_world(a.world + sb + i), sb + i, b);
   };
 
-  // (1) centre voxel: every lane of the group probes the same slot (one broadcast load)
-  {
-    uint32_t s0 = 0u, c0 = 0u;
-    if (searchable) probe_voxel(a.hash, a.hash_mask, pack_key(cx, cy, cz), s0, c0);
+  // Every phase below runs in warp-uniform control flow (the ballots and shuffles need all 32
+  // lanes); what a group actually does inside a phase is predicated on its own state.
+  const bool cells_on = a.cell_tab != nullptr;
+  const double qq[3] = {wx, wy, wz};
+  const int cc[3] = {cx, cy, cz};
+  double margin[3], vlo[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    vlo[k] = (double)cc[k] * w;
+    margin[k] = 1e-9 * (1.0 + fabs(qq[k])) + 4e-16 * fabs(vlo[k]);
+  }
+
+  // (1) centre voxel: every lane of the group probes the same slot (one broadcast load).  If its
+  // bucket is cell-ordered only the query's own cell is scanned here.
+  uint32_t s0 = 0u, c0raw = 0u;
+  if (searchable) probe_voxel(a.hash, a.hash_mask, pack_key(cx, cy, cz), s0, c0raw);
+  const uint32_t c0 = c0raw & ~kCellFlag;
+  const bool tabled = cells_on && (c0raw & kCellFlag) != 0u; // uniform within the group
+  const double cw = w * (1.0 / kCellSub), inv_cw = (double)kCellSub * iw;
+  int f0[3] = {0, 0, 0}; // the query's cell inside the centre voxel
+  if (tabled) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) f0[k] = cell_index(qq[k] - vlo[k], inv_cw);
+    const int code = (f0[0] * kCellSub + f0[1]) * kCellSub + f0[2];
+    const unsigned short *tab = reinterpret_cast<const unsigned short *>(a.cell_tab + s0);
+    const uint32_t lo = code ? tab[code - 1] : 0u, hi = tab[code];
+    scan_bucket(0, s0 + lo, hi - lo);
+  } else {
     scan_bucket(0, s0, c0);
   }
-  double bound = best;
+  auto group_min = [&](double v) {
 #pragma unroll
-  for (int off = kQueryLanes / 2; off > 0; off >>= 1)
-    bound = fmin(bound, __shfl_xor_sync(0xffffffffu, bound, off));
+    for (int off = kQueryLanes / 2; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+  };
+  double bound = group_min(best);
 
-  // (2) squared distance from the query to the box of each of this lane's voxels, shrunk by a
-  // safety margin that covers the rounding of floor(x / w) at the voxel faces.  All shifts
-  // are -1 / 0 / +1 per axis, so the per-axis terms are the distances to the two faces of
-  // the centre voxel - computed once per query, then three selects per voxel.
+  // Squared distances from the query to the two faces, per axis, of a box that contains it -
+  // shrunk by a safety margin that covers the rounding of floor(x / w) at the faces.  With the
+  // box = the centre VOXEL they bound the 26 neighbour voxels (all shifts are -1 / 0 / +1 per
+  // axis); with the box = the query's CELL they bound the 26 adjacent cells the same way.
   constexpr unsigned kGroupMask = kQueryLanes == 32 ? 0xffffffffu : ((1u << (kQueryLanes & 31)) - 1u);
-  double face2[3][2]; // [axis][0: towards -1, 1: towards +1], squared, margin applied
-  {
-    const double qq[3] = {wx, wy, wz};
-    const int cc[3] = {cx, cy, cz};
+  auto faces_of = [&](const double (&lo)[3], double width, double (&f2)[3][2]) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const double lo = (double)cc[k] * w, hi = lo + w;
-      const double margin = 1e-9 * (1.0 + fabs(qq[k])) + 4e-16 * fabs(lo);
-      const double dm = fmax(qq[k] - lo - margin, 0.0); // to the lower face (voxels with shift -1)
-      const double dp = fmax(hi - qq[k] - margin, 0.0); // to the upper face (voxels with shift +1)
-      face2[k][0] = dm * dm;
-      face2[k][1] = dp * dp;
+      const double dm = fmax(qq[k] - lo[k] - margin[k], 0.0);           // towards shift -1
+      const double dp = fmax(lo[k] + width - qq[k] - margin[k], 0.0);   // towards shift +1
+      f2[k][0] = dm * dm;
+      f2[k][1] = dp * dp;
     }
+  };
+  double vface2[3][2], cface2[3][2];
+  faces_of(vlo, w, vface2);
+  {
+    double clo[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) clo[k] = vlo[k] + (double)f0[k] * cw;
+    faces_of(clo, cw, cface2);
   }
-  unsigned survivors = 0; // bit v: the voxel with shift rank v of this group's query must be searched
-  bool keep[kVox];
+
+  // One search pass over the 26 shifts: `enable` groups bound their share of the shifts with
+  // `f2`, keep those whose box can still hold a point at least as close as `limit` (exact
+  // pruning), compact the survivors through shared memory so that one lane resolves one
+  // survivor to a point range - a neighbour VOXEL's whole bucket, or (as_cells) the adjacent
+  // CELL's slice of the bucket of the voxel that holds it - and scan the ranges one by one.
+  auto search_pass = [&](bool enable, bool as_cells, const double (&f2)[3][2], double limit) {
+    unsigned survivors = 0; // bit v: shift rank v of this group's query survives
+    bool keep[kVox];
 #pragma unroll
-  for (int r = 0; r < kVox; ++r) {
-    const int v = sub | (kQueryLanes * r);
-    keep[r] = false;
-    if (searchable && v > 0 && v < 27) {
-      double lb = 0.0;
+    for (int r = 0; r < kVox; ++r) {
+      const int v = sub | (kQueryLanes * r);
+      keep[r] = false;
+      if (enable && v > 0 && v < 27) {
+        double lb = 0.0;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int sh = lane_shift(v, k);
-        lb += sh == 0 ? 0.0 : sh < 0 ? face2[k][0] : face2[k][1];
+        for (int k = 0; k < 3; ++k) {
+          const int sh = lane_shift(v, k);
+          lb += sh == 0 ? 0.0 : sh < 0 ? f2[k][0] : f2[k][1];
+        }
+        keep[r] = lb <= limit;
       }
-      keep[r] = lb <= bound;
+      const unsigned bal = __ballot_sync(0xffffffffu, keep[r]);
+      survivors |= ((bal >> (grp * kQueryLanes)) & kGroupMask) << ((kQueryLanes * r) & 31);
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep[r]);
-    survivors |= ((bal >> (grp * kQueryLanes)) & kGroupMask) << ((kQueryLanes * r) & 31);
-  }
-
-  // (3) compaction: the i-th surviving rank is probed by lane i % kQueryLanes, which leaves the
-  // bucket's {start, count} in shared memory for the whole group
-  const int n_surv = __popc(survivors);
+    const int n_surv = __popc(survivors);
 #pragma unroll
-  for (int r = 0; r < kVox; ++r) {
-    const int v = sub | (kQueryLanes * r);
-    if (keep[r]) s_list[warp][grp][__popc(survivors & ((1u << v) - 1u))] = (unsigned char)v;
-  }
-  __syncwarp();
-  for (int i = sub; i < n_surv; i += kQueryLanes) {
-    const int v = s_list[warp][grp][i];
-    uint32_t st = 0u, ct = 0u;
-    probe_voxel(a.hash, a.hash_mask,
-                pack_key(cx + lane_shift(v, 0), cy + lane_shift(v, 1), cz + lane_shift(v, 2)), st, ct);
-    s_bucket[warp][grp][i] = make_uint2(st, ct);
-  }
-  __syncwarp();
+    for (int r = 0; r < kVox; ++r) {
+      const int v = sub | (kQueryLanes * r);
+      if (keep[r]) s_list[warp][grp][__popc(survivors & ((1u << v) - 1u))] = (unsigned char)v;
+    }
+    __syncwarp();
+    for (int i = sub; i < n_surv; i += kQueryLanes) {
+      const int v = s_list[warp][grp][i];
+      int sh[3] = {lane_shift(v, 0), lane_shift(v, 1), lane_shift(v, 2)};
+      uint32_t st = 0u, ct = 0u;
+      int rank = v;
+      if (!as_cells) {
+        probe_voxel(a.hash, a.hash_mask, pack_key(cx + sh[0], cy + sh[1], cz + sh[2]), st, ct);
+        ct &= ~kCellFlag; // the whole bucket, cell-ordered or not
+      } else {
+        // adjacent cell f0 + sh: it lies in the centre voxel or in the neighbour voxel `carry`
+        int carry[3], ci[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int f = f0[k] + sh[k];
+          carry[k] = f < 0 ? -1 : f >= kCellSub ? 1 : 0;
+          ci[k] = f - kCellSub * carry[k];
+        }
+        rank = shift_rank(carry[0], carry[1], carry[2]);
+        uint32_t ctraw = c0raw;
+        st = s0;
+        if (rank != 0) {
+          ctraw = 0u;
+          probe_voxel(a.hash, a.hash_mask, pack_key(cx + carry[0], cy + carry[1], cz + carry[2]), st, ctraw);
+        }
+        if (ctraw & kCellFlag) {
+          const int code = (ci[0] * kCellSub + ci[1]) * kCellSub + ci[2];
+          const unsigned short *tab = reinterpret_cast<const unsigned short *>(a.cell_tab + st);
+          const uint32_t lo = code ? tab[code - 1] : 0u, hi = tab[code];
+          st += lo;
+          ct = hi - lo;
+        } else {
+          ct = ctraw; // a voxel too small (or too large) for a table: its whole bucket
+        }
+      }
+      s_bucket[warp][grp][i] = make_uint2(st, ct);
+      s_list[warp][grp][i] = (unsigned char)rank;
+    }
+    __syncwarp();
+    for (int i = 0; i < n_surv; ++i) {
+      const uint2 bk = s_bucket[warp][grp][i];
+      if (bk.y) scan_bucket(s_list[warp][grp][i], bk.x, bk.y);
+    }
+    __syncwarp(); // the lists are reused by the next pass
+  };
 
-  // (4) the survivors' non-empty buckets, one after the other (no warp-wide operation inside:
-  // every group runs its own trip count)
-  for (int i = 0; i < n_surv; ++i) {
-    const uint2 bk = s_bucket[warp][grp][i];
-    if (bk.y) scan_bucket(s_list[warp][grp][i], bk.x, bk.y);
+  // (2) adjacent cells of a cell-ordered centre voxel, or the 26 neighbour voxels
+  search_pass(searchable, tabled, tabled ? cface2 : vface2, bound);
+
+  // (3) a cell-ordered search is complete once the best is closer than any cell that is not
+  // adjacent to the query's own (at least one cell width away along some axis); otherwise the
+  // group repeats the search the plain way: the whole centre bucket and the neighbour voxels.
+  bound = group_min(best);
+  const double reach = cw - fmax(margin[0], fmax(margin[1], margin[2]));
+  const bool redo = tabled && !(bound < reach * reach);
+  if (redo) scan_bucket(0, s0, c0);
+  if (cells_on) { // warp-uniform: without cell-ordered buckets no group ever repeats
+    bound = group_min(best);
+    search_pass(redo, false, vface2, bound);
   }
   // arg-min over the group's lanes with the same key
 #pragma unroll
@@ -484,7 +699,7 @@ __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs q
   assoc_nn_body<kLanesSingle>(blockIdx.y == 0 ? pa : qa);
 }
 template <int kQueryLanes>
-__global__ void __launch_bounds__(256, 4) assoc_nn_batch_kernel(const AssocArgs *items) {
+__global__ void __launch_bounds__(256, 3) assoc_nn_batch_kernel(const AssocArgs *items) {
   __shared__ AssocArgs s_a;
   load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
   if ((int)(blockIdx.x * queries_per_cta(kQueryLanes)) >= s_a.n_query) return;
