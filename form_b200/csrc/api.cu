@@ -213,6 +213,7 @@ static int create_impl(formgpu_ctx *ctx) {
     FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_world_tmp[t], cap[t]));
     FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_world_slot[t], cap[t]));
     FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_world_src[t], cap[t]));
+    FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_voxel_list[t], cap[t]));
   }
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_mapmem,
                               256 + (ctx->hash_cap[0] + ctx->hash_cap[1]) * sizeof(HashSlot)));
@@ -301,7 +302,7 @@ void formgpu_destroy(formgpu_ctx *ctx) {
   F(ctx->d_store_planar); F(ctx->d_store_point);
   for (int t = 0; t < 2; ++t) {
     F(ctx->d_world[t]); F(ctx->d_world_tmp[t]);
-    F(ctx->d_world_slot[t]); F(ctx->d_world_src[t]); F(ctx->d_match[t]);
+    F(ctx->d_world_slot[t]); F(ctx->d_world_src[t]); F(ctx->d_voxel_list[t]); F(ctx->d_match[t]);
   }
   F(ctx->d_mapmem); F(ctx->d_map_req); F(ctx->d_export); H(ctx->h_map_req);
   if (ctx->ev_upload) cudaEventDestroy(ctx->ev_upload);

@@ -561,8 +561,10 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       if (rc) return rc;
       const int n_items = (int)aitems.size() / 2;
       const bool moments = b->moment_cache;
+      const bool cells = aitems[0].cell_tab != nullptr; // one switch per process (FORMGPU_CELL_BUCKETS)
       launchers.push_back([=]() -> int {
-        assoc_batch_launch(staged<AssocArgs>(b, off_a), n_items, max_query, b->assoc_lanes, b->stream, b->prof);
+        assoc_batch_launch(staged<AssocArgs>(b, off_a), n_items, max_query, cells ? 1 : b->assoc_lanes, b->stream,
+                           b->prof);
         segment_build_batch_launch(staged<SegmentArgs>(b, off_s), n_items, max_query, b->stream, b->prof);
         if (moments) moments_batch_launch(staged<MomentArgs>(b, off_m), n_items, max_units, b->stream, b->prof);
         BATCH_CUDA(b, cudaGetLastError());

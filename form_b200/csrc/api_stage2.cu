@@ -143,6 +143,7 @@ int map_rebuild_prepare(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
     a[t].world_src = ctx->d_world_src[t];
     a[t].world = ctx->d_world[t];
     a[t].cursor = reinterpret_cast<uint32_t *>(ctx->d_mapmem) + 16 * t;
+    a[t].voxel_list = ctx->d_voxel_list[t];
   }
   ctx->map_built = true;
   return FORMGPU_OK;

@@ -199,6 +199,7 @@ struct formgpu_ctx {
   formgpu::WorldPoint *d_world_tmp[2] = {nullptr, nullptr}; // unsorted, store order
   uint32_t *d_world_slot[2] = {nullptr, nullptr}; // hash slot of each store point
   uint32_t *d_world_src[2] = {nullptr, nullptr};  // voxel-sorted -> (slot<<20 | k)... see map.cu
+  uint32_t *d_voxel_list[2] = {nullptr, nullptr}; // hash slots of the occupied voxels
   size_t map_n[2] = {0, 0};                       // points in the built map
   size_t map_cap[2] = {0, 0};
   // rebuild request, one H2D: [W][12] poses | [W] scan ids | [2][W+1] offsets | [W] order

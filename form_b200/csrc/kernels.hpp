@@ -77,7 +77,8 @@ struct MapArgs {
   uint32_t *world_slot;  // hash slot per store-order point; with cells: the final world_src
   uint32_t *world_src;   // voxel-sorted -> (window slot << 24 | k)
   WorldPoint *world;     // voxel-sorted; with cells: the per-voxel cell tables (pass 4)
-  uint32_t *cursor;      // allocation cursor (zeroed before the build)
+  uint32_t *cursor;      // [0] allocation cursor, [1] occupied voxels (zeroed before the build)
+  uint32_t *voxel_list;  // hash slots of the occupied voxels, in creation order (insert pass)
 };
 /// Cell-ordered buckets (map_assoc.cu, pass 4): a voxel holding kCellMin..kCellMax points gets
 /// kCellFlag in its slot's count; its bucket is ordered by a kCellSub^3 cell code and carries a

@@ -167,7 +167,12 @@ __device__ __forceinline__ void map_insert_body(const MapArgs &a) {
   for (;;) {
     unsigned long long *kp = &a.hash[h].key;
     unsigned long long cur = *kp;
-    if (cur == kEmptyKey) cur = atomicCAS(kp, kEmptyKey, key);
+    if (cur == kEmptyKey) {
+      cur = atomicCAS(kp, kEmptyKey, key);
+      // this thread created the voxel: it also enters it in the list of occupied slots, so that
+      // the later passes walk the voxels instead of the (mostly empty) table
+      if (cur == kEmptyKey) a.voxel_list[atomicAdd(a.cursor + 1, 1u)] = h;
+    }
     if (cur == kEmptyKey || cur == key) break;
     h = (h + 1) & a.hash_mask;
   }
@@ -193,14 +198,13 @@ __global__ void __launch_bounds__(256) map_insert_batch_kernel(const MapArgs *it
 namespace {
 __device__ __forceinline__ void map_alloc_body(const MapArgs &a) {
   if (a.n_total <= 0) return;
-  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h > a.hash_mask) return;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= __ldcg(a.cursor + 1)) return; // occupied voxels (<= points)
+  const uint32_t h = a.voxel_list[i];
   const uint32_t cnt = a.hash[h].count;
-  if (cnt) {
-    a.hash[h].start = atomicAdd(a.cursor, cnt) + cnt;
-    // cell-ordered bucket (map_cells_body): the flag travels in the count's top bit
-    if (a.cells && cnt >= kCellMin && cnt <= kCellMax) a.hash[h].count = cnt | kCellFlag;
-  }
+  a.hash[h].start = atomicAdd(a.cursor, cnt) + cnt;
+  // cell-ordered bucket (map_cells_body): the flag travels in the count's top bit
+  if (a.cells && cnt >= kCellMin && cnt <= kCellMax) a.hash[h].count = cnt | kCellFlag;
 }
 } // namespace
 __global__ void __launch_bounds__(256) map_alloc_kernel(MapArgs pa, MapArgs qa) {
@@ -269,15 +273,14 @@ __device__ __forceinline__ void map_cells_body(const MapArgs &a) {
   if (!a.cells || a.n_total <= 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   CellSmem &S = s_cells[warp];
-  const uint32_t n_slots = a.hash_mask + 1u;
+  const uint32_t n_vox = __ldcg(a.cursor + 1); // occupied voxels, listed by the insert pass
   const uint32_t stride = gridDim.x * kCellWarps * 32u;
   const double w = a.voxel_width, inv_cw = (double)kCellSub * a.inv_voxel_width;
-  for (uint32_t base = (blockIdx.x * kCellWarps + warp) * 32u; base < n_slots; base += stride) {
-    const uint32_t h = base + lane;
+  for (uint32_t base = (blockIdx.x * kCellWarps + warp) * 32u; base < n_vox; base += stride) {
     HashSlot s;
     s.key = 0ull;
     s.start = s.count = 0u;
-    if (h < n_slots) s = a.hash[h];
+    if (base + lane < n_vox) s = a.hash[a.voxel_list[base + lane]];
     // small buckets: copied as they are, one lane per voxel
     if (s.count != 0u && (s.count & kCellFlag) == 0u) {
       for (uint32_t i = 0; i < s.count; ++i) {
@@ -354,12 +357,13 @@ void map_build_launch(const MapArgs &pa, const MapArgs &qa, cudaStream_t stream,
   prof.begin(FORMGPU_KG_MAP_BUILD);
   const dim3 gp((n + 255) / 256, 2);
   map_insert_kernel<<<gp, 256, 0, stream>>>(pa, qa);
-  const uint32_t hs = max(pa.hash_mask, qa.hash_mask) + 1;
-  map_alloc_kernel<<<dim3((hs + 255) / 256, 2), 256, 0, stream>>>(pa, qa);
+  const int nt = max(pa.n_total, qa.n_total); // voxels <= points
+  map_alloc_kernel<<<dim3((nt + 255) / 256, 2), 256, 0, stream>>>(pa, qa);
   map_scatter_kernel<<<gp, 256, 0, stream>>>(pa, qa);
   int launches = 3;
   if (pa.cells || qa.cells) {
-    const unsigned blocks = std::min<unsigned>((hs + kCellWarps * 32 - 1) / (kCellWarps * 32), 4 * 148);
+    // one warp takes 32 voxels per round; a bucket holds ~17 points on average
+    const unsigned blocks = std::max(1u, std::min<unsigned>((unsigned)nt / (16u * kCellWarps * 32u) + 1u, 4 * 148));
     map_cells_kernel<<<dim3(blocks, 2), kCellWarps * 32, 0, stream>>>(pa, qa);
     ++launches;
   }
@@ -377,11 +381,12 @@ void map_build_batch_launch(const MapArgs *items_dev, const MapClearRegion *regi
   if (max_points > 0) {
     const dim3 gp((max_points + 255) / 256, 2, n_items);
     map_insert_batch_kernel<<<gp, 256, 0, stream>>>(items_dev);
-    map_alloc_batch_kernel<<<dim3((max_hash + 255) / 256, 2, n_items), 256, 0, stream>>>(items_dev);
+    map_alloc_batch_kernel<<<dim3((max_points + 255) / 256, 2, n_items), 256, 0, stream>>>(items_dev);
     map_scatter_batch_kernel<<<gp, 256, 0, stream>>>(items_dev);
     launches += 3;
     if (cells) {
-      const unsigned blocks = std::max(1u, std::min<unsigned>((max_hash + kCellWarps * 32 - 1) / (kCellWarps * 32), 32u));
+      const unsigned blocks =
+          std::max(1u, std::min<unsigned>((unsigned)max_points / (16u * kCellWarps * 32u) + 1u, 64u));
       map_cells_batch_kernel<<<dim3(blocks, 2, n_items), kCellWarps * 32, 0, stream>>>(items_dev);
       ++launches;
     }
@@ -508,155 +513,79 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
     for (; i < cb; i += kQueryLanes) consider(load_world(a.world + sb + i), sb + i, b);
   };
 
-  // Every phase below runs in warp-uniform control flow (the ballots and shuffles need all 32
-  // lanes); what a group actually does inside a phase is predicated on its own state.
-  const bool cells_on = a.cell_tab != nullptr;
-  const double qq[3] = {wx, wy, wz};
-  const int cc[3] = {cx, cy, cz};
-  double margin[3], vlo[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    vlo[k] = (double)cc[k] * w;
-    margin[k] = 1e-9 * (1.0 + fabs(qq[k])) + 4e-16 * fabs(vlo[k]);
-  }
-
-  // (1) centre voxel: every lane of the group probes the same slot (one broadcast load).  If its
-  // bucket is cell-ordered only the query's own cell is scanned here.
-  uint32_t s0 = 0u, c0raw = 0u;
-  if (searchable) probe_voxel(a.hash, a.hash_mask, pack_key(cx, cy, cz), s0, c0raw);
-  const uint32_t c0 = c0raw & ~kCellFlag;
-  const bool tabled = cells_on && (c0raw & kCellFlag) != 0u; // uniform within the group
-  const double cw = w * (1.0 / kCellSub), inv_cw = (double)kCellSub * iw;
-  int f0[3] = {0, 0, 0}; // the query's cell inside the centre voxel
-  if (tabled) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) f0[k] = cell_index(qq[k] - vlo[k], inv_cw);
-    const int code = (f0[0] * kCellSub + f0[1]) * kCellSub + f0[2];
-    const unsigned short *tab = reinterpret_cast<const unsigned short *>(a.cell_tab + s0);
-    const uint32_t lo = code ? tab[code - 1] : 0u, hi = tab[code];
-    scan_bucket(0, s0 + lo, hi - lo);
-  } else {
+  // (1) centre voxel: every lane of the group probes the same slot (one broadcast load)
+  {
+    uint32_t s0 = 0u, c0 = 0u;
+    if (searchable) probe_voxel(a.hash, a.hash_mask, pack_key(cx, cy, cz), s0, c0);
+    c0 &= ~kCellFlag;
     scan_bucket(0, s0, c0);
   }
-  auto group_min = [&](double v) {
+  double bound = best;
 #pragma unroll
-    for (int off = kQueryLanes / 2; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
-    return v;
-  };
-  double bound = group_min(best);
+  for (int off = kQueryLanes / 2; off > 0; off >>= 1)
+    bound = fmin(bound, __shfl_xor_sync(0xffffffffu, bound, off));
 
-  // Squared distances from the query to the two faces, per axis, of a box that contains it -
-  // shrunk by a safety margin that covers the rounding of floor(x / w) at the faces.  With the
-  // box = the centre VOXEL they bound the 26 neighbour voxels (all shifts are -1 / 0 / +1 per
-  // axis); with the box = the query's CELL they bound the 26 adjacent cells the same way.
+  // (2) squared distance from the query to the box of each of this lane's voxels, shrunk by a
+  // safety margin that covers the rounding of floor(x / w) at the voxel faces.  All shifts
+  // are -1 / 0 / +1 per axis, so the per-axis terms are the distances to the two faces of
+  // the centre voxel - computed once per query, then three selects per voxel.
   constexpr unsigned kGroupMask = kQueryLanes == 32 ? 0xffffffffu : ((1u << (kQueryLanes & 31)) - 1u);
-  auto faces_of = [&](const double (&lo)[3], double width, double (&f2)[3][2]) {
+  double face2[3][2]; // [axis][0: towards -1, 1: towards +1], squared, margin applied
+  {
+    const double qq[3] = {wx, wy, wz};
+    const int cc[3] = {cx, cy, cz};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const double dm = fmax(qq[k] - lo[k] - margin[k], 0.0);           // towards shift -1
-      const double dp = fmax(lo[k] + width - qq[k] - margin[k], 0.0);   // towards shift +1
-      f2[k][0] = dm * dm;
-      f2[k][1] = dp * dp;
+      const double lo = (double)cc[k] * w, hi = lo + w;
+      const double margin = 1e-9 * (1.0 + fabs(qq[k])) + 4e-16 * fabs(lo);
+      const double dm = fmax(qq[k] - lo - margin, 0.0); // to the lower face (voxels with shift -1)
+      const double dp = fmax(hi - qq[k] - margin, 0.0); // to the upper face (voxels with shift +1)
+      face2[k][0] = dm * dm;
+      face2[k][1] = dp * dp;
     }
-  };
-  double vface2[3][2], cface2[3][2];
-  faces_of(vlo, w, vface2);
-  {
-    double clo[3];
+  }
+  unsigned survivors = 0; // bit v: the voxel with shift rank v of this group's query must be searched
+  bool keep[kVox];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) clo[k] = vlo[k] + (double)f0[k] * cw;
-    faces_of(clo, cw, cface2);
+  for (int r = 0; r < kVox; ++r) {
+    const int v = sub | (kQueryLanes * r);
+    keep[r] = false;
+    if (searchable && v > 0 && v < 27) {
+      double lb = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int sh = lane_shift(v, k);
+        lb += sh == 0 ? 0.0 : sh < 0 ? face2[k][0] : face2[k][1];
+      }
+      keep[r] = lb <= bound;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep[r]);
+    survivors |= ((bal >> (grp * kQueryLanes)) & kGroupMask) << ((kQueryLanes * r) & 31);
   }
 
-  // One search pass over the 26 shifts: `enable` groups bound their share of the shifts with
-  // `f2`, keep those whose box can still hold a point at least as close as `limit` (exact
-  // pruning), compact the survivors through shared memory so that one lane resolves one
-  // survivor to a point range - a neighbour VOXEL's whole bucket, or (as_cells) the adjacent
-  // CELL's slice of the bucket of the voxel that holds it - and scan the ranges one by one.
-  auto search_pass = [&](bool enable, bool as_cells, const double (&f2)[3][2], double limit) {
-    unsigned survivors = 0; // bit v: shift rank v of this group's query survives
-    bool keep[kVox];
+  // (3) compaction: the i-th surviving rank is probed by lane i % kQueryLanes, which leaves the
+  // bucket's {start, count} in shared memory for the whole group
+  const int n_surv = __popc(survivors);
 #pragma unroll
-    for (int r = 0; r < kVox; ++r) {
-      const int v = sub | (kQueryLanes * r);
-      keep[r] = false;
-      if (enable && v > 0 && v < 27) {
-        double lb = 0.0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int sh = lane_shift(v, k);
-          lb += sh == 0 ? 0.0 : sh < 0 ? f2[k][0] : f2[k][1];
-        }
-        keep[r] = lb <= limit;
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, keep[r]);
-      survivors |= ((bal >> (grp * kQueryLanes)) & kGroupMask) << ((kQueryLanes * r) & 31);
-    }
-    const int n_surv = __popc(survivors);
-#pragma unroll
-    for (int r = 0; r < kVox; ++r) {
-      const int v = sub | (kQueryLanes * r);
-      if (keep[r]) s_list[warp][grp][__popc(survivors & ((1u << v) - 1u))] = (unsigned char)v;
-    }
-    __syncwarp();
-    for (int i = sub; i < n_surv; i += kQueryLanes) {
-      const int v = s_list[warp][grp][i];
-      int sh[3] = {lane_shift(v, 0), lane_shift(v, 1), lane_shift(v, 2)};
-      uint32_t st = 0u, ct = 0u;
-      int rank = v;
-      if (!as_cells) {
-        probe_voxel(a.hash, a.hash_mask, pack_key(cx + sh[0], cy + sh[1], cz + sh[2]), st, ct);
-        ct &= ~kCellFlag; // the whole bucket, cell-ordered or not
-      } else {
-        // adjacent cell f0 + sh: it lies in the centre voxel or in the neighbour voxel `carry`
-        int carry[3], ci[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int f = f0[k] + sh[k];
-          carry[k] = f < 0 ? -1 : f >= kCellSub ? 1 : 0;
-          ci[k] = f - kCellSub * carry[k];
-        }
-        rank = shift_rank(carry[0], carry[1], carry[2]);
-        uint32_t ctraw = c0raw;
-        st = s0;
-        if (rank != 0) {
-          ctraw = 0u;
-          probe_voxel(a.hash, a.hash_mask, pack_key(cx + carry[0], cy + carry[1], cz + carry[2]), st, ctraw);
-        }
-        if (ctraw & kCellFlag) {
-          const int code = (ci[0] * kCellSub + ci[1]) * kCellSub + ci[2];
-          const unsigned short *tab = reinterpret_cast<const unsigned short *>(a.cell_tab + st);
-          const uint32_t lo = code ? tab[code - 1] : 0u, hi = tab[code];
-          st += lo;
-          ct = hi - lo;
-        } else {
-          ct = ctraw; // a voxel too small (or too large) for a table: its whole bucket
-        }
-      }
-      s_bucket[warp][grp][i] = make_uint2(st, ct);
-      s_list[warp][grp][i] = (unsigned char)rank;
-    }
-    __syncwarp();
-    for (int i = 0; i < n_surv; ++i) {
-      const uint2 bk = s_bucket[warp][grp][i];
-      if (bk.y) scan_bucket(s_list[warp][grp][i], bk.x, bk.y);
-    }
-    __syncwarp(); // the lists are reused by the next pass
-  };
+  for (int r = 0; r < kVox; ++r) {
+    const int v = sub | (kQueryLanes * r);
+    if (keep[r]) s_list[warp][grp][__popc(survivors & ((1u << v) - 1u))] = (unsigned char)v;
+  }
+  __syncwarp();
+  for (int i = sub; i < n_surv; i += kQueryLanes) {
+    const int v = s_list[warp][grp][i];
+    uint32_t st = 0u, ct = 0u;
+    probe_voxel(a.hash, a.hash_mask,
+                pack_key(cx + lane_shift(v, 0), cy + lane_shift(v, 1), cz + lane_shift(v, 2)), st, ct);
+    s_bucket[warp][grp][i] = make_uint2(st, ct & ~kCellFlag);
+  }
+  __syncwarp();
 
-  // (2) adjacent cells of a cell-ordered centre voxel, or the 26 neighbour voxels
-  search_pass(searchable, tabled, tabled ? cface2 : vface2, bound);
-
-  // (3) a cell-ordered search is complete once the best is closer than any cell that is not
-  // adjacent to the query's own (at least one cell width away along some axis); otherwise the
-  // group repeats the search the plain way: the whole centre bucket and the neighbour voxels.
-  bound = group_min(best);
-  const double reach = cw - fmax(margin[0], fmax(margin[1], margin[2]));
-  const bool redo = tabled && !(bound < reach * reach);
-  if (redo) scan_bucket(0, s0, c0);
-  if (cells_on) { // warp-uniform: without cell-ordered buckets no group ever repeats
-    bound = group_min(best);
-    search_pass(redo, false, vface2, bound);
+  // (4) the survivors' non-empty buckets, one after the other (no warp-wide operation inside:
+  // every group runs its own trip count)
+  for (int i = 0; i < n_surv; ++i) {
+    const uint2 bk = s_bucket[warp][grp][i];
+    if (bk.y) scan_bucket(s_list[warp][grp][i], bk.x, bk.y);
   }
   // arg-min over the group's lanes with the same key
 #pragma unroll
@@ -695,11 +624,303 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
   }
 }
 } // namespace
+// ---------------------------------------------------------------------------
+// association over cell-ordered buckets: one THREAD per query
+// ---------------------------------------------------------------------------
+// With the buckets ordered by 4x4x4 sub-cells (map_cells_body) a query whose nearest neighbour
+// is a few centimetres away - the usual case: the map holds the same surfaces seen from the
+// previous poses - has to look at the ~10 points of its own 20 cm cell and of the one to three
+// adjacent cells that lie within its best distance, instead of the 100+ points of the whole
+// 0.8 m voxel.  That is too little work to share between lanes (the cooperative kernel above
+// spends its instructions on ballots, compaction and shuffles), so here a thread owns a query and
+// runs the whole search by itself; a warp holds 32 consecutive keypoints, which are neighbours in
+// space and mostly take the same path.
+//   1. centre voxel probe; if its bucket is cell-ordered: scan the query's own cell, then the
+//      adjacent cells whose box can hold a point at least as close as the best so far (per axis
+//      only the directions whose cell face is that close are enumerated);
+//   2. complete if the best is closer than one cell width (every cell that was not visited is at
+//      least that far away) - otherwise, and for small or absent centre buckets, the exact
+//      whole-voxel search: centre bucket + the neighbour voxels that survive the face bound.
+// Same candidates' arg-min key (dist^2, shift rank, scan, k) = rule R5, so results are those of
+// the cooperative kernel and of the reference, bit for bit.
+namespace {
+struct NnBest {
+  double d = DBL_MAX; // Match::dist_sqrd default (map.hpp:55)
+  unsigned long long tie = ~0ull;
+  int rank = 32;
+  uint32_t pos = kNoSlot;
+};
+__device__ __forceinline__ void nn_consider(NnBest &b, const WorldPoint &p, uint32_t pos, int rank, double wx,
+                                            double wy, double wz) {
+  // 4-lane double squared norm, lane 3 = 0 padding: (d0^2 + d2^2) + (d1^2 + 0)
+  const double d0 = p.x - wx, d1 = p.y - wy, d2 = p.z - wz;
+  const double dist = (d0 * d0 + d2 * d2) + (d1 * d1 + 0.0);
+  if (dist < b.d || (dist == b.d && (rank < b.rank || (rank == b.rank && p.tie < b.tie)))) {
+    b.d = dist;
+    b.tie = p.tie;
+    b.rank = rank;
+    b.pos = pos;
+  }
+}
+__device__ __forceinline__ void nn_scan(NnBest &b, const WorldPoint *world, uint32_t lo, uint32_t n, int rank,
+                                        double wx, double wy, double wz) {
+  uint32_t i = 0;
+  for (; i + 1 < n; i += 2) { // two points in flight
+    const WorldPoint p0 = load_world(world + lo + i), p1 = load_world(world + lo + i + 1);
+    nn_consider(b, p0, lo + i, rank, wx, wy, wz);
+    nn_consider(b, p1, lo + i + 1, rank, wx, wy, wz);
+  }
+  if (i < n) nn_consider(b, load_world(world + lo + i), lo + i, rank, wx, wy, wz);
+}
+// point range of cell (ci) of a bucket: the whole bucket when it carries no table
+__device__ __forceinline__ void cell_range(const AssocArgs &a, uint32_t start, uint32_t count_raw, int cix,
+                                           int ciy, int ciz, uint32_t &lo, uint32_t &n) {
+  if (count_raw & kCellFlag) {
+    const int code = (cix * kCellSub + ciy) * kCellSub + ciz;
+    const unsigned short *tab = reinterpret_cast<const unsigned short *>(a.cell_tab + start);
+    const uint32_t b = code ? __ldg(tab + code - 1) : 0u, e = __ldg(tab + code);
+    lo = start + b;
+    n = e - b;
+  } else {
+    lo = start;
+    n = count_raw;
+  }
+}
+
+// bit v of kShiftMask[axis][0 / 1]: shift rank v moves by -1 / +1 along the axis
+constexpr unsigned shift_mask(int axis, int dir) {
+  constexpr int T[27][3] = {
+      {0, 0, 0},   {1, 0, 0},   {-1, 0, 0},  {0, 1, 0},   {0, -1, 0},  {0, 0, 1},   {0, 0, -1},
+      {1, 1, 0},   {1, -1, 0},  {-1, 1, 0},  {-1, -1, 0}, {1, 0, 1},   {1, 0, -1},  {-1, 0, 1},
+      {-1, 0, -1}, {0, 1, 1},   {0, 1, -1},  {0, -1, 1},  {0, -1, -1}, {1, 1, 1},   {1, 1, -1},
+      {1, -1, 1},  {1, -1, -1}, {-1, 1, 1},  {-1, 1, -1}, {-1, -1, 1}, {-1, -1, -1}};
+  unsigned m = 0;
+  for (int v = 1; v < 27; ++v)
+    if (T[v][axis] == dir) m |= 1u << v;
+  return m;
+}
+constexpr unsigned kShiftNeg[3] = {shift_mask(0, -1), shift_mask(1, -1), shift_mask(2, -1)};
+constexpr unsigned kShiftPos[3] = {shift_mask(0, 1), shift_mask(1, 1), shift_mask(2, 1)};
+constexpr int kMaxAdjacent = 26; // adjacent units a thread visits by itself (26 = all: measured, capping at 8 and
+                                 // sending the rest to the cooperative phase cost 12 % more)
+
+__device__ __forceinline__ void assoc_cells_body(const AssocArgs &a) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int nb = a.W + 1;
+  const bool active = q < a.n_query;
+  const bool searchable = active && a.n_map > 0;
+  const double w = a.voxel_width, iw = a.inv_voxel_width;
+  const double cw = w * (1.0 / kCellSub), inv_cw = (double)kCellSub * iw;
+  NnBest best;
+  double wx = 0.0, wy = 0.0, wz = 0.0;
+  int c[3] = {0, 0, 0};
+  uint32_t s0 = 0u, c0raw = 0u;
+  if (searchable) {
+    double x, y, z;
+    if (a.type == 0) load_xyz(reinterpret_cast<const PlanarRec *>(a.queries) + q, x, y, z);
+    else load_xyz(reinterpret_cast<const PointRec *>(a.queries) + q, x, y, z);
+    transform_point(a.pose, x, y, z, wx, wy, wz); // kp->transform(init), matcher.hpp:89
+    c[0] = voxel_coord(wx, w, iw);
+    c[1] = voxel_coord(wy, w, iw);
+    c[2] = voxel_coord(wz, w, iw);
+    probe_voxel(a.hash, a.hash_mask, pack_key(c[0], c[1], c[2]), s0, c0raw);
+  }
+  // ---- phase 1: the query's own search unit - its CELL when the centre bucket is cell-ordered,
+  // the whole centre VOXEL otherwise (small or absent bucket) ----
+  const bool by_cell = (c0raw & kCellFlag) != 0u;
+  const double qq[3] = {wx, wy, wz};
+  int f0[3] = {0, 0, 0};
+  double face2[3][2]; // squared distance to the lower / upper face of the unit, margin applied
+  double margin_max = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double vlo = (double)c[k] * w;
+    // covers the rounding of floor(x / w) at the voxel (and cell) faces
+    const double margin = 1e-9 * (1.0 + fabs(qq[k])) + 4e-16 * fabs(vlo);
+    margin_max = fmax(margin_max, margin);
+    double ulo = vlo, uw = w;
+    if (by_cell) {
+      f0[k] = cell_index(qq[k] - vlo, inv_cw);
+      ulo = vlo + (double)f0[k] * cw;
+      uw = cw;
+    }
+    const double dm = fmax(qq[k] - ulo - margin, 0.0), dp = fmax(ulo + uw - qq[k] - margin, 0.0);
+    face2[k][0] = dm * dm;
+    face2[k][1] = dp * dp;
+  }
+  {
+    uint32_t lo = s0, n = c0raw & ~kCellFlag;
+    if (by_cell) cell_range(a, s0, c0raw, f0[0], f0[1], f0[2], lo, n);
+    nn_scan(best, a.world, lo, n, 0, wx, wy, wz);
+  }
+  // ---- phase 2: the adjacent units (cells, or voxels) that can hold a point at least as close
+  // as the best so far.  Per axis a direction qualifies only if its face alone is that close (six
+  // comparisons select the candidate shifts; the summed bound is tested when a shift is popped).
+  // A query with more than kMaxAdjacent candidates - its own unit is empty, or its best is far -
+  // is left to the cooperative phase 3: in a warp of 32 unrelated queries one such lane would keep
+  // the other 31 waiting for up to 26 probe + scan rounds.
+  unsigned surv = 0u;
+  if (searchable) {
+    surv = 0x07fffffeu; // shift ranks 1..26
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      constexpr unsigned neg[3] = {kShiftNeg[0], kShiftNeg[1], kShiftNeg[2]};
+      constexpr unsigned pos[3] = {kShiftPos[0], kShiftPos[1], kShiftPos[2]};
+      if (!(face2[k][0] <= best.d)) surv &= ~neg[k];
+      if (!(face2[k][1] <= best.d)) surv &= ~pos[k];
+    }
+  }
+  bool unresolved = __popc(surv) > kMaxAdjacent;
+  if (unresolved) surv = 0u;
+  while (surv) {
+    const int v = __ffs(surv) - 1;
+    surv &= surv - 1u;
+    const int sh[3] = {lane_shift(v, 0), lane_shift(v, 1), lane_shift(v, 2)};
+    double lb = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) lb += sh[k] == 0 ? 0.0 : sh[k] < 0 ? face2[k][0] : face2[k][1];
+    uint32_t lo = 0u, n = 0u;
+    int rank = v;
+    if (lb <= best.d) { // exact pruning against the best SO FAR
+      if (by_cell) {
+        // the cell f0 + sh lies in the centre voxel or in the neighbour voxel `carry`
+        int carry[3], ci[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int f = f0[k] + sh[k];
+          carry[k] = f < 0 ? -1 : f >= kCellSub ? 1 : 0;
+          ci[k] = f - kCellSub * carry[k];
+        }
+        rank = shift_rank(carry[0], carry[1], carry[2]);
+        uint32_t st = s0, ctraw = c0raw;
+        if (rank != 0) {
+          st = 0u;
+          ctraw = 0u;
+          probe_voxel(a.hash, a.hash_mask, pack_key(c[0] + carry[0], c[1] + carry[1], c[2] + carry[2]), st, ctraw);
+        }
+        if (ctraw) cell_range(a, st, ctraw, ci[0], ci[1], ci[2], lo, n);
+      } else {
+        uint32_t ct = 0u;
+        probe_voxel(a.hash, a.hash_mask, pack_key(c[0] + sh[0], c[1] + sh[1], c[2] + sh[2]), lo, ct);
+        n = ct & ~kCellFlag;
+      }
+    }
+    nn_scan(best, a.world, lo, n, rank, wx, wy, wz);
+  }
+  if (by_cell && !unresolved) {
+    // every cell that was not visited is at least one cell width away (along some axis) or was
+    // pruned against a bound >= the final best: complete once the best is closer than that.
+    // (A search by voxels is the reference's own 27-voxel search: complete by construction.)
+    const double reach = cw - margin_max;
+    unresolved = !(best.d < reach * reach);
+  }
+  // ---- phase 3: the exact whole-voxel search (the reference's 27 buckets, face-distance pruned)
+  // for the few queries of this warp that are still unresolved, one after the other, ALL 32 LANES
+  // on each: the lanes scan the centre bucket together, lane v bounds and probes neighbour voxel
+  // v, the surviving buckets are scanned together, and a shuffle arg-min returns the result to
+  // the owner.
+  unsigned todo = __ballot_sync(0xffffffffu, unresolved);
+  while (todo) {
+    const int owner = __ffs(todo) - 1;
+    todo &= todo - 1u;
+    const double ox = __shfl_sync(0xffffffffu, wx, owner), oy = __shfl_sync(0xffffffffu, wy, owner),
+                 oz = __shfl_sync(0xffffffffu, wz, owner);
+    const int oc[3] = {__shfl_sync(0xffffffffu, c[0], owner), __shfl_sync(0xffffffffu, c[1], owner),
+                       __shfl_sync(0xffffffffu, c[2], owner)};
+    const uint32_t os0 = __shfl_sync(0xffffffffu, s0, owner);
+    const uint32_t oc0 = __shfl_sync(0xffffffffu, c0raw, owner) & ~kCellFlag;
+    NnBest mine; // this lane's share of the owner's candidates, seeded with the owner's best:
+    mine.d = __shfl_sync(0xffffffffu, best.d, owner);       // it prunes, and ties resolve as if
+    mine.tie = __shfl_sync(0xffffffffu, best.tie, owner);   // the point had been found here
+    mine.rank = __shfl_sync(0xffffffffu, best.rank, owner);
+    mine.pos = __shfl_sync(0xffffffffu, best.pos, owner);
+    for (uint32_t i = lane; i < oc0; i += 32u) nn_consider(mine, load_world(a.world + os0 + i), os0 + i, 0, ox, oy, oz);
+    double bound = mine.d;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) bound = fmin(bound, __shfl_xor_sync(0xffffffffu, bound, off));
+    // lane v (1..26): neighbour voxel v of the owner
+    uint32_t vst = 0u, vct = 0u;
+    if (lane >= 1 && lane < 27) {
+      const int sh[3] = {lane_shift(lane, 0), lane_shift(lane, 1), lane_shift(lane, 2)};
+      const double oq[3] = {ox, oy, oz};
+      double lb = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double vlo = (double)oc[k] * w;
+        const double margin = 1e-9 * (1.0 + fabs(oq[k])) + 4e-16 * fabs(vlo);
+        const double dm = fmax(oq[k] - vlo - margin, 0.0), dp = fmax(vlo + w - oq[k] - margin, 0.0);
+        lb += sh[k] == 0 ? 0.0 : sh[k] < 0 ? dm * dm : dp * dp;
+      }
+      if (lb <= bound) {
+        probe_voxel(a.hash, a.hash_mask, pack_key(oc[0] + sh[0], oc[1] + sh[1], oc[2] + sh[2]), vst, vct);
+        vct &= ~kCellFlag;
+      }
+    }
+    unsigned vox = __ballot_sync(0xffffffffu, vct != 0u);
+    while (vox) {
+      const int v = __ffs(vox) - 1;
+      vox &= vox - 1u;
+      const uint32_t st = __shfl_sync(0xffffffffu, vst, v), ct = __shfl_sync(0xffffffffu, vct, v);
+      for (uint32_t i = lane; i < ct; i += 32u) nn_consider(mine, load_world(a.world + st + i), st + i, v, ox, oy, oz);
+    }
+    // arg-min over the lanes with the rule-R5 key
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, mine.d, off);
+      const unsigned long long ot = __shfl_xor_sync(0xffffffffu, mine.tie, off);
+      const uint32_t op = __shfl_xor_sync(0xffffffffu, mine.pos, off);
+      const int orank = __shfl_xor_sync(0xffffffffu, mine.rank, off);
+      const bool take = (op != kNoSlot) &&
+                        (mine.pos == kNoSlot || od < mine.d ||
+                         (od == mine.d && (orank < mine.rank || (orank == mine.rank && ot < mine.tie))));
+      if (take) {
+        mine.d = od;
+        mine.tie = ot;
+        mine.pos = op;
+        mine.rank = orank;
+      }
+    }
+    if (lane == owner) best = mine;
+  }
+  // ---- match record + per-256-query histogram by matched scan (warp-aggregated atomics) ----
+  const bool mine = active;
+  MatchRec m;
+  m.dist_sqrd = DBL_MAX;
+  m.slot = kNoSlot;
+  m.k = 0u;
+  if (mine && best.pos != kNoSlot) {
+    const uint32_t src = a.world_src[best.pos];
+    m.dist_sqrd = best.d;
+    m.slot = src >> 24;
+    m.k = src & 0xFFFFFFu;
+  }
+  if (mine) a.match[q] = m;
+  const int bin = mine ? match_bin(m, a.max_dist2) : -1;
+  const bool novel = mine && m.dist_sqrd > a.min_dist2;
+  // a warp covers 32 consecutive queries of one 256-query block
+  const unsigned peers = __match_any_sync(0xffffffffu, bin);
+  if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&a.hist_cnt[(size_t)(q >> 8) * nb + bin], (unsigned)__popc(peers));
+  const unsigned nov = __ballot_sync(0xffffffffu, novel);
+  if (nov && lane == __ffs(nov) - 1) atomicAdd(&a.hist_cnt[(size_t)(q >> 8) * nb + a.W], (unsigned)__popc(nov));
+}
+} // namespace
+constexpr int kCellQueryThreads = 128;
+__global__ void __launch_bounds__(kCellQueryThreads) assoc_cells_kernel(AssocArgs pa, AssocArgs qa) {
+  assoc_cells_body(blockIdx.y == 0 ? pa : qa);
+}
+__global__ void __launch_bounds__(kCellQueryThreads) assoc_cells_batch_kernel(const AssocArgs *items) {
+  __shared__ AssocArgs s_a;
+  load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
+  if ((int)(blockIdx.x * kCellQueryThreads) >= s_a.n_query) return;
+  assoc_cells_body(s_a);
+}
+
 __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs qa) {
   assoc_nn_body<kLanesSingle>(blockIdx.y == 0 ? pa : qa);
 }
 template <int kQueryLanes>
-__global__ void __launch_bounds__(256, 3) assoc_nn_batch_kernel(const AssocArgs *items) {
+__global__ void __launch_bounds__(256, 4) assoc_nn_batch_kernel(const AssocArgs *items) {
   __shared__ AssocArgs s_a;
   load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
   if ((int)(blockIdx.x * queries_per_cta(kQueryLanes)) >= s_a.n_query) return;
@@ -710,8 +931,14 @@ void assoc_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream,
   const int n = max(pa.n_query, qa.n_query);
   if (n <= 0) return;
   prof.begin(FORMGPU_KG_ASSOC_NN);
-  constexpr int per_cta = queries_per_cta(kLanesSingle);
-  assoc_nn_kernel<<<dim3((n + per_cta - 1) / per_cta, 2), 256, 0, stream>>>(pa, qa);
+  if (pa.cell_tab) { // cell-ordered buckets: one thread per query
+    assoc_cells_kernel<<<dim3((n + kCellQueryThreads - 1) / kCellQueryThreads, 2), kCellQueryThreads, 0, stream>>>(pa, qa);
+    prof.end(FORMGPU_KG_ASSOC_NN, 1);
+    return;
+  } else {
+    constexpr int per_cta = queries_per_cta(kLanesSingle);
+    assoc_nn_kernel<<<dim3((n + per_cta - 1) / per_cta, 2), 256, 0, stream>>>(pa, qa);
+  }
   prof.end(FORMGPU_KG_ASSOC_NN, 1);
 }
 
@@ -719,6 +946,12 @@ void assoc_batch_launch(const AssocArgs *items_dev, int n_items, int max_query, 
                         Profiler &prof) {
   if (n_items <= 0 || max_query <= 0) return;
   prof.begin(FORMGPU_KG_ASSOC_NN);
+  if (lanes == 1) { // cell-ordered buckets: one thread per query
+    assoc_cells_batch_kernel<<<dim3((max_query + kCellQueryThreads - 1) / kCellQueryThreads, 2, n_items),
+                               kCellQueryThreads, 0, stream>>>(items_dev);
+    prof.end(FORMGPU_KG_ASSOC_NN, 1);
+    return;
+  }
   const auto grid = [&](int per_cta) { return dim3((max_query + per_cta - 1) / per_cta, 2, n_items); };
   switch (lanes) {
   case 2: assoc_nn_batch_kernel<2><<<grid(queries_per_cta(2)), 256, 0, stream>>>(items_dev); break;

@@ -22,7 +22,11 @@
 #pragma once
 
 #include "form/constraints.hpp"
+// FORM_HOTPATH_INJECTED_ONLY (test infrastructure: the oracle library): the estimator only ever
+// runs over an injected HotPath and the translation unit must not reference the CUDA library.
+#ifndef FORM_HOTPATH_INJECTED_ONLY
 #include "form/gpu_hotpath.hpp"
+#endif
 #include "form/hotpath.hpp"
 #include "form/keyscanner.hpp"
 #include "form/pose3.hpp"
@@ -78,9 +82,13 @@ public:
   extract(const std::vector<Point> &scan, size_t scan_idx) const {
     static_assert(sizeof(Point) == sizeof(PointXYZf), "scan points must be 16-byte x,y,z,_ floats");
     if (!m_hotpath) {
+#ifndef FORM_HOTPATH_INJECTED_ONLY
       HotPathParams hp;
       fill(hp);
       m_hotpath = std::make_shared<GpuHotPath>(hp, 0, nullptr, 2);
+#else
+      throw HotPathError("FeatureExtractor: no hot path injected");
+#endif
     }
     std::vector<PlanarFeat> planar;
     std::vector<PointFeat> point;
@@ -161,10 +169,14 @@ struct Estimator {
         m_constraints(params.constraints), m_matcher{params.matcher}, m_keyscanner(params.scans),
         m_keypoint_map{params.map, nullptr}, m_hotpath(std::move(hotpath)) {
     if (!m_hotpath) {
+#ifndef FORM_HOTPATH_INJECTED_ONLY
       const size_t window = 1 + params.scans.max_num_recent_scans +
                             (params.scans.max_num_keyscans > 0 ? (size_t)params.scans.max_num_keyscans + 1 : 64) + 2;
       m_hotpath = std::make_shared<GpuHotPath>(hotpath_params(params), params.device, nullptr,
                                                (int)std::min<size_t>(window, 128));
+#else
+      throw HotPathError("Estimator: no hot path injected");
+#endif
     }
     m_extractor.set_hotpath(m_hotpath);
     m_constraints.set_hotpath(m_hotpath.get());
