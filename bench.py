@@ -135,11 +135,17 @@ def algorithmic_bytes(s: dict, group: str) -> float:
     """Compulsory HBM bytes of one kernel group over the replayed region:
     every input read once, every output written once; re-reads that hit L2/smem are
     not counted."""
-    if group in ("lin_chunk", "lin_finalize"):
-        # lossless f32 SoA correspondences: 36 B planar, 24 B point (+ 728 B block per pair)
-        return 36.0 * s["lin_planar"] + 24.0 * s["lin_point"] + 728.0 * s["lin_pairs"]
-    if group in ("err_chunk", "err_finalize"):
-        return 36.0 * s["err_planar"] + 24.0 * s["err_point"] + 8.0 * s["err_pairs"]
+    if group == "lin_chunk":
+        # pair-moment kernel: every correspondence of an association streamed ONCE (lossless f32
+        # SoA, 36 B planar / 24 B point); the 1056 B cache entries it writes are < 2 % of that
+        return 36.0 * s["assoc_planar"] + 24.0 * s["assoc_point"]
+    if group == "lin_finalize":
+        # cached evaluation: 1056 B entry read + 728 B block written per pair
+        return (1056.0 + 728.0) * s["lin_pairs"]
+    if group == "err_chunk":
+        return 0.0
+    if group == "err_finalize":
+        return (1056.0 + 8.0) * s["err_pairs"]
     if group in ("extract_select", "extract_normals", "extract_pack"):
         # scan read (16 B/pt) + keypoint records written (32 B planar, 16 B point)
         return 16.0 * s["points"] + 32.0 * s["planar_kp"] + 16.0 * s["point_kp"]
@@ -152,22 +158,37 @@ def algorithmic_bytes(s: dict, group: str) -> float:
     return 0.0  # map_build / commit: the replay does not count their units
 
 
-# DRAM bytes actually moved per algorithmic byte, from the committed `ncu --set full` captures
-# of the batched kernels (dram__bytes_read.sum + dram__bytes_write.sum of a launch / its
-# algorithmic bytes).  assoc_nn (profiles/r02_ncu_full_metrics.txt): 9.06 MB for 147 456
-# queries (75.5 MB algorithmic) - hash slots and buckets are shared between queries and hit
-# L1/L2, and only the centre voxel plus the few unpruned neighbours are probed at all;
-# lin_chunk (profiles/r01b_ncu_full_metrics.txt): 51.9 MB for 49.5 MB of correspondences
-# (sector granularity at slice edges).
-NCU_TRAFFIC_RATIO = {"assoc_nn": 0.120, "lin_chunk": 1.05}
+def ncu_capture(group: str):
+    """DRAM traffic of one launch of a kernel group, MEASURED by `ncu --set full` (dram__bytes_read.sum
+    + dram__bytes_write.sum) and committed with the launch it belongs to in profiles/ncu_capture.json
+    (written from the .ncu-rep by profiles/ncu_capture.py).  Not scaled to this run: the entry names
+    its own launch (queries, duration), so the reader can compare bytes per unit."""
+    path = os.path.join(ROOT, "profiles", "ncu_capture.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(group)
+    except (OSError, ValueError):
+        return None
+
 
 
 def whole_step_bytes(s: dict) -> float:
-    """SURVEY 8(d) B_scan with this implementation's record sizes."""
+    """SURVEY 8(d) B_scan - the REFERENCE ALGORITHM's compulsory traffic (every linearisation
+    streams its correspondences) - with this implementation's record sizes."""
     return (16.0 * s["points"] + 32.0 * s["planar_kp"] + 16.0 * s["point_kp"]
             + s["assoc_queries"] * (32.0 + 27 * 16.0 + 32.0 + 16.0)
             + 36.0 * (s["lin_planar"] + s["err_planar"]) + 24.0 * (s["lin_point"] + s["err_point"])
             + 728.0 * s["lin_pairs"] + 8.0 * s["err_pairs"]
+            + 32.0 * s["novel_planar"] + 16.0 * s["novel_point"])
+
+
+def own_step_bytes(s: dict) -> float:
+    """The same step with THIS implementation's algorithm: correspondences are streamed once per
+    association (pair-moment cache), linearisations read and write per-pair records only."""
+    return (16.0 * s["points"] + 32.0 * s["planar_kp"] + 16.0 * s["point_kp"]
+            + s["assoc_queries"] * (32.0 + 27 * 16.0 + 32.0 + 16.0)
+            + 36.0 * s["assoc_planar"] + 24.0 * s["assoc_point"]
+            + (1056.0 + 728.0) * s["lin_pairs"] + (1056.0 + 8.0) * s["err_pairs"]
             + 32.0 * s["novel_planar"] + 16.0 * s["novel_point"])
 
 
@@ -199,7 +220,9 @@ def run_ours(args, rank, world, local_rank):
     rows, cols = synth.shape(args.sensor)
     n_points = rows * cols
     W, K = args.warmup, args.steps
-    S = W + K
+    P0 = max(0, args.preroll)
+    W0 = P0 + W  # first timed scan
+    S = W0 + K
     cores = host_cores()
     sched_cores = args.emulate_cores if args.emulate_cores > 0 else cores  # cores of the timed region
     M = args.sequences_per_gpu
@@ -211,16 +234,13 @@ def run_ours(args, rank, world, local_rank):
         need_128 = 128 * S * n_points * 16
         # (x3 headroom: on a 196 GB box one or two ranks take 128 sequences, four or eight take 64)
         M = 128 if psutil.virtual_memory().available / max(world, 1) >= 3 * need_128 else 64
-    # one host thread per batch, each mostly polling for its round's results: with a core per
-    # thread they spin; when a rank has fewer than 4 spare cores (8 ranks on a 16-core box) it
-    # still runs --yield-batches batches and the polling loops yield (FORMGPU_YIELD_WAIT, api.cu
-    # poll_relax); measured on 2 cores, 32 sequences: 1 spinning batch 2227 scans/s, 4 yielding
-    # batches 4280, 8 yielding batches 4807
+    # G batches (one stream each) driven by T host threads: a thread queues a round on each of
+    # its batches (formgpu_batch_submit_async) before it waits for the first, so G rounds are in
+    # flight however few cores the rank has.  T never exceeds the rank's spare cores, so the
+    # waiting threads spin without competing with each other (no FORMGPU_YIELD_WAIT).
     spare = max(1, sched_cores // max(world, 1) - 1)
-    yield_wait = spare < 4
-    if yield_wait:
-        os.environ["FORMGPU_YIELD_WAIT"] = "1"  # read at the library's first poll
-    G = max(1, min(args.batches_per_gpu, M, spare if not yield_wait else args.yield_batches))
+    G = max(1, min(args.batches_per_gpu, M))
+    T = max(1, min(G, spare, args.host_threads if args.host_threads > 0 else G))
     p = _capi.default_est_params(rows, cols, record_trace=1, device=local_rank)
     pool = ThreadPoolExecutor(max_workers=max(1, min(16, cores // max(world, 1))))
 
@@ -274,14 +294,14 @@ def run_ours(args, rank, world, local_rank):
         events on the current stream around a full-device synchronize on both sides."""
         reps = [BatchReplay([traces[i] for i in grp], p) for grp in groups]
         gptrs = [[ptr_table[i] for i in grp] for grp in groups]
-        run_batches(reps, 0, W, gptrs, on_device)  # warm-up: fills every fixed-lag window
+        run_batches(reps, 0, W0, gptrs, on_device, T)  # pre-roll + warm-up: fills every fixed-lag window
         for r_ in reps:
             r_.reset_stats()
         launches0 = sum(r_.launch_count() for r_ in reps)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         a.record()
-        t_host = run_batches(reps, W, S, gptrs, on_device)
+        t_host = run_batches(reps, W0, S, gptrs, on_device, T)
         torch.cuda.synchronize()
         b.record()
         torch.cuda.synchronize()
@@ -310,18 +330,18 @@ def run_ours(args, rank, world, local_rank):
     # ---- per-kernel-group CUDA-event timing of the same region: ONE batch with all M
     # sequences, events around every launch (this inflates short launches by a few us) ----
     rp = BatchReplay(traces, p)
-    rp.run(0, W, dev_ptrs)
+    rp.run(0, W0, dev_ptrs)
     rp.reset_stats()
     rp.profile_read()
     rp.profile_enable(True)
-    t_prof, rounds = rp.run(W, S, dev_ptrs)
+    t_prof, rounds = rp.run(W0, S, dev_ptrs)
     prof = rp.profile_read()
     rp.profile_enable(False)
     stats_p = rp.stats()
     rp.close()
 
     # ---- latency mode: ONE sequence, the single-context entry points ----
-    single = run_single(torch, Replay, traces[0], p, dev_ptrs[0], host_np[0], W, S, n_points)
+    single = run_single(torch, Replay, traces[0], p, dev_ptrs[0], host_np[0], W0, S, n_points)
 
     # max over ranks, whole-job aggregate
     if dist is not None:
@@ -348,14 +368,19 @@ def run_ours(args, rank, world, local_rank):
                      "achieved_GBps": round(ab / (ms / 1e3) / 1e9, 1),
                      "frac": round(ab / (ms / 1e3) / 1e9 / peak, 4),
                      "share_of_gpu_time": round(ms / total_kernel_ms, 4)}
+        cap = ncu_capture(dom)
         roofline = {
             "bound": "hbm", "kernel": dom, "achieved": kg[dom]["achieved_GBps"], "peak": peak,
             "unit": "GB/s", "frac": kg[dom]["frac"],
-            "traffic": (round(NCU_TRAFFIC_RATIO[dom] * kg[dom]["algorithmic_MB_per_launch"] * 1e6)
-                        if dom in NCU_TRAFFIC_RATIO else None),
-            "traffic_source": "ncu dram bytes per algorithmic byte of this kernel (profiles/"
-                              "r02_ncu_full_metrics.txt, r01b_ncu_full_metrics.txt) x this run's "
-                              "algorithmic bytes per launch",
+            # measured DRAM bytes of ONE launch of this kernel (ncu --set full), with the launch it
+            # was measured on; null when no capture of the dominant kernel is committed
+            "traffic": cap["dram_bytes"] if cap else None,
+            "traffic_capture": cap,
+            "dram_frac": round(cap["dram_GBps"] / peak, 4) if cap else None,
+            "note": "frac = SURVEY 8(d) algorithmic bytes (the reference algorithm's probes: 27 hash slots "
+                    "per query) / CUDA-event time; the kernel keeps its working set in L1/L2 and is bound "
+                    "by instruction issue and L2 latency, so dram_frac (measured DRAM bytes / time / peak) "
+                    "is what it really asks of HBM",
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": round(kg[dom]["algorithmic_MB_per_launch"] * 1e6),
             "avg_launch_us": kg[dom]["avg_launch_us"], "launches": kg[dom]["launches"],
@@ -365,13 +390,17 @@ def run_ours(args, rank, world, local_rank):
             "kernel_groups": kg,
             "whole_step_algorithmic_GBps": round(whole_step_bytes(stats_d) / t_value / 1e9, 2),
             "whole_step_frac": round(whole_step_bytes(stats_d) / t_value / 1e9 / peak, 4),
+            "whole_step_note": "reference algorithm's compulsory bytes per step (every linearisation "
+                               "streams its correspondences) / measured step time",
+            "own_algorithm_step_GBps": round(own_step_bytes(stats_d) / t_value / 1e9, 2),
+            "own_algorithm_step_frac": round(own_step_bytes(stats_d) / t_value / 1e9 / peak, 4),
         }
         h2d = 16.0 * n_points  # the scan (requests are < 1% of it)
         d2h = (72.0 * stats_h["planar_kp"] + 40.0 * stats_h["point_kp"] + 728.0 * stats_h["lin_pairs"]
                + 8.0 * stats_h["err_pairs"] + stats_h["assoc_calls"] * 4 * 4 * (p.hot.max_window_scans + 1)) / (M * K)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline_multi(args, rows, cols, W, S, host_np)
+            cpu = cpu_baseline_multi(args, rows, cols, W0, S, host_np)
         n_seq_scans = M * S
         result = {
             "metric": METRIC, "value": round(value, 3),
@@ -383,8 +412,13 @@ def run_ours(args, rank, world, local_rank):
                 "workload": SENSOR_OF_WORKLOAD[args.sensor] + f"; {M} independent sequences per GPU "
                             f"advanced in lock step (formgpu_batch_submit), {G} concurrent batches",
                 "sensor": args.sensor, "rows": rows, "cols": cols, "scans_per_sequence": S,
+                "preroll_scans": P0,
+                "steady_state": f"{P0} untimed pre-roll scans + {W} warm-up scans per sequence precede the "
+                                f"timed ones, so the fixed-lag window is at its steady size from the first "
+                                f"timed scan whatever --warmup is",
                 "sequences_per_gpu": M, "batches_per_gpu": G, "sequences": world * M,
-                "host_wait": "yield (fewer spare host cores than batches)" if yield_wait else "spin",
+                "host_threads_per_gpu": T,
+                "host_wait": "spin; a thread pipelines its batches (submit_async to each, then wait)",
                 "step": "hot-path calls of one scan of one sequence, replayed from the recorded pipeline "
                         "trace; `steps` timed scans per sequence after `warmup` untimed ones",
                 "l2": f"inputs larger than L2: every round touches {M} scans + {M} maps (> 126 MB); no flush",
@@ -394,6 +428,9 @@ def run_ours(args, rank, world, local_rank):
                 "icp_iterations_per_scan": round(est_stats["icp_iterations"] / n_seq_scans, 2),
                 "lm_iterations_per_scan": round(est_stats["lm_iterations"] / n_seq_scans, 2),
                 "lm_schedule": "fused: trial steps are linearised (error = f/2), accepted blocks reused",
+                "stage3": "pair-moment cache: correspondences streamed once per association, every "
+                          "linearize / error call is a per-pair 13x13 congruence (moments.cu)",
+                "correspondences_streamed_per_step": round((stats_d["assoc_planar"] + stats_d["assoc_point"]) / (M * K)),
                 "window_size_mean": round(est_stats["window_size"] / M, 1),
                 "pipeline_final_position_error_m": round(final_err, 4),
                 "assoc_calls_per_step": round(stats_d["assoc_calls"] / (M * K), 2),
@@ -410,6 +447,11 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(gpu_launches),
             "roofline": roofline,
             "single_sequence": single,
+            "live_pipeline": {
+                "value": round(M * S / t_record, 2), "unit": "scans/s",
+                "what": f"the untimed recording pass: {M} live form::Estimators (host smoother, key-scan "
+                        f"logic and LM in the loop, one private context each) on {pool._max_workers} host "
+                        f"threads, all {S} scans per sequence - the drop-in rate with nothing replayed"},
             "cpu_baseline": cpu,
         }
         if cpu:
@@ -480,28 +522,37 @@ def run_single(torch, Replay, trace, p, dev_ptrs, scans_np, W, S, n_points):
     }
 
 
-def cpu_multi_sequence(rows, cols, W, last, scans_of, n_workers):
+def cpu_multi_sequence(rows, cols, W, last, scans_of, n_workers, gtsam_schedule=1, live=None):
     """The multi-sequence job on the CPU oracle: one single-threaded worker per host core,
-    each recording (untimed, the reference's GTSAM LM schedule) and then replaying the
-    hot-path calls of scans W..last-1 of its own sequence after an untimed window warm-up.
+    each recording (untimed) and then replaying the hot-path calls of scans W..last-1 of its
+    own sequence after an untimed window warm-up.  gtsam_schedule=1: the reference's LM schedule
+    (one linearisation per iteration + one error evaluation per trial); 0: the fused schedule
+    our arm replays (every trial linearised).  `live` (a dict) receives the rate of the recording
+    pass itself - the whole pipeline with the host smoother in the loop - over scans W..last-1.
     Returns (scans/s over all workers, seconds)."""
     import oracle_lib
     from form_b200 import _capi
 
-    p = _capi.default_est_params(rows, cols, record_trace=1, gtsam_lm_schedule=1, num_threads=1)
+    p = _capi.default_est_params(rows, cols, record_trace=1, gtsam_lm_schedule=gtsam_schedule, num_threads=1)
 
     def prepare(w):
         scans = scans_of(w)
         est = oracle_lib.OracleEstimator(p)
-        for s in scans[:last]:
+        for s in scans[:W]:
             est.register_scan(s)
+        t0 = time.perf_counter()
+        for s in scans[W:last]:
+            est.register_scan(s)
+        t_live = time.perf_counter() - t0
         ro = oracle_lib.OracleReplay(est.trace(), p)
         ro.run_host(0, W, scans)
         ro.reset_stats()
-        return est, ro, scans
+        return est, ro, scans, t_live
 
     with ThreadPoolExecutor(max_workers=n_workers) as ex:
         prepared = list(ex.map(prepare, range(n_workers)))
+        if live is not None:
+            live["value"] = round(sum((last - W) / pr[3] for pr in prepared), 4)
         t0 = time.perf_counter()
         list(ex.map(lambda pr: pr[1].run_host(W, last, pr[2]), prepared))
         dt = time.perf_counter() - t0
@@ -529,9 +580,20 @@ def cpu_baseline_multi(args, rows, cols, W, S, host_np):
     last = min(S, W + max(1, args.cpu_sample))
     n = last - W
     workers = min(cores, len(host_np))
-    value, dt = cpu_multi_sequence(rows, cols, W, last, lambda w: [host_np[w][k] for k in range(S)], workers)
+    scans_of = lambda w: [host_np[w][k] for k in range(S)]  # noqa: E731
+    live = {}
+    value, dt = cpu_multi_sequence(rows, cols, W, last, scans_of, workers, 1, live)
+    fused, _ = cpu_multi_sequence(rows, cols, W, last, scans_of, workers, 0)
     single = cpu_single_sequence(rows, cols, W, last, [host_np[0][k] for k in range(S)])
     return {"value": round(value, 4), "unit": "scans/s", "cores": workers, "kind": "port",
+            "lm_schedule": "the reference's (GTSAM): one linearisation per LM iteration + one error "
+                           "evaluation per trial step",
+            "fused_schedule_value": round(fused, 4),
+            "fused_schedule_note": "the same CPU job replaying the schedule our arm replays (every trial "
+                                   "step linearised, accepted blocks reused): same iterates, more CPU work",
+            "live_pipeline_value": live.get("value"),
+            "live_pipeline_note": "the recording pass itself: the whole pipeline with the host smoother in "
+                                  "the loop, one single-threaded sequence per host core",
             "sample": f"{workers} sequences x {n} scans (scans {W}..{last - 1}) after an untimed {W}-scan "
                       f"window warm-up: one single-threaded oracle replay per host core, {round(dt, 1)} s; "
                       f"oracle/ C++17 restatement, -O3 no -march",
@@ -549,7 +611,7 @@ def run_reference(args, rank, world):
     from form_b200 import synth
 
     rows, cols = synth.shape(args.sensor)
-    W, K = args.warmup, args.steps
+    W, K = args.preroll + args.warmup, args.steps  # same pre-roll + warm-up as our arm
     S = W + K
     cores = host_cores()
     workers = cores if args.sequences_per_gpu <= 0 else min(cores, args.sequences_per_gpu)
@@ -567,7 +629,7 @@ def run_reference(args, rank, world):
                      f"warm-up, one single-threaded replay per host core, {round(dt, 1)} s"}
     return {
         "impl": "reference", "metric": METRIC,
-        "value": round(value, 4), "unit": "scans/s", "n_gpus": world, "steps": n, "warmup": W,
+        "value": round(value, 4), "unit": "scans/s", "n_gpus": world, "steps": n, "warmup": args.warmup,
         "ms_per_step": round(1e3 / value, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": DTYPE,
         "data": "synthetic", "mpoints_per_s": round(value * n_points / 1e6, 4),
@@ -588,13 +650,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=40)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sensor", default="os0-128", choices=sorted(SENSOR_OF_WORKLOAD))
-    ap.add_argument("--cpu-sample", type=int, default=30, help="scans per sequence timed on the CPU")
+    ap.add_argument("--cpu-sample", type=int, default=20, help="scans per sequence timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sequences-per-gpu", type=int, default=0,
                     help="independent sequences sharing one GPU (0 = 128 if host memory allows, else 64)")
     ap.add_argument("--only-value", action="store_true", help="development: only the device-resident leg")
-    ap.add_argument("--yield-batches", type=int, default=8,
-                    help="batches per GPU when the rank has fewer than 4 spare host cores (yielding waits)")
+    ap.add_argument("--host-threads", type=int, default=0,
+                    help="host threads driving the batches of a GPU (0 = one per batch, capped at the "
+                         "rank's spare cores); a thread pipelines the batches it owns")
+    ap.add_argument("--preroll", type=int, default=24,
+                    help="untimed scans per sequence BEFORE the warm-up, so that the fixed-lag window has "
+                         "reached its steady-state size whatever --warmup is")
     ap.add_argument("--emulate-cores", type=int, default=0,
                     help="development: restrict the timed legs to this many host cores (what a rank "
                          "gets on a box with few cores per GPU)")

@@ -253,7 +253,7 @@ FORMHOST_SYMBOLS = {
 REPLAY_STAT_NAMES = (
     "scans", "points", "planar_kp", "point_kp", "assoc_calls", "assoc_queries", "map_rebuilds",
     "map_points", "lin_calls", "lin_pairs", "lin_planar", "lin_point", "err_calls", "err_pairs",
-    "err_planar", "err_point", "novel_planar", "novel_point",
+    "err_planar", "err_point", "novel_planar", "novel_point", "assoc_planar", "assoc_point",
 )
 
 

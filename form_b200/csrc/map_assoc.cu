@@ -203,8 +203,13 @@ __device__ __forceinline__ void map_alloc_body(const MapArgs &a) {
   const uint32_t h = a.voxel_list[i];
   const uint32_t cnt = a.hash[h].count;
   a.hash[h].start = atomicAdd(a.cursor, cnt) + cnt;
-  // cell-ordered bucket (map_cells_body): the flag travels in the count's top bit
-  if (a.cells && cnt >= kCellMin && cnt <= kCellMax) a.hash[h].count = cnt | kCellFlag;
+  // cell-ordered bucket (map_cells_body): the flag travels in the count's top bit, and the voxel
+  // enters the list of cell-ordered voxels, which grows downwards from the end of voxel_list
+  // (occupied + cell-ordered voxels <= points, so the two lists cannot meet)
+  if (a.cells && cnt >= kCellMin && cnt <= kCellMax) {
+    a.hash[h].count = cnt | kCellFlag;
+    a.voxel_list[(uint32_t)a.n_total - 1u - atomicAdd(a.cursor + 2, 1u)] = h;
+  }
 }
 } // namespace
 __global__ void __launch_bounds__(256) map_alloc_kernel(MapArgs pa, MapArgs qa) {
@@ -273,62 +278,90 @@ __device__ __forceinline__ void map_cells_body(const MapArgs &a) {
   if (!a.cells || a.n_total <= 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   CellSmem &S = s_cells[warp];
-  const uint32_t n_vox = __ldcg(a.cursor + 1); // occupied voxels, listed by the insert pass
-  const uint32_t stride = gridDim.x * kCellWarps * 32u;
   const double w = a.voxel_width, inv_cw = (double)kCellSub * a.inv_voxel_width;
-  for (uint32_t base = (blockIdx.x * kCellWarps + warp) * 32u; base < n_vox; base += stride) {
-    HashSlot s;
-    s.key = 0ull;
-    s.start = s.count = 0u;
-    if (base + lane < n_vox) s = a.hash[a.voxel_list[base + lane]];
-    // small buckets: copied as they are, one lane per voxel
-    if (s.count != 0u && (s.count & kCellFlag) == 0u) {
-      for (uint32_t i = 0; i < s.count; ++i) {
-        a.world_tmp[s.start + i] = a.world[s.start + i];
-        a.world_slot[s.start + i] = a.world_src[s.start + i];
-      }
+  // ---- small buckets (< kCellMin points): copied as they are, one THREAD per voxel ----
+  const uint32_t n_vox = __ldcg(a.cursor + 1); // occupied voxels, listed by the insert pass
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vox; i += gridDim.x * blockDim.x) {
+    const HashSlot s = a.hash[a.voxel_list[i]];
+    if (s.count & kCellFlag) continue;
+    for (uint32_t k = 0; k < s.count; ++k) {
+      a.world_tmp[s.start + k] = a.world[s.start + k];
+      a.world_slot[s.start + k] = a.world_src[s.start + k];
     }
-    unsigned todo = __ballot_sync(0xffffffffu, (s.count & kCellFlag) != 0u);
-    while (todo) {
-      const int owner = __ffs(todo) - 1;
-      todo &= todo - 1u;
-      const uint32_t start = __shfl_sync(0xffffffffu, s.start, owner);
-      const uint32_t cnt = __shfl_sync(0xffffffffu, s.count, owner) & ~kCellFlag;
-      const unsigned long long key = __shfl_sync(0xffffffffu, s.key, owner);
-      const double lx = (double)unpack_coord(key, 42) * w, ly = (double)unpack_coord(key, 21) * w,
-                   lz = (double)unpack_coord(key, 0) * w;
-      S.hist[lane] = 0u;
-      S.hist[lane + 32] = 0u;
-      __syncwarp();
-      auto code_of = [&](const WorldPoint &p) {
-        return (cell_index(p.x - lx, inv_cw) * kCellSub + cell_index(p.y - ly, inv_cw)) * kCellSub +
-               cell_index(p.z - lz, inv_cw);
-      };
-      for (uint32_t i = lane; i < cnt; i += 32) atomicAdd(&S.hist[code_of(a.world[start + i])], 1u);
-      __syncwarp();
-      // exclusive prefix over the 64 bins, two per lane
-      const uint32_t c0 = S.hist[2 * lane], c1 = S.hist[2 * lane + 1];
-      uint32_t incl = c0 + c1;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+  }
+  // ---- cell-ordered buckets: one WARP per voxel ----
+  const uint32_t n_tab = __ldcg(a.cursor + 2); // listed by the alloc pass
+  const uint32_t n_warps = gridDim.x * kCellWarps;
+  for (uint32_t j = blockIdx.x * kCellWarps + warp; j < n_tab; j += n_warps) {
+    const HashSlot s = a.hash[a.voxel_list[(uint32_t)a.n_total - 1u - j]];
+    const uint32_t start = s.start, cnt = s.count & ~kCellFlag;
+    const double lx = (double)unpack_coord(s.key, 42) * w, ly = (double)unpack_coord(s.key, 21) * w,
+                 lz = (double)unpack_coord(s.key, 0) * w;
+    auto code_of = [&](const WorldPoint &p) {
+      return (cell_index(p.x - lx, inv_cw) * kCellSub + cell_index(p.y - ly, inv_cw)) * kCellSub +
+             cell_index(p.z - lz, inv_cw);
+    };
+    S.hist[lane] = 0u;
+    S.hist[lane + 32] = 0u;
+    __syncwarp();
+    // buckets of up to 64 points (most): a lane keeps its one or two points in registers, so
+    // the bucket is read once; larger ones are read twice
+    const bool in_regs = cnt <= 64u;
+    WorldPoint p0, p1;
+    uint32_t src0 = 0u, src1 = 0u;
+    int c0 = -1, c1 = -1;
+    if (in_regs) {
+      if ((uint32_t)lane < cnt) {
+        p0 = a.world[start + lane];
+        src0 = a.world_src[start + lane];
+        c0 = code_of(p0);
+        atomicAdd(&S.hist[c0], 1u);
       }
-      const uint32_t excl = incl - (c0 + c1);
-      S.cur[2 * lane] = excl;
-      S.cur[2 * lane + 1] = excl + c0;
-      __syncwarp();
+      if ((uint32_t)lane + 32u < cnt) {
+        p1 = a.world[start + lane + 32];
+        src1 = a.world_src[start + lane + 32];
+        c1 = code_of(p1);
+        atomicAdd(&S.hist[c1], 1u);
+      }
+    } else {
+      for (uint32_t i = lane; i < cnt; i += 32) atomicAdd(&S.hist[code_of(a.world[start + i])], 1u);
+    }
+    __syncwarp();
+    // exclusive prefix over the 64 bins, two per lane
+    const uint32_t h0 = S.hist[2 * lane], h1 = S.hist[2 * lane + 1];
+    uint32_t incl = h0 + h1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - (h0 + h1);
+    S.cur[2 * lane] = excl;
+    S.cur[2 * lane + 1] = excl + h0;
+    __syncwarp();
+    if (in_regs) {
+      if (c0 >= 0) {
+        const uint32_t pos = atomicAdd(&S.cur[c0], 1u);
+        a.world_tmp[start + pos] = p0;
+        a.world_slot[start + pos] = src0;
+      }
+      if (c1 >= 0) {
+        const uint32_t pos = atomicAdd(&S.cur[c1], 1u);
+        a.world_tmp[start + pos] = p1;
+        a.world_slot[start + pos] = src1;
+      }
+    } else {
       for (uint32_t i = lane; i < cnt; i += 32) {
         const WorldPoint p = a.world[start + i];
         const uint32_t pos = atomicAdd(&S.cur[code_of(p)], 1u);
         a.world_tmp[start + pos] = p;
         a.world_slot[start + pos] = a.world_src[start + i];
       }
-      __syncwarp(); // every read of the source bucket is done: its head becomes the table
-      // END offsets of cells 2 lane and 2 lane + 1 as one 32-bit word
-      reinterpret_cast<uint32_t *>(a.world + start)[lane] = (excl + c0) | ((excl + c0 + c1) << 16);
-      __syncwarp();
     }
+    __syncwarp(); // every read of the source bucket is done: its head becomes the table
+    // END offsets of cells 2 lane and 2 lane + 1 as one 32-bit word
+    reinterpret_cast<uint32_t *>(a.world + start)[lane] = (excl + h0) | ((excl + h0 + h1) << 16);
+    __syncwarp();
   }
 }
 } // namespace
@@ -362,8 +395,8 @@ void map_build_launch(const MapArgs &pa, const MapArgs &qa, cudaStream_t stream,
   map_scatter_kernel<<<gp, 256, 0, stream>>>(pa, qa);
   int launches = 3;
   if (pa.cells || qa.cells) {
-    // one warp takes 32 voxels per round; a bucket holds ~17 points on average
-    const unsigned blocks = std::max(1u, std::min<unsigned>((unsigned)nt / (16u * kCellWarps * 32u) + 1u, 4 * 148));
+    // grid-stride: a thread per small voxel, a warp per cell-ordered voxel (<= points / 16)
+    const unsigned blocks = std::max(1u, std::min<unsigned>((unsigned)nt / (16u * kCellWarps) + 1u, 8 * 148));
     map_cells_kernel<<<dim3(blocks, 2), kCellWarps * 32, 0, stream>>>(pa, qa);
     ++launches;
   }
@@ -386,7 +419,7 @@ void map_build_batch_launch(const MapArgs *items_dev, const MapClearRegion *regi
     launches += 3;
     if (cells) {
       const unsigned blocks =
-          std::max(1u, std::min<unsigned>((unsigned)max_points / (16u * kCellWarps * 32u) + 1u, 64u));
+          std::max(1u, std::min<unsigned>((unsigned)max_points / (16u * kCellWarps) + 1u, 512u));
       map_cells_batch_kernel<<<dim3(blocks, 2, n_items), kCellWarps * 32, 0, stream>>>(items_dev);
       ++launches;
     }

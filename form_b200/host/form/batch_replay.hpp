@@ -224,8 +224,11 @@ private:
       table.erase(std::remove_if(table.begin(), table.end(),
                                  [&](const auto &e) { return e.first.j == q.cur_scan; }),
                   table.end());
-      for (size_t c = 0; c < r.n_counts; ++c)
+      for (size_t c = 0; c < r.n_counts; ++c) {
         table.push_back({{q.counts[c].i, q.cur_scan}, {q.counts[c].n_planar, q.counts[c].n_point}});
+        st.assoc_planar += q.counts[c].n_planar;
+        st.assoc_point += q.counts[c].n_point;
+      }
     };
     switch (op.kind) {
     case TraceOp::EXTRACT:

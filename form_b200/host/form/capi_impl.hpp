@@ -192,7 +192,7 @@ inline void replay_stats(const ReplayHandle *r, uint64_t out[20], double *checks
   const uint64_t v[20] = {s.scans,       s.points,      s.planar_kp,   s.point_kp,  s.assoc_calls,
                           s.assoc_queries, s.map_rebuilds, s.map_points, s.lin_calls, s.lin_pairs,
                           s.lin_planar,  s.lin_point,   s.err_calls,   s.err_pairs, s.err_planar,
-                          s.err_point,   s.novel_planar, s.novel_point, 0,          0};
+                          s.err_point,   s.novel_planar, s.novel_point, s.assoc_planar, s.assoc_point};
   std::memcpy(out, v, sizeof(v));
   if (checksum) *checksum = s.checksum;
 }

@@ -123,6 +123,7 @@ struct ReplayStats {
   uint64_t lin_calls = 0, lin_pairs = 0, lin_planar = 0, lin_point = 0;
   uint64_t err_calls = 0, err_pairs = 0, err_planar = 0, err_point = 0;
   uint64_t novel_planar = 0, novel_point = 0;
+  uint64_t assoc_planar = 0, assoc_point = 0; // correspondences accepted by the associations
   double checksum = 0.0; // sum of every returned block / error, to keep the work observable
   // correspondence counts per live pair (carried across replay() calls)
   std::vector<std::pair<PairKey, std::pair<uint32_t, uint32_t>>> table;
@@ -167,7 +168,11 @@ inline void replay(const Trace &trace, HotPath &hp, size_t first, size_t last,
         table.erase(std::remove_if(table.begin(), table.end(),
                                    [&](const auto &e) { return e.first.j == cur_scan; }),
                     table.end());
-        for (const auto &c : counts) table.push_back({{c.i, cur_scan}, {c.n_planar, c.n_point}});
+        for (const auto &c : counts) {
+          table.push_back({{c.i, cur_scan}, {c.n_planar, c.n_point}});
+          st.assoc_planar += c.n_planar;
+          st.assoc_point += c.n_point;
+        }
         break;
       }
       case TraceOp::ASSOC_LIN: {
@@ -177,7 +182,11 @@ inline void replay(const Trace &trace, HotPath &hp, size_t first, size_t last,
         table.erase(std::remove_if(table.begin(), table.end(),
                                    [&](const auto &e) { return e.first.j == cur_scan; }),
                     table.end());
-        for (const auto &c : counts) table.push_back({{c.i, cur_scan}, {c.n_planar, c.n_point}});
+        for (const auto &c : counts) {
+          table.push_back({{c.i, cur_scan}, {c.n_planar, c.n_point}});
+          st.assoc_planar += c.n_planar;
+          st.assoc_point += c.n_point;
+        }
         st.lin_calls += 1;
         st.lin_pairs += counts.size();
         for (size_t p = 0; p < counts.size(); ++p) {

@@ -97,3 +97,16 @@ def test_trace_replay_device_host_and_oracle_agree():
     assert sh["checksum"] == sd["checksum"]  # same kernels, same order: deterministic
     assert abs(sh["checksum"] - so["checksum"]) <= 1e-8 * abs(so["checksum"])
     assert rd.launch_count() > 0
+
+
+def test_run_sequence_writes_evalio_trajectories(tmp_path):
+    """the trajectory of a run in evalio's CSV layout, next to the ground truth."""
+    from form_b200 import run_sequence, trajectory
+
+    run_sequence.main(["--sensor", "vlp-16", "--scans", "12", "--out", str(tmp_path)])
+    meta, st, tr, rot = trajectory.read_evalio_csv(tmp_path / "form.csv")
+    gmeta, gst, gtr, grot = trajectory.read_evalio_csv(tmp_path / "gt.csv")
+    assert meta["status"] == "complete" and meta["pipeline"] == "form" and gmeta["name"] == "gt"
+    assert len(st) == len(gst) == 12 and np.allclose(st, gst)
+    assert np.max(np.linalg.norm(tr - gtr, axis=1)) < 0.1  # 1 cm range noise, 1.1 m travelled
+    assert np.max(np.abs(rot - grot)) < 0.02
