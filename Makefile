@@ -13,7 +13,7 @@ CXXFLAGS  := -O3 -std=c++17 -fPIC -pthread -ffp-contract=off -Wall -Iinclude -If
 LIBDIR    := form_b200/lib
 OBJDIR    := build/obj
 
-GPU_OBJS  := $(OBJDIR)/extract.o $(OBJDIR)/map_assoc.o $(OBJDIR)/linearize.o $(OBJDIR)/moments.o $(OBJDIR)/api.o $(OBJDIR)/api_stage2.o $(OBJDIR)/api_stage3.o $(OBJDIR)/api_batch.o
+GPU_OBJS  := $(OBJDIR)/extract.o $(OBJDIR)/map_assoc.o $(OBJDIR)/linearize.o $(OBJDIR)/moments.o $(OBJDIR)/api.o $(OBJDIR)/api_stage2.o $(OBJDIR)/api_stage3.o $(OBJDIR)/api_batch.o $(OBJDIR)/comm.o
 HOST_SRCS := $(wildcard form_b200/host/src/*.cpp)
 HOST_OBJS := $(HOST_SRCS:form_b200/host/src/%.cpp=$(OBJDIR)/host_%.o)
 CSRC_HDRS := $(wildcard form_b200/csrc/*.hpp) $(wildcard form_b200/csrc/*.cuh) include/formgpu.h
@@ -43,7 +43,7 @@ $(OBJDIR)/%.o: form_b200/csrc/%.cu $(CSRC_HDRS)
 
 $(LIBDIR)/libformgpu.so: $(GPU_OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(ARCH) -shared -o $@ $(GPU_OBJS) -cudart static
+	$(NVCC) $(ARCH) -shared -o $@ $(GPU_OBJS) -cudart static -ldl
 
 $(OBJDIR)/host_%.o: form_b200/host/src/%.cpp $(HOST_HDRS)
 	@mkdir -p $(OBJDIR)

@@ -174,6 +174,9 @@ FORMGPU_SYMBOLS = {
     "formgpu_launch_count": (_u64, [_vp]),
     "formgpu_synchronize": (_i, [_vp]),
     "formgpu_set_shard": (_i, [_vp, _i, _i]),
+    "formgpu_comm_unique_id": (_i, [_vp]),
+    "formgpu_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "formgpu_comm_destroy": (_i, [_vp]),
     "formgpu_linearize_device": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "formgpu_error_device": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "formgpu_batch_create": (_i, [C.POINTER(Params), _i, _vp, _sz, C.POINTER(_vp)]),

@@ -173,6 +173,27 @@ class Context:
         return out
 
     # -- point-sharded mode ----------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """formgpu_comm_unique_id: 128 bytes one rank creates and every rank passes to comm_init."""
+        import ctypes as C
+
+        buf = C.create_string_buffer(128)
+        rc = _capi.gpu_lib().formgpu_comm_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError(f"formgpu_comm_unique_id failed ({rc}): NCCL not available?")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """formgpu_comm_init: make this context rank `rank` of a point-sharded sequence (collective)."""
+        import ctypes as C
+
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.formgpu_comm_init(self._h, buf, rank, world))
+
+    def comm_destroy(self):
+        self._check(self._lib.formgpu_comm_destroy(self._h))
+
     def set_shard(self, rank: int, world: int):
         """Stage-3 calls reduce only the rank-th of `world` shares of every pair (the caller
         sums the blocks over the ranks); (0, 1) switches the mode off."""

@@ -195,6 +195,7 @@ static int create_impl(formgpu_ctx *ctx) {
   FORMGPU_CUDA(ctx, extract_configure(ctx->cols, ctx->words * 32, ctx->words, ctx->pr_cap));
   FORMGPU_CUDA(ctx, linearize_configure());
   if (const char *env = std::getenv("FORMGPU_CELL_BUCKETS")) ctx->cell_buckets = env[0] != '0';
+  if (const char *env = std::getenv("FORMGPU_SINGLE_CELL_SEARCH")) ctx->cell_search_single = env[0] == '1';
 
   // window / keypoint store
   ctx->slot_scan.assign(W, 0);
@@ -225,8 +226,9 @@ static int create_impl(formgpu_ctx *ctx) {
   FORMGPU_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_upload, cudaEventDisableTiming));
 
   // matches / correspondences
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_match[0], ctx->kp_cap));
-  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_match[1], ctx->kq_cap));
+  // + 64: the in-place all-gather of point-sharded mode rounds every rank's share up
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_match[0], ctx->kp_cap + 64));
+  FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_match[1], ctx->kq_cap + 64));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_seg_planar, W * 9 * ctx->kp_cap));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_seg_point, W * 6 * ctx->kq_cap));
   for (int t = 0; t < 2; ++t) {
@@ -309,6 +311,7 @@ void formgpu_destroy(formgpu_ctx *ctx) {
   F(ctx->d_seg_planar); F(ctx->d_seg_point); F(ctx->d_pair);
   F(ctx->d_partials); F(ctx->d_request); F(ctx->d_counters);
   F(ctx->d_moments); F(ctx->d_mom_partials); F(ctx->d_mom_tickets);
+  comm_release(ctx);
   if (ctx->h_flags) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_flags));
   H(ctx->h_counts); H(ctx->h_planar); H(ctx->h_point); H(ctx->h_upload);
   if (ctx->h_out) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_out));

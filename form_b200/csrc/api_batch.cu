@@ -348,7 +348,7 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       return bfail(b, FORMGPU_ERR_INVALID_ARG, "formgpu_batch_submit: bad sequence index or op");
     if (seen[q.sequence])
       return bfail(b, FORMGPU_ERR_INVALID_ARG, "formgpu_batch_submit: two requests for one sequence");
-    if (b->ctx[q.sequence]->shard_world > 1)
+    if (b->ctx[q.sequence]->shard_world > 1 || b->ctx[q.sequence]->comm)
       return bfail(b, FORMGPU_ERR_UNSUPPORTED,
                    "formgpu_batch_submit: point-sharded contexts (formgpu_set_shard) are not batched");
     seen[q.sequence] = 1;

@@ -55,6 +55,8 @@ void poll_relax(unsigned spins);
 void relative_pose(const formgpu_pose &Ti, const formgpu_pose &Tj, double rel[12]);
 /// true: linearize / error of this context are evaluated from the pair-moment cache
 inline bool use_moment_cache(const formgpu_ctx *ctx) { return ctx->moment_cache && ctx->shard_world == 1; }
+/// true: the context is one rank of a point-sharded sequence (formgpu_comm_init)
+inline bool sharded_comm(const formgpu_ctx *ctx) { return ctx->comm != nullptr && ctx->comm_world > 1; }
 /// Launch one cluster per task - or, from the moment cache, one warp per task (no wait).
 /// Assigns and returns the sequence number.
 int lin_launch(formgpu_ctx *ctx, const std::vector<LinTask> &tasks, bool error_only,
@@ -124,6 +126,15 @@ struct CommitPlan {
 };
 int commit_prepare(formgpu_ctx *ctx, CommitPlan &plan);
 void commit_finish(formgpu_ctx *ctx, const CommitPlan &plan);
+
+/// Point-sharded mode over NCCL (comm.cu): collectives queued on the context's stream.
+int comm_allgather_matches(formgpu_ctx *ctx, int type, int n_query);
+int comm_allreduce_f64(formgpu_ctx *ctx, double *dev, size_t count);
+int comm_ensure_reduce(formgpu_ctx *ctx, size_t doubles);
+void comm_release(formgpu_ctx *ctx);
+/// Blocks / errors of a request in point-sharded mode: d_red holds this rank's partial results
+/// (n_pairs * per_pair doubles, zero for pairs without a task); all-reduce, copy out.
+int lin_collect_comm(formgpu_ctx *ctx, size_t n_pairs, size_t per_pair, double *out);
 
 /// Ensure the pinned upload / result staging buffers are large enough.
 int ensure_upload(formgpu_ctx *ctx, size_t bytes);

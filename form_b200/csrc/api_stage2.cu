@@ -213,6 +213,13 @@ int assoc_prepare(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_sc
     const size_t kcap = t == 0 ? ctx->kp_cap : ctx->kq_cap;
     aa[t].type = t;
     aa[t].n_query = nq[t];
+    aa[t].q_begin = 0;
+    aa[t].q_end = nq[t];
+    if (sharded_comm(ctx)) { // this rank's share of the keypoints (equal chunks: in-place all-gather)
+      const int chunk = (nq[t] + ctx->comm_world - 1) / ctx->comm_world;
+      aa[t].q_begin = std::min(nq[t], chunk * ctx->comm_rank);
+      aa[t].q_end = std::min(nq[t], chunk * (ctx->comm_rank + 1));
+    }
     aa[t].n_map = (int)ctx->map_n[t];
     aa[t].queries = queries;
     std::memcpy(aa[t].pose, pose_k, 12 * sizeof(double));
@@ -268,8 +275,10 @@ int assoc_prepare(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_sc
   m.tickets = ctx->d_mom_tickets;
   m.W = W;
   m.n_pairs = W;
-  m.shard_rank = 0; // the cache always holds the whole pair; sharded contexts stream (lin_launch)
-  m.shard_world = 1;
+  // formgpu_set_shard contexts stream their share at linearisation time (lin_launch) and keep
+  // whole pairs here; ranks of a communicator accumulate their share of every pair
+  m.shard_rank = sharded_comm(ctx) ? ctx->comm_rank : 0;
+  m.shard_world = sharded_comm(ctx) ? ctx->comm_world : 1;
   for (int i = 0; i < W; ++i) m.slots[i] = (unsigned char)i;
   plan.mom_units = std::min(ctx->mom_max_units, moment_max_units((size_t)nq[0] + (size_t)nq[1], W));
   return FORMGPU_OK;
@@ -331,8 +340,17 @@ int assoc_finish(formgpu_ctx *ctx, AssocPlan &plan, const formgpu_scan_pose *pos
           return fail(ctx, FORMGPU_ERR_INVALID_ARG, "associate_linearize: no pose for a matched scan");
         idx.push_back((int)(it - plan.lin_slots.begin()));
       }
-      const int rc = lin_wait(ctx, idx.data(), idx.size(), plan.lin_seq, 91, out91);
-      if (rc) return rc;
+      if (sharded_comm(ctx)) {
+        // partial blocks of all plan.lin_tasks sit in d_red: all-reduce, then pick the non-empty pairs
+        std::vector<double> all(91 * plan.lin_tasks.size());
+        const int rc = lin_collect_comm(ctx, plan.lin_tasks.size(), 91, all.data());
+        if (rc) return rc;
+        for (size_t k = 0; k < idx.size(); ++k)
+          std::memcpy(out91 + 91 * k, all.data() + 91 * (size_t)idx[k], 91 * sizeof(double));
+      } else {
+        const int rc = lin_wait(ctx, idx.data(), idx.size(), plan.lin_seq, 91, out91);
+        if (rc) return rc;
+      }
     } else if (!out.empty()) {
       // nothing was matched in this call (no keypoints): linearise what is there
       std::vector<formgpu_pair> pairs;
@@ -357,12 +375,32 @@ static int associate_impl(formgpu_ctx *ctx, const formgpu_pose *pose_k, const fo
   int rc = assoc_prepare(ctx, pose_k, poses, n_poses, out91 != nullptr, plan);
   if (rc) return rc;
   if (plan.any_query) {
-    assoc_launch(plan.aa[0], plan.aa[1], ctx->stream, ctx->prof);
+    if (sharded_comm(ctx)) {
+      // the association kernels see this rank's queries only: matches are all-gathered in place,
+      // then every rank builds the histogram over all of them
+      AssocArgs part[2] = {plan.aa[0], plan.aa[1]};
+      part[0].hist_cnt = part[1].hist_cnt = nullptr;
+      assoc_launch(part[0], part[1], ctx->cell_search_single, ctx->stream, ctx->prof);
+      for (int t = 0; t < 2; ++t) {
+        rc = comm_allgather_matches(ctx, t, plan.nq[t]);
+        if (rc) return rc;
+      }
+      assoc_hist_launch(plan.aa[0], plan.aa[1], ctx->stream, ctx->prof);
+    } else {
+      assoc_launch(plan.aa[0], plan.aa[1], ctx->cell_search_single, ctx->stream, ctx->prof);
+    }
     segment_build_launch(plan.sa[0], plan.sa[1], ctx->stream, ctx->prof);
     if (ctx->moment_cache) moments_launch(plan.ma, plan.mom_units, ctx->stream, ctx->prof);
     FORMGPU_CUDA(ctx, cudaGetLastError());
     if (plan.fused) {
-      rc = lin_launch(ctx, plan.lin_tasks, false, &plan.lin_seq);
+      if (sharded_comm(ctx)) {
+        rc = comm_ensure_reduce(ctx, 91 * (plan.lin_tasks.size() + 1));
+        if (rc) return rc;
+        FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_red, 0, 91 * plan.lin_tasks.size() * sizeof(double), ctx->stream));
+        rc = lin_launch(ctx, plan.lin_tasks, false, &plan.lin_seq, ctx->d_red);
+      } else {
+        rc = lin_launch(ctx, plan.lin_tasks, false, &plan.lin_seq);
+      }
       if (rc) return rc;
     }
   }

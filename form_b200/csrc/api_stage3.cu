@@ -152,6 +152,18 @@ int lin_build_tasks(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
   return FORMGPU_OK;
 }
 
+int lin_collect_comm(formgpu_ctx *ctx, size_t n_pairs, size_t per_pair, double *out) {
+  const size_t count = n_pairs * per_pair;
+  if (count == 0) return FORMGPU_OK;
+  int rc = comm_allreduce_f64(ctx, ctx->d_red, count);
+  if (rc) return rc;
+  FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->h_red, ctx->d_red, count * sizeof(double), cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+  FORMGPU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::memcpy(out, ctx->h_red, count * sizeof(double));
+  return FORMGPU_OK;
+}
+
 int lin_collect(formgpu_ctx *ctx, const std::vector<int> &indices, unsigned long long seq,
                 size_t per_pair, double *out) {
   // decode into a dense scratch, then scatter to the pairs' positions
@@ -182,6 +194,16 @@ int run(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs, const formg
   if (rc) return rc;
   unsigned long long seq = 0;
   const auto t1 = clk::now();
+  if (sharded_comm(ctx)) {
+    // every rank evaluates the pairs from its partial moments into d_red (zeros for pairs without
+    // a task), one all-reduce sums the blocks, the result is copied out
+    rc = comm_ensure_reduce(ctx, n_pairs * per_pair);
+    if (rc) return rc;
+    FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_red, 0, n_pairs * per_pair * sizeof(double), ctx->stream));
+    rc = lin_launch(ctx, tasks, error_only, &seq, ctx->d_red);
+    if (rc) return rc;
+    return lin_collect_comm(ctx, n_pairs, per_pair, out);
+  }
   rc = lin_launch(ctx, tasks, error_only, &seq);
   if (rc) return rc;
   const auto t2 = clk::now();

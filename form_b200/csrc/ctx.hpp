@@ -211,6 +211,9 @@ struct formgpu_ctx {
   // voxel buckets ordered by 4x4x4 sub-cells, association searches cell by cell (default);
   // FORMGPU_CELL_BUCKETS=0 at formgpu_create keeps the whole-bucket scans
   bool cell_buckets = true;
+  // single-sequence associations: warp-per-query whole-bucket search (lowest latency, default) or,
+  // with FORMGPU_SINGLE_CELL_SEARCH=1, the cell search of the batched submits (tests)
+  bool cell_search_single = false;
   void *d_export = nullptr;           // lazily allocated world export buffer
   size_t export_bytes = 0;
 
@@ -241,6 +244,11 @@ struct formgpu_ctx {
 
   // ---- point-sharded mode (formgpu_set_shard) ----
   int shard_rank = 0, shard_world = 1;
+  // ---- point-sharded mode over NCCL (formgpu_comm_init, comm.cu) ----
+  void *comm = nullptr; // ncclComm_t
+  int comm_rank = 0, comm_world = 1;
+  double *d_red = nullptr, *h_red = nullptr; // blocks / errors of a request: all-reduced, then copied out
+  size_t red_cap = 0;
 
   // ---- pair-moment cache (moments.cu) ----
   // [W(j)][W(i)][kMomentStride] doubles: moments of pair (i, j) left by scan j's last association

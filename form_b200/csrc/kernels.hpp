@@ -101,6 +101,9 @@ struct AssocArgs {
   int type;
   int n_query;
   int n_map;
+  // queries this launch searches: [q_begin, q_end) - the whole scan, or this rank's share of it
+  // in point-sharded mode (the other ranks' matches arrive by all-gather)
+  int q_begin, q_end;
   const void *queries; // PlanarRec* / PointRec* of the current scan
   double pose[12];     // pose of the current scan
   double voxel_width;
@@ -116,9 +119,17 @@ struct AssocArgs {
   // fused histogram: matches per (256-query block, matched slot), entry W = novel keypoints
   int W;
   double max_dist2, min_dist2;
-  uint32_t *hist_cnt;      // [blocks256][W+1] atomic counters, zero on entry
+  uint32_t *hist_cnt;      // [blocks256][W+1] atomic counters, zero on entry; nullptr: the
+                           // histogram is built by assoc_hist_launch once all matches are there
 };
-void assoc_launch(const AssocArgs &planar, const AssocArgs &point, cudaStream_t stream, Profiler &prof);
+/// Histogram of the matches by matched scan (+ novel count) as the association kernels build it
+/// themselves when they see every query: point-sharded mode runs it after the all-gather.
+void assoc_hist_launch(const AssocArgs &planar, const AssocArgs &point, cudaStream_t stream, Profiler &prof);
+/// One sequence: `cell_search` = the one-thread-per-query search over the cell-ordered buckets (what
+/// batched submits always use); otherwise one WARP per query scans whole buckets - the lower
+/// latency for a single scan's ~30 k queries, which cannot fill the GPU either way.
+void assoc_launch(const AssocArgs &planar, const AssocArgs &point, bool cell_search, cudaStream_t stream,
+                  Profiler &prof);
 /// `lanes` = lanes that share one query in the batched kernel (2, 4 or 8; kAssocLanes by default,
 /// FORMGPU_ASSOC_LANES overrides it per batch for tuning).
 constexpr int kAssocLanes = 4;

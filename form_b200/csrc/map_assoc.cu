@@ -504,7 +504,7 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
   const int warp = threadIdx.x >> 5;
   const int q = (blockIdx.x * (blockDim.x >> 5) + warp) * kGroups + grp;
   const int nb = a.W + 1;
-  const bool active = q < a.n_query; // whole groups are active or not; shuffles need every lane
+  const bool active = q >= a.q_begin && q < a.q_end; // whole groups are active or not; shuffles need every lane
   const bool searchable = active && a.n_map > 0;
   double x = 0.0, y = 0.0, z = 0.0;
   if (active) {
@@ -651,9 +651,11 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
     }
     a.match[q] = m;
     // per-256-query histogram of the accepted matches by matched scan (+ novel count)
-    const int bin = match_bin(m, a.max_dist2);
-    if (bin >= 0) atomicAdd(&a.hist_cnt[(size_t)(q >> 8) * nb + bin], 1u);
-    if (m.dist_sqrd > a.min_dist2) atomicAdd(&a.hist_cnt[(size_t)(q >> 8) * nb + a.W], 1u);
+    if (a.hist_cnt) {
+      const int bin = match_bin(m, a.max_dist2);
+      if (bin >= 0) atomicAdd(&a.hist_cnt[(size_t)(q >> 8) * nb + bin], 1u);
+      if (m.dist_sqrd > a.min_dist2) atomicAdd(&a.hist_cnt[(size_t)(q >> 8) * nb + a.W], 1u);
+    }
   }
 }
 } // namespace
@@ -677,6 +679,17 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
 // Same candidates' arg-min key (dist^2, shift rank, scan, k) = rule R5, so results are those of
 // the cooperative kernel and of the reference, bit for bit.
 namespace {
+// per-256-query histogram of the accepted matches by matched scan (+ novel count), warp-aggregated;
+// a warp covers 32 consecutive queries of one 256-query block.  Called by all 32 lanes.
+__device__ __forceinline__ void hist_add(const AssocArgs &a, int q, int lane, bool counted, const MatchRec &m) {
+  const int nb = a.W + 1;
+  const int bin = counted ? match_bin(m, a.max_dist2) : -1;
+  const bool novel = counted && m.dist_sqrd > a.min_dist2;
+  const unsigned peers = __match_any_sync(0xffffffffu, bin);
+  if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&a.hist_cnt[(size_t)(q >> 8) * nb + bin], (unsigned)__popc(peers));
+  const unsigned nov = __ballot_sync(0xffffffffu, novel);
+  if (nov && lane == __ffs(nov) - 1) atomicAdd(&a.hist_cnt[(size_t)(q >> 8) * nb + a.W], (unsigned)__popc(nov));
+}
 struct NnBest {
   double d = DBL_MAX; // Match::dist_sqrd default (map.hpp:55)
   unsigned long long tie = ~0ull;
@@ -740,8 +753,7 @@ constexpr int kMaxAdjacent = 26; // adjacent units a thread visits by itself (26
 __device__ __forceinline__ void assoc_cells_body(const AssocArgs &a) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  const int nb = a.W + 1;
-  const bool active = q < a.n_query;
+  const bool active = q >= a.q_begin && q < a.q_end;
   const bool searchable = active && a.n_map > 0;
   const double w = a.voxel_width, iw = a.inv_voxel_width;
   const double cw = w * (1.0 / kCellSub), inv_cw = (double)kCellSub * iw;
@@ -929,15 +941,29 @@ __device__ __forceinline__ void assoc_cells_body(const AssocArgs &a) {
     m.k = src & 0xFFFFFFu;
   }
   if (mine) a.match[q] = m;
-  const int bin = mine ? match_bin(m, a.max_dist2) : -1;
-  const bool novel = mine && m.dist_sqrd > a.min_dist2;
-  // a warp covers 32 consecutive queries of one 256-query block
-  const unsigned peers = __match_any_sync(0xffffffffu, bin);
-  if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&a.hist_cnt[(size_t)(q >> 8) * nb + bin], (unsigned)__popc(peers));
-  const unsigned nov = __ballot_sync(0xffffffffu, novel);
-  if (nov && lane == __ffs(nov) - 1) atomicAdd(&a.hist_cnt[(size_t)(q >> 8) * nb + a.W], (unsigned)__popc(nov));
+  if (a.hist_cnt) hist_add(a, q, lane, mine, m);
 }
 } // namespace
+// histogram alone, over matches that are already there (point-sharded mode, after the all-gather)
+__global__ void __launch_bounds__(256) assoc_hist_kernel(AssocArgs pa, AssocArgs qa) {
+  const AssocArgs &a = blockIdx.y == 0 ? pa : qa;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((int)(blockIdx.x * blockDim.x) >= a.n_query) return;
+  const bool active = q < a.n_query;
+  MatchRec m;
+  m.dist_sqrd = DBL_MAX;
+  m.slot = kNoSlot;
+  m.k = 0u;
+  if (active) m = a.match[q];
+  hist_add(a, q, threadIdx.x & 31, active, m);
+}
+void assoc_hist_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream, Profiler &prof) {
+  const int n = max(pa.n_query, qa.n_query);
+  if (n <= 0) return;
+  prof.begin(FORMGPU_KG_ASSOC_NN);
+  assoc_hist_kernel<<<dim3((n + 255) / 256, 2), 256, 0, stream>>>(pa, qa);
+  prof.end(FORMGPU_KG_ASSOC_NN, 1);
+}
 constexpr int kCellQueryThreads = 128;
 __global__ void __launch_bounds__(kCellQueryThreads) assoc_cells_kernel(AssocArgs pa, AssocArgs qa) {
   assoc_cells_body(blockIdx.y == 0 ? pa : qa);
@@ -960,11 +986,12 @@ __global__ void __launch_bounds__(256, 4) assoc_nn_batch_kernel(const AssocArgs 
   assoc_nn_body<kQueryLanes>(s_a);
 }
 
-void assoc_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream, Profiler &prof) {
+void assoc_launch(const AssocArgs &pa, const AssocArgs &qa, bool cell_search, cudaStream_t stream,
+                  Profiler &prof) {
   const int n = max(pa.n_query, qa.n_query);
   if (n <= 0) return;
   prof.begin(FORMGPU_KG_ASSOC_NN);
-  if (pa.cell_tab) { // cell-ordered buckets: one thread per query
+  if (pa.cell_tab && cell_search) { // cell-ordered buckets: one thread per query
     assoc_cells_kernel<<<dim3((n + kCellQueryThreads - 1) / kCellQueryThreads, 2), kCellQueryThreads, 0, stream>>>(pa, qa);
     prof.end(FORMGPU_KG_ASSOC_NN, 1);
     return;

@@ -260,6 +260,26 @@ int formgpu_linearize_device(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t
 int formgpu_error_device(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
                          const formgpu_scan_pose *poses, size_t n_poses, double *out_dev);
 
+/* Point-sharded mode over NCCL: the same dense sequence on `world` GPUs of one node, one process
+ * (or thread) and one context per GPU, every context fed the same calls with the same inputs.
+ * formgpu_comm_unique_id (any one rank; 128 bytes, to be handed to the other ranks by the caller's
+ * own means) + formgpu_comm_init (every rank, collectively) attach a communicator to the context.
+ * From then on
+ *   - formgpu_associate / _associate_linearize search only this rank's share of the keypoints;
+ *     an in-place ncclAllGather per keypoint type returns all matches to every rank, so pair
+ *     counts, segments, formgpu_get_matches and formgpu_commit_scan stay replicated and
+ *     bit-identical to a single GPU;
+ *   - the pair moments (stage 3) are accumulated over this rank's share of every pair, and
+ *     formgpu_linearize / formgpu_error / the blocks of formgpu_associate_linearize are the
+ *     evaluation of those partial moments followed by ONE ncclAllReduce(sum, f64, 91 * n_pairs)
+ *     on the context's stream - the only stage-3 bytes that cross NVLink.  Every rank receives
+ *     the full result (equal across ranks; differs from one GPU by fp64 summation order only).
+ * Extraction and the map rebuild are replicated.  NCCL is loaded at run time (libnccl.so.2);
+ * FORMGPU_ERR_UNSUPPORTED when it is not there.  Contexts of a batch cannot be sharded. */
+int formgpu_comm_unique_id(void *id128);
+int formgpu_comm_init(formgpu_ctx *ctx, const void *id128, int rank, int world);
+int formgpu_comm_destroy(formgpu_ctx *ctx);
+
 /* ---- batched submit: many independent sequences per launch --------------- */
 #define FORMGPU_KG_COUNT 12 /* kernel groups, listed under "instrumentation" below */
 
