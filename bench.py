@@ -463,6 +463,263 @@ def run_ours(args, rank, world, local_rank):
     return result
 
 
+# ---------------------------------------------------------------------------------------------
+# --mode sharded: BASELINE.json configs[4] - ONE dense 128x2048 sequence against a map of about a
+# million occupied voxels, point-sharded over the ranks (formgpu_comm_init): strong scaling
+# ---------------------------------------------------------------------------------------------
+STRESS_TILES = 40  # far tiles that seed the map: ~25 k planar + ~5 k point voxels each
+STRESS_ICP = 4     # associate_linearize calls per scan (ICP iterations)
+STRESS_FULL = 2    # full-window linearisations per scan
+STRESS_KEEP = 8    # scans of the driven tile kept in the window
+
+
+def run_sharded(args, rank, world, local_rank):
+    import torch
+
+    from form_b200 import _capi, synth
+    from form_b200.context import Context
+    from helpers import perturbed, scan_poses
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sensor = "stress-128x2048"
+    rows, cols = synth.shape(sensor)
+    n_points = rows * cols
+    W, K = args.warmup, args.steps
+    S = W + K
+    params = _capi.default_params(rows, cols)
+    scans = [synth.stress_scan(0, k) for k in range(S)]
+    pinned = [torch.from_numpy(s.view(np.uint8)).pin_memory() for s in scans]
+    dev = [t.cuda() for t in pinned]
+    host_np = [t.numpy().view(_capi.POINT4F) for t in pinned]
+    seeds = [synth.stress_scan(t, 0) for t in range(1, STRESS_TILES + 1)]
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rng0 = np.random.default_rng(5)  # same stream on every rank: identical calls
+    trial_pose = [[perturbed(synth.stress_pose(0, k), rng0, 0.002 / (it + 1), 0.02 / (it + 1))
+                   for it in range(STRESS_ICP)] for k in range(S)]
+
+    def one_pass(on_device, profile=False):
+        """Seeds the map, then drives scans 0..S-1 of tile 0; returns (seconds of the timed scans,
+        work counters, kernel-group profile, launches)."""
+        st = dict(points=0, planar_kp=0, point_kp=0, assoc_calls=0, assoc_queries=0, assoc_corr=0,
+                  lin_calls=0, lin_pairs=0, lin_corr=0)
+        with torch.cuda.stream(side), Context(params, device=local_rank, stream=side.cuda_stream) as ctx:
+            if world > 1:  # a fresh NCCL id per communicator (rank 0 creates, torch.distributed carries it)
+                ident = [Context.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(ident, src=0)
+                ctx.comm_init(ident[0], rank, world)
+            poses, counts_of = {}, {}
+            ctx.map_rebuild(scan_poses([], []))
+            for t, scan in enumerate(seeds, start=1):
+                ctx.extract(scan, t)
+                poses[t] = synth.stress_pose(t, 0)
+                ctx.associate(poses[t])
+                ctx.commit_scan()
+            seed_arr = scan_poses(sorted(poses), [poses[s] for s in sorted(poses)])  # never changes
+            n_seed = len(poses)
+
+            def window_poses():
+                own = sorted(poses)[n_seed:]  # the driven tile's scans (ids >= 1000)
+                return np.concatenate([seed_arr, scan_poses(own, [poses[s] for s in own])])
+
+            mine = []
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = 0
+            for k in range(S):
+                if k == W:
+                    if profile:
+                        ctx.profile_read()
+                        ctx.profile_enable(True)
+                    for key in st:
+                        st[key] = 0
+                    l0 = ctx.launch_count()
+                    barrier()
+                    a.record(side)
+                idx = 1000 + k
+                if on_device:
+                    n_pl, n_pt = ctx.extract_device(dev[k].data_ptr(), n_points, idx)
+                else:
+                    pl, pt = ctx.extract(host_np[k], idx)
+                    n_pl, n_pt = len(pl), len(pt)
+                ctx.map_rebuild(window_poses())
+                counts = None
+                for it in range(STRESS_ICP):
+                    poses[idx] = trial_pose[k][it]
+                    counts, _ = ctx.associate_linearize(window_poses())
+                    corr = int(counts["n_planar"].sum() + counts["n_point"].sum())
+                    st["assoc_calls"] += 1
+                    st["assoc_queries"] += n_pl + n_pt
+                    st["assoc_corr"] += corr
+                    st["lin_calls"] += 1
+                    st["lin_pairs"] += len(counts)
+                    st["lin_corr"] += corr
+                counts_of[idx] = counts
+                all_poses = window_poses()
+                pairs = np.zeros(sum(len(c) for c in counts_of.values()), dtype=_capi.PAIR)
+                at = 0
+                for j in sorted(counts_of):
+                    pairs["i"][at:at + len(counts_of[j])] = counts_of[j]["i"]
+                    pairs["j"][at:at + len(counts_of[j])] = j
+                    at += len(counts_of[j])
+                for _ in range(STRESS_FULL):
+                    if len(pairs):
+                        ctx.linearize(pairs, all_poses)
+                        st["lin_calls"] += 1
+                        st["lin_pairs"] += len(pairs)
+                        st["lin_corr"] += sum(int(c["n_planar"].sum() + c["n_point"].sum()) for c in counts_of.values())
+                ctx.commit_scan()
+                mine.append(idx)
+                if len(mine) > STRESS_KEEP:
+                    old = mine.pop(0)
+                    ctx.remove_scans([old])
+                    poses.pop(old)
+                    counts_of.pop(old)
+                    for j in counts_of:
+                        counts_of[j] = counts_of[j][counts_of[j]["i"] != old]
+                st["points"] += n_points
+                st["planar_kp"] += n_pl
+                st["point_kp"] += n_pt
+            ctx.synchronize()
+            b.record(side)
+            torch.cuda.synchronize()
+            seconds = a.elapsed_time(b) / 1e3
+            prof = ctx.profile_read() if profile else None
+            launches = ctx.launch_count() - l0
+            if world > 1:
+                ctx.comm_destroy()
+        return seconds, st, prof, launches
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_value, st, _, launches = one_pass(True)
+    t_e2e, st_h, _, _ = one_pass(False)
+    barrier()
+    clocks = sampler.stop()
+    _, st_p, prof, _ = one_pass(True, profile=True)
+    if dist is not None:
+        t = torch.tensor([t_value, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_value, t_e2e = float(t[0]), float(t[1])
+    result = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        kernel_ms = {g: v["ms"] for g, v in prof.items() if v["launches"]}
+        total_ms = sum(kernel_ms.values()) or 1.0
+        ab_of = {"assoc_nn": st_p["assoc_queries"] * (32.0 + 27 * 16.0 + 32.0 + 16.0),
+                 "segment": st_p["assoc_queries"] * (16.0 + 36.0 + 32.0),
+                 "lin_chunk": 36.0 * st_p["assoc_corr"],
+                 "lin_finalize": (1056.0 + 728.0) * st_p["lin_pairs"],
+                 "extract_select": 16.0 * st_p["points"], "extract_normals": 16.0 * st_p["points"],
+                 "extract_pack": 32.0 * st_p["planar_kp"] + 16.0 * st_p["point_kp"]}
+        kg = {}
+        for g, ms in sorted(kernel_ms.items()):
+            n = prof[g]["launches"]
+            ab = ab_of.get(g, 0.0) / max(world, 1) if g in ("assoc_nn", "lin_chunk") else ab_of.get(g, 0.0)
+            kg[g] = {"ms_per_scan": round(ms / K, 5), "launches": n, "avg_launch_us": round(1e3 * ms / n, 2),
+                     "algorithmic_MB_per_launch": round(ab / n / 1e6, 3),
+                     "achieved_GBps": round(ab / (ms / 1e3) / 1e9, 1), "frac": round(ab / (ms / 1e3) / 1e9 / peak, 4),
+                     "share_of_gpu_time": round(ms / total_ms, 4)}
+        dom = max(kernel_ms, key=kernel_ms.get)
+        cap = ncu_capture(dom + "_single")
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_sharded(args, rows, cols, scans, seeds)
+        value, e2e_value = K / t_value, K / t_e2e
+        result = {
+            "metric": METRIC, "value": round(value, 3), "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(1e3 * t_value / K, 4), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "mpoints_per_s": round(value * n_points / 1e6, 3),
+            "config": {
+                "workload": SENSOR_OF_WORKLOAD[sensor] + f"; ONE sequence point-sharded over {world} GPU(s) "
+                            f"(formgpu_comm_init): map seeded with {STRESS_TILES} far tiles (~1.2 M occupied voxels, "
+                            f"1.5 M points) + the last {STRESS_KEEP} scans of the driven tile",
+                "sensor": sensor, "rows": rows, "cols": cols,
+                "step": f"extract + reparative rebuild of the whole map + {STRESS_ICP} x associate_linearize at "
+                        f"perturbed poses + {STRESS_FULL} x linearize of every pair of the driven tile + commit "
+                        f"(fixed schedule, no smoother in the loop)",
+                "parallelism": f"{world} rank(s): keypoint-sharded association (all-gather of matches), "
+                               f"correspondence-sharded pair moments, ncclAllReduce of 91 doubles per pair; "
+                               f"extraction and map rebuild replicated",
+                "l2": "the map (1.5 M points x 32 B + 16 MB hash) exceeds L2 and is rebuilt every step; no flush",
+                "timing": "CUDA events on the context's stream, barrier + device synchronize on both sides, max over ranks",
+                "keypoints_per_scan": round((st["planar_kp"] + st["point_kp"]) / K),
+                "correspondences_per_association": round(st["assoc_corr"] / max(st["assoc_calls"], 1)),
+            },
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 3), "unit": "scans/s", "h2d_bytes_per_step": 16 * n_points,
+                    "d2h_bytes_per_step": int((72.0 * st_h["planar_kp"] + 40.0 * st_h["point_kp"] + 728.0 * st_h["lin_pairs"]) / K),
+                    "ms_per_step": round(1e3 * t_e2e / K, 4)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kg[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
+                         "frac": kg[dom]["frac"], "traffic": cap["dram_bytes"] if cap else None, "traffic_capture": cap,
+                         "peak_source": peak_src, "kernel_groups": kg},
+            "cpu_baseline": cpu,
+        }
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+def cpu_baseline_sharded(args, rows, cols, scans, seeds):
+    """The same fixed schedule on the CPU oracle (all host threads over keypoints, as the
+    reference's TBB loops), bounded sample of 3 scans after the map is seeded."""
+    import oracle_lib
+    from form_b200 import _capi, synth
+    from helpers import perturbed, scan_poses
+
+    params = _capi.default_params(rows, cols)
+    ref = oracle_lib.Oracle(params)
+    rng = np.random.default_rng(5)
+    poses, counts_of = {}, {}
+    ref.map_rebuild(scan_poses([], []))
+    for t, scan in enumerate(seeds, start=1):
+        ref.extract(scan, t)
+        poses[t] = synth.stress_pose(t, 0)
+        ref.associate(poses[t])
+        ref.commit_scan()
+    n = min(3, len(scans))
+    t0 = time.perf_counter()
+    for k in range(n):
+        idx = 1000 + k
+        ref.extract(scans[k], idx)
+        window = sorted(poses)
+        ref.map_rebuild(scan_poses(window, [poses[s] for s in window]))
+        counts = None
+        for it in range(STRESS_ICP):
+            poses[idx] = perturbed(synth.stress_pose(0, k), rng, 0.002 / (it + 1), 0.02 / (it + 1))
+            now = sorted(poses)
+            all_poses = scan_poses(now, [poses[s] for s in now])
+            counts = ref.associate(poses[idx])
+            if len(counts):
+                pairs = np.zeros(len(counts), dtype=_capi.PAIR)
+                pairs["i"], pairs["j"] = counts["i"], idx
+                ref.linearize(pairs, all_poses)
+        counts_of[idx] = counts
+        now = sorted(poses)
+        all_poses = scan_poses(now, [poses[s] for s in now])
+        pairs = np.array([(int(c["i"]), j) for j in sorted(counts_of) for c in counts_of[j]], dtype=_capi.PAIR)
+        for _ in range(STRESS_FULL):
+            if len(pairs):
+                ref.linearize(pairs, all_poses)
+        ref.commit_scan()
+    dt = time.perf_counter() - t0
+    return {"value": round(n / dt, 4), "unit": "scans/s", "cores": host_cores(), "kind": "port",
+            "sample": f"{n} scans of the same fixed schedule on the oracle after seeding the map, {round(dt, 1)} s; "
+                      f"worker threads over keypoints where the reference uses TBB"}
+
+
 def run_single(torch, Replay, trace, p, dev_ptrs, scans_np, W, S, n_points):
     """Latency mode: one sequence through the single-context entry points.  Per-step CUDA
     events on the launching stream, 256 MiB L2 flush between steps (outside the intervals)."""
@@ -649,6 +906,9 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=40)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="sequences", choices=["sequences", "sharded"],
+                    help="sequences: independent sequences per GPU (the headline, weak scaling); sharded: "
+                         "configs[4], ONE dense 128x2048 sequence point-sharded over the ranks (strong scaling)")
     ap.add_argument("--sensor", default="os0-128", choices=sorted(SENSOR_OF_WORKLOAD))
     ap.add_argument("--cpu-sample", type=int, default=20, help="scans per sequence timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -678,6 +938,8 @@ def main():
     g.build(only_if_missing=True)
     if args.impl == "reference":
         res = run_reference(args, rank, world)
+    elif args.mode == "sharded":
+        res = run_sharded(args, rank, world, local_rank)
     else:
         res = run_ours(args, rank, world, local_rank)
     if rank == 0 and res is not None:

@@ -128,7 +128,7 @@ int commit_prepare(formgpu_ctx *ctx, CommitPlan &plan);
 void commit_finish(formgpu_ctx *ctx, const CommitPlan &plan);
 
 /// Point-sharded mode over NCCL (comm.cu): collectives queued on the context's stream.
-int comm_allgather_matches(formgpu_ctx *ctx, int type, int n_query);
+int comm_allgather_matches(formgpu_ctx *ctx, int n_planar, int n_point);
 int comm_allreduce_f64(formgpu_ctx *ctx, double *dev, size_t count);
 int comm_ensure_reduce(formgpu_ctx *ctx, size_t doubles);
 void comm_release(formgpu_ctx *ctx);

@@ -91,6 +91,8 @@ int map_rebuild_prepare(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
     std::memcpy(h.pose + 12 * s, &poses[p].pose, 12 * sizeof(double));
     has_pose[s] = 1;
   }
+  // point-sharded mode: the map of this rank holds the scans of ITS window slots only
+  const bool part = sharded_comm(ctx);
   for (int t = 0; t < 2; ++t) {
     int run = 0;
     for (int s = 0; s < W; ++s) {
@@ -100,7 +102,7 @@ int map_rebuild_prepare(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
           return fail(ctx, FORMGPU_ERR_INVALID_ARG,
                       "formgpu_map_rebuild: stored scan " + std::to_string(ctx->slot_scan[s]) +
                           " has no pose");
-        run += ctx->store_n[t][s];
+        if (!part || s % ctx->comm_world == ctx->comm_rank) run += ctx->store_n[t][s];
       }
     }
     h.off[t * (W + 1) + W] = run;
@@ -215,12 +217,9 @@ int assoc_prepare(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_sc
     aa[t].n_query = nq[t];
     aa[t].q_begin = 0;
     aa[t].q_end = nq[t];
-    if (sharded_comm(ctx)) { // this rank's share of the keypoints (equal chunks: in-place all-gather)
-      const int chunk = (nq[t] + ctx->comm_world - 1) / ctx->comm_world;
-      aa[t].q_begin = std::min(nq[t], chunk * ctx->comm_rank);
-      aa[t].q_end = std::min(nq[t], chunk * (ctx->comm_rank + 1));
-    }
-    aa[t].n_map = (int)ctx->map_n[t];
+    aa[t].pack_rank = 0;
+    aa[t].pad_rank = 0;
+    aa[t].n_map = (int)ctx->map_n[t]; // point-sharded mode: this rank's sub-map
     aa[t].queries = queries;
     std::memcpy(aa[t].pose, pose_k, 12 * sizeof(double));
     aa[t].voxel_width = ctx->P.max_dist_matching;
@@ -376,16 +375,26 @@ static int associate_impl(formgpu_ctx *ctx, const formgpu_pose *pose_k, const fo
   if (rc) return rc;
   if (plan.any_query) {
     if (sharded_comm(ctx)) {
-      // the association kernels see this rank's queries only: matches are all-gathered in place,
-      // then every rank builds the histogram over all of them
+      // every rank searches its sub-map for all queries; the candidates are all-gathered in
+      // place and reduced with the rule-R5 key (+ the histogram) by the combine kernel
       AssocArgs part[2] = {plan.aa[0], plan.aa[1]};
-      part[0].hist_cnt = part[1].hist_cnt = nullptr;
-      assoc_launch(part[0], part[1], ctx->cell_search_single, ctx->stream, ctx->prof);
+      CombineArgs comb[2];
+      const int stride = plan.nq[0] + plan.nq[1];
       for (int t = 0; t < 2; ++t) {
-        rc = comm_allgather_matches(ctx, t, plan.nq[t]);
-        if (rc) return rc;
+        const size_t off = t == 0 ? 0 : (size_t)plan.nq[0]; // a rank's block: [planar | point]
+        part[t].hist_cnt = nullptr;
+        part[t].pack_rank = 1;
+        part[t].match = ctx->d_gather + (size_t)ctx->comm_rank * stride + off;
+        comb[t].a = plan.aa[t];
+        comb[t].gathered = ctx->d_gather + off;
+        comb[t].slot_scan = reinterpret_cast<const uint64_t *>(ctx->d_map_req + (size_t)ctx->W * 12 * sizeof(double));
+        comb[t].world = ctx->comm_world;
+        comb[t].stride = stride;
       }
-      assoc_hist_launch(plan.aa[0], plan.aa[1], ctx->stream, ctx->prof);
+      assoc_launch(part[0], part[1], ctx->cell_search_single, ctx->stream, ctx->prof);
+      rc = comm_allgather_matches(ctx, plan.nq[0], plan.nq[1]);
+      if (rc) return rc;
+      assoc_combine_launch(comb[0], comb[1], ctx->stream, ctx->prof);
     } else {
       assoc_launch(plan.aa[0], plan.aa[1], ctx->cell_search_single, ctx->stream, ctx->prof);
     }

@@ -2,11 +2,14 @@
 // node (BASELINE.json configs[4]) - the collectives.
 //
 // The reference has no distributed code; this is the B200-native extension the north star names:
-// every rank keeps a replica of the sequence's context, the association of a scan is sharded by
-// KEYPOINTS (rank r searches the r-th share of the queries; one in-place ncclAllGather per
-// keypoint type returns every rank's matches to all of them, so segments, pair counts and the
-// novel-keypoint commit stay replicated and bit-identical), the pair moments are accumulated over
-// the rank's share of every pair's correspondences, and a linearisation is the cached evaluation
+// every rank keeps a replica of the sequence's keypoint store, but the reparative MAP - the large
+// and expensive object of this configuration (1.5 M points, a million voxels, rebuilt every scan) -
+// is sharded by scans: rank r transforms, hashes and cell-orders only the scans whose window slot
+// is congruent to r.  Every rank searches its sub-map for all keypoints of the scan; one in-place
+// ncclAllGather per keypoint type collects the candidates and a combine kernel applies the full
+// rule-R5 key across ranks, so matches, segments, pair counts and the novel-keypoint commit are
+// replicated and bit-identical to one GPU.  The pair moments are accumulated over the rank's
+// share of every pair's correspondences, and a linearisation is the cached evaluation
 // of those partial moments followed by ONE ncclAllReduce(sum, f64, 91 * P) of the blocks on the
 // context's stream - the only bytes of stage 3 that cross NVLink.  NCCL is resolved at run time
 // (dlopen of libnccl.so.2 - the copy the process already holds, e.g. PyTorch's, if any), so the
@@ -76,12 +79,12 @@ int nccl_fail(formgpu_ctx *ctx, const char *what, ncclResult_t r) {
 
 namespace formgpu {
 
-int comm_allgather_matches(formgpu_ctx *ctx, int type, int n_query) {
+int comm_allgather_matches(formgpu_ctx *ctx, int n_planar, int n_point) {
   NcclApi &api = nccl();
-  const size_t chunk = ((size_t)n_query + ctx->comm_world - 1) / ctx->comm_world;
+  const size_t chunk = (size_t)n_planar + (size_t)n_point; // a candidate per query and rank
   if (chunk == 0) return FORMGPU_OK;
-  MatchRec *buf = ctx->d_match[type];
-  // in place: this rank's share already sits at its position
+  MatchRec *buf = ctx->d_gather;
+  // in place: this rank's candidates already sit at their position
   const ncclResult_t r = api.AllGather(buf + chunk * ctx->comm_rank, buf, 2 * chunk, kNcclUint64,
                                        static_cast<ncclComm_t>(ctx->comm), ctx->stream);
   if (r != 0) return nccl_fail(ctx, "ncclAllGather(matches)", r);
@@ -120,11 +123,14 @@ void comm_release(formgpu_ctx *ctx) {
   }
   if (ctx->d_red) cudaFree(ctx->d_red);
   if (ctx->h_red) cudaFreeHost(ctx->h_red);
+  if (ctx->d_gather) cudaFree(ctx->d_gather);
+  ctx->d_gather = nullptr;
   ctx->d_red = nullptr;
   ctx->h_red = nullptr;
   ctx->red_cap = 0;
   ctx->comm_rank = 0;
   ctx->comm_world = 1;
+  ctx->map_built = false; // the map of a sharded context holds a share of the scans only
 }
 
 } // namespace formgpu
@@ -160,6 +166,10 @@ int formgpu_comm_init(formgpu_ctx *ctx, const void *id128, int rank, int world) 
   ctx->comm = comm;
   ctx->comm_rank = rank;
   ctx->comm_world = world;
+  ctx->map_built = false; // rebuilt sharded from now on
+  if (world > 1)
+    FORMGPU_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->d_gather),
+                                 (size_t)world * (ctx->kp_cap + ctx->kq_cap) * sizeof(MatchRec)));
   return FORMGPU_OK;
 }
 

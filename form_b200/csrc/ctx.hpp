@@ -249,6 +249,8 @@ struct formgpu_ctx {
   int comm_rank = 0, comm_world = 1;
   double *d_red = nullptr, *h_red = nullptr; // blocks / errors of a request: all-reduced, then copied out
   size_t red_cap = 0;
+  // [world][planar candidates | point candidates of the current scan]: one in-place all-gather
+  formgpu::MatchRec *d_gather = nullptr;
 
   // ---- pair-moment cache (moments.cu) ----
   // [W(j)][W(i)][kMomentStride] doubles: moments of pair (i, j) left by scan j's last association

@@ -101,9 +101,11 @@ struct AssocArgs {
   int type;
   int n_query;
   int n_map;
-  // queries this launch searches: [q_begin, q_end) - the whole scan, or this rank's share of it
-  // in point-sharded mode (the other ranks' matches arrive by all-gather)
+  // queries this launch searches: [q_begin, q_end) (the whole scan)
   int q_begin, q_end;
+  // point-sharded mode: the map holds only this rank's scans; the winner's shift rank travels in
+  // bits 8..12 of MatchRec::slot so that assoc_combine can apply rule R5 across the ranks
+  int pack_rank, pad_rank;
   const void *queries; // PlanarRec* / PointRec* of the current scan
   double pose[12];     // pose of the current scan
   double voxel_width;
@@ -122,9 +124,17 @@ struct AssocArgs {
   uint32_t *hist_cnt;      // [blocks256][W+1] atomic counters, zero on entry; nullptr: the
                            // histogram is built by assoc_hist_launch once all matches are there
 };
-/// Histogram of the matches by matched scan (+ novel count) as the association kernels build it
-/// themselves when they see every query: point-sharded mode runs it after the all-gather.
-void assoc_hist_launch(const AssocArgs &planar, const AssocArgs &point, cudaStream_t stream, Profiler &prof);
+/// Point-sharded mode: per query the rule-R5 minimum over the `world` candidate records the ranks
+/// found in their sub-maps (gathered[r * n_query + q], shift rank packed into the slot), written to
+/// a.match with the histogram the association kernels otherwise build themselves.
+struct CombineArgs {
+  AssocArgs a;                // n_query, match (output), hist_cnt, W, max / min dist
+  const MatchRec *gathered;   // rank r's candidate of query q: gathered[r * stride + q]
+  const uint64_t *slot_scan;  // [W] scan id of every window slot (tie-break, rule R4)
+  int world;
+  int stride;                 // records per rank (planar + point candidates of the scan)
+};
+void assoc_combine_launch(const CombineArgs &planar, const CombineArgs &point, cudaStream_t stream, Profiler &prof);
 /// One sequence: `cell_search` = the one-thread-per-query search over the cell-ordered buckets (what
 /// batched submits always use); otherwise one WARP per query scans whole buckets - the lower
 /// latency for a single scan's ~30 k queries, which cannot fill the GPU either way.

@@ -647,6 +647,7 @@ template <int kQueryLanes> __device__ __forceinline__ void assoc_nn_body(const A
       const uint32_t src = a.world_src[best_pos];
       m.dist_sqrd = best;
       m.slot = src >> 24;
+      if (a.pack_rank) m.slot |= (uint32_t)best_rank << 8;
       m.k = src & 0xFFFFFFu;
     }
     a.match[q] = m;
@@ -938,32 +939,58 @@ __device__ __forceinline__ void assoc_cells_body(const AssocArgs &a) {
     const uint32_t src = a.world_src[best.pos];
     m.dist_sqrd = best.d;
     m.slot = src >> 24;
+    if (a.pack_rank) m.slot |= (uint32_t)best.rank << 8;
     m.k = src & 0xFFFFFFu;
   }
   if (mine) a.match[q] = m;
   if (a.hist_cnt) hist_add(a, q, lane, mine, m);
 }
 } // namespace
-// histogram alone, over matches that are already there (point-sharded mode, after the all-gather)
-__global__ void __launch_bounds__(256) assoc_hist_kernel(AssocArgs pa, AssocArgs qa) {
-  const AssocArgs &a = blockIdx.y == 0 ? pa : qa;
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// point-sharded mode: every rank searched ITS sub-map (the scans it owns) for every query; the
+// all-gathered candidates are reduced here with the full rule-R5 key (dist^2, shift rank, scan,
+// k) - the key the single-GPU search applies inside one map - so the winner is bit-identical
+__global__ void __launch_bounds__(256) assoc_combine_kernel(CombineArgs pc, CombineArgs qc) {
+  const CombineArgs &c = blockIdx.y == 0 ? pc : qc;
+  const AssocArgs &a = c.a;
   if ((int)(blockIdx.x * blockDim.x) >= a.n_query) return;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = q < a.n_query;
-  MatchRec m;
-  m.dist_sqrd = DBL_MAX;
-  m.slot = kNoSlot;
-  m.k = 0u;
-  if (active) m = a.match[q];
-  hist_add(a, q, threadIdx.x & 31, active, m);
+  MatchRec best;
+  best.dist_sqrd = DBL_MAX;
+  best.slot = kNoSlot;
+  best.k = 0u;
+  int best_rank = 32;
+  unsigned long long best_scan = ~0ull;
+  if (active) {
+    for (int r = 0; r < c.world; ++r) {
+      const MatchRec m = c.gathered[(size_t)r * c.stride + q];
+      if (m.slot == kNoSlot) continue;
+      const uint32_t slot = m.slot & 0xffu;
+      const int rank = (int)((m.slot >> 8) & 31u);
+      const unsigned long long scan = c.slot_scan[slot];
+      const bool take = m.dist_sqrd < best.dist_sqrd ||
+                        (m.dist_sqrd == best.dist_sqrd &&
+                         (rank < best_rank || (rank == best_rank && (scan < best_scan || (scan == best_scan && m.k < best.k)))));
+      if (take) {
+        best.dist_sqrd = m.dist_sqrd;
+        best.slot = slot;
+        best.k = m.k;
+        best_rank = rank;
+        best_scan = scan;
+      }
+    }
+    a.match[q] = best;
+  }
+  hist_add(a, q, threadIdx.x & 31, active, best);
 }
-void assoc_hist_launch(const AssocArgs &pa, const AssocArgs &qa, cudaStream_t stream, Profiler &prof) {
-  const int n = max(pa.n_query, qa.n_query);
+void assoc_combine_launch(const CombineArgs &pc, const CombineArgs &qc, cudaStream_t stream, Profiler &prof) {
+  const int n = max(pc.a.n_query, qc.a.n_query);
   if (n <= 0) return;
   prof.begin(FORMGPU_KG_ASSOC_NN);
-  assoc_hist_kernel<<<dim3((n + 255) / 256, 2), 256, 0, stream>>>(pa, qa);
+  assoc_combine_kernel<<<dim3((n + 255) / 256, 2), 256, 0, stream>>>(pc, qc);
   prof.end(FORMGPU_KG_ASSOC_NN, 1);
 }
+
 constexpr int kCellQueryThreads = 128;
 __global__ void __launch_bounds__(kCellQueryThreads) assoc_cells_kernel(AssocArgs pa, AssocArgs qa) {
   assoc_cells_body(blockIdx.y == 0 ? pa : qa);
