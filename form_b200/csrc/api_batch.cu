@@ -52,6 +52,10 @@ struct formgpu_batch {
   int assoc_lanes = kAssocLanes; // lanes per query of the batched association kernel (FORMGPU_ASSOC_LANES)
   // stage 3 from the pair-moment cache (moments.cu); FORMGPU_STREAM_LINEARIZE=1 streams instead
   bool moment_cache = true;
+  // host-scan extraction: keypoint structs go back by DMA from a device staging buffer (default)
+  // or, with FORMGPU_PACK_DMA=0, by the pack kernel's own stores into mapped host memory
+  bool pack_dma = true;
+  cudaEvent_t ev_extract = nullptr; // extraction kernels of the submission queued
   // the submission in flight (formgpu_batch_submit_async ... formgpu_batch_wait)
   struct Pending {
     bool active = false;
@@ -231,6 +235,7 @@ int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size
   b->stream = static_cast<cudaStream_t>(stream);
   if (const char *env = std::getenv("FORMGPU_MANY_ROWS_MIN")) b->many_rows_min = std::atoi(env);
   if (const char *env = std::getenv("FORMGPU_ASSOC_LANES")) b->assoc_lanes = std::atoi(env);
+  if (const char *env = std::getenv("FORMGPU_PACK_DMA")) b->pack_dma = env[0] != '0';
   auto bail = [&](int rc, const std::string &msg) {
     g_batch_error = msg;
     formgpu_batch_destroy(b);
@@ -248,6 +253,7 @@ int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size
   }
   b->prof.stream = b->stream;
   if (cudaEventCreateWithFlags(&b->ev_args, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&b->ev_extract, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&b->ev_copy, cudaEventDisableTiming) != cudaSuccess)
     return bail(FORMGPU_ERR_CUDA, "cudaEventCreate failed");
   if (cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -278,6 +284,7 @@ void formgpu_batch_destroy(formgpu_batch *b) {
   if (b->d_tickets) cudaFree(b->d_tickets);
   if (b->ev_args) cudaEventDestroy(b->ev_args);
   if (b->ev_copy) cudaEventDestroy(b->ev_copy);
+  if (b->ev_extract) cudaEventDestroy(b->ev_extract);
   if (b->copy_stream) {
     cudaStreamSynchronize(b->copy_stream);
     cudaStreamDestroy(b->copy_stream);
@@ -407,7 +414,17 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
                                       cudaMemcpyHostToDevice, b->copy_stream));
         scans_uploading = true;
         scan_dev = ctx->d_scan;
-        extract_direct_targets(ctx, q.planar_out, q.planar_cap, q.point_out, q.point_cap, dp, dq);
+        if (b->pack_dma && q.planar_out && q.point_out) {
+          // f64 structs into device staging; a copy engine takes them to the caller (collect phase)
+          if (!ctx->d_stage_planar) {
+            BATCH_CUDA(b, cudaMalloc(reinterpret_cast<void **>(&ctx->d_stage_planar), ctx->kp_cap * sizeof(formgpu_planar_feat)));
+            BATCH_CUDA(b, cudaMalloc(reinterpret_cast<void **>(&ctx->d_stage_point), ctx->kq_cap * sizeof(formgpu_point_feat)));
+          }
+          dp = ctx->d_stage_planar;
+          dq = ctx->d_stage_point;
+        } else {
+          extract_direct_targets(ctx, q.planar_out, q.planar_cap, q.point_out, q.point_cap, dp, dq);
+        }
         host_records = dp == nullptr && (q.planar_out || q.point_out);
       }
       ExtractArgs &a = b->extract_args[q.sequence];
@@ -427,6 +444,7 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
         if (scans_uploading) BATCH_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_copy, 0));
         extract_batch_launch(shape, staged<ExtractArgs>(b, off), n_items, b->many_rows_min, b->stream, b->prof);
         BATCH_CUDA(b, cudaGetLastError());
+        BATCH_CUDA(b, cudaEventRecord(b->ev_extract, b->stream));
         return FORMGPU_OK;
       };
     }
@@ -681,6 +699,7 @@ int submit_collect(formgpu_batch *b) {
   const std::vector<size_t> &live_extract = pend.live_extract, &live_assoc = pend.live_assoc,
                             &live_commit = pend.live_commit;
   const std::vector<size_t>(&live_lin)[2] = pend.live_lin;
+  bool dma_pending = false;
   for (size_t r : live_extract) {
     formgpu_request &q = reqs[r];
     formgpu_ctx *ctx = b->ctx[q.sequence];
@@ -689,8 +708,23 @@ int submit_collect(formgpu_batch *b) {
     if (rc == FORMGPU_OK) {
       q.n_planar = (size_t)ctx->cur_n[0];
       q.n_point = (size_t)ctx->cur_n[1];
-      if (a.host_planar || a.host_point)
+      if (a.host_planar || a.host_point) {
         rc = extract_widen(ctx, q.scan_idx, q.planar_out, q.planar_cap, q.point_out, q.point_cap);
+      } else if (a.host_planar_f64 && a.host_planar_f64 == ctx->d_stage_planar) {
+        // the counts are known now: exactly the written structs travel, on the copy stream
+        if (q.n_planar > q.planar_cap || q.n_point > q.point_cap) {
+          rc = fail(ctx, FORMGPU_ERR_CAPACITY, "formgpu_extract: output buffers too small");
+        } else {
+          if (!dma_pending) BATCH_CUDA(b, cudaStreamWaitEvent(b->copy_stream, b->ev_extract, 0));
+          dma_pending = true;
+          if (q.n_planar)
+            BATCH_CUDA(b, cudaMemcpyAsync(q.planar_out, ctx->d_stage_planar, q.n_planar * sizeof(formgpu_planar_feat),
+                                          cudaMemcpyDeviceToHost, b->copy_stream));
+          if (q.n_point)
+            BATCH_CUDA(b, cudaMemcpyAsync(q.point_out, ctx->d_stage_point, q.n_point * sizeof(formgpu_point_feat),
+                                          cudaMemcpyDeviceToHost, b->copy_stream));
+        }
+      }
     }
     set_status(q, rc);
   }
@@ -716,6 +750,7 @@ int submit_collect(formgpu_batch *b) {
     q.n_planar = plan.added[0];
     q.n_point = plan.added[1];
   }
+  if (dma_pending) BATCH_CUDA(b, cudaStreamSynchronize(b->copy_stream)); // keypoints have landed
   if (b->prof.timing) b->prof.collect();
   return first_error;
 }

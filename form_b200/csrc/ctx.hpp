@@ -169,6 +169,11 @@ struct formgpu_ctx {
   volatile unsigned long long *h_out = nullptr;
   size_t h_out_bytes = 0;
 
+  // batched host-scan extraction: the pack kernel leaves the f64 API structs here (device memory)
+  // and a copy engine moves them to the caller's buffers - SM stores over PCIe kept the pack
+  // kernel resident for ~30 us per scan (profiles/r03/e2e_probe.txt)
+  formgpu_planar_feat *d_stage_planar = nullptr; // [kp_cap], allocated on first use
+  formgpu_point_feat *d_stage_point = nullptr;   // [kq_cap]
   // caller output buffers last probed for page-locked-ness, and their device aliases
   void *direct_probe[2] = {nullptr, nullptr};
   void *direct_alias[2] = {nullptr, nullptr};
