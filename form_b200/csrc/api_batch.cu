@@ -56,12 +56,24 @@ struct formgpu_batch {
   // or, with FORMGPU_PACK_DMA=0, by the pack kernel's own stores into mapped host memory
   bool pack_dma = true;
   cudaEvent_t ev_extract = nullptr; // extraction kernels of the submission queued
+  // 13x13 blocks of a submission: the evaluation kernels write plain doubles into d_blocks and ONE
+  // copy-engine transfer per submission takes them to h_blocks (page-locked).  SM stores of
+  // sequence-tagged words into mapped host memory (the single-sequence protocol, FORMGPU_BLOCK_DMA=0)
+  // move twice the bytes in 8-byte PCIe writes and kept the evaluation CTAs resident until the
+  // writes drained: 52 us per launch of ~1000 pairs, i.e. ~28 GB/s of PCIe stores.
+  bool block_dma = true;
+  double *d_blocks = nullptr, *h_blocks = nullptr;
+  size_t blocks_cap = 0, blocks_used = 0; // doubles
+  cudaStream_t d2h_stream = nullptr;
+  cudaEvent_t ev_lin = nullptr, ev_blocks = nullptr;
+  std::vector<size_t> assoc_block_off, lin_block_off; // per sequence: offset into h_blocks, or kNoBlocks
   // the submission in flight (formgpu_batch_submit_async ... formgpu_batch_wait)
   struct Pending {
     bool active = false;
     formgpu_request *reqs = nullptr;
     size_t n = 0;
     int first_error = FORMGPU_OK;
+    bool blocks_dma = false; // a block transfer of this submission is in flight (ev_blocks)
     std::vector<size_t> live_extract, live_assoc, live_lin[2], live_commit;
   } pend;
 };
@@ -83,6 +95,37 @@ int bfail(formgpu_batch *b, int code, const std::string &msg) {
   } while (0)
 
 size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr size_t kNoBlocks = ~(size_t)0;
+
+// room for `doubles` block words of one submission (called before anything of it is staged)
+int ensure_blocks(formgpu_batch *b, size_t doubles) {
+  if (doubles <= b->blocks_cap) return FORMGPU_OK;
+  BATCH_CUDA(b, cudaStreamSynchronize(b->stream));
+  BATCH_CUDA(b, cudaStreamSynchronize(b->d2h_stream));
+  size_t cap = std::max<size_t>(b->blocks_cap * 2, 91 * 1024);
+  while (cap < doubles) cap *= 2;
+  if (b->d_blocks) cudaFree(b->d_blocks);
+  if (b->h_blocks) cudaFreeHost(b->h_blocks);
+  b->d_blocks = b->h_blocks = nullptr;
+  b->blocks_cap = 0;
+  BATCH_CUDA(b, cudaMalloc(reinterpret_cast<void **>(&b->d_blocks), cap * sizeof(double)));
+  BATCH_CUDA(b, cudaHostAlloc(reinterpret_cast<void **>(&b->h_blocks), cap * sizeof(double), cudaHostAllocDefault));
+  b->blocks_cap = cap;
+  return FORMGPU_OK;
+}
+
+// Spin until `ev` has completed (same polling discipline as the mapped-memory flags).
+int wait_event(formgpu_batch *b, cudaEvent_t ev) {
+  unsigned spins = 0;
+  for (;;) {
+    const cudaError_t e = cudaEventQuery(ev);
+    if (e == cudaSuccess) return FORMGPU_OK;
+    if (e != cudaErrorNotReady)
+      return bfail(b, FORMGPU_ERR_CUDA, std::string("block transfer failed: ") + cudaGetErrorString(e));
+    poll_relax(++spins);
+  }
+}
 
 // make room for `bytes` more staged argument bytes (contents staged so far are kept)
 int ensure_args(formgpu_batch *b, size_t bytes) {
@@ -236,6 +279,7 @@ int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size
   if (const char *env = std::getenv("FORMGPU_MANY_ROWS_MIN")) b->many_rows_min = std::atoi(env);
   if (const char *env = std::getenv("FORMGPU_ASSOC_LANES")) b->assoc_lanes = std::atoi(env);
   if (const char *env = std::getenv("FORMGPU_PACK_DMA")) b->pack_dma = env[0] != '0';
+  if (const char *env = std::getenv("FORMGPU_BLOCK_DMA")) b->block_dma = env[0] != '0';
   auto bail = [&](int rc, const std::string &msg) {
     g_batch_error = msg;
     formgpu_batch_destroy(b);
@@ -254,9 +298,12 @@ int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size
   b->prof.stream = b->stream;
   if (cudaEventCreateWithFlags(&b->ev_args, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&b->ev_extract, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&b->ev_copy, cudaEventDisableTiming) != cudaSuccess)
+      cudaEventCreateWithFlags(&b->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&b->ev_lin, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&b->ev_blocks, cudaEventDisableTiming) != cudaSuccess)
     return bail(FORMGPU_ERR_CUDA, "cudaEventCreate failed");
-  if (cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+  if (cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&b->d2h_stream, cudaStreamNonBlocking) != cudaSuccess)
     return bail(FORMGPU_ERR_CUDA, "cudaStreamCreate failed");
   for (size_t i = 0; i < n_sequences; ++i) {
     formgpu_ctx *c = nullptr;
@@ -265,6 +312,9 @@ int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size
     b->ctx.push_back(c);
   }
   b->moment_cache = b->ctx[0]->moment_cache;
+  b->block_dma = b->block_dma && b->moment_cache; // the evaluation kernels write plain blocks
+  b->assoc_block_off.assign(n_sequences, kNoBlocks);
+  b->lin_block_off.assign(n_sequences, kNoBlocks);
   b->assoc_plans.resize(n_sequences);
   b->extract_args.resize(n_sequences);
   b->commit_plans.resize(n_sequences);
@@ -289,6 +339,14 @@ void formgpu_batch_destroy(formgpu_batch *b) {
     cudaStreamSynchronize(b->copy_stream);
     cudaStreamDestroy(b->copy_stream);
   }
+  if (b->d2h_stream) {
+    cudaStreamSynchronize(b->d2h_stream);
+    cudaStreamDestroy(b->d2h_stream);
+  }
+  if (b->ev_lin) cudaEventDestroy(b->ev_lin);
+  if (b->ev_blocks) cudaEventDestroy(b->ev_blocks);
+  if (b->d_blocks) cudaFree(b->d_blocks);
+  if (b->h_blocks) cudaFreeHost(b->h_blocks);
   b->prof.destroy();
   if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -363,6 +421,17 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
   }
   // previous submit's argument uploads must have been consumed before the ring restarts
   BATCH_CUDA(b, cudaEventSynchronize(b->ev_args));
+  pend.blocks_dma = false;
+  b->blocks_used = 0;
+  if (b->block_dma) {
+    // upper bound of the block words this submission can produce (sized before anything is staged:
+    // the argument blocks carry pointers into d_blocks)
+    size_t doubles = 0;
+    for (size_t r : by_op[FORMGPU_OP_ASSOC_LIN]) doubles += 91 * (size_t)b->ctx[reqs[r].sequence]->W;
+    for (size_t r : by_op[FORMGPU_OP_LINEARIZE]) doubles += 91 * reqs[r].n_pairs;
+    const int rc = ensure_blocks(b, doubles);
+    if (rc) return rc;
+  }
   b->args_used = 0;
   b->partials_used = 0;
   b->tickets_used = 0;
@@ -530,6 +599,7 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
           continue;
         }
         live_assoc.push_back(r);
+        b->assoc_block_off[q.sequence] = kNoBlocks;
         if (!plan.any_query) continue;
         aitems.push_back(plan.aa[0]);
         aitems.push_back(plan.aa[1]);
@@ -542,6 +612,11 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
           LinArgs la;
           lin_make_args(ctx, (int)plan.lin_tasks.size(), la);
           plan.lin_seq = la.seq;
+          if (b->block_dma) {
+            la.out_plain = b->d_blocks + b->blocks_used;
+            b->assoc_block_off[q.sequence] = b->blocks_used;
+            b->blocks_used += 91 * plan.lin_tasks.size();
+          }
           const uint32_t ci = (uint32_t)lin_ctx.size();
           lin_ctx.push_back(la);
           for (size_t k = 0; k < plan.lin_tasks.size(); ++k) {
@@ -625,7 +700,13 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       lin_make_args(ctx, (int)tasks.size(), la);
       b->lin_seqs[q.sequence] = la.seq;
       live_lin[eo].push_back(r);
+      if (!eo) b->lin_block_off[q.sequence] = kNoBlocks;
       if (tasks.empty()) continue;
+      if (!eo && b->block_dma) {
+        la.out_plain = b->d_blocks + b->blocks_used; // task.out_index = position in q.pairs
+        b->lin_block_off[q.sequence] = b->blocks_used;
+        b->blocks_used += 91 * q.n_pairs;
+      }
       const uint32_t ci = (uint32_t)lin_ctx.size();
       lin_ctx.push_back(la);
       for (LinTask &t : tasks) {
@@ -636,6 +717,19 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
     }
     const int rc = stage_lin_groups(b, lin_ctx, lin_tasks, hints, eo != 0, launchers);
     if (rc) return rc;
+  }
+  if (b->blocks_used) {
+    // every block of the submission goes home in one transfer on the D2H stream, behind the last
+    // evaluation kernel; the commit / extraction kernels queued after it do not wait for it
+    const size_t bytes = b->blocks_used * sizeof(double);
+    pend.blocks_dma = true;
+    launchers.push_back([=]() -> int {
+      BATCH_CUDA(b, cudaEventRecord(b->ev_lin, b->stream));
+      BATCH_CUDA(b, cudaStreamWaitEvent(b->d2h_stream, b->ev_lin, 0));
+      BATCH_CUDA(b, cudaMemcpyAsync(b->h_blocks, b->d_blocks, bytes, cudaMemcpyDeviceToHost, b->d2h_stream));
+      BATCH_CUDA(b, cudaEventRecord(b->ev_blocks, b->d2h_stream));
+      return FORMGPU_OK;
+    });
   }
 
   // ---- commit ----
@@ -728,20 +822,33 @@ int submit_collect(formgpu_batch *b) {
     }
     set_status(q, rc);
   }
+  if (pend.blocks_dma) {
+    pend.blocks_dma = false;
+    const int rc = wait_event(b, b->ev_blocks);
+    if (rc) return rc;
+  }
   for (size_t r : live_assoc) {
     formgpu_request &q = reqs[r];
     formgpu_ctx *ctx = b->ctx[q.sequence];
     AssocPlan &plan = b->assoc_plans[q.sequence];
     const bool want_blocks = q.op == FORMGPU_OP_ASSOC_LIN;
+    const size_t off = want_blocks && plan.fused ? b->assoc_block_off[q.sequence] : kNoBlocks;
     set_status(q, assoc_finish(ctx, plan, q.poses, q.n_poses, q.counts_out, q.counts_cap, &q.n_counts,
-                               want_blocks ? q.out : nullptr));
+                               want_blocks ? q.out : nullptr, off != kNoBlocks ? b->h_blocks + off : nullptr));
   }
   for (int eo = 0; eo < 2; ++eo)
     for (size_t r : live_lin[eo]) {
       formgpu_request &q = reqs[r];
       if (q.n_pairs == 0) continue;
-      set_status(q, lin_collect(b->ctx[q.sequence], b->lin_indices[q.sequence], b->lin_seqs[q.sequence],
-                                eo ? 1 : 91, q.out));
+      const std::vector<int> &indices = b->lin_indices[q.sequence];
+      const size_t off = eo ? kNoBlocks : b->lin_block_off[q.sequence];
+      if (off != kNoBlocks) {
+        for (int p : indices)
+          std::memcpy(q.out + 91 * (size_t)p, b->h_blocks + off + 91 * (size_t)p, 91 * sizeof(double));
+        continue;
+      }
+      if (indices.empty()) continue;
+      set_status(q, lin_collect(b->ctx[q.sequence], indices, b->lin_seqs[q.sequence], eo ? 1 : 91, q.out));
     }
   for (size_t r : live_commit) {
     formgpu_request &q = reqs[r];
@@ -789,7 +896,8 @@ int formgpu_batch_wait(formgpu_batch *b) {
 int formgpu_batch_done(formgpu_batch *b) {
   if (!b) return -FORMGPU_ERR_INVALID_ARG;
   if (!b->pend.active) return 1;
-  const cudaError_t e = cudaEventQuery(b->ev_args);
+  cudaError_t e = cudaEventQuery(b->ev_args);
+  if (e == cudaSuccess && b->pend.blocks_dma) e = cudaEventQuery(b->ev_blocks);
   if (e == cudaSuccess) return 1;
   if (e == cudaErrorNotReady) return 0;
   b->err = std::string("cudaEventQuery: ") + cudaGetErrorString(e);

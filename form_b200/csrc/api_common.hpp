@@ -103,8 +103,11 @@ struct AssocPlan {
 };
 int assoc_prepare(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_scan_pose *poses,
                   size_t n_poses, bool want_blocks, AssocPlan &plan);
+/// dma_blocks != nullptr: the blocks of plan.lin_tasks ([task][91] plain doubles) are already in host
+/// memory (batched submits); otherwise they are collected from the context's tagged words.
 int assoc_finish(formgpu_ctx *ctx, AssocPlan &plan, const formgpu_scan_pose *poses, size_t n_poses,
-                 formgpu_pair_count *counts_out, size_t counts_cap, size_t *n_counts, double *out91);
+                 formgpu_pair_count *counts_out, size_t counts_cap, size_t *n_counts, double *out91,
+                 const double *dma_blocks);
 
 /// Linearisation / error: argument block of a launch over `n_tasks` tasks of this context
 /// (assigns the sequence number that tags the results).

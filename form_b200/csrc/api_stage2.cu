@@ -284,7 +284,8 @@ int assoc_prepare(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_sc
 }
 
 int assoc_finish(formgpu_ctx *ctx, AssocPlan &plan, const formgpu_scan_pose *poses, size_t n_poses,
-                 formgpu_pair_count *counts_out, size_t counts_cap, size_t *n_counts, double *out91) {
+                 formgpu_pair_count *counts_out, size_t counts_cap, size_t *n_counts, double *out91,
+                 const double *dma_blocks) {
   const int W = ctx->W;
   const int slot_k = plan.slot_k;
   const int *nq = plan.nq;
@@ -339,7 +340,11 @@ int assoc_finish(formgpu_ctx *ctx, AssocPlan &plan, const formgpu_scan_pose *pos
           return fail(ctx, FORMGPU_ERR_INVALID_ARG, "associate_linearize: no pose for a matched scan");
         idx.push_back((int)(it - plan.lin_slots.begin()));
       }
-      if (sharded_comm(ctx)) {
+      if (dma_blocks) {
+        // batched submits: the blocks of all plan.lin_tasks have arrived by DMA (api_batch.cu)
+        for (size_t k = 0; k < idx.size(); ++k)
+          std::memcpy(out91 + 91 * k, dma_blocks + 91 * (size_t)idx[k], 91 * sizeof(double));
+      } else if (sharded_comm(ctx)) {
         // partial blocks of all plan.lin_tasks sit in d_red: all-reduce, then pick the non-empty pairs
         std::vector<double> all(91 * plan.lin_tasks.size());
         const int rc = lin_collect_comm(ctx, plan.lin_tasks.size(), 91, all.data());
@@ -413,7 +418,7 @@ static int associate_impl(formgpu_ctx *ctx, const formgpu_pose *pose_k, const fo
       if (rc) return rc;
     }
   }
-  return assoc_finish(ctx, plan, poses, n_poses, counts_out, counts_cap, n_counts, out91);
+  return assoc_finish(ctx, plan, poses, n_poses, counts_out, counts_cap, n_counts, out91, nullptr);
 }
 
 extern "C" {
