@@ -317,6 +317,10 @@ def run_ours(args, rank, world, local_rank):
     # ---- value: scans resident in HBM ----
     sampler = ClockSampler(local_rank)
     sampler.start()
+    if args.only_e2e:  # development aid: only the host-buffer leg
+        t_e2e, _, _, _ = timed_batched(host_ptrs, False)
+        sampler.stop()
+        return {"sequences_per_gpu": M, "batches_per_gpu": G, "e2e": round(M * K / t_e2e, 2)} if rank == 0 else None
     t_value, t_value_host, stats_d, gpu_launches = timed_batched(dev_ptrs, True)
     if args.only_value:  # development aid (configuration sweeps): not a bench line
         sampler.stop()
@@ -915,6 +919,7 @@ def main():
     ap.add_argument("--sequences-per-gpu", type=int, default=0,
                     help="independent sequences sharing one GPU (0 = 128 if host memory allows, else 64)")
     ap.add_argument("--only-value", action="store_true", help="development: only the device-resident leg")
+    ap.add_argument("--only-e2e", action="store_true", help="development: only the host-buffer leg")
     ap.add_argument("--host-threads", type=int, default=0,
                     help="host threads driving the batches of a GPU (0 = one per batch, capped at the "
                          "rank's spare cores); a thread pipelines the batches it owns")

@@ -243,7 +243,10 @@ static int create_impl(formgpu_ctx *ctx) {
   FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_pair, 0, 4 * (W + 1) * sizeof(uint32_t), ctx->stream));
   // pair-moment cache + the scratch of the kernel that fills it
   if (const char *env = std::getenv("FORMGPU_STREAM_LINEARIZE")) ctx->moment_cache = env[0] != '1';
-  ctx->mom_max_units = moment_max_units(ctx->kp_cap + ctx->kq_cap, W);
+  ctx->moment_unit = kMomentUnitSingle;
+  if (const char *env = std::getenv("FORMGPU_MOMENT_UNIT")) // tuning: 128 .. 4096, multiple of 32
+    ctx->moment_unit = (uint32_t)std::min(4096, std::max(128, std::atoi(env) / 32 * 32));
+  ctx->mom_max_units = moment_max_units(ctx->kp_cap + ctx->kq_cap, W, kMomentUnitSingle); // the smaller unit sizes the scratch
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_moments, (size_t)W * W * kMomentStride));
   FORMGPU_CUDA(ctx, cudaMemsetAsync(ctx->d_moments, 0, (size_t)W * W * kMomentStride * sizeof(double), ctx->stream));
   FORMGPU_CUDA(ctx, dev_alloc(&ctx->d_mom_partials, (size_t)ctx->mom_max_units * kMomentPartial));

@@ -309,6 +309,7 @@ int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size
     formgpu_ctx *c = nullptr;
     const int rc = formgpu_create(p, device, b->stream, &c); // every context shares the batch stream
     if (rc != FORMGPU_OK) return bail(rc, std::string("formgpu_create: ") + formgpu_last_error(nullptr));
+    c->moment_unit = kMomentUnit; // throughput-sized units (kernels.hpp)
     b->ctx.push_back(c);
   }
   b->moment_cache = b->ctx[0]->moment_cache;

@@ -279,7 +279,8 @@ int assoc_prepare(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_sc
   m.shard_rank = sharded_comm(ctx) ? ctx->comm_rank : 0;
   m.shard_world = sharded_comm(ctx) ? ctx->comm_world : 1;
   for (int i = 0; i < W; ++i) m.slots[i] = (unsigned char)i;
-  plan.mom_units = std::min(ctx->mom_max_units, moment_max_units((size_t)nq[0] + (size_t)nq[1], W));
+  m.unit = ctx->moment_unit;
+  plan.mom_units = std::min(ctx->mom_max_units, moment_max_units((size_t)nq[0] + (size_t)nq[1], W, m.unit));
   return FORMGPU_OK;
 }
 

@@ -263,6 +263,7 @@ struct formgpu_ctx {
   double *d_mom_partials = nullptr; // [mom_max_units][kMomentPartial]
   unsigned *d_mom_tickets = nullptr; // [W], self-cleaning
   int mom_max_units = 0;
+  uint32_t moment_unit = 128; // kMomentUnitSingle; contexts of a batch use kMomentUnit (api_batch.cu)
   // linearize / error are evaluated from the cache (default) or, with
   // FORMGPU_STREAM_LINEARIZE=1 and always in point-sharded mode, by streaming the correspondences
   bool moment_cache = true;

@@ -806,12 +806,27 @@ __device__ __forceinline__ int closest_in_row_thread(const float4 *rowp, const u
     w_seed = w_min;
     eval(w_seed);
   }
-  // every other chunk the bound cannot exclude; the bound tightens as chunks are evaluated
-  // (still exact: a chunk is skipped only if each of its points loses to the current best)
-  for (int w = 0; w < words; ++w) {
-    if (w == w_seed) continue;
-    const float lb = box_dist2(box[2 * w], box[2 * w + 1], p);
-    if (lb < INFINITY && lb * (1.0f - 1e-5f) <= best) eval(w);
+  // Every other chunk the bound cannot exclude.  The chunks are first COLLECTED (box tests against
+  // the best of the seed chunk, 32 chunks per mask) and then evaluated from ONE loop: evaluating
+  // inside the box loop left every thread of a warp at a different chunk index - the ~30-iteration
+  // point loop then ran once per distinct index with a handful of lanes (ncu: 8 of 32).  Testing
+  // against the seed's best instead of the running best is still exact (a chunk is skipped only
+  // if each of its points loses to a best that can only improve); the bound is re-tested when
+  // a chunk is popped.
+  for (int w0 = 0; w0 < words; w0 += 32) {
+    uint32_t need = 0u;
+    const int wn = min(32, words - w0);
+    for (int i = 0; i < wn; ++i) {
+      const int w = w0 + i;
+      const float lb = box_dist2(box[2 * w], box[2 * w + 1], p);
+      if (w != w_seed && lb < INFINITY && lb * (1.0f - 1e-5f) <= best) need |= 1u << i;
+    }
+    while (need) {
+      const int w = w0 + __ffs(need) - 1;
+      need &= need - 1u;
+      const float lb = box_dist2(box[2 * w], box[2 * w + 1], p);
+      if (lb * (1.0f - 1e-5f) <= best) eval(w);
+    }
   }
   return bc == 0x7fffffff ? -1 : bc;
 }

@@ -288,7 +288,10 @@ constexpr int kMomentPoint = 28;     // packed upper triangle of sum zeta zeta^T
 constexpr int kMomentStride = 132;   // doubles per entry: M_p[91] | M_q[28] | rel0[12] | counts (2 x u32)
 constexpr int kMomentAcc = 73;       // distinct planar sums a thread accumulates
 constexpr int kMomentPartial = 104;  // doubles per unit partial: 73 planar | 28 point | pad
-constexpr uint32_t kMomentUnit = 512; // correspondences per warp-sized unit of work
+// correspondences per warp-sized unit of work (MomentArgs::unit): batched submits amortise the
+// per-unit reduction over 512 correspondences; a single sequence's association (~15 k accepted
+// matches) would occupy ~40 warps of the GPU that way, so it is cut into units of 128
+constexpr uint32_t kMomentUnit = 512, kMomentUnitSingle = 128;
 
 struct MomentArgs { // one association of one context
   size_t kp_cap, kq_cap;
@@ -303,11 +306,13 @@ struct MomentArgs { // one association of one context
   int W;
   int n_pairs;               // map slots listed in `slots`
   int shard_rank, shard_world;
+  uint32_t unit, pad_unit;   // correspondences per unit (kMomentUnit or kMomentUnitSingle)
   unsigned char slots[kMaxWindow];
 };
+static_assert(sizeof(MomentArgs) % 8 == 0, "MomentArgs is copied in 8-byte words");
 /// Upper bound of the units (= warps) one association with n_corr accepted matches over n_pairs
 /// pairs can need.
-inline int moment_max_units(size_t n_corr, int n_pairs) { return (int)(n_corr / kMomentUnit) + n_pairs; }
+inline int moment_max_units(size_t n_corr, int n_pairs, uint32_t unit) { return (int)(n_corr / unit) + n_pairs; }
 void moments_launch(const MomentArgs &a, int max_units, cudaStream_t stream, Profiler &prof);
 void moments_batch_launch(const MomentArgs *items_dev, int n_items, int max_units, cudaStream_t stream,
                           Profiler &prof);

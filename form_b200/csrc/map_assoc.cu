@@ -702,11 +702,14 @@ __device__ __forceinline__ void nn_consider(NnBest &b, const WorldPoint &p, uint
   // 4-lane double squared norm, lane 3 = 0 padding: (d0^2 + d2^2) + (d1^2 + 0)
   const double d0 = p.x - wx, d1 = p.y - wy, d2 = p.z - wz;
   const double dist = (d0 * d0 + d2 * d2) + (d1 * d1 + 0.0);
-  if (dist < b.d || (dist == b.d && (rank < b.rank || (rank == b.rank && p.tie < b.tie)))) {
-    b.d = dist;
-    b.tie = p.tie;
-    b.rank = rank;
-    b.pos = pos;
+  // one comparison rejects nearly every candidate; the rule-R5 tie-break is off the hot path
+  if (dist <= b.d) {
+    if (dist < b.d || rank < b.rank || (rank == b.rank && p.tie < b.tie)) {
+      b.d = dist;
+      b.tie = p.tie;
+      b.rank = rank;
+      b.pos = pos;
+    }
   }
 }
 __device__ __forceinline__ void nn_scan(NnBest &b, const WorldPoint *world, uint32_t lo, uint32_t n, int rank,
@@ -748,9 +751,6 @@ constexpr unsigned shift_mask(int axis, int dir) {
 }
 constexpr unsigned kShiftNeg[3] = {shift_mask(0, -1), shift_mask(1, -1), shift_mask(2, -1)};
 constexpr unsigned kShiftPos[3] = {shift_mask(0, 1), shift_mask(1, 1), shift_mask(2, 1)};
-constexpr int kMaxAdjacent = 26; // adjacent units a thread visits by itself (26 = all: measured, capping at 8 and
-                                 // sending the rest to the cooperative phase cost 12 % more)
-
 __device__ __forceinline__ void assoc_cells_body(const AssocArgs &a) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -777,58 +777,40 @@ __device__ __forceinline__ void assoc_cells_body(const AssocArgs &a) {
   const bool by_cell = (c0raw & kCellFlag) != 0u;
   const double qq[3] = {wx, wy, wz};
   int f0[3] = {0, 0, 0};
-  double face2[3][2]; // squared distance to the lower / upper face of the unit, margin applied
-  double margin_max = 0.0;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < 3; ++k)
+    if (by_cell) f0[k] = cell_index(qq[k] - (double)c[k] * w, inv_cw);
+  // squared distance from the query to the lower / upper face of its unit along axis k, shrunk by a
+  // margin that covers the rounding of floor(x / w) at the voxel (and cell) faces.  Recomputed
+  // where needed instead of kept: the far faces are only looked at by the rare far-side pass.
+  auto faces = [&](const int k, double &lo2, double &hi2) -> double {
     const double vlo = (double)c[k] * w;
-    // covers the rounding of floor(x / w) at the voxel (and cell) faces
     const double margin = 1e-9 * (1.0 + fabs(qq[k])) + 4e-16 * fabs(vlo);
-    margin_max = fmax(margin_max, margin);
-    double ulo = vlo, uw = w;
-    if (by_cell) {
-      f0[k] = cell_index(qq[k] - vlo, inv_cw);
-      ulo = vlo + (double)f0[k] * cw;
-      uw = cw;
-    }
+    const double ulo = by_cell ? vlo + (double)f0[k] * cw : vlo, uw = by_cell ? cw : w;
     const double dm = fmax(qq[k] - ulo - margin, 0.0), dp = fmax(ulo + uw - qq[k] - margin, 0.0);
-    face2[k][0] = dm * dm;
-    face2[k][1] = dp * dp;
-  }
+    lo2 = dm * dm;
+    hi2 = dp * dp;
+    return margin;
+  };
   {
     uint32_t lo = s0, n = c0raw & ~kCellFlag;
     if (by_cell) cell_range(a, s0, c0raw, f0[0], f0[1], f0[2], lo, n);
     nn_scan(best, a.world, lo, n, 0, wx, wy, wz);
   }
   // ---- phase 2: the adjacent units (cells, or voxels) that can hold a point at least as close
-  // as the best so far.  Per axis a direction qualifies only if its face alone is that close (six
-  // comparisons select the candidate shifts; the summed bound is tested when a shift is popped).
-  // A query with more than kMaxAdjacent candidates - its own unit is empty, or its best is far -
-  // is left to the cooperative phase 3: in a warp of 32 unrelated queries one such lane would keep
-  // the other 31 waiting for up to 26 probe + scan rounds.
-  unsigned surv = 0u;
-  if (searchable) {
-    surv = 0x07fffffeu; // shift ranks 1..26
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      constexpr unsigned neg[3] = {kShiftNeg[0], kShiftNeg[1], kShiftNeg[2]};
-      constexpr unsigned pos[3] = {kShiftPos[0], kShiftPos[1], kShiftPos[2]};
-      if (!(face2[k][0] <= best.d)) surv &= ~neg[k];
-      if (!(face2[k][1] <= best.d)) surv &= ~pos[k];
-    }
-  }
-  bool unresolved = __popc(surv) > kMaxAdjacent;
-  if (unresolved) surv = 0u;
-  while (surv) {
-    const int v = __ffs(surv) - 1;
-    surv &= surv - 1u;
-    const int sh[3] = {lane_shift(v, 0), lane_shift(v, 1), lane_shift(v, 2)};
-    double lb = 0.0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) lb += sh[k] == 0 ? 0.0 : sh[k] < 0 ? face2[k][0] : face2[k][1];
+  // as the best so far.  (a) The seven units of the NEAR octant - per axis the unit behind the
+  // closer face - in ascending order of their lower bound (sort of three face distances: a <= b
+  // <= c gives a, b, {c, a+b}, a+c, b+c, a+b+c), leaving at the first bound above the best: a
+  // query whose own unit is empty gets a finite best from its nearest neighbours first instead of
+  // walking all 26 shifts against an infinite one, and a typical query stops after one or two
+  // units.  (b) The 19 units with a component beyond a FAR face: six comparisons against the best
+  // select the candidate shifts (usually none), the summed bound is tested when a shift is popped.
+  // All pruning is against the best SO FAR with the margin-shrunk bounds: exact.
+  auto visit = [&](const int sh0, const int sh1, const int sh2, const double lb) {
+    const int sh[3] = {sh0, sh1, sh2};
     uint32_t lo = 0u, n = 0u;
-    int rank = v;
-    if (lb <= best.d) { // exact pruning against the best SO FAR
+    int rank = 0;
+    if (lb <= best.d) {
       if (by_cell) {
         // the cell f0 + sh lies in the centre voxel or in the neighbour voxel `carry`
         int carry[3], ci[3];
@@ -847,12 +829,77 @@ __device__ __forceinline__ void assoc_cells_body(const AssocArgs &a) {
         }
         if (ctraw) cell_range(a, st, ctraw, ci[0], ci[1], ci[2], lo, n);
       } else {
+        rank = shift_rank(sh0, sh1, sh2);
         uint32_t ct = 0u;
-        probe_voxel(a.hash, a.hash_mask, pack_key(c[0] + sh[0], c[1] + sh[1], c[2] + sh[2]), lo, ct);
+        probe_voxel(a.hash, a.hash_mask, pack_key(c[0] + sh0, c[1] + sh1, c[2] + sh2), lo, ct);
         n = ct & ~kCellFlag;
       }
     }
     nn_scan(best, a.world, lo, n, rank, wx, wy, wz);
+  };
+  bool unresolved = false;
+  double margin_max = 0.0;
+  if (searchable) {
+    // near face per axis, then the three (bound, axis bit) pairs in ascending order
+    double fa, fb, fc;
+    unsigned nneg_bits = 0u; // bit k: the lower face of axis k is the near one
+    {
+      double lo2, hi2;
+      margin_max = faces(0, lo2, hi2);
+      if (lo2 <= hi2) nneg_bits |= 1u;
+      fa = fmin(lo2, hi2);
+      margin_max = fmax(margin_max, faces(1, lo2, hi2));
+      if (lo2 <= hi2) nneg_bits |= 2u;
+      fb = fmin(lo2, hi2);
+      margin_max = fmax(margin_max, faces(2, lo2, hi2));
+      if (lo2 <= hi2) nneg_bits |= 4u;
+      fc = fmin(lo2, hi2);
+    }
+    unsigned ma = 1u, mb = 2u, mc = 4u;
+    auto order2 = [](double &x, unsigned &mx, double &y, unsigned &my) {
+      if (y < x) {
+        const double t = x; x = y; y = t;
+        const unsigned u = mx; mx = my; my = u;
+      }
+    };
+    order2(fa, ma, fb, mb);
+    order2(fb, mb, fc, mc);
+    order2(fa, ma, fb, mb);
+    // subsets of the sorted axes (bit 0 = a, 1 = b, 2 = c), three bits per step, first step lowest
+    const unsigned seq = (fc <= fa + fb) ? 07653421u : 07654321u;
+#pragma unroll 1
+    for (int i = 0; i < 7; ++i) {
+      const unsigned t = (seq >> (3 * i)) & 7u;
+      const double lb = (((t & 1u) ? fa : 0.0) + ((t & 2u) ? fb : 0.0)) + ((t & 4u) ? fc : 0.0);
+      if (!(lb <= best.d)) break; // ascending bounds: nothing later can qualify either
+      const unsigned m = ((t & 1u) ? ma : 0u) | ((t & 2u) ? mb : 0u) | ((t & 4u) ? mc : 0u);
+      visit((m & 1u) ? ((nneg_bits & 1u) ? -1 : 1) : 0, (m & 2u) ? ((nneg_bits & 2u) ? -1 : 1) : 0,
+            (m & 4u) ? ((nneg_bits & 4u) ? -1 : 1) : 0, lb);
+    }
+    // shifts with a component beyond a far face, face-tested against the best so far
+    constexpr unsigned neg[3] = {kShiftNeg[0], kShiftNeg[1], kShiftNeg[2]};
+    constexpr unsigned pos[3] = {kShiftPos[0], kShiftPos[1], kShiftPos[2]};
+    unsigned surv = 0u;
+    double face2[3][2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      faces(k, face2[k][0], face2[k][1]);
+      surv |= ((nneg_bits >> k) & 1u) ? pos[k] : neg[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (!(face2[k][0] <= best.d)) surv &= ~neg[k];
+      if (!(face2[k][1] <= best.d)) surv &= ~pos[k];
+    }
+    while (surv) {
+      const int v = __ffs(surv) - 1;
+      surv &= surv - 1u;
+      const int sh[3] = {lane_shift(v, 0), lane_shift(v, 1), lane_shift(v, 2)};
+      double lb = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) lb += sh[k] == 0 ? 0.0 : sh[k] < 0 ? face2[k][0] : face2[k][1];
+      visit(sh[0], sh[1], sh[2], lb);
+    }
   }
   if (by_cell && !unresolved) {
     // every cell that was not visited is at least one cell width away (along some axis) or was
@@ -1064,13 +1111,23 @@ __device__ __forceinline__ void block_prefix(const uint32_t *hist_cnt, int nbloc
   for (int i = threadIdx.x; i < nb; i += blockDim.x) s_pre[i] = s_tot[i] = 0u;
   __syncthreads();
   const int total = nblocks * nb;
-#pragma unroll 4
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const uint32_t c = __ldcg(&hist_cnt[i]);
-    if (c) {
-      const int bb = i / nb, b = i - bb * nb;
-      atomicAdd(&s_tot[b], c);
-      if (bb < blk) atomicAdd(&s_pre[b], c);
+  // eight counters per thread are requested before the first is consumed (the loop was one L2
+  // round trip per four counters: ncu, 43 % of the kernel's samples on the consuming compare)
+  for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {
+    uint32_t c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * (int)blockDim.x;
+      c[u] = i < total ? __ldcg(&hist_cnt[i]) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (c[u]) {
+        const int i = i0 + u * (int)blockDim.x;
+        const int bb = i / nb, b = i - bb * nb;
+        atomicAdd(&s_tot[b], c[u]);
+        if (bb < blk) atomicAdd(&s_pre[b], c[u]);
+      }
     }
   }
   __syncthreads();

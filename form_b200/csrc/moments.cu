@@ -26,7 +26,7 @@
 // against the oracle the blocks agree to <= 1e-11 (tests/test_moment_model.py, test_gpu_stages.py).
 //
 // Kernels:
-//   moment_kernel      one WARP per unit of kMomentUnit correspondences of one pair (units are
+//   moment_kernel      one WARP per unit of MomentArgs::unit correspondences of one pair (units are
 //                      numbered pair by pair from the device-resident counts, so the launch needs
 //                      no host knowledge of the association's outcome); a lane accumulates the 73
 //                      distinct planar products of its correspondences, the warp reduces them with
@@ -103,12 +103,25 @@ __device__ __forceinline__ void moment_unit(const MomentArgs &a, MomentWarpSmem 
   {
     const float *s = a.seg_planar;
     const size_t st = a.kp_cap;
+    // the nine planes of the NEXT correspondence are requested before the current one is reduced:
+    // the loop was stalled at the first conversion of a freshly loaded value (ncu: 58 % long
+    // scoreboard), one L2 round trip per iteration on a warp that runs alone on its scheduler
+    float cur[9], nxt[9];
+    uint32_t c = p_lo + (uint32_t)lane;
+    if (c < p_hi) {
+#pragma unroll
+      for (int pl = 0; pl < 9; ++pl) cur[pl] = __ldg(s + pl * st + c);
+    }
 #pragma unroll 1
-    for (uint32_t c = p_lo + (uint32_t)lane; c < p_hi; c += 32u) {
-      const double pix = s[0 * st + c], piy = s[1 * st + c], piz = s[2 * st + c];
-      const double n[3] = {(double)s[3 * st + c], (double)s[4 * st + c], (double)s[5 * st + c]};
+    for (; c < p_hi; c += 32u) {
+      if (c + 32u < p_hi) {
+#pragma unroll
+        for (int pl = 0; pl < 9; ++pl) nxt[pl] = __ldg(s + pl * st + c + 32u);
+      }
+      const double pix = cur[0], piy = cur[1], piz = cur[2];
+      const double n[3] = {(double)cur[3], (double)cur[4], (double)cur[5]};
       double q[3];
-      apply_rel(rel0, (double)s[6 * st + c], (double)s[7 * st + c], (double)s[8 * st + c], q[0], q[1], q[2]);
+      apply_rel(rel0, (double)cur[6], (double)cur[7], (double)cur[8], q[0], q[1], q[2]);
       const double r0 = n[0] * (q[0] - pix) + n[1] * (q[1] - piy) + n[2] * (q[2] - piz);
       double nn[6], qq[6];
       {
@@ -140,6 +153,8 @@ __device__ __forceinline__ void moment_unit(const MomentArgs &a, MomentWarpSmem 
 #pragma unroll
       for (int ac = 0; ac < 6; ++ac) MOM_ACC(63 + ac) += nn[ac];
       MOM_ACC(72) += r0 * r0;
+#pragma unroll
+      for (int pl = 0; pl < 9; ++pl) cur[pl] = nxt[pl];
     }
   }
 #undef MOM_ACC
@@ -205,7 +220,7 @@ __device__ __forceinline__ void moment_body(const MomentArgs &a, MomentWarpSmem 
       }
       // a non-empty pair always gets a unit, so its entry is (re)written even when this
       // rank's share is empty
-      if (total_raw) units = max(1, (int)((np + nq + kMomentUnit - 1u) / kMomentUnit));
+      if (total_raw) units = max(1, (int)((np + nq + a.unit - 1u) / a.unit));
     }
     int incl = units;
 #pragma unroll
@@ -247,8 +262,8 @@ __device__ __forceinline__ void moment_body(const MomentArgs &a, MomentWarpSmem 
   }
   __syncwarp();
   // ---- this unit's slice of the concatenated [planar | point] range ----
-  const uint32_t lo = (uint32_t)my_rank * kMomentUnit;
-  const uint32_t hi = min(lo + kMomentUnit, n_p + n_q);
+  const uint32_t lo = (uint32_t)my_rank * a.unit;
+  const uint32_t hi = min(lo + a.unit, n_p + n_q);
   const uint32_t p_lo = min(lo, n_p), p_hi = min(hi, n_p);
   const uint32_t q_lo = max(lo, n_p) - n_p, q_hi = max(hi, n_p) - n_p;
   moment_unit(a, S, off_p + p_lo, off_p + p_hi, off_q + q_lo, off_q + q_hi, lane);

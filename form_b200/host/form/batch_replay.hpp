@@ -9,6 +9,7 @@
 #include "form/trace.hpp"
 
 #include <chrono>
+#include <cstdlib>
 #include <memory>
 
 namespace form {
@@ -22,6 +23,7 @@ public:
     formgpu_params g = to_formgpu_params(hp);
     g.max_window_scans = max_window_scans;
     m_points = (size_t)g.num_rows * (size_t)g.num_columns;
+    if (const char *env = std::getenv("FORM_REPLAY_SKIP_KEYPOINTS")) m_skip_keypoints = env[0] == '1'; // probe only
     const int rc = formgpu_batch_create(&g, device, stream, traces.size(), &m_batch);
     if (rc != FORMGPU_OK)
       throw HotPathError(std::string("formgpu_batch_create: ") + formgpu_batch_last_error(nullptr));
@@ -159,7 +161,7 @@ private:
       r.scan = scans[op.scan];
       r.n_points = m_points;
       r.scan_idx = op.scan;
-      if (!on_device) {
+      if (!on_device && !m_skip_keypoints) {
         r.planar_out = reinterpret_cast<formgpu_planar_feat *>(q.planar);
         r.planar_cap = m_planar_cap;
         r.point_out = reinterpret_cast<formgpu_point_feat *>(q.point);
@@ -305,6 +307,7 @@ private:
   size_t m_planar_cap = 0, m_point_cap = 0;
   bool m_host_ready = false;
   bool m_on_device = false;
+  bool m_skip_keypoints = false; // development probe: host scans in, only the counts back
   size_t m_rounds = 0;
   std::vector<formgpu_request> m_reqs; // the round in flight (must outlive formgpu_batch_wait)
   std::vector<size_t> m_owner;
