@@ -231,9 +231,11 @@ def run_ours(args, rank, world, local_rank):
         # S x 2 MiB of page-locked host memory each - only when every rank of the box has ample room
         import psutil
 
-        need_128 = 128 * S * n_points * 16
-        # (x3 headroom: on a 196 GB box one or two ranks take 128 sequences, four or eight take 64)
-        M = 128 if psutil.virtual_memory().available / max(world, 1) >= 3 * need_128 else 64
+        per_seq = S * n_points * 16
+        # the largest multiple of 16 (at most 128, at least 32) whose page-locked scans fit this rank's
+        # share of the free host memory twice over
+        share = psutil.virtual_memory().available / max(world, 1)
+        M = int(max(32, min(128, (share / (2 * per_seq)) // 16 * 16)))
     # G batches (one stream each) driven by T host threads: a thread queues a round on each of
     # its batches (formgpu_batch_submit_async) before it waits for the first, so G rounds are in
     # flight however few cores the rank has.  T never exceeds the rank's spare cores, so the

@@ -187,6 +187,7 @@ FORMGPU_SYMBOLS = {
     "formgpu_batch_submit_async": (_i, [_vp, _vp, _sz]),
     "formgpu_batch_wait": (_i, [_vp]),
     "formgpu_batch_done": (_i, [_vp]),
+    "formgpu_batch_prefetch_scan": (_i, [_vp, _sz, _vp, _sz]),
     "formgpu_batch_last_error": (C.c_char_p, [_vp]),
     "formgpu_batch_profile_enable": (_i, [_vp, _i]),
     "formgpu_batch_profile_read": (_i, [_vp, _vp, _vp]),

@@ -316,6 +316,8 @@ void formgpu_destroy(formgpu_ctx *ctx) {
   F(ctx->d_moments); F(ctx->d_mom_partials); F(ctx->d_mom_tickets);
   comm_release(ctx);
   F(ctx->d_stage_planar); F(ctx->d_stage_point);
+  F(ctx->d_scan_next);
+  if (ctx->ev_prefetch) cudaEventDestroy(ctx->ev_prefetch);
   if (ctx->h_flags) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_flags));
   H(ctx->h_counts); H(ctx->h_planar); H(ctx->h_point); H(ctx->h_upload);
   if (ctx->h_out) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_out));

@@ -13,6 +13,7 @@
 #include "api_common.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <functional>
 #include <new>
@@ -67,6 +68,17 @@ struct formgpu_batch {
   cudaStream_t d2h_stream = nullptr;
   cudaEvent_t ev_lin = nullptr, ev_blocks = nullptr;
   std::vector<size_t> assoc_block_off, lin_block_off; // per sequence: offset into h_blocks, or kNoBlocks
+  // FORMGPU_BATCH_TRACE=1: host-side timing of the submissions, by kind of round (with / without
+  // an extraction), printed when the batch is destroyed - a development probe
+  struct Trace {
+    bool on = false;
+    double build_us[2] = {0, 0}, collect_us[2] = {0, 0}, flight_us[2] = {0, 0}, idle_us = 0;
+    double extract_wait_us = 0, dma_us = 0, blocks_wait_us = 0;
+    size_t rounds[2] = {0, 0};
+    std::chrono::steady_clock::time_point t_submit, t_built, t_done;
+    bool have_done = false;
+    int kind = 0;
+  } trace;
   // the submission in flight (formgpu_batch_submit_async ... formgpu_batch_wait)
   struct Pending {
     bool active = false;
@@ -280,6 +292,7 @@ int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size
   if (const char *env = std::getenv("FORMGPU_ASSOC_LANES")) b->assoc_lanes = std::atoi(env);
   if (const char *env = std::getenv("FORMGPU_PACK_DMA")) b->pack_dma = env[0] != '0';
   if (const char *env = std::getenv("FORMGPU_BLOCK_DMA")) b->block_dma = env[0] != '0';
+  if (const char *env = std::getenv("FORMGPU_BATCH_TRACE")) b->trace.on = env[0] == '1';
   auto bail = [&](int rc, const std::string &msg) {
     g_batch_error = msg;
     formgpu_batch_destroy(b);
@@ -328,6 +341,17 @@ int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size
 void formgpu_batch_destroy(formgpu_batch *b) {
   if (!b) return;
   if (b->stream) cudaStreamSynchronize(b->stream);
+  if (b->trace.on && (b->trace.rounds[0] || b->trace.rounds[1])) {
+    const formgpu_batch::Trace &t = b->trace;
+    for (int k = 0; k < 2; ++k)
+      if (t.rounds[k])
+        std::fprintf(stderr, "[formgpu batch %p] %s rounds %zu: build %.1f us, in flight before wait %.1f us, collect %.1f us\n",
+                     (void *)b, k ? "extract" : "other  ", t.rounds[k], t.build_us[k] / t.rounds[k],
+                     t.flight_us[k] / t.rounds[k], t.collect_us[k] / t.rounds[k]);
+    std::fprintf(stderr, "[formgpu batch %p] idle between rounds %.1f us/round; extract rounds: flag wait %.1f us, keypoint DMA %.1f us; block wait %.1f us/round\n",
+                 (void *)b, t.idle_us / (t.rounds[0] + t.rounds[1]), t.rounds[1] ? t.extract_wait_us / t.rounds[1] : 0.0,
+                 t.rounds[1] ? t.dma_us / t.rounds[1] : 0.0, t.blocks_wait_us / (t.rounds[0] + t.rounds[1]));
+  }
   for (formgpu_ctx *c : b->ctx) formgpu_destroy(c);
   if (b->h_args) cudaFreeHost(b->h_args);
   if (b->d_args) cudaFree(b->d_args);
@@ -459,6 +483,7 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
   // ---- stage 1 ----
   std::function<int()> extract_launcher; // queued after every other group (see copy_stream)
   bool scans_uploading = false;
+  std::vector<cudaEvent_t> prefetch_events; // uploads started earlier that the extraction must see complete
   {
     std::vector<ExtractArgs> items;
     for (size_t r : by_op[FORMGPU_OP_EXTRACT]) {
@@ -480,9 +505,16 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       formgpu_point_feat *dq = nullptr;
       bool host_records = false;
       if (!on_device) {
-        BATCH_CUDA(b, cudaMemcpyAsync(ctx->d_scan, q.scan, q.n_points * sizeof(float4),
-                                      cudaMemcpyHostToDevice, b->copy_stream));
-        scans_uploading = true;
+        if (ctx->d_scan_next && ctx->prefetched_host == q.scan) {
+          // uploaded ahead of this request (formgpu_batch_prefetch_scan): adopt the buffer
+          std::swap(ctx->d_scan, ctx->d_scan_next);
+          prefetch_events.push_back(ctx->ev_prefetch);
+        } else {
+          BATCH_CUDA(b, cudaMemcpyAsync(ctx->d_scan, q.scan, q.n_points * sizeof(float4),
+                                        cudaMemcpyHostToDevice, b->copy_stream));
+          scans_uploading = true;
+        }
+        ctx->prefetched_host = nullptr;
         scan_dev = ctx->d_scan;
         if (b->pack_dma && q.planar_out && q.point_out) {
           // f64 structs into device staging; a copy engine takes them to the caller (collect phase)
@@ -512,6 +544,7 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       if (scans_uploading) BATCH_CUDA(b, cudaEventRecord(b->ev_copy, b->copy_stream));
       extract_launcher = [=]() -> int {
         if (scans_uploading) BATCH_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_copy, 0));
+        for (cudaEvent_t ev : prefetch_events) BATCH_CUDA(b, cudaStreamWaitEvent(b->stream, ev, 0));
         extract_batch_launch(shape, staged<ExtractArgs>(b, off), n_items, b->many_rows_min, b->stream, b->prof);
         BATCH_CUDA(b, cudaGetLastError());
         BATCH_CUDA(b, cudaEventRecord(b->ev_extract, b->stream));
@@ -795,6 +828,7 @@ int submit_collect(formgpu_batch *b) {
                             &live_commit = pend.live_commit;
   const std::vector<size_t>(&live_lin)[2] = pend.live_lin;
   bool dma_pending = false;
+  const auto tc0 = std::chrono::steady_clock::now();
   for (size_t r : live_extract) {
     formgpu_request &q = reqs[r];
     formgpu_ctx *ctx = b->ctx[q.sequence];
@@ -823,10 +857,16 @@ int submit_collect(formgpu_batch *b) {
     }
     set_status(q, rc);
   }
+  const auto tc1 = std::chrono::steady_clock::now();
   if (pend.blocks_dma) {
     pend.blocks_dma = false;
     const int rc = wait_event(b, b->ev_blocks);
     if (rc) return rc;
+  }
+  const auto tc2 = std::chrono::steady_clock::now();
+  if (b->trace.on) {
+    b->trace.extract_wait_us += std::chrono::duration<double, std::micro>(tc1 - tc0).count();
+    b->trace.blocks_wait_us += std::chrono::duration<double, std::micro>(tc2 - tc1).count();
   }
   for (size_t r : live_assoc) {
     formgpu_request &q = reqs[r];
@@ -858,7 +898,11 @@ int submit_collect(formgpu_batch *b) {
     q.n_planar = plan.added[0];
     q.n_point = plan.added[1];
   }
-  if (dma_pending) BATCH_CUDA(b, cudaStreamSynchronize(b->copy_stream)); // keypoints have landed
+  if (dma_pending) {
+    const auto td0 = std::chrono::steady_clock::now();
+    BATCH_CUDA(b, cudaStreamSynchronize(b->copy_stream)); // keypoints have landed
+    if (b->trace.on) b->trace.dma_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - td0).count();
+  }
   if (b->prof.timing) b->prof.collect();
   return first_error;
 }
@@ -874,7 +918,19 @@ int formgpu_batch_submit_async(formgpu_batch *b, formgpu_request *reqs, size_t n
   if (n == 0) return FORMGPU_OK;
   if (!reqs) return bfail(b, FORMGPU_ERR_INVALID_ARG, "formgpu_batch_submit: null requests");
   for (size_t r = 0; r < n; ++r) reqs[r].status = FORMGPU_OK;
+  if (b->trace.on) {
+    b->trace.t_submit = std::chrono::steady_clock::now();
+    if (b->trace.have_done)
+      b->trace.idle_us += std::chrono::duration<double, std::micro>(b->trace.t_submit - b->trace.t_done).count();
+    b->trace.kind = 0;
+    for (size_t r = 0; r < n; ++r)
+      if (reqs[r].op == FORMGPU_OP_EXTRACT) b->trace.kind = 1;
+  }
   const int rc = submit_build(b, reqs, n);
+  if (b->trace.on) {
+    b->trace.t_built = std::chrono::steady_clock::now();
+    b->trace.build_us[b->trace.kind] += std::chrono::duration<double, std::micro>(b->trace.t_built - b->trace.t_submit).count();
+  }
   if (rc != FORMGPU_OK) {
     // aborted before the collect phase: no request may be taken for completed.  Whatever was
     // already queued is drained so that the caller can reuse its buffers.
@@ -891,7 +947,16 @@ int formgpu_batch_wait(formgpu_batch *b) {
   if (!b) return FORMGPU_ERR_INVALID_ARG;
   if (!b->pend.active) return FORMGPU_OK;
   b->pend.active = false;
-  return submit_collect(b);
+  if (!b->trace.on) return submit_collect(b);
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = submit_collect(b);
+  formgpu_batch::Trace &t = b->trace;
+  t.t_done = std::chrono::steady_clock::now();
+  t.have_done = true;
+  t.flight_us[t.kind] += std::chrono::duration<double, std::micro>(t0 - t.t_built).count();
+  t.collect_us[t.kind] += std::chrono::duration<double, std::micro>(t.t_done - t0).count();
+  t.rounds[t.kind] += 1;
+  return rc;
 }
 
 int formgpu_batch_done(formgpu_batch *b) {
@@ -903,6 +968,25 @@ int formgpu_batch_done(formgpu_batch *b) {
   if (e == cudaErrorNotReady) return 0;
   b->err = std::string("cudaEventQuery: ") + cudaGetErrorString(e);
   return -FORMGPU_ERR_CUDA;
+}
+
+int formgpu_batch_prefetch_scan(formgpu_batch *b, size_t sequence, const formgpu_point4f *scan, size_t n_points) {
+  if (!b || sequence >= b->ctx.size() || !scan) return bfail(b, FORMGPU_ERR_INVALID_ARG, "formgpu_batch_prefetch_scan: bad argument");
+  formgpu_ctx *ctx = b->ctx[sequence];
+  if (n_points != ctx->n_points)
+    return bfail(b, FORMGPU_ERR_BAD_SCAN_SIZE, "formgpu_batch_prefetch_scan: scan does not match the expected size");
+  BATCH_CUDA(b, cudaSetDevice(b->device));
+  if (!ctx->d_scan_next) {
+    BATCH_CUDA(b, cudaMalloc(reinterpret_cast<void **>(&ctx->d_scan_next), ctx->n_points * sizeof(float4)));
+    BATCH_CUDA(b, cudaEventCreateWithFlags(&ctx->ev_prefetch, cudaEventDisableTiming));
+  }
+  // d_scan_next is free: the extraction that last read it (as d_scan, before a swap) has been
+  // waited for - a sequence has one request per submission and prefetches between them
+  BATCH_CUDA(b, cudaMemcpyAsync(ctx->d_scan_next, scan, n_points * sizeof(float4), cudaMemcpyHostToDevice,
+                                b->copy_stream));
+  BATCH_CUDA(b, cudaEventRecord(ctx->ev_prefetch, b->copy_stream));
+  ctx->prefetched_host = scan;
+  return FORMGPU_OK;
 }
 
 int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n) {

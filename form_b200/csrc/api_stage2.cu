@@ -193,6 +193,7 @@ int assoc_prepare(formgpu_ctx *ctx, const formgpu_pose *pose_k, const formgpu_sc
       relative_pose(poses[pose_idx[order[n]]].pose, poses[pk].pose, t.rel);
       t.slot_j = slot_k;
       t.slot_i = order[n];
+      t.entry = ctx->d_moments + ((size_t)slot_k * W + order[n]) * kMomentStride;
       t.out_index = (int)n;
       t.dyn_slot_i_plus1 = (uint32_t)order[n] + 1u;
       plan.lin_tasks.push_back(t);

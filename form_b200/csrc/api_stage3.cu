@@ -145,6 +145,7 @@ int lin_build_tasks(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_pairs,
     t.n_point = e->n_point;
     t.slot_j = sj;
     t.slot_i = si;
+    t.entry = ctx->d_moments + ((size_t)sj * W + si) * kMomentStride;
     t.out_index = (int)p;
     tasks.push_back(t);
     indices.push_back((int)p);

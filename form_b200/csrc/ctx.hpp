@@ -137,6 +137,11 @@ struct formgpu_ctx {
 
   // ---- stage 1 ----
   float4 *d_scan = nullptr;
+  // batched submits, host scans: the NEXT scan of the sequence, uploaded ahead of its EXTRACT
+  // request (formgpu_batch_prefetch_scan); swapped with d_scan when that request arrives
+  float4 *d_scan_next = nullptr;
+  const void *prefetched_host = nullptr; // host pointer the copy in d_scan_next came from
+  cudaEvent_t ev_prefetch = nullptr;
   uint32_t *d_valid_bits = nullptr;
   float4 *d_row_box = nullptr; // [B][rows][words][2]
   uint16_t *d_planar_cols = nullptr;

@@ -215,7 +215,9 @@ struct LinTask { // one scan pair with at least one correspondence (144 B)
                              // (association and linearisation queued back to back)
   uint32_t ctx_index;        // batched launches: which context's LinArgs the task uses
   int slot_i;                // window slot of scan i: the pair's entry in the moment cache
-  int pad_[3];
+  int pad_;
+  const double *entry;       // the pair's cache entry (ctx->d_moments + (slot_j * W + slot_i) * kMomentStride):
+                             // resolved by the host so that the evaluation kernel's first load is the entry itself
 };
 static_assert(sizeof(LinTask) == 144, "LinTask size");
 

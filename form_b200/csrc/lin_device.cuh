@@ -90,49 +90,73 @@ template <bool kWarpScope> __device__ __forceinline__ void scope_sync() {
   else __syncthreads();
 }
 
-template <bool kWarpScope = false>
-__device__ __forceinline__ void build_basis(ExpandSmem &S, const double *rel) {
+// entry (r, c) of the skew matrix [t]x
+__device__ __forceinline__ double skew_entry(const double *t, int r, int c) {
+  if (r == c) return 0.0;
+  const double v = t[3 - r - c];
+  return ((c - r + 3) % 3 == 1) ? -v : v;
+}
+
+template <bool kWarpScope = false> __device__ __forceinline__ void zero_basis(ExpandSmem &S) {
   const int tid = kWarpScope ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
   const int nthreads = kWarpScope ? 32 : (int)blockDim.x;
   for (int i = tid; i < 7 * 13; i += nthreads) (&S.Bp[0][0])[i] = 0.0;
   for (int i = tid; i < 7 * 3 * 13; i += nthreads) (&S.Bq[0][0][0])[i] = 0.0;
-  scope_sync<kWarpScope>();
+}
+
+// The non-zero entries of the two bases, 39 independent work items (9 + 27 + 3) spread over the
+// threads `first_thread + item` (a 3-thread version of this fill was 30 % of the evaluation
+// kernel's stall samples: three serial chains while 125 threads waited at the barrier).
+//   plane-point: row = [ u1, -u2, -R^T u1 - R^T [t]x u2, R^T u2, -r ]
+//   point-point: rows = [ [P]x, -I, -[c]x R, R, -e ],  c = P + e - t
+template <bool kWarpScope = false>
+__device__ __forceinline__ void fill_basis(ExpandSmem &S, const double *rel, int first_thread = 0) {
+  const int tid = (kWarpScope ? (int)(threadIdx.x & 31) : (int)threadIdx.x) - first_thread;
+  const int nthreads = kWarpScope ? 32 : (int)blockDim.x;
   const double *R = rel, *t = rel + 9;
-  if (tid < 3) {
-    const int k = tid;
-    // ---- plane-point: row = [ u1, -u2, -R^T u1 - R^T [t]x u2, R^T u2, -r ] ----
-    const double K[3][3] = {{0, -t[2], t[1]}, {t[2], 0, -t[0]}, {-t[1], t[0], 0}}; // skew(t)
-    S.Bp[k][k] = 1.0;          // J_i rot   =  u1
-    S.Bp[3 + k][3 + k] = -1.0; // J_i trans = -u2
-    for (int c = 0; c < 3; ++c) {
-      S.Bp[k][6 + c] = -R[3 * k + c]; // -R^T u1
-      double bt = 0.0;                // (R^T [t]x)[c][k]
-      for (int b = 0; b < 3; ++b) bt += R[3 * b + c] * K[b][k];
-      S.Bp[3 + k][6 + c] = -bt;          // -R^T [t]x u2
+  for (int item = tid; item >= 0 && item < 39; item += nthreads) {
+    if (item < 9) { // (k, c)
+      const int k = item / 3, c = item % 3;
+      S.Bp[k][6 + c] = -R[3 * k + c];    // -R^T u1
       S.Bp[3 + k][9 + c] = R[3 * k + c]; //  R^T u2
-    }
-    if (k == 0) {
-      S.Bp[6][12] = -1.0; // b = -r
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) // +[t]x R, the constant part of -[c]x R
-          S.Bq[6][r][6 + c] = K[r][0] * R[c] + K[r][1] * R[3 + c] + K[r][2] * R[6 + c];
-    }
-    // ---- point-point: rows = [ [P]x, -I, -[c]x R, R, -e ],  c = P + e - t ----
-    double E[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
-    E[k2][k1] = 1.0; // skew(e_k): [k2][k1] = +1, [k1][k2] = -1
-    E[k1][k2] = -1.0;
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) {
-        const double er = E[r][0] * R[c] + E[r][1] * R[3 + c] + E[r][2] * R[6 + c]; // (E_k R)[r][c]
-        S.Bq[k][r][c] = E[r][c];     // [P]x
-        S.Bq[k][r][6 + c] = -er;     // -[P]x R
-        S.Bq[3 + k][r][6 + c] = -er; // -[e]x R
+      double bt = 0.0, kr = 0.0;
+      for (int b = 0; b < 3; ++b) {
+        bt += R[3 * b + c] * skew_entry(t, b, k); // (R^T [t]x)[c][k]
+        kr += skew_entry(t, k, b) * R[3 * b + c]; // ([t]x R)[k][c]
       }
-    S.Bq[3 + k][k][12] = -1.0; // -e
-    S.Bq[6][k][3 + k] = -1.0;  // -I
-    for (int c = 0; c < 3; ++c) S.Bq[6][k][9 + c] = R[3 * k + c]; // R
+      S.Bp[3 + k][6 + c] = -bt;   // -R^T [t]x u2
+      S.Bq[6][k][6 + c] = kr;     // +[t]x R, the constant part of -[c]x R
+      S.Bq[6][k][9 + c] = R[3 * k + c]; // R
+    } else if (item < 36) { // (k, r, c): E_k = skew(e_k)
+      const int j = item - 9, k = j / 9, r = (j / 3) % 3, c = j % 3;
+      // skew(e_k)[x][y]: +-1 where 3 - x - y == k
+      auto ek = [k](int x, int y) {
+        return (x == y || 3 - x - y != k) ? 0.0 : (((y - x + 3) % 3 == 1) ? -1.0 : 1.0);
+      };
+      double er = 0.0; // (E_k R)[r][c]
+      for (int b = 0; b < 3; ++b) er += ek(r, b) * R[3 * b + c];
+      S.Bq[k][r][c] = ek(r, c); // [P]x
+      S.Bq[k][r][6 + c] = -er;              // -[P]x R
+      S.Bq[3 + k][r][6 + c] = -er;          // -[e]x R
+    } else { // k
+      const int k = item - 36;
+      S.Bp[k][k] = 1.0;          // J_i rot   =  u1
+      S.Bp[3 + k][3 + k] = -1.0; // J_i trans = -u2
+      S.Bq[3 + k][k][12] = -1.0; // -e
+      S.Bq[6][k][3 + k] = -1.0;  // -I
+      if (k == 0) S.Bp[6][12] = -1.0; // b = -r
+    }
   }
+}
+
+// The basis only depends on the relative pose, so CTA 0 builds it at kernel start while the
+// rest of the CTA is already streaming correspondences (the first __syncthreads of the
+// reduction publishes it).
+template <bool kWarpScope = false>
+__device__ __forceinline__ void build_basis(ExpandSmem &S, const double *rel) {
+  zero_basis<kWarpScope>(S);
+  scope_sync<kWarpScope>();
+  fill_basis<kWarpScope>(S, rel);
 }
 
 // out = B^T W B in two short unrolled passes: T = W B (7 MACs per entry, all threads),

@@ -330,31 +330,30 @@ __global__ void __launch_bounds__(kMomentThreads, 2) moment_batch_kernel(const M
 // ---------------------------------------------------------------------------
 // evaluation: one CTA of 128 threads per pair
 // ---------------------------------------------------------------------------
-// The work of a pair is ~7 k multiply-adds in six dependent phases (S M, (S M) S^T, W B,
-// B^T (W B), twice).  One warp per pair left every phase several rounds deep and the launch
-// latency-bound (r2 profile: 64 us for 10 k pairs, 17 us for 12); with 128 threads every phase
-// is one to three rounds, and the inputs of the two congruences share their shared memory with
-// the expansion scratch (7.5 KB per pair, 16 pairs resident per SM).
+// The work of a pair is ~7 k multiply-adds; what the kernel costs is its dependency chain (one
+// warp per pair left every phase several rounds deep: 64 us for 10 k pairs, 17 us for 12).  With
+// 128 threads every phase is one to three rounds, and the chain is kept short:
+//   * the cache entry (and, for launches whose tasks live in device memory, the context's argument
+//     block) is requested before anything else; while the loads are in flight the CTA zero-fills
+//     the basis and coefficient matrices;
+//   * the basis of the 13x13 expansion and the coefficient matrices S(dR, dt), Z(dR, dt) depend on
+//     the two relative poses only and are filled in ONE phase, every thread deriving the entries
+//     of dR / dt it needs itself (no dR -> dt -> coefficients barrier chain, no 3-thread fill);
+//   * six barriers in all: loads | basis + coefficients | S M, Z M_q | congruences | W B | B^T (W B).
 namespace {
 
 constexpr int kEvalThreads = 128;
 
-struct EvalCongruence { // phase 1-2 operands; dead once Wp28 / Wq28 exist
+struct EvalSmem {
   double M[13][13];  // sum phi phi^T
   double Mq[7][7];   // sum zeta zeta^T
   double Sc[7][13];  // s = Sc phi
   double Zc[7][7];   // z = Zc zeta
   double T[7][13];   // Sc M
   double TZ[7][7];   // Zc Mq
-};
-struct EvalSmem {
-  union {
-    EvalCongruence c;
-    ExpandSmem exp;
-  };
+  ExpandSmem exp;
   double Wp28[28], Wq28[28];
   double rel[12], rel0[12];
-  double dR[9], dt[3];
   LinTask task; // eval_global_kernel: the task / context blocks of this CTA
   LinArgs args;
 };
@@ -363,9 +362,41 @@ __device__ __forceinline__ int eps3(int k, int a, int b) { // Levi-Civita symbol
   return (k == a || a == b || k == b) ? 0 : (((a - k + 3) % 3 == 1) ? 1 : -1);
 }
 
+// `a` may still be in flight when the body starts (eval_global_kernel loads it with the first
+// phase): it is read after the first barrier only.
 template <bool kErrorOnly>
 __device__ __forceinline__ void eval_body(const LinArgs &a, const LinTask &task, EvalSmem &S) {
   const int tid = threadIdx.x;
+  // ---- phase 0: the pair's cache entry into registers; zero fills while it travels ----
+  const double *entry = task.entry;
+  double ev = 0.0, r0v = 0.0;
+  if (tid < kMomentPlanar + kMomentPoint) ev = __ldcg(entry + tid);
+  if (tid < 12) r0v = __ldcg(entry + kMomentPlanar + kMomentPoint + tid);
+  if (!kErrorOnly) zero_basis<false>(S.exp);
+  for (int i = tid; i < 7 * 13; i += kEvalThreads) (&S.Sc[0][0])[i] = 0.0;
+  for (int i = tid; i < 7 * 7; i += kEvalThreads) (&S.Zc[0][0])[i] = 0.0;
+  if (tid < kMomentPlanar) {
+    int x = 0, e = tid;
+    while (e >= 13 - x) {
+      e -= 13 - x;
+      ++x;
+    }
+    S.M[x][x + e] = ev;
+    S.M[x + e][x] = ev;
+  } else if (tid < kMomentPlanar + kMomentPoint) {
+    int p = 0, e = tid - kMomentPlanar;
+    while (e >= 7 - p) {
+      e -= 7 - p;
+      ++p;
+    }
+    S.Mq[p][p + e] = ev;
+    S.Mq[p + e][p] = ev;
+  }
+  if (tid < 12) {
+    S.rel0[tid] = r0v;
+    S.rel[tid] = task.rel[tid];
+  }
+  __syncthreads();
   if (task.dyn_slot_i_plus1) {
     // queued right behind the association: an empty pair publishes nothing (the host learns
     // the counts from the association and does not wait for it)
@@ -373,90 +404,71 @@ __device__ __forceinline__ void eval_body(const LinArgs &a, const LinTask &task,
     const uint32_t n = __ldcg(&a.pair_row[1 * nb + si]) + __ldcg(&a.pair_row[3 * nb + si]);
     if (n == 0) return; // CTA-uniform
   }
-  EvalCongruence &C = S.c;
-  const double *entry = a.moments + ((size_t)task.slot_j * a.W + task.slot_i) * kMomentStride;
-  if (tid < kMomentPlanar) {
-    int x = 0, e = tid;
-    while (e >= 13 - x) {
-      e -= 13 - x;
-      ++x;
-    }
-    const double v = entry[tid];
-    C.M[x][x + e] = v;
-    C.M[x + e][x] = v;
-  } else if (tid < kMomentPlanar + kMomentPoint) {
-    int p = 0, e = tid - kMomentPlanar;
-    while (e >= 7 - p) {
-      e -= 7 - p;
-      ++p;
-    }
-    const double v = entry[tid];
-    C.Mq[p][p + e] = v;
-    C.Mq[p + e][p] = v;
-  }
-  if (tid < 12) {
-    S.rel0[tid] = entry[kMomentPlanar + kMomentPoint + tid];
-    S.rel[tid] = task.rel[tid];
-  }
-  for (int i = tid; i < 7 * 13; i += kEvalThreads) (&C.Sc[0][0])[i] = 0.0;
-  for (int i = tid; i < 7 * 7; i += kEvalThreads) (&C.Zc[0][0])[i] = 0.0;
-  __syncthreads();
-  // dR = R R0^T, dt = t - dR t0
-  if (tid < 9) {
-    const int r = tid / 3, c = tid % 3;
-    S.dR[tid] = S.rel[3 * r] * S.rel0[3 * c] + S.rel[3 * r + 1] * S.rel0[3 * c + 1] +
-                S.rel[3 * r + 2] * S.rel0[3 * c + 2];
-  }
-  __syncthreads();
-  if (tid < 3)
-    S.dt[tid] = S.rel[9 + tid] - (S.dR[3 * tid] * S.rel0[9] + S.dR[3 * tid + 1] * S.rel0[10] +
-                                  S.dR[3 * tid + 2] * S.rel0[11]);
-  __syncthreads();
-  // coefficient matrices (tests/test_moment_model.py: coeff_S, coeff_Z)
-  if (tid < 27) { // (k, a, c): rows n x (dR q0)
-    const int k = tid / 9, a_ = (tid / 3) % 3, c = tid % 3;
-    double v = 0.0;
+  // ---- phase 1: basis (threads 72..110) and coefficient matrices (threads 0..26, 32..40, 64..66,
+  // 96; tests/test_moment_model.py: coeff_S, coeff_Z), both from rel / rel0 alone ----
+  if (!kErrorOnly) fill_basis<false>(S.exp, S.rel, 72);
+  {
+    const double *rel = S.rel, *rel0 = S.rel0;
+    auto dR = [&](int r, int c) { // (R R0^T)[r][c]
+      return rel[3 * r] * rel0[3 * c] + rel[3 * r + 1] * rel0[3 * c + 1] + rel[3 * r + 2] * rel0[3 * c + 2];
+    };
+    auto dt = [&](int k) { // t - dR t0
+      return rel[9 + k] - (dR(k, 0) * rel0[9] + dR(k, 1) * rel0[10] + dR(k, 2) * rel0[11]);
+    };
+    if (tid < 27) { // (k, a, c): rows n x (dR q0)
+      const int k = tid / 9, a_ = (tid / 3) % 3, c = tid % 3;
+      double v = 0.0;
 #pragma unroll
-    for (int b = 0; b < 3; ++b) v += (double)eps3(k, a_, b) * S.dR[3 * b + c];
-    C.Sc[k][3 * a_ + c] = v;
-  } else if (tid >= 32 && tid < 41) { // (k, a): rows n x dt, and the residual row
-    const int k = (tid - 32) / 3, a_ = (tid - 32) % 3;
-    double v = 0.0;
+      for (int b = 0; b < 3; ++b) {
+        const int e = eps3(k, a_, b);
+        if (e) v += (double)e * dR(b, c);
+      }
+      S.Sc[k][3 * a_ + c] = v;
+    } else if (tid >= 32 && tid < 41) { // (k, a): rows n x dt, and the residual row
+      const int k = (tid - 32) / 3, a_ = (tid - 32) % 3;
+      double v = 0.0;
 #pragma unroll
-    for (int b = 0; b < 3; ++b) v += (double)eps3(k, a_, b) * S.dt[b];
-    C.Sc[k][9 + a_] = v;
-    C.Sc[6][3 * k + a_] = S.dR[3 * k + a_] - (k == a_ ? 1.0 : 0.0);
-    C.Zc[3 + k][a_] = S.dR[3 * k + a_] - (k == a_ ? 1.0 : 0.0);
-  } else if (tid >= 64 && tid < 67) {
-    const int k = tid - 64;
-    C.Sc[3 + k][9 + k] = 1.0;
-    C.Sc[6][9 + k] = S.dt[k];
-    C.Zc[k][k] = 1.0;
-    C.Zc[k][3 + k] = -1.0;
-    C.Zc[3 + k][3 + k] = 1.0;
-    C.Zc[3 + k][6] = S.dt[k];
-  } else if (tid == 96) {
-    C.Sc[6][12] = 1.0;
-    C.Zc[6][6] = 1.0;
+      for (int b = 0; b < 3; ++b) {
+        const int e = eps3(k, a_, b);
+        if (e) v += (double)e * dt(b);
+      }
+      S.Sc[k][9 + a_] = v;
+      const double d = dR(k, a_) - (k == a_ ? 1.0 : 0.0);
+      S.Sc[6][3 * k + a_] = d;
+      S.Zc[3 + k][a_] = d;
+    } else if (tid >= 64 && tid < 67) {
+      const int k = tid - 64;
+      const double d = dt(k);
+      S.Sc[3 + k][9 + k] = 1.0;
+      S.Sc[6][9 + k] = d;
+      S.Zc[k][k] = 1.0;
+      S.Zc[k][3 + k] = -1.0;
+      S.Zc[3 + k][3 + k] = 1.0;
+      S.Zc[3 + k][6] = d;
+    } else if (tid == 96) {
+      S.Sc[6][12] = 1.0;
+      S.Zc[6][6] = 1.0;
+    }
   }
   __syncthreads();
-  // T = Sc M (91 entries), TZ = Zc Mq (49 entries)
+  // ---- phase 2: T = Sc M (91 entries), TZ = Zc Mq (49 entries) ----
   for (int idx = tid; idx < 7 * 13 + 7 * 7; idx += kEvalThreads) {
     double v = 0.0;
     if (idx < 91) {
       const int k = idx / 13, y = idx % 13;
 #pragma unroll
-      for (int l = 0; l < 13; ++l) v += C.Sc[k][l] * C.M[l][y];
-      C.T[k][y] = v;
+      for (int l = 0; l < 13; ++l) v += S.Sc[k][l] * S.M[l][y];
+      S.T[k][y] = v;
     } else {
       const int j = idx - 91, k = j / 7, y = j % 7;
 #pragma unroll
-      for (int l = 0; l < 7; ++l) v += C.Zc[k][l] * C.Mq[l][y];
-      C.TZ[k][y] = v;
+      for (int l = 0; l < 7; ++l) v += S.Zc[k][l] * S.Mq[l][y];
+      S.TZ[k][y] = v;
     }
   }
   __syncthreads();
-  // W_p = T Sc^T, W_q = TZ Zc^T (packed upper triangles, the order expand_and_publish expects)
+  // ---- phase 3: W_p = T Sc^T, W_q = TZ Zc^T (packed upper triangles, the order
+  // expand_and_publish expects) ----
   if (tid < 56) {
     const int which = tid / 28;
     int p = 0, e = tid % 28;
@@ -468,15 +480,15 @@ __device__ __forceinline__ void eval_body(const LinArgs &a, const LinTask &task,
     double v = 0.0;
     if (which == 0) {
 #pragma unroll
-      for (int y = 0; y < 13; ++y) v += C.T[p][y] * C.Sc[q][y];
+      for (int y = 0; y < 13; ++y) v += S.T[p][y] * S.Sc[q][y];
       S.Wp28[tid] = v;
     } else {
 #pragma unroll
-      for (int y = 0; y < 7; ++y) v += C.TZ[p][y] * C.Zc[q][y];
+      for (int y = 0; y < 7; ++y) v += S.TZ[p][y] * S.Zc[q][y];
       S.Wq28[tid - 28] = v;
     }
   }
-  __syncthreads(); // the congruence operands are dead from here on: S.exp reuses their memory
+  __syncthreads();
   const unsigned long long tag = a.seq & 0xffffffffull;
   if (kErrorOnly) {
     if (tid == 0) {
@@ -487,8 +499,7 @@ __device__ __forceinline__ void eval_body(const LinArgs &a, const LinTask &task,
     }
     return;
   }
-  build_basis<false>(S.exp, S.rel); // zero-fills, then three threads write the entries
-  __syncthreads();
+  // ---- phases 4-5: the 13x13 block ----
   expand_and_publish<false>(S.exp, S.Wp28, S.Wq28, true, true, a.inv_sigma2,
                             a.out + 182 * (size_t)task.out_index, tag,
                             a.out_plain ? a.out_plain + 91 * (size_t)task.out_index : nullptr);
@@ -511,10 +522,10 @@ eval_global_kernel(const LinArgs *ctx_args, const LinTask *tasks, int n_tasks) {
   if (tid < (int)(sizeof(LinTask) / 8))
     reinterpret_cast<unsigned long long *>(&s.task)[tid] =
         reinterpret_cast<const unsigned long long *>(tasks + blockIdx.x)[tid];
-  __syncthreads();
-  if (tid < (int)(sizeof(LinArgs) / 8))
-    reinterpret_cast<unsigned long long *>(&s.args)[tid] =
-        reinterpret_cast<const unsigned long long *>(ctx_args + s.task.ctx_index)[tid];
+  // the context's argument block travels together with the cache entry (first phase of the body)
+  if (tid >= 32 && tid < 32 + (int)(sizeof(LinArgs) / 8))
+    reinterpret_cast<unsigned long long *>(&s.args)[tid - 32] =
+        reinterpret_cast<const unsigned long long *>(ctx_args + tasks[blockIdx.x].ctx_index)[tid - 32];
   __syncthreads();
   eval_body<kErrorOnly>(s.args, s.task, s);
 }

@@ -24,6 +24,7 @@ public:
     g.max_window_scans = max_window_scans;
     m_points = (size_t)g.num_rows * (size_t)g.num_columns;
     if (const char *env = std::getenv("FORM_REPLAY_SKIP_KEYPOINTS")) m_skip_keypoints = env[0] == '1'; // probe only
+    if (const char *env = std::getenv("FORM_REPLAY_PREFETCH")) m_prefetch = env[0] != '0';
     const int rc = formgpu_batch_create(&g, device, stream, traces.size(), &m_batch);
     if (rc != FORMGPU_OK)
       throw HotPathError(std::string("formgpu_batch_create: ") + formgpu_batch_last_error(nullptr));
@@ -63,6 +64,7 @@ public:
       const size_t lo = std::min(first, t.num_scans()), hi = std::min(last, t.num_scans());
       m_seq[s].op = lo < hi ? t.scan_begin[lo] : 0;
       m_seq[s].end = lo < hi ? t.op_end(hi - 1) : 0;
+      m_seq[s].scan_hi = hi;
     }
     m_on_device = on_device;
     m_rounds = 0;
@@ -71,6 +73,7 @@ public:
   /// Queues the next pending call of every sequence (formgpu_batch_submit_async); false when
   /// every sequence has reached its end.
   bool submit_next(const formgpu_point4f *const *const *scans) {
+    m_scans = scans;
     m_reqs.clear();
     m_owner.clear();
     for (size_t s = 0; s < m_traces.size(); ++s) {
@@ -92,8 +95,13 @@ public:
       throw HotPathError(std::string("formgpu_batch_submit: ") + formgpu_batch_last_error(m_batch));
     for (size_t r = 0; r < m_reqs.size(); ++r) {
       const size_t s = m_owner[r];
-      account(s, (*m_traces[s]).ops[m_seq[s].op], m_reqs[r]);
+      const TraceOp &op = (*m_traces[s]).ops[m_seq[s].op];
+      account(s, op, m_reqs[r]);
       m_seq[s].op += 1;
+      // a log is being reprocessed: the next scan of the sequence is known, so its upload starts
+      // as soon as the extraction of this one has completed (the scan buffers alternate)
+      if (m_prefetch && !m_on_device && op.kind == TraceOp::EXTRACT && m_scans && op.scan + 1 < m_seq[s].scan_hi)
+        formgpu_batch_prefetch_scan(m_batch, s, m_scans[s][op.scan + 1], m_points);
     }
     ++m_rounds;
   }
@@ -126,6 +134,7 @@ public:
 private:
   struct Seq {
     size_t op = 0, end = 0;
+    size_t scan_hi = 0; // scans [.., scan_hi) belong to the run in progress
     uint64_t cur_scan = 0;
     size_t cur_np = 0, cur_nq = 0;
     std::vector<PairCount> counts;
@@ -308,6 +317,8 @@ private:
   bool m_host_ready = false;
   bool m_on_device = false;
   bool m_skip_keypoints = false; // development probe: host scans in, only the counts back
+  bool m_prefetch = true;        // FORM_REPLAY_PREFETCH=0: every scan is uploaded by its EXTRACT request
+  const formgpu_point4f *const *const *m_scans = nullptr;
   size_t m_rounds = 0;
   std::vector<formgpu_request> m_reqs; // the round in flight (must outlive formgpu_batch_wait)
   std::vector<size_t> m_owner;

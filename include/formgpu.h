@@ -372,6 +372,16 @@ int formgpu_batch_submit(formgpu_batch *b, formgpu_request *reqs, size_t n);
 int formgpu_batch_submit_async(formgpu_batch *b, formgpu_request *reqs, size_t n);
 int formgpu_batch_wait(formgpu_batch *b);
 int formgpu_batch_done(formgpu_batch *b);
+/* Upload ahead: `scan` (host memory, page-locked for a truly asynchronous copy) is the scan that
+ * `sequence` will pass to its next FORMGPU_OP_EXTRACT - known early when recorded logs are
+ * reprocessed, or when a driver thread receives the next revolution while the current one is being
+ * registered (the reference copies nothing: extract() reads the caller's std::vector in place,
+ * /root/reference/form/feature/extraction.tpp:29-45).  The copy starts now on the batch's copy
+ * stream into the sequence's second scan buffer; the EXTRACT request that names the same pointer
+ * finds its input on the device.  The scan must stay unmodified until that request has completed;
+ * a different pointer in the request simply discards the prefetched copy.  Call it between
+ * formgpu_batch_wait and the next submission of the batch. */
+int formgpu_batch_prefetch_scan(formgpu_batch *b, size_t sequence, const formgpu_point4f *scan, size_t n_points);
 const char *formgpu_batch_last_error(const formgpu_batch *b);
 /* As formgpu_profile_enable / _read / formgpu_launch_count, for the batched launches. */
 int formgpu_batch_profile_enable(formgpu_batch *b, int on);

@@ -64,6 +64,18 @@ def test_batched_replay_is_bit_identical_to_single_contexts():
     bh.run(0, n, host_ptrs, on_device=False)
     for s, ref in enumerate(singles):
         same(bh.stats(s), ref, s)
+    # ... by default every next scan is uploaded ahead (formgpu_batch_prefetch_scan, alternating scan
+    # buffers); with the prefetch off each EXTRACT request uploads its own scan: same results
+    import os
+
+    os.environ["FORM_REPLAY_PREFETCH"] = "0"
+    try:
+        bn = BatchReplay([est.trace() for est, _, _ in runs], p)
+        bn.run(0, n, host_ptrs, on_device=False)
+    finally:
+        del os.environ["FORM_REPLAY_PREFETCH"]
+    for s in range(3):
+        assert bn.stats(s) == bh.stats(s)
     # run to run the batched path is deterministic (fixed partition, fixed reduction trees)
     b2 = BatchReplay([est.trace() for est, _, _ in runs], p)
     b2.run(0, n, ptrs, on_device=True)
