@@ -12,7 +12,10 @@
 // the host collects results through the same mapped-memory flags as the single calls.
 #include "api_common.hpp"
 
+#include <cuda.h>
+
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include <functional>
@@ -29,11 +32,6 @@ struct formgpu_batch {
   // argument staging: pinned host ring + device mirror, bump-allocated per submit
   unsigned char *h_args = nullptr, *d_args = nullptr;
   size_t args_cap = 0, args_used = 0;
-  cudaEvent_t ev_args = nullptr;
-  // host scans are uploaded on a side stream while the other groups' kernels of the same
-  // submit run; the extraction kernels (queued last) wait for ev_copy
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_copy = nullptr;
   Profiler prof;
   // scratch reused across submits
   std::vector<AssocPlan> assoc_plans;
@@ -56,7 +54,6 @@ struct formgpu_batch {
   // host-scan extraction: keypoint structs go back by DMA from a device staging buffer (default)
   // or, with FORMGPU_PACK_DMA=0, by the pack kernel's own stores into mapped host memory
   bool pack_dma = true;
-  cudaEvent_t ev_extract = nullptr; // extraction kernels of the submission queued
   // 13x13 blocks of a submission: the evaluation kernels write plain doubles into d_blocks and ONE
   // copy-engine transfer per submission takes them to h_blocks (page-locked).  SM stores of
   // sequence-tagged words into mapped host memory (the single-sequence protocol, FORMGPU_BLOCK_DMA=0)
@@ -65,9 +62,15 @@ struct formgpu_batch {
   bool block_dma = true;
   double *d_blocks = nullptr, *h_blocks = nullptr;
   size_t blocks_cap = 0, blocks_used = 0; // doubles
-  cudaStream_t d2h_stream = nullptr;
-  cudaEvent_t ev_lin = nullptr, ev_blocks = nullptr;
   std::vector<size_t> assoc_block_off, lin_block_off; // per sequence: offset into h_blocks, or kNoBlocks
+  // Completion of a submission: ONE 32-bit stream write (cuStreamWriteValue32) into mapped host
+  // memory behind the last operation of the submission; the host polls the word - no CUDA call
+  // while it waits.  The process-wide rate of CUDA API calls is what bounds the batched engine
+  // (~70 calls per scan from 15 threads, ~1.5 us each under the driver's lock), so a submission
+  // makes as few as it can: no events, copies on the batch's own stream.
+  volatile uint32_t *h_done = nullptr; // [0] submission counter reached, [1] keypoint copies of the collect phase
+  CUdeviceptr d_done = 0;              // device address of h_done
+  uint32_t done_seq = 0, kp_seq = 0;
   // FORMGPU_BATCH_TRACE=1: host-side timing of the submissions, by kind of round (with / without
   // an extraction), printed when the batch is destroyed - a development probe
   struct Trace {
@@ -85,7 +88,6 @@ struct formgpu_batch {
     formgpu_request *reqs = nullptr;
     size_t n = 0;
     int first_error = FORMGPU_OK;
-    bool blocks_dma = false; // a block transfer of this submission is in flight (ev_blocks)
     std::vector<size_t> live_extract, live_assoc, live_lin[2], live_commit;
   } pend;
 };
@@ -114,7 +116,6 @@ constexpr size_t kNoBlocks = ~(size_t)0;
 int ensure_blocks(formgpu_batch *b, size_t doubles) {
   if (doubles <= b->blocks_cap) return FORMGPU_OK;
   BATCH_CUDA(b, cudaStreamSynchronize(b->stream));
-  BATCH_CUDA(b, cudaStreamSynchronize(b->d2h_stream));
   size_t cap = std::max<size_t>(b->blocks_cap * 2, 91 * 1024);
   while (cap < doubles) cap *= 2;
   if (b->d_blocks) cudaFree(b->d_blocks);
@@ -127,15 +128,58 @@ int ensure_blocks(formgpu_batch *b, size_t doubles) {
   return FORMGPU_OK;
 }
 
-// Spin until `ev` has completed (same polling discipline as the mapped-memory flags).
-int wait_event(formgpu_batch *b, cudaEvent_t ev) {
-  unsigned spins = 0;
-  for (;;) {
-    const cudaError_t e = cudaEventQuery(ev);
-    if (e == cudaSuccess) return FORMGPU_OK;
-    if (e != cudaErrorNotReady)
-      return bfail(b, FORMGPU_ERR_CUDA, std::string("block transfer failed: ") + cudaGetErrorString(e));
-    poll_relax(++spins);
+// cuStreamWriteValue32 through the runtime's driver-entry-point lookup (no link dependency on
+// libcuda); nullptr when the driver does not offer it - a one-thread kernel writes the word then
+typedef CUresult (*StreamWrite32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWrite32Fn stream_write32_fn() {
+  static const StreamWrite32Fn fn = [] {
+    void *p = nullptr;
+    if (std::getenv("FORMGPU_NO_STREAM_MEMOPS")) return (StreamWrite32Fn) nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<StreamWrite32Fn>(p);
+  }();
+  return fn;
+}
+
+__global__ void flag_write_kernel(volatile uint32_t *flag, uint32_t value) {
+  __threadfence_system();
+  *flag = value;
+}
+
+// queue "h_done[word] = value" behind everything already on the batch's stream
+int queue_flag(formgpu_batch *b, int word, uint32_t value) {
+  if (StreamWrite32Fn fn = stream_write32_fn()) {
+    const CUresult r = fn(reinterpret_cast<CUstream>(b->stream), b->d_done + 4u * (unsigned)word, value, 0u);
+    if (r == CUDA_SUCCESS) return FORMGPU_OK;
+  }
+  flag_write_kernel<<<1, 1, 0, b->stream>>>(reinterpret_cast<volatile uint32_t *>(b->d_done) + word, value);
+  BATCH_CUDA(b, cudaGetLastError());
+  return FORMGPU_OK;
+}
+
+// Spin (no CUDA call) until h_done[word] == value; the stream state is looked at every 4096 polls
+// so that a faulted kernel cannot hang the caller.
+int wait_done(formgpu_batch *b, int word, uint32_t value) {
+  volatile uint32_t *f = b->h_done + word;
+  for (unsigned spins = 0;; ++spins) {
+    if (*f == value) {
+      std::atomic_thread_fence(std::memory_order_acquire); // results are read after the word
+      return FORMGPU_OK;
+    }
+    if ((spins & 0xfff) == 0xfff) {
+      const cudaError_t e = cudaStreamQuery(b->stream);
+      if (e == cudaSuccess) {
+        if (*f == value) return FORMGPU_OK;
+        return bfail(b, FORMGPU_ERR_STATE, "submission finished without raising its completion word");
+      }
+      if (e != cudaErrorNotReady)
+        return bfail(b, FORMGPU_ERR_CUDA, std::string("submission failed: ") + cudaGetErrorString(e));
+    }
+    poll_relax(spins);
   }
 }
 
@@ -309,15 +353,14 @@ int formgpu_batch_create(const formgpu_params *p, int device, void *stream, size
     b->own_stream = true;
   }
   b->prof.stream = b->stream;
-  if (cudaEventCreateWithFlags(&b->ev_args, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&b->ev_extract, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&b->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&b->ev_lin, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&b->ev_blocks, cudaEventDisableTiming) != cudaSuccess)
-    return bail(FORMGPU_ERR_CUDA, "cudaEventCreate failed");
-  if (cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&b->d2h_stream, cudaStreamNonBlocking) != cudaSuccess)
-    return bail(FORMGPU_ERR_CUDA, "cudaStreamCreate failed");
+  {
+    void *h = nullptr, *d = nullptr;
+    if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess)
+      return bail(FORMGPU_ERR_CUDA, "cudaHostAlloc (completion word) failed");
+    std::memset(h, 0, 64);
+    b->h_done = static_cast<volatile uint32_t *>(h);
+    b->d_done = reinterpret_cast<CUdeviceptr>(d);
+  }
   for (size_t i = 0; i < n_sequences; ++i) {
     formgpu_ctx *c = nullptr;
     const int rc = formgpu_create(p, device, b->stream, &c); // every context shares the batch stream
@@ -357,19 +400,7 @@ void formgpu_batch_destroy(formgpu_batch *b) {
   if (b->d_args) cudaFree(b->d_args);
   if (b->d_partials) cudaFree(b->d_partials);
   if (b->d_tickets) cudaFree(b->d_tickets);
-  if (b->ev_args) cudaEventDestroy(b->ev_args);
-  if (b->ev_copy) cudaEventDestroy(b->ev_copy);
-  if (b->ev_extract) cudaEventDestroy(b->ev_extract);
-  if (b->copy_stream) {
-    cudaStreamSynchronize(b->copy_stream);
-    cudaStreamDestroy(b->copy_stream);
-  }
-  if (b->d2h_stream) {
-    cudaStreamSynchronize(b->d2h_stream);
-    cudaStreamDestroy(b->d2h_stream);
-  }
-  if (b->ev_lin) cudaEventDestroy(b->ev_lin);
-  if (b->ev_blocks) cudaEventDestroy(b->ev_blocks);
+  if (b->h_done) cudaFreeHost(const_cast<uint32_t *>(b->h_done));
   if (b->d_blocks) cudaFree(b->d_blocks);
   if (b->h_blocks) cudaFreeHost(b->h_blocks);
   b->prof.destroy();
@@ -444,9 +475,12 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
     seen[q.sequence] = 1;
     by_op[q.op].push_back(r);
   }
-  // previous submit's argument uploads must have been consumed before the ring restarts
-  BATCH_CUDA(b, cudaEventSynchronize(b->ev_args));
-  pend.blocks_dma = false;
+  // the previous submission's argument upload has been consumed before the ring restarts: its
+  // completion word was waited for (formgpu_batch_wait), and the word is raised behind everything
+  {
+    const int rc = wait_done(b, 0, b->done_seq);
+    if (rc) return rc;
+  }
   b->blocks_used = 0;
   if (b->block_dma) {
     // upper bound of the block words this submission can produce (sized before anything is staged:
@@ -481,9 +515,8 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
   }
 
   // ---- stage 1 ----
-  std::function<int()> extract_launcher; // queued after every other group (see copy_stream)
-  bool scans_uploading = false;
-  std::vector<cudaEvent_t> prefetch_events; // uploads started earlier that the extraction must see complete
+  std::function<int()> extract_launcher; // queued after every other group: extraction is the long pole
+  std::vector<std::pair<float4 *, const void *>> scan_uploads; // host scans of this submission
   {
     std::vector<ExtractArgs> items;
     for (size_t r : by_op[FORMGPU_OP_EXTRACT]) {
@@ -506,13 +539,10 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       bool host_records = false;
       if (!on_device) {
         if (ctx->d_scan_next && ctx->prefetched_host == q.scan) {
-          // uploaded ahead of this request (formgpu_batch_prefetch_scan): adopt the buffer
+          // uploaded ahead of this request (formgpu_batch_prefetch_scan, same stream): adopt the buffer
           std::swap(ctx->d_scan, ctx->d_scan_next);
-          prefetch_events.push_back(ctx->ev_prefetch);
         } else {
-          BATCH_CUDA(b, cudaMemcpyAsync(ctx->d_scan, q.scan, q.n_points * sizeof(float4),
-                                        cudaMemcpyHostToDevice, b->copy_stream));
-          scans_uploading = true;
+          scan_uploads.push_back({ctx->d_scan, q.scan});
         }
         ctx->prefetched_host = nullptr;
         scan_dev = ctx->d_scan;
@@ -541,13 +571,14 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       if (rc) return rc;
       const ExtractArgs shape = items[0];
       const int n_items = (int)items.size();
-      if (scans_uploading) BATCH_CUDA(b, cudaEventRecord(b->ev_copy, b->copy_stream));
+      const size_t scan_bytes = b->ctx[0]->n_points * sizeof(float4);
       extract_launcher = [=]() -> int {
-        if (scans_uploading) BATCH_CUDA(b, cudaStreamWaitEvent(b->stream, b->ev_copy, 0));
-        for (cudaEvent_t ev : prefetch_events) BATCH_CUDA(b, cudaStreamWaitEvent(b->stream, ev, 0));
+        // on the batch's own stream, right before the kernels that read them (every other group of
+        // the submission is already queued ahead): no side stream, no event pair per submission
+        for (const auto &u : scan_uploads)
+          BATCH_CUDA(b, cudaMemcpyAsync(u.first, u.second, scan_bytes, cudaMemcpyHostToDevice, b->stream));
         extract_batch_launch(shape, staged<ExtractArgs>(b, off), n_items, b->many_rows_min, b->stream, b->prof);
         BATCH_CUDA(b, cudaGetLastError());
-        BATCH_CUDA(b, cudaEventRecord(b->ev_extract, b->stream));
         return FORMGPU_OK;
       };
     }
@@ -569,10 +600,19 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       }
       MapArgs a[2];
       MapClearRegion clear;
-      const int rc = map_rebuild_prepare(ctx, q.poses, q.n_poses, b->stream, a, clear);
+      int rc = map_rebuild_prepare(ctx, q.poses, q.n_poses, b->stream, a, clear, false);
       if (rc) {
         set_status(q, rc);
         continue;
+      }
+      {
+        // the request travels with the submission's arguments; the clear kernel puts it in place
+        size_t off_req = 0;
+        rc = stage_args(b, reinterpret_cast<const unsigned char *>(ctx->h_map_req), ctx->map_req_bytes, &off_req);
+        if (rc) return rc;
+        clear.copy_src_off = off_req;
+        clear.copy_dst = ctx->d_map_req;
+        clear.copy_bytes = ctx->map_req_bytes;
       }
       items.push_back(a[0]);
       items.push_back(a[1]);
@@ -590,7 +630,7 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
       const int n_items = (int)regions.size();
       const bool cells = items[0].cells != 0; // one switch per process (FORMGPU_CELL_BUCKETS)
       launchers.push_back([=]() -> int {
-        map_build_batch_launch(staged<MapArgs>(b, off_items), staged<MapClearRegion>(b, off_regions), n_items,
+        map_build_batch_launch(staged<MapArgs>(b, off_items), staged<MapClearRegion>(b, off_regions), b->d_args, n_items,
                                max_points, max_hash, max_clear, cells, b->stream, b->prof);
         BATCH_CUDA(b, cudaGetLastError());
         return FORMGPU_OK;
@@ -752,20 +792,6 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
     const int rc = stage_lin_groups(b, lin_ctx, lin_tasks, hints, eo != 0, launchers);
     if (rc) return rc;
   }
-  if (b->blocks_used) {
-    // every block of the submission goes home in one transfer on the D2H stream, behind the last
-    // evaluation kernel; the commit / extraction kernels queued after it do not wait for it
-    const size_t bytes = b->blocks_used * sizeof(double);
-    pend.blocks_dma = true;
-    launchers.push_back([=]() -> int {
-      BATCH_CUDA(b, cudaEventRecord(b->ev_lin, b->stream));
-      BATCH_CUDA(b, cudaStreamWaitEvent(b->d2h_stream, b->ev_lin, 0));
-      BATCH_CUDA(b, cudaMemcpyAsync(b->h_blocks, b->d_blocks, bytes, cudaMemcpyDeviceToHost, b->d2h_stream));
-      BATCH_CUDA(b, cudaEventRecord(b->ev_blocks, b->d2h_stream));
-      return FORMGPU_OK;
-    });
-  }
-
   // ---- commit ----
   {
     std::vector<CommitArgs> items;
@@ -807,8 +833,12 @@ int submit_build(formgpu_batch *b, formgpu_request *reqs, size_t n) {
     const int rc = extract_launcher();
     if (rc) return rc;
   }
-  BATCH_CUDA(b, cudaEventRecord(b->ev_args, b->stream));
-  return FORMGPU_OK;
+  // every block of the submission goes home in ONE transfer, behind the last kernel (the collect
+  // phase waits for the whole submission anyway), and the completion word behind that
+  if (b->blocks_used)
+    BATCH_CUDA(b, cudaMemcpyAsync(b->h_blocks, b->d_blocks, b->blocks_used * sizeof(double), cudaMemcpyDeviceToHost,
+                                  b->stream));
+  return queue_flag(b, 0, ++b->done_seq);
 }
 
 // Collect phase: wait for the results of the submission in flight (mapped-memory flags and
@@ -828,6 +858,13 @@ int submit_collect(formgpu_batch *b) {
                             &live_commit = pend.live_commit;
   const std::vector<size_t>(&live_lin)[2] = pend.live_lin;
   bool dma_pending = false;
+  const auto tc00 = std::chrono::steady_clock::now();
+  {
+    // ONE wait for the whole submission: the word is raised behind its last operation, so every
+    // flag and tagged word the per-request code below looks at has already arrived
+    const int rc = wait_done(b, 0, b->done_seq);
+    if (rc) return rc;
+  }
   const auto tc0 = std::chrono::steady_clock::now();
   for (size_t r : live_extract) {
     formgpu_request &q = reqs[r];
@@ -840,33 +877,32 @@ int submit_collect(formgpu_batch *b) {
       if (a.host_planar || a.host_point) {
         rc = extract_widen(ctx, q.scan_idx, q.planar_out, q.planar_cap, q.point_out, q.point_cap);
       } else if (a.host_planar_f64 && a.host_planar_f64 == ctx->d_stage_planar) {
-        // the counts are known now: exactly the written structs travel, on the copy stream
+        // the counts are known now: exactly the written structs travel (the batch's stream is idle)
         if (q.n_planar > q.planar_cap || q.n_point > q.point_cap) {
           rc = fail(ctx, FORMGPU_ERR_CAPACITY, "formgpu_extract: output buffers too small");
         } else {
-          if (!dma_pending) BATCH_CUDA(b, cudaStreamWaitEvent(b->copy_stream, b->ev_extract, 0));
-          dma_pending = true;
+          dma_pending = true; // the stream is idle: the copies start at once
           if (q.n_planar)
             BATCH_CUDA(b, cudaMemcpyAsync(q.planar_out, ctx->d_stage_planar, q.n_planar * sizeof(formgpu_planar_feat),
-                                          cudaMemcpyDeviceToHost, b->copy_stream));
+                                          cudaMemcpyDeviceToHost, b->stream));
           if (q.n_point)
             BATCH_CUDA(b, cudaMemcpyAsync(q.point_out, ctx->d_stage_point, q.n_point * sizeof(formgpu_point_feat),
-                                          cudaMemcpyDeviceToHost, b->copy_stream));
+                                          cudaMemcpyDeviceToHost, b->stream));
         }
       }
     }
     set_status(q, rc);
   }
   const auto tc1 = std::chrono::steady_clock::now();
-  if (pend.blocks_dma) {
-    pend.blocks_dma = false;
-    const int rc = wait_event(b, b->ev_blocks);
+  if (dma_pending) {
+    // keypoint copies queued above: their own completion word, polled without CUDA calls while
+    // the remaining requests are collected
+    const int rc = queue_flag(b, 1, ++b->kp_seq);
     if (rc) return rc;
   }
-  const auto tc2 = std::chrono::steady_clock::now();
   if (b->trace.on) {
+    b->trace.blocks_wait_us += std::chrono::duration<double, std::micro>(tc0 - tc00).count();
     b->trace.extract_wait_us += std::chrono::duration<double, std::micro>(tc1 - tc0).count();
-    b->trace.blocks_wait_us += std::chrono::duration<double, std::micro>(tc2 - tc1).count();
   }
   for (size_t r : live_assoc) {
     formgpu_request &q = reqs[r];
@@ -900,7 +936,8 @@ int submit_collect(formgpu_batch *b) {
   }
   if (dma_pending) {
     const auto td0 = std::chrono::steady_clock::now();
-    BATCH_CUDA(b, cudaStreamSynchronize(b->copy_stream)); // keypoints have landed
+    const int rc = wait_done(b, 1, b->kp_seq); // keypoints have landed
+    if (rc) return rc;
     if (b->trace.on) b->trace.dma_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - td0).count();
   }
   if (b->prof.timing) b->prof.collect();
@@ -962,11 +999,10 @@ int formgpu_batch_wait(formgpu_batch *b) {
 int formgpu_batch_done(formgpu_batch *b) {
   if (!b) return -FORMGPU_ERR_INVALID_ARG;
   if (!b->pend.active) return 1;
-  cudaError_t e = cudaEventQuery(b->ev_args);
-  if (e == cudaSuccess && b->pend.blocks_dma) e = cudaEventQuery(b->ev_blocks);
-  if (e == cudaSuccess) return 1;
-  if (e == cudaErrorNotReady) return 0;
-  b->err = std::string("cudaEventQuery: ") + cudaGetErrorString(e);
+  if (b->h_done[0] == b->done_seq) return 1;
+  const cudaError_t e = cudaStreamQuery(b->stream);
+  if (e == cudaSuccess || e == cudaErrorNotReady) return b->h_done[0] == b->done_seq ? 1 : 0;
+  b->err = std::string("cudaStreamQuery: ") + cudaGetErrorString(e);
   return -FORMGPU_ERR_CUDA;
 }
 
@@ -978,13 +1014,12 @@ int formgpu_batch_prefetch_scan(formgpu_batch *b, size_t sequence, const formgpu
   BATCH_CUDA(b, cudaSetDevice(b->device));
   if (!ctx->d_scan_next) {
     BATCH_CUDA(b, cudaMalloc(reinterpret_cast<void **>(&ctx->d_scan_next), ctx->n_points * sizeof(float4)));
-    BATCH_CUDA(b, cudaEventCreateWithFlags(&ctx->ev_prefetch, cudaEventDisableTiming));
   }
   // d_scan_next is free: the extraction that last read it (as d_scan, before a swap) has been
   // waited for - a sequence has one request per submission and prefetches between them
+  // on the batch's own stream: in order with the extraction that will read it, no event needed
   BATCH_CUDA(b, cudaMemcpyAsync(ctx->d_scan_next, scan, n_points * sizeof(float4), cudaMemcpyHostToDevice,
-                                b->copy_stream));
-  BATCH_CUDA(b, cudaEventRecord(ctx->ev_prefetch, b->copy_stream));
+                                b->stream));
   ctx->prefetched_host = scan;
   return FORMGPU_OK;
 }

@@ -83,8 +83,10 @@ int extract_widen(formgpu_ctx *ctx, uint64_t scan_idx, formgpu_planar_feat *plan
 
 /// Reparative rebuild: uploads the request of this context on `stream` and fills the two
 /// MapArgs and the region (cursor + hash tables) that must be zero before the build.
+/// upload = false: the request is left in ctx->h_map_req (ctx->map_req_bytes) for the caller to
+/// bring to ctx->d_map_req before the insert pass (batched submits stage it with their arguments).
 int map_rebuild_prepare(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t n_poses,
-                        cudaStream_t stream, MapArgs a[2], MapClearRegion &clear);
+                        cudaStream_t stream, MapArgs a[2], MapClearRegion &clear, bool upload = true);
 
 /// Association (+ optionally the fused linearisation of the current scan's pairs).
 struct AssocPlan {

@@ -80,9 +80,9 @@ int formgpu_map_rebuild(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
 namespace formgpu {
 
 int map_rebuild_prepare(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t n_poses,
-                        cudaStream_t stream, MapArgs a[2], MapClearRegion &clear) {
+                        cudaStream_t stream, MapArgs a[2], MapClearRegion &clear, bool upload) {
   const int W = ctx->W;
-  FORMGPU_CUDA(ctx, cudaEventSynchronize(ctx->ev_upload));
+  if (upload) FORMGPU_CUDA(ctx, cudaEventSynchronize(ctx->ev_upload));
   MapReq h = map_req_view(ctx->h_map_req, W);
   std::vector<uint8_t> has_pose(W, 0);
   for (size_t p = 0; p < n_poses; ++p) {
@@ -109,9 +109,11 @@ int map_rebuild_prepare(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
     ctx->map_n[t] = (size_t)run;
   }
   for (int s = 0; s < W; ++s) h.scan[s] = ctx->slot_scan[s];
-  FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_map_req, ctx->h_map_req, ctx->map_req_bytes,
-                                    cudaMemcpyHostToDevice, stream));
-  FORMGPU_CUDA(ctx, cudaEventRecord(ctx->ev_upload, stream));
+  if (upload) {
+    FORMGPU_CUDA(ctx, cudaMemcpyAsync(ctx->d_map_req, ctx->h_map_req, ctx->map_req_bytes,
+                                      cudaMemcpyHostToDevice, stream));
+    FORMGPU_CUDA(ctx, cudaEventRecord(ctx->ev_upload, stream));
+  }
 
   // size the tables for this rebuild (load factor <= 0.5); cursor + both tables are one
   // contiguous region, cleared in one go by the caller
@@ -124,6 +126,9 @@ int map_rebuild_prepare(formgpu_ctx *ctx, const formgpu_scan_pose *poses, size_t
   ctx->d_hash[1] = ctx->d_hash[0] + hs[0];
   clear.base = ctx->d_mapmem;
   clear.bytes = 256 + (hs[0] + hs[1]) * sizeof(HashSlot);
+  clear.copy_src_off = 0;
+  clear.copy_dst = nullptr;
+  clear.copy_bytes = 0;
   MapReq d = map_req_view(ctx->d_map_req, W);
   for (int t = 0; t < 2; ++t) {
     a[t].type = t;

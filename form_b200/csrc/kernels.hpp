@@ -90,11 +90,18 @@ void map_build_launch(const MapArgs &planar, const MapArgs &point, cudaStream_t 
 struct MapClearRegion {
   void *base;   // 16-byte aligned
   size_t bytes; // multiple of 16
+  // batched rebuilds: the request of the context (slot offsets, poses, scan ids) rides in the
+  // submission's argument upload and the clear kernel - the first launch of the rebuild - moves it
+  // to its place, instead of one upload + event pair per sequence (copy_bytes a multiple of 8)
+  size_t copy_src_off; // offset of the staged request inside the submission's argument ring
+  void *copy_dst;
+  size_t copy_bytes;
 };
 /// Rebuild of n_items maps in one pass of four launches: items_dev = [item][type] MapArgs,
 /// regions_dev[item] = the cursor + hash tables to clear first.
-void map_build_batch_launch(const MapArgs *items_dev, const MapClearRegion *regions_dev, int n_items,
-                            int max_points, uint32_t max_hash, size_t max_clear_bytes, bool cells,
+/// `ring_dev`: base of the argument ring the regions' copy_src_off refer to.
+void map_build_batch_launch(const MapArgs *items_dev, const MapClearRegion *regions_dev, const unsigned char *ring_dev,
+                            int n_items, int max_points, uint32_t max_hash, size_t max_clear_bytes, bool cells,
                             cudaStream_t stream, Profiler &prof);
 
 struct AssocArgs {

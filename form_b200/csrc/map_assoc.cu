@@ -376,12 +376,19 @@ __global__ void __launch_bounds__(kCellWarps * 32) map_cells_batch_kernel(const 
 
 // clears the hash tables (and allocation cursors) of every item of a batched rebuild:
 // regions[i] = {base, bytes}, bytes a multiple of 16
-__global__ void __launch_bounds__(256) map_clear_batch_kernel(const MapClearRegion *regions) {
+__global__ void __launch_bounds__(256) map_clear_batch_kernel(const MapClearRegion *regions, const unsigned char *ring) {
   const MapClearRegion r = regions[blockIdx.y];
   uint4 *p = reinterpret_cast<uint4 *>(r.base);
   const size_t n = r.bytes / sizeof(uint4);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     p[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (r.copy_bytes) { // the context's rebuild request, staged with the submission's arguments
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(ring + r.copy_src_off);
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(r.copy_dst);
+    const size_t m = r.copy_bytes / sizeof(unsigned long long);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x)
+      dst[i] = src[i];
+  }
 }
 
 void map_build_launch(const MapArgs &pa, const MapArgs &qa, cudaStream_t stream, Profiler &prof) {
@@ -403,13 +410,13 @@ void map_build_launch(const MapArgs &pa, const MapArgs &qa, cudaStream_t stream,
   prof.end(FORMGPU_KG_MAP_BUILD, launches);
 }
 
-void map_build_batch_launch(const MapArgs *items_dev, const MapClearRegion *regions_dev, int n_items,
-                            int max_points, uint32_t max_hash, size_t max_clear_bytes, bool cells,
+void map_build_batch_launch(const MapArgs *items_dev, const MapClearRegion *regions_dev, const unsigned char *ring_dev,
+                            int n_items, int max_points, uint32_t max_hash, size_t max_clear_bytes, bool cells,
                             cudaStream_t stream, Profiler &prof) {
   if (n_items <= 0) return;
   prof.begin(FORMGPU_KG_MAP_BUILD);
   const unsigned clear_blocks = (unsigned)std::min<size_t>((max_clear_bytes / 16 + 255) / 256, 592);
-  map_clear_batch_kernel<<<dim3(std::max(clear_blocks, 1u), n_items), 256, 0, stream>>>(regions_dev);
+  map_clear_batch_kernel<<<dim3(std::max(clear_blocks, 1u), n_items), 256, 0, stream>>>(regions_dev, ring_dev);
   int launches = 1;
   if (max_points > 0) {
     const dim3 gp((max_points + 255) / 256, 2, n_items);
