@@ -71,6 +71,7 @@ struct formgpu_batch {
   volatile uint32_t *h_done = nullptr; // [0] submission counter reached, [1] keypoint copies of the collect phase
   CUdeviceptr d_done = 0;              // device address of h_done
   uint32_t done_seq = 0, kp_seq = 0;
+  uint32_t done_polls = 0;
   // FORMGPU_BATCH_TRACE=1: host-side timing of the submissions, by kind of round (with / without
   // an extraction), printed when the batch is destroyed - a development probe
   struct Trace {
@@ -78,6 +79,7 @@ struct formgpu_batch {
     double build_us[2] = {0, 0}, collect_us[2] = {0, 0}, flight_us[2] = {0, 0}, idle_us = 0;
     double extract_wait_us = 0, dma_us = 0, blocks_wait_us = 0;
     size_t rounds[2] = {0, 0};
+    size_t build_outliers = 0;
     std::chrono::steady_clock::time_point t_submit, t_built, t_done;
     bool have_done = false;
     int kind = 0;
@@ -391,9 +393,9 @@ void formgpu_batch_destroy(formgpu_batch *b) {
         std::fprintf(stderr, "[formgpu batch %p] %s rounds %zu: build %.1f us, in flight before wait %.1f us, collect %.1f us\n",
                      (void *)b, k ? "extract" : "other  ", t.rounds[k], t.build_us[k] / t.rounds[k],
                      t.flight_us[k] / t.rounds[k], t.collect_us[k] / t.rounds[k]);
-    std::fprintf(stderr, "[formgpu batch %p] idle between rounds %.1f us/round; extract rounds: flag wait %.1f us, keypoint DMA %.1f us; block wait %.1f us/round\n",
+    std::fprintf(stderr, "[formgpu batch %p] idle between rounds %.1f us/round; extract rounds: flag wait %.1f us, keypoint DMA %.1f us; block wait %.1f us/round; builds > 1.5 ms: %zu\n",
                  (void *)b, t.idle_us / (t.rounds[0] + t.rounds[1]), t.rounds[1] ? t.extract_wait_us / t.rounds[1] : 0.0,
-                 t.rounds[1] ? t.dma_us / t.rounds[1] : 0.0, t.blocks_wait_us / (t.rounds[0] + t.rounds[1]));
+                 t.rounds[1] ? t.dma_us / t.rounds[1] : 0.0, t.blocks_wait_us / (t.rounds[0] + t.rounds[1]), t.build_outliers);
   }
   for (formgpu_ctx *c : b->ctx) formgpu_destroy(c);
   if (b->h_args) cudaFreeHost(b->h_args);
@@ -966,7 +968,9 @@ int formgpu_batch_submit_async(formgpu_batch *b, formgpu_request *reqs, size_t n
   const int rc = submit_build(b, reqs, n);
   if (b->trace.on) {
     b->trace.t_built = std::chrono::steady_clock::now();
-    b->trace.build_us[b->trace.kind] += std::chrono::duration<double, std::micro>(b->trace.t_built - b->trace.t_submit).count();
+    const double us = std::chrono::duration<double, std::micro>(b->trace.t_built - b->trace.t_submit).count();
+    if (us < 1500.0) b->trace.build_us[b->trace.kind] += us; // first-use allocations are counted apart
+    else b->trace.build_outliers += 1;
   }
   if (rc != FORMGPU_OK) {
     // aborted before the collect phase: no request may be taken for completed.  Whatever was
@@ -1000,6 +1004,9 @@ int formgpu_batch_done(formgpu_batch *b) {
   if (!b) return -FORMGPU_ERR_INVALID_ARG;
   if (!b->pend.active) return 1;
   if (b->h_done[0] == b->done_seq) return 1;
+  // a caller that polls this in a loop must not enter the driver every time: the stream state is
+  // looked at (so that a faulted kernel is noticed) once in 4096 polls
+  if ((++b->done_polls & 0xfffu) != 0u) return 0;
   const cudaError_t e = cudaStreamQuery(b->stream);
   if (e == cudaSuccess || e == cudaErrorNotReady) return b->h_done[0] == b->done_seq ? 1 : 0;
   b->err = std::string("cudaStreamQuery: ") + cudaGetErrorString(e);

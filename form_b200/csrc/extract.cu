@@ -20,6 +20,7 @@
 #include "kernels.hpp"
 
 #include <cfloat>
+#include <cstdlib>
 
 namespace formgpu {
 
@@ -1104,8 +1105,15 @@ void extract_batch_launch(const ExtractArgs &shape, const ExtractArgs *items_dev
   // part of a row takes four times longer, but five times as many serial walks overlap it.
   const bool many_rows = a.rows * n_items >= many_rows_min;
   const int select_threads = many_rows ? 128 : 512;
-  extract_select_batch_kernel<<<grid, select_threads, extract_select_smem(a.cols, a.cols_pad, a.words),
-                                stream>>>(items_dev);
+  // development probe (the kernel is idempotent): how much does the step time move when this
+  // kernel's work doubles?
+  static const int repeat = [] {
+    const char *e = std::getenv("FORMGPU_DEBUG_SELECT_REPEAT");
+    return e ? std::atoi(e) : 0;
+  }();
+  for (int r = 0; r <= repeat; ++r)
+    extract_select_batch_kernel<<<grid, select_threads, extract_select_smem(a.cols, a.cols_pad, a.words),
+                                  stream>>>(items_dev);
   prof.end(FORMGPU_KG_EXTRACT_SELECT, 1);
   prof.begin(FORMGPU_KG_EXTRACT_NORMALS);
   // many rows: one thread per pick (one CTA per row); few rows: one warp per pick, four CTAs

@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 namespace formgpu {
 
@@ -758,7 +759,7 @@ constexpr unsigned shift_mask(int axis, int dir) {
 }
 constexpr unsigned kShiftNeg[3] = {shift_mask(0, -1), shift_mask(1, -1), shift_mask(2, -1)};
 constexpr unsigned kShiftPos[3] = {shift_mask(0, 1), shift_mask(1, 1), shift_mask(2, 1)};
-__device__ __forceinline__ void assoc_cells_body(const AssocArgs &a) {
+template <bool kDry = false> __device__ __forceinline__ void assoc_cells_body(const AssocArgs &a) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool active = q >= a.q_begin && q < a.q_end;
@@ -996,6 +997,10 @@ __device__ __forceinline__ void assoc_cells_body(const AssocArgs &a) {
     if (a.pack_rank) m.slot |= (uint32_t)best.rank << 8;
     m.k = src & 0xFFFFFFu;
   }
+  if (kDry) { // sensitivity probe (FORMGPU_DEBUG_ASSOC_REPEAT): the whole search, no side effects
+    if (mine && m.dist_sqrd < -1.0) a.match[q] = m; // never true: keeps the search alive
+    return;
+  }
   if (mine) a.match[q] = m;
   if (a.hist_cnt) hist_add(a, q, lane, mine, m);
 }
@@ -1049,11 +1054,12 @@ constexpr int kCellQueryThreads = 128;
 __global__ void __launch_bounds__(kCellQueryThreads) assoc_cells_kernel(AssocArgs pa, AssocArgs qa) {
   assoc_cells_body(blockIdx.y == 0 ? pa : qa);
 }
+template <bool kDry>
 __global__ void __launch_bounds__(kCellQueryThreads) assoc_cells_batch_kernel(const AssocArgs *items) {
   __shared__ AssocArgs s_a;
   load_item_args(s_a, items + 2 * blockIdx.z + blockIdx.y);
   if ((int)(blockIdx.x * kCellQueryThreads) >= s_a.n_query) return;
-  assoc_cells_body(s_a);
+  assoc_cells_body<kDry>(s_a);
 }
 
 __global__ void __launch_bounds__(256) assoc_nn_kernel(AssocArgs pa, AssocArgs qa) {
@@ -1088,8 +1094,16 @@ void assoc_batch_launch(const AssocArgs *items_dev, int n_items, int max_query, 
   if (n_items <= 0 || max_query <= 0) return;
   prof.begin(FORMGPU_KG_ASSOC_NN);
   if (lanes == 1) { // cell-ordered buckets: one thread per query
-    assoc_cells_batch_kernel<<<dim3((max_query + kCellQueryThreads - 1) / kCellQueryThreads, 2, n_items),
-                               kCellQueryThreads, 0, stream>>>(items_dev);
+    // development probe: how much does the step time move when this kernel's work doubles?
+    static const int repeat = [] {
+      const char *e = std::getenv("FORMGPU_DEBUG_ASSOC_REPEAT");
+      return e ? std::atoi(e) : 0;
+    }();
+    for (int r = 0; r < repeat; ++r)
+      assoc_cells_batch_kernel<true><<<dim3((max_query + kCellQueryThreads - 1) / kCellQueryThreads, 2, n_items),
+                                       kCellQueryThreads, 0, stream>>>(items_dev);
+    assoc_cells_batch_kernel<false><<<dim3((max_query + kCellQueryThreads - 1) / kCellQueryThreads, 2, n_items),
+                                      kCellQueryThreads, 0, stream>>>(items_dev);
     prof.end(FORMGPU_KG_ASSOC_NN, 1);
     return;
   }

@@ -106,6 +106,12 @@ public:
     ++m_rounds;
   }
   size_t rounds() const { return m_rounds; }
+  /// true when finish_round() would not block (the round in flight has completed)
+  bool round_done() const {
+    const int d = formgpu_batch_done(m_batch);
+    if (d < 0) throw HotPathError(std::string("formgpu_batch_done: ") + formgpu_batch_last_error(m_batch));
+    return d == 1;
+  }
 
   /// One host thread, several batches (one stream each) on the same GPU: the thread queues a
   /// round on every batch before it waits for the first, so reps.size() rounds are in flight
