@@ -319,6 +319,17 @@ def run_ours(args, rank, world, local_rank):
     # ---- value: scans resident in HBM ----
     sampler = ClockSampler(local_rank)
     sampler.start()
+    if args.only_profile:  # development aid: only the per-kernel-group event timing
+        sampler.stop()
+        rp = BatchReplay(traces, p)
+        rp.run(0, W0, dev_ptrs)
+        rp.reset_stats()
+        rp.profile_read()
+        rp.profile_enable(True)
+        rp.run(W0, S, dev_ptrs)
+        prof = rp.profile_read()
+        rp.close()
+        return {g: round(1e3 * v["ms"] / (M * K), 2) for g, v in sorted(prof.items()) if v["launches"]} if rank == 0 else None
     if args.only_e2e:  # development aid: only the host-buffer leg
         t_e2e, _, _, _ = timed_batched(host_ptrs, False)
         sampler.stop()
@@ -922,6 +933,8 @@ def main():
                     help="independent sequences sharing one GPU (0 = 128 if host memory allows, else 64)")
     ap.add_argument("--only-value", action="store_true", help="development: only the device-resident leg")
     ap.add_argument("--only-e2e", action="store_true", help="development: only the host-buffer leg")
+    ap.add_argument("--only-profile", action="store_true",
+                    help="development: only the per-kernel-group CUDA-event times (us per scan)")
     ap.add_argument("--host-threads", type=int, default=0,
                     help="host threads driving the batches of a GPU (0 = one per batch, capped at the "
                          "rank's spare cores); a thread pipelines the batches it owns")

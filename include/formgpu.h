@@ -265,16 +265,19 @@ int formgpu_error_device(formgpu_ctx *ctx, const formgpu_pair *pairs, size_t n_p
  * formgpu_comm_unique_id (any one rank; 128 bytes, to be handed to the other ranks by the caller's
  * own means) + formgpu_comm_init (every rank, collectively) attach a communicator to the context.
  * From then on
- *   - formgpu_associate / _associate_linearize search only this rank's share of the keypoints;
- *     an in-place ncclAllGather per keypoint type returns all matches to every rank, so pair
- *     counts, segments, formgpu_get_matches and formgpu_commit_scan stay replicated and
- *     bit-identical to a single GPU;
+ *   - formgpu_map_rebuild builds, on rank r, the map of the scans whose window slot is congruent
+ *     to r only (the map - 1.5 M points rebuilt every scan in configs[4] - is what is expensive);
+ *     formgpu_associate / _associate_linearize search that sub-map for ALL keypoints, ONE in-place
+ *     ncclAllGather (planar and point candidates together) and a combine kernel that applies the
+ *     full rule-R5 key across the ranks return all matches to every rank, so pair counts,
+ *     segments, formgpu_get_matches and formgpu_commit_scan stay replicated and bit-identical to
+ *     a single GPU;
  *   - the pair moments (stage 3) are accumulated over this rank's share of every pair, and
  *     formgpu_linearize / formgpu_error / the blocks of formgpu_associate_linearize are the
  *     evaluation of those partial moments followed by ONE ncclAllReduce(sum, f64, 91 * n_pairs)
  *     on the context's stream - the only stage-3 bytes that cross NVLink.  Every rank receives
  *     the full result (equal across ranks; differs from one GPU by fp64 summation order only).
- * Extraction and the map rebuild are replicated.  NCCL is loaded at run time (libnccl.so.2);
+ * Extraction, segments and the commit are replicated.  NCCL is loaded at run time (libnccl.so.2);
  * FORMGPU_ERR_UNSUPPORTED when it is not there.  Contexts of a batch cannot be sharded. */
 int formgpu_comm_unique_id(void *id128);
 int formgpu_comm_init(formgpu_ctx *ctx, const void *id128, int rank, int world);

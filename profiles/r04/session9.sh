@@ -1,4 +1,5 @@
 #!/bin/bash
+# NOTE: the switch this session drives existed in the working tree for the experiment only (result: assoc_experiments.txt / e2e_variants.txt)
 OUT=gpurun_out/r4k
 mkdir -p $OUT
 run() { name=$1; shift; "$@" > $OUT/$name.json 2> $OUT/$name.err; echo "$name: $(tail -1 $OUT/$name.json | cut -c1-200)"; }
