@@ -471,14 +471,17 @@ __device__ __forceinline__ HashSlot load_slot(const HashSlot *p) {
   s.count = v.w;
   return s;
 }
+// One 256-bit load per 32-byte map point (sm_100: LDG.E.256; the arrays come from cudaMalloc and the
+// records are 32 bytes, so every point is 32-byte aligned): half the load instructions and half the
+// L1 tag look-ups of the two 128-bit loads this replaces - every lane of a scan touches its own sector.
 __device__ __forceinline__ WorldPoint load_world(const WorldPoint *p) {
-  const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
-  const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  unsigned long long a, b, c, d;
+  asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
   WorldPoint w;
-  w.x = a.x;
-  w.y = a.y;
-  w.z = b.x;
-  w.tie = (unsigned long long)__double_as_longlong(b.y);
+  w.x = __longlong_as_double((long long)a);
+  w.y = __longlong_as_double((long long)b);
+  w.z = __longlong_as_double((long long)c);
+  w.tie = d;
   return w;
 }
 // bucket of the voxel `key`: linear probing (load <= 0.5); absent -> count stays 0
