@@ -849,6 +849,47 @@ def cpu_single_sequence(rows, cols, W, last, scans):
     return (last - W) / t
 
 
+def reference_code_stage1(rows, cols, scans):
+    """Extra CPU row (labelled, not the baseline): FORM's OWN extract() - the reference's
+    extraction.tpp compiled unmodified into oracle/_ref/libformref.so against the API stand-ins of
+    oracle/shim (so Eigen's arithmetic is a restatement and TBB is serial) - timed next to the
+    restatement's extraction on the same scans, one thread each.  None when the library is absent."""
+    import ctypes as C
+
+    lib_path = os.path.join(ROOT, "oracle", "_ref", "libformref.so")
+    if not os.path.exists(lib_path):
+        return None
+    import oracle_lib
+    from form_b200 import _capi
+
+    lib = C.CDLL(lib_path)
+    psz = C.POINTER(C.c_size_t)
+    lib.formref_extract.restype = C.c_int
+    lib.formref_extract.argtypes = [C.POINTER(_capi.Params), C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p,
+                                    C.c_size_t, psz, C.c_void_p, C.c_size_t, psz]
+    params = _capi.default_params(rows, cols)
+    n = rows * cols
+    pl, pt = np.zeros(n, dtype=_capi.PLANAR_FEAT), np.zeros(n, dtype=_capi.POINT_FEAT)
+    a, b = C.c_size_t(), C.c_size_t()
+    t0 = time.perf_counter()
+    for k, scan in enumerate(scans):
+        if lib.formref_extract(C.byref(params), _capi.ptr(scan), n, k, _capi.ptr(pl), n, C.byref(a), _capi.ptr(pt), n,
+                               C.byref(b)) != 0:
+            return None
+    t_ref = (time.perf_counter() - t0) / len(scans)
+    o = oracle_lib.Oracle(params, threads=1)
+    t0 = time.perf_counter()
+    for k, scan in enumerate(scans):
+        o.extract(scan, k)
+    t_port = (time.perf_counter() - t0) / len(scans)
+    return {"form_extract_ms_per_scan": round(1e3 * t_ref, 2), "restatement_extract_ms_per_scan": round(1e3 * t_port, 2),
+            "scans": len(scans), "threads": 1,
+            "what": "stage 1 only: FORM's own FeatureExtractor::extract (oracle/_ref, compiled from "
+                    "/root/reference against the stand-ins of oracle/shim: restated Eigen arithmetic, serial TBB) "
+                    "next to the restatement's extraction on the same scans - a check that the restatement is not "
+                    "a slower baseline than the reference's code, not a baseline itself"}
+
+
 def cpu_baseline_multi(args, rows, cols, W, S, host_np):
     cores = host_cores()
     last = min(S, W + max(1, args.cpu_sample))
@@ -874,7 +915,8 @@ def cpu_baseline_multi(args, rows, cols, W, S, host_np):
             "ms_per_step": round(1e3 / value, 3),
             "single_sequence_reference_threading": {
                 "value": round(single, 4), "unit": "scans/s", "cores": cores,
-                "what": "ONE sequence, worker threads over keypoints where the reference uses TBB"}}
+                "what": "ONE sequence, worker threads over keypoints where the reference uses TBB"},
+            "reference_code_stage1": reference_code_stage1(rows, cols, [host_np[0][k] for k in range(W, min(S, W + 4))])}
 
 
 def run_reference(args, rank, world):

@@ -281,7 +281,23 @@ __device__ __forceinline__ void moment_body(const MomentArgs &a, MomentWarpSmem 
     __threadfence();
     const double *all = a.partials + (size_t)(u - my_rank) * kMomentPartial;
     double v[4] = {0.0, 0.0, 0.0, 0.0}; // elements lane, lane + 32, lane + 64, lane + 96
-    for (int r = 0; r < my_units; ++r) {
+    // four units' partial sums are requested together (16 loads in flight), added in unit order
+    int r = 0;
+    for (; r + 4 <= my_units; r += 4) {
+      double t[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          t[u][k] = lane + 32 * k < kMomentAcc + kMomentPoint
+                        ? __ldcg(&all[(size_t)(r + u) * kMomentPartial + lane + 32 * k])
+                        : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] += t[u][k];
+    }
+    for (; r < my_units; ++r) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if (lane + 32 * k < kMomentAcc + kMomentPoint) v[k] += __ldcg(&all[(size_t)r * kMomentPartial + lane + 32 * k]);

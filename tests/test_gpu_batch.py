@@ -125,6 +125,42 @@ def test_batch_submit_extract_matches_oracle_and_reports_errors():
         lib.formgpu_batch_destroy(h)
 
 
+def test_prefetched_scan_is_used_or_discarded():
+    """formgpu_batch_prefetch_scan: the EXTRACT request that names the prefetched pointer takes the copy
+    uploaded ahead (the scan buffers alternate); a request that names another scan discards it.  Either way
+    the keypoints are those of the oracle for the scan the REQUEST names."""
+    import oracle_lib
+
+    rows, cols = synth.shape("vlp-16")
+    params = _capi.default_params(rows, cols)
+    lib = _capi.gpu_lib()
+    h = C.c_void_p()
+    assert lib.formgpu_batch_create(C.byref(params), 0, None, 1, C.byref(h)) == 0
+    try:
+        cap_p = lib.formgpu_max_planar(lib.formgpu_batch_ctx(h, 0))
+        cap_q = lib.formgpu_max_point(lib.formgpu_batch_ctx(h, 0))
+        scans = [synth.scan("vlp-16", 2, k) for k in range(4)]
+        planar, point = np.zeros(cap_p, _capi.PLANAR_FEAT), np.zeros(cap_q, _capi.POINT_FEAT)
+        ref = oracle_lib.Oracle(params)
+        req = (_capi.Request * 1)()
+        # (prefetched, requested): used, discarded, used again (other buffer), no prefetch at all
+        for k, (pre, use) in enumerate([(0, 0), (1, 2), (3, 3), (None, 1)]):
+            if pre is not None:
+                assert lib.formgpu_batch_prefetch_scan(h, 0, scans[pre].ctypes.data, rows * cols) == 0
+            req[0].sequence, req[0].op = 0, _capi.OP_EXTRACT
+            req[0].scan, req[0].n_points, req[0].scan_idx = scans[use].ctypes.data, rows * cols, k
+            req[0].planar_out, req[0].planar_cap = planar.ctypes.data, cap_p
+            req[0].point_out, req[0].point_cap = point.ctypes.data, cap_q
+            assert lib.formgpu_batch_submit(h, req, 1) == 0 and req[0].status == 0
+            rp, rq = ref.extract(scans[use], k)
+            assert planar[: req[0].n_planar].tobytes() == rp.tobytes(), (pre, use)
+            assert point[: req[0].n_point].tobytes() == rq.tobytes(), (pre, use)
+        assert lib.formgpu_batch_prefetch_scan(h, 0, scans[0].ctypes.data, 17) == _capi.ERR_BAD_SCAN_SIZE
+        assert lib.formgpu_batch_prefetch_scan(h, 5, scans[0].ctypes.data, rows * cols) == _capi.ERR_INVALID_ARG
+    finally:
+        lib.formgpu_batch_destroy(h)
+
+
 def test_batches_run_concurrently():
     import torch
 
