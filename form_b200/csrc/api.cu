@@ -192,7 +192,22 @@ static int create_impl(formgpu_ctx *ctx) {
                                   ctx->kp_cap * sizeof(PlanarRec), cudaHostAllocMapped));
   FORMGPU_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_point),
                                   ctx->kq_cap * sizeof(PointRec), cudaHostAllocMapped));
-  FORMGPU_CUDA(ctx, extract_configure(ctx->cols, ctx->words * 32, ctx->words, ctx->pr_cap));
+  {
+    ExtractArgs shape{};
+    shape.cols = ctx->cols;
+    shape.words = ctx->words;
+    shape.cols_pad = ctx->words * 32;
+    shape.num_sectors = ctx->P.num_sectors;
+    shape.np = ctx->P.neighbor_points;
+    shape.pps = ctx->cols / ctx->P.num_sectors;
+    shape.planar_per_sector = ctx->P.planar_feats_per_sector;
+    shape.point_per_sector = ctx->P.point_feats_per_sector;
+    shape.pr_cap = ctx->pr_cap;
+    shape.qr_cap = ctx->qr_cap;
+    if (shape.num_sectors > kExtractMaxSectors)
+      return fail(ctx, FORMGPU_ERR_INVALID_ARG, "num_sectors exceeds " + std::to_string(kExtractMaxSectors));
+    FORMGPU_CUDA(ctx, extract_configure(shape));
+  }
   FORMGPU_CUDA(ctx, linearize_configure());
   if (const char *env = std::getenv("FORMGPU_CELL_BUCKETS")) ctx->cell_buckets = env[0] != '0';
   if (const char *env = std::getenv("FORMGPU_SINGLE_CELL_SEARCH")) ctx->cell_search_single = env[0] == '1';

@@ -19,8 +19,10 @@
 #include "ctx.hpp"
 #include "kernels.hpp"
 
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
+#include <mutex>
 
 namespace formgpu {
 
@@ -94,6 +96,137 @@ __device__ __forceinline__ void load_item_args(ExtractArgs &dst, const ExtractAr
   for (int i = threadIdx.x; i < (int)(sizeof(ExtractArgs) / 8); i += blockDim.x)
     reinterpret_cast<unsigned long long *>(&dst)[i] = reinterpret_cast<const unsigned long long *>(src)[i];
   __syncthreads();
+}
+
+constexpr int kMaxSectors = kExtractMaxSectors;
+
+// extract_planar (extraction.tpp:332-358) on ONE sector: 32 sorted candidates per step.  `mask` is
+// the used-mask the walk reads and suppresses in (the row's shared mask, or a private copy); the
+// picks go to out[0..], the return value is their number.  Called by all lanes of one warp.
+__device__ __forceinline__ int planar_walk_sector(const ExtractArgs &a, const uint32_t *keys, const uint16_t *sorted,
+                                                  uint32_t *mask, int s, int pps, int S, int cols, int np, int lane,
+                                                  uint16_t *out) {
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int start = s * pps;
+  const int len = ((s == S - 1) ? cols : start + pps) - start;
+  int count = 0;
+  bool done = false;
+  for (int base = 0; base < len && !done; base += 32) {
+    const int i = base + lane;
+    const bool in = i < len;
+    const int col = in ? (int)sorted[start + i] : 0;
+    const float curv = in ? __uint_as_float(keys[col]) : FLT_MAX;
+    const bool below = in && ((double)curv < a.planar_threshold);
+    const bool cand = below && get_bit(mask, col);
+    const bool alive = resolve_group(cand, col, np, lane);
+    const unsigned sel = __ballot_sync(0xffffffffu, alive);
+    const int rank = __popc(sel & lt_mask);
+    // visited iff the count after all earlier visits is still <= cap (:354 '>')
+    const bool accept = alive && (count + rank <= a.planar_per_sector);
+    if (accept) {
+      out[count + rank] = (uint16_t)col;
+      clear_bits(mask, col - (np - 1), col + (np - 1));
+    }
+    count += __popc(__ballot_sync(0xffffffffu, accept));
+    if (count > a.planar_per_sector) done = true;
+    // sorted ascending: once one in-range lane is >= threshold nothing later qualifies
+    if (__ballot_sync(0xffffffffu, below) != __ballot_sync(0xffffffffu, in)) done = true;
+    __syncwarp();
+  }
+  return count;
+}
+
+// extract_point (extraction.tpp:360-399) on ONE sector; `mask` as above, `ulist_base` = the row's
+// scratch list (the sector uses its own columns' slice of it).  Called by all lanes of one warp.
+__device__ __forceinline__ int point_walk_sector(const ExtractArgs &a, uint32_t *mask, uint16_t *ulist_base, int s,
+                                                 int pps, int S, int cols, int np, int pfps, int lane, uint16_t *out) {
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int start = s * pps;
+  const int end = (s == S - 1) ? cols : start + pps;
+  uint16_t *ulist = ulist_base + start;
+  // unused_points (:371-376): ascending list of still-valid columns
+  int U = 0;
+  for (int base = start; base < end; base += 32) {
+    const int c = base + lane;
+    const bool bit = c < end && get_bit(mask, c);
+    const unsigned bal = __ballot_sync(0xffffffffu, bit);
+    if (bit) ulist[U + __popc(bal & lt_mask)] = (uint16_t)c;
+    U += __popc(bal);
+  }
+  __syncwarp();
+  const int factor = 1 + U / pfps; // :379
+  // The reference visits u = offset + m * factor for offset = 0 .. factor-1 (outer) and
+  // m = 0, 1, .. (inner), leaving the inner loop once count > pfps (:394-396).  Equivalently,
+  // in that (offset, m) order: the first element of every pass is ALWAYS visited, a later
+  // element (m > 0) is visited iff the running count is still <= pfps.  A pass holds at most
+  // ceil(U / factor) <= pfps + 1 elements, so stepping pass by pass would keep 3-4 lanes of
+  // the warp busy; instead 32 consecutive elements of the whole visiting sequence (several
+  // passes) are resolved per step.  Pass `o` has n_full + 1 elements if o < rem, else n_full.
+  const int n_full = U / factor, rem = U - n_full * factor;
+  const int split = rem * (n_full + 1); // sequence index of the first element of pass `rem`
+  auto pass_of = [&](int t, int &o, int &m) {
+    if (t < split) {
+      o = t / (n_full + 1);
+      m = t - o * (n_full + 1);
+    } else {
+      const int t2 = t - split, d = t2 / n_full; // n_full > 0 whenever such a t exists
+      o = rem + d;
+      m = t2 - d * n_full;
+    }
+  };
+  int count = 0;
+  int offset = factor; // first pass the strided phase has not touched when it stops
+  for (int base = 0; base < U && count <= pfps; base += 32) {
+    const int t = base + lane;
+    const bool in = t < U;
+    int o = 0, m = 0;
+    if (in) pass_of(t, o, m);
+    const int col = in ? (int)ulist[o + m * factor] : 0;
+    const bool cand = in && get_bit(mask, col);
+    bool alive = resolve_group(cand, col, np, lane);
+    unsigned sel = __ballot_sync(0xffffffffu, alive);
+    // lanes whose count-before already exceeds pfps (a suffix of the group): their m > 0
+    // candidates are not visited and must not suppress anything - resolve again without them
+    // (the outcome of the lanes before the suffix does not depend on later lanes)
+    const unsigned over_bits = __ballot_sync(0xffffffffu, count + __popc(sel & lt_mask) > pfps);
+    if (over_bits) {
+      const int first_over = __ffs(over_bits) - 1;
+      const bool dropped = cand && m > 0 && lane >= first_over;
+      if (__ballot_sync(0xffffffffu, dropped)) {
+        alive = resolve_group(cand && !dropped, col, np, lane);
+        sel = __ballot_sync(0xffffffffu, alive);
+      }
+    }
+    if (alive) {
+      out[count + __popc(sel & lt_mask)] = (uint16_t)col;
+      clear_bits(mask, col - (np - 1), col + (np - 1));
+    }
+    count += __popc(sel);
+    if (count > pfps) { // only the first element of every later pass is still visited
+      int o_last, m_last;
+      pass_of(min(base + 31, U - 1), o_last, m_last);
+      offset = o_last + 1;
+    }
+    __syncwarp();
+  }
+  // Phase B: count > pfps, so every remaining pass visits only u = offset
+  for (int base = offset; base < factor; base += 32) {
+    const int o = base + lane;
+    const bool in = o < factor && o < U;
+    if (__ballot_sync(0xffffffffu, in) == 0) break;
+    const int col = in ? (int)ulist[o] : 0;
+    const bool cand = in && get_bit(mask, col);
+    const bool alive = resolve_group(cand, col, np, lane);
+    const unsigned sel = __ballot_sync(0xffffffffu, alive);
+    const int rank = __popc(sel & lt_mask);
+    if (alive) {
+      out[count + rank] = (uint16_t)col;
+      clear_bits(mask, col - (np - 1), col + (np - 1));
+    }
+    count += __popc(sel);
+    __syncwarp();
+  }
+  return count;
 }
 
 __device__ __forceinline__ void extract_select_body(const ExtractArgs &a, const int row, const int b) {
@@ -223,140 +356,111 @@ __device__ __forceinline__ void extract_select_body(const ExtractArgs &a, const 
   }
   __syncthreads();
 
-  if (tid >= 32) return;
-  const unsigned lt_mask = (1u << lane) - 1u;
+  // ---- greedy walks.  The reference walks the sectors of a row one after the other on ONE mask
+  // (extraction.tpp:44-68), so the walks are sequential by definition - but sectors interact only
+  // through the np-1 columns at their boundaries: a pick near the end of sector s suppresses the
+  // first columns of sector s+1.  So every warp walks a sector SPECULATIVELY on a private copy of
+  // the mask, and warp 0 then validates the sectors in order on the shared mask:
+  //   planar: a speculative result stands iff none of its picks has been suppressed by the
+  //           sectors before it (then both walks take the same decisions candidate by candidate);
+  //   point:  it stands iff the shared mask still equals the initial one on the sector's own
+  //           columns (the list of unused points, and with it the pass structure, is built from
+  //           exactly those bits);
+  // a sector that fails is walked again on the shared mask, which then holds the true state
+  // (CPU models of both rules against the reference's sequential form: tests/test_kernel_models.py).
+  // The walk of one warp was 76 % of a row's latency (ncu, profiles/r04).
+  const int warp = tid >> 5, nwarps = (int)blockDim.x >> 5;
+  uint32_t *m_priv = m_used + words;            // [S][words] private masks
+  uint32_t *m_pinit = m_priv + (size_t)S * words; // [words] point mask before any point pick
+  uint16_t *spec_cols = reinterpret_cast<uint16_t *>(m_pinit + words); // [S][cap_spec]
+  const int cap_spec = extract_spec_cap(a);
+  __shared__ int s_spec_cnt[kMaxSectors];
 
-  // ---- extract_planar (extraction.tpp:332-358), sectors in ascending order ----
-  uint16_t *out_pl = a.planar_cols + ((size_t)b * a.rows + row) * a.pr_cap;
-  int total = 0;
-  for (int s = 0; s < S; ++s) {
-    const int start = s * pps;
-    const int len = ((s == S - 1) ? cols : start + pps) - start;
-    int count = 0;
-    bool done = false;
-    for (int base = 0; base < len && !done; base += 32) {
-      const int i = base + lane;
-      const bool in = i < len;
-      const int col = in ? (int)sorted[start + i] : 0;
-      const float curv = in ? __uint_as_float(keys[col]) : FLT_MAX;
-      const bool below = in && ((double)curv < a.planar_threshold);
-      const bool cand = below && get_bit(m_used, col);
-      const bool alive = resolve_group(cand, col, np, lane);
-      const unsigned sel = __ballot_sync(0xffffffffu, alive);
-      const int rank = __popc(sel & lt_mask);
-      // visited iff the count after all earlier visits is still <= cap (:354 '>')
-      const bool accept = alive && (count + rank <= a.planar_per_sector);
-      if (accept) {
-        out_pl[total + count + rank] = (uint16_t)col;
-        clear_bits(m_used, col - (np - 1), col + (np - 1));
-      }
-      count += __popc(__ballot_sync(0xffffffffu, accept));
-      if (count > a.planar_per_sector) done = true;
-      // sorted ascending: once one in-range lane is >= threshold nothing later qualifies
-      if (__ballot_sync(0xffffffffu, below) != __ballot_sync(0xffffffffu, in)) done = true;
-      __syncwarp();
-    }
-    total += count;
-  }
-  if (lane == 0) {
-    a.planar_cnt[(size_t)b * a.rows + row] = total;
-    a.keep_cnt[(size_t)b * a.rows + row] = 0; // accumulated by the normals kernel
-  }
-
-  // ---- point candidates (extraction.tpp:72-80): untouched by planar picks and
-  // range-valid.  m_pvalid becomes the working mask of extract_point. ----
-  for (int w = lane; w < words; w += 32) m_pvalid[w] = ~(m_used[w] ^ m_valid[w]) & m_pvalid[w];
-  __syncwarp();
-
-  // ---- extract_point (extraction.tpp:360-399) ----
-  uint16_t *out_pt = a.point_cols + ((size_t)b * a.rows + row) * a.qr_cap;
-  int ptotal = 0;
-  const int pfps = a.point_per_sector;
-  for (int s = 0; s < S && pfps > 0; ++s) {
-    const int start = s * pps;
-    const int end = (s == S - 1) ? cols : start + pps;
-    // unused_points (:371-376): ascending list of still-valid columns
-    int U = 0;
-    for (int base = start; base < end; base += 32) {
-      const int c = base + lane;
-      const bool bit = c < end && get_bit(m_pvalid, c);
-      const unsigned bal = __ballot_sync(0xffffffffu, bit);
-      if (bit) ulist[U + __popc(bal & lt_mask)] = (uint16_t)c;
-      U += __popc(bal);
-    }
+  // ---- extract_planar (extraction.tpp:332-358) ----
+  for (int s = warp; s < S; s += nwarps) {
+    uint32_t *mask = m_priv + (size_t)s * words;
+    for (int w = lane; w < words; w += 32) mask[w] = m_valid[w];
     __syncwarp();
-    const int factor = 1 + U / pfps; // :379
-    // The reference visits u = offset + m * factor for offset = 0 .. factor-1 (outer) and
-    // m = 0, 1, .. (inner), leaving the inner loop once count > pfps (:394-396).  Equivalently,
-    // in that (offset, m) order: the first element of every pass is ALWAYS visited, a later
-    // element (m > 0) is visited iff the running count is still <= pfps.  A pass holds at most
-    // ceil(U / factor) <= pfps + 1 elements, so stepping pass by pass would keep 3-4 lanes of
-    // the warp busy; instead 32 consecutive elements of the whole visiting sequence (several
-    // passes) are resolved per step.  Pass `o` has n_full + 1 elements if o < rem, else n_full.
-    const int n_full = U / factor, rem = U - n_full * factor;
-    const int split = rem * (n_full + 1); // sequence index of the first element of pass `rem`
-    auto pass_of = [&](int t, int &o, int &m) {
-      if (t < split) {
-        o = t / (n_full + 1);
-        m = t - o * (n_full + 1);
+    const int n = planar_walk_sector(a, keys, sorted, mask, s, pps, S, cols, np, lane, spec_cols + (size_t)s * cap_spec);
+    if (lane == 0) s_spec_cnt[s] = n;
+  }
+  __syncthreads();
+  uint16_t *out_pl = a.planar_cols + ((size_t)b * a.rows + row) * a.pr_cap;
+  if (warp == 0) {
+    int total = 0;
+    for (int s = 0; s < S; ++s) {
+      const int n = s_spec_cnt[s];
+      const uint16_t *sc = spec_cols + (size_t)s * cap_spec;
+      bool lost = false;
+      for (int i = lane; i < n; i += 32) lost = lost || !get_bit(m_used, (int)sc[i]);
+      int count = n;
+      if (__ballot_sync(0xffffffffu, lost)) {
+        count = planar_walk_sector(a, keys, sorted, m_used, s, pps, S, cols, np, lane, out_pl + total);
       } else {
-        const int t2 = t - split, d = t2 / n_full; // n_full > 0 whenever such a t exists
-        o = rem + d;
-        m = t2 - d * n_full;
-      }
-    };
-    int count = 0;
-    int offset = factor; // first pass the strided phase has not touched when it stops
-    for (int base = 0; base < U && count <= pfps; base += 32) {
-      const int t = base + lane;
-      const bool in = t < U;
-      int o = 0, m = 0;
-      if (in) pass_of(t, o, m);
-      const int col = in ? (int)ulist[o + m * factor] : 0;
-      const bool cand = in && get_bit(m_pvalid, col);
-      bool alive = resolve_group(cand, col, np, lane);
-      unsigned sel = __ballot_sync(0xffffffffu, alive);
-      // lanes whose count-before already exceeds pfps (a suffix of the group): their m > 0
-      // candidates are not visited and must not suppress anything - resolve again without them
-      // (the outcome of the lanes before the suffix does not depend on later lanes)
-      const unsigned over_bits = __ballot_sync(0xffffffffu, count + __popc(sel & lt_mask) > pfps);
-      if (over_bits) {
-        const int first_over = __ffs(over_bits) - 1;
-        const bool dropped = cand && m > 0 && lane >= first_over;
-        if (__ballot_sync(0xffffffffu, dropped)) {
-          alive = resolve_group(cand && !dropped, col, np, lane);
-          sel = __ballot_sync(0xffffffffu, alive);
+        for (int i = lane; i < n; i += 32) {
+          const int col = sc[i];
+          out_pl[total + i] = (uint16_t)col;
+          clear_bits(m_used, col - (np - 1), col + (np - 1));
         }
       }
-      if (alive) {
-        out_pt[ptotal + count + __popc(sel & lt_mask)] = (uint16_t)col;
+      __syncwarp();
+      total += count;
+    }
+    if (lane == 0) {
+      a.planar_cnt[(size_t)b * a.rows + row] = total;
+      a.keep_cnt[(size_t)b * a.rows + row] = 0; // accumulated by the normals kernel
+    }
+    // ---- point candidates (extraction.tpp:72-80): untouched by planar picks and
+    // range-valid.  m_pvalid becomes the working mask of extract_point. ----
+    for (int w = lane; w < words; w += 32) {
+      const uint32_t v = ~(m_used[w] ^ m_valid[w]) & m_pvalid[w];
+      m_pvalid[w] = v;
+      m_pinit[w] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- extract_point (extraction.tpp:360-399) ----
+  const int pfps = a.point_per_sector;
+  uint16_t *out_pt = a.point_cols + ((size_t)b * a.rows + row) * a.qr_cap;
+  if (pfps <= 0) {
+    if (tid == 0) a.point_cnt[(size_t)b * a.rows + row] = 0;
+    return;
+  }
+  for (int s = warp; s < S; s += nwarps) {
+    uint32_t *mask = m_priv + (size_t)s * words;
+    for (int w = lane; w < words; w += 32) mask[w] = m_pinit[w];
+    __syncwarp();
+    const int n = point_walk_sector(a, mask, ulist, s, pps, S, cols, np, pfps, lane, spec_cols + (size_t)s * cap_spec);
+    if (lane == 0) s_spec_cnt[s] = n;
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  int ptotal = 0;
+  for (int s = 0; s < S; ++s) {
+    const int start = s * pps;
+    const int end = (s == S - 1) ? cols : start + pps;
+    // does the shared mask still equal the initial one on the sector's own columns?
+    bool differs = false;
+    for (int w = (start >> 5) + lane; w <= ((end - 1) >> 5); w += 32) {
+      uint32_t in = 0xffffffffu;
+      if (w == (start >> 5)) in &= 0xffffffffu << (start & 31);
+      if (w == ((end - 1) >> 5)) in &= 0xffffffffu >> (31 - ((end - 1) & 31));
+      differs = differs || (((m_pvalid[w] ^ m_pinit[w]) & in) != 0u);
+    }
+    int count;
+    if (__ballot_sync(0xffffffffu, differs)) {
+      count = point_walk_sector(a, m_pvalid, ulist, s, pps, S, cols, np, pfps, lane, out_pt + ptotal);
+    } else {
+      count = s_spec_cnt[s];
+      const uint16_t *sc = spec_cols + (size_t)s * cap_spec;
+      for (int i = lane; i < count; i += 32) {
+        const int col = sc[i];
+        out_pt[ptotal + i] = (uint16_t)col;
         clear_bits(m_pvalid, col - (np - 1), col + (np - 1));
       }
-      count += __popc(sel);
-      if (count > pfps) { // only the first element of every later pass is still visited
-        int o_last, m_last;
-        pass_of(min(base + 31, U - 1), o_last, m_last);
-        offset = o_last + 1;
-      }
-      __syncwarp();
     }
-    // Phase B: count > pfps, so every remaining pass visits only u = offset
-    for (int base = offset; base < factor; base += 32) {
-      const int o = base + lane;
-      const bool in = o < factor && o < U;
-      if (__ballot_sync(0xffffffffu, in) == 0) break;
-      const int col = in ? (int)ulist[o] : 0;
-      const bool cand = in && get_bit(m_pvalid, col);
-      const bool alive = resolve_group(cand, col, np, lane);
-      const unsigned sel = __ballot_sync(0xffffffffu, alive);
-      const int rank = __popc(sel & lt_mask);
-      if (alive) {
-        out_pt[ptotal + count + rank] = (uint16_t)col;
-        clear_bits(m_pvalid, col - (np - 1), col + (np - 1));
-      }
-      count += __popc(sel);
-      __syncwarp();
-    }
+    __syncwarp();
     ptotal += count;
   }
   if (lane == 0) a.point_cnt[(size_t)b * a.rows + row] = ptotal;
@@ -1067,22 +1171,30 @@ __global__ void __launch_bounds__(128) extract_pack_batch_kernel(const ExtractAr
 // ---------------------------------------------------------------------------
 // host-side launcher
 // ---------------------------------------------------------------------------
-size_t extract_select_smem(int cols, int cols_pad, int words) {
+size_t extract_select_smem(int cols, int cols_pad, int words, int sectors, int spec_cap) {
+  // staged row, keys, sorted + unused lists, the four row masks; then the private masks of the
+  // speculative walks ([sectors][words]), the initial point mask and the speculative pick lists
   return (size_t)cols * sizeof(float4) + (size_t)cols_pad * (sizeof(uint32_t) + 2 * sizeof(uint16_t)) +
-         (size_t)words * 4 * sizeof(uint32_t);
+         (size_t)words * 4 * sizeof(uint32_t) + (size_t)(sectors + 1) * words * sizeof(uint32_t) +
+         ((size_t)sectors * spec_cap * sizeof(uint16_t) + 15) / 16 * 16;
 }
 size_t extract_normals_smem(int cols, int words, int pr_cap) {
   return (size_t)cols * 3 * sizeof(float4) + (size_t)words * 4 * sizeof(float4) +
          (size_t)words * 2 * sizeof(uint32_t) + (size_t)pr_cap * sizeof(PickDesc);
 }
 
-cudaError_t extract_configure(int cols, int cols_pad, int words, int pr_cap) {
+cudaError_t extract_configure(const ExtractArgs &shape) {
+  const int cols = shape.cols, words = shape.words, pr_cap = shape.pr_cap;
+  // the attribute belongs to the function, not to a context: it only ever grows, so that contexts
+  // of different scan shapes can live in one process
+  static std::mutex mu;
+  static size_t select_hi = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  select_hi = std::max(select_hi, extract_select_smem(shape));
   cudaError_t e = cudaFuncSetAttribute(extract_select_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)extract_select_smem(cols, cols_pad, words));
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_hi);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(extract_select_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)extract_select_smem(cols, cols_pad, words));
+  e = cudaFuncSetAttribute(extract_select_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_hi);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(extract_normals_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)extract_normals_smem(cols, words, pr_cap));
@@ -1104,7 +1216,14 @@ void extract_batch_launch(const ExtractArgs &shape, const ExtractArgs *items_dev
   // of 128).  Launches with more rows than fit at 512 threads use 128-thread CTAs: the parallel
   // part of a row takes four times longer, but five times as many serial walks overlap it.
   const bool many_rows = a.rows * n_items >= many_rows_min;
-  const int select_threads = many_rows ? 128 : 512;
+  // many rows: one warp per sector for the speculative walks (six sectors by default) and as many
+  // rows resident as the registers allow; FORMGPU_SELECT_THREADS overrides it for tuning
+  static const int select_many = [] {
+    const char *e = std::getenv("FORMGPU_SELECT_THREADS");
+    const int v = e ? std::atoi(e) : 0;
+    return v >= 32 && v <= 512 && v % 32 == 0 ? v : 192;
+  }();
+  const int select_threads = many_rows ? select_many : 512;
   // development probe (the kernel is idempotent): how much does the step time move when this
   // kernel's work doubles?
   static const int repeat = [] {
@@ -1112,8 +1231,7 @@ void extract_batch_launch(const ExtractArgs &shape, const ExtractArgs *items_dev
     return e ? std::atoi(e) : 0;
   }();
   for (int r = 0; r <= repeat; ++r)
-    extract_select_batch_kernel<<<grid, select_threads, extract_select_smem(a.cols, a.cols_pad, a.words),
-                                  stream>>>(items_dev);
+    extract_select_batch_kernel<<<grid, select_threads, extract_select_smem(a), stream>>>(items_dev);
   prof.end(FORMGPU_KG_EXTRACT_SELECT, 1);
   prof.begin(FORMGPU_KG_EXTRACT_NORMALS);
   // many rows: one thread per pick (one CTA per row); few rows: one warp per pick, four CTAs
@@ -1132,7 +1250,7 @@ void extract_batch_launch(const ExtractArgs &shape, const ExtractArgs *items_dev
 void extract_launch(const ExtractArgs &a, int n_scans, cudaStream_t stream, Profiler &prof) {
   const dim3 grid(a.rows, n_scans);
   prof.begin(FORMGPU_KG_EXTRACT_SELECT);
-  extract_select_kernel<<<grid, 512, extract_select_smem(a.cols, a.cols_pad, a.words), stream>>>(a);
+  extract_select_kernel<<<grid, 512, extract_select_smem(a), stream>>>(a);
   prof.end(FORMGPU_KG_EXTRACT_SELECT, 1);
   prof.begin(FORMGPU_KG_EXTRACT_NORMALS);
   extract_normals_kernel<<<dim3(a.rows * kNormalSplit, n_scans), 256,

@@ -44,8 +44,19 @@ struct ExtractArgs {
   unsigned pad_;
 };
 
-cudaError_t extract_configure(int cols, int cols_pad, int words, int pr_cap);
-size_t extract_select_smem(int cols, int cols_pad, int words);
+constexpr int kExtractMaxSectors = 64; // sectors per row the select kernel validates in order
+/// Entries of a sector's speculative pick list in the select kernel (planar or point picks).
+/// Picks of one sector are pairwise >= np columns apart (suppression +-(np-1)); the last sector is
+/// the longest (it takes the remainder columns).
+__host__ __device__ inline int extract_spec_cap(const ExtractArgs &a) {
+  const int longest = a.cols - (a.num_sectors - 1) * a.pps;
+  return (longest + a.np - 1) / a.np + 1;
+}
+cudaError_t extract_configure(const ExtractArgs &shape);
+size_t extract_select_smem(int cols, int cols_pad, int words, int sectors, int spec_cap);
+inline size_t extract_select_smem(const ExtractArgs &a) {
+  return extract_select_smem(a.cols, a.cols_pad, a.words, a.num_sectors, extract_spec_cap(a));
+}
 size_t extract_normals_smem(int cols, int words, int pr_cap);
 /// Launches the three stage-1 kernels.
 void extract_launch(const ExtractArgs &a, int n_scans, cudaStream_t stream, Profiler &prof);

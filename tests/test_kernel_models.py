@@ -391,3 +391,102 @@ def test_face_pruned_search_equals_brute_force_r5(kind):
         scanned.append(n)
     if kind == "surface":  # queries near the surfaces (the second group) touch few of the 26 neighbours
         assert np.mean(scanned[300:600]) < 4
+
+
+# --------------------------------------------------------------------------- sector-parallel walks
+# extract.cu runs the greedy walks of a row's sectors in parallel on private copies of the mask
+# and validates them in sector order (the reference walks the sectors one after the other on ONE
+# mask, extraction.tpp:44-68 / :332-399, so a pick near the end of sector s suppresses the first
+# np-1 columns of sector s+1).  These models pin the two validation rules the kernel rests on.
+def _planar_sector(order, curv, thr, mask, np_, cap):
+    """extract_planar (extraction.tpp:332-358) on one sector: `order` = its columns sorted by
+    (curvature, column); returns the picks, mutates mask."""
+    out = []
+    for c in order:
+        if mask[c] and curv[c] < thr:
+            out.append(c)
+            for n in range(np_):
+                mask[c + n] = False
+                mask[c - n] = False
+        if len(out) > cap:
+            break
+    return out
+
+
+def _point_sector(start, end, mask, np_, pfps):
+    ulist = [c for c in range(start, end) if mask[c]]
+    return reference_point_walk(ulist, mask, np_, pfps)
+
+
+def _row_case(rng, cols, S, np_, density):
+    valid = np.zeros(cols + 2 * np_, dtype=bool)  # columns 0..cols-1 live at [np_, np_ + cols)
+    valid[np_: np_ + cols] = rng.random(cols) < density
+    valid[np_: 2 * np_] = False
+    valid[cols: np_ + cols] = False
+    pps = cols // S
+    bounds = [(np_ + s * pps, np_ + (cols if s == S - 1 else (s + 1) * pps)) for s in range(S)]
+    curv = rng.random(cols + 2 * np_)
+    return valid, bounds, curv
+
+
+@pytest.mark.parametrize("np_,cap,density", [(5, 50, 0.9), (5, 3, 0.9), (3, 50, 0.5), (2, 8, 1.0), (5, 50, 0.2)])
+def test_speculative_sector_parallel_planar_walk(np_, cap, density):
+    rng = np.random.default_rng(zlib.crc32(f"pl{np_}{cap}{density}".encode()))
+    redone = 0
+    for _ in range(300):
+        cols, S = int(rng.integers(40, 200)), int(rng.integers(1, 7))
+        valid, bounds, curv = _row_case(rng, cols, S, np_, density)
+        thr = float(rng.choice([0.3, 0.8, 2.0]))
+        orders = [sorted(range(a, b), key=lambda c: (curv[c], c)) for a, b in bounds]
+        # reference: one mask, sectors in order
+        m_ref = valid.copy()
+        ref = [_planar_sector(orders[s], curv, thr, m_ref, np_, cap) for s in range(S)]
+        # kernel: every sector on a private copy of the INITIAL mask ...
+        spec = [_planar_sector(orders[s], curv, thr, valid.copy(), np_, cap) for s in range(S)]
+        # ... then, in sector order on the shared mask: a speculative result stands iff none of its
+        # picks has been suppressed by the sectors before it; otherwise the sector is walked again
+        m = valid.copy()
+        got = []
+        for s in range(S):
+            if all(m[c] for c in spec[s]):
+                got.append(spec[s])
+                for c in spec[s]:
+                    for n in range(np_):
+                        m[c + n] = False
+                        m[c - n] = False
+            else:
+                redone += 1
+                got.append(_planar_sector(orders[s], curv, thr, m, np_, cap))
+        assert got == ref
+        assert np.array_equal(m, m_ref)
+    assert redone > 0 or density < 0.5  # the redo path is exercised
+
+
+@pytest.mark.parametrize("np_,pfps,density", [(5, 10, 0.9), (5, 3, 0.6), (3, 20, 0.5), (2, 4, 1.0), (5, 1, 0.3), (4, 0, 0.9)])
+def test_speculative_sector_parallel_point_walk(np_, pfps, density):
+    rng = np.random.default_rng(zlib.crc32(f"pt{np_}{pfps}{density}".encode()))
+    redone = 0
+    for _ in range(300):
+        cols, S = int(rng.integers(40, 200)), int(rng.integers(1, 7))
+        valid, bounds, _ = _row_case(rng, cols, S, np_, density)
+        m_ref = valid.copy()
+        ref = [_point_sector(a, b, m_ref, np_, pfps) for a, b in bounds]
+        spec = [_point_sector(a, b, valid.copy(), np_, pfps) for a, b in bounds]
+        # a speculative result stands iff the shared mask still equals the initial one on the
+        # sector's own columns (the list of unused points, and with it the pass structure, is
+        # built from exactly those bits)
+        m = valid.copy()
+        got = []
+        for s, (a, b) in enumerate(bounds):
+            if np.array_equal(m[a:b], valid[a:b]):
+                got.append(spec[s])
+                for c in spec[s]:
+                    for n in range(np_):
+                        m[c + n] = False
+                        m[c - n] = False
+            else:
+                redone += 1
+                got.append(_point_sector(a, b, m, np_, pfps))
+        assert got == ref
+        assert np.array_equal(m, m_ref)
+    assert redone > 0 or pfps == 0
