@@ -1,4 +1,4 @@
-"""Kernel variants that only batched submits use.  Many-row extraction kernels (128-thread select
+"""Kernel variants that only batched submits use.  Many-row extraction kernels (192-thread select
 CTAs, thread-per-pick normals; kernels.hpp: kManyRowsMin, FORMGPU_MANY_ROWS_MIN) and the lanes
 per query of the batched association kernel (kAssocLanes, FORMGPU_ASSOC_LANES): keypoints -
 normals included - are compared bit for bit with the CPU oracle on the synthetic sensor shapes,
