@@ -313,6 +313,13 @@ public:
   size_t current_scan() const noexcept { return m_scan; }
   const SmootherStats &stats() const noexcept { return m_stats; }
   const std::map<uint64_t, PairCounts> &pair_counts() const noexcept { return m_counts; }
+  /// The live marginal factors (the LinearContainerFactors of m_other_factors).
+  std::vector<std::shared_ptr<const LinearContainer>> marginals() const {
+    std::vector<std::shared_ptr<const LinearContainer>> out;
+    for (const auto &m : m_marginals)
+      if (m) out.push_back(m);
+    return out;
+  }
 
   /// constraints.cpp:319-336
   size_t num_recent_connections(const ScanIndex &scan, const ScanIndex &oldest) const noexcept {
