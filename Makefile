@@ -1,7 +1,9 @@
 # Builds the product libraries in-tree (they travel to the GPU box with the
 # snapshot):
 #   form_b200/lib/libformgpu.so   CUDA hot path + C-ABI (include/formgpu.h)
-#   form_b200/lib/libformhost.so  C++ host facade (form::Estimator, synthetic scans)
+#   form_b200/lib/libformhost.so  C++ host facade (form::Estimator, batch replay)
+#   form_b200/lib/libformsynth.so synthetic scans + SE(3) hooks only: no CUDA dependency, so that the
+#                                 CPU baseline / oracle tests never map the product's CUDA library
 # and, for tests / bench baselines only, oracle/_build/liboracle.so and oracle/_ref/libformref.so.
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       ?= g++
@@ -22,7 +24,7 @@ HOST_HDRS := $(wildcard form_b200/host/form/*.hpp) include/formgpu.h
 PYTHON    ?= python3
 PYEXT     := python/form/_core$(shell $(PYTHON) -c "import sysconfig; print(sysconfig.get_config_var('EXT_SUFFIX'))")
 
-all: $(LIBDIR)/libformgpu.so $(LIBDIR)/libformhost.so $(PYEXT) oracle
+all: $(LIBDIR)/libformgpu.so $(LIBDIR)/libformhost.so $(LIBDIR)/libformsynth.so $(PYEXT) oracle
 
 # form._core: the reference's Python surface (python/bindings.cpp) with pybind11
 $(PYEXT): python/bindings.cpp $(HOST_HDRS) $(LIBDIR)/libformgpu.so
@@ -51,6 +53,10 @@ $(OBJDIR)/host_%.o: form_b200/host/src/%.cpp $(HOST_HDRS)
 
 $(LIBDIR)/libformhost.so: $(HOST_OBJS) $(LIBDIR)/libformgpu.so
 	$(CXX) -shared -pthread -o $@ $(HOST_OBJS) -L$(LIBDIR) -lformgpu -Wl,-rpath,'$$ORIGIN'
+
+$(LIBDIR)/libformsynth.so: $(OBJDIR)/host_synth_capi.o
+	@mkdir -p $(LIBDIR)
+	$(CXX) -shared -pthread -Wl,--no-undefined -Wl,-Bsymbolic -o $@ $<
 
 # oracle/_ref: FORM's own stage-1/2 sources compiled from /root/reference against API
 # stand-ins (test infrastructure; skipped where the reference tree is absent)

@@ -919,6 +919,21 @@ def cpu_baseline_multi(args, rows, cols, W, S, host_np):
             "reference_code_stage1": reference_code_stage1(rows, cols, [host_np[0][k] for k in range(W, min(S, W + 4))])}
 
 
+def repo_libs_mapped():
+    """Shared objects of this repository in the process's address space (/proc/self/maps)."""
+    root = os.path.dirname(os.path.abspath(__file__))
+    libs = set()
+    try:
+        with open("/proc/self/maps") as f:
+            for line in f:
+                path = line.split(None, 5)[-1].strip()
+                if path.endswith(".so") and os.path.realpath(path).startswith(os.path.realpath(root) + os.sep):
+                    libs.add(os.path.relpath(os.path.realpath(path), os.path.realpath(root)))
+    except OSError:
+        pass
+    return sorted(libs)
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU path (oracle port: the reference cannot be built here) on the
     same multi-sequence job: one single-threaded sequence replay per host core."""
@@ -956,6 +971,9 @@ def run_reference(args, rank, world):
         "cpu_baseline": cpu,
         "e2e": {"value": round(value, 4), "unit": "scans/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
+        # the repository's shared objects this process has mapped: the oracle and the scan
+        # generator, none of the product's (form_b200/lib/libformgpu.so, libformhost.so)
+        "native_libs_mapped": repo_libs_mapped(),
     }
 
 
@@ -999,7 +1017,8 @@ def main():
 
     import __graft_entry__ as g
 
-    g.build(only_if_missing=True)
+    # the reference arm maps the oracle and the scan generator only, never the product's libraries
+    g.build(only_if_missing=True, load=args.impl != "reference")
     if args.impl == "reference":
         res = run_reference(args, rank, world)
     elif args.mode == "sharded":

@@ -217,7 +217,8 @@ def estimator_symbols(prefix: str) -> dict:
     }
 
 
-FORMHOST_SYMBOLS = {
+# host/src/synth_capi.cpp: exported by libformsynth.so (no CUDA dependency) and by libformhost.so
+FORMSYNTH_SYMBOLS = {
     "formhost_synth_shape": (_sz, [_i, C.POINTER(_i), C.POINTER(_i)]),
     "formhost_synth_scan": (_i, [_i, _u64, _u64, _vp, _i]),
     "formhost_synth_gt_pose": (None, [_u64, _u64, _vp]),
@@ -230,6 +231,10 @@ FORMHOST_SYMBOLS = {
     "formhost_pose_inverse": (None, [_vp, _vp]),
     "formhost_pose_rzryrx": (None, [_d, _d, _d, _vp, _vp]),
     "formhost_pose_normalized": (None, [_vp, _vp]),
+}
+
+FORMHOST_SYMBOLS = {
+    **FORMSYNTH_SYMBOLS,
     "formhost_default_est_params": (None, [_pest]),
     "formhost_last_error": (C.c_char_p, []),
     "formhost_est_error": (C.c_char_p, [_vp]),
@@ -261,13 +266,13 @@ REPLAY_STAT_NAMES = (
 )
 
 
-def _load(path: str, symbols: dict) -> C.CDLL:
+def _load(path: str, symbols: dict, mode: int = C.RTLD_GLOBAL) -> C.CDLL:
     if not os.path.exists(path):
         raise ImportError(
             f"{path} is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(or `make`) at the repository root"
         )
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path, mode=mode)
     for name, (res, args) in symbols.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
@@ -277,6 +282,7 @@ def _load(path: str, symbols: dict) -> C.CDLL:
 
 _gpu = None
 _host = None
+_synth = None
 
 
 def gpu_lib() -> C.CDLL:
@@ -285,6 +291,19 @@ def gpu_lib() -> C.CDLL:
     if _gpu is None:
         _gpu = _load(os.path.join(LIB_DIR, "libformgpu.so"), FORMGPU_SYMBOLS)
     return _gpu
+
+
+def synth_lib() -> C.CDLL:
+    """libformsynth.so: the seeded scan generators and the SE(3) hooks of the host side, built
+    without any CUDA dependency - what the CPU baseline and the oracle tests load, so that
+    they never map the product's CUDA library."""
+    global _synth
+    if _synth is None:
+        path = os.path.join(LIB_DIR, "libformsynth.so")
+        if not os.path.exists(path) and os.path.exists(os.path.join(LIB_DIR, "libformhost.so")):
+            return host_lib()  # a tree built before libformsynth existed: same symbols, same code
+        _synth = _load(path, FORMSYNTH_SYMBOLS, C.DEFAULT_MODE)
+    return _synth
 
 
 def host_lib() -> C.CDLL:

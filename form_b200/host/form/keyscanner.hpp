@@ -59,7 +59,9 @@ public:
     for (auto &kf : m_keyscans) {
       if (connections(kf.idx) > 0) kf.unused_count = 0;
       else ++kf.unused_count;
-      if (static_cast<int64_t>(kf.unused_count) > m_params.max_steps_unused_keyscan) {
+      // size_t > int64_t compares as unsigned in the reference (keyscanner.cpp:66): a negative
+      // max_steps_unused_keyscan means "never"
+      if (kf.unused_count > static_cast<size_t>(m_params.max_steps_unused_keyscan)) {
         marg.push_back(kf.idx);
         finished.push_back(kf.idx);
       }

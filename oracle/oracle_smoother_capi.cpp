@@ -181,3 +181,49 @@ void oracle_smoother_marginal_quadratic(void *h, size_t idx, double *G, double *
 }
 
 } // extern "C"
+
+// ---- form::KeyScanner (host/form/keyscanner.hpp; /root/reference/form/mapping/keyscanner.cpp:29-91)
+// behind a C callback for the connection counts, for tests/test_keyscanner_model.py ----
+#include "form/keyscanner.hpp"
+
+extern "C" {
+
+typedef size_t (*oracle_connections_fn)(uint64_t scan, void *user);
+
+void *oracle_keyscanner_create(int64_t max_num_keyscans, int64_t max_steps_unused_keyscan,
+                               size_t max_num_recent_scans, double keyscan_match_ratio) {
+  KeyScanner::Params p;
+  p.max_num_keyscans = max_num_keyscans;
+  p.max_steps_unused_keyscan = max_steps_unused_keyscan;
+  p.max_num_recent_scans = max_num_recent_scans;
+  p.keyscan_match_ratio = keyscan_match_ratio;
+  return new KeyScanner(p);
+}
+void oracle_keyscanner_destroy(void *h) { delete static_cast<KeyScanner *>(h); }
+
+/// KeyScanner::step; returns the number of scans to marginalise (written to marg, in order)
+size_t oracle_keyscanner_step(void *h, uint64_t idx, size_t size, oracle_connections_fn fn, void *user,
+                              uint64_t *marg, size_t cap) {
+  const std::vector<ScanIndex> out =
+      static_cast<KeyScanner *>(h)->step(idx, size, [&](ScanIndex s) { return fn(s, user); });
+  for (size_t k = 0; k < out.size() && k < cap; ++k) marg[k] = out[k];
+  return out.size();
+}
+
+/// key scans then recent scans, oldest first; returns their numbers through n_key / n_recent
+void oracle_keyscanner_state(void *h, uint64_t *key, size_t *n_key, uint64_t *recent, size_t *n_recent, size_t cap) {
+  const KeyScanner &ks = *static_cast<KeyScanner *>(h);
+  size_t k = 0;
+  for (const Scan &s : ks.keyscans())
+    if (k < cap) key[k++] = s.idx;
+  *n_key = ks.keyscans().size();
+  k = 0;
+  for (const Scan &s : ks.recent_scans())
+    if (k < cap) recent[k++] = s.idx;
+  *n_recent = ks.recent_scans().size();
+}
+size_t oracle_keyscanner_oldest_rf(void *h) { return static_cast<KeyScanner *>(h)->oldest_rf(); }
+
+} // extern "C"
+
+extern "C" size_t oracle_keyscanner_size(void *h) { return static_cast<KeyScanner *>(h)->size(); }

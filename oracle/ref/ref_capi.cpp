@@ -277,3 +277,34 @@ int formref_linearize_raw(const double *p_i, const double *n_i, const double *p_
 }
 
 } // extern "C"
+
+// ---- FORM's own KeyScanner (form/mapping/keyscanner.{hpp,cpp}, no external dependency):
+// pins form_b200/host/form/keyscanner.hpp in tests/test_reference_pins.py ----
+#include "form/mapping/keyscanner.hpp"
+
+extern "C" {
+
+typedef size_t (*ref_connections_fn)(uint64_t scan, void *user);
+
+void *ref_keyscanner_create(int64_t max_num_keyscans, int64_t max_steps_unused_keyscan,
+                            size_t max_num_recent_scans, double keyscan_match_ratio) {
+  form::KeyScanner::Params p;
+  p.max_num_keyscans = max_num_keyscans;
+  p.max_steps_unused_keyscan = max_steps_unused_keyscan;
+  p.max_num_recent_scans = max_num_recent_scans;
+  p.keyscan_match_ratio = keyscan_match_ratio;
+  return new form::KeyScanner(p);
+}
+void ref_keyscanner_destroy(void *h) { delete static_cast<form::KeyScanner *>(h); }
+
+/// KeyScanner::step (keyscanner.cpp:29-91); returns the number of scans to marginalise
+size_t ref_keyscanner_step(void *h, uint64_t idx, size_t size, ref_connections_fn fn, void *user, uint64_t *marg,
+                           size_t cap) {
+  const std::vector<form::ScanIndex> out =
+      static_cast<form::KeyScanner *>(h)->step(idx, size, [=](form::ScanIndex s) { return fn(s, user); });
+  for (size_t k = 0; k < out.size() && k < cap; ++k) marg[k] = out[k];
+  return out.size();
+}
+size_t ref_keyscanner_size(void *h) { return static_cast<form::KeyScanner *>(h)->size(); }
+
+} // extern "C"

@@ -4,7 +4,7 @@ from scipy.linalg import expm, logm
 
 from form_b200 import _capi
 
-L = _capi.host_lib
+L = _capi.synth_lib
 
 
 def P(R, t):

@@ -15,21 +15,21 @@ from helpers import perturbed, scan_poses, unpack91
 def pose_rzryrx(rx, ry, rz, t):
     out = np.zeros(1, dtype=_capi.POSE)
     tt = np.asarray(t, dtype=np.float64)
-    _capi.host_lib().formhost_pose_rzryrx(rx, ry, rz, _capi.ptr(tt), _capi.ptr(out))
+    _capi.synth_lib().formhost_pose_rzryrx(rx, ry, rz, _capi.ptr(tt), _capi.ptr(out))
     return out[0]
 
 
 def expmap(xi):
     out = np.zeros(1, dtype=_capi.POSE)
     x = np.asarray(xi, dtype=np.float64)
-    _capi.host_lib().formhost_pose_expmap(_capi.ptr(x), _capi.ptr(out))
+    _capi.synth_lib().formhost_pose_expmap(_capi.ptr(x), _capi.ptr(out))
     return out[0]
 
 
 def compose(a, b):
     out = np.zeros(1, dtype=_capi.POSE)
     aa, bb = np.array([a], dtype=_capi.POSE), np.array([b], dtype=_capi.POSE)
-    _capi.host_lib().formhost_pose_compose(_capi.ptr(aa), _capi.ptr(bb), _capi.ptr(out))
+    _capi.synth_lib().formhost_pose_compose(_capi.ptr(aa), _capi.ptr(bb), _capi.ptr(out))
     return out[0]
 
 
