@@ -5,12 +5,17 @@
 //     through the model's virtual WhitenInPlace / whitenInPlace;
 //   * NoiseModelFactor2::unwhitenedError(x, H) = evaluateError(x[key1], x[key2], &H[0], &H[1]);
 //   * JacobianFactor(terms, b) keeps the blocks; HessianFactor(JacobianFactor) is the
-//     augmented information matrix [A b]^T [A b], variables in term order.
+//     augmented information matrix [A b]^T [A b], variables in term order;
+//   * NonlinearFactor as the common base (keys, error = 0.5 |whitened residual|^2, linearize),
+//     noiseModel::Isotropic, NoiseModelFactor1's default linearisation - what
+//     form/optimization/constraints.cpp needs on top (the smoother stand-ins are in
+//     gtsam/shim_smoother.h).
 #pragma once
 
 #include <gtsam/base/Vector.h>
 #include <gtsam/nonlinear/Values.h>
 
+#include <cmath>
 #include <iostream>
 #include <memory>
 #include <string>
@@ -60,13 +65,36 @@ public:
     whitenInPlace(b);
   }
 };
+/// noiseModel::Isotropic::Sigma(dim, sigma): whitening = division by sigma
+class Isotropic : public Gaussian {
+public:
+  typedef std::shared_ptr<Isotropic> shared_ptr;
+  static shared_ptr Sigma(size_t dim, double sigma) { return shared_ptr(new Isotropic(dim, sigma)); }
+  void print(const std::string &s = "") const override { std::cout << s << "Isotropic(" << m_sigma << ")\n"; }
+  bool equals(const Base &expected, double tol = 1e-9) const override {
+    const Isotropic *p = dynamic_cast<const Isotropic *>(&expected);
+    return p && std::fabs(p->m_sigma - m_sigma) <= tol && p->dim() == dim();
+  }
+  Vector whiten(const Vector &v) const override { return v * m_inv; }
+  Vector unwhiten(const Vector &v) const override { return v * m_sigma; }
+  Matrix Whiten(const Matrix &H) const override { return H * m_inv; }
+  void WhitenInPlace(Matrix &H) const override { H *= m_inv; }
+  void whitenInPlace(Vector &v) const override { v *= m_inv; }
+  void WhitenInPlace(Eigen::Block<Matrix> H) const override { H *= m_inv; }
+
+private:
+  Isotropic(size_t dim, double sigma) : Gaussian(dim), m_sigma(sigma), m_inv(1.0 / sigma) {}
+  double m_sigma, m_inv;
+};
 } // namespace noiseModel
 using SharedNoiseModel = noiseModel::Base::shared_ptr;
+using KeyVector = std::vector<Key>;
 
 class GaussianFactor {
 public:
   virtual ~GaussianFactor() = default;
 };
+class GaussianFactorGraph;
 class JacobianFactor : public GaussianFactor {
 public:
   JacobianFactor(const std::vector<std::pair<Key, Matrix>> &terms, const Vector &b) : terms(terms), b(b) {}
@@ -75,6 +103,9 @@ public:
 };
 class HessianFactor : public GaussianFactor {
 public:
+  HessianFactor() = default;
+  /// all factors of a linear graph combined into one dense factor (shim_smoother.h)
+  explicit HessianFactor(const GaussianFactorGraph &graph);
   explicit HessianFactor(const JacobianFactor &jf) {
     size_t n = 0;
     for (const auto &t : jf.terms) {
@@ -96,14 +127,35 @@ public:
   Matrix info; // (n + 1) x (n + 1) augmented information matrix
 };
 
-template <typename V1, typename V2> class NoiseModelFactor2 {
+/// gtsam::NonlinearFactor: what a NonlinearFactorGraph holds
+class NonlinearFactor {
+public:
+  typedef std::shared_ptr<NonlinearFactor> shared_ptr;
+  virtual ~NonlinearFactor() = default;
+  virtual const KeyVector &keys() const = 0;
+  virtual double error(const Values &x) const = 0;
+  virtual std::shared_ptr<GaussianFactor> linearize(const Values &x) const = 0;
+};
+
+namespace shim {
+/// 0.5 * |whiten(e)|^2 (NoiseModelFactor::error)
+inline double half_whitened_norm(const SharedNoiseModel &model, Vector e) {
+  static_cast<const noiseModel::Gaussian *>(model.get())->whitenInPlace(e);
+  double s = 0.0;
+  for (size_t r = 0; r < e.size(); ++r) s += e(r) * e(r);
+  return 0.5 * s;
+}
+} // namespace shim
+
+template <typename V1, typename V2> class NoiseModelFactor2 : public NonlinearFactor {
 public:
   NoiseModelFactor2(const SharedNoiseModel &noiseModel, Key i, Key j) : noiseModel_(noiseModel), keys_{i, j} {}
-  virtual ~NoiseModelFactor2() = default;
   virtual Vector evaluateError(const V1 &, const V2 &, Matrix *H1 = nullptr, Matrix *H2 = nullptr) const = 0;
-  virtual std::shared_ptr<GaussianFactor> linearize(const Values &x) const = 0;
   size_t size() const { return 2; }
-  const std::vector<Key> &keys() const { return keys_; }
+  const KeyVector &keys() const override { return keys_; }
+  double error(const Values &x) const override {
+    return shim::half_whitened_norm(noiseModel_, evaluateError(x.template at<V1>(keys_[0]), x.template at<V2>(keys_[1])));
+  }
   const SharedNoiseModel &noiseModel() const { return noiseModel_; }
   Vector unwhitenedError(const Values &x, std::vector<Matrix> &H) const {
     return evaluateError(x.at<V1>(keys_[0]), x.at<V2>(keys_[1]), &H[0], &H[1]);
@@ -121,14 +173,28 @@ protected:
   std::vector<Key> keys_;
 };
 
-template <typename V1> class NoiseModelFactor1 {
+template <typename V1> class NoiseModelFactor1 : public NonlinearFactor {
 public:
   NoiseModelFactor1(const SharedNoiseModel &noiseModel, Key i) : noiseModel_(noiseModel), keys_{i} {}
-  virtual ~NoiseModelFactor1() = default;
+  virtual Vector evaluateError(const V1 &, Matrix *H = nullptr) const = 0;
+  const KeyVector &keys() const override { return keys_; }
+  double error(const Values &x) const override {
+    return shim::half_whitened_norm(noiseModel_, evaluateError(x.template at<V1>(keys_[0])));
+  }
+  /// NoiseModelFactor::linearize: whitened Jacobian and rhs b = -error
+  std::shared_ptr<GaussianFactor> linearize(const Values &x) const override {
+    std::vector<Matrix> A(1);
+    Vector b = -evaluateError(x.template at<V1>(keys_[0]), &A[0]);
+    static_cast<const noiseModel::Gaussian *>(noiseModel_.get())->WhitenSystem(A, b);
+    std::vector<std::pair<Key, Matrix>> terms(1);
+    terms[0].first = keys_[0];
+    terms[0].second.swap(A[0]);
+    return std::make_shared<HessianFactor>(JacobianFactor(terms, b));
+  }
 
 protected:
   SharedNoiseModel noiseModel_;
-  std::vector<Key> keys_;
+  KeyVector keys_;
 };
 
 } // namespace gtsam
