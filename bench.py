@@ -890,6 +890,71 @@ def reference_code_stage1(rows, cols, scans):
                     "a slower baseline than the reference's code, not a baseline itself"}
 
 
+def reference_code_pipeline(rows, cols, scans):
+    """Extra CPU row (labelled, not the baseline): FORM's OWN Estimator::register_scan - form.cpp,
+    constraints.cpp, extraction / map / matcher / factor / key-scanner sources compiled unmodified into
+    oracle/_ref/libformref.so over the stand-ins of oracle/shim (restated Eigen arithmetic, serial TBB,
+    GTSAM's optimiser restated) - next to the host logic over the restatement (reference LM schedule) on
+    the same scans, one thread each, with the largest pose difference between the two.  None when the
+    library is absent."""
+    import ctypes as C
+
+    lib_path = os.path.join(ROOT, "oracle", "_ref", "libformref.so")
+    if not os.path.exists(lib_path):
+        return None
+    import oracle_lib
+    from form_b200 import _capi
+
+    lib = C.CDLL(lib_path)
+    if not hasattr(lib, "formref_est_create"):
+        return None
+    psz = C.POINTER(C.c_size_t)
+    lib.formref_est_create.restype = C.c_void_p
+    lib.formref_est_create.argtypes = [C.POINTER(_capi.Params), C.c_double, C.c_double, C.c_int, C.c_int, C.c_int64,
+                                       C.c_size_t, C.c_int64]
+    lib.formref_est_destroy.argtypes = [C.c_void_p]
+    lib.formref_est_register_scan.restype = C.c_int
+    lib.formref_est_register_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, psz,
+                                              C.c_void_p, C.c_size_t, psz]
+    lib.formref_est_pose.argtypes = [C.c_void_p, C.c_void_p]
+    p = _capi.default_est_params(rows, cols, num_threads=1, gtsam_lm_schedule=1)
+    n = rows * cols
+    h = lib.formref_est_create(C.byref(p.hot), p.new_pose_threshold, p.keyscan_match_ratio, p.max_num_rematches,
+                               p.disable_smoothing, p.max_num_keyscans, p.max_num_recent_scans,
+                               p.max_steps_unused_keyscan)
+    ours = oracle_lib.OracleEstimator(p)
+    pl, pt = np.zeros(n, dtype=_capi.PLANAR_FEAT), np.zeros(n, dtype=_capi.POINT_FEAT)
+    a, b = C.c_size_t(), C.c_size_t()
+    t_ref = t_port = worst = 0.0
+    same_keypoints = True
+    for scan in scans:
+        t0 = time.perf_counter()
+        rc = lib.formref_est_register_scan(h, _capi.ptr(scan), n, _capi.ptr(pl), n, C.byref(a), _capi.ptr(pt), n,
+                                           C.byref(b))
+        t_ref += time.perf_counter() - t0
+        if rc != 0:
+            lib.formref_est_destroy(h)
+            return None
+        t0 = time.perf_counter()
+        kp, kq = ours.register_scan(scan)
+        t_port += time.perf_counter() - t0
+        same_keypoints = same_keypoints and kp.tobytes() == pl[: a.value].tobytes() and kq.tobytes() == pt[: b.value].tobytes()
+        pr = np.zeros(1, dtype=_capi.POSE)
+        lib.formref_est_pose(h, _capi.ptr(pr))
+        po = ours.pose()
+        worst = max(worst, float(np.linalg.norm(po["t"] - pr[0]["t"])), float(np.abs(po["R"] - pr[0]["R"]).max()))
+    lib.formref_est_destroy(h)
+    ours.close()
+    return {"form_register_scan_ms_per_scan": round(1e3 * t_ref / len(scans), 2),
+            "restatement_register_scan_ms_per_scan": round(1e3 * t_port / len(scans), 2),
+            "scans": len(scans), "threads": 1, "keypoints_identical": bool(same_keypoints),
+            "max_pose_difference": worst,
+            "what": "the whole pipeline, smoother included: FORM's own Estimator::register_scan (oracle/_ref: form.cpp "
+                    "and constraints.cpp compiled from /root/reference over stand-ins for Eigen / TBB / GTSAM) next to "
+                    "this repository's host logic over the restatement, first scans of one sequence - a live check "
+                    "that the two agree and that the restatement is not the slower CPU code, not a baseline itself"}
+
+
 def cpu_baseline_multi(args, rows, cols, W, S, host_np):
     cores = host_cores()
     last = min(S, W + max(1, args.cpu_sample))
@@ -916,7 +981,8 @@ def cpu_baseline_multi(args, rows, cols, W, S, host_np):
             "single_sequence_reference_threading": {
                 "value": round(single, 4), "unit": "scans/s", "cores": cores,
                 "what": "ONE sequence, worker threads over keypoints where the reference uses TBB"},
-            "reference_code_stage1": reference_code_stage1(rows, cols, [host_np[0][k] for k in range(W, min(S, W + 4))])}
+            "reference_code_stage1": reference_code_stage1(rows, cols, [host_np[0][k] for k in range(W, min(S, W + 4))]),
+            "reference_code_pipeline": reference_code_pipeline(rows, cols, [host_np[0][k] for k in range(min(S, 6))])}
 
 
 def repo_libs_mapped():
@@ -973,6 +1039,8 @@ def run_reference(args, rank, world):
                 "d2h_bytes_per_step": 0},
         # the repository's shared objects this process has mapped: the oracle and the scan
         # generator, none of the product's (form_b200/lib/libformgpu.so, libformhost.so)
+        "reference_code_pipeline": reference_code_pipeline(
+            rows, cols, [synth.scan(args.sensor, sequence_id(0, 0), k, 1) for k in range(6)]),
         "native_libs_mapped": repo_libs_mapped(),
     }
 
