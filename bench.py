@@ -955,6 +955,14 @@ def reference_code_pipeline(rows, cols, scans):
                     "that the two agree and that the restatement is not the slower CPU code, not a baseline itself"}
 
 
+def optional_row(fn, *a):
+    """The labelled extra rows must never take the bench line down with them."""
+    try:
+        return fn(*a)
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def cpu_baseline_multi(args, rows, cols, W, S, host_np):
     cores = host_cores()
     last = min(S, W + max(1, args.cpu_sample))
@@ -981,8 +989,8 @@ def cpu_baseline_multi(args, rows, cols, W, S, host_np):
             "single_sequence_reference_threading": {
                 "value": round(single, 4), "unit": "scans/s", "cores": cores,
                 "what": "ONE sequence, worker threads over keypoints where the reference uses TBB"},
-            "reference_code_stage1": reference_code_stage1(rows, cols, [host_np[0][k] for k in range(W, min(S, W + 4))]),
-            "reference_code_pipeline": reference_code_pipeline(rows, cols, [host_np[0][k] for k in range(min(S, 6))])}
+            "reference_code_stage1": optional_row(reference_code_stage1, rows, cols, [host_np[0][k] for k in range(W, min(S, W + 4))]),
+            "reference_code_pipeline": optional_row(reference_code_pipeline, rows, cols, [host_np[0][k] for k in range(min(S, 6))])}
 
 
 def repo_libs_mapped():
@@ -1039,8 +1047,8 @@ def run_reference(args, rank, world):
                 "d2h_bytes_per_step": 0},
         # the repository's shared objects this process has mapped: the oracle and the scan
         # generator, none of the product's (form_b200/lib/libformgpu.so, libformhost.so)
-        "reference_code_pipeline": reference_code_pipeline(
-            rows, cols, [synth.scan(args.sensor, sequence_id(0, 0), k, 1) for k in range(6)]),
+        "reference_code_pipeline": optional_row(
+            reference_code_pipeline, rows, cols, [synth.scan(args.sensor, sequence_id(0, 0), k, 1) for k in range(6)]),
         "native_libs_mapped": repo_libs_mapped(),
     }
 

@@ -21,6 +21,7 @@ def test_reference_arm_line_and_mapped_libraries():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     rp = line["reference_code_pipeline"]  # FORM's own register_scan next to the host logic over the restatement
     if rp is not None:                    # (None only where oracle/_ref is not built)
+        assert "unavailable" not in rp, rp
         assert rp["keypoints_identical"] is True and rp["max_pose_difference"] < 1e-9
     mapped = line["native_libs_mapped"]
     assert any(p.endswith("liboracle.so") for p in mapped)
