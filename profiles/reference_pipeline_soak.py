@@ -1,0 +1,39 @@
+"""Soak of the pipeline pin (tests/test_reference_pipeline.py) beyond what the CPU suite has time
+for: FORM's OWN Estimator::register_scan (oracle/_ref) next to this repository's host logic over
+the oracle on longer sequences, more seeds and corner-case key-scan parameters.  CPU only; needs
+oracle/_ref (i.e. the container that has /root/reference).  Log of the round: profiles/r05/reference_pipeline_soak.txt
+
+    python profiles/reference_pipeline_soak.py
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import test_reference_pipeline as t  # noqa: E402
+
+CASES = [
+    ("os1-64", 200, dict(seq=0, gtsam_lm_schedule=1)),  # BASELINE configs[0]: 200 scans
+    ("vlp-16", 120, dict(seq=1)),
+    ("vlp-16", 120, dict(seq=2, gtsam_lm_schedule=1, keyscan_match_ratio=0.02)),  # the window fills up to 60 scans
+    ("vlp-16", 80, dict(seq=3, max_num_recent_scans=2, max_num_keyscans=2, max_steps_unused_keyscan=1, keyscan_match_ratio=0.0)),
+    ("vlp-16", 80, dict(seq=4, max_num_recent_scans=6, max_num_keyscans=0, max_steps_unused_keyscan=5, keyscan_match_ratio=0.01)),
+    ("vlp-16", 60, dict(seq=5, new_pose_threshold=1e-6, max_num_rematches=5)),  # holds an equal-curvature tie (scan 40)
+    ("os0-128", 30, dict(seq=6)),
+    ("vlp-16", 100, dict(seq=8, gtsam_lm_schedule=1, disable_smoothing=1)),
+    ("os1-64", 60, dict(seq=9, point_feats_per_sector=0)),
+]
+
+if __name__ == "__main__":
+    for sensor, n, kw in CASES:
+        t0 = time.time()
+        try:
+            ours, worst, sizes = t.compare(sensor, n, 1e-9, **kw)
+            print(sensor, n, kw, "| worst pose difference", worst, "| window sizes", min(sizes), "-", max(sizes),
+                  "| ICP iterations", ours.stats()["icp_iterations"], "| tie reorders at scans", ours.tie_reorders,
+                  "|", round(time.time() - t0), "s", flush=True)
+        except AssertionError as e:
+            print("FAIL", sensor, n, kw, e, flush=True)

@@ -83,17 +83,26 @@ def compare(sensor, n_scans, tol, seq=0, check_every_pose=True, **over):
     theirs = FormEstimator(p)
     worst = 0.0
     sizes = set()
+    reorders = []  # scans whose keypoints came out in another order (equal-curvature ties)
     for k in range(n_scans):
         scan = synth.scan(sensor, seq, k)
         a, b = ours.register_scan(scan)
         c, d = theirs.register_scan(scan)
-        assert a.tobytes() == c.tobytes() and b.tobytes() == d.tobytes(), f"keypoints differ at scan {k}"
+        for mine, ref_ in ((a, c), (b, d)):
+            if mine.tobytes() != ref_.tobytes():
+                # the only licensed difference: FORM's unstable std::sort may emit two picks of EQUAL
+                # curvature in either order (extraction.tpp:57-58; rule R1 of SURVEY A.1 fixes index
+                # order) - the keypoints must then be the same set
+                assert len(mine) == len(ref_) and sorted(r.tobytes() for r in mine) == sorted(r.tobytes() for r in ref_), \
+                    f"keypoints differ at scan {k}"
+                reorders.append(k)
         wo, wt = ours.window(), theirs.window()
         assert list(wo["scan"]) == list(wt["scan"]), f"window differs at scan {k}: {wo['scan']} vs {wt['scan']}"
         sizes.add(len(wo))
         for x, y in zip(wo, wt) if check_every_pose else [(ours.pose(), theirs.pose())]:
             worst = max(worst, float(np.linalg.norm(x["t"] - y["t"])), float(np.abs(x["R"] - y["R"]).max()))
         assert worst < tol, f"poses differ by {worst} at scan {k}"
+    ours.tie_reorders = reorders
     return ours, worst, sizes
 
 
@@ -132,3 +141,11 @@ def test_no_point_features_ablation():
 def test_os1_64_sequence():
     """BASELINE configs[0]'s sensor shape (64 x 1024), another seeded sequence."""
     compare("os1-64", 8, 1e-9, seq=3, gtsam_lm_schedule=1)
+
+
+def test_equal_curvature_tie_is_the_only_licensed_difference():
+    """Scan 40 of this sequence holds two planar picks of bit-identical curvature in one sector:
+    FORM's std::sort emits them in one order, rule R1 (ties by column) in the other.  Same set,
+    same window, poses unaffected - and nothing else differs anywhere in the 42 scans."""
+    ours, worst, _ = compare("vlp-16", 42, 1e-9, seq=5, new_pose_threshold=1e-6, max_num_rematches=5)
+    assert ours.tie_reorders == [40] and worst < 1e-12
