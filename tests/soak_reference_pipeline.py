@@ -3,7 +3,7 @@ for: FORM's OWN Estimator::register_scan (oracle/_ref) next to this repository's
 the oracle on longer sequences, more seeds and corner-case key-scan parameters.  CPU only; needs
 oracle/_ref (i.e. the container that has /root/reference).  Log of the round: profiles/r05/reference_pipeline_soak.txt
 
-    python profiles/reference_pipeline_soak.py
+    python tests/soak_reference_pipeline.py
 """
 import os
 import sys
@@ -11,7 +11,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # test infrastructure: the oracle is only used from tests/
 
 import test_reference_pipeline as t  # noqa: E402
 
