@@ -8,7 +8,7 @@ candidates scanned in that step).  Orders compared: the keypoint order of the ex
 sector, curvature rank), range-image tiles (rows/8 x cols/32), and a Morton order of the world
 cell - the upper bound of what spatial ordering can buy.
 
-usage: python profiles/assoc_order_model.py [--sensor os0-128] [--scans 30] [--window 13]"""
+usage: python tests/assoc_order_model.py [--sensor os0-128] [--scans 30] [--window 13]"""
 import argparse
 import os
 import sys

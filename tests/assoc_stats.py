@@ -4,7 +4,7 @@ candidates c-bar a query examines (B_assoc = ... + 32 c-bar K ...).
 
 A synthetic sequence is driven through the oracle's stages with the ground-truth poses and a
 sliding window of `--window` scans (the bench's key-scan logic keeps ~13); the statistics are taken
-for the last scan's association.  usage: python profiles/assoc_stats.py [--sensor os0-128]
+for the last scan's association.  usage: python tests/assoc_stats.py [--sensor os0-128]
 [--scans 30] [--window 13]"""
 import argparse
 import os

@@ -195,7 +195,7 @@ def test_voxel_coord_fast_path_is_exact(w):
 
 
 # --------------------------------------------------------------------------- cell-ordered buckets
-# Blueprint of the next association kernel (profiles/assoc_stats.py): every voxel's
+# Blueprint of the next association kernel (tests/assoc_stats.py): every voxel's
 # bucket is ordered by a 4x4x4 cell code; a query scans its own cell, then the adjacent fine cells
 # whose box bound does not exceed the best so far, and falls back to the whole-voxel search (the
 # current kernel) only when the best is not inside the adjacency radius.  The model carries the
