@@ -54,3 +54,24 @@ def test_ablations_run():
     g0, gk = synth.gt_pose(0, 0), synth.gt_pose(0, 5)
     rel = g0["R"].reshape(3, 3).T @ (gk["t"] - g0["t"])
     assert np.linalg.norm(poses[5]["t"] - rel) < 0.05
+
+
+def test_every_old_pose_moves_between_map_rebuilds():
+    """The measurement behind DESIGN 10 (row f3, incremental map): a result-identical incremental
+    map may only skip scans whose pose is bit-identical to the previous rebuild.  With the
+    smoother on, no old pose of the window ever is (they move by ~0.6 mm per scan); only the
+    disable_smoothing ablation freezes them."""
+    for over, expect_frozen in (({}, False), ({"disable_smoothing": 1}, True)):
+        rows, cols = synth.shape("vlp-16")
+        est = oracle_lib.OracleEstimator(_capi.default_est_params(rows, cols, num_threads=1, **over))
+        prev, same, total = {}, 0, 0
+        for k in range(16):
+            est.register_scan(synth.scan("vlp-16", 0, k))
+            cur = {int(e["scan"]): e.tobytes() for e in est.window()}
+            for s, b in cur.items():
+                if s in prev and s != k:
+                    total += 1
+                    same += prev[s] == b
+            prev = cur
+        assert total > 50
+        assert same == (total if expect_frozen else 0), (over, same, total)
