@@ -11,7 +11,8 @@ from form_b200 import _capi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
-LIB = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+# FORM_ORACLE_LIB: another build of the same sources (tests/sanitize_host.sh: ASan / UBSan / TSan)
+LIB = os.environ.get("FORM_ORACLE_LIB") or os.path.join(ORACLE_DIR, "_build", "liboracle.so")
 
 _vp, _sz, _u64, _i, _d = C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_double
 _psz = C.POINTER(C.c_size_t)
