@@ -27,6 +27,19 @@ CASES = [
     ("os1-64", 60, dict(seq=9, point_feats_per_sector=0)),
 ]
 
+# twelve more seeds with mixed parameters (LM schedule, key-scan limits, feature density, matching radius)
+for _seq in range(20, 32):
+    _kw = dict(seq=_seq)
+    if _seq % 2:
+        _kw["gtsam_lm_schedule"] = 1
+    if _seq % 3 == 0:
+        _kw.update(max_num_recent_scans=5, max_num_keyscans=6, max_steps_unused_keyscan=4, keyscan_match_ratio=0.03)
+    if _seq % 5 == 0:
+        _kw.update(planar_feats_per_sector=20, radius=0.5)
+    if _seq % 7 == 0:
+        _kw.update(max_dist_matching=0.5, min_dist_map=0.2)
+    CASES.append(("vlp-16" if _seq % 4 else "os1-64", 70 if _seq % 4 else 30, _kw))
+
 if __name__ == "__main__":
     for sensor, n, kw in CASES:
         t0 = time.time()
