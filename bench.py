@@ -811,6 +811,8 @@ def cpu_multi_sequence(rows, cols, W, last, scans_of, n_workers, gtsam_schedule=
     from form_b200 import _capi
 
     p = _capi.default_est_params(rows, cols, record_trace=1, gtsam_lm_schedule=gtsam_schedule, num_threads=1)
+    oracle_lib._pipe_lib()  # load and configure the library here, before the worker threads use it
+    _capi.synth_lib()
 
     def prepare(w):
         scans = scans_of(w)

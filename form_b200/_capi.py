@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 
@@ -283,13 +284,16 @@ def _load(path: str, symbols: dict, mode: int = C.RTLD_GLOBAL) -> C.CDLL:
 _gpu = None
 _host = None
 _synth = None
+_load_lock = threading.RLock()  # callers load lazily, possibly from worker threads
 
 
 def gpu_lib() -> C.CDLL:
     """libformgpu.so: the CUDA hot path behind the C-ABI.  No fallback."""
     global _gpu
     if _gpu is None:
-        _gpu = _load(os.path.join(LIB_DIR, "libformgpu.so"), FORMGPU_SYMBOLS)
+        with _load_lock:
+            if _gpu is None:
+                _gpu = _load(os.path.join(LIB_DIR, "libformgpu.so"), FORMGPU_SYMBOLS)
     return _gpu
 
 
@@ -302,7 +306,9 @@ def synth_lib() -> C.CDLL:
         path = os.path.join(LIB_DIR, "libformsynth.so")
         if not os.path.exists(path) and os.path.exists(os.path.join(LIB_DIR, "libformhost.so")):
             return host_lib()  # a tree built before libformsynth existed: same symbols, same code
-        _synth = _load(path, FORMSYNTH_SYMBOLS, C.DEFAULT_MODE)
+        with _load_lock:
+            if _synth is None:
+                _synth = _load(path, FORMSYNTH_SYMBOLS, C.DEFAULT_MODE)
     return _synth
 
 
@@ -310,6 +316,8 @@ def host_lib() -> C.CDLL:
     """libformhost.so: host-side C++ (synthetic scans, Estimator facade)."""
     global _host
     if _host is None:
-        gpu_lib()  # libformhost links against libformgpu
-        _host = _load(os.path.join(LIB_DIR, "libformhost.so"), FORMHOST_SYMBOLS)
+        with _load_lock:
+            if _host is None:
+                gpu_lib()  # libformhost links against libformgpu
+                _host = _load(os.path.join(LIB_DIR, "libformhost.so"), FORMHOST_SYMBOLS)
     return _host

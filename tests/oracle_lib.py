@@ -4,6 +4,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import threading
 
 import numpy as np
 
@@ -42,17 +43,23 @@ _SYMS = {
 }
 
 _lib = None
+_lock = threading.Lock()  # bench.py's CPU legs create their estimators from worker threads
 
 
 def lib() -> C.CDLL:
+    """The library with every prototype set.  Published only once it is fully configured: a
+    thread that used a function before its restype was set would truncate the returned handle."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
-        _lib = C.CDLL(LIB)
-        for name, (res, args) in _SYMS.items():
-            fn = getattr(_lib, name)
-            fn.restype, fn.argtypes = res, args
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB):
+                    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
+                loaded = C.CDLL(LIB)
+                for name, (res, args) in _SYMS.items():
+                    fn = getattr(loaded, name)
+                    fn.restype, fn.argtypes = res, args
+                _lib = loaded
     return _lib
 
 
@@ -173,13 +180,15 @@ def _pipe_lib():
     global _pipe_ready
     l = lib()
     if not _pipe_ready:
-        for name, (res, args) in _capi.estimator_symbols("oracle_").items():
-            fn = getattr(l, name)
-            fn.restype, fn.argtypes = res, args
-        l.oracle_est_last_error.restype = C.c_char_p
-        l.oracle_replay_create.restype = _vp
-        l.oracle_replay_create.argtypes = [_vp, C.POINTER(_capi.EstParams)]
-        _pipe_ready = True
+        with _lock:
+            if not _pipe_ready:
+                for name, (res, args) in _capi.estimator_symbols("oracle_").items():
+                    fn = getattr(l, name)
+                    fn.restype, fn.argtypes = res, args
+                l.oracle_est_last_error.restype = C.c_char_p
+                l.oracle_replay_create.restype = _vp
+                l.oracle_replay_create.argtypes = [_vp, C.POINTER(_capi.EstParams)]
+                _pipe_ready = True
     return l
 
 
