@@ -24,3 +24,8 @@ LD_PRELOAD=$(g++ -print-file-name=libtsan.so) TSAN_OPTIONS="halt_on_error=0 repo
   python -m pytest tests/test_pipeline_cpu.py tests/test_golden.py -q -s -m "not gpu" -p no:cacheprovider > "$OUT/tsan.log" 2>&1 || true
 tail -1 "$OUT/tsan.log"
 echo "ThreadSanitizer reports: $(grep -c 'WARNING: ThreadSanitizer' "$OUT/tsan.log" || true)"
+echo "== TSan: the threaded CPU leg of bench.py (one single-threaded estimator + replay per host core)"
+LD_PRELOAD=$(g++ -print-file-name=libtsan.so) TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0" \
+  FORM_ORACLE_LIB="$OUT/liboracle_tsan.so" \
+  python bench.py --impl reference --sensor vlp-16 --steps 3 --warmup 3 --preroll 0 > "$OUT/tsan_bench.log" 2>&1 || true
+echo "bench line printed: $(grep -c '"impl": "reference"' "$OUT/tsan_bench.log")   ThreadSanitizer reports: $(grep -c 'WARNING: ThreadSanitizer' "$OUT/tsan_bench.log" || true)"
