@@ -71,8 +71,8 @@ int formref_est_register_scan(void *h, const formgpu_point4f *scan, size_t n, fo
   *n_planar = pl.size();
   *n_point = pt.size();
   if (pl.size() > planar_cap || pt.size() > point_cap) return 3;
-  std::memcpy(planar, pl.data(), pl.size() * sizeof(form::PlanarFeat));
-  std::memcpy(point, pt.data(), pt.size() * sizeof(form::PointFeat));
+  if (!pl.empty()) std::memcpy(planar, pl.data(), pl.size() * sizeof(form::PlanarFeat));
+  if (!pt.empty()) std::memcpy(point, pt.data(), pt.size() * sizeof(form::PointFeat)); // data() may be null when empty
   return 0;
 }
 

@@ -30,7 +30,8 @@ from form_b200 import _capi, synth
 from helpers import block_rel_err, perturbed, scan_poses
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libformref.so")
+# FORM_REF_LIB: another build of the same sources (sanitizer runs)
+REF_LIB = os.environ.get("FORM_REF_LIB") or os.path.join(ROOT, "oracle", "_ref", "libformref.so")
 
 _vp, _sz, _u64, _i, _d = C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_double
 _psz = C.POINTER(C.c_size_t)
