@@ -40,6 +40,11 @@ for _seq in range(20, 32):
         _kw.update(max_dist_matching=0.5, min_dist_map=0.2)
     CASES.append(("vlp-16" if _seq % 4 else "os1-64", 70 if _seq % 4 else 30, _kw))
 
+# the benchmarked shape (configs[1])
+CASES += [("os0-128", 40, dict(seq=40)), ("os0-128", 40, dict(seq=41, gtsam_lm_schedule=1)),
+          ("os0-128", 40, dict(seq=42, max_num_recent_scans=4, max_num_keyscans=4, max_steps_unused_keyscan=3,
+                               keyscan_match_ratio=0.02))]
+
 if __name__ == "__main__":
     for sensor, n, kw in CASES:
         t0 = time.time()
